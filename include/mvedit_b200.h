@@ -1,0 +1,106 @@
+/*
+ * mvedit_b200.h -- C ABI of libmvedit_b200.so (hand-written sm_100a CUDA).
+ *
+ * Drop-in boundary for the MVEdit multi-view denoise -> reconstruct -> render hot
+ * path.  Every entry point takes raw DEVICE pointers, sizes, and
+ * a cudaStream_t passed as void*; returns 0 on success or a cudaError_t value
+ * (negative values: argument errors detected on the host).  No torch / ATen /
+ * pybind types appear here.  All buffers are caller-allocated; kernels write in
+ * place, exactly like the reference's native layer
+ * (/root/reference/lib/ops/raymarching/src/raymarching.h:8-18), except that
+ *   - work is enqueued on the given stream (the reference uses the legacy
+ *     default stream, raymarching.cu:483),
+ *   - random noise is an explicit input (the reference draws it in Python,
+ *     raymarching.py:279-282),
+ *   - nothing synchronises with the host.
+ *
+ * Each declaration cites the reference interface it replaces.
+ */
+#ifndef MVEDIT_B200_H
+#define MVEDIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* library / device info ------------------------------------------------------ */
+int mve_version(void);                 /* ABI version, currently 1 */
+const char* mve_last_error(void);      /* human-readable text of the last non-zero return */
+
+/* ---------------------------------------------------------------------------
+ * B3: ray-marching ops  (replaces lib/ops/raymarching/src/raymarching.h:8-18,
+ *     Python wrappers lib/ops/raymarching/raymarching.py:31-524)
+ * ------------------------------------------------------------------------- */
+
+/* raymarching.h:8 near_far_from_aabb ; kernel raymarching.cu:92-145.
+ * rays_o/rays_d [N,3] f32, aabb [6] f32, nears/fars [N] f32 out. */
+int mve_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb,
+                           uint32_t N, float min_near, float* nears, float* fars, void* stream);
+
+/* raymarching.h:10-11 morton3D / morton3D_invert ; kernels raymarching.cu:214-254. */
+int mve_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, void* stream);
+int mve_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, void* stream);
+
+/* raymarching.h:12 packbits ; kernel raymarching.cu:268-289.
+ * grid [8*N] f32 (or f16 when grid_is_half != 0: the reference's density grid is fp16,
+ * base_nerf.py:208-211, and is cast to f32 by custom_fwd before the kernel), bitfield [N] u8 out. */
+int mve_packbits(const void* grid, int grid_is_half, uint32_t N, float density_thresh,
+                 uint8_t* bitfield, void* stream);
+
+/* raymarching.h:15 march_rays_train ; kernel raymarching.cu:338-475 (the reference runs it twice
+ * around a host .item(), raymarching.py:286-300).  Here ONE launch does count -> block scan ->
+ * one atomic per block on *counter -> write.  counter [1] i32 must be zeroed by the caller and holds
+ * the total M afterwards.  Samples of a ray are contiguous; rays[n] = (offset, count).  Rays whose
+ * samples would not fit in max_M keep their (offset,count) but write nothing (composite treats
+ * offset+count > M as an empty ray, raymarching.cu:523).  If xyzs == NULL only rays/counter are written
+ * (the reference's first pass).  noises [N] f32 may be NULL (= zeros, perturb=False). */
+int mve_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* density_bitfield,
+                         float bound, int contract, float dt_gamma, uint32_t max_steps,
+                         uint32_t N, uint32_t C, uint32_t H,
+                         const float* nears, const float* fars, const float* noises,
+                         float* xyzs, float* dirs, float* ts, uint32_t max_M,
+                         int32_t* rays, int32_t* counter, void* stream);
+/* second pass of the reference protocol: rays[n] already holds (offset,count); write the samples. */
+int mve_march_rays_train_write(const float* rays_o, const float* rays_d, const uint8_t* density_bitfield,
+                               float bound, int contract, float dt_gamma, uint32_t max_steps,
+                               uint32_t N, uint32_t C, uint32_t H,
+                               const float* nears, const float* fars, const float* noises,
+                               float* xyzs, float* dirs, float* ts, uint32_t max_M,
+                               const int32_t* rays, void* stream);
+
+/* raymarching.h:16 composite_rays_train_forward ; kernel raymarching.cu:501-579.
+ * M may also be given on the device: if M_dev != NULL the kernel reads *M_dev instead of M
+ * (lets the caller skip the host sync after mve_march_rays_train).
+ * weights [M] is fully written for every sample covered by a ray (zeros after early termination),
+ * so the caller need not pre-zero it. */
+int mve_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* ts, const int32_t* rays,
+                                     uint32_t M, const int32_t* M_dev, uint32_t N, float T_thresh, int binarize,
+                                     float* weights, float* weights_sum, float* depth, float* image, void* stream);
+
+/* raymarching.h:17 composite_rays_train_backward ; kernel raymarching.cu:606-695.
+ * grad_sigmas [M], grad_rgbs [M,3] are fully written for every sample covered by a ray. */
+int mve_composite_rays_train_backward(const float* grad_weights, const float* grad_weights_sum, const float* grad_depth,
+                                      const float* grad_image, const float* sigmas, const float* rgbs, const float* ts,
+                                      const int32_t* rays, const float* weights_sum, const float* depth, const float* image,
+                                      uint32_t M, const int32_t* M_dev, uint32_t N, float T_thresh, int binarize,
+                                      float* grad_sigmas, float* grad_rgbs, void* stream);
+
+/* raymarching.h:19 march_rays (inference) ; kernel raymarching.cu:714-829.
+ * xyzs/dirs/ts [n_alive*n_step, 3|3|2] are fully written (zeros past a ray's end), noises may be NULL. */
+int mve_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                   const float* rays_o, const float* rays_d, float bound, int contract, float dt_gamma,
+                   uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* density_bitfield,
+                   const float* nears, const float* fars, float* xyzs, float* dirs, float* ts,
+                   const float* noises, void* stream);
+
+/* raymarching.h:20 composite_rays (inference, in place) ; kernel raymarching.cu:843-925. */
+int mve_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int binarize,
+                       int32_t* rays_alive, float* rays_t, const float* sigmas, const float* rgbs, const float* ts,
+                       float* weights_sum, float* depth, float* image, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVEDIT_B200_H */
