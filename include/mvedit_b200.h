@@ -100,6 +100,30 @@ int mve_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int bi
                        int32_t* rays_alive, float* rays_t, const float* sigmas, const float* rgbs, const float* ts,
                        float* weights_sum, float* depth, float* image, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * B2: denoiser building blocks (tcgen05 tensor cores).  These replace the cuBLAS / cuDNN calls that
+ * diffusers' UNet2DConditionModel / ControlNetModel make under Adapter3DMixin.get_noise_pred*
+ * (lib/pipelines/adapter3d_mixin.py:68-317; lib/models/architecture/diffusers.py:57-164).
+ * All activations are bf16, NHWC / row-major; accumulation is fp32 in TMEM.
+ * ------------------------------------------------------------------------- */
+
+/* C[M,N] = act(A[M,K] . B[N,K]^T + bias[N] + row_bias[row / rows_per_group, N]) * alpha + residual[M,N]
+ * A, B, C, residual bf16 (lda/ldb/ldc/ldr in elements, multiples of 8); bias/row_bias f32 or NULL; K % 64 == 0.
+ * act: 0 none, 1 SiLU, 2 GELU(erf).  Replaces torch.nn.functional.linear / 1x1 conv (cuBLAS) on the UNet path. */
+int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N, uint32_t K,
+                  uint32_t lda, uint32_t ldb, uint32_t ldc,
+                  const float* bias, const float* row_bias, uint32_t rows_per_group,
+                  const void* residual, uint32_t ldr, int act, float alpha, void* stream);
+
+/* 3x3 convolution, stride 1, pad 1, as an implicit GEMM (no im2col buffer): X [B,H,W,Cin] bf16 NHWC,
+ * Wt [Cout,3,3,Cin] bf16, Y [B*H*W, ldy] bf16.  Epilogue as mve_gemm_bf16 with rows_per_group = H*W
+ * (row_bias [B,Cout] = the time-embedding projection of a ResnetBlock2D).  Cin % 64 == 0.
+ * Replaces torch.nn.functional.conv2d (cuDNN) on the UNet path. */
+int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t B, uint32_t H, uint32_t W,
+                     uint32_t Cin, uint32_t Cout, uint32_t ldy,
+                     const float* bias, const float* row_bias, const void* residual, uint32_t ldr,
+                     int act, float alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,371 @@
+// gemm_tc.cu -- bf16 GEMM and implicit-GEMM 3x3 convolution on tcgen05 tensor cores (sm_100a).
+//
+// One persistent, warp-specialised kernel:
+//   warp 0     TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1     MMA issuer     (one elected lane: tcgen05.mma kind::f16, M=128, N=BN, K=16; fp32 accumulators in TMEM,
+//                              two accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1)
+//   warps 2-5  epilogue       (tcgen05.ld 32x32b -> bias / per-image bias / activation / scale / residual -> bf16 -> global)
+//
+//   C[M,N] = epi( A[M,K] . B[N,K]^T )       A, B bf16 K-major (row-major with K contiguous), C bf16 row-major.
+//
+// MODE 1 (conv3x3, stride 1, pad 1, NHWC): A is never materialised.  The producer walks K as 9 taps x (Cin/64) chunks and
+// fetches, for tap (dy,dx), the box {64 ch, BW, BH, BB} of the NHWC activation at (w0+dx-1, h0+dy-1, b0) with a 4-D tensor map;
+// TMA's out-of-bounds zero fill supplies the padding.  The 128 rows of the box are 128 consecutive output pixels.
+// Weights are [Cout][ky][kx][Cin] so that B's K index = tap*Cin + c.
+//
+// Replaces, on the reference's path, the cuDNN/cuBLAS calls under diffusers' UNet2DConditionModel / ControlNetModel
+// (SURVEY.md §8 a-1/a-2, Appendix A).
+#include "tc_common.cuh"
+#include "../../include/mvedit_b200.h"
+
+namespace {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int A_BYTES = BM * BK * 2;
+
+struct GemmParams {
+    __nv_bfloat16* C;
+    uint32_t M, N, ldc;
+    uint32_t num_kb;        // K / 64 (conv: 9 * Cin/64)
+    uint32_t m_tiles, n_tiles;
+    // epilogue
+    const float* bias;              // [N] or null
+    const float* row_bias;          // [M / rows_per_group, N] or null
+    uint32_t rows_per_group;
+    const __nv_bfloat16* residual;  // [M, ldr] or null
+    uint32_t ldr;
+    int act;                        // 0 none, 1 SiLU, 2 GELU(erf)
+    float alpha;                    // out = act(acc + bias + row_bias) * alpha + residual
+    // conv geometry (MODE 1)
+    uint32_t H, W, cin_chunks;
+};
+
+template <int BN>
+struct Cfg {
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int ACC_STRIDE = (BN > 128) ? 256 : BN;  // column offset of accumulator stage 1
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == 1) return v / (1.0f + __expf(-v));
+    if (act == 2) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    return v;
+}
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                            const GemmParams p) {
+    using C_ = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::STAGES * C_::STAGE_BYTES);
+    uint64_t* full = bars;                        // [STAGES]
+    uint64_t* empty = bars + C_::STAGES;          // [STAGES]
+    uint64_t* tfull = bars + 2 * C_::STAGES;      // [2]
+    uint64_t* tempty = bars + 2 * C_::STAGES + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C_::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmA);
+        tc::prefetch_tmap(&tmB);
+        for (int s = 0; s < C_::STAGES; s++) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; s++) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], 4); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, C_::TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t num_tiles = p.m_tiles * p.n_tiles;
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const uint32_t mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+                const int m0 = mt * BM, n0 = nt * BN;
+                int b0 = 0, h0 = 0, w0 = 0;
+                if (MODE == 1) {
+                    const uint32_t hw = p.H * p.W;
+                    b0 = m0 / hw;
+                    const uint32_t rem = m0 % hw;
+                    h0 = rem / p.W;
+                    w0 = rem % p.W;
+                }
+                for (uint32_t kb = 0; kb < p.num_kb; kb++) {
+                    tc::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * C_::STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    tc::mbar_arrive_expect_tx(&full[stage], C_::STAGE_BYTES);
+                    if (MODE == 0) {
+                        tc::tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
+                    } else {
+                        const uint32_t tap = kb / p.cin_chunks, cc = kb % p.cin_chunks;
+                        const int dy = (int)(tap / 3) - 1, dx = (int)(tap % 3) - 1;
+                        tc::tma_load_4d(sa, &tmA, &full[stage], cc * BK, w0 + dx, h0 + dy, b0);
+                    }
+                    tc::tma_load_2d(sb, &tmB, &full[stage], kb * BK, n0);
+                    if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * C_::ACC_STRIDE;
+                for (uint32_t kb = 0; kb < p.num_kb; kb++) {
+                    tc::mbar_wait(&full[stage], phase);
+                    tc::tc_fence_after();
+                    const uint32_t sa = tc::smem_u32(smem + stage * C_::STAGE_BYTES);
+                    const uint64_t da = tc::make_desc_k_sw128(sa), db = tc::make_desc_k_sw128(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
+                        tc::umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    }
+                    tc::umma_commit(&empty[stage]);
+                    if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit(&tfull[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
+        const int q = warp & 3;
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const uint32_t mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+            const uint32_t row = mt * BM + q * 32 + lane;
+            const uint32_t n0 = nt * BN;
+            tc::mbar_wait(&tfull[acc], acc_phase);
+            tc::tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * C_::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+            const bool row_ok = row < p.M;
+            const float* rb = (p.row_bias && row_ok) ? p.row_bias + (size_t)(row / p.rows_per_group) * p.N : nullptr;
+            constexpr int CH = (BN >= 32) ? 32 : 16;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += CH) {
+                uint32_t v[32];
+                if (CH == 32) {
+                    tc::tmem_ld32(t_row + c, v);
+                } else {
+                    uint32_t v16[16];
+                    tc::tmem_ld16(t_row + c, v16);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = v16[i];
+                }
+                tc::tmem_ld_wait();
+                const uint32_t col0 = n0 + c;
+                if (row_ok && col0 < p.N) {
+                    __nv_bfloat16* out = p.C + (size_t)row * p.ldc + col0;
+                    const __nv_bfloat16* res = p.residual ? p.residual + (size_t)row * p.ldr + col0 : nullptr;
+                    const bool full_chunk = (col0 + CH <= p.N) && ((p.ldc & 7) == 0) && (!res || (p.ldr & 7) == 0);
+                    if (full_chunk) {
+#pragma unroll
+                        for (int g = 0; g < CH / 8; g++) {
+                            float f[8];
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                float x = __uint_as_float(v[g * 8 + i]);
+                                if (p.bias) x += p.bias[col0 + g * 8 + i];
+                                if (rb) x += rb[col0 + g * 8 + i];
+                                f[i] = act_apply(x, p.act) * p.alpha;
+                            }
+                            if (res) {
+                                const uint4 r4 = *reinterpret_cast<const uint4*>(res + g * 8);
+                                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+                                for (int i = 0; i < 4; i++) { const float2 t = __bfloat1622float2(r2[i]); f[2 * i] += t.x; f[2 * i + 1] += t.y; }
+                            }
+                            uint4 o;
+                            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                            for (int i = 0; i < 4; i++) o2[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                            *reinterpret_cast<uint4*>(out + g * 8) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < CH; i++) {
+                            if (col0 + i >= p.N) break;
+                            float x = __uint_as_float(v[i]);
+                            if (p.bias) x += p.bias[col0 + i];
+                            if (rb) x += rb[col0 + i];
+                            x = act_apply(x, p.act) * p.alpha;
+                            if (res) x += __bfloat162float(res[i]);
+                            out[i] = __float2bfloat16(x);
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, C_::TMEM_COLS);
+    }
+}
+
+int pick_bn(uint32_t N) {
+    if (N % 256 == 0) return 256;
+    if (N % 160 == 0) return 160;
+    if (N % 128 == 0) return 128;
+    if (N >= 192) return 128;
+    if (N > 32) return 64;
+    if (N > 16) return 32;
+    return 16;
+}
+
+template <int BN, int MODE>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    using C_ = Cfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        MVE_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
+        configured = true;
+    }
+    const uint32_t tiles = p.m_tiles * p.n_tiles;
+    const uint32_t grid = tiles < (uint32_t)kNumSM ? tiles : (uint32_t)kNumSM;
+    k_gemm_tc<BN, MODE><<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    MVE_CHECK_LAUNCH("k_gemm_tc");
+    return 0;
+}
+
+template <int MODE>
+int dispatch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t s) {
+    switch (bn) {
+        case 256: return launch<256, MODE>(tmA, tmB, p, s);
+        case 160: return launch<160, MODE>(tmA, tmB, p, s);
+        case 128: return launch<128, MODE>(tmA, tmB, p, s);
+        case 64: return launch<64, MODE>(tmA, tmB, p, s);
+        case 32: return launch<32, MODE>(tmA, tmB, p, s);
+        default: return launch<16, MODE>(tmA, tmB, p, s);
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- host helpers (declared in tc_common.cuh)
+PFN_tmapEncodeTiled mve_get_tmap_encode() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = (PFN_tmapEncodeTiled)f;
+    }
+    return fn;
+}
+
+int mve_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, const char* what) {
+    PFN_tmapEncodeTiled enc = mve_get_tmap_encode();
+    if (!enc) { mve_set_error("%s: cuTensorMapEncodeTiled entry point not available (no CUDA driver?)", what); return -2; }
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        mve_set_error("%s: cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]", what, (int)r, rank,
+                      (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), (unsigned long long)(rank > 2 ? dims[2] : 0),
+                      (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+        return -3;
+    }
+    return 0;
+}
+
+extern "C" {
+
+int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb, uint32_t ldc,
+                  const float* bias, const float* row_bias, uint32_t rows_per_group, const void* residual, uint32_t ldr, int act,
+                  float alpha, void* stream) {
+    if (M == 0 || N == 0) return 0;
+    MVE_ARG(K % BK == 0 && K > 0, "gemm: K must be a positive multiple of 64");
+    MVE_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (16-byte TMA strides)");
+    MVE_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "gemm: pointers must be 16-byte aligned");
+    MVE_ARG(!row_bias || rows_per_group > 0, "gemm: rows_per_group must be > 0 with row_bias");
+    const int bn = pick_bn(N);
+    CUtensorMap tmA, tmB;
+    {
+        const uint64_t dims[2] = {K, M}, str[1] = {(uint64_t)lda * 2};
+        const uint32_t box[2] = {BK, BM};
+        int r = mve_make_tmap_bf16(&tmA, A, 2, dims, str, box, "gemm A");
+        if (r) return r;
+    }
+    {
+        const uint64_t dims[2] = {K, N}, str[1] = {(uint64_t)ldb * 2};
+        const uint32_t box[2] = {BK, (uint32_t)bn};
+        int r = mve_make_tmap_bf16(&tmB, B, 2, dims, str, box, "gemm B");
+        if (r) return r;
+    }
+    GemmParams p{};
+    p.C = (__nv_bfloat16*)C; p.M = M; p.N = N; p.ldc = ldc; p.num_kb = K / BK;
+    p.m_tiles = (M + BM - 1) / BM; p.n_tiles = (N + bn - 1) / bn;
+    p.bias = bias; p.row_bias = row_bias; p.rows_per_group = rows_per_group;
+    p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act; p.alpha = alpha;
+    return dispatch<0>(bn, tmA, tmB, p, (cudaStream_t)stream);
+}
+
+int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32_t H, uint32_t W, uint32_t Cin, uint32_t Cout,
+                     uint32_t ldy, const float* bias, const float* row_bias, const void* residual, uint32_t ldr, int act, float alpha,
+                     void* stream) {
+    if (Bn == 0) return 0;
+    MVE_ARG(Cin % BK == 0, "conv3x3: Cin must be a multiple of 64 (pad channels)");
+    MVE_ARG((W <= 128 && 128 % W == 0) || W % 128 == 0, "conv3x3: W must divide 128 or be a multiple of 128");
+    const uint32_t BW = W < 128 ? W : 128;
+    uint32_t BH = 128 / BW;
+    if (BH > H) BH = H;
+    const uint32_t BB = 128 / (BW * BH);
+    MVE_ARG(BW * BH * BB == 128 && (H % BH) == 0 && (Bn % BB) == 0, "conv3x3: 128-pixel tile must cover whole rows / images");
+    const uint32_t M = Bn * H * W;
+    const int bn = pick_bn(Cout);
+    CUtensorMap tmA, tmB;
+    {
+        const uint64_t dims[4] = {Cin, W, H, Bn};
+        const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        const uint32_t box[4] = {BK, BW, BH, BB};
+        int r = mve_make_tmap_bf16(&tmA, X, 4, dims, str, box, "conv3x3 X");
+        if (r) return r;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)9 * Cin, Cout}, str[1] = {(uint64_t)9 * Cin * 2};
+        const uint32_t box[2] = {BK, (uint32_t)bn};
+        int r = mve_make_tmap_bf16(&tmB, Wt, 2, dims, str, box, "conv3x3 W");
+        if (r) return r;
+    }
+    GemmParams p{};
+    p.C = (__nv_bfloat16*)Y; p.M = M; p.N = Cout; p.ldc = ldy; p.num_kb = 9 * (Cin / BK);
+    p.m_tiles = M / BM; p.n_tiles = (Cout + bn - 1) / bn;
+    p.bias = bias; p.row_bias = row_bias; p.rows_per_group = H * W;
+    p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act; p.alpha = alpha;
+    p.H = H; p.W = W; p.cin_chunks = Cin / BK;
+    return dispatch<1>(bn, tmA, tmB, p, (cudaStream_t)stream);
+}
+
+}  // extern "C"
