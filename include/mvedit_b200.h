@@ -124,6 +124,66 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t B, uint32_
                      const float* bias, const float* row_bias, const void* residual, uint32_t ldr,
                      int act, float alpha, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * B4: Instant-NGP field = tcnn-style HashGrid (Smoothstep, 2 features/level, fp32 table) + Linear(2L,64)+ReLU+Linear(64,4)
+ * + trunc_exp(h0 + blob) / sigmoid saturation, fused.  Replaces tinycudann.Encoding fwd/bwd + torch Linear x2
+ * under iNGPDecoder.point_decode / point_density_decode (lib/models/decoders/ingp_decoder.py:62-74,101-125;
+ * lib/ops/activation.py:8-23).  level_* are HOST arrays of n_levels entries (scale, resolution, entries, entry offset);
+ * table [n_entries,2] f32; w1 [64,2L], b1 [64], w2 [4,64], b2 [4] f32 (nn.Linear layout).
+ * M_dev (optional, device): actual sample count <= M.
+ * ------------------------------------------------------------------------- */
+int mve_field_forward(const float* xyz, uint32_t M, const int32_t* M_dev, const float* table,
+                      const float* w1, const float* b1, const float* w2, const float* b2,
+                      uint32_t n_levels, const float* level_scale, const uint32_t* level_res,
+                      const uint32_t* level_size, const uint32_t* level_offset,
+                      float bound, float blob_density, float blob_radius, float sigmoid_saturation,
+                      int density_only, float* sigma, float* rgb, void* stream);
+
+/* Backward of mve_field_forward w.r.t. table (atomically ACCUMULATED into grad_table: caller zeroes / owns .grad),
+ * MLP parameters (written, or added when accumulate_mlp != 0; deterministic two-stage reduction through `workspace`
+ * of mve_field_backward_workspace_floats(n_levels) floats) and optionally xyz (grad_xyz [M,3] or NULL).
+ * grad_rgb may be NULL (density-only graph). */
+uint32_t mve_field_backward_workspace_floats(uint32_t n_levels);
+int mve_field_backward(const float* xyz, uint32_t M, const int32_t* M_dev, const float* table,
+                       const float* w1, const float* b1, const float* w2, const float* b2,
+                       uint32_t n_levels, const float* level_scale, const uint32_t* level_res,
+                       const uint32_t* level_size, const uint32_t* level_offset,
+                       float bound, float blob_density, float blob_radius, float sigmoid_saturation,
+                       const float* grad_sigma, const float* grad_rgb,
+                       float* grad_table, float* grad_w1, float* grad_b1, float* grad_w2, float* grad_b2,
+                       int accumulate_mlp, float* workspace, float* grad_xyz, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * a-6 / a-9: fused NeRF-adapter kernels (no reference native counterpart: they replace Python loops)
+ * ------------------------------------------------------------------------- */
+
+/* Whole inference branch of VolumeRenderer.forward (lib/models/decoders/base_volume_renderer.py:264-329) + BaseNeRF.render's ray
+ * generation (lib/models/autoencoders/base_nerf.py:489-556; lib/core/utils/geometry_utils.py:18-55) in one launch.
+ * Rays: either rays_o/rays_d [N,3], or cameras (poses [V,4,4] c2w, intrinsics [V,4]=fx,fy,cx,cy at the render size, h, w; N = V*h*w,
+ * optional dt_gamma_per_view [V]).  perturb=False semantics.  Outputs weights_sum [N], depth [N] (sum w/t), image [N,3]. */
+int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses, const float* intrinsics,
+                    const float* dt_gamma_per_view, uint32_t h, uint32_t w, uint32_t N,
+                    const float* aabb, float min_near, const uint8_t* density_bitfield, float bound, float dt_gamma,
+                    uint32_t max_steps, uint32_t C, uint32_t H, float T_thresh,
+                    const float* table, const float* w1, const float* b1, const float* w2, const float* b2,
+                    uint32_t n_levels, const float* level_scale, const uint32_t* level_res,
+                    const uint32_t* level_size, const uint32_t* level_offset,
+                    float blob_density, float blob_radius, float sigmoid_saturation,
+                    float* weights_sum, float* depth, float* image, void* stream);
+
+/* Weight culling of the training branch (base_volume_renderer.py:222-246): keep samples with weight > th, compact xyzs/ts,
+ * rebuild rays (offset,count); *counter (zeroed by the caller) receives the kept total. */
+int mve_cull_samples(const float* weights, float th, const int32_t* rays_in, const float* xyzs_in, const float* ts_in,
+                     uint32_t N, uint32_t M, const int32_t* M_dev,
+                     int32_t* rays_out, float* xyzs_out, float* ts_out, int32_t* counter, void* stream);
+
+/* Occupancy-grid refresh tail of VolumeRenderer.update_extra_state (base_volume_renderer.py:163-175): fp16 EMA
+ * grid = where(grid>=0 & s>=0, max(grid*decay, s), grid), mean of clamp(grid,0), packbits with min(mean, density_thresh).
+ * sigmas [n_cells] are the freshly decoded densities in Morton order (indices must be NULL: full update, the only mode
+ * the pipelines reach -- SURVEY.md Appendix F).  sum_scratch: 1 float of device scratch. */
+int mve_density_grid_update(void* grid_half, const float* sigmas, const int32_t* indices, uint32_t n, float decay,
+                            float* sum_scratch, uint32_t n_cells, float density_thresh, uint8_t* bitfield, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

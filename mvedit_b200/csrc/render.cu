@@ -1,0 +1,261 @@
+// render.cu -- fused kernels of the NeRF adapter's render / reconstruct loop.
+//
+// k_render_rays: the whole inference branch of VolumeRenderer.forward
+//   (/root/reference/lib/models/decoders/base_volume_renderer.py:264-329: a Python while-loop of march_rays ->
+//   point_decode -> composite_rays -> boolean compaction -> host sync, up to max_steps/n_step rounds) in ONE launch:
+//   one thread per ray keeps (t, weight_sum, depth, rgb) in registers, walks the occupancy grid with the shared DDA,
+//   evaluates the hash-grid + MLP field in place and stops at T < T_thresh.  No sample ever touches HBM.
+//   Ray generation (geometry_utils.get_ray_directions/get_rays, :18-55) is fused in: rays come from (pose, intrinsics,
+//   pixel) so the [N,H,W,3] origin/direction tensors of base_nerf.py:489-556 are never materialised (optional).
+//
+// k_cull_compact: the weight-culling step of the training branch (:222-246: boolean masks, split, cumsum, index):
+//   keeps samples with weight > th, warp-per-ray ballot compaction, CTA scan + one atomic for the new offsets.
+#include "march_device.cuh"
+#include "field_device.cuh"
+#include "../../include/mvedit_b200.h"
+
+using namespace march;
+using namespace field;
+
+namespace {
+
+__device__ __forceinline__ void slab(const Ray& r, const float* __restrict__ aabb, const float min_near, float& near_o, float& far_o) {
+    // raymarching.cu:110-144
+    constexpr float kMax = 3.402823466e+38f;
+    float near = (aabb[0] - r.ox) * r.rdx, far = (aabb[3] - r.ox) * r.rdx, tmp;
+    if (near > far) { tmp = near; near = far; far = tmp; }
+    float near_y = (aabb[1] - r.oy) * r.rdy, far_y = (aabb[4] - r.oy) * r.rdy;
+    if (near_y > far_y) { tmp = near_y; near_y = far_y; far_y = tmp; }
+    if (near > far_y || near_y > far) { near_o = far_o = kMax; return; }
+    if (near_y > near) near = near_y;
+    if (far_y < far) far = far_y;
+    float near_z = (aabb[2] - r.oz) * r.rdz, far_z = (aabb[5] - r.oz) * r.rdz;
+    if (near_z > far_z) { tmp = near_z; near_z = far_z; far_z = tmp; }
+    if (near > far_z || near_z > far) { near_o = far_o = kMax; return; }
+    if (near_z > near) near = near_z;
+    if (far_z < far) far = far_z;
+    if (near < min_near) near = min_near;
+    near_o = near; far_o = far;
+}
+
+struct RenderParams {
+    const float* rays_o;   // [N,3] or null when cameras are given
+    const float* rays_d;
+    // camera mode: ray n -> view n / (h*w), pixel (n % (h*w)); direction = R * ((i+0.5-cx)/fx, (j+0.5-cy)/fy, 1) normalised
+    const float* poses;       // [V,4,4] c2w row-major
+    const float* intrinsics;  // [V,4] fx fy cx cy (already scaled to the render size)
+    uint32_t h, w;
+    uint32_t N;
+    const float* aabb;
+    float min_near, T_thresh;
+    uint32_t max_steps;
+    float* weights_sum; float* depth; float* image;   // [N], [N], [N,3]
+    const float* dt_gamma_per_view;  // [V] or null (then march.dt_gamma is used)
+};
+
+template <int L>
+__global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, MarchParams mp, const float2* __restrict__ table,
+                                                     const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                                                     const float* __restrict__ b2, const Levels lv, const FieldCfg cfg) {
+    using R = Rec<L>;
+    __shared__ __align__(16) float rec[HID * R::STRIDE];
+    stage_mlp<L>(rec, w1, b1, w2);
+    __syncthreads();
+    const float ob0 = b2[0], ob1 = b2[1], ob2 = b2[2], ob3 = b2[3];
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < rp.N; n += gridDim.x * blockDim.x) {
+        Ray r;
+        if (rp.rays_o) {
+            r = load_ray(rp.rays_o, rp.rays_d, n);
+        } else {
+            const uint32_t hw = rp.h * rp.w, v = n / hw, pix = n % hw;
+            const float pi = (float)(pix % rp.w) + 0.5f, pj = (float)(pix / rp.w) + 0.5f;
+            const float* K = rp.intrinsics + v * 4;
+            const float* P = rp.poses + v * 16;
+            const float cxd = (pi - K[2]) / K[0], cyd = (pj - K[3]) / K[1];
+            float dx = P[0] * cxd + P[1] * cyd + P[2], dy = P[4] * cxd + P[5] * cyd + P[6], dz = P[8] * cxd + P[9] * cyd + P[10];
+            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            r.ox = P[3]; r.oy = P[7]; r.oz = P[11];
+            r.dx = dx * inv; r.dy = dy * inv; r.dz = dz * inv;
+            r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+            if (rp.dt_gamma_per_view) mp.dt_gamma = rp.dt_gamma_per_view[v];
+        }
+        float near, far;
+        slab(r, rp.aabb, rp.min_near, near, far);
+        float t = near;
+        float ws = 0.f, dsum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+        uint32_t step = 0;
+        float cx, cy, cz, dt;
+        while (t < far && step < rp.max_steps) {
+            if (!dda_step(r, mp, t, cx, cy, cz, dt)) continue;
+            t += dt;
+            float enc[R::IN];
+            encode<L>(lv, table, (cx + cfg.bound) * cfg.inv2b, (cy + cfg.bound) * cfg.inv2b, (cz + cfg.bound) * cfg.inv2b, enc);
+            float o0 = ob0, o1 = ob1, o2 = ob2, o3 = ob3;
+            mlp_forward<L, false>(rec, enc, o0, o1, o2, o3);
+            const float sigma = __expf(o0 + blob_of(cfg, cx, cy, cz));
+            // kernel_composite_rays (raymarching.cu:878-903): T = 1 - weight_sum, break after accumulating
+            const float alpha = 1.0f - __expf(-sigma * dt);
+            const float T = 1 - ws;
+            const float weight = alpha * T;
+            ws += weight;
+            dsum += weight / t;
+            cr += weight * fmaf(1.f / (1.f + __expf(-o1)), cfg.sat_scale, cfg.sat_shift);
+            cg += weight * fmaf(1.f / (1.f + __expf(-o2)), cfg.sat_scale, cfg.sat_shift);
+            cb += weight * fmaf(1.f / (1.f + __expf(-o3)), cfg.sat_scale, cfg.sat_shift);
+            step++;
+            if (T < rp.T_thresh) break;
+        }
+        rp.weights_sum[n] = ws;
+        rp.depth[n] = dsum;
+        rp.image[(size_t)n * 3] = cr; rp.image[(size_t)n * 3 + 1] = cg; rp.image[(size_t)n * 3 + 2] = cb;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight culling: warp per ray, 8 rays per CTA
+// ---------------------------------------------------------------------------------------------
+constexpr int CC_T = 256;
+__global__ void __launch_bounds__(CC_T) k_cull_compact(const float* __restrict__ weights, const float th, const int* __restrict__ rays_in,
+                                                       const float* __restrict__ xyzs_in, const float* __restrict__ ts_in, const uint32_t N,
+                                                       uint32_t M, const int* __restrict__ M_dev, int* __restrict__ rays_out,
+                                                       float* __restrict__ xyzs_out, float* __restrict__ ts_out, int* __restrict__ counter) {
+    __shared__ uint32_t s_cnt[CC_T / 32];
+    __shared__ uint32_t s_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n = blockIdx.x * (CC_T / 32) + warp;
+    if (M_dev) M = (uint32_t)*M_dev;
+    uint32_t offset = 0, num = 0;
+    if (n < N) {
+        offset = rays_in[n * 2]; num = rays_in[n * 2 + 1];
+        if ((uint64_t)offset + num > M) num = 0;
+    }
+    uint32_t kept = 0;
+    for (uint32_t i = lane; i < num; i += 32) kept += (weights[offset + i] > th) ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+    if (lane == 0) s_cnt[warp] = kept;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < CC_T / 32; w++) { const uint32_t v = s_cnt[w]; s_cnt[w] = tot; tot += v; }
+        s_base = tot ? (uint32_t)atomicAdd(counter, (int)tot) : 0u;
+    }
+    __syncthreads();
+    if (n >= N) return;
+    uint32_t out = s_base + s_cnt[warp];
+    if (lane == 0) { rays_out[n * 2] = (int)out; rays_out[n * 2 + 1] = (int)kept; }
+    for (uint32_t base = 0; base < num; base += 32) {
+        const uint32_t i = base + lane;
+        const bool k = (i < num) && (weights[offset + i] > th);
+        const uint32_t bal = __ballot_sync(0xffffffffu, k);
+        if (k) {
+            const uint32_t dst = out + __popc(bal & ((1u << lane) - 1u));
+            const size_t src = offset + i;
+            xyzs_out[(size_t)dst * 3] = xyzs_in[src * 3]; xyzs_out[(size_t)dst * 3 + 1] = xyzs_in[src * 3 + 1]; xyzs_out[(size_t)dst * 3 + 2] = xyzs_in[src * 3 + 2];
+            ts_out[(size_t)dst * 2] = ts_in[src * 2]; ts_out[(size_t)dst * 2 + 1] = ts_in[src * 2 + 1];
+        }
+        out += __popc(bal);
+    }
+}
+
+// occupancy-grid EMA (base_volume_renderer.py:163-167): grid = where(grid>=0 & tmp>=0, max(grid*decay, tmp), grid), fp16 grid;
+// also accumulates sum(max(grid,0)) for the mean-density threshold (:166).
+__global__ void k_grid_ema(__half* __restrict__ grid, const float* __restrict__ sigmas, const int* __restrict__ indices, const uint32_t n,
+                           const float decay, float* __restrict__ sum_out) {
+    float local = 0.f;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t cell = indices ? (uint32_t)indices[i] : i;
+        const float g = __half2float(grid[cell]);
+        // tmp_grid = sigmas.clamp(max=fp16 max).to(fp16) (:139-140)
+        const float tmp = __half2float(__float2half(fminf(sigmas[i], 65504.f)));
+        float v = g;
+        if (g >= 0.f && tmp >= 0.f) v = __half2float(__float2half(fmaxf(__half2float(__float2half(g * decay)), tmp)));
+        grid[cell] = __float2half(v);
+        local += fmaxf(v, 0.f);
+    }
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0 && local != 0.f) atomicAdd(sum_out, local);
+}
+
+// packbits with the threshold min(mean, density_thresh) read from the device (:166-175)
+__global__ void k_packbits_dev(const __half* __restrict__ grid, const uint32_t N, const float* __restrict__ sum, const float inv_count,
+                               const float density_thresh, uint8_t* __restrict__ bitfield) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const float thresh = fminf(__half2float(__float2half(sum[0] * inv_count)), density_thresh);  // torch.mean of an fp16 grid is fp16
+    const uint4 raw = reinterpret_cast<const uint4*>(grid)[n];
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float2 f = __half22float2(h[i]);
+        bits |= (f.x >= thresh) ? (1u << (2 * i)) : 0u;
+        bits |= (f.y >= thresh) ? (1u << (2 * i + 1)) : 0u;
+    }
+    bitfield[n] = (uint8_t)bits;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses, const float* intrinsics, const float* dt_gamma_per_view,
+                    uint32_t h, uint32_t w, uint32_t N, const float* aabb, float min_near, const uint8_t* density_bitfield, float bound,
+                    float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, float T_thresh, const float* table, const float* w1,
+                    const float* b1, const float* w2, const float* b2, uint32_t n_levels, const float* level_scale,
+                    const uint32_t* level_res, const uint32_t* level_size, const uint32_t* level_offset, float blob_density,
+                    float blob_radius, float sigmoid_saturation, float* weights_sum, float* depth, float* image, void* stream) {
+    if (N == 0) return 0;
+    MVE_ARG((rays_o && rays_d) || (poses && intrinsics && h && w), "render_rays: give rays_o/rays_d or poses/intrinsics/h/w");
+    Levels lv;
+    MVE_ARG(fill_levels(lv, n_levels, level_scale, level_res, level_size, level_offset) == 0, "field: n_levels > 16");
+    MVE_ARG(n_levels == 12 || n_levels == 14 || n_levels == 16, "field: n_levels must be 12, 14 or 16");
+    const FieldCfg cfg = make_cfg(bound, blob_density, blob_radius, sigmoid_saturation);
+    const MarchParams mp = make_params(density_bitfield, bound, false, dt_gamma, max_steps, C, H);
+    RenderParams rp{};
+    rp.rays_o = rays_o; rp.rays_d = rays_d; rp.poses = poses; rp.intrinsics = intrinsics; rp.h = h; rp.w = w; rp.N = N; rp.aabb = aabb;
+    rp.min_near = min_near; rp.T_thresh = T_thresh; rp.max_steps = max_steps; rp.weights_sum = weights_sum; rp.depth = depth;
+    rp.image = image; rp.dt_gamma_per_view = dt_gamma_per_view;
+    uint32_t grid = cdiv(N, 128);
+    if (grid > (uint32_t)(16 * kNumSM)) grid = 16 * kNumSM;
+    const float2* t2 = reinterpret_cast<const float2*>(table);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_levels == 12) k_render_rays<12><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg);
+    else if (n_levels == 14) k_render_rays<14><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg);
+    else k_render_rays<16><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg);
+    MVE_CHECK_LAUNCH("mve_render_rays");
+    return 0;
+}
+
+int mve_cull_samples(const float* weights, float th, const int32_t* rays_in, const float* xyzs_in, const float* ts_in, uint32_t N,
+                     uint32_t M, const int32_t* M_dev, int32_t* rays_out, float* xyzs_out, float* ts_out, int32_t* counter,
+                     void* stream) {
+    if (N == 0) return 0;
+    k_cull_compact<<<cdiv(N, CC_T / 32), CC_T, 0, (cudaStream_t)stream>>>(weights, th, rays_in, xyzs_in, ts_in, N, M, M_dev, rays_out,
+                                                                           xyzs_out, ts_out, counter);
+    MVE_CHECK_LAUNCH("mve_cull_samples");
+    return 0;
+}
+
+int mve_density_grid_update(void* grid_half, const float* sigmas, const int32_t* indices, uint32_t n, float decay, float* sum_scratch,
+                            uint32_t n_cells, float density_thresh, uint8_t* bitfield, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    MVE_ARG(n_cells % 8 == 0, "density_grid_update: n_cells must be a multiple of 8");
+    MVE_CUDA(cudaMemsetAsync(sum_scratch, 0, sizeof(float), s));
+    // the mean is over ALL cells: when only a subset (indices) was refreshed the untouched cells are added by a second pass
+    if (n > 0) {
+        uint32_t g = cdiv(n, 256);
+        if (g > (uint32_t)(8 * kNumSM)) g = 8 * kNumSM;
+        MVE_ARG(indices == nullptr || n <= n_cells, "density_grid_update: bad index count");
+        MVE_ARG(indices != nullptr || n == n_cells, "density_grid_update: dense update needs n == n_cells");
+        MVE_ARG(indices == nullptr, "density_grid_update: partial (indexed) update is not implemented; the pipeline always runs the full update");
+        k_grid_ema<<<g, 256, 0, s>>>((__half*)grid_half, sigmas, indices, n, decay, sum_scratch);
+    }
+    k_packbits_dev<<<cdiv(n_cells / 8, 256), 256, 0, s>>>((const __half*)grid_half, n_cells / 8, sum_scratch, 1.0f / (float)n_cells,
+                                                          density_thresh, bitfield);
+    MVE_CHECK_LAUNCH("mve_density_grid_update");
+    return 0;
+}
+
+}  // extern "C"

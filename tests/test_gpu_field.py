@@ -1,0 +1,206 @@
+"""GPU parity of the fused Instant-NGP field (hash grid + MLP + activations), the fused renderer and the decoder's
+training forward against the CPU oracles (oracle/field_oracle.py -- tcnn algorithm restated, PARITY UNPINNED, see its header --
+and oracle/raymarching_oracle.c).
+
+Tolerances: forward fp32 rtol 2e-4 (fast-math __expf + different summation order of 8 corners / 24-wide dot products);
+table / MLP gradients rtol 2e-3 relative to the gradient's max (atomic accumulation order)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import field_oracle as fo
+from oracle import raymarching_oracle as orc
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+AABB = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+
+
+def make_decoder(n_levels=12, max_resolution=320, table_scale=0.3, seed=0, **kw):
+    from mvedit_b200.ingp_decoder import iNGPDecoder
+    dec = iNGPDecoder(n_levels=n_levels, max_resolution=max_resolution, **kw).cuda()
+    levels, n_entries = fo.level_table(n_levels=n_levels, max_resolution=max_resolution)
+    table, w1, b1, w2, b2 = fo.init_params(levels, n_entries, seed=seed, table_scale=table_scale)
+    g = torch.Generator().manual_seed(seed + 1)
+    b1 = torch.randn(64, generator=g) * 0.1
+    b2 = torch.randn(4, generator=g) * 0.1
+    with torch.no_grad():
+        dec.encoder.params.copy_(table.reshape(-1))
+        dec.mlp.net[0].weight.copy_(w1); dec.mlp.net[0].bias.copy_(b1)
+        dec.mlp.net[1].weight.copy_(w2); dec.mlp.net[1].bias.copy_(b2)
+    return dec, levels, (table, w1, b1, w2, b2)
+
+
+def test_level_table_matches_oracle_and_survey():
+    from mvedit_b200.ingp_decoder import level_table
+    for L, R in ((12, 320), (14, 512)):
+        lt = level_table(L, 16, R)
+        levels, n = fo.level_table(L, 16, R)
+        assert lt['n_entries'] == n
+        assert [int(r) for r in lt['res']] == [l[1] for l in levels]
+    assert level_table(12, 16, 320)['n_entries'] == 3593720
+    assert [int(r) for r in level_table(12, 16, 320)['res']] == [16, 22, 28, 37, 48, 63, 82, 108, 142, 186, 244, 320]
+    assert level_table(14, 16, 512)['n_entries'] == 4594792
+
+
+@pytest.mark.parametrize('L,R', [(12, 320), (14, 512)])
+def test_field_forward_backward_vs_oracle(L, R):
+    dec, levels, (table, w1, b1, w2, b2) = make_decoder(L, R)
+    g = torch.Generator().manual_seed(3)
+    M = 3001
+    xyz = (torch.rand(M, 3, generator=g) * 2 - 1) * 0.999
+    xyz[:7] = torch.tensor([[1., 1, 1], [-1, -1, -1], [0, 0, 0], [1, -1, 0.5], [0.999999, 0.3, -0.2], [0.25, 0.25, 0.25], [-0.5, 0.5, 1.0]])
+    # oracle
+    pt = [t.clone().requires_grad_(True) for t in (table, w1, b1, w2, b2)]
+    xo = xyz.clone().requires_grad_(True)
+    sig_o, rgb_o = fo.point_decode(xo, *pt, levels)
+    gs, gr = torch.randn(M, generator=g), torch.randn(M, 3, generator=g)
+    (sig_o * gs).sum().add((rgb_o * gr).sum()).backward()
+    # ours
+    xg = xyz.cuda().requires_grad_(True)
+    sig, rgb, _ = dec.point_decode([xg], None, None)
+    np.testing.assert_allclose(sig.detach().cpu().numpy(), sig_o.detach().numpy(), rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(rgb.detach().cpu().numpy(), rgb_o.detach().numpy(), rtol=2e-4, atol=1e-6)
+    sd, _ = dec.point_density_decode([xyz.cuda()], None)
+    np.testing.assert_allclose(sd.cpu().numpy(), sig_o.detach().numpy(), rtol=2e-4, atol=1e-6)
+    torch.autograd.backward([sig, rgb], [gs.cuda(), gr.cuda()])
+
+    def close(a, b, rel):
+        a, b = a.detach().cpu().double().reshape(-1), b.detach().double().reshape(-1)
+        assert (a - b).abs().max().item() <= rel * b.abs().max().item() + 1e-7, ((a - b).abs().max().item(), b.abs().max().item())
+
+    close(dec.encoder.params.grad, pt[0].grad, 2e-3)
+    close(dec.mlp.net[0].weight.grad, pt[1].grad, 2e-3)
+    close(dec.mlp.net[0].bias.grad, pt[2].grad, 2e-3)
+    close(dec.mlp.net[1].weight.grad, pt[3].grad, 2e-3)
+    close(dec.mlp.net[1].bias.grad, pt[4].grad, 2e-3)
+    close(xg.grad, xo.grad, 5e-3)   # d/dxyz (DMTet stage)
+
+
+def test_field_empty_and_tiny():
+    dec, levels, params = make_decoder()
+    s, r, n = dec.point_decode([torch.zeros(0, 3, device='cuda')], None, None)
+    assert s.numel() == 0 and r.shape == (0, 3) and n == [0]
+    s, r, _ = dec.point_decode([torch.zeros(1, 3, device='cuda')], None, None)
+    so, ro = fo.point_decode(torch.zeros(1, 3), *params, levels)
+    np.testing.assert_allclose(s.cpu().numpy(), so.numpy(), rtol=2e-4)
+    np.testing.assert_allclose(r.cpu().numpy(), ro.numpy(), rtol=2e-4)
+
+
+def _scene(H=32, views=2, size=24):
+    grid = synth.sphere_density_grid(H=H, radius=0.6)
+    bitfield = orc.packbits(grid, 0.5)
+    poses = synth.surround_poses(views, seed=2)
+    ro, rd, f = synth.camera_rays(poses, size)
+    return H, bitfield, poses, ro, rd, f
+
+
+def test_fused_render_vs_oracle_loop():
+    """mve_render_rays == the reference's inference while-loop (oracle march_rays/composite_rays + field oracle)."""
+    dec, levels, params = make_decoder(table_scale=1.0)
+    dec.max_steps = 128
+    dec.eval()
+    H, bitfield, poses, ro, rd, f = _scene()
+    N = ro.shape[0]
+    nears, fars = orc.near_far_from_aabb(ro, rd, AABB, 0.2)
+    ws, d, img = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
+    alive, rt = np.arange(N, dtype=np.int32), nears.copy()
+    step = 0
+    while step < 128 and alive.size:
+        n_alive = alive.size
+        n_step = min(max(N // n_alive, 1), 8)
+        x, _, t = orc.march_rays(n_alive, n_step, alive, rt, ro, rd, 1.0, bitfield, 1, H, nears, fars, None, dt_gamma=1 / f, max_steps=128)
+        with torch.no_grad():
+            s_, c_ = fo.point_decode(torch.from_numpy(x), *params, levels)
+        orc.composite_rays(n_alive, n_step, alive, rt, s_.numpy(), c_.numpy(), t, ws, d, img, T_thresh=1e-2)
+        alive = np.ascontiguousarray(alive[alive >= 0])
+        step += n_step
+    out = dec(torch.from_numpy(ro).cuda()[None], torch.from_numpy(rd).cuda()[None], None, torch.from_numpy(bitfield).cuda()[None], H,
+              dt_gamma=1 / f, perturb=False)
+    assert ws.max() > 0.5
+    ok = np.abs(out['weights_sum'][0].cpu().numpy() - ws) < 2e-3
+    assert ok.mean() > 0.995   # a march cell flipped by 1 ulp changes a whole ray; the rest must agree tightly
+    np.testing.assert_allclose(out['weights_sum'][0].cpu().numpy()[ok], ws[ok], rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(out['image'][0].cpu().numpy()[ok], img[ok], rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(out['depth'][0].cpu().numpy()[ok], d[ok], rtol=1e-3, atol=2e-5)
+    # camera mode == explicit rays
+    size = int(round((N // poses.shape[0]) ** 0.5))
+    K = torch.tensor([[f, f, size / 2, size / 2]] * poses.shape[0], device='cuda')
+    ws_c, d_c, img_c = dec.render_cameras(torch.from_numpy(poses).cuda(), K, size, size, torch.from_numpy(bitfield).cuda(), H, dt_gamma=1 / f)
+    okc = (ws_c.reshape(-1) - out['weights_sum'][0]).abs() < 2e-3
+    assert okc.float().mean() > 0.99
+    torch.testing.assert_close(img_c.reshape(-1, 3)[okc], out['image'][0][okc], rtol=1e-3, atol=1e-4)
+
+
+def test_decoder_training_forward_backward_vs_oracle():
+    """VolumeRenderer.forward training branch with weight culling (base_volume_renderer.py:207-262)."""
+    dec, levels, params = make_decoder(table_scale=1.0, weight_culling_th=0.001)
+    dec.max_steps = 128
+    dec.train()
+    H, bitfield, poses, ro, rd, f = _scene(views=1, size=32)
+    N = ro.shape[0]
+    rng = np.random.default_rng(0)
+    noises = rng.random(N).astype(np.float32)
+    nears, fars = orc.near_far_from_aabb(ro, rd, AABB, 0.2)
+    x, _, t, rays = orc.march_rays_train(ro, rd, 1.0, bitfield, 1, H, nears, fars, noises, dt_gamma=1 / f, max_steps=128)
+    pt = [p.clone().requires_grad_(True) for p in params]
+    with torch.no_grad():
+        s0, _ = fo.point_decode(torch.from_numpy(x), *params, levels)
+    w0, _, _, _ = orc.composite_rays_train_forward(s0.numpy(), np.zeros((x.shape[0], 3), np.float32), t, rays)
+    keep = w0 > 0.001
+    filt = np.concatenate([[0], np.cumsum(keep)])
+    rays2 = np.stack([filt[rays[:, 0]], filt[rays[:, 0] + rays[:, 1]] - filt[rays[:, 0]]], -1).astype(np.int32)
+    x2, t2 = x[keep], t[keep]
+    sig_o, rgb_o = fo.point_decode(torch.from_numpy(x2), *pt, levels)
+    w_o, ws_o, d_o, img_o = orc.composite_rays_train_forward(sig_o.detach().numpy(), rgb_o.detach().numpy(), t2, rays2)
+    gws, gd, gi = (rng.normal(size=s).astype(np.float32) for s in [(N,), (N,), (N, 3)])
+    gw = np.zeros(x2.shape[0], np.float32)
+    gs_o, gc_o = orc.composite_rays_train_backward(gw, gws, gd, gi, sig_o.detach().numpy(), rgb_o.detach().numpy(), t2, rays2, ws_o, d_o, img_o)
+    torch.autograd.backward([sig_o, rgb_o], [torch.from_numpy(gs_o), torch.from_numpy(gc_o)])
+    out = dec(torch.from_numpy(ro).cuda()[None], torch.from_numpy(rd).cuda()[None], None, torch.from_numpy(bitfield).cuda()[None], H,
+              dt_gamma=1 / f, perturb=True, noises=torch.from_numpy(noises).cuda())
+    assert abs(out['ts'][0].shape[0] - x2.shape[0]) <= max(3, 0.002 * x2.shape[0])
+    ok = np.abs(out['weights_sum'][0].detach().cpu().numpy() - ws_o) < 2e-3
+    assert ok.mean() > 0.99
+    np.testing.assert_allclose(out['image'][0].detach().cpu().numpy()[ok], img_o[ok], rtol=2e-3, atol=5e-5)
+    np.testing.assert_allclose(out['depth'][0].detach().cpu().numpy()[ok], d_o[ok], rtol=2e-3, atol=5e-5)
+    gmask = torch.from_numpy(ok.astype(np.float32)).cuda()
+    torch.autograd.backward([out['weights_sum'], out['depth'], out['image']],
+                            [torch.from_numpy(gws).cuda()[None] , torch.from_numpy(gd).cuda()[None], torch.from_numpy(gi).cuda()[None]])
+    a, b = dec.mlp.net[1].weight.grad.cpu().double(), pt[3].grad.double()
+    assert (a - b).abs().max() <= 2e-2 * b.abs().max()
+    a, b = dec.encoder.params.grad.cpu().double(), pt[0].grad.double().reshape(-1)
+    assert (a - b).abs().max() <= 2e-2 * b.abs().max()
+
+
+def test_update_extra_state_vs_oracle():
+    dec, levels, params = make_decoder(table_scale=1.0)
+    H = 32
+    g = torch.Generator().manual_seed(5)
+    noise = torch.rand(H ** 3, 3, generator=g)
+    grid = torch.zeros(1, H ** 3, dtype=torch.float16, device='cuda')
+    grid[0, ::7] = 0.3
+    grid[0, 5::11] = -1.0        # cells marked invalid stay untouched
+    bitfield = torch.zeros(1, H ** 3 // 8, dtype=torch.uint8, device='cuda')
+    grid_o = grid.cpu().clone()
+    dec.update_extra_state(None, grid, bitfield, 0, density_thresh=0.1, noise=noise)
+    # oracle: base_volume_renderer.py:118-175 restated with numpy / the field oracle
+    c = torch.arange(H)
+    xx, yy, zz = torch.meshgrid(c, c, c, indexing='ij')
+    coords = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], -1)
+    idx = torch.from_numpy(orc.morton3D(coords.numpy().astype(np.int32)).astype(np.int64))
+    xyzs = (coords.float() - (H - 1) / 2) * (2 * 1.0 / H) + noise * (2 * 1.0 / H) - 1.0 / H
+    with torch.no_grad():
+        sig, _ = fo.point_decode(xyzs, *params, levels)
+    tmp = torch.full_like(grid_o, -1)
+    tmp[0, idx] = sig.clamp(max=torch.finfo(torch.float16).max).to(torch.float16)
+    valid = (grid_o >= 0) & (tmp >= 0)
+    new = torch.where(valid, torch.maximum(grid_o * 0.9, tmp), grid_o)
+    mean = torch.mean(new.clamp(min=0))
+    thresh = min(float(mean), 0.1)
+    bf_o = orc.packbits(new.float().numpy().reshape(-1), thresh)
+    got = grid.cpu().float().numpy().reshape(-1)
+    exp = new.float().numpy().reshape(-1)
+    np.testing.assert_allclose(got, exp, rtol=2e-3, atol=1e-4)    # fp16 grid: 1 ulp = 1e-3 relative
+    diff = np.unpackbits(bitfield.cpu().numpy().reshape(-1) ^ bf_o).sum()
+    assert diff <= 0.002 * H ** 3
