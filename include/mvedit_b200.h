@@ -184,6 +184,28 @@ int mve_cull_samples(const float* weights, float th, const int32_t* rays_in, con
 int mve_density_grid_update(void* grid_half, const float* sigmas, const int32_t* indices, uint32_t n, float decay,
                             float* sum_scratch, uint32_t n_cells, float density_thresh, uint8_t* bitfield, void* stream);
 
+/* Flash attention (tcgen05): O[b, i, h, :] = softmax_j(scale * Q[b,i,h,:].K[b,j,h,:]) V[b,j,h,:].
+ * Q [batch, q_len, heads, d] with row stride ldq (elements; e.g. the q slice of a fused qkv GEMM output), K/V [batch, kv_len, heads, d]
+ * (ldk/ldv), O [batch, q_len, heads*d] (ldo).  bf16, d in {40,64,80,128,160}.  Replaces F.scaled_dot_product_attention under
+ * AttnProcessor2_0 / CrossImageAttnProcWrapper (lib/models/architecture/joint_attn.py:11-37). */
+int mve_attention_bf16(const void* Q, const void* K, const void* V, void* O, uint32_t batch, uint32_t heads,
+                       uint32_t q_len, uint32_t kv_len, uint32_t d, uint32_t ldq, uint32_t ldk, uint32_t ldv, uint32_t ldo,
+                       float scale, void* stream);
+
+/* HBM-bound glue of the UNet path (bf16, NHWC / row-major).  Replace torch.nn.GroupNorm / LayerNorm / GEGLU / F.interpolate /
+ * strided-conv unfolding inside diffusers ResnetBlock2D, Transformer2DModel, Upsample2D, Downsample2D. */
+/* x,y [B,HW,C]; G groups (32); stats_scratch: B*G*2 floats of device scratch. */
+int mve_groupnorm_bf16(const void* x, void* y, uint32_t B, uint32_t HW, uint32_t C, uint32_t G,
+                       const float* gamma, const float* beta, float eps, int silu_act, float* stats_scratch, void* stream);
+int mve_layernorm_bf16(const void* x, void* y, uint32_t rows, uint32_t C, const float* gamma, const float* beta, float eps, void* stream);
+/* h [M,2F] -> y [M,F] = h[:, :F] * gelu(h[:, F:]) */
+int mve_geglu_bf16(const void* h, void* y, uint64_t M, uint32_t F, void* stream);
+int mve_upsample2x_bf16(const void* x, void* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* stream);
+/* x [B,H,W,C] -> y [B*(H/2)*(W/2), 9*C] patches of a 3x3 stride-2 pad-1 conv (K index = tap*C + c) */
+int mve_im2col3x3s2_bf16(const void* x, void* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* stream);
+/* x [B,C,HW] (f32 or bf16) -> y [B,HW,Cpad] bf16, channels >= C zero-filled */
+int mve_nchw_to_nhwc_pad_bf16(const void* x, int x_is_f32, void* y, uint32_t B, uint32_t C, uint32_t HW, uint32_t Cpad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

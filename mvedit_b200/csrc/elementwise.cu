@@ -1,0 +1,269 @@
+// elementwise.cu -- HBM-bound glue of the UNet / ControlNet path (bf16, NHWC / row-major, 16-byte vector accesses):
+//   GroupNorm(32)+SiLU, LayerNorm, GEGLU gate, nearest x2 upsample, stride-2 3x3 im2col, timestep sinusoid.
+// These replace torch.nn.GroupNorm / LayerNorm / F.gelu / F.interpolate calls inside diffusers' ResnetBlock2D,
+// Transformer2DModel, Upsample2D, Downsample2D; each is one read + one write of its tensor.
+#include "common.cuh"
+#include "../../include/mvedit_b200.h"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+using bf162 = __nv_bfloat162;
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+    const bf162* h = reinterpret_cast<const bf162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 o;
+    bf162* h = reinterpret_cast<bf162*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return o;
+}
+__device__ __forceinline__ float silu(float v) { return v / (1.0f + __expf(-v)); }
+
+// ---------------------------------------------------------------- GroupNorm
+// stats: grid (chunks, B). Each CTA walks a pixel range of image b; thread t owns the 8-channel vector (t % (C/8)) and a pixel
+// lane (t / (C/8)); per-channel partial sums are folded to their groups with shared-memory atomics, one global atomic per
+// (group, CTA).  stats[b][g] = (sum, sumsq) fp32, zeroed by the launcher.
+constexpr int GN_T = 256;
+__global__ void __launch_bounds__(GN_T) k_gn_stats(const bf16* __restrict__ x, const uint32_t HW, const uint32_t C, const uint32_t G,
+                                                   const uint32_t px_per_cta, float* __restrict__ stats) {
+    __shared__ float s_sum[64], s_sq[64];
+    const uint32_t b = blockIdx.y;
+    const uint32_t vec_per_px = C / 8;
+    if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+    __syncthreads();
+    const uint32_t p0 = blockIdx.x * px_per_cta, p1 = min(HW, p0 + px_per_cta);
+    const size_t base = (size_t)b * HW * C;
+    const uint32_t cpg = C / G;
+    // flat vector index over [p0, p1) x vec_per_px, strided by the CTA
+    const uint32_t total = (p1 > p0 ? (p1 - p0) : 0) * vec_per_px;
+    // a thread keeps the same channel vector when GN_T % vec_per_px == 0 (C = 320, 640, 1280, 2560 do not all satisfy it), so accumulate per visit
+    for (uint32_t i = threadIdx.x; i < total; i += GN_T) {
+        const uint32_t px = p0 + i / vec_per_px, cv = i % vec_per_px;
+        const uint4 raw = *reinterpret_cast<const uint4*>(x + base + (size_t)px * C + cv * 8);
+        float f[8];
+        unpack8(raw, f);
+        const uint32_t c0 = cv * 8;
+        const uint32_t g0 = c0 / cpg, g1 = (c0 + 7) / cpg;
+        if (g0 == g1) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { s += f[k]; q += f[k] * f[k]; }
+            atomicAdd(&s_sum[g0], s); atomicAdd(&s_sq[g0], q);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const uint32_t g = (c0 + k) / cpg; atomicAdd(&s_sum[g], f[k]); atomicAdd(&s_sq[g], f[k] * f[k]); }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        atomicAdd(&stats[((size_t)b * G + threadIdx.x) * 2], s_sum[threadIdx.x]);
+        atomicAdd(&stats[((size_t)b * G + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+    }
+}
+
+// apply: y = (x - mean) * rstd * gamma + beta, optional SiLU.  grid (chunks, B); per-channel scale/shift staged in smem.
+__global__ void __launch_bounds__(GN_T) k_gn_apply(const bf16* __restrict__ x, bf16* __restrict__ y, const uint32_t HW, const uint32_t C,
+                                                   const uint32_t G, const uint32_t px_per_cta, const float* __restrict__ stats,
+                                                   const float* __restrict__ gamma, const float* __restrict__ beta, const float eps,
+                                                   const int act) {
+    extern __shared__ float s_ab[];  // [2][C]
+    const uint32_t b = blockIdx.y;
+    const uint32_t cpg = C / G;
+    const float inv_n = 1.0f / ((float)HW * (float)cpg);
+    for (uint32_t c = threadIdx.x; c < C; c += GN_T) {
+        const uint32_t g = c / cpg;
+        const float mean = stats[((size_t)b * G + g) * 2] * inv_n;
+        const float var = fmaxf(stats[((size_t)b * G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+        const float a = rsqrtf(var + eps) * gamma[c];
+        s_ab[c] = a;
+        s_ab[C + c] = beta[c] - mean * a;
+    }
+    __syncthreads();
+    const uint32_t vec_per_px = C / 8;
+    const uint32_t p0 = blockIdx.x * px_per_cta, p1 = min(HW, p0 + px_per_cta);
+    const size_t base = (size_t)b * HW * C;
+    const uint32_t total = (p1 > p0 ? (p1 - p0) : 0) * vec_per_px;
+    for (uint32_t i = threadIdx.x; i < total; i += GN_T) {
+        const uint32_t px = p0 + i / vec_per_px, cv = i % vec_per_px;
+        const size_t off = base + (size_t)px * C + cv * 8;
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + off), f);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            float v = fmaf(f[k], s_ab[cv * 8 + k], s_ab[C + cv * 8 + k]);
+            f[k] = act ? silu(v) : v;
+        }
+        *reinterpret_cast<uint4*>(y + off) = pack8(f);
+    }
+}
+
+// ---------------------------------------------------------------- LayerNorm over the last dim, one warp per row
+__global__ void __launch_bounds__(256) k_layernorm(const bf16* __restrict__ x, bf16* __restrict__ y, const uint32_t rows, const uint32_t C,
+                                                   const float* __restrict__ gamma, const float* __restrict__ beta, const float eps) {
+    const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const bf16* xr = x + (size_t)row * C;
+    const uint32_t nvec = C / 8;
+    float s = 0.f, q = 0.f;
+    // C <= 1280 on this path: at most 5 vectors per lane, kept in registers
+    float f[5][8];
+    int cnt = 0;
+    for (uint32_t v = lane; v < nvec; v += 32, cnt++) {
+        unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f[cnt]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { s += f[cnt][k]; q += f[cnt][k] * f[cnt][k]; }
+    }
+    s = warp_sum(s); q = warp_sum(q);
+    const float mean = s / C;
+    const float rstd = rsqrtf(fmaxf(q / C - mean * mean, 0.f) + eps);
+    cnt = 0;
+    for (uint32_t v = lane; v < nvec; v += 32, cnt++) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = (f[cnt][k] - mean) * rstd * gamma[v * 8 + k] + beta[v * 8 + k];
+        *reinterpret_cast<uint4*>(y + (size_t)row * C + v * 8) = pack8(o);
+    }
+}
+
+// ---------------------------------------------------------------- GEGLU: y[m, j] = h[m, j] * gelu(h[m, F + j]),  h [M, 2F]
+__global__ void __launch_bounds__(256) k_geglu(const bf16* __restrict__ h, bf16* __restrict__ y, const size_t M, const uint32_t F) {
+    const size_t nvec = M * (F / 8);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (size_t)gridDim.x * 256) {
+        const size_t m = i / (F / 8);
+        const uint32_t j = (uint32_t)(i % (F / 8)) * 8;
+        float a[8], g[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(h + m * 2 * F + j), a);
+        unpack8(*reinterpret_cast<const uint4*>(h + m * 2 * F + F + j), g);
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = a[k] * (0.5f * g[k] * (1.0f + erff(g[k] * 0.70710678118654752f)));
+        *reinterpret_cast<uint4*>(y + m * F + j) = pack8(o);
+    }
+}
+
+// ---------------------------------------------------------------- nearest x2 upsample NHWC
+__global__ void __launch_bounds__(256) k_upsample2x(const bf16* __restrict__ x, bf16* __restrict__ y, const uint32_t B, const uint32_t H,
+                                                    const uint32_t W, const uint32_t C) {
+    const uint32_t vpp = C / 8;
+    const size_t total = (size_t)B * 2 * H * 2 * W * vpp;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const uint32_t cv = (uint32_t)(i % vpp);
+        size_t px = i / vpp;
+        const uint32_t ow = (uint32_t)(px % (2 * W)); px /= 2 * W;
+        const uint32_t oh = (uint32_t)(px % (2 * H));
+        const uint32_t b = (uint32_t)(px / (2 * H));
+        const uint4 v = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + oh / 2) * W + ow / 2) * C + cv * 8);
+        *reinterpret_cast<uint4*>(y + i * 8) = v;
+    }
+}
+
+// ---------------------------------------------------------------- im2col for 3x3 stride-2 pad-1 conv: out [B*Ho*Wo, 9*C], K index = tap*C + c
+__global__ void __launch_bounds__(256) k_im2col_s2(const bf16* __restrict__ x, bf16* __restrict__ y, const uint32_t B, const uint32_t H,
+                                                   const uint32_t W, const uint32_t C) {
+    const uint32_t Ho = H / 2, Wo = W / 2, vpp = C / 8;
+    const size_t total = (size_t)B * Ho * Wo * 9 * vpp;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const uint32_t cv = (uint32_t)(i % vpp);
+        size_t r = i / vpp;
+        const uint32_t tap = (uint32_t)(r % 9); r /= 9;
+        const uint32_t wo = (uint32_t)(r % Wo); r /= Wo;
+        const uint32_t ho = (uint32_t)(r % Ho);
+        const uint32_t b = (uint32_t)(r / Ho);
+        const int ih = (int)(2 * ho) + (int)(tap / 3) - 1, iw = (int)(2 * wo) + (int)(tap % 3) - 1;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (ih >= 0 && ih < (int)H && iw >= 0 && iw < (int)W) v = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + ih) * W + iw) * C + cv * 8);
+        *reinterpret_cast<uint4*>(y + i * 8) = v;
+    }
+}
+
+// ---------------------------------------------------------------- NCHW fp32/bf16 <-> NHWC bf16 with channel padding (latents 4ch, control images 3ch)
+template <typename T>
+__global__ void k_nchw_to_nhwc_pad(const T* __restrict__ x, bf16* __restrict__ y, const uint32_t B, const uint32_t C, const uint32_t HW,
+                                   const uint32_t Cpad) {
+    const size_t total = (size_t)B * HW * Cpad;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const uint32_t c = (uint32_t)(i % Cpad);
+        const size_t px = i / Cpad;
+        const uint32_t b = (uint32_t)(px / HW), p = (uint32_t)(px % HW);
+        y[i] = (c < C) ? __float2bfloat16((float)x[((size_t)b * C + c) * HW + p]) : __float2bfloat16(0.f);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mve_groupnorm_bf16(const void* x, void* y, uint32_t B, uint32_t HW, uint32_t C, uint32_t G, const float* gamma, const float* beta,
+                       float eps, int silu_act, float* stats_scratch, void* stream) {
+    if (B == 0) return 0;
+    MVE_ARG(C % 8 == 0 && C % G == 0 && G <= 64, "groupnorm: C % 8 == 0, C % G == 0, G <= 64 required");
+    cudaStream_t s = (cudaStream_t)stream;
+    MVE_CUDA(cudaMemsetAsync(stats_scratch, 0, (size_t)B * G * 2 * sizeof(float), s));
+    // aim for ~4 CTAs per SM in total
+    uint32_t chunks = (4 * kNumSM + B - 1) / B;
+    if (chunks < 1) chunks = 1;
+    uint32_t px_per_cta = (HW + chunks - 1) / chunks;
+    if (px_per_cta < 8) px_per_cta = 8;
+    chunks = (HW + px_per_cta - 1) / px_per_cta;
+    const dim3 grid(chunks, B);
+    k_gn_stats<<<grid, GN_T, 0, s>>>((const bf16*)x, HW, C, G, px_per_cta, stats_scratch);
+    k_gn_apply<<<grid, GN_T, 2 * C * sizeof(float), s>>>((const bf16*)x, (bf16*)y, HW, C, G, px_per_cta, stats_scratch, gamma, beta, eps,
+                                                          silu_act);
+    MVE_CHECK_LAUNCH("mve_groupnorm_bf16");
+    return 0;
+}
+
+int mve_layernorm_bf16(const void* x, void* y, uint32_t rows, uint32_t C, const float* gamma, const float* beta, float eps, void* stream) {
+    if (rows == 0) return 0;
+    MVE_ARG(C % 8 == 0 && C <= 1280, "layernorm: C % 8 == 0 and C <= 1280 required");
+    k_layernorm<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, rows, C, gamma, beta, eps);
+    MVE_CHECK_LAUNCH("mve_layernorm_bf16");
+    return 0;
+}
+
+int mve_geglu_bf16(const void* h, void* y, uint64_t M, uint32_t F, void* stream) {
+    if (M == 0) return 0;
+    MVE_ARG(F % 8 == 0, "geglu: F % 8 == 0 required");
+    const size_t nvec = (size_t)M * (F / 8);
+    uint32_t grid = (uint32_t)((nvec + 255) / 256 < (size_t)(16 * kNumSM) ? (nvec + 255) / 256 : (size_t)(16 * kNumSM));
+    k_geglu<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)h, (bf16*)y, (size_t)M, F);
+    MVE_CHECK_LAUNCH("mve_geglu_bf16");
+    return 0;
+}
+
+int mve_upsample2x_bf16(const void* x, void* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* stream) {
+    if (B == 0) return 0;
+    MVE_ARG(C % 8 == 0, "upsample2x: C % 8 == 0 required");
+    const size_t total = (size_t)B * 4 * H * W * (C / 8);
+    uint32_t grid = (uint32_t)((total + 255) / 256 < (size_t)(16 * kNumSM) ? (total + 255) / 256 : (size_t)(16 * kNumSM));
+    k_upsample2x<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, C);
+    MVE_CHECK_LAUNCH("mve_upsample2x_bf16");
+    return 0;
+}
+
+int mve_im2col3x3s2_bf16(const void* x, void* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* stream) {
+    if (B == 0) return 0;
+    MVE_ARG(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "im2col3x3s2: C % 8 == 0, even H and W required");
+    const size_t total = (size_t)B * (H / 2) * (W / 2) * 9 * (C / 8);
+    uint32_t grid = (uint32_t)((total + 255) / 256 < (size_t)(16 * kNumSM) ? (total + 255) / 256 : (size_t)(16 * kNumSM));
+    k_im2col_s2<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, C);
+    MVE_CHECK_LAUNCH("mve_im2col3x3s2_bf16");
+    return 0;
+}
+
+int mve_nchw_to_nhwc_pad_bf16(const void* x, int x_is_f32, void* y, uint32_t B, uint32_t C, uint32_t HW, uint32_t Cpad, void* stream) {
+    if (B == 0) return 0;
+    MVE_ARG(Cpad >= C, "nchw_to_nhwc_pad: Cpad >= C required");
+    const size_t total = (size_t)B * HW * Cpad;
+    uint32_t grid = (uint32_t)((total + 255) / 256 < (size_t)(16 * kNumSM) ? (total + 255) / 256 : (size_t)(16 * kNumSM));
+    if (x_is_f32) k_nchw_to_nhwc_pad<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (bf16*)y, B, C, HW, Cpad);
+    else k_nchw_to_nhwc_pad<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, C, HW, Cpad);
+    MVE_CHECK_LAUNCH("mve_nchw_to_nhwc_pad_bf16");
+    return 0;
+}
+
+}  // extern "C"

@@ -347,7 +347,7 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
             loss.backward()
             optimizer.step()
             if debug:
-                log.append(dict(loss=float(loss), pixel_rgb=float(pixel_rgb_loss), alpha=float(alphas_loss),
-                                normal_reg=float(normal_reg_loss), entropy=float(entropy_loss)))
+                log.append(dict(loss=float(loss.detach()), pixel_rgb=float(pixel_rgb_loss.detach()), alpha=float(alphas_loss.detach()),
+                                normal_reg=float(normal_reg_loss.detach()), entropy=float(entropy_loss.detach())))
     nerf.decoder.train(decoder_training_prev)
     return log

@@ -62,7 +62,7 @@ def test_field_forward_backward_vs_oracle(L, R):
     np.testing.assert_allclose(sig.detach().cpu().numpy(), sig_o.detach().numpy(), rtol=2e-4, atol=1e-6)
     np.testing.assert_allclose(rgb.detach().cpu().numpy(), rgb_o.detach().numpy(), rtol=2e-4, atol=1e-6)
     sd, _ = dec.point_density_decode([xyz.cuda()], None)
-    np.testing.assert_allclose(sd.cpu().numpy(), sig_o.detach().numpy(), rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(sd.detach().cpu().numpy(), sig_o.detach().numpy(), rtol=2e-4, atol=1e-6)
     torch.autograd.backward([sig, rgb], [gs.cuda(), gr.cuda()])
 
     def close(a, b, rel):
@@ -83,8 +83,8 @@ def test_field_empty_and_tiny():
     assert s.numel() == 0 and r.shape == (0, 3) and n == [0]
     s, r, _ = dec.point_decode([torch.zeros(1, 3, device='cuda')], None, None)
     so, ro = fo.point_decode(torch.zeros(1, 3), *params, levels)
-    np.testing.assert_allclose(s.cpu().numpy(), so.numpy(), rtol=2e-4)
-    np.testing.assert_allclose(r.cpu().numpy(), ro.numpy(), rtol=2e-4)
+    np.testing.assert_allclose(s.detach().cpu().numpy(), so.detach().numpy(), rtol=2e-4)
+    np.testing.assert_allclose(r.detach().cpu().numpy(), ro.detach().numpy(), rtol=2e-4)
 
 
 def _scene(H=32, views=2, size=24):
