@@ -108,11 +108,11 @@ int mve_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int bi
  * ------------------------------------------------------------------------- */
 
 /* C[M,N] = act(A[M,K] . B[N,K]^T + bias[N] + row_bias[row / rows_per_group, N]) * alpha + residual[M,N]
- * A, B, C, residual bf16 (lda/ldb/ldc/ldr in elements, multiples of 8); bias/row_bias f32 or NULL; K % 64 == 0.
+ * A, B, C, residual bf16 (lda/ldb/ldc/ldr in elements, multiples of 8); bias/row_bias f32 or NULL (row_bias row stride ldrb, 0 = N); K % 64 == 0.
  * act: 0 none, 1 SiLU, 2 GELU(erf).  Replaces torch.nn.functional.linear / 1x1 conv (cuBLAS) on the UNet path. */
 int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N, uint32_t K,
                   uint32_t lda, uint32_t ldb, uint32_t ldc,
-                  const float* bias, const float* row_bias, uint32_t rows_per_group,
+                  const float* bias, const float* row_bias, uint32_t rows_per_group, uint32_t ldrb,
                   const void* residual, uint32_t ldr, int act, float alpha, void* stream);
 
 /* 3x3 convolution, stride 1, pad 1, as an implicit GEMM (no im2col buffer): X [B,H,W,Cin] bf16 NHWC,
@@ -121,7 +121,7 @@ int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N,
  * Replaces torch.nn.functional.conv2d (cuDNN) on the UNet path. */
 int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t B, uint32_t H, uint32_t W,
                      uint32_t Cin, uint32_t Cout, uint32_t ldy,
-                     const float* bias, const float* row_bias, const void* residual, uint32_t ldr,
+                     const float* bias, const float* row_bias, uint32_t ldrb, const void* residual, uint32_t ldr,
                      int act, float alpha, void* stream);
 
 /* ---------------------------------------------------------------------------

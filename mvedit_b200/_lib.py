@@ -39,6 +39,15 @@ def ptr(t):
     return c_void_p(t.data_ptr())
 
 
+def raw_ptr(t):
+    """Device pointer of a (possibly strided) CUDA tensor view; the caller passes the strides explicitly."""
+    if t is None:
+        return c_void_p(0)
+    if not t.is_cuda:
+        raise RuntimeError('mvedit_b200 ops need CUDA tensors (no CPU fallback); got device %s' % t.device)
+    return c_void_p(t.data_ptr())
+
+
 def stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -32,7 +32,7 @@ struct GemmParams {
     // epilogue
     const float* bias;              // [N] or null
     const float* row_bias;          // [M / rows_per_group, N] or null
-    uint32_t rows_per_group;
+    uint32_t rows_per_group, ldrb;
     const __nv_bfloat16* residual;  // [M, ldr] or null
     uint32_t ldr;
     int act;                        // 0 none, 1 SiLU, 2 GELU(erf)
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
             tc::tc_fence_after();
             const uint32_t t_row = tmem_base + acc * C_::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
             const bool row_ok = row < p.M;
-            const float* rb = (p.row_bias && row_ok) ? p.row_bias + (size_t)(row / p.rows_per_group) * p.N : nullptr;
+            const float* rb = (p.row_bias && row_ok) ? p.row_bias + (size_t)(row / p.rows_per_group) * p.ldrb : nullptr;
             constexpr int CH = (BN >= 32) ? 32 : 16;
 #pragma unroll 1
             for (int c = 0; c < BN; c += CH) {
@@ -303,8 +303,8 @@ int mve_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint6
 extern "C" {
 
 int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb, uint32_t ldc,
-                  const float* bias, const float* row_bias, uint32_t rows_per_group, const void* residual, uint32_t ldr, int act,
-                  float alpha, void* stream) {
+                  const float* bias, const float* row_bias, uint32_t rows_per_group, uint32_t ldrb, const void* residual, uint32_t ldr,
+                  int act, float alpha, void* stream) {
     if (M == 0 || N == 0) return 0;
     MVE_ARG(K % BK == 0 && K > 0, "gemm: K must be a positive multiple of 64");
     MVE_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (16-byte TMA strides)");
@@ -327,14 +327,14 @@ int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N,
     GemmParams p{};
     p.C = (__nv_bfloat16*)C; p.M = M; p.N = N; p.ldc = ldc; p.num_kb = K / BK;
     p.m_tiles = (M + BM - 1) / BM; p.n_tiles = (N + bn - 1) / bn;
-    p.bias = bias; p.row_bias = row_bias; p.rows_per_group = rows_per_group;
+    p.bias = bias; p.row_bias = row_bias; p.rows_per_group = rows_per_group; p.ldrb = ldrb ? ldrb : N;
     p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act; p.alpha = alpha;
     return dispatch<0>(bn, tmA, tmB, p, (cudaStream_t)stream);
 }
 
 int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32_t H, uint32_t W, uint32_t Cin, uint32_t Cout,
-                     uint32_t ldy, const float* bias, const float* row_bias, const void* residual, uint32_t ldr, int act, float alpha,
-                     void* stream) {
+                     uint32_t ldy, const float* bias, const float* row_bias, uint32_t ldrb, const void* residual, uint32_t ldr, int act,
+                     float alpha, void* stream) {
     if (Bn == 0) return 0;
     MVE_ARG(Cin % BK == 0, "conv3x3: Cin must be a multiple of 64 (pad channels)");
     MVE_ARG((W <= 128 && 128 % W == 0) || W % 128 == 0, "conv3x3: W must divide 128 or be a multiple of 128");
@@ -362,7 +362,7 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32
     GemmParams p{};
     p.C = (__nv_bfloat16*)Y; p.M = M; p.N = Cout; p.ldc = ldy; p.num_kb = 9 * (Cin / BK);
     p.m_tiles = M / BM; p.n_tiles = (Cout + bn - 1) / bn;
-    p.bias = bias; p.row_bias = row_bias; p.rows_per_group = H * W;
+    p.bias = bias; p.row_bias = row_bias; p.rows_per_group = H * W; p.ldrb = ldrb ? ldrb : Cout;
     p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act; p.alpha = alpha;
     p.H = H; p.W = W; p.cin_chunks = Cin / BK;
     return dispatch<1>(bn, tmA, tmB, p, (cudaStream_t)stream);

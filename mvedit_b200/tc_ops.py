@@ -5,7 +5,9 @@ Adapter3DMixin.get_noise_pred* makes, adapter3d_mixin.py:101-125).  bf16 storage
 """
 import torch
 
-from ._lib import call, ptr, stream, c_int, c_u32, c_f32
+import ctypes
+
+from ._lib import call, ptr, raw_ptr, stream, c_int, c_u32, c_f32
 
 ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2}
 
@@ -22,8 +24,10 @@ def gemm(a, w, bias=None, row_bias=None, rows_per_group=0, residual=None, act=No
         assert bias.dtype == torch.float32 and bias.numel() == N
     if row_bias is not None:
         assert row_bias.dtype == torch.float32 and row_bias.shape[-1] == N
-    call('mve_gemm_bf16', ptr(a), ptr(w), ptr(out), c_u32(M), c_u32(N), c_u32(K), c_u32(a.stride(0)), c_u32(w.stride(0)),
-         c_u32(out.stride(0)), ptr(bias), ptr(row_bias), c_u32(rows_per_group), ptr(residual),
+    assert a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1
+    call('mve_gemm_bf16', raw_ptr(a), raw_ptr(w), raw_ptr(out), c_u32(M), c_u32(N), c_u32(K), c_u32(a.stride(0)), c_u32(w.stride(0)),
+         c_u32(out.stride(0)), ptr(bias), raw_ptr(row_bias), c_u32(rows_per_group),
+         c_u32(row_bias.stride(0) if row_bias is not None else 0), raw_ptr(residual),
          c_u32(residual.stride(0) if residual is not None else 0), c_int(ACT[act]), c_f32(alpha), stream())
     return out
 
@@ -38,6 +42,86 @@ def conv3x3(x, w, bias=None, row_bias=None, residual=None, act=None, alpha=1.0, 
     if out is None:
         out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=x.device)
     call('mve_conv3x3_bf16', ptr(x), ptr(w), ptr(out), c_u32(B), c_u32(H), c_u32(W), c_u32(Cin), c_u32(Cout), c_u32(out.stride(2)),
-         ptr(bias), ptr(row_bias), ptr(residual), c_u32(residual.stride(2) if residual is not None else 0), c_int(ACT[act]),
+         ptr(bias), raw_ptr(row_bias), c_u32(row_bias.stride(0) if row_bias is not None else 0), ptr(residual),
+         c_u32(residual.stride(2) if residual is not None else 0), c_int(ACT[act]),
          c_f32(alpha), stream())
+    return out
+
+
+def attention(q, k, v, heads, scale=None, out=None):
+    """q [B, Sq, heads*d] (row stride may exceed heads*d: slices of a fused projection), k/v [B, Skv, heads*d] -> [B, Sq, heads*d]."""
+    B, Sq, C = q.shape
+    Skv = k.shape[1]
+    d = C // heads
+    assert q.dtype == torch.bfloat16 and q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    assert q.stride(0) == Sq * q.stride(1) and k.stride(0) == Skv * k.stride(1) and v.stride(0) == Skv * v.stride(1)
+    if out is None:
+        out = torch.empty(B, Sq, C, dtype=torch.bfloat16, device=q.device)
+    call('mve_attention_bf16', raw_ptr(q), raw_ptr(k), raw_ptr(v), ptr(out), c_u32(B), c_u32(heads), c_u32(Sq), c_u32(Skv), c_u32(d),
+         c_u32(q.stride(1)), c_u32(k.stride(1)), c_u32(v.stride(1)), c_u32(out.stride(1)), c_f32(scale if scale is not None else d ** -0.5),
+         stream())
+    return out
+
+
+_gn_scratch = {}
+
+
+def groupnorm(x, gamma, beta, groups=32, eps=1e-5, silu=False, out=None):
+    """x [B, ..., C] bf16 channels-last -> same shape."""
+    B, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C)
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty_like(x)
+    key = (x.device, B * groups)
+    if key not in _gn_scratch:
+        _gn_scratch[key] = torch.empty(B * groups * 2, dtype=torch.float32, device=x.device)
+    call('mve_groupnorm_bf16', ptr(x), ptr(out), c_u32(B), c_u32(HW), c_u32(C), c_u32(groups), ptr(gamma), ptr(beta), c_f32(eps),
+         c_int(int(silu)), ptr(_gn_scratch[key]), stream())
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    C = x.shape[-1]
+    rows = x.numel() // C
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty_like(x)
+    call('mve_layernorm_bf16', ptr(x), ptr(out), c_u32(rows), c_u32(C), ptr(gamma), ptr(beta), c_f32(eps), stream())
+    return out
+
+
+def geglu(h, out=None):
+    F2 = h.shape[-1]
+    M = h.numel() // F2
+    assert h.is_contiguous() and h.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty(*h.shape[:-1], F2 // 2, dtype=torch.bfloat16, device=h.device)
+    call('mve_geglu_bf16', ptr(h), ptr(out), ctypes.c_uint64(M), c_u32(F2 // 2), stream())
+    return out
+
+
+def upsample2x(x):
+    B, H, W, C = x.shape
+    out = torch.empty(B, 2 * H, 2 * W, C, dtype=torch.bfloat16, device=x.device)
+    call('mve_upsample2x_bf16', ptr(x), ptr(out), c_u32(B), c_u32(H), c_u32(W), c_u32(C), stream())
+    return out
+
+
+def im2col3x3s2(x):
+    B, H, W, C = x.shape
+    out = torch.empty(B * (H // 2) * (W // 2), 9 * C, dtype=torch.bfloat16, device=x.device)
+    call('mve_im2col3x3s2_bf16', ptr(x), ptr(out), c_u32(B), c_u32(H), c_u32(W), c_u32(C), stream())
+    return out
+
+
+def nchw_to_nhwc_pad(x, cpad):
+    """x [B,C,H,W] f32/bf16 -> [B,H,W,cpad] bf16 (zero channel padding)."""
+    B, C, H, W = x.shape
+    x = x.contiguous()
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    out = torch.empty(B, H, W, cpad, dtype=torch.bfloat16, device=x.device)
+    call('mve_nchw_to_nhwc_pad_bf16', ptr(x), c_int(int(x.dtype == torch.float32)), ptr(out), c_u32(B), c_u32(C), c_u32(H * W), c_u32(cpad),
+         stream())
     return out

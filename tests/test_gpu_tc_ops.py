@@ -58,3 +58,79 @@ def test_conv3x3(B, H, W, Cin, Cout):
     ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1)
     ref = (ref + rb[:, :, None, None]).permute(0, 2, 3, 1)
     _check(out, ref, 9 * Cin)
+
+
+@pytest.mark.parametrize('B,heads,Sq,Skv,d', [(2, 8, 256, 256, 40), (1, 8, 1024, 1024, 80), (2, 8, 256, 256, 160), (3, 8, 64, 64, 160),
+                                              (2, 8, 1024, 77, 40), (2, 8, 256, 77, 80), (1, 8, 4096, 4096, 40), (2, 2, 128, 128, 64),
+                                              (1, 8, 512, 93, 160), (2, 1, 200, 300, 64)])
+def test_attention(B, heads, Sq, Skv, d):
+    """vs F.scaled_dot_product_attention in fp32 on the same bf16 inputs.  P is rounded to bf16 before P.V (as every flash
+    kernel does): tolerance 2e-2 of the output scale."""
+    from mvedit_b200 import tc_ops
+    g = torch.Generator(device='cuda').manual_seed(Sq + Skv + d)
+    C = heads * d
+    # q comes as a slice of a wider fused projection (row stride 3C), like in the UNet
+    qkv = torch.randn(B, Sq, 3 * C, device='cuda', generator=g).bfloat16()
+    q = qkv[:, :, :C]
+    k = torch.randn(B, Skv, C, device='cuda', generator=g).bfloat16()
+    v = torch.randn(B, Skv, C, device='cuda', generator=g).bfloat16()
+    out = tc_ops.attention(q, k, v, heads)
+    sh = lambda t, S: t.float().reshape(B, S, heads, d).transpose(1, 2)
+    ref = torch.nn.functional.scaled_dot_product_attention(sh(q, Sq), sh(k, Skv), sh(v, Skv)).transpose(1, 2).reshape(B, Sq, C)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item() + 1e-3, (err, ref.abs().max().item())
+    assert (out.float() - ref).abs().mean().item() <= 4e-3 * ref.abs().mean().item() + 1e-4
+
+
+def test_attention_peaked_softmax_rescale():
+    """large score range -> the running max moves in later key blocks, exercising the TMEM O-rescale path."""
+    from mvedit_b200 import tc_ops
+    g = torch.Generator(device='cuda').manual_seed(0)
+    B, heads, S, d = 1, 8, 512, 40
+    q = (torch.randn(B, S, heads * d, device='cuda', generator=g) * 4).bfloat16()
+    k = (torch.randn(B, S, heads * d, device='cuda', generator=g) * 4).bfloat16()
+    k[:, 300:] *= 2      # later keys dominate
+    v = torch.randn(B, S, heads * d, device='cuda', generator=g).bfloat16()
+    out = tc_ops.attention(q, k, v, heads)
+    sh = lambda t: t.float().reshape(B, S, heads, d).transpose(1, 2)
+    ref = torch.nn.functional.scaled_dot_product_attention(sh(q), sh(k), sh(v)).transpose(1, 2).reshape(B, S, heads * d)
+    assert (out.float() - ref).abs().max().item() <= 3e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize('B,HW,C', [(2, 64, 64), (3, 1024, 320), (2, 4096, 640), (2, 256, 1280), (1, 64, 2560), (2, 4096, 960)])
+@pytest.mark.parametrize('silu', [False, True])
+def test_groupnorm(B, HW, C, silu):
+    from mvedit_b200 import tc_ops
+    g = torch.Generator(device='cuda').manual_seed(C)
+    x = (torch.randn(B, HW, C, device='cuda', generator=g) * 2 + 0.5).bfloat16()
+    gamma, beta = torch.randn(C, device='cuda', generator=g), torch.randn(C, device='cuda', generator=g)
+    y = tc_ops.groupnorm(x, gamma, beta, 32, 1e-5, silu)
+    ref = torch.nn.functional.group_norm(x.float().transpose(1, 2), 32, gamma, beta, 1e-5).transpose(1, 2)
+    if silu:
+        ref = torch.nn.functional.silu(ref)
+    assert (y.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    assert (y.float() - ref).abs().mean().item() <= 4e-3 * ref.abs().mean().item() + 1e-4
+
+
+def test_layernorm_geglu_upsample_im2col_layout():
+    from mvedit_b200 import tc_ops
+    g = torch.Generator(device='cuda').manual_seed(0)
+    for C in (64, 320, 640, 1280):
+        x = torch.randn(777, C, device='cuda', generator=g).bfloat16()
+        gamma, beta = torch.randn(C, device='cuda', generator=g), torch.randn(C, device='cuda', generator=g)
+        ref = torch.nn.functional.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+        assert (tc_ops.layernorm(x, gamma, beta).float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    h = torch.randn(500, 2 * 1280, device='cuda', generator=g).bfloat16()
+    a, gate = h.float().chunk(2, dim=-1)
+    ref = a * torch.nn.functional.gelu(gate)
+    assert (tc_ops.geglu(h).float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    x = torch.randn(2, 8, 8, 64, device='cuda', generator=g).bfloat16()
+    up = tc_ops.upsample2x(x)
+    assert torch.equal(up, x.repeat_interleave(2, 1).repeat_interleave(2, 2))
+    cols = tc_ops.im2col3x3s2(x)
+    unf = torch.nn.functional.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)      # [B, C*9, L]  (c-major, tap-minor)
+    unf = unf.view(2, 64, 9, 16).permute(0, 3, 2, 1).reshape(2 * 16, 9 * 64)                      # -> tap-major, c-minor
+    assert torch.equal(cols.float(), unf)
+    lat = torch.randn(2, 4, 8, 8, device='cuda', generator=g)
+    nh = tc_ops.nchw_to_nhwc_pad(lat, 64)
+    assert torch.equal(nh[..., :4].float(), lat.bfloat16().float().permute(0, 2, 3, 1)) and nh[..., 4:].abs().sum() == 0

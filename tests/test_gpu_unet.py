@@ -1,0 +1,134 @@
+"""UNet / ControlNet / get_noise_pred{,_p1,_p2} on the tcgen05 kernels vs the fp32 oracle (oracle/unet_oracle.py, run in fp32 on
+the GPU with TF32 off) on the same random-init weights (diffusers key names).
+
+Tolerance (stated per north_star "within a stated FP tolerance on denoised latents"): the path stores every activation in bf16
+(8 mantissa bits) through ~60 layers; the bound used is  ||out - ref||_2 / ||ref||_2 <= 3e-2  and max-abs error <= 8e-2 * max|ref|.
+"""
+import pytest
+import torch
+
+from oracle import unet_oracle as uo
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm()).item(), ((a - b).abs().max() / b.abs().max()).item()
+
+
+@pytest.fixture(scope='module', autouse=True)
+def no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def _to(sd, dev):
+    return {k: v.to(dev) for k, v in sd.items()}
+
+
+@pytest.fixture(scope='module')
+def tiny():
+    from mvedit_b200.unet import UNet, ControlNet, MultiControlNet
+    cfg = uo.TINY
+    usd, c1, c2 = uo.random_unet_state_dict(cfg, 0), uo.random_controlnet_state_dict(cfg, 1), uo.random_controlnet_state_dict(cfg, 2)
+    return dict(cfg=cfg, usd=_to(usd, 'cuda'), csd=[_to(c1, 'cuda'), _to(c2, 'cuda')], unet=UNet(usd, cfg), cn=[ControlNet(c1, cfg), ControlNet(c2, cfg)],
+                multi=MultiControlNet)
+
+
+def test_unet_tiny_blocks_and_full(tiny):
+    cfg = tiny['cfg']
+    g = torch.Generator(device='cuda').manual_seed(0)
+    B, L = 4, 16
+    x = torch.randn(B, 4, L, L, device='cuda', generator=g)
+    ctx = torch.randn(B, 77, cfg.cross_attention_dim, device='cuda', generator=g)
+    with torch.no_grad():
+        ref = uo.unet_forward(tiny['usd'], cfg, x, 500, ctx)
+        out = tiny['unet'](x, 500, ctx)
+        assert out.shape == ref.shape
+        r2, rmax = rel(out, ref)
+        assert r2 <= 3e-2 and rmax <= 8e-2, (r2, rmax)
+        # enc/dec split returns the 12 skips in the reference's order and shapes (diffusers.py:85-97)
+        emb, res, s = tiny['unet'].enc(x, 500, ctx)
+        emb_o, res_o, s_o = uo.unet_enc(tiny['usd'], cfg, x, 500, ctx)
+        assert len(res) == len(res_o) == 12
+        for a, b in zip(res, res_o):
+            assert a.permute(0, 3, 1, 2).shape == b.shape
+            assert rel(a.permute(0, 3, 1, 2), b)[0] <= 3e-2
+        assert rel(s.permute(0, 3, 1, 2), s_o)[0] <= 3e-2
+
+
+def test_controlnet_and_noise_pred_modes(tiny):
+    from mvedit_b200.adapter3d_mixin import Adapter3DMixin
+    cfg = tiny['cfg']
+    g = torch.Generator(device='cuda').manual_seed(1)
+    N, L = 4, 16
+    lat = torch.randn(N, 4, L, L, device='cuda', generator=g)
+    pe = torch.randn(2 * N, 77, cfg.cross_attention_dim, device='cuda', generator=g)
+    ci = torch.rand(N, 3, 8 * L, 8 * L, device='cuda', generator=g)
+    cd = torch.rand(N, 3, 8 * L, 8 * L, device='cuda', generator=g)
+    with torch.no_grad():
+        d_o, m_o = uo.controlnet_forward(tiny['csd'][0], cfg, lat, 300, pe[:N], ci, 0.7)
+        d, m = tiny['cn'][0](lat, 300, pe[:N], ci, 0.7)
+        for a, b in zip(d, d_o):
+            assert rel(a.permute(0, 3, 1, 2), b)[0] <= 3e-2
+        assert rel(m.permute(0, 3, 1, 2), m_o)[0] <= 3e-2
+
+        pipe = Adapter3DMixin()
+        pipe.unet, pipe.controlnet = tiny['unet'], tiny['multi'](tiny['cn'])
+        # chunks of 2 as the pipeline builds them: [uncond..., cond...]
+        lb = list(lat.split(2)) * 2
+        pb = list(pe.split(2))
+        cib, cdb = list(ci.split(2)) * 2, list(cd.split(2)) * 2
+        ref = uo.get_noise_pred(tiny['usd'], tiny['csd'], cfg, lb, pb, cib, cdb, 300, 0.6, 0.4, 7.0)
+        out = pipe.get_noise_pred(lb, pb, cib, cdb, 300, 0.6, 0.4, 7.0)
+        assert out.shape == (N, 4, L, L)
+        r2, rmax = rel(out, ref)
+        assert r2 <= 4e-2, (r2, rmax)     # CFG (g=7) amplifies the cond-uncond difference error
+
+        ref1, da_o, dk_o = uo.get_noise_pred_p1(tiny['usd'], cfg, lb, pb, 300, 7.0)
+        out1, da, dk = pipe.get_noise_pred_p1(lb, pb, 300, 7.0)
+        assert rel(out1, ref1)[0] <= 4e-2
+        ref2 = uo.get_noise_pred_p2(tiny['usd'], tiny['csd'], cfg, lb, pb, da_o, dk_o, 300, 7.0, cib, 0.6, cdb, 0.4)
+        out2 = pipe.get_noise_pred_p2(lb, pb, da, dk, 300, 7.0, cib, 0.6, cdb, 0.4)
+        assert rel(out2, ref2)[0] <= 4e-2
+        # 1-pass == 2-pass second pass (same nets, same inputs) in the oracle; ours must agree with itself too
+        assert rel(out2, out)[0] <= 3e-2
+
+
+def test_reference_image_mode(tiny):
+    """latents (N,4,2L,L) = ref||view on the cond half only (mvedit_3d_pipeline.py:1227-1228): joint attention over the pair."""
+    from mvedit_b200.adapter3d_mixin import Adapter3DMixin
+    cfg = tiny['cfg']
+    g = torch.Generator(device='cuda').manual_seed(2)
+    N, L = 2, 16
+    lat_u = torch.randn(N, 4, L, L, device='cuda', generator=g)
+    lat_c = torch.randn(N, 4, 2 * L, L, device='cuda', generator=g)
+    pe = torch.randn(2 * N, 77, cfg.cross_attention_dim, device='cuda', generator=g)
+    ci = torch.rand(N, 3, 8 * L, 8 * L, device='cuda', generator=g)
+    cd = torch.rand(N, 3, 8 * L, 8 * L, device='cuda', generator=g)
+    pipe = Adapter3DMixin()
+    pipe.unet, pipe.controlnet = tiny['unet'], tiny['multi'](tiny['cn'])
+    with torch.no_grad():
+        ref = uo.get_noise_pred(tiny['usd'], tiny['csd'], cfg, [lat_u, lat_c], list(pe.split(N)), [ci, ci], [cd, cd], 700, 0.5, 0.5, 5.0)
+        out = pipe.get_noise_pred([lat_u, lat_c], list(pe.split(N)), [ci, ci], [cd, cd], 700, 0.5, 0.5, 5.0)
+    assert out.shape == (N, 4, L, L)
+    assert rel(out, ref)[0] <= 4e-2
+
+
+def test_unet_sd15_shapes_one_image():
+    """Full SD-1.5 widths (320/640/1280, head dim 40/80/160) at latent 32 on 2 images vs the fp32 oracle."""
+    from mvedit_b200.unet import UNet
+    cfg = uo.SD15
+    usd = uo.random_unet_state_dict(cfg, 0)
+    unet = UNet(usd, cfg)
+    usd_g = _to(usd, 'cuda')
+    g = torch.Generator(device='cuda').manual_seed(3)
+    x = torch.randn(2, 4, 32, 32, device='cuda', generator=g)
+    ctx = torch.randn(2, 77, 768, device='cuda', generator=g)
+    with torch.no_grad():
+        ref = uo.unet_forward(usd_g, cfg, x, 981, ctx)
+        out = unet(x, 981, ctx)
+    r2, rmax = rel(out, ref)
+    assert r2 <= 3e-2 and rmax <= 8e-2, (r2, rmax)
