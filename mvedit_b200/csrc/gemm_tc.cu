@@ -342,7 +342,7 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32
     uint32_t BH = 128 / BW;
     if (BH > H) BH = H;
     const uint32_t BB = 128 / (BW * BH);
-    MVE_ARG(BW * BH * BB == 128 && (H % BH) == 0 && (Bn % BB) == 0, "conv3x3: 128-pixel tile must cover whole rows / images");
+    MVE_ARG(BW * BH * BB == 128 && (H % BH) == 0 && BB <= 256, "conv3x3: 128-pixel tile must cover whole rows / images");
     const uint32_t M = Bn * H * W;
     const int bn = pick_bn(Cout);
     CUtensorMap tmA, tmB;
@@ -361,7 +361,7 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32
     }
     GemmParams p{};
     p.C = (__nv_bfloat16*)Y; p.M = M; p.N = Cout; p.ldc = ldy; p.num_kb = 9 * (Cin / BK);
-    p.m_tiles = M / BM; p.n_tiles = (Cout + bn - 1) / bn;
+    p.m_tiles = (M + BM - 1) / BM; p.n_tiles = (Cout + bn - 1) / bn;   // a last partial tile reads zero-filled images (TMA OOB)
     p.bias = bias; p.row_bias = row_bias; p.rows_per_group = H * W; p.ldrb = ldrb ? ldrb : Cout;
     p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act; p.alpha = alpha;
     p.H = H; p.W = W; p.cin_chunks = Cin / BK;
