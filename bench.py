@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 hot path (contract: see the task statement / DESIGN.md §Measurement).
+
+metric   : denoise + 3D-adapter steps/sec @ 32 x 512^2 views  (BASELINE.json; one "step" = one iteration of the loop at
+           /root/reference/lib/pipelines/mvedit_3d_pipeline.py:1141 with t != None)
+workload : BASELINE.json configs[1]: 32-view 512^2 SD1.5 + ControlNet tile+depth, text-to-3D recipe ('2-pass'), NeRF adapter,
+           CFG (64 UNet images per pass), 96 recon iterations x 16 384 rays, render 32 x 512^2, random-init weights, synthetic rig.
+           VAE decode / TRACER / LPIPS are neighbours of the path and are NOT in the step: the decoded targets are
+           synthetic images handed in by a hook (stated in "config").
+
+python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+Under torchrun (N > 1) one rank per GPU; views shard across ranks (strong scaling: 32 views in total).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_VIEWS, LATENT, IMG, T_TOKENS = 32, 64, 512, 77
+N_INVERSE_STEPS, N_INVERSE_RAYS, GRID = 96, 2 ** 14, 128
+METRIC = 'denoise+3D-adapter steps/sec @32x512^2 views'
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sustained=d['bf16_tflops_sustained'], src='measured')
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------------------- synthetic workload
+def make_rig(device):
+    from tests import synth
+    poses = torch.from_numpy(synth.surround_poses(N_VIEWS, seed=0)).to(device)
+    f = 0.5 * IMG / math.tan(math.radians(15))
+    K = torch.tensor([[f, f, IMG / 2, IMG / 2]] * N_VIEWS, device=device)
+    return poses, K
+
+
+def synth_targets(poses, K, size, device):
+    """Analytic multi-view targets (textured sphere, white background): stands in for vae.decode(pred_x0) + TRACER masks."""
+    from mvedit_b200.nerf import get_ray_directions, get_rays
+    d = get_ray_directions(size, size, K[None], device=device)
+    ro, rd = get_rays(d, poses[None], norm=True)
+    b = (ro * rd).sum(-1)
+    disc = b * b - ((ro * ro).sum(-1) - 0.25)
+    hit = disc > 0
+    p = ro + (-b - disc.clamp(min=0).sqrt())[..., None] * rd
+    col = 0.5 + 0.5 * torch.sin(p * 6)
+    img = torch.where(hit[..., None], col, torch.ones_like(col))
+    return img[0].contiguous(), hit[0][..., None].float().contiguous()
+
+
+def build(device, rank, world):
+    from mvedit_b200 import unet_config as uc
+    from mvedit_b200.unet import UNet, ControlNet, MultiControlNet
+    from mvedit_b200.nerf import BaseNeRF
+    from mvedit_b200.ingp_decoder import iNGPDecoder
+    from mvedit_b200.pipeline import MVEdit3DStep, EulerAncestralScheduler
+    cfg = uc.SD15
+    unet = UNet(uc.random_unet_state_dict(cfg, 0, device), cfg, device)
+    cns = [ControlNet(uc.random_controlnet_state_dict(cfg, 1, device), cfg, device),
+           ControlNet(uc.random_controlnet_state_dict(cfg, 2, device), cfg, device)]
+    torch.manual_seed(0)
+    nerf = BaseNeRF(grid_size=GRID, decoder=iNGPDecoder(max_resolution=320, n_levels=12, max_steps=1024, weight_culling_th=0.001),
+                    patch_size=128).to(device)
+    sch = EulerAncestralScheduler()
+    sch.set_timesteps(24, device=device)
+    pipe = MVEdit3DStep(unet, MultiControlNet(cns), nerf, sch)
+    return pipe
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback exists)'
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    from mvedit_b200 import view_shard, _lib
+    pipe = build(device, rank, world)
+    poses, K = make_rig(device)
+    lo, hi = view_shard.local_range(N_VIEWS)
+    n_local = hi - lo
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    tgt_img, tgt_msk = synth_targets(poses, K, IMG, device)                 # all views, device resident
+    tgt_img_h, tgt_msk_h = tgt_img[lo:hi].cpu().pin_memory(), tgt_msk[lo:hi].cpu().pin_memory()
+    lat0 = torch.randn(n_local, 4, LATENT, LATENT, device=device, generator=g) * pipe.scheduler.init_noise_sigma
+    pe = torch.randn(2 * n_local, T_TOKENS, 768, device=device, generator=g).to(torch.bfloat16)
+    lat_h, pe_h = lat0.cpu().pin_memory(), pe.cpu().pin_memory()
+    noise = torch.randn(n_local, 4, LATENT, LATENT, device=device, generator=g)
+    grid = pipe.nerf.get_init_density_grid(1, device)
+    bitfield = pipe.nerf.get_init_density_bitfield(1, device)
+    opt = torch.optim.Adam(pipe.nerf.decoder.parameters(), lr=0.01)
+    cam_w = torch.ones(N_VIEWS, device=device)
+    lights = torch.nn.functional.normalize(torch.randn(N_VIEWS, 3, device=device, generator=g), dim=-1)
+    out_h = torch.empty(n_local, 4, LATENT, LATENT).pin_memory()
+    step_i = 8    # a mid-schedule timestep
+
+    def decode_dev(pred_x0, lo_, hi_):
+        return tgt_img[lo_:hi_], tgt_msk[lo_:hi_]
+
+    def decode_h2d(pred_x0, lo_, hi_):
+        return tgt_img_h.to(device, non_blocking=True), tgt_msk_h.to(device, non_blocking=True)
+
+    kw = dict(density_grid=grid, density_bitfield=bitfield, optimizer=opt, camera_poses=poses, intrinsics=K, intrinsics_size=IMG,
+              cam_weights=cam_w, cam_lights=lights, ancestral_noise=noise, guidance_scale=7.0, render_size=IMG,
+              n_inverse_steps=N_INVERSE_STEPS, n_inverse_rays=N_INVERSE_RAYS)
+
+    def one_step(e2e):
+        if e2e:
+            lat = lat_h.to(device, non_blocking=True)
+            p = pe_h.to(device, non_blocking=True)
+            new, ci, cd = pipe.step(step_i, lat, p, decode_h2d, **kw)
+            out_h.copy_(new, non_blocking=True)
+        else:
+            new, ci, cd = pipe.step(step_i, lat0, pe, decode_dev, **kw)
+        return new
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # the very first NeRF fit from scratch (init) is not the timed step: bring the field to a fitted state first
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            one_step(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    with torch.no_grad():
+        _lib.LAUNCHES[0] = 0
+        ms = timed(lambda: one_step(False), args.steps)
+        launches = _lib.LAUNCHES[0]
+    clocks = sampler.stop() if rank == 0 else None
+    with torch.no_grad():
+        one_step(True)
+        ms_e2e = timed(lambda: one_step(True), args.steps)
+
+    # ---- roofline pass: per-launch CUDA events on the launching stream (one extra, untimed step)
+    prof = []
+    _lib.PROFILE[0] = prof
+    with torch.no_grad():
+        one_step(False)
+    torch.cuda.synchronize()
+    _lib.PROFILE[0] = None
+    cat = {}
+    for name, a, b, meta in prof:
+        c = cat.setdefault(name, dict(ms=0.0, n=0, flops=0.0))
+        c['ms'] += a.elapsed_time(b); c['n'] += 1; c['flops'] += (meta or {}).get('flops', 0.0)
+    pk = peaks()
+    tc_ms = cat.get('mve_gemm_bf16', dict(ms=0))['ms'] + cat.get('mve_conv3x3_bf16', dict(ms=0))['ms']
+    tc_fl = cat.get('mve_gemm_bf16', dict(flops=0))['flops'] + cat.get('mve_conv3x3_bf16', dict(flops=0))['flops']
+    tc_n = cat.get('mve_gemm_bf16', dict(n=0))['n'] + cat.get('mve_conv3x3_bf16', dict(n=0))['n']
+    achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    total_prof_ms = sum(c['ms'] for c in cat.values())
+    breakdown = {k: dict(ms=round(v['ms'], 3), launches=v['n'], tflops=round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1) if v['flops'] and v['ms'] else None)
+                 for k, v in sorted(cat.items(), key=lambda kv: -kv[1]['ms'])}
+
+    if rank != 0:
+        return
+    steps_per_s = args.steps / (ms * 1e-3)
+    e2e_steps_per_s = args.steps / (ms_e2e * 1e-3)
+    h2d = lat_h.numel() * 4 + pe_h.numel() * 2 + tgt_img_h.numel() * 4 + tgt_msk_h.numel() * 4
+    line = dict(
+        metric=METRIC, value=round(steps_per_s, 4), unit='steps/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=round(ms / args.steps, 2), higher_is_better=True, scaling='strong', vs_baseline=None, dtype='bf16', data='synthetic',
+        config=dict(workload='BASELINE configs[1]: 32-view 512^2 SD1.5 UNet + ControlNet tile+depth (2-pass, CFG: 64 UNet images/pass) '
+                             '+ NeRF adapter (96 iters x 16384 rays, 12-level hash grid) + render 32x512^2 + Euler-ancestral step',
+                    views=N_VIEWS, image=IMG, latent=LATENT, recon_iters=N_INVERSE_STEPS, rays_per_iter=N_INVERSE_RAYS,
+                    weights='random-init SD1.5 / ControlNet v1.1 shapes', parallelism='view-shard x%d, recon replicated + bcast' % world,
+                    neighbours_not_in_step='vae.decode/encode, TRACER masks, LPIPS patch loss (SURVEY.md §8f): targets are synthetic images',
+                    l2='per-step working set (168 MB per activation tensor, >5 GB live) >> 126 MB L2'),
+        e2e=dict(value=round(e2e_steps_per_s, 4), unit='steps/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(out_h.numel() * 4)),
+        gpu_launches=int(launches),
+        clocks=clocks,
+        roofline=dict(bound='tensor', kernel='k_gemm_tc (mve_gemm_bf16 + mve_conv3x3_bf16)', achieved=round(achieved, 1), peak=pk['tf_sustained'],
+                      unit='TFLOP/s', frac=round(achieved / pk['tf_sustained'], 4), traffic=None, peak_source=pk['src'] + ' (sustained)',
+                      launches_per_step=tc_n, share_of_step=round(tc_ms / total_prof_ms, 3) if total_prof_ms else None),
+        kernel_breakdown_ms=breakdown,
+    )
+    if world == 1:
+        line['raster_hbm'] = raymarch_microbench(device, pk)
+        line['cpu_baseline'] = cpu_baseline()
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------- config-5 microbench (HBM)
+def raymarch_microbench(device, pk):
+    """BASELINE config 5: 64-view 256^2 ray-march / composite fwd+bwd, algorithmic bytes / CUDA-event time."""
+    from tests import synth
+    from mvedit_b200 import raymarching as rm
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    H = 128
+    bf = rm.packbits(cu(synth.sphere_density_grid(H=H, radius=0.5)), 0.5)
+    ro, rd, f = synth.camera_rays(synth.surround_poses(64, seed=0), 256)
+    ro, rd = cu(ro), cu(rd)
+    N = ro.shape[0]
+    aabb = cu(np.array([-1, -1, -1, 1, 1, 1], np.float32))
+    nears, fars = rm.near_far_from_aabb(ro, rd, aabb, 0.2)
+    noises = torch.rand(N, device=device)
+    x, d, t, rays = rm.march_rays_train(ro, rd, 1.0, bf, 1, H, nears, fars, perturb=True, dt_gamma=1 / f, max_steps=1024, noises=noises)
+    M = x.shape[0]
+    sig, rgb = torch.exp(torch.randn(M, device=device)), torch.rand(M, 3, device=device)
+    from mvedit_b200._lib import call, ptr, stream, c_int, c_u32, c_f32
+    w, ws, dep, img = (torch.empty(M, device=device), torch.empty(N, device=device), torch.empty(N, device=device), torch.empty(N, 3, device=device))
+    gw, gws, gd, gi = torch.randn(M, device=device), torch.randn(N, device=device), torch.randn(N, device=device), torch.randn(N, 3, device=device)
+    gs, gc = torch.empty(M, device=device), torch.empty(M, 3, device=device)
+    xb, db, tb = torch.empty(M + 16, 3, device=device), torch.empty(M + 16, 3, device=device), torch.empty(M + 16, 2, device=device)
+    rays2, counter = torch.empty_like(rays), torch.zeros(1, dtype=torch.int32, device=device)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=device)
+
+    def t_of(fn, n=5):
+        ts = []
+        for _ in range(n + 1):
+            flush.zero_()                     # L2 flush between timed iterations
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts[1:]))
+
+    fwd = lambda: call('mve_composite_rays_train_forward', ptr(sig), ptr(rgb), ptr(t), ptr(rays), c_u32(M), ptr(None), c_u32(N), c_f32(1e-4),
+                       c_int(0), ptr(w), ptr(ws), ptr(dep), ptr(img), stream())
+    bwd = lambda: call('mve_composite_rays_train_backward', ptr(gw), ptr(gws), ptr(gd), ptr(gi), ptr(sig), ptr(rgb), ptr(t), ptr(rays), ptr(ws),
+                       ptr(dep), ptr(img), c_u32(M), ptr(None), c_u32(N), c_f32(1e-4), c_int(0), ptr(gs), ptr(gc), stream())
+
+    def march():
+        counter.zero_()
+        call('mve_march_rays_train', ptr(ro), ptr(rd), ptr(bf), c_f32(1.0), c_int(0), c_f32(1 / f), c_u32(1024), c_u32(N), c_u32(1), c_u32(H),
+             ptr(nears), ptr(fars), ptr(noises), ptr(xb), ptr(db), ptr(tb), c_u32(M + 16), ptr(rays2), ptr(counter), stream())
+
+    fwd()
+    tf, tbw, tm = t_of(fwd), t_of(bwd), t_of(march)
+    gb = lambda bytes_, ms: round(bytes_ / ms / 1e6, 1)
+    out = dict(workload='BASELINE configs[4]: 64 views x 256^2 rays, 128^3 grid', rays=N, samples=M, l2='flushed (256 MB write) between iterations',
+               composite_fwd=dict(ms=round(tf, 3), gbs=gb(M * 28 + N * 28, tf)), composite_bwd=dict(ms=round(tbw, 3), gbs=gb(M * 44 + N * 48, tbw)),
+               march_fused=dict(ms=round(tm, 3), gbs=gb(M * 32 + N * 44, tm)), peak_gbs=pk['hbm_gbs'], peak_source=pk['src'])
+    for k in ('composite_fwd', 'composite_bwd', 'march_fused'):
+        out[k]['frac'] = round(out[k]['gbs'] / pk['hbm_gbs'], 3)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_baseline(as_line=False, args=None):
+    """The reference cannot run on CPU (raymarching.py:46-51 forces CUDA; tcnn / nvdiffrast are CUDA-only), so the CPU arm is the
+    ORACLE PORT (kind 'port') on the host cores, on a bounded sample of the same workload, extrapolated linearly:
+      UNet: 1 image through unet_enc + 2 x unet_dec and 2 ControlNets at latent 64 (x64 images per step),
+      recon: 1 iteration (16 384 rays: C march + composite, torch field fwd/bwd)           (x96 per step),
+      render: 1 view at 128^2 through the inference loop (x32 views x16 for 512^2)."""
+    from oracle import unet_oracle as uo, field_oracle as fo, raymarching_oracle as orc
+    from tests import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+    cfg = uo.SD15
+    g = torch.Generator().manual_seed(0)
+    usd, csd = uo.random_unet_state_dict(cfg, 0), uo.random_controlnet_state_dict(cfg, 1)
+    x = torch.randn(1, 4, LATENT, LATENT, generator=g)
+    ctx = torch.randn(1, T_TOKENS, 768, generator=g)
+    cond = torch.rand(1, 3, IMG, IMG, generator=g)
+    with torch.no_grad():
+        t0 = time.time()
+        emb, res, s = uo.unet_enc(usd, cfg, x, 500, ctx)
+        uo.unet_dec(usd, cfg, emb, res, s, ctx)
+        down, mid = uo.controlnet_forward(csd, cfg, x, 500, ctx, cond, 1.0)
+        d2, m2 = uo.controlnet_forward(csd, cfg, x, 500, ctx, cond, 1.0)
+        uo.unet_dec(usd, cfg, emb, res, s, ctx, None, [a + b for a, b in zip(down, d2)], mid + m2)
+        t_unet_img = time.time() - t0
+    # recon iteration
+    levels, n_entries = fo.level_table(12, 16, 320)
+    params = [p.requires_grad_(True) for p in fo.init_params(levels, n_entries, table_scale=0.3)]
+    H = GRID
+    bitfield = orc.packbits(synth.sphere_density_grid(H=H, radius=0.5), 0.5)
+    poses = synth.surround_poses(4, seed=0)
+    ro, rd, f = synth.camera_rays(poses[:1], 128)
+    aabb = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    t0 = time.time()
+    nears, fars = orc.near_far_from_aabb(ro, rd, aabb, 0.2)
+    xs, _, ts, rays = orc.march_rays_train(ro, rd, 1.0, bitfield, 1, H, nears, fars, np.random.default_rng(0).random(ro.shape[0]).astype(np.float32),
+                                           dt_gamma=1 / f, max_steps=1024)
+    sig, rgb = fo.point_decode(torch.from_numpy(xs), *params, levels)
+    w, ws, dep, img = orc.composite_rays_train_forward(sig.detach().numpy(), rgb.detach().numpy(), ts, rays)
+    N = ro.shape[0]
+    gs, gc = orc.composite_rays_train_backward(np.zeros_like(w), np.ones(N, np.float32), np.ones(N, np.float32), np.ones((N, 3), np.float32),
+                                               sig.detach().numpy(), rgb.detach().numpy(), ts, rays, ws, dep, img)
+    torch.autograd.backward([sig, rgb], [torch.from_numpy(gs), torch.from_numpy(gc)])
+    t_recon_iter = time.time() - t0
+    # render one 128^2 view
+    t0 = time.time()
+    ws_, d_, im_ = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
+    alive, rt = np.arange(N, dtype=np.int32), nears.copy()
+    st = 0
+    with torch.no_grad():
+        while st < 1024 and alive.size:
+            n_alive = alive.size
+            n_step = min(max(N // n_alive, 1), 8)
+            xi, _, ti = orc.march_rays(n_alive, n_step, alive, rt, ro, rd, 1.0, bitfield, 1, H, nears, fars, None, dt_gamma=0.25 / f, max_steps=1024)
+            s_, c_ = fo.point_decode(torch.from_numpy(xi), *[p.detach() for p in params], levels)
+            orc.composite_rays(n_alive, n_step, alive, rt, s_.numpy(), c_.numpy(), ti, ws_, d_, im_, T_thresh=1e-2)
+            alive = np.ascontiguousarray(alive[alive >= 0])
+            st += n_step
+    t_render_view128 = time.time() - t0
+    step_s = 2 * N_VIEWS * t_unet_img + N_INVERSE_STEPS * t_recon_iter + N_VIEWS * 16 * t_render_view128
+    out = dict(value=round(1.0 / step_s, 6), unit='steps/s', cores=cores, kind='port',
+               sample='oracle port on host cores: 1 image of (unet_enc + 2x unet_dec + 2 ControlNets) @latent 64 = %.1f s (x64/step); '
+                      '1 recon iteration of 16384 rays = %.2f s (x96/step); 1 view 128^2 inference render = %.2f s (x32x16/step); '
+                      'extrapolated step = %.0f s' % (t_unet_img, t_recon_iter, t_render_view128, step_s))
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cb = cpu_baseline()
+    line = dict(impl='reference', metric=METRIC, value=cb['value'], unit='steps/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=round(1e3 / cb['value'], 1), higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload='BASELINE configs[1] (bounded sample, extrapolated; see cpu_baseline.sample)', views=N_VIEWS, image=IMG),
+                cpu_baseline=cb, e2e=dict(value=cb['value'], unit='steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

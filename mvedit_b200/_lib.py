@@ -57,6 +57,21 @@ def check(code, name):
         raise RuntimeError('%s failed (%d): %s' % (name, code, get_lib().mve_last_error().decode()))
 
 
-def call(name, *args):
+# kernels launched per C-ABI call (memsets not counted); used for the bench's "gpu_launches" claim
+KERNELS_PER_CALL = {'mve_groupnorm_bf16': 2, 'mve_field_backward': 2, 'mve_density_grid_update': 2}
+LAUNCHES = [0]
+PROFILE = [None]      # set to a list to record (name, start_event, end_event, meta) per call (bench.py roofline pass)
+
+
+def call(name, *args, _meta=None):
     fn = getattr(get_lib(), name)
+    LAUNCHES[0] += KERNELS_PER_CALL.get(name, 1)
+    prof = PROFILE[0]
+    if prof is None:
+        check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(fn(*args), name)
+    e1.record()
+    prof.append((name, e0, e1, _meta))

@@ -28,7 +28,8 @@ def gemm(a, w, bias=None, row_bias=None, rows_per_group=0, residual=None, act=No
     call('mve_gemm_bf16', raw_ptr(a), raw_ptr(w), raw_ptr(out), c_u32(M), c_u32(N), c_u32(K), c_u32(a.stride(0)), c_u32(w.stride(0)),
          c_u32(out.stride(0)), ptr(bias), raw_ptr(row_bias), c_u32(rows_per_group),
          c_u32(row_bias.stride(0) if row_bias is not None else 0), raw_ptr(residual),
-         c_u32(residual.stride(0) if residual is not None else 0), c_int(ACT[act]), c_f32(alpha), stream())
+         c_u32(residual.stride(0) if residual is not None else 0), c_int(ACT[act]), c_f32(alpha), stream(),
+         _meta=dict(flops=2.0 * M * N * K))
     return out
 
 
@@ -44,7 +45,7 @@ def conv3x3(x, w, bias=None, row_bias=None, residual=None, act=None, alpha=1.0, 
     call('mve_conv3x3_bf16', ptr(x), ptr(w), ptr(out), c_u32(B), c_u32(H), c_u32(W), c_u32(Cin), c_u32(Cout), c_u32(out.stride(2)),
          ptr(bias), raw_ptr(row_bias), c_u32(row_bias.stride(0) if row_bias is not None else 0), ptr(residual),
          c_u32(residual.stride(2) if residual is not None else 0), c_int(ACT[act]),
-         c_f32(alpha), stream())
+         c_f32(alpha), stream(), _meta=dict(flops=2.0 * B * H * W * Cout * 9 * Cin))
     return out
 
 
@@ -59,7 +60,7 @@ def attention(q, k, v, heads, scale=None, out=None):
         out = torch.empty(B, Sq, C, dtype=torch.bfloat16, device=q.device)
     call('mve_attention_bf16', raw_ptr(q), raw_ptr(k), raw_ptr(v), ptr(out), c_u32(B), c_u32(heads), c_u32(Sq), c_u32(Skv), c_u32(d),
          c_u32(q.stride(1)), c_u32(k.stride(1)), c_u32(v.stride(1)), c_u32(out.stride(1)), c_f32(scale if scale is not None else d ** -0.5),
-         stream())
+         stream(), _meta=dict(flops=4.0 * B * heads * Sq * Skv * d))
     return out
 
 

@@ -45,7 +45,7 @@ class _Weights:
             w = self.sd[name + '.weight']                      # [Cout, Cin, 3, 3]
             cout, cin = w.shape[:2]
             cp = _pad64(cin) if cin_pad is None else cin_pad
-            wp = torch.zeros(cout, 3, 3, cp, dtype=torch.float32)
+            wp = torch.zeros(cout, 3, 3, cp, dtype=torch.float32, device=w.device)
             wp[..., :cin] = w.float().permute(0, 2, 3, 1)
             self.conv3[name] = (_bf(wp, self.dev), _f32(self.sd[name + '.bias'], self.dev))
         return self.conv3[name]
@@ -282,7 +282,7 @@ class ControlNet(_Net):
             key = name + '.__s2__'
             if key not in w.lin:
                 wt = w.sd[name + '.weight']
-                wp = torch.zeros(wt.shape[0], 3, 3, cp)
+                wp = torch.zeros(wt.shape[0], 3, 3, cp, device=wt.device)
                 wp[..., :cin] = wt.float().permute(0, 2, 3, 1)
                 w.lin[key] = (_bf(wp.reshape(wt.shape[0], -1), self.device), _f32(w.sd[name + '.bias'], self.device))
             wd, bd = w.lin[key]
