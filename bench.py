@@ -147,7 +147,9 @@ def run_ours(args):
     noise = torch.randn(n_local, 4, LATENT, LATENT, device=device, generator=g)
     grid = pipe.nerf.get_init_density_grid(1, device)
     bitfield = pipe.nerf.get_init_density_bitfield(1, device)
-    opt = torch.optim.Adam(pipe.nerf.decoder.parameters(), lr=0.01)
+    pipe.nerf.decoder.sample_capacity = N_INVERSE_RAYS * 160      # 2.6 M samples: sync-free training forward
+    pipe.nerf.use_cuda_graph = not args.no_graph
+    opt = torch.optim.Adam(pipe.nerf.decoder.parameters(), lr=0.01, capturable=not args.no_graph)
     cam_w = torch.ones(N_VIEWS, device=device)
     lights = torch.nn.functional.normalize(torch.randn(N_VIEWS, 3, device=device, generator=g), dim=-1)
     out_h = torch.empty(n_local, 4, LATENT, LATENT).pin_memory()
@@ -297,7 +299,7 @@ def raymarch_microbench(device, pk):
     def march():
         counter.zero_()
         call('mve_march_rays_train', ptr(ro), ptr(rd), ptr(bf), c_f32(1.0), c_int(0), c_f32(1 / f), c_u32(1024), c_u32(N), c_u32(1), c_u32(H),
-             ptr(nears), ptr(fars), ptr(noises), ptr(xb), ptr(db), ptr(tb), c_u32(M + 16), ptr(rays2), ptr(counter), stream())
+             ptr(nears), ptr(fars), ptr(noises), ptr(xb), ptr(db), ptr(tb), c_u32(M + 16), ptr(rays2), ptr(counter), ptr(None), stream())
 
     fwd()
     tf, tbw, tm = t_of(fwd), t_of(bwd), t_of(march)
@@ -319,7 +321,7 @@ def cpu_baseline(as_line=False, args=None):
       render: 1 view at 128^2 through the inference loop (x32 views x16 for 512^2)."""
     from oracle import unet_oracle as uo, field_oracle as fo, raymarching_oracle as orc
     from tests import synth
-    cores = os.cpu_count() or 1
+    cores = min(len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1), 32)
     torch.set_num_threads(cores)
     os.environ.setdefault('OMP_NUM_THREADS', str(cores))
     cfg = uo.SD15
@@ -396,6 +398,7 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-graph', action='store_true', help='run the recon iterations eagerly instead of as CUDA graphs')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

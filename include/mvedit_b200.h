@@ -55,13 +55,14 @@ int mve_packbits(const void* grid, int grid_is_half, uint32_t N, float density_t
  * the total M afterwards.  Samples of a ray are contiguous; rays[n] = (offset, count).  Rays whose
  * samples would not fit in max_M keep their (offset,count) but write nothing (composite treats
  * offset+count > M as an empty ray, raymarching.cu:523).  If xyzs == NULL only rays/counter are written
- * (the reference's first pass).  noises [N] f32 may be NULL (= zeros, perturb=False). */
+ * (the reference's first pass).  noises [N] f32 may be NULL (= zeros, perturb=False).
+ * dt_gamma_dev (optional, device, 1 float) overrides dt_gamma so a captured CUDA graph can change it between replays. */
 int mve_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* density_bitfield,
                          float bound, int contract, float dt_gamma, uint32_t max_steps,
                          uint32_t N, uint32_t C, uint32_t H,
                          const float* nears, const float* fars, const float* noises,
                          float* xyzs, float* dirs, float* ts, uint32_t max_M,
-                         int32_t* rays, int32_t* counter, void* stream);
+                         int32_t* rays, int32_t* counter, const float* dt_gamma_dev, void* stream);
 /* second pass of the reference protocol: rays[n] already holds (offset,count); write the samples. */
 int mve_march_rays_train_write(const float* rays_o, const float* rays_d, const uint8_t* density_bitfield,
                                float bound, int contract, float dt_gamma, uint32_t max_steps,
@@ -71,10 +72,10 @@ int mve_march_rays_train_write(const float* rays_o, const float* rays_d, const u
                                const int32_t* rays, void* stream);
 
 /* raymarching.h:16 composite_rays_train_forward ; kernel raymarching.cu:501-579.
- * M may also be given on the device: if M_dev != NULL the kernel reads *M_dev instead of M
- * (lets the caller skip the host sync after mve_march_rays_train).
+ * M may also be given on the device: if M_dev != NULL the kernel uses min(M, *M_dev)
+ * (lets the caller skip the host sync after mve_march_rays_train; M is then the buffer capacity).
  * weights [M] is fully written for every sample covered by a ray (zeros after early termination),
- * so the caller need not pre-zero it. */
+ * so the caller need not pre-zero it.  rgbs may be NULL (weights / weights_sum / depth only: the culling pre-pass). */
 int mve_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* ts, const int32_t* rays,
                                      uint32_t M, const int32_t* M_dev, uint32_t N, float T_thresh, int binarize,
                                      float* weights, float* weights_sum, float* depth, float* image, void* stream);

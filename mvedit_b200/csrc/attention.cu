@@ -260,6 +260,244 @@ __global__ void __launch_bounds__(NUM_THREADS_A, 1) k_attention(const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Ping-pong variant for head dims <= 64 (one 64-wide atom): one CTA owns TWO 128-row query tiles (A, B) of the same (batch, head).
+// 10 warps: 0-3 softmax A, 4-7 softmax B, 8 MMA issuer, 9 TMA producer.  While the softmax warps of tile A work on S_A(j), the tensor
+// core runs Q_B K_j^T / P_B V_j and vice versa, so softmax (MUFU / FMA pipes) and MMA overlap inside one SM, and every K/V tile
+// fetched by TMA is used by both query tiles.  TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int DPAD>
+__global__ void __launch_bounds__(320, 1) k_attention_pp(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                         const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+    static_assert(DPAD <= 64, "ping-pong kernel: one 64-wide head-dim atom");
+    constexpr int ST = 2;
+    constexpr uint32_t O_COL0 = 256, O_COL1 = 320;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;                          // [2][ATOM]
+    uint8_t* sK = sQ + 2 * ATOM_BYTES;           // [ST][ATOM]
+    uint8_t* sV = sK + ST * ATOM_BYTES;          // [ST][ATOM]
+    uint8_t* sP = sV + ST * ATOM_BYTES;          // [2][2*ATOM]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATOM_BYTES);
+    uint64_t* bar_q = bars;               // 1
+    uint64_t* kv_full = bars + 1;         // [2]
+    uint64_t* kv_empty = bars + 3;        // [2]
+    uint64_t* s_full = bars + 5;          // [2 tiles]
+    uint64_t* p_full = bars + 7;          // [2 tiles], 128 arrivals
+    uint64_t* pv_done = bars + 9;         // [2 tiles]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t qb = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+    const uint32_t nblk = p.n_kv_blocks;
+
+    if (warp == 9 && lane == 0) {
+        tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV);
+        tc::mbar_init(bar_q, 1);
+        for (int s = 0; s < 2; s++) {
+            tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1);
+            tc::mbar_init(&s_full[s], 1); tc::mbar_init(&p_full[s], 128); tc::mbar_init(&pv_done[s], 1);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 9) {
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(bar_q, 2 * ATOM_BYTES);
+            tc::tma_load_4d(sQ, &tmQ, bar_q, 0, head, qb * 256, batch);
+            tc::tma_load_4d(sQ + ATOM_BYTES, &tmQ, bar_q, 0, head, qb * 256 + 128, batch);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t j = 0; j < nblk; j++) {
+                tc::mbar_wait(&kv_empty[stage], phase ^ 1);
+                tc::mbar_arrive_expect_tx(&kv_full[stage], 2 * ATOM_BYTES);
+                tc::tma_load_4d(sK + stage * ATOM_BYTES, &tmK, &kv_full[stage], 0, head, j * BKV, batch);
+                tc::tma_load_4d(sV + stage * ATOM_BYTES, &tmV, &kv_full[stage], 0, head, j * BKV, batch);
+                if (++stage == ST) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = tc::make_idesc_bf16(128, BKV, false, false);
+            constexpr uint32_t idesc_pv = tc::make_idesc_bf16(128, DPAD, false, true);
+            const uint32_t aQ = tc::smem_u32(sQ), aP = tc::smem_u32(sP);
+            auto issue_qk = [&](uint32_t tile, uint32_t j) {
+                const uint32_t aK = tc::smem_u32(sK + (j % ST) * ATOM_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < DPAD / 16; kk++)
+                    tc::umma_f16(tmem_base + tile * 128, tc::make_desc_k_sw128(aQ + tile * ATOM_BYTES + kk * 32), tc::make_desc_k_sw128(aK + kk * 32),
+                                 idesc_qk, kk ? 1u : 0u);
+                tc::umma_commit(&s_full[tile]);
+            };
+            tc::mbar_wait(bar_q, 0);
+            tc::mbar_wait(&kv_full[0], 0);
+            tc::tc_fence_after();
+            issue_qk(0, 0);
+            issue_qk(1, 0);
+            for (uint32_t j = 0; j < nblk; j++) {
+                const uint32_t st = j % ST;
+                const uint32_t aV = tc::smem_u32(sV + st * ATOM_BYTES);
+#pragma unroll
+                for (uint32_t tile = 0; tile < 2; tile++) {
+                    tc::mbar_wait(&p_full[tile], j & 1);
+                    tc::tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < BKV / 16; kk++) {
+                        const uint64_t da = tc::make_desc_k_sw128(aP + tile * 2 * ATOM_BYTES + (kk / 4) * ATOM_BYTES + (kk % 4) * 32);
+                        const uint64_t db = tc::make_desc_mn_sw128(aV + kk * 2048, ATOM_BYTES, 1024);
+                        tc::umma_f16(tmem_base + (tile ? O_COL1 : O_COL0), da, db, idesc_pv, (j | kk) ? 1u : 0u);
+                    }
+                    if (tile == 1) tc::umma_commit(&kv_empty[st]);
+                    tc::umma_commit(&pv_done[tile]);
+                    if (j + 1 < nblk) {
+                        if (tile == 0) {
+                            tc::mbar_wait(&kv_full[(j + 1) % ST], ((j + 1) / ST) & 1);
+                            tc::tc_fence_after();
+                        }
+                        issue_qk(tile, j + 1);
+                    }
+                }
+            }
+        }
+    } else {
+        const uint32_t tile = warp >> 2;
+        const uint32_t row = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t s_addr = lane_addr + tile * 128;
+        const uint32_t o_addr = lane_addr + (tile ? O_COL1 : O_COL0);
+        float m = -INFINITY, l = 0.f;
+        uint8_t* prow = sP + tile * 2 * ATOM_BYTES + row * 128;
+        const uint32_t sw = row & 7;
+        for (uint32_t j = 0; j < nblk; j++) {
+            tc::mbar_wait(&s_full[tile], j & 1);
+            tc::tc_fence_after();
+            const uint32_t kv_valid = min((uint32_t)BKV, p.kv_len - j * BKV);
+            const bool full_blk = kv_valid == BKV;
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < BKV; c += 32) {
+                uint32_t v[32];
+                tc::tmem_ld32(s_addr + c, v);
+                tc::tmem_ld_wait();
+                if (full_blk) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(v[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        if ((uint32_t)(c + i) < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                }
+            }
+            const float m_new = fmaxf(m, mx * p.scale_log2);
+            const float alpha = ex2_approx(m - m_new);
+            if (j > 0) {
+                tc::mbar_wait(&pv_done[tile], (j - 1) & 1);
+                tc::tc_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+                    for (int c = 0; c < DPAD; c += 16) {
+                        uint32_t v[16];
+                        tc::tmem_ld16(o_addr + c, v);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                        tmem_st16(o_addr + c, v);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            float lsum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < BKV; c += 32) {
+                uint32_t v[32];
+                tc::tmem_ld32(s_addr + c, v);
+                tc::tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+                    float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_new));
+                    if (!full_blk) {
+                        if ((uint32_t)(c + i) >= kv_valid) p0 = 0.f;
+                        if ((uint32_t)(c + i + 1) >= kv_valid) p1 = 0.f;
+                    }
+                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+                    const float2 back = __bfloat1622float2(b2);
+                    lsum += back.x + back.y;
+                    pk[i / 2] = *reinterpret_cast<const uint32_t*>(&b2);
+                }
+                uint8_t* base = prow + (c / 64) * ATOM_BYTES;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t chunk = ((c % 64) / 8 + q) ^ sw;
+                    *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                }
+            }
+            l = l * alpha + lsum;
+            m = m_new;
+            tc::fence_proxy_async_smem();
+            tc::tc_fence_before();
+            tc::mbar_arrive(&p_full[tile]);
+        }
+        tc::mbar_wait(&pv_done[tile], (nblk - 1) & 1);
+        tc::tc_fence_after();
+        const uint32_t qrow = qb * 256 + tile * 128 + row;
+        const float inv_l = 1.0f / l;
+        __nv_bfloat16* out = p.O + ((size_t)batch * p.q_len + qrow) * p.ldo + head * p.d;
+#pragma unroll 1
+        for (int c = 0; c < DPAD; c += 16) {
+            uint32_t v[16];
+            tc::tmem_ld16(o_addr + c, v);
+            tc::tmem_ld_wait();
+            if (qrow < p.q_len) {
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    if ((uint32_t)(c + g * 8) < p.d) {
+                        uint4 o;
+                        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            o2[i] = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 2 * i]) * inv_l, __uint_as_float(v[g * 8 + 2 * i + 1]) * inv_l);
+                        *reinterpret_cast<uint4*>(out + c + g * 8) = o;
+                    }
+                }
+            }
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int DPAD>
+int launch_attn_pp(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, uint32_t heads, uint32_t batch,
+                   cudaStream_t s) {
+    constexpr int SMEM = ATOM_BYTES * (2 + 2 + 2 + 4) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        MVE_CUDA(cudaFuncSetAttribute(k_attention_pp<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
+    const dim3 grid((p.q_len + 255) / 256, heads, batch);
+    k_attention_pp<DPAD><<<grid, 320, SMEM, s>>>(tq, tk, tv, p);
+    MVE_CHECK_LAUNCH("k_attention_pp");
+    return 0;
+}
+
 template <int DPAD, int ST>
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid, cudaStream_t s) {
     constexpr int DA = (DPAD + 63) / 64;
@@ -304,8 +542,8 @@ int mve_attention_bf16(const void* Q, const void* K, const void* V, void* O, uin
     p.n_kv_blocks = (kv_len + BKV - 1) / BKV;
     const dim3 grid((q_len + BQ - 1) / BQ, heads, batch);
     cudaStream_t s = (cudaStream_t)stream;
-    if (d <= 48) return launch_attn<48, 2>(tq, tk, tv, p, grid, s);
-    if (d <= 64) return launch_attn<64, 2>(tq, tk, tv, p, grid, s);
+    if (d <= 48) return launch_attn_pp<48>(tq, tk, tv, p, heads, batch, s);
+    if (d <= 64) return launch_attn_pp<64>(tq, tk, tv, p, heads, batch, s);
     if (d <= 80) return launch_attn<80, 2>(tq, tk, tv, p, grid, s);
     if (d <= 128) return launch_attn<128, 2>(tq, tk, tv, p, grid, s);
     return launch_attn<160, 1>(tq, tk, tv, p, grid, s);

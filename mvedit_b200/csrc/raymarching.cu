@@ -117,8 +117,8 @@ __device__ __forceinline__ uint32_t march_one(const Ray& r, const MarchParams& p
 
 // Fused train marcher (raymarching.cu:338-475 + raymarching.py:286-300 in one launch).
 constexpr int MT_T = 128;
-__global__ void __launch_bounds__(MT_T) k_march_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const MarchParams p,
-                                                      const uint32_t max_steps, const uint32_t N, const float* __restrict__ nears,
+__global__ void __launch_bounds__(MT_T) k_march_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d, MarchParams p,
+                                                      const float* __restrict__ dt_gamma_dev, const uint32_t max_steps, const uint32_t N, const float* __restrict__ nears,
                                                       const float* __restrict__ fars, const float* __restrict__ noises,
                                                       float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ ts,
                                                       const uint32_t max_M, int* __restrict__ rays, int* __restrict__ counter) {
@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(MT_T) k_march_train(const float* __restrict__ 
     __shared__ uint32_t cta_base;
     const uint32_t n = threadIdx.x + blockIdx.x * MT_T;
     const bool live = n < N;
+    if (dt_gamma_dev) p.dt_gamma = dt_gamma_dev[0];
     Ray r;
     float near = 0, far = 0, noise = 0;
     uint32_t cnt = 0;
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(CP_T) k_composite_train_fwd(const float* __res
     if (n >= N) return;  // whole groups leave together
     const int lane = threadIdx.x & 31, gl = lane % G;
     const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - gl));
-    if (M_dev) M = (uint32_t)*M_dev;
+    if (M_dev) M = min(M, (uint32_t)*M_dev);
     const uint32_t offset = rays[n * 2], num_steps = rays[n * 2 + 1];
     if (num_steps == 0 || (uint64_t)offset + num_steps > M) {
         if (gl == 0) { weights_sum[n] = 0; depth[n] = 0; image[n * 3] = 0; image[n * 3 + 1] = 0; image[n * 3 + 2] = 0; }
@@ -237,7 +238,10 @@ __global__ void __launch_bounds__(CP_T) k_composite_train_fwd(const float* __res
         const bool valid = i < num_steps;
         float sigma = 0, cr = 0, cg = 0, cb = 0;
         float2 td = make_float2(1.0f, 0.0f);
-        if (valid) { sigma = sg[i]; td = tt[i]; cr = cl[i * 3]; cg = cl[i * 3 + 1]; cb = cl[i * 3 + 2]; }
+        if (valid) {
+            sigma = sg[i]; td = tt[i];
+            if (rgbs) { cr = cl[i * 3]; cg = cl[i * 3 + 1]; cb = cl[i * 3 + 2]; }   // rgbs == NULL: weights-only pass (culling)
+        }
         const float real_alpha = 1.0f - __expf(-sigma * td.y);
         const float alpha = valid ? (binarize ? (real_alpha > 0.5f ? 1.0f : 0.0f) : real_alpha) : 0.0f;
         const float pin = group_scan_mul<G>(1.0f - alpha, gmask, gl);      // inclusive product within the round
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(CP_T) k_composite_train_bwd(const float* __res
     if (n >= N) return;
     const int lane = threadIdx.x & 31, gl = lane % G;
     const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - gl));
-    if (M_dev) M = (uint32_t)*M_dev;
+    if (M_dev) M = min(M, (uint32_t)*M_dev);
     const uint32_t offset = rays[n * 2], num_steps = rays[n * 2 + 1];
     if (num_steps == 0 || (uint64_t)offset + num_steps > M) return;
 
@@ -444,11 +448,11 @@ int mve_packbits(const void* grid, int grid_is_half, uint32_t N, float density_t
 int mve_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* density_bitfield, float bound, int contract,
                          float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, const float* nears, const float* fars,
                          const float* noises, float* xyzs, float* dirs, float* ts, uint32_t max_M, int32_t* rays, int32_t* counter,
-                         void* stream) {
+                         const float* dt_gamma_dev, void* stream) {
     if (N == 0) return 0;
     MVE_ARG(max_steps > 0 && H > 0 && C > 0, "march_rays_train: max_steps, H, C must be positive");
     const MarchParams p = make_params(density_bitfield, bound, contract != 0, dt_gamma, max_steps, C, H);
-    k_march_train<<<cdiv(N, MT_T), MT_T, 0, (cudaStream_t)stream>>>(rays_o, rays_d, p, max_steps, N, nears, fars, noises, xyzs, dirs, ts,
+    k_march_train<<<cdiv(N, MT_T), MT_T, 0, (cudaStream_t)stream>>>(rays_o, rays_d, p, dt_gamma_dev, max_steps, N, nears, fars, noises, xyzs, dirs, ts,
                                                                      max_M, rays, counter);
     MVE_CHECK_LAUNCH("mve_march_rays_train");
     return 0;

@@ -53,47 +53,79 @@ struct RenderParams {
     const float* dt_gamma_per_view;  // [V] or null (then march.dt_gamma is used)
 };
 
+// Lane-level dynamic scheduling: a lane that finishes its ray immediately fetches the next one (chunks of RAY_CHUNK consecutive
+// rays per atomic), and the loop is split in two phases so the expensive part stays converged:
+//   phase 1 (divergent, cheap)   every lane advances its DDA / retires its ray / fetches a new ray until it holds ONE sample to shade
+//   phase 2 (converged, heavy)   all lanes that hold a sample run the 96 hash-grid gathers + MLP + compositing together
+// so empty-space rays and early-terminated rays never idle a warp while a neighbour shades hundreds of samples.
+constexpr int RAY_CHUNK = 8;
+
 template <int L>
 __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, MarchParams mp, const float2* __restrict__ table,
                                                      const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                                                     const float* __restrict__ b2, const Levels lv, const FieldCfg cfg) {
+                                                     const float* __restrict__ b2, const Levels lv, const FieldCfg cfg,
+                                                     unsigned int* __restrict__ next_ray) {
     using R = Rec<L>;
     __shared__ __align__(16) float rec[HID * R::STRIDE];
     stage_mlp<L>(rec, w1, b1, w2);
     __syncthreads();
     const float ob0 = b2[0], ob1 = b2[1], ob2 = b2[2], ob3 = b2[3];
-    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < rp.N; n += gridDim.x * blockDim.x) {
-        Ray r;
-        if (rp.rays_o) {
-            r = load_ray(rp.rays_o, rp.rays_d, n);
-        } else {
-            const uint32_t hw = rp.h * rp.w, v = n / hw, pix = n % hw;
-            const float pi = (float)(pix % rp.w) + 0.5f, pj = (float)(pix / rp.w) + 0.5f;
-            const float* K = rp.intrinsics + v * 4;
-            const float* P = rp.poses + v * 16;
-            const float cxd = (pi - K[2]) / K[0], cyd = (pj - K[3]) / K[1];
-            float dx = P[0] * cxd + P[1] * cyd + P[2], dy = P[4] * cxd + P[5] * cyd + P[6], dz = P[8] * cxd + P[9] * cyd + P[10];
-            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-            r.ox = P[3]; r.oy = P[7]; r.oz = P[11];
-            r.dx = dx * inv; r.dy = dy * inv; r.dz = dz * inv;
-            r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
-            if (rp.dt_gamma_per_view) mp.dt_gamma = rp.dt_gamma_per_view[v];
+
+    bool have_ray = false, exhausted = false;
+    uint32_t n = 0, cur = 0, chunk_left = 0, step = 0;
+    Ray r;
+    float t = 0.f, far = 0.f, ws = 0.f, dsum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+    bool terminated = false;
+    float cx = 0.f, cy = 0.f, cz = 0.f, dt = 0.f;
+
+    for (;;) {
+        bool has = false;
+        // ---------------- phase 1
+        while (!exhausted) {
+            if (!have_ray) {
+                if (chunk_left == 0) { cur = atomicAdd(next_ray, (unsigned int)RAY_CHUNK); chunk_left = RAY_CHUNK; }
+                if (cur >= rp.N) { exhausted = true; break; }
+                n = cur++; chunk_left--;
+                if (rp.rays_o) {
+                    r = load_ray(rp.rays_o, rp.rays_d, n);
+                } else {
+                    const uint32_t hw = rp.h * rp.w, v = n / hw, pix = n % hw;
+                    const float pi = (float)(pix % rp.w) + 0.5f, pj = (float)(pix / rp.w) + 0.5f;
+                    const float* K = rp.intrinsics + v * 4;
+                    const float* P = rp.poses + v * 16;
+                    const float cxd = (pi - K[2]) / K[0], cyd = (pj - K[3]) / K[1];
+                    const float dx = P[0] * cxd + P[1] * cyd + P[2], dy = P[4] * cxd + P[5] * cyd + P[6], dz = P[8] * cxd + P[9] * cyd + P[10];
+                    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+                    r.ox = P[3]; r.oy = P[7]; r.oz = P[11];
+                    r.dx = dx * inv; r.dy = dy * inv; r.dz = dz * inv;
+                    r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+                    if (rp.dt_gamma_per_view) mp.dt_gamma = rp.dt_gamma_per_view[v];
+                }
+                float near;
+                slab(r, rp.aabb, rp.min_near, near, far);
+                t = near;
+                ws = 0.f; dsum = 0.f; cr = 0.f; cg = 0.f; cb = 0.f; step = 0; terminated = false;
+                have_ray = true;
+            }
+            if (!terminated && t < far && step < rp.max_steps) {
+                if (dda_step(r, mp, t, cx, cy, cz, dt)) { has = true; break; }
+            } else {
+                rp.weights_sum[n] = ws;
+                rp.depth[n] = dsum;
+                rp.image[(size_t)n * 3] = cr; rp.image[(size_t)n * 3 + 1] = cg; rp.image[(size_t)n * 3 + 2] = cb;
+                have_ray = false;
+            }
         }
-        float near, far;
-        slab(r, rp.aabb, rp.min_near, near, far);
-        float t = near;
-        float ws = 0.f, dsum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
-        uint32_t step = 0;
-        float cx, cy, cz, dt;
-        while (t < far && step < rp.max_steps) {
-            if (!dda_step(r, mp, t, cx, cy, cz, dt)) continue;
+        if (!__any_sync(0xffffffffu, has)) break;
+        // ---------------- phase 2
+        if (has) {
             t += dt;
             float enc[R::IN];
             encode<L>(lv, table, (cx + cfg.bound) * cfg.inv2b, (cy + cfg.bound) * cfg.inv2b, (cz + cfg.bound) * cfg.inv2b, enc);
             float o0 = ob0, o1 = ob1, o2 = ob2, o3 = ob3;
             mlp_forward<L, false>(rec, enc, o0, o1, o2, o3);
             const float sigma = __expf(o0 + blob_of(cfg, cx, cy, cz));
-            // kernel_composite_rays (raymarching.cu:878-903): T = 1 - weight_sum, break after accumulating
+            // kernel_composite_rays (raymarching.cu:878-903): T = 1 - weight_sum, the ray dies after accumulating the sample
             const float alpha = 1.0f - __expf(-sigma * dt);
             const float T = 1 - ws;
             const float weight = alpha * T;
@@ -103,11 +135,8 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
             cg += weight * fmaf(1.f / (1.f + __expf(-o2)), cfg.sat_scale, cfg.sat_shift);
             cb += weight * fmaf(1.f / (1.f + __expf(-o3)), cfg.sat_scale, cfg.sat_shift);
             step++;
-            if (T < rp.T_thresh) break;
+            if (T < rp.T_thresh) terminated = true;
         }
-        rp.weights_sum[n] = ws;
-        rp.depth[n] = dsum;
-        rp.image[(size_t)n * 3] = cr; rp.image[(size_t)n * 3 + 1] = cg; rp.image[(size_t)n * 3 + 2] = cb;
     }
 }
 
@@ -123,7 +152,7 @@ __global__ void __launch_bounds__(CC_T) k_cull_compact(const float* __restrict__
     __shared__ uint32_t s_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n = blockIdx.x * (CC_T / 32) + warp;
-    if (M_dev) M = (uint32_t)*M_dev;
+    if (M_dev) M = min(M, (uint32_t)*M_dev);
     uint32_t offset = 0, num = 0;
     if (n < N) {
         offset = rays_in[n * 2]; num = rays_in[n * 2 + 1];
@@ -217,13 +246,16 @@ int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses
     rp.rays_o = rays_o; rp.rays_d = rays_d; rp.poses = poses; rp.intrinsics = intrinsics; rp.h = h; rp.w = w; rp.N = N; rp.aabb = aabb;
     rp.min_near = min_near; rp.T_thresh = T_thresh; rp.max_steps = max_steps; rp.weights_sum = weights_sum; rp.depth = depth;
     rp.image = image; rp.dt_gamma_per_view = dt_gamma_per_view;
-    uint32_t grid = cdiv(N, 128);
-    if (grid > (uint32_t)(16 * kNumSM)) grid = 16 * kNumSM;
+    uint32_t grid = cdiv(N, 128 * RAY_CHUNK);
+    if (grid > (uint32_t)(8 * kNumSM)) grid = 8 * kNumSM;
     const float2* t2 = reinterpret_cast<const float2*>(table);
     cudaStream_t s = (cudaStream_t)stream;
-    if (n_levels == 12) k_render_rays<12><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg);
-    else if (n_levels == 14) k_render_rays<14><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg);
-    else k_render_rays<16><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg);
+    static unsigned int* next_ray = nullptr;   // one process drives one GPU: a process-wide work counter is enough
+    if (!next_ray) MVE_CUDA(cudaMalloc(&next_ray, sizeof(unsigned int)));
+    MVE_CUDA(cudaMemsetAsync(next_ray, 0, sizeof(unsigned int), s));
+    if (n_levels == 12) k_render_rays<12><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray);
+    else if (n_levels == 14) k_render_rays<14><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray);
+    else k_render_rays<16><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray);
     MVE_CHECK_LAUNCH("mve_render_rays");
     return 0;
 }

@@ -79,18 +79,20 @@ class _FieldFn(Function):
     """Fused point_decode: (xyz, table, w1, b1, w2, b2) -> (sigma, rgb)."""
 
     @staticmethod
-    def forward(ctx, xyz, table, w1, b1, w2, b2, dec, density_only):
+    def forward(ctx, xyz, table, w1, b1, w2, b2, dec, density_only, m_dev=None):
         xyz = xyz.float().contiguous()
         M = xyz.shape[0]
-        sigma = torch.empty(M, dtype=torch.float32, device=xyz.device)
-        rgb = None if density_only else torch.empty(M, 3, dtype=torch.float32, device=xyz.device)
+        alloc = torch.empty if m_dev is None else torch.zeros      # capacity buffers: the tail past *m_dev must read as 0
+        sigma = alloc(M, dtype=torch.float32, device=xyz.device)
+        rgb = None if density_only else alloc(M, 3, dtype=torch.float32, device=xyz.device)
         if M > 0:
-            call('mve_field_forward', ptr(xyz), c_u32(M), ptr(None), ptr(table), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
+            call('mve_field_forward', ptr(xyz), c_u32(M), ptr(m_dev), ptr(table), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
                  *dec.encoder._largs.args(), c_f32(dec.bound), c_f32(dec.blob_density), c_f32(dec.blob_radius),
                  c_f32(dec.sigmoid_saturation), c_int(int(density_only)), ptr(sigma), ptr(rgb), stream())
         ctx.save_for_backward(xyz, table, w1, b1, w2, b2)
         ctx.dec = dec
         ctx.density_only = density_only
+        ctx.m_dev = m_dev
         if density_only:
             empty = sigma.new_zeros(0)
             ctx.mark_non_differentiable(empty)
@@ -109,11 +111,11 @@ class _FieldFn(Function):
         ws = dec._workspace(xyz.device)
         g_sigma = g_sigma.float().contiguous()
         g_rgb = None if (ctx.density_only or g_rgb is None) else g_rgb.float().contiguous()
-        call('mve_field_backward', ptr(xyz), c_u32(M), ptr(None), ptr(table), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
+        call('mve_field_backward', ptr(xyz), c_u32(M), ptr(ctx.m_dev), ptr(table), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
              *dec.encoder._largs.args(), c_f32(dec.bound), c_f32(dec.blob_density), c_f32(dec.blob_radius),
              c_f32(dec.sigmoid_saturation), ptr(g_sigma), ptr(g_rgb), ptr(g_table), ptr(g_w1), ptr(g_b1), ptr(g_w2), ptr(g_b2),
              c_int(0), ptr(ws), ptr(g_xyz), stream())
-        return g_xyz, g_table, g_w1, g_b1, g_w2, g_b2, None, None
+        return g_xyz, g_table, g_w1, g_b1, g_w2, g_b2, None, None, None
 
 
 class iNGPDecoder(nn.Module):
@@ -138,6 +140,7 @@ class iNGPDecoder(nn.Module):
         self.blob_density = blob_density
         self.blob_radius = blob_radius
         self.state_dict_bak = None
+        self.sample_capacity = 0      # > 0: sync-free training forward with capacity-sized sample buffers
         self._ws = None
         self._grid_cache = {}
         self.init_weights()
@@ -180,11 +183,11 @@ class iNGPDecoder(nn.Module):
         d = (x ** 2).sum(-1).clamp(min=0.2)
         return self.blob_density * torch.exp(-d / (2 * self.blob_radius ** 2))
 
-    def point_decode(self, xyzs, dirs, code, density_only=False, use_2nd_order=False):
+    def point_decode(self, xyzs, dirs, code, density_only=False, use_2nd_order=False, m_dev=None):
         """ingp_decoder.py:106-120.  xyzs: list with one [M,3] tensor (or a [1,M,3] tensor)."""
         assert len(xyzs) == 1, "Multiple scenes not implemented"
         assert not use_2nd_order
-        sigmas, rgbs = _FieldFn.apply(xyzs[0], *self._field_params(), self, density_only)
+        sigmas, rgbs = _FieldFn.apply(xyzs[0], *self._field_params(), self, density_only, m_dev)
         return sigmas, (None if density_only else rgbs), [len(xyzs[0])]
 
     def point_density_decode(self, xyzs, code, **kwargs):
@@ -239,13 +242,44 @@ class iNGPDecoder(nn.Module):
         assert num_scenes == 1, 'Multiple scenes not implemented (as ingp_decoder.py:110)'
         if isinstance(grid_size, (list, tuple)):
             grid_size = grid_size[0]
+        dt_gamma_t = None
         if isinstance(dt_gamma, torch.Tensor):
-            dt_gamma = float(dt_gamma.reshape(-1)[0])          # only element 0 is used by the reference (:212-218)
+            if self.training and self.sample_capacity:
+                dt_gamma_t = dt_gamma.reshape(-1)[:1].float().contiguous()   # read on the device: no sync, graph-safe
+                dt_gamma = 0.0
+            else:
+                dt_gamma = float(dt_gamma.reshape(-1)[0])          # only element 0 is used by the reference (:212-218)
         elif isinstance(dt_gamma, (list, tuple)):
             dt_gamma = float(dt_gamma[0])
         ro, rd = rays_o[0], rays_d[0]
         bitfield = density_bitfield[0]
-        if self.training:
+        if self.training and self.sample_capacity:
+            # B200-native protocol: fixed-capacity sample buffers + device-side counts -> no host sync anywhere in the iteration
+            # (the reference syncs three times here: raymarching.py:290, base_volume_renderer.py:235-241), CUDA-graph capturable.
+            cap = int(self.sample_capacity)
+            nears, fars = rm.near_far_from_aabb(ro, rd, self.aabb, self.min_near)
+            xyzs, dirs, ts, rays, counter = rm.march_rays_train(ro, rd, self.bound, bitfield, 1, grid_size, nears, fars, perturb=perturb,
+                                                                dt_gamma=dt_gamma_t if dt_gamma_t is not None else dt_gamma,
+                                                                max_steps=self.max_steps, noises=noises, max_points=cap)
+            N = rays.shape[0]
+            if self.weight_culling_th > 0:
+                with torch.no_grad():
+                    sig0, _, _ = self.point_decode([xyzs], None, code, density_only=True, m_dev=counter)
+                    w0 = torch.empty(cap, dtype=torch.float32, device=xyzs.device)
+                    scratch = torch.empty(N * 5, dtype=torch.float32, device=xyzs.device)
+                    call('mve_composite_rays_train_forward', ptr(sig0), ptr(None), ptr(ts), ptr(rays), c_u32(cap), ptr(counter), c_u32(N),
+                         c_f32(1e-4), c_int(0), ptr(w0), ptr(scratch[:N]), ptr(scratch[N:2 * N]), ptr(scratch[2 * N:]), stream())
+                    counter2 = torch.zeros(1, dtype=torch.int32, device=xyzs.device)
+                    rays2 = torch.empty_like(rays)
+                    xyzs2, ts2 = torch.zeros_like(xyzs), torch.zeros_like(ts)
+                    call('mve_cull_samples', ptr(w0), c_f32(self.weight_culling_th), ptr(rays), ptr(xyzs), ptr(ts), c_u32(N), c_u32(cap),
+                         ptr(counter), ptr(rays2), ptr(xyzs2), ptr(ts2), ptr(counter2), stream())
+                    xyzs, ts, rays, counter = xyzs2, ts2, rays2, counter2
+            sigmas, rgbs, num_points = self.point_decode([xyzs], None, code, m_dev=counter)
+            weights, weights_sum, depth, image = rm.composite_rays_train(sigmas, rgbs, ts, rays, 1e-4, False, counter)
+            results = dict(weights=weights, weights_sum=weights_sum[None], depth=depth[None], image=image[None], rays=[rays], normal=None,
+                           ts=[ts], num_samples=counter)
+        elif self.training:
             nears, fars = rm.near_far_from_aabb(ro, rd, self.aabb, self.min_near)
             xyzs, dirs, ts, rays = rm.march_rays_train(ro, rd, self.bound, bitfield, 1, grid_size, nears, fars, perturb=perturb,
                                                        dt_gamma=dt_gamma, max_steps=self.max_steps, noises=noises)

@@ -232,6 +232,21 @@ class BaseNeRF(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------ nerf_optim
+def _patch_view(t, ps):
+    """(1, V, h, w, C) -> non-materialised view (V, h/ps, w/ps, ps, ps, C): indexing it gathers only the chosen patches
+    (the reference reshapes the permuted tensor, i.e. copies all V*h*w pixels every iteration, base_nerf.py:266-282)."""
+    _, V, h, w, C = t.shape
+    return t[0].reshape(V, h // ps, ps, w // ps, ps, C).permute(0, 1, 3, 2, 4, 5)
+
+
+def _gather_patches(view, inds):
+    V, nh, nw = view.shape[:3]
+    v = torch.div(inds, nh * nw, rounding_mode='floor')
+    r = inds - v * (nh * nw)
+    ih = torch.div(r, nw, rounding_mode='floor')
+    return view[v, ih, r - ih * nw], v
+
+
 def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_steps, n_inverse_rays,
                patch_rgb_weight, patch_normal_weight, alpha_soften, normal_reg_weight, entropy_weight,
                nerf_code, density_grid, density_bitfield,
@@ -242,13 +257,20 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
     """MVEdit3DPipeline.nerf_optim (mvedit_3d_pipeline.py:452-656), same arguments (``self`` -> ``nerf`` + ``tonemapping``).
 
     tgt_images (1,V,rs,rs,3), tgt_masks (1,V,rs,rs,1), intrinsics (V,4), camera_poses (V,3|4,4), cam_weights (V,), cam_lights (V,3).
-    Returns the list of per-iteration loss values only when debug, else None."""
+
+    Same objective, term by term; what differs from the reference is the execution plan:
+      * rays of the drawn patches are generated from (pose, directions[patch]) -- the two (1,V,rs,rs,3) origin/direction tensors and
+        the per-iteration whole-image patch reshuffle are never materialised;
+      * with ``nerf.decoder.sample_capacity > 0`` the iteration has no host sync, and with ``nerf.use_cuda_graph`` (needs
+        ``Adam(capturable=True)``) forward + losses + backward + Adam of one iteration replay as ONE CUDA graph; the occupancy
+        refresh every ``update_extra_interval`` iterations runs between replays.
+    Returns the per-iteration loss log when ``debug`` else None."""
     device = tgt_images.device
     loss_tv = TVLoss(loss_weight=1.0, power=1.5)
     use_normal = tgt_normals is not None
     use_depth = tgt_depths is not None and depth_weight > 0
-    num_cameras = camera_poses.shape[0]
-    cam_ids_dense = torch.arange(num_cameras, device=device)[None, :, None, None, None].expand(-1, -1, render_size, render_size, -1)
+    ps = nerf.patch_size
+    assert patch_size == ps
     cam_weights_mean = cam_weights.mean()
 
     if alpha_blur_std > 0:
@@ -257,97 +279,125 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
                                        ).permute(0, 2, 3, 1)[None].clamp(min=alpha_soften ** 2, max=(1 - alpha_soften) ** 2).sqrt()
     else:
         tgt_masks_blur = tgt_masks.clamp(min=alpha_soften ** 2, max=(1 - alpha_soften) ** 2).sqrt()
-
     directions = get_ray_directions(render_size, render_size, intrinsics[None] * (render_size / intrinsics_size), norm=False,
                                     device=intrinsics.device)
-    cond_rays_o, cond_rays_d = get_rays(directions, camera_poses[None], norm=True)
     normal_bg_t = tgt_images.new_tensor(normal_bg)
+    R, Tr = camera_poses[:, :3, :3].float(), camera_poses[:, :3, 3].float()
+    pv_img, pv_msk, pv_dir = _patch_view(tgt_images, ps), _patch_view(tgt_masks_blur, ps), _patch_view(directions, ps)
+    pv_nrm = _patch_view(tgt_normals, ps) if use_normal else None
+    pv_dep = _patch_view(tgt_depths, ps) if use_depth else None
+    n_patches_total = pv_img.shape[0] * pv_img.shape[1] * pv_img.shape[2]
+    n_sel = max(n_inverse_rays // (ps * ps), 1)
     decoder_training_prev = nerf.decoder.training
     nerf.decoder.train(True)
     log = [] if debug else None
-    ps = nerf.patch_size
+    # schedule-dependent scalars live on the device so that a captured graph sees their current values
+    sc = dict(normal_reg=torch.tensor(float(normal_reg_weight) * 10, device=device), entropy=torch.tensor(float(entropy_weight), device=device),
+              alpha_mul=torch.tensor(5.0 if is_init else 1.0, device=device))
+    inds_static = torch.zeros(min(n_sel, n_patches_total), dtype=torch.long, device=device)
 
+    def iteration():
+        inds = inds_static
+        target_rgbs, target_cam_ids = _gather_patches(pv_img, inds)
+        target_m_blur, _ = _gather_patches(pv_msk, inds)
+        target_dir, _ = _gather_patches(pv_dir, inds)
+        Rv = R[target_cam_ids]
+        rays_d = F.normalize(target_dir @ Rv[:, None].transpose(-1, -2), dim=-1).reshape(1, -1, 3)
+        rays_o = Tr[target_cam_ids][:, None, None, :].expand(-1, ps, ps, -1).reshape(1, -1, 3)
+        target_w = cam_weights[target_cam_ids][:, None, None, None].expand(-1, ps, ps, 1)
+        target_lights = cam_lights[target_cam_ids][:, None, None, :].expand(-1, ps, ps, 3)
+        dt_gamma = dt_gamma_scale / (intrinsics[target_cam_ids, :2].mean(dim=-1) * render_size / intrinsics_size)
+
+        outputs = nerf.decoder(rays_o, rays_d, nerf_code, density_bitfield, nerf.grid_size, dt_gamma=dt_gamma, perturb=True)
+        out_rgbs = outputs['image'].reshape(target_rgbs.size())
+        out_alphas = outputs['weights_sum'].reshape(target_m_blur.size())
+        out_depth = outputs['depth'].reshape(-1, ps, ps)
+        out_depth = out_depth * torch.linalg.norm(target_dir, dim=-1).reshape(out_depth.size())  # 1/r -> 1/z
+        out_depth_fg = out_depth / out_alphas.reshape(-1, ps, ps).clamp(min=1e-6)
+        out_normals_fg = depth_to_normal(out_depth_fg, target_dir)
+        out_normals_fg_mask = out_alphas.reshape(-1, ps, ps, 1)
+        out_normals = out_normals_fg * out_normals_fg_mask + normal_bg_t * (1 - out_normals_fg_mask)
+        out_normals_fg_weight = -F.max_pool2d(-out_normals_fg_mask.detach().squeeze(-1).unsqueeze(1), 3, stride=1, padding=1
+                                              ).squeeze(1).unsqueeze(-1)
+        if not is_init or init_shaded:
+            out_normals_fg_opencv = torch.cat([out_normals_fg[..., :1] * 2 - 1, -out_normals_fg[..., 1:3] * 2 + 1], dim=-1)
+            nerf_shading = ((target_lights[..., None, :] @ out_normals_fg_opencv[..., :, None]).clamp(min=0)
+                            * (1 - ambient_light) + ambient_light).squeeze(-1)
+            if tonemapping is None:
+                out_rgbs = out_rgbs * nerf_shading + nerf.bg_color * (1 - out_alphas)
+            else:
+                out_rgbs = tonemapping.lut(tonemapping.inverse_lut(out_rgbs / out_alphas.clamp(min=1e-6))
+                                           + nerf_shading.clamp(min=1e-6).log2()) * out_alphas + nerf.bg_color * (1 - out_alphas)
+        else:
+            out_rgbs = out_rgbs + nerf.bg_color * (1 - out_alphas)
+
+        pixel_rgb_loss = nerf.pixel_loss(out_rgbs.reshape(target_rgbs.size()), target_rgbs, weight=target_w / cam_weights_mean) * 4.5
+        alphas_loss = nerf.pixel_loss(out_alphas.reshape(target_m_blur.size()), target_m_blur, weight=target_w / cam_weights_mean
+                                      ) * sc['alpha_mul']
+        target_n = _gather_patches(pv_nrm, inds)[0] if use_normal else None
+        normal_reg_loss = loss_tv(out_normals_fg.permute(0, 3, 1, 2), target_n.permute(0, 3, 1, 2) if use_normal else None,
+                                  weight=out_normals_fg_weight.permute(0, 3, 1, 2)) * sc['normal_reg']
+        loss = pixel_rgb_loss + alphas_loss + normal_reg_loss
+        if use_depth:
+            target_depth = _gather_patches(pv_dep, inds)[0]
+            loss = loss + nerf.pixel_loss(out_depth.reshape(target_depth.size()), target_depth, weight=target_w / cam_weights_mean) * depth_weight
+        bin_weights_sum = outputs['weights'].float()
+        bin_width = outputs['ts'][0][:, 1].float()
+        bg_weights_sum = 1 - outputs['weights_sum'].flatten()
+        entropy_loss = -(torch.sum(bin_weights_sum * (torch.log(bin_weights_sum.clamp(min=1e-6)) - torch.log(bin_width.clamp(min=1e-6))))
+                         + torch.sum(bg_weights_sum * (torch.log(bg_weights_sum.clamp(min=1e-6)) - math.log(bg_width)))
+                         ) * (sc['entropy'] / target_rgbs.shape[:-1].numel())
+        loss = loss + entropy_loss
+        if patch_rgb_weight > 0 and nerf.patch_loss is not None:
+            loss = loss + nerf.patch_loss(out_rgbs.reshape(target_rgbs.size()).permute(0, 3, 1, 2), target_rgbs.permute(0, 3, 1, 2),
+                                          weight=target_w[:, 0, 0, 0] / cam_weights_mean) * patch_rgb_weight
+        if use_normal and patch_normal_weight > 0 and nerf.patch_loss is not None and highpass is not None:
+            loss = loss + nerf.patch_loss(highpass(out_normals.reshape(target_n.size()).permute(0, 3, 1, 2)),
+                                          highpass(target_n.permute(0, 3, 1, 2)),
+                                          weight=target_w[:, 0, 0, 0] / cam_weights_mean) * patch_normal_weight
+        optimizer.zero_grad(set_to_none=not use_graph)
+        loss.backward()
+        optimizer.step()
+        return torch.stack([loss.detach(), pixel_rgb_loss.detach(), alphas_loss.detach(), normal_reg_loss.detach(), entropy_loss.detach()])
+
+    use_graph = bool(getattr(nerf, 'use_cuda_graph', False)) and bool(optimizer.defaults.get('capturable', False)) \
+        and nerf.decoder.sample_capacity > 0 and not debug
     with torch.enable_grad():
-        optimizer.param_groups[0]['lr'] = lr
+        if use_graph:
+            if not isinstance(optimizer.param_groups[0]['lr'], torch.Tensor):
+                optimizer.param_groups[0]['lr'] = torch.tensor(float(lr), device=device)
+            optimizer.param_groups[0]['lr'].fill_(float(lr))
+        else:
+            optimizer.param_groups[0]['lr'] = lr
         raybatch_inds, num_raybatch = nerf.get_raybatch_inds(tgt_images, n_inverse_rays)
         iter_density = 0
+        graph = None
         for inverse_step_id in range(inverse_steps):
             if inverse_step_id % nerf.update_extra_interval == 0:
-                update_extra_state = nerf.update_extra_iters
-                extra_args = (density_grid, density_bitfield, iter_density)
-                extra_kwargs = dict(density_thresh=0.1)
+                for _ in range(nerf.update_extra_iters):
+                    nerf.decoder.update_extra_state(nerf_code, density_grid, density_bitfield, iter_density, density_thresh=0.1)
+            if raybatch_inds is not None:
+                inds_static.copy_(raybatch_inds[inverse_step_id % num_raybatch][0][:inds_static.numel()])
             else:
-                update_extra_state = 0
-                extra_args = extra_kwargs = None
-            inds = raybatch_inds[inverse_step_id % num_raybatch] if raybatch_inds is not None else None
-            cond_extras = [tgt_masks_blur, directions, cam_ids_dense]
-            if use_normal:
-                cond_extras.append(tgt_normals)
-            if use_depth:
-                cond_extras.append(tgt_depths)
-            ray_samples = nerf.ray_sample(cond_rays_o, cond_rays_d, tgt_images, n_inverse_rays, sample_inds=inds, cond_extras=cond_extras)
-            rays_o, rays_d, target_rgbs, target_m_blur, target_dir, target_cam_ids = ray_samples[:6]
-            ray_samples = list(ray_samples[6:])
-            if use_normal:
-                target_n = ray_samples.pop(0)
-            if use_depth:
-                target_depth = ray_samples.pop(0)
-            target_cam_ids = target_cam_ids[:, 0, 0, 0]
-            target_w = cam_weights[target_cam_ids][:, None, None, None].expand(-1, patch_size, patch_size, 1)
-            target_lights = cam_lights[target_cam_ids][:, None, None, :].expand(-1, patch_size, patch_size, 3)
-            dt_gamma = dt_gamma_scale / (intrinsics[target_cam_ids, :2].mean(dim=-1) * render_size / intrinsics_size)
-
-            outputs = nerf.decoder(rays_o, rays_d, nerf_code, density_bitfield, nerf.grid_size, dt_gamma=dt_gamma, perturb=True,
-                                   update_extra_state=update_extra_state, extra_args=extra_args, extra_kwargs=extra_kwargs)
-            out_rgbs = outputs['image'].reshape(target_rgbs.size())
-            out_alphas = outputs['weights_sum'].reshape(target_m_blur.size())
-            out_depth = outputs['depth'].reshape(-1, ps, ps)
-            out_depth = out_depth * torch.linalg.norm(target_dir, dim=-1).reshape(out_depth.size())  # 1/r -> 1/z
-            out_depth_fg = out_depth / out_alphas.reshape(-1, ps, ps).clamp(min=1e-6)
-            out_normals_fg = depth_to_normal(out_depth_fg, target_dir)
-            out_normals_fg_mask = out_alphas.reshape(-1, ps, ps, 1)
-            out_normals = out_normals_fg * out_normals_fg_mask + normal_bg_t * (1 - out_normals_fg_mask)
-            out_normals_fg_weight = -F.max_pool2d(-out_normals_fg_mask.detach().squeeze(-1).unsqueeze(1), 3, stride=1, padding=1
-                                                  ).squeeze(1).unsqueeze(-1)
-            if not is_init or init_shaded:
-                out_normals_fg_opencv = torch.cat([out_normals_fg[..., :1] * 2 - 1, -out_normals_fg[..., 1:3] * 2 + 1], dim=-1)
-                nerf_shading = ((target_lights[..., None, :] @ out_normals_fg_opencv[..., :, None]).clamp(min=0)
-                                * (1 - ambient_light) + ambient_light).squeeze(-1)
-                if tonemapping is None:
-                    out_rgbs = out_rgbs * nerf_shading + nerf.bg_color * (1 - out_alphas)
-                else:
-                    out_rgbs = tonemapping.lut(tonemapping.inverse_lut(out_rgbs / out_alphas.clamp(min=1e-6))
-                                               + nerf_shading.clamp(min=1e-6).log2()) * out_alphas + nerf.bg_color * (1 - out_alphas)
+                inds_static.copy_(torch.arange(inds_static.numel(), device=device))
+            if not use_graph:
+                vals = iteration()
+            elif graph is None:
+                # iteration 0 runs eagerly on a side stream (allocator warm-up, Adam state creation) and is then captured;
+                # iterations >= 1 are replays of the captured graph
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    vals = iteration()
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    vals_static = iteration()
             else:
-                out_rgbs = out_rgbs + nerf.bg_color * (1 - out_alphas)
-
-            loss = pixel_rgb_loss = nerf.pixel_loss(out_rgbs.reshape(target_rgbs.size()), target_rgbs, weight=target_w / cam_weights_mean) * 4.5
-            alphas_loss = nerf.pixel_loss(out_alphas.reshape(target_m_blur.size()), target_m_blur, weight=target_w / cam_weights_mean
-                                          ) * (5.0 if is_init else 1.0)
-            normal_reg_loss = loss_tv(out_normals_fg.permute(0, 3, 1, 2), target_n.permute(0, 3, 1, 2) if use_normal else None,
-                                      weight=out_normals_fg_weight.permute(0, 3, 1, 2)) * (normal_reg_weight * 10)
-            loss = loss + alphas_loss + normal_reg_loss
-            if use_depth:
-                loss = loss + nerf.pixel_loss(out_depth.reshape(target_depth.size()), target_depth, weight=target_w / cam_weights_mean) * depth_weight
-            bin_weights_sum = outputs['weights'].float()
-            bin_width = outputs['ts'][0][:, 1].float()
-            bg_weights_sum = 1 - outputs['weights_sum'].flatten()
-            entropy_loss = -(torch.sum(bin_weights_sum * (torch.log(bin_weights_sum.clamp(min=1e-6)) - torch.log(bin_width.clamp(min=1e-6))))
-                             + torch.sum(bg_weights_sum * (torch.log(bg_weights_sum.clamp(min=1e-6)) - math.log(bg_width)))
-                             ) * (entropy_weight / target_rgbs.shape[:-1].numel())
-            loss = loss + entropy_loss
-            if patch_rgb_weight > 0 and nerf.patch_loss is not None:
-                loss = loss + nerf.patch_loss(out_rgbs.reshape(target_rgbs.size()).permute(0, 3, 1, 2), target_rgbs.permute(0, 3, 1, 2),
-                                              weight=target_w[:, 0, 0, 0] / cam_weights_mean) * patch_rgb_weight
-            if use_normal and patch_normal_weight > 0 and nerf.patch_loss is not None and highpass is not None:
-                loss = loss + nerf.patch_loss(highpass(out_normals.reshape(target_n.size()).permute(0, 3, 1, 2)),
-                                              highpass(target_n.permute(0, 3, 1, 2)),
-                                              weight=target_w[:, 0, 0, 0] / cam_weights_mean) * patch_normal_weight
-            optimizer.zero_grad()
-            loss.backward()
-            optimizer.step()
+                graph.replay()
+                vals = vals_static
             if debug:
-                log.append(dict(loss=float(loss.detach()), pixel_rgb=float(pixel_rgb_loss.detach()), alpha=float(alphas_loss.detach()),
-                                normal_reg=float(normal_reg_loss.detach()), entropy=float(entropy_loss.detach())))
+                v = [float(x) for x in vals]
+                log.append(dict(loss=v[0], pixel_rgb=v[1], alpha=v[2], normal_reg=v[3], entropy=v[4]))
     nerf.decoder.train(decoder_training_prev)
     return log

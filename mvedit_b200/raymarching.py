@@ -124,15 +124,17 @@ def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars,
         noises = _cuda_f32(noises)
     counter = torch.zeros(1, dtype=torch.int32, device=dev)
     rays = torch.empty(N, 2, dtype=torch.int32, device=dev)
-    common = (ptr(rays_o), ptr(rays_d), ptr(density_bitfield), c_f32(bound), c_int(int(contract)), c_f32(float(dt_gamma)),
+    dtg = 0.0 if isinstance(dt_gamma, torch.Tensor) else float(dt_gamma)   # a tensor dt_gamma is read on the device (graph-safe)
+    common = (ptr(rays_o), ptr(rays_d), ptr(density_bitfield), c_f32(bound), c_int(int(contract)), c_f32(dtg),
               c_u32(max_steps), c_u32(N), c_u32(C), c_u32(H), ptr(nears), ptr(fars), ptr(noises))
     if max_points is not None:
-        xyzs = torch.empty(max_points, 3, dtype=torch.float32, device=dev)
+        xyzs = torch.zeros(max_points, 3, dtype=torch.float32, device=dev)
         dirs = torch.empty(max_points, 3, dtype=torch.float32, device=dev)
-        ts = torch.empty(max_points, 2, dtype=torch.float32, device=dev)
-        call('mve_march_rays_train', *common, ptr(xyzs), ptr(dirs), ptr(ts), c_u32(max_points), ptr(rays), ptr(counter), stream())
+        ts = torch.zeros(max_points, 2, dtype=torch.float32, device=dev)
+        call('mve_march_rays_train', *common, ptr(xyzs), ptr(dirs), ptr(ts), c_u32(max_points), ptr(rays), ptr(counter),
+             ptr(dt_gamma if isinstance(dt_gamma, torch.Tensor) else None), stream())
         return xyzs, dirs, ts, rays, counter
-    call('mve_march_rays_train', *common, ptr(None), ptr(None), ptr(None), c_u32(0), ptr(rays), ptr(counter), stream())
+    call('mve_march_rays_train', *common, ptr(None), ptr(None), ptr(None), c_u32(0), ptr(rays), ptr(counter), ptr(None), stream())
     M = int(counter.item())
     xyzs = torch.empty(M, 3, dtype=torch.float32, device=dev)
     dirs = torch.empty(M, 3, dtype=torch.float32, device=dev)
@@ -146,7 +148,7 @@ class _composite_rays_train(Function):
     """raymarching.py:314-368."""
 
     @staticmethod
-    def forward(ctx, sigmas, rgbs, ts, rays, T_thresh=1e-4, binarize=False):
+    def forward(ctx, sigmas, rgbs, ts, rays, T_thresh=1e-4, binarize=False, m_dev=None):
         sigmas = sigmas.float().contiguous()
         rgbs = rgbs.float().contiguous()
         ts = ts.float().contiguous()
@@ -158,10 +160,11 @@ class _composite_rays_train(Function):
         weights_sum = torch.empty(N, dtype=torch.float32, device=dev)
         depth = torch.empty(N, dtype=torch.float32, device=dev)
         image = torch.empty(N, 3, dtype=torch.float32, device=dev)
-        call('mve_composite_rays_train_forward', ptr(sigmas), ptr(rgbs), ptr(ts), ptr(rays), c_u32(M), ptr(None), c_u32(N),
+        call('mve_composite_rays_train_forward', ptr(sigmas), ptr(rgbs), ptr(ts), ptr(rays), c_u32(M), ptr(m_dev), c_u32(N),
              c_f32(T_thresh), c_int(int(binarize)), ptr(weights), ptr(weights_sum), ptr(depth), ptr(image), stream())
         ctx.save_for_backward(sigmas, rgbs, ts, rays, weights_sum, depth, image)
         ctx.dims = [M, N, T_thresh, binarize]
+        ctx.m_dev = m_dev
         return weights, weights_sum, depth, image
 
     @staticmethod
@@ -175,9 +178,9 @@ class _composite_rays_train(Function):
         grad_sigmas = torch.zeros_like(sigmas)
         grad_rgbs = torch.zeros_like(rgbs)
         call('mve_composite_rays_train_backward', ptr(grad_weights), ptr(grad_weights_sum), ptr(grad_depth), ptr(grad_image),
-             ptr(sigmas), ptr(rgbs), ptr(ts), ptr(rays), ptr(weights_sum), ptr(depth), ptr(image), c_u32(M), ptr(None), c_u32(N),
+             ptr(sigmas), ptr(rgbs), ptr(ts), ptr(rays), ptr(weights_sum), ptr(depth), ptr(image), c_u32(M), ptr(ctx.m_dev), c_u32(N),
              c_f32(T_thresh), c_int(int(binarize)), ptr(grad_sigmas), ptr(grad_rgbs), stream())
-        return grad_sigmas, grad_rgbs, None, None, None, None
+        return grad_sigmas, grad_rgbs, None, None, None, None, None
 
 
 composite_rays_train = _composite_rays_train.apply

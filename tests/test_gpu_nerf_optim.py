@@ -27,7 +27,10 @@ def _targets(poses, K, size):
     return img, hit[..., None].float()
 
 
-def test_nerf_optim_fits_targets():
+@pytest.mark.parametrize('mode', ['sync', 'capacity', 'graph'])
+def test_nerf_optim_fits_targets(mode):
+    """sync: reference protocol (host reads M twice per iteration); capacity: sync-free fixed-capacity buffers;
+    graph: capacity + one CUDA graph per iteration (forward + losses + backward + capturable Adam)."""
     from mvedit_b200.nerf import BaseNeRF, nerf_optim
     from mvedit_b200.ingp_decoder import iNGPDecoder
     torch.manual_seed(0)
@@ -39,18 +42,22 @@ def test_nerf_optim_fits_targets():
     nerf = BaseNeRF(grid_size=64, decoder=iNGPDecoder(max_steps=256, weight_culling_th=0.001), patch_size=ps).cuda()
     grid = nerf.get_init_density_grid(1, 'cuda')
     bitfield = nerf.get_init_density_bitfield(1, 'cuda')
-    opt = torch.optim.Adam(nerf.decoder.parameters(), lr=0.01)
+    if mode != 'sync':
+        nerf.decoder.sample_capacity = ps * ps * 2 * 192
+    nerf.use_cuda_graph = mode == 'graph'
+    opt = torch.optim.Adam(nerf.decoder.parameters(), lr=0.01, capturable=(mode == 'graph'))
     cam_w = torch.ones(V, device='cuda')
     lights = torch.nn.functional.normalize(torch.randn(V, 3, device='cuda'), dim=-1)
     kw = dict(optimizer=opt, lr=0.01, n_inverse_rays=ps * ps * 2, patch_rgb_weight=0.0, patch_normal_weight=0.0, alpha_soften=0.02,
               normal_reg_weight=0.1, entropy_weight=0.01, nerf_code=None, density_grid=grid, density_bitfield=bitfield, render_size=size,
               intrinsics=K, intrinsics_size=size, camera_poses=poses, cam_weights=cam_w, cam_lights=lights, patch_size=ps, is_init=True,
-              bg_width=0.015, ambient_light=0.2, dt_gamma_scale=0.5, init_shaded=False, debug=True)
+              bg_width=0.015, ambient_light=0.2, dt_gamma_scale=0.5, init_shaded=False, debug=(mode != 'graph'))
     log1 = nerf_optim(nerf, tgt_images, tgt_masks, None, inverse_steps=48, **kw)
     log2 = nerf_optim(nerf, tgt_images, tgt_masks, None, inverse_steps=150, **kw)
-    first = np.mean([l['pixel_rgb'] + l['alpha'] for l in log1[:8]])
-    last = np.mean([l['pixel_rgb'] + l['alpha'] for l in log2[-8:]])
-    assert last < 0.35 * first, (first, last)
+    if mode != 'graph':
+        first = np.mean([l['pixel_rgb'] + l['alpha'] for l in log1[:8]])
+        last = np.mean([l['pixel_rgb'] + l['alpha'] for l in log2[-8:]])
+        assert last < 0.35 * first, (first, last)
     assert bitfield.sum() > 0
     img, depth = nerf.render(nerf.decoder, None, bitfield, size, size, K[None], poses[None], cfg=dict(dt_gamma_scale=0.5, return_rgba=True))
     assert img.shape == (1, V, size, size, 4)
