@@ -108,11 +108,18 @@ class MVEdit3DStep(Adapter3DMixin):
              intrinsics_size, cam_weights, cam_lights, ancestral_noise, guidance_scale=7.0, render_size=512, n_inverse_steps=96,
              n_inverse_rays=2 ** 14, lr=0.01, alpha_soften=0.02, normal_reg_weight=0.1, entropy_weight=0.01, patch_rgb_weight=0.0,
              patch_normal_weight=0.0, bg_width=0.015, ambient_light=0.2, dt_gamma_scale=1.0, testmode_dt_gamma_scale=0.25,
-             is_init=False, tile_weight=1.0, depth_weight=1.0):
+             is_init=False, tile_weight=1.0, depth_weight=1.0, phase_events=None):
         """latents (n_local,4,L,L) fp32; prompt_embeds (2*n_local,T,D) as [neg ; pos]; cameras are the GLOBAL set (all views);
         with view sharding the local slice is ``view_shard.local_range``.  Returns (new latents, ctrl_images, ctrl_depths)."""
+        def mark(name):
+            if phase_events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                phase_events.append((name, e))
+
         sch = self.scheduler
         t = sch.timesteps[i]
+        mark('start')
         lo, hi = view_shard.local_range(camera_poses.shape[0])
         n_local = hi - lo
         assert latents.shape[0] == n_local
@@ -123,26 +130,31 @@ class MVEdit3DStep(Adapter3DMixin):
         prompt_batches = [prompt_embeds]
         noise_pred, dec_args, dec_kwargs = self.get_noise_pred_p1(latent_batches, prompt_batches, t, guidance_scale)
         pred_x0 = ((latents_scaled - sqrt_1mab * noise_pred.float()) / sqrt_ab)
+        mark('denoise_p1')
         # ---- decode (neighbour hook) + exchange of the decoded views (:1258-1266)
         tgt_images, tgt_masks = decode_fn(pred_x0, lo, hi)              # (n_local, rs, rs, 3), (n_local, rs, rs, 1) fp32
         tgt_images = view_shard.gather_views(tgt_images)[None]
         tgt_masks = view_shard.gather_views(tgt_masks)[None]
+        mark('decode_hook+gather')
         # ---- reconstruct (:1296-1305)
         nerf_optim(self.nerf, tgt_images, tgt_masks, None, optimizer, lr, n_inverse_steps, n_inverse_rays, patch_rgb_weight,
                    patch_normal_weight, alpha_soften, normal_reg_weight, entropy_weight, None, density_grid, density_bitfield,
                    render_size, intrinsics, intrinsics_size, camera_poses, cam_weights, cam_lights, self.nerf.patch_size, is_init,
                    bg_width, ambient_light, dt_gamma_scale, init_shaded=False, tonemapping=self.tonemapping)
         view_shard.broadcast_field(self.nerf.decoder, density_grid, density_bitfield)
+        mark('nerf_optim')
         # ---- render my views (:1341-1395)
         ctrl_images, ctrl_depths = self.render_views(density_bitfield, camera_poses[lo:hi], intrinsics[lo:hi], intrinsics_size,
                                                      render_size, cam_lights[lo:hi], ambient_light, testmode_dt_gamma_scale)
         if render_size != 512:
             ctrl_images = torch.nn.functional.interpolate(ctrl_images.float(), size=(512, 512), mode='bilinear').clamp(0, 1).to(torch.bfloat16)
             ctrl_depths = torch.nn.functional.interpolate(ctrl_depths.float(), size=(512, 512), mode='bilinear').to(torch.bfloat16)
+        mark('render_views')
         # ---- denoise P2 (:1413-1426)
         noise_pred = self.get_noise_pred_p2(latent_batches, prompt_batches, dec_args, dec_kwargs, t, guidance_scale,
                                             [torch.cat([ctrl_images] * 2, dim=0)], tile_weight, [torch.cat([ctrl_depths] * 2, dim=0)],
                                             depth_weight)
         # ---- solver step (:1438-1461, blend_weight 0)
         latents = sch.step(noise_pred.float(), i, latents, ancestral_noise)
+        mark('denoise_p2+solver')
         return latents, ctrl_images, ctrl_depths
