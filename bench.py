@@ -342,7 +342,7 @@ def raymarch_microbench(device, pk):
     fwd = lambda: call('mve_composite_rays_train_forward', ptr(sig), ptr(rgb), ptr(t), ptr(rays), c_u32(M), ptr(None), c_u32(N), c_f32(1e-4),
                        c_int(0), ptr(w), ptr(ws), ptr(dep), ptr(img), stream())
     bwd = lambda: call('mve_composite_rays_train_backward', ptr(gw), ptr(gws), ptr(gd), ptr(gi), ptr(sig), ptr(rgb), ptr(t), ptr(rays), ptr(ws),
-                       ptr(dep), ptr(img), c_u32(M), ptr(None), c_u32(N), c_f32(1e-4), c_int(0), ptr(gs), ptr(gc), stream())
+                       ptr(dep), ptr(img), c_u32(M), ptr(None), c_u32(N), c_f32(1e-4), c_int(0), ptr(None), c_f32(0.0), ptr(gs), ptr(gc), stream())
 
     def march():
         counter.zero_()

@@ -56,6 +56,7 @@ int mve_packbits(const void* grid, int grid_is_half, uint32_t N, float density_t
  * samples would not fit in max_M keep their (offset,count) but write nothing (composite treats
  * offset+count > M as an empty ray, raymarching.cu:523).  If xyzs == NULL only rays/counter are written
  * (the reference's first pass).  noises [N] f32 may be NULL (= zeros, perturb=False).
+ * dirs may be NULL (view-independent fields never read it).
  * dt_gamma_dev (optional, device, 1 float) overrides dt_gamma so a captured CUDA graph can change it between replays. */
 int mve_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* density_bitfield,
                          float bound, int contract, float dt_gamma, uint32_t max_steps,
@@ -81,11 +82,14 @@ int mve_composite_rays_train_forward(const float* sigmas, const float* rgbs, con
                                      float* weights, float* weights_sum, float* depth, float* image, void* stream);
 
 /* raymarching.h:17 composite_rays_train_backward ; kernel raymarching.cu:606-695.
- * grad_sigmas [M], grad_rgbs [M,3] are fully written for every sample covered by a ray. */
+ * grad_sigmas [M], grad_rgbs [M,3] are fully written for every sample covered by a ray.  grad_weights may be NULL (= 0).
+ * entropy_weight_dev (optional, device scalar c) adds the gradient of the reference's sample-entropy regulariser
+ * -c*entropy_scale*sum_i w_i (log max(w_i,1e-6) - log max(dt_i,1e-6))  (mvedit_3d_pipeline.py:595-603) to grad_weights on the fly. */
 int mve_composite_rays_train_backward(const float* grad_weights, const float* grad_weights_sum, const float* grad_depth,
                                       const float* grad_image, const float* sigmas, const float* rgbs, const float* ts,
                                       const int32_t* rays, const float* weights_sum, const float* depth, const float* image,
                                       uint32_t M, const int32_t* M_dev, uint32_t N, float T_thresh, int binarize,
+                                      const float* entropy_weight_dev, float entropy_scale,
                                       float* grad_sigmas, float* grad_rgbs, void* stream);
 
 /* raymarching.h:19 march_rays (inference) ; kernel raymarching.cu:714-829.
@@ -172,10 +176,14 @@ int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses
                     float blob_density, float blob_radius, float sigmoid_saturation,
                     float* weights_sum, float* depth, float* image, void* stream);
 
+/* Statistics of the most recent mve_render_rays launch: number of samples shaded (host-synchronous; diagnostics / bench only). */
+int mve_render_last_sample_count(uint64_t* host_out);
+
 /* Weight culling of the training branch (base_volume_renderer.py:222-246): keep samples with weight > th, compact xyzs/ts,
- * rebuild rays (offset,count); *counter (zeroed by the caller) receives the kept total. */
+ * rebuild rays (offset,count); *counter (zeroed by the caller) receives the kept total.  Rays whose kept samples would not fit
+ * in the M_out_cap-sample output buffers are emitted as empty. */
 int mve_cull_samples(const float* weights, float th, const int32_t* rays_in, const float* xyzs_in, const float* ts_in,
-                     uint32_t N, uint32_t M, const int32_t* M_dev,
+                     uint32_t N, uint32_t M, const int32_t* M_dev, uint32_t M_out_cap,
                      int32_t* rays_out, float* xyzs_out, float* ts_out, int32_t* counter, void* stream);
 
 /* Occupancy-grid refresh tail of VolumeRenderer.update_extra_state (base_volume_renderer.py:163-175): fp16 EMA
@@ -206,6 +214,17 @@ int mve_upsample2x_bf16(const void* x, void* y, uint32_t B, uint32_t H, uint32_t
 int mve_im2col3x3s2_bf16(const void* x, void* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* stream);
 /* x [B,C,HW] (f32 or bf16) -> y [B,HW,Cpad] bf16, channels >= C zero-filled */
 int mve_nchw_to_nhwc_pad_bf16(const void* x, int x_is_f32, void* y, uint32_t B, uint32_t C, uint32_t HW, uint32_t Cpad, void* stream);
+
+/* Fused objective of one nerf_optim iteration on P patches of ps x ps rays (mvedit_3d_pipeline.py:541-603 without target normals /
+ * depths / tonemapping): depth->normals, Lambert shading, L1 rgb, L1 alpha, TV^1.5 normal regulariser, background entropy.
+ * Produces the 5 loss terms (total, rgb, alpha, normal_reg, bg-entropy) and d/d(image, weights_sum, depth).
+ * w_* are device scalars (schedule dependent).  scratch: mve_nerf_patch_loss_scratch_floats(N) floats. */
+uint32_t mve_nerf_patch_loss_scratch_floats(uint32_t n_rays);
+int mve_nerf_patch_loss(const float* image, const float* alpha, const float* depth, const float* tgt_rgb, const float* tgt_mask,
+                        const float* dirs, const float* patch_w, const float* lights, uint32_t n_patches, uint32_t patch_size,
+                        int shaded, float ambient, float bg_color, float bg_width, float pixel_loss_weight,
+                        const float* w_alpha_mul, const float* w_normal_reg, const float* w_entropy,
+                        float* scratch, float* g_image, float* g_alpha, float* g_depth, float* loss5, void* stream);
 
 #ifdef __cplusplus
 }

@@ -106,9 +106,9 @@ __device__ __forceinline__ uint32_t march_one(const Ray& r, const MarchParams& p
             t += dt;
             if (WRITE) {
                 xyzs[0] = cx; xyzs[1] = cy; xyzs[2] = cz;
-                dirs[0] = r.dx; dirs[1] = r.dy; dirs[2] = r.dz;
+                if (dirs) { dirs[0] = r.dx; dirs[1] = r.dy; dirs[2] = r.dz; dirs += 3; }   // view-independent fields skip dirs
                 ts[0] = t; ts[1] = dt;
-                xyzs += 3; dirs += 3; ts += 2;
+                xyzs += 3; ts += 2;
             }
         }
     }
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(MT_T) k_march_train(const float* __restrict__ 
     rays[n * 2] = (int)offset;
     rays[n * 2 + 1] = (int)cnt;
     if (xyzs == nullptr || cnt == 0 || (uint64_t)offset + cnt > max_M) return;
-    march_one<true>(r, p, near, far, noise, cnt, xyzs + (size_t)offset * 3, dirs + (size_t)offset * 3, ts + (size_t)offset * 2);
+    march_one<true>(r, p, near, far, noise, cnt, xyzs + (size_t)offset * 3, dirs ? dirs + (size_t)offset * 3 : nullptr, ts + (size_t)offset * 2);
 }
 
 // second pass only (reference protocol: offsets already in rays)
@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(MT_T) k_march_train_write(const float* __restr
     const uint32_t offset = rays[n * 2], cnt = rays[n * 2 + 1];
     if (cnt == 0 || (uint64_t)offset + cnt > max_M) return;
     const Ray r = load_ray(rays_o, rays_d, n);
-    march_one<true>(r, p, nears[n], fars[n], noises ? noises[n] : 0.0f, cnt, xyzs + (size_t)offset * 3, dirs + (size_t)offset * 3,
-                    ts + (size_t)offset * 2);
+    march_one<true>(r, p, nears[n], fars[n], noises ? noises[n] : 0.0f, cnt, xyzs + (size_t)offset * 3,
+                    dirs ? dirs + (size_t)offset * 3 : nullptr, ts + (size_t)offset * 2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(CP_T) k_composite_train_bwd(const float* __res
                                                               const float* __restrict__ weights_sum, const float* __restrict__ depth,
                                                               const float* __restrict__ image, uint32_t M, const int* __restrict__ M_dev,
                                                               const uint32_t N, const float T_thresh, const bool binarize,
+                                                              const float* __restrict__ ent_w, const float ent_scale,
                                                               float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
     const uint32_t n = (blockIdx.x * CP_T + threadIdx.x) / G;
     if (n >= N) return;
@@ -288,6 +289,8 @@ __global__ void __launch_bounds__(CP_T) k_composite_train_bwd(const float* __res
     if (M_dev) M = min(M, (uint32_t)*M_dev);
     const uint32_t offset = rays[n * 2], num_steps = rays[n * 2 + 1];
     if (num_steps == 0 || (uint64_t)offset + num_steps > M) return;
+    // optional fused term: L_ent = -c * sum_i w_i (log max(w_i,1e-6) - log max(dt_i,1e-6))  (mvedit_3d_pipeline.py:595-603, sample part)
+    const float ent_c = ent_w ? ent_w[0] * ent_scale : 0.0f;
 
     const float gws = grad_weights_sum[n], gd = grad_depth[n];
     const float g0 = grad_image[n * 3], g1 = grad_image[n * 3 + 1], g2 = grad_image[n * 3 + 2];
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(CP_T) k_composite_train_bwd(const float* __res
         const bool valid = i < num_steps;
         float sigma = 0, cr = 0, cg = 0, cb = 0, gwi = 0;
         float2 td = make_float2(1.0f, 0.0f);
-        if (valid) { sigma = sg[i]; td = tt[i]; cr = cl[i * 3]; cg = cl[i * 3 + 1]; cb = cl[i * 3 + 2]; gwi = gw[i]; }
+        if (valid) { sigma = sg[i]; td = tt[i]; cr = cl[i * 3]; cg = cl[i * 3 + 1]; cb = cl[i * 3 + 2]; gwi = grad_weights ? gw[i] : 0.0f; }
         const float real_alpha = 1.0f - __expf(-sigma * td.y);
         const float alpha = valid ? (binarize ? (real_alpha > 0.5f ? 1.0f : 0.0f) : real_alpha) : 0.0f;
         const float pin = group_scan_mul<G>(1.0f - alpha, gmask, gl);
@@ -320,6 +323,8 @@ __global__ void __launch_bounds__(CP_T) k_composite_train_bwd(const float* __res
         const int first = stop ? (__ffs(stop) - 1) : G;
         const bool keep = valid && gl <= first;
         const float w = keep ? weight : 0.0f;
+        if (ent_c != 0.0f && valid)
+            gwi -= ent_c * ((__logf(fmaxf(w, 1e-6f)) - __logf(fmaxf(td.y, 1e-6f))) + ((w > 1e-6f) ? 1.0f : 0.0f));
         const float q = g0 * cr + g1 * cg + g2 * cb + gws + gd / td.x;
         const float S_i = S_carry + group_scan_add<G>(w * q, gmask, gl);
         const float ws_i = ws_carry + group_scan_add<G>(w, gmask, gl);
@@ -491,12 +496,13 @@ int mve_composite_rays_train_forward(const float* sigmas, const float* rgbs, con
 int mve_composite_rays_train_backward(const float* grad_weights, const float* grad_weights_sum, const float* grad_depth,
                                       const float* grad_image, const float* sigmas, const float* rgbs, const float* ts, const int32_t* rays,
                                       const float* weights_sum, const float* depth, const float* image, uint32_t M, const int32_t* M_dev,
-                                      uint32_t N, float T_thresh, int binarize, float* grad_sigmas, float* grad_rgbs, void* stream) {
+                                      uint32_t N, float T_thresh, int binarize, const float* entropy_weight_dev, float entropy_scale,
+                                      float* grad_sigmas, float* grad_rgbs, void* stream) {
     if (N == 0) return 0;
     const int g = pick_group(M, N);
     MVE_DISPATCH_G(g, k_composite_train_bwd<G><<<cdiv((uint64_t)N * G, CP_T), CP_T, 0, (cudaStream_t)stream>>>(
                           grad_weights, grad_weights_sum, grad_depth, grad_image, sigmas, rgbs, ts, rays, weights_sum, depth, image, M, M_dev,
-                          N, T_thresh, binarize != 0, grad_sigmas, grad_rgbs));
+                          N, T_thresh, binarize != 0, entropy_weight_dev, entropy_scale, grad_sigmas, grad_rgbs));
     MVE_CHECK_LAUNCH("mve_composite_rays_train_backward");
     return 0;
 }

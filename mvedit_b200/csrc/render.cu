@@ -53,91 +53,117 @@ struct RenderParams {
     const float* dt_gamma_per_view;  // [V] or null (then march.dt_gamma is used)
 };
 
-// Lane-level dynamic scheduling: a lane that finishes its ray immediately fetches the next one (chunks of RAY_CHUNK consecutive
-// rays per atomic), and the loop is split in two phases so the expensive part stays converged:
-//   phase 1 (divergent, cheap)   every lane advances its DDA / retires its ray / fetches a new ray until it holds ONE sample to shade
-//   phase 2 (converged, heavy)   all lanes that hold a sample run the 96 hash-grid gathers + MLP + compositing together
-// so empty-space rays and early-terminated rays never idle a warp while a neighbour shades hundreds of samples.
-constexpr int RAY_CHUNK = 8;
+// Round-based lane scheduling.  Every round (all steps converged except the bounded DDA loop):
+//   1. lanes without a ray fetch the next one with ONE warp-aggregated atomic,
+//   2. every lane without a sample advances its DDA by at most DDA_BUDGET voxel steps (retiring the ray if it ends); the loop
+//      stops as soon as no lane is still searching, so a warp full of surface rays pays one DDA step per round,
+//   3. the lanes that hold a sample shade it together (96 hash-grid gathers + MLP + compositing) -- the expensive part stays converged.
+// A ray crossing empty space therefore never stalls its neighbours' shading for more than DDA_BUDGET steps, and finished /
+// missing / early-terminated rays are replaced immediately.
+constexpr int DDA_BUDGET = 8;
 
 template <int L>
 __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, MarchParams mp, const float2* __restrict__ table,
                                                      const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                                                      const float* __restrict__ b2, const Levels lv, const FieldCfg cfg,
-                                                     unsigned int* __restrict__ next_ray) {
+                                                     unsigned int* __restrict__ next_ray, unsigned long long* __restrict__ stats) {
     using R = Rec<L>;
     __shared__ __align__(16) float rec[HID * R::STRIDE];
     stage_mlp<L>(rec, w1, b1, w2);
     __syncthreads();
     const float ob0 = b2[0], ob1 = b2[1], ob2 = b2[2], ob3 = b2[3];
+    const int lane = threadIdx.x & 31;
 
-    bool have_ray = false, exhausted = false;
-    uint32_t n = 0, cur = 0, chunk_left = 0, step = 0;
+    bool have_ray = false;
+    bool exhausted = false;      // warp-uniform
+    uint32_t n = 0, step = 0, shaded = 0;
     Ray r;
     float t = 0.f, far = 0.f, ws = 0.f, dsum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
     bool terminated = false;
     float cx = 0.f, cy = 0.f, cz = 0.f, dt = 0.f;
 
     for (;;) {
-        bool has = false;
-        // ---------------- phase 1
-        while (!exhausted) {
-            if (!have_ray) {
-                if (chunk_left == 0) { cur = atomicAdd(next_ray, (unsigned int)RAY_CHUNK); chunk_left = RAY_CHUNK; }
-                if (cur >= rp.N) { exhausted = true; break; }
-                n = cur++; chunk_left--;
-                if (rp.rays_o) {
-                    r = load_ray(rp.rays_o, rp.rays_d, n);
-                } else {
-                    const uint32_t hw = rp.h * rp.w, v = n / hw, pix = n % hw;
-                    const float pi = (float)(pix % rp.w) + 0.5f, pj = (float)(pix / rp.w) + 0.5f;
-                    const float* K = rp.intrinsics + v * 4;
-                    const float* P = rp.poses + v * 16;
-                    const float cxd = (pi - K[2]) / K[0], cyd = (pj - K[3]) / K[1];
-                    const float dx = P[0] * cxd + P[1] * cyd + P[2], dy = P[4] * cxd + P[5] * cyd + P[6], dz = P[8] * cxd + P[9] * cyd + P[10];
-                    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-                    r.ox = P[3]; r.oy = P[7]; r.oz = P[11];
-                    r.dx = dx * inv; r.dy = dy * inv; r.dz = dz * inv;
-                    r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
-                    if (rp.dt_gamma_per_view) mp.dt_gamma = rp.dt_gamma_per_view[v];
+        // ---------------- 1. fetch
+        if (!exhausted) {
+            const uint32_t need = __ballot_sync(0xffffffffu, !have_ray);
+            if (need) {
+                uint32_t base = 0;
+                if (lane == __ffs(need) - 1) base = atomicAdd(next_ray, (unsigned int)__popc(need));
+                base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
+                if (base >= rp.N) exhausted = true;
+                if (!have_ray) {
+                    const uint32_t mine = base + __popc(need & ((1u << lane) - 1u));
+                    if (mine < rp.N) {
+                        n = mine;
+                        if (rp.rays_o) {
+                            r = load_ray(rp.rays_o, rp.rays_d, n);
+                        } else {
+                            const uint32_t hw = rp.h * rp.w, v = n / hw, pix = n % hw;
+                            const float pi = (float)(pix % rp.w) + 0.5f, pj = (float)(pix / rp.w) + 0.5f;
+                            const float* K = rp.intrinsics + v * 4;
+                            const float* P = rp.poses + v * 16;
+                            const float cxd = (pi - K[2]) / K[0], cyd = (pj - K[3]) / K[1];
+                            const float dx = P[0] * cxd + P[1] * cyd + P[2], dy = P[4] * cxd + P[5] * cyd + P[6], dz = P[8] * cxd + P[9] * cyd + P[10];
+                            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+                            r.ox = P[3]; r.oy = P[7]; r.oz = P[11];
+                            r.dx = dx * inv; r.dy = dy * inv; r.dz = dz * inv;
+                            r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+                            if (rp.dt_gamma_per_view) mp.dt_gamma = rp.dt_gamma_per_view[v];
+                        }
+                        float near;
+                        slab(r, rp.aabb, rp.min_near, near, far);
+                        t = near;
+                        ws = 0.f; dsum = 0.f; cr = 0.f; cg = 0.f; cb = 0.f; step = 0; terminated = false;
+                        have_ray = true;
+                    }
                 }
-                float near;
-                slab(r, rp.aabb, rp.min_near, near, far);
-                t = near;
-                ws = 0.f; dsum = 0.f; cr = 0.f; cg = 0.f; cb = 0.f; step = 0; terminated = false;
-                have_ray = true;
-            }
-            if (!terminated && t < far && step < rp.max_steps) {
-                if (dda_step(r, mp, t, cx, cy, cz, dt)) { has = true; break; }
-            } else {
-                rp.weights_sum[n] = ws;
-                rp.depth[n] = dsum;
-                rp.image[(size_t)n * 3] = cr; rp.image[(size_t)n * 3 + 1] = cg; rp.image[(size_t)n * 3 + 2] = cb;
-                have_ray = false;
             }
         }
-        if (!__any_sync(0xffffffffu, has)) break;
-        // ---------------- phase 2
-        if (has) {
-            t += dt;
-            float enc[R::IN];
-            encode<L>(lv, table, (cx + cfg.bound) * cfg.inv2b, (cy + cfg.bound) * cfg.inv2b, (cz + cfg.bound) * cfg.inv2b, enc);
-            float o0 = ob0, o1 = ob1, o2 = ob2, o3 = ob3;
-            mlp_forward<L, false>(rec, enc, o0, o1, o2, o3);
-            const float sigma = __expf(o0 + blob_of(cfg, cx, cy, cz));
-            // kernel_composite_rays (raymarching.cu:878-903): T = 1 - weight_sum, the ray dies after accumulating the sample
-            const float alpha = 1.0f - __expf(-sigma * dt);
-            const float T = 1 - ws;
-            const float weight = alpha * T;
-            ws += weight;
-            dsum += weight / t;
-            cr += weight * fmaf(1.f / (1.f + __expf(-o1)), cfg.sat_scale, cfg.sat_shift);
-            cg += weight * fmaf(1.f / (1.f + __expf(-o2)), cfg.sat_scale, cfg.sat_shift);
-            cb += weight * fmaf(1.f / (1.f + __expf(-o3)), cfg.sat_scale, cfg.sat_shift);
-            step++;
-            if (T < rp.T_thresh) terminated = true;
+        if (!__any_sync(0xffffffffu, have_ray)) break;     // nothing in flight and nothing left to fetch
+        // ---------------- 2. bounded search for the next sample
+        bool has = false;
+#pragma unroll 1
+        for (int k = 0; k < DDA_BUDGET; k++) {
+            const bool searching = have_ray && !has;
+            if (!__any_sync(0xffffffffu, searching)) break;
+            if (searching) {
+                if (!terminated && t < far && step < rp.max_steps) {
+                    has = dda_step(r, mp, t, cx, cy, cz, dt);
+                } else {
+                    rp.weights_sum[n] = ws;
+                    rp.depth[n] = dsum;
+                    rp.image[(size_t)n * 3] = cr; rp.image[(size_t)n * 3 + 1] = cg; rp.image[(size_t)n * 3 + 2] = cb;
+                    have_ray = false;
+                }
+            }
+        }
+        // ---------------- 3. shade
+        if (__any_sync(0xffffffffu, has)) {
+            if (has) {
+                t += dt;
+                float enc[R::IN];
+                encode<L>(lv, table, (cx + cfg.bound) * cfg.inv2b, (cy + cfg.bound) * cfg.inv2b, (cz + cfg.bound) * cfg.inv2b, enc);
+                float o0 = ob0, o1 = ob1, o2 = ob2, o3 = ob3;
+                mlp_forward<L, false>(rec, enc, o0, o1, o2, o3);
+                const float sigma = __expf(o0 + blob_of(cfg, cx, cy, cz));
+                // kernel_composite_rays (raymarching.cu:878-903): T = 1 - weight_sum, the ray dies after accumulating the sample
+                const float alpha = 1.0f - __expf(-sigma * dt);
+                const float T = 1 - ws;
+                const float weight = alpha * T;
+                ws += weight;
+                dsum += weight / t;
+                cr += weight * fmaf(1.f / (1.f + __expf(-o1)), cfg.sat_scale, cfg.sat_shift);
+                cg += weight * fmaf(1.f / (1.f + __expf(-o2)), cfg.sat_scale, cfg.sat_shift);
+                cb += weight * fmaf(1.f / (1.f + __expf(-o3)), cfg.sat_scale, cfg.sat_shift);
+                step++; shaded++;
+                if (T < rp.T_thresh) terminated = true;
+            }
         }
     }
+    // statistics: samples shaded (one atomic per warp)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) shaded += __shfl_xor_sync(0xffffffffu, shaded, o);
+    if (lane == 0 && shaded) atomicAdd(stats, (unsigned long long)shaded);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -146,8 +172,9 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
 constexpr int CC_T = 256;
 __global__ void __launch_bounds__(CC_T) k_cull_compact(const float* __restrict__ weights, const float th, const int* __restrict__ rays_in,
                                                        const float* __restrict__ xyzs_in, const float* __restrict__ ts_in, const uint32_t N,
-                                                       uint32_t M, const int* __restrict__ M_dev, int* __restrict__ rays_out,
-                                                       float* __restrict__ xyzs_out, float* __restrict__ ts_out, int* __restrict__ counter) {
+                                                       uint32_t M, const int* __restrict__ M_dev, const uint32_t M_out_cap,
+                                                       int* __restrict__ rays_out, float* __restrict__ xyzs_out, float* __restrict__ ts_out,
+                                                       int* __restrict__ counter) {
     __shared__ uint32_t s_cnt[CC_T / 32];
     __shared__ uint32_t s_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -173,6 +200,10 @@ __global__ void __launch_bounds__(CC_T) k_cull_compact(const float* __restrict__
     __syncthreads();
     if (n >= N) return;
     uint32_t out = s_base + s_cnt[warp];
+    if ((uint64_t)out + kept > M_out_cap) {      // output buffer full: the ray is dropped (empty) rather than written out of bounds
+        if (lane == 0) { rays_out[n * 2] = 0; rays_out[n * 2 + 1] = 0; }
+        return;
+    }
     if (lane == 0) { rays_out[n * 2] = (int)out; rays_out[n * 2 + 1] = (int)kept; }
     for (uint32_t base = 0; base < num; base += 32) {
         const uint32_t i = base + lane;
@@ -225,9 +256,19 @@ __global__ void k_packbits_dev(const __half* __restrict__ grid, const uint32_t N
     bitfield[n] = (uint8_t)bits;
 }
 
+static unsigned char* g_render_scratch = nullptr;
+
 }  // namespace
 
 extern "C" {
+
+int mve_render_last_sample_count(uint64_t* host_out) {
+    MVE_ARG(host_out != nullptr, "render_last_sample_count: null output");
+    *host_out = 0;
+    if (!g_render_scratch) return 0;
+    MVE_CUDA(cudaMemcpy(host_out, g_render_scratch + 8, 8, cudaMemcpyDeviceToHost));   // synchronises: statistics only
+    return 0;
+}
 
 int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses, const float* intrinsics, const float* dt_gamma_per_view,
                     uint32_t h, uint32_t w, uint32_t N, const float* aabb, float min_near, const uint8_t* density_bitfield, float bound,
@@ -246,26 +287,28 @@ int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses
     rp.rays_o = rays_o; rp.rays_d = rays_d; rp.poses = poses; rp.intrinsics = intrinsics; rp.h = h; rp.w = w; rp.N = N; rp.aabb = aabb;
     rp.min_near = min_near; rp.T_thresh = T_thresh; rp.max_steps = max_steps; rp.weights_sum = weights_sum; rp.depth = depth;
     rp.image = image; rp.dt_gamma_per_view = dt_gamma_per_view;
-    uint32_t grid = cdiv(N, 128 * RAY_CHUNK);
+    uint32_t grid = cdiv(N, 128);
     if (grid > (uint32_t)(8 * kNumSM)) grid = 8 * kNumSM;
     const float2* t2 = reinterpret_cast<const float2*>(table);
     cudaStream_t s = (cudaStream_t)stream;
-    static unsigned int* next_ray = nullptr;   // one process drives one GPU: a process-wide work counter is enough
-    if (!next_ray) MVE_CUDA(cudaMalloc(&next_ray, sizeof(unsigned int)));
-    MVE_CUDA(cudaMemsetAsync(next_ray, 0, sizeof(unsigned int), s));
-    if (n_levels == 12) k_render_rays<12><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray);
-    else if (n_levels == 14) k_render_rays<14><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray);
-    else k_render_rays<16><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray);
+    // one process drives one GPU: process-wide scratch = [work counter (u32) | pad | samples shaded (u64)]
+    if (!g_render_scratch) MVE_CUDA(cudaMalloc(&g_render_scratch, 16));
+    MVE_CUDA(cudaMemsetAsync(g_render_scratch, 0, 16, s));
+    unsigned int* next_ray = reinterpret_cast<unsigned int*>(g_render_scratch);
+    unsigned long long* stats = reinterpret_cast<unsigned long long*>(g_render_scratch + 8);
+    if (n_levels == 12) k_render_rays<12><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);
+    else if (n_levels == 14) k_render_rays<14><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);
+    else k_render_rays<16><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);
     MVE_CHECK_LAUNCH("mve_render_rays");
     return 0;
 }
 
 int mve_cull_samples(const float* weights, float th, const int32_t* rays_in, const float* xyzs_in, const float* ts_in, uint32_t N,
-                     uint32_t M, const int32_t* M_dev, int32_t* rays_out, float* xyzs_out, float* ts_out, int32_t* counter,
-                     void* stream) {
+                     uint32_t M, const int32_t* M_dev, uint32_t M_out_cap, int32_t* rays_out, float* xyzs_out, float* ts_out,
+                     int32_t* counter, void* stream) {
     if (N == 0) return 0;
-    k_cull_compact<<<cdiv(N, CC_T / 32), CC_T, 0, (cudaStream_t)stream>>>(weights, th, rays_in, xyzs_in, ts_in, N, M, M_dev, rays_out,
-                                                                           xyzs_out, ts_out, counter);
+    k_cull_compact<<<cdiv(N, CC_T / 32), CC_T, 0, (cudaStream_t)stream>>>(weights, th, rays_in, xyzs_in, ts_in, N, M, M_dev, M_out_cap,
+                                                                           rays_out, xyzs_out, ts_out, counter);
     MVE_CHECK_LAUNCH("mve_cull_samples");
     return 0;
 }

@@ -233,7 +233,7 @@ class iNGPDecoder(nn.Module):
 
     # ------------------------------------------------------------------ renderer
     def forward(self, rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma=0.0, perturb=False, return_loss=False,
-                compute_normal=False, update_extra_state=0, extra_args=None, extra_kwargs=None, noises=None):
+                compute_normal=False, update_extra_state=0, extra_args=None, extra_kwargs=None, noises=None, fused_entropy=None):
         """base_volume_renderer.py:179-343 (one scene).  rays_o/rays_d: (1, N, 3); density_bitfield: (1, H^3/8)."""
         assert not compute_normal, 'compute_normal is not used on the MVEdit path'
         for _ in range(update_extra_state):
@@ -256,27 +256,30 @@ class iNGPDecoder(nn.Module):
         if self.training and self.sample_capacity:
             # B200-native protocol: fixed-capacity sample buffers + device-side counts -> no host sync anywhere in the iteration
             # (the reference syncs three times here: raymarching.py:290, base_volume_renderer.py:235-241), CUDA-graph capturable.
-            cap = int(self.sample_capacity)
+            cap = int(self.sample_capacity)                      # post-cull capacity (zero-filled tails: torch may reduce over them)
             nears, fars = rm.near_far_from_aabb(ro, rd, self.aabb, self.min_near)
+            N = ro.shape[0]
+            cap1 = N * int(self.max_steps) if self.weight_culling_th > 0 else cap   # the marcher can never overflow N*max_steps
             xyzs, dirs, ts, rays, counter = rm.march_rays_train(ro, rd, self.bound, bitfield, 1, grid_size, nears, fars, perturb=perturb,
                                                                 dt_gamma=dt_gamma_t if dt_gamma_t is not None else dt_gamma,
-                                                                max_steps=self.max_steps, noises=noises, max_points=cap)
-            N = rays.shape[0]
+                                                                max_steps=self.max_steps, noises=noises, max_points=cap1,
+                                                                zero_tail=not self.weight_culling_th > 0, want_dirs=False)
             if self.weight_culling_th > 0:
                 with torch.no_grad():
                     sig0, _, _ = self.point_decode([xyzs], None, code, density_only=True, m_dev=counter)
-                    w0 = torch.empty(cap, dtype=torch.float32, device=xyzs.device)
+                    w0 = torch.empty(cap1, dtype=torch.float32, device=xyzs.device)
                     scratch = torch.empty(N * 5, dtype=torch.float32, device=xyzs.device)
-                    call('mve_composite_rays_train_forward', ptr(sig0), ptr(None), ptr(ts), ptr(rays), c_u32(cap), ptr(counter), c_u32(N),
+                    call('mve_composite_rays_train_forward', ptr(sig0), ptr(None), ptr(ts), ptr(rays), c_u32(cap1), ptr(counter), c_u32(N),
                          c_f32(1e-4), c_int(0), ptr(w0), ptr(scratch[:N]), ptr(scratch[N:2 * N]), ptr(scratch[2 * N:]), stream())
                     counter2 = torch.zeros(1, dtype=torch.int32, device=xyzs.device)
                     rays2 = torch.empty_like(rays)
-                    xyzs2, ts2 = torch.zeros_like(xyzs), torch.zeros_like(ts)
-                    call('mve_cull_samples', ptr(w0), c_f32(self.weight_culling_th), ptr(rays), ptr(xyzs), ptr(ts), c_u32(N), c_u32(cap),
-                         ptr(counter), ptr(rays2), ptr(xyzs2), ptr(ts2), ptr(counter2), stream())
+                    xyzs2 = torch.zeros(cap, 3, dtype=torch.float32, device=xyzs.device)
+                    ts2 = torch.zeros(cap, 2, dtype=torch.float32, device=xyzs.device)
+                    call('mve_cull_samples', ptr(w0), c_f32(self.weight_culling_th), ptr(rays), ptr(xyzs), ptr(ts), c_u32(N), c_u32(cap1),
+                         ptr(counter), c_u32(cap), ptr(rays2), ptr(xyzs2), ptr(ts2), ptr(counter2), stream())
                     xyzs, ts, rays, counter = xyzs2, ts2, rays2, counter2
             sigmas, rgbs, num_points = self.point_decode([xyzs], None, code, m_dev=counter)
-            weights, weights_sum, depth, image = rm.composite_rays_train(sigmas, rgbs, ts, rays, 1e-4, False, counter)
+            weights, weights_sum, depth, image = rm.composite_rays_train(sigmas, rgbs, ts, rays, 1e-4, False, counter, fused_entropy)
             results = dict(weights=weights, weights_sum=weights_sum[None], depth=depth[None], image=image[None], rays=[rays], normal=None,
                            ts=[ts], num_samples=counter)
         elif self.training:
@@ -297,7 +300,7 @@ class iNGPDecoder(nn.Module):
                     rays2 = torch.empty_like(rays)
                     xyzs2, ts2 = torch.empty_like(xyzs), torch.empty_like(ts)
                     call('mve_cull_samples', ptr(w0), c_f32(self.weight_culling_th), ptr(rays), ptr(xyzs), ptr(ts), c_u32(N),
-                         c_u32(M), ptr(None), ptr(rays2), ptr(xyzs2), ptr(ts2), ptr(counter), stream())
+                         c_u32(M), ptr(None), c_u32(M), ptr(rays2), ptr(xyzs2), ptr(ts2), ptr(counter), stream())
                     M2 = int(counter.item())
                     xyzs, ts, rays, dirs = xyzs2[:M2], ts2[:M2], rays2, None
             sigmas, rgbs, num_points = self.point_decode([xyzs], [dirs], code)

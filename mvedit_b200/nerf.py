@@ -17,6 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .ingp_decoder import iNGPDecoder
+from ._lib import call, ptr, stream, get_lib, c_int, c_u32, c_f32
 
 
 # ------------------------------------------------------------------------------------------------ geometry
@@ -231,6 +232,35 @@ class BaseNeRF(nn.Module):
         return out_image, out_depth
 
 
+
+class _PatchLossFn(torch.autograd.Function):
+    """Fused objective of one nerf_optim iteration (libmvedit_b200: mve_nerf_patch_loss).  Returns the 5 loss terms
+    [total, rgb, alpha, normal_reg, background-entropy]; only element 0 is meant to be back-propagated."""
+
+    @staticmethod
+    def forward(ctx, image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps, shaded, ambient, bg_color, bg_width,
+                pixel_loss_weight, w_alpha_mul, w_normal_reg, w_entropy):
+        N = alpha.numel()
+        P = N // (ps * ps)
+        dev = alpha.device
+        f = lambda t: t.float().contiguous()
+        image, alpha, depth = f(image).view(N, 3), f(alpha).view(N), f(depth).view(N)
+        scratch = torch.empty(N * 10, dtype=torch.float32, device=dev)
+        g_image, g_alpha, g_depth = torch.empty(N, 3, device=dev), torch.empty(N, device=dev), torch.empty(N, device=dev)
+        loss5 = torch.empty(5, dtype=torch.float32, device=dev)
+        call('mve_nerf_patch_loss', ptr(image), ptr(alpha), ptr(depth), ptr(f(tgt_rgb)), ptr(f(tgt_mask)), ptr(f(dirs)), ptr(f(patch_w)),
+             ptr(f(lights)), c_u32(P), c_u32(ps), c_int(int(shaded)), c_f32(ambient), c_f32(bg_color), c_f32(bg_width), c_f32(pixel_loss_weight),
+             ptr(w_alpha_mul), ptr(w_normal_reg), ptr(w_entropy), ptr(scratch), ptr(g_image), ptr(g_alpha), ptr(g_depth), ptr(loss5), stream())
+        ctx.save_for_backward(g_image, g_alpha, g_depth)
+        return loss5
+
+    @staticmethod
+    def backward(ctx, g):
+        g_image, g_alpha, g_depth = ctx.saved_tensors
+        s = g[0]
+        return (g_image * s, g_alpha * s, g_depth * s) + (None,) * 14
+
+
 # ------------------------------------------------------------------------------------------------ nerf_optim
 def _patch_view(t, ps):
     """(1, V, h, w, C) -> non-materialised view (V, h/ps, w/ps, ps, ps, C): indexing it gathers only the chosen patches
@@ -308,6 +338,19 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
         target_lights = cam_lights[target_cam_ids][:, None, None, :].expand(-1, ps, ps, 3)
         dt_gamma = dt_gamma_scale / (intrinsics[target_cam_ids, :2].mean(dim=-1) * render_size / intrinsics_size)
 
+        if fused:
+            n_rays = rays_o.shape[1]
+            outputs = nerf.decoder(rays_o, rays_d, nerf_code, density_bitfield, nerf.grid_size, dt_gamma=dt_gamma, perturb=True,
+                                   fused_entropy=(sc['entropy'], 1.0 / n_rays))
+            terms = _PatchLossFn.apply(outputs['image'], outputs['weights_sum'], outputs['depth'], target_rgbs, target_m_blur, target_dir,
+                                       target_w[:, 0, 0, 0] / cam_weights_mean, cam_lights[target_cam_ids], ps, (not is_init) or init_shaded,
+                                       ambient_light, float(nerf.bg_color), bg_width, float(nerf.pixel_loss.loss_weight), sc['alpha_mul'],
+                                       sc['normal_reg'], sc['entropy'])
+            loss = terms[0]
+            optimizer.zero_grad(set_to_none=not use_graph)
+            loss.backward()
+            optimizer.step()
+            return terms.detach()
         outputs = nerf.decoder(rays_o, rays_d, nerf_code, density_bitfield, nerf.grid_size, dt_gamma=dt_gamma, perturb=True)
         out_rgbs = outputs['image'].reshape(target_rgbs.size())
         out_alphas = outputs['weights_sum'].reshape(target_m_blur.size())
@@ -360,6 +403,9 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
         optimizer.step()
         return torch.stack([loss.detach(), pixel_rgb_loss.detach(), alphas_loss.detach(), normal_reg_loss.detach(), entropy_loss.detach()])
 
+    # fused objective (4 kernels instead of ~300 eager ops + autograd) for the configuration it covers
+    fused = bool(getattr(nerf, 'fused_loss', True)) and tonemapping is None and not use_normal and not use_depth \
+        and not (patch_rgb_weight > 0 and nerf.patch_loss is not None) and nerf.decoder.sample_capacity > 0 and tgt_images.is_cuda
     use_graph = bool(getattr(nerf, 'use_cuda_graph', False)) and bool(optimizer.defaults.get('capturable', False)) \
         and nerf.decoder.sample_capacity > 0 and not debug
     with torch.enable_grad():

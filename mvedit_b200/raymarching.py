@@ -103,7 +103,7 @@ def packbits(grid, thresh, bitfield=None):
 # ----------------------------------------------------------------------------------------------
 
 def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars,
-                     perturb=False, dt_gamma=0, max_steps=1024, contract=False, noises=None, max_points=None):
+                     perturb=False, dt_gamma=0, max_steps=1024, contract=False, noises=None, max_points=None, zero_tail=True, want_dirs=True):
     """raymarching.py:232-311.  Returns xyzs [M,3], dirs [M,3], ts [M,2], rays int32 [N,2] = (offset, count).
 
     Reference protocol: count pass -> host reads M -> alloc -> write pass.  Here the count pass is the fused kernel
@@ -128,9 +128,10 @@ def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars,
     common = (ptr(rays_o), ptr(rays_d), ptr(density_bitfield), c_f32(bound), c_int(int(contract)), c_f32(dtg),
               c_u32(max_steps), c_u32(N), c_u32(C), c_u32(H), ptr(nears), ptr(fars), ptr(noises))
     if max_points is not None:
-        xyzs = torch.zeros(max_points, 3, dtype=torch.float32, device=dev)
-        dirs = torch.empty(max_points, 3, dtype=torch.float32, device=dev)
-        ts = torch.zeros(max_points, 2, dtype=torch.float32, device=dev)
+        alloc = torch.zeros if zero_tail else torch.empty
+        xyzs = alloc(max_points, 3, dtype=torch.float32, device=dev)
+        dirs = torch.empty(max_points, 3, dtype=torch.float32, device=dev) if want_dirs else None
+        ts = alloc(max_points, 2, dtype=torch.float32, device=dev)
         call('mve_march_rays_train', *common, ptr(xyzs), ptr(dirs), ptr(ts), c_u32(max_points), ptr(rays), ptr(counter),
              ptr(dt_gamma if isinstance(dt_gamma, torch.Tensor) else None), stream())
         return xyzs, dirs, ts, rays, counter
@@ -148,7 +149,7 @@ class _composite_rays_train(Function):
     """raymarching.py:314-368."""
 
     @staticmethod
-    def forward(ctx, sigmas, rgbs, ts, rays, T_thresh=1e-4, binarize=False, m_dev=None):
+    def forward(ctx, sigmas, rgbs, ts, rays, T_thresh=1e-4, binarize=False, m_dev=None, entropy=None):
         sigmas = sigmas.float().contiguous()
         rgbs = rgbs.float().contiguous()
         ts = ts.float().contiguous()
@@ -165,22 +166,26 @@ class _composite_rays_train(Function):
         ctx.save_for_backward(sigmas, rgbs, ts, rays, weights_sum, depth, image)
         ctx.dims = [M, N, T_thresh, binarize]
         ctx.m_dev = m_dev
+        ctx.entropy = entropy        # (device scalar weight, python scale) or None: fused sample-entropy gradient
+        if entropy is not None:
+            ctx.mark_non_differentiable(weights)      # its gradient is produced inside the backward kernel
+            ctx.set_materialize_grads(False)
         return weights, weights_sum, depth, image
 
     @staticmethod
     def backward(ctx, grad_weights, grad_weights_sum, grad_depth, grad_image):
-        grad_weights = grad_weights.float().contiguous()
-        grad_weights_sum = grad_weights_sum.float().contiguous()
-        grad_depth = grad_depth.float().contiguous()
-        grad_image = grad_image.float().contiguous()
         sigmas, rgbs, ts, rays, weights_sum, depth, image = ctx.saved_tensors
         M, N, T_thresh, binarize = ctx.dims
+        z = lambda g, like: torch.zeros_like(like) if g is None else g.float().contiguous()
+        grad_weights = None if (ctx.entropy is not None or grad_weights is None) else grad_weights.float().contiguous()
+        grad_weights_sum, grad_depth, grad_image = z(grad_weights_sum, weights_sum), z(grad_depth, depth), z(grad_image, image)
         grad_sigmas = torch.zeros_like(sigmas)
         grad_rgbs = torch.zeros_like(rgbs)
         call('mve_composite_rays_train_backward', ptr(grad_weights), ptr(grad_weights_sum), ptr(grad_depth), ptr(grad_image),
              ptr(sigmas), ptr(rgbs), ptr(ts), ptr(rays), ptr(weights_sum), ptr(depth), ptr(image), c_u32(M), ptr(ctx.m_dev), c_u32(N),
-             c_f32(T_thresh), c_int(int(binarize)), ptr(grad_sigmas), ptr(grad_rgbs), stream())
-        return grad_sigmas, grad_rgbs, None, None, None, None, None
+             c_f32(T_thresh), c_int(int(binarize)), ptr(ctx.entropy[0] if ctx.entropy else None),
+             c_f32(ctx.entropy[1] if ctx.entropy else 0.0), ptr(grad_sigmas), ptr(grad_rgbs), stream())
+        return grad_sigmas, grad_rgbs, None, None, None, None, None, None
 
 
 composite_rays_train = _composite_rays_train.apply
