@@ -262,6 +262,12 @@ def run_ours(args):
         one_step(False, phase_events)
     torch.cuda.synchronize()
     phases = {b[0]: round(a[1].elapsed_time(b[1]), 2) for a, b in zip(phase_events[:-1], phase_events[1:])}
+    rs = pipe.nerf.decoder.last_render_stats()
+    lc = [int(c.item()) for c in pipe.nerf.decoder.last_counts]
+    work = dict(render_samples_shaded=rs[0], render_lane_utilisation=round(rs[0] / max(rs[1] * 32, 1), 3), render_warp_rounds=rs[2],
+                render_shading_warp_rounds=rs[1], recon_last_iter_samples_marched=lc[0], recon_last_iter_samples_kept=lc[1],
+                occupied_cells=int((((bitfield.view(-1).to(torch.int32).unsqueeze(-1) >> torch.arange(8, device=device)) & 1).sum()).item()),
+                grid_cells=GRID ** 3)
     pipe.nerf.use_cuda_graph = graph_flag
     cat = {}
     for name, a, b, meta in prof:
@@ -296,7 +302,7 @@ def run_ours(args):
         roofline=dict(bound='tensor', kernel='k_gemm_tc (mve_gemm_bf16 + mve_conv3x3_bf16)', achieved=round(achieved, 1), peak=pk['tf_sustained'],
                       unit='TFLOP/s', frac=round(achieved / pk['tf_sustained'], 4), traffic=None, peak_source=pk['src'] + ' (sustained)',
                       launches_per_step=tc_n, share_of_step=round(tc_ms / total_prof_ms, 3) if total_prof_ms else None),
-        phase_ms=phases, init_recon_640_iters_s=round(init_s, 2),
+        phase_ms=phases, init_recon_640_iters_s=round(init_s, 2), work=work,
         kernel_breakdown_ms=breakdown,
     )
     if world == 1:

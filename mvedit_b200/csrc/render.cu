@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
 
     bool have_ray = false;
     bool exhausted = false;      // warp-uniform
-    uint32_t n = 0, step = 0, shaded = 0;
+    uint32_t n = 0, step = 0, shaded = 0, shade_rounds = 0, rounds = 0;
     Ray r;
     float t = 0.f, far = 0.f, ws = 0.f, dsum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
     bool terminated = false;
@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
             }
         }
         if (!__any_sync(0xffffffffu, have_ray)) break;     // nothing in flight and nothing left to fetch
+        rounds++;
         // ---------------- 2. bounded search for the next sample
         bool has = false;
 #pragma unroll 1
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
         }
         // ---------------- 3. shade
         if (__any_sync(0xffffffffu, has)) {
+            shade_rounds++;
             if (has) {
                 t += dt;
                 float enc[R::IN];
@@ -163,7 +165,11 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
     // statistics: samples shaded (one atomic per warp)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) shaded += __shfl_xor_sync(0xffffffffu, shaded, o);
-    if (lane == 0 && shaded) atomicAdd(stats, (unsigned long long)shaded);
+    if (lane == 0) {
+        if (shaded) atomicAdd(stats, (unsigned long long)shaded);
+        atomicAdd(stats + 1, (unsigned long long)shade_rounds);     // warp-rounds that shaded (x32 = lane slots)
+        atomicAdd(stats + 2, (unsigned long long)rounds);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -264,9 +270,9 @@ extern "C" {
 
 int mve_render_last_sample_count(uint64_t* host_out) {
     MVE_ARG(host_out != nullptr, "render_last_sample_count: null output");
-    *host_out = 0;
+    host_out[0] = host_out[1] = host_out[2] = 0;
     if (!g_render_scratch) return 0;
-    MVE_CUDA(cudaMemcpy(host_out, g_render_scratch + 8, 8, cudaMemcpyDeviceToHost));   // synchronises: statistics only
+    MVE_CUDA(cudaMemcpy(host_out, g_render_scratch + 8, 24, cudaMemcpyDeviceToHost));   // synchronises: statistics only
     return 0;
 }
 
@@ -292,8 +298,8 @@ int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses
     const float2* t2 = reinterpret_cast<const float2*>(table);
     cudaStream_t s = (cudaStream_t)stream;
     // one process drives one GPU: process-wide scratch = [work counter (u32) | pad | samples shaded (u64)]
-    if (!g_render_scratch) MVE_CUDA(cudaMalloc(&g_render_scratch, 16));
-    MVE_CUDA(cudaMemsetAsync(g_render_scratch, 0, 16, s));
+    if (!g_render_scratch) MVE_CUDA(cudaMalloc(&g_render_scratch, 32));
+    MVE_CUDA(cudaMemsetAsync(g_render_scratch, 0, 32, s));
     unsigned int* next_ray = reinterpret_cast<unsigned int*>(g_render_scratch);
     unsigned long long* stats = reinterpret_cast<unsigned long long*>(g_render_scratch + 8);
     if (n_levels == 12) k_render_rays<12><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);

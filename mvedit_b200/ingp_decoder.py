@@ -264,6 +264,7 @@ class iNGPDecoder(nn.Module):
                                                                 dt_gamma=dt_gamma_t if dt_gamma_t is not None else dt_gamma,
                                                                 max_steps=self.max_steps, noises=noises, max_points=cap1,
                                                                 zero_tail=not self.weight_culling_th > 0, want_dirs=False)
+            counter1 = counter
             if self.weight_culling_th > 0:
                 with torch.no_grad():
                     sig0, _, _ = self.point_decode([xyzs], None, code, density_only=True, m_dev=counter)
@@ -280,6 +281,7 @@ class iNGPDecoder(nn.Module):
                     xyzs, ts, rays, counter = xyzs2, ts2, rays2, counter2
             sigmas, rgbs, num_points = self.point_decode([xyzs], None, code, m_dev=counter)
             weights, weights_sum, depth, image = rm.composite_rays_train(sigmas, rgbs, ts, rays, 1e-4, False, counter, fused_entropy)
+            self.last_counts = (counter1, counter)       # device counters: marched / kept samples of the last training forward
             results = dict(weights=weights, weights_sum=weights_sum[None], depth=depth[None], image=image[None], rays=[rays], normal=None,
                            ts=[ts], num_samples=counter)
         elif self.training:
@@ -322,6 +324,14 @@ class iNGPDecoder(nn.Module):
         if return_loss:
             results.update(decoder_reg_loss=self.loss())
         return results
+
+    @staticmethod
+    def last_render_stats():
+        """(samples shaded, warp-rounds that shaded, warp-rounds) of the most recent fused render launch (synchronises)."""
+        import ctypes as _c
+        buf = (_c.c_uint64 * 3)()
+        call('mve_render_last_sample_count', buf)
+        return int(buf[0]), int(buf[1]), int(buf[2])
 
     def render_cameras(self, poses, intrinsics, h, w, density_bitfield, grid_size, dt_gamma=0.0):
         """Fused BaseNeRF.render core (base_nerf.py:489-556): rays are generated inside the kernel from (pose, intrinsics, pixel).

@@ -244,6 +244,7 @@ class _PatchLossFn(torch.autograd.Function):
         P = N // (ps * ps)
         dev = alpha.device
         f = lambda t: t.float().contiguous()
+        ctx.shapes = (image.shape, alpha.shape, depth.shape)
         image, alpha, depth = f(image).view(N, 3), f(alpha).view(N), f(depth).view(N)
         scratch = torch.empty(N * 10, dtype=torch.float32, device=dev)
         g_image, g_alpha, g_depth = torch.empty(N, 3, device=dev), torch.empty(N, device=dev), torch.empty(N, device=dev)
@@ -258,7 +259,8 @@ class _PatchLossFn(torch.autograd.Function):
     def backward(ctx, g):
         g_image, g_alpha, g_depth = ctx.saved_tensors
         s = g[0]
-        return (g_image * s, g_alpha * s, g_depth * s) + (None,) * 14
+        si, sa, sd = ctx.shapes
+        return ((g_image * s).view(si), (g_alpha * s).view(sa), (g_depth * s).view(sd)) + (None,) * 14
 
 
 # ------------------------------------------------------------------------------------------------ nerf_optim
