@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(NUM_THREADS_A, 1) k_attention(const __grid_con
 
 // ------------------------------------------------------------------------------------------------------------------
 // Ping-pong variant for head dims <= 64 (one 64-wide atom): one CTA owns TWO 128-row query tiles (A, B) of the same (batch, head).
-// 10 warps: 0-3 softmax A, 4-7 softmax B, 8 MMA issuer, 9 TMA producer.  While the softmax warps of tile A work on S_A(j), the tensor
+// 18 warps: 0-7 softmax A, 8-15 softmax B (two warps per TMEM lane quadrant, 64 key columns each), 16 MMA issuer, 17 TMA producer.  While the softmax warps of tile A work on S_A(j), the tensor
 // core runs Q_B K_j^T / P_B V_j and vice versa, so softmax (MUFU / FMA pipes) and MMA overlap inside one SM, and every K/V tile
 // fetched by TMA is used by both query tiles.  TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
 // ------------------------------------------------------------------------------------------------------------------
@@ -273,23 +273,25 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <int DPAD>
-__global__ void __launch_bounds__(320, 1) k_attention_pp(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+__global__ void __launch_bounds__(576, 1) k_attention_pp(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                          const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
     static_assert(DPAD <= 64, "ping-pong kernel: one 64-wide head-dim atom");
     constexpr int ST = 2;
     constexpr uint32_t O_COL0 = 256, O_COL1 = 320;
+    constexpr int NCH = DPAD / 16;                 // 16-column chunks of O
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;                          // [2][ATOM]
     uint8_t* sK = sQ + 2 * ATOM_BYTES;           // [ST][ATOM]
     uint8_t* sV = sK + ST * ATOM_BYTES;          // [ST][ATOM]
     uint8_t* sP = sV + ST * ATOM_BYTES;          // [2][2*ATOM]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATOM_BYTES);
+    float* xch = reinterpret_cast<float*>(sP + 4 * ATOM_BYTES);   // [2 parity][2 tiles][2 halves][128] row-max exchange (+ final row sums)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 2 * 2 * 128);
     uint64_t* bar_q = bars;               // 1
     uint64_t* kv_full = bars + 1;         // [2]
     uint64_t* kv_empty = bars + 3;        // [2]
     uint64_t* s_full = bars + 5;          // [2 tiles]
-    uint64_t* p_full = bars + 7;          // [2 tiles], 128 arrivals
+    uint64_t* p_full = bars + 7;          // [2 tiles], 256 arrivals
     uint64_t* pv_done = bars + 9;         // [2 tiles]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
@@ -297,22 +299,22 @@ __global__ void __launch_bounds__(320, 1) k_attention_pp(const __grid_constant__
     const uint32_t qb = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
     const uint32_t nblk = p.n_kv_blocks;
 
-    if (warp == 9 && lane == 0) {
+    if (warp == 17 && lane == 0) {
         tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV);
         tc::mbar_init(bar_q, 1);
         for (int s = 0; s < 2; s++) {
             tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1);
-            tc::mbar_init(&s_full[s], 1); tc::mbar_init(&p_full[s], 128); tc::mbar_init(&pv_done[s], 1);
+            tc::mbar_init(&s_full[s], 1); tc::mbar_init(&p_full[s], 256); tc::mbar_init(&pv_done[s], 1);
         }
         tc::fence_barrier_init();
     }
-    if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+    if (warp == 16) tc::tmem_alloc(tmem_slot, 512);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 9) {
+    if (warp == 17) {
         if (lane == 0) {
             tc::mbar_arrive_expect_tx(bar_q, 2 * ATOM_BYTES);
             tc::tma_load_4d(sQ, &tmQ, bar_q, 0, head, qb * 256, batch);
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(320, 1) k_attention_pp(const __grid_constant__
                 if (++stage == ST) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == 16) {
         if (lane == 0) {
             constexpr uint32_t idesc_qk = tc::make_idesc_bf16(128, BKV, false, false);
             constexpr uint32_t idesc_pv = tc::make_idesc_bf16(128, DPAD, false, true);
@@ -370,22 +372,26 @@ __global__ void __launch_bounds__(320, 1) k_attention_pp(const __grid_constant__
             }
         }
     } else {
-        const uint32_t tile = warp >> 2;
-        const uint32_t row = (warp & 3) * 32 + lane;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t s_addr = lane_addr + tile * 128;
+        // 16 softmax warps: tile = warp / 8; inside a tile two warps share each TMEM lane quadrant and split the 128 key columns
+        const uint32_t tile = warp >> 3, w8 = warp & 7, quad = w8 & 3, half = w8 >> 2;
+        const uint32_t row = quad * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const uint32_t s_addr = lane_addr + tile * 128 + half * 64;
         const uint32_t o_addr = lane_addr + (tile ? O_COL1 : O_COL0);
+        constexpr int C0 = 0, C1 = (NCH + 1) / 2;                  // O chunks [C0,C1) -> half 0, [C1,NCH) -> half 1
+        const int oc_lo = half ? C1 : C0, oc_hi = half ? NCH : C1;
         float m = -INFINITY, l = 0.f;
-        uint8_t* prow = sP + tile * 2 * ATOM_BYTES + row * 128;
+        uint8_t* prow = sP + tile * 2 * ATOM_BYTES + half * ATOM_BYTES + row * 128;
         const uint32_t sw = row & 7;
         for (uint32_t j = 0; j < nblk; j++) {
             tc::mbar_wait(&s_full[tile], j & 1);
             tc::tc_fence_after();
             const uint32_t kv_valid = min((uint32_t)BKV, p.kv_len - j * BKV);
             const bool full_blk = kv_valid == BKV;
+            const uint32_t col0 = half * 64;
             float mx = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < BKV; c += 32) {
+            for (int c = 0; c < 64; c += 32) {
                 uint32_t v[32];
                 tc::tmem_ld32(s_addr + c, v);
                 tc::tmem_ld_wait();
@@ -395,9 +401,13 @@ __global__ void __launch_bounds__(320, 1) k_attention_pp(const __grid_constant__
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; i++)
-                        if ((uint32_t)(c + i) < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                        if (col0 + c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
                 }
             }
+            float* xm = xch + (((j & 1) * 2 + tile) * 2) * 128;
+            xm[half * 128 + row] = mx;
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + (int)tile) : "memory");
+            mx = fmaxf(mx, xm[(half ^ 1) * 128 + row]);
             const float m_new = fmaxf(m, mx * p.scale_log2);
             const float alpha = ex2_approx(m - m_new);
             if (j > 0) {
@@ -405,20 +415,20 @@ __global__ void __launch_bounds__(320, 1) k_attention_pp(const __grid_constant__
                 tc::tc_fence_after();
                 if (__any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
-                    for (int c = 0; c < DPAD; c += 16) {
+                    for (int c = oc_lo; c < oc_hi; c++) {
                         uint32_t v[16];
-                        tc::tmem_ld16(o_addr + c, v);
+                        tc::tmem_ld16(o_addr + c * 16, v);
                         tc::tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                        tmem_st16(o_addr + c, v);
+                        tmem_st16(o_addr + c * 16, v);
                     }
                     tmem_st_wait();
                 }
             }
             float lsum = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < BKV; c += 32) {
+            for (int c = 0; c < 64; c += 32) {
                 uint32_t v[32];
                 tc::tmem_ld32(s_addr + c, v);
                 tc::tmem_ld_wait();
@@ -428,19 +438,17 @@ __global__ void __launch_bounds__(320, 1) k_attention_pp(const __grid_constant__
                     float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
                     float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_new));
                     if (!full_blk) {
-                        if ((uint32_t)(c + i) >= kv_valid) p0 = 0.f;
-                        if ((uint32_t)(c + i + 1) >= kv_valid) p1 = 0.f;
+                        if (col0 + c + i >= kv_valid) p0 = 0.f;
+                        if (col0 + c + i + 1 >= kv_valid) p1 = 0.f;
                     }
                     const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-                    const float2 back = __bfloat1622float2(b2);
-                    lsum += back.x + back.y;
+                    lsum += p0 + p1;
                     pk[i / 2] = *reinterpret_cast<const uint32_t*>(&b2);
                 }
-                uint8_t* base = prow + (c / 64) * ATOM_BYTES;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const uint32_t chunk = ((c % 64) / 8 + q) ^ sw;
-                    *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    const uint32_t chunk = (c / 8 + q) ^ sw;
+                    *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
             }
             l = l * alpha + lsum;
@@ -449,13 +457,19 @@ __global__ void __launch_bounds__(320, 1) k_attention_pp(const __grid_constant__
             tc::tc_fence_before();
             tc::mbar_arrive(&p_full[tile]);
         }
+        // combine the two halves' row sums, then O / l -> bf16 -> global (each half stores its O chunks)
+        float* xs = xch + (((nblk & 1) * 2 + tile) * 2) * 128;
+        xs[half * 128 + row] = l;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + (int)tile) : "memory");
+        l += xs[(half ^ 1) * 128 + row];
         tc::mbar_wait(&pv_done[tile], (nblk - 1) & 1);
         tc::tc_fence_after();
         const uint32_t qrow = qb * 256 + tile * 128 + row;
         const float inv_l = 1.0f / l;
         __nv_bfloat16* out = p.O + ((size_t)batch * p.q_len + qrow) * p.ldo + head * p.d;
 #pragma unroll 1
-        for (int c = 0; c < DPAD; c += 16) {
+        for (int cc = oc_lo; cc < oc_hi; cc++) {
+            const int c = cc * 16;
             uint32_t v[16];
             tc::tmem_ld16(o_addr + c, v);
             tc::tmem_ld_wait();
@@ -477,7 +491,7 @@ __global__ void __launch_bounds__(320, 1) k_attention_pp(const __grid_constant__
 
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 16) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
     }
@@ -486,14 +500,14 @@ __global__ void __launch_bounds__(320, 1) k_attention_pp(const __grid_constant__
 template <int DPAD>
 int launch_attn_pp(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, uint32_t heads, uint32_t batch,
                    cudaStream_t s) {
-    constexpr int SMEM = ATOM_BYTES * (2 + 2 + 2 + 4) + 1024 + 256;
+    constexpr int SMEM = ATOM_BYTES * (2 + 2 + 2 + 4) + 2 * 2 * 2 * 128 * 4 + 1024 + 256;
     static bool configured = false;
     if (!configured) {
         MVE_CUDA(cudaFuncSetAttribute(k_attention_pp<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
     }
     const dim3 grid((p.q_len + 255) / 256, heads, batch);
-    k_attention_pp<DPAD><<<grid, 320, SMEM, s>>>(tq, tk, tv, p);
+    k_attention_pp<DPAD><<<grid, 576, SMEM, s>>>(tq, tk, tv, p);
     MVE_CHECK_LAUNCH("k_attention_pp");
     return 0;
 }

@@ -4,7 +4,8 @@
 //   warp 0     TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1     MMA issuer     (one elected lane: tcgen05.mma kind::f16, M=128, N=BN, K=16; fp32 accumulators in TMEM,
 //                              two accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1)
-//   warps 2-5  epilogue       (tcgen05.ld 32x32b -> bias / per-image bias / activation / scale / residual -> bf16 -> global)
+//   warps 2-9  epilogue       (tcgen05.ld 32x32b -> bias / per-image bias / activation / scale / residual -> bf16 -> global;
+//                              two warps per TMEM lane quadrant take alternate 32-column chunks)
 //
 //   C[M,N] = epi( A[M,K] . B[N,K]^T )       A, B bf16 K-major (row-major with K contiguous), C bf16 row-major.
 //
@@ -21,7 +22,7 @@
 namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warps per TMEM lane quadrant, interleaved column chunks)
 constexpr int A_BYTES = BM * BK * 2;
 
 struct GemmParams {
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
         tc::prefetch_tmap(&tmA);
         tc::prefetch_tmap(&tmB);
         for (int s = 0; s < C_::STAGES; s++) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; s++) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 2; s++) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], 8); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, C_::TMEM_COLS);
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
     } else {
         // ------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;     // 0: even column chunks, 1: odd column chunks
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const uint32_t mt = tile / p.n_tiles, nt = tile % p.n_tiles;
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
             const float* rb = (p.row_bias && row_ok) ? p.row_bias + (size_t)(row / p.rows_per_group) * p.ldrb : nullptr;
             constexpr int CH = (BN >= 32) ? 32 : 16;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += CH) {
+            for (int c = half * CH; c < BN; c += 2 * CH) {
                 uint32_t v[32];
                 if (CH == 32) {
                     tc::tmem_ld32(t_row + c, v);
