@@ -136,6 +136,8 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t B, uint32_
  * lib/ops/activation.py:8-23).  level_* are HOST arrays of n_levels entries (scale, resolution, entries, entry offset);
  * table [n_entries,2] f32; w1 [64,2L], b1 [64], w2 [4,64], b2 [4] f32 (nn.Linear layout).
  * M_dev (optional, device): actual sample count <= M.
+ * density_only: 0 = sigma+rgb (fp32 FFMA MLP), 1 = sigma only (fp32), 2 = sigma only with the MLP on tensor cores in TF32 -- the
+ * reference's own matmul precision (allow_tf32) -- used for the culling pre-pass.
  * ------------------------------------------------------------------------- */
 int mve_field_forward(const float* xyz, uint32_t M, const int32_t* M_dev, const float* table,
                       const float* w1, const float* b1, const float* w2, const float* b2,

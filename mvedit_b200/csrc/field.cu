@@ -13,6 +13,7 @@
 // second tiny kernel sums in a fixed order (deterministic MLP gradients; the table scatter is atomic like tcnn's).
 // Optionally d/d xyz (needed by the DMTet stage, base_mesh_renderer.py:277-283).
 #include "field_device.cuh"
+#include "mlp_mma.cuh"
 #include "../../include/mvedit_b200.h"
 
 using namespace field;
@@ -55,6 +56,41 @@ __global__ void __launch_bounds__(256) k_field_fwd(const float* __restrict__ xyz
             rgb[(size_t)i * 3 + 1] = fmaf(1.f / (1.f + __expf(-o2)), cfg.sat_scale, cfg.sat_shift);
             rgb[(size_t)i * 3 + 2] = fmaf(1.f / (1.f + __expf(-o3)), cfg.sat_scale, cfg.sat_shift);
         }
+    }
+}
+
+// Density-only decode of the training pre-pass (point_density_decode before weight culling, base_volume_renderer.py:222-227): the MLP
+// runs on tensor cores (mlp_mma.cuh, TF32 like the reference's matmuls); its output only decides which samples survive the cull.
+template <int L>
+__global__ void __launch_bounds__(128) k_field_density_mma(const float* __restrict__ xyz, uint32_t M, const int* __restrict__ M_dev,
+                                                           const float2* __restrict__ table, const float* __restrict__ w1,
+                                                           const float* __restrict__ b1, const float* __restrict__ w2,
+                                                           const float* __restrict__ b2, const Levels lv, const FieldCfg cfg,
+                                                           float* __restrict__ sigma) {
+    using R = Rec<L>;
+    using MC = mlpmma::Cfg<L>;
+    __shared__ __align__(16) float frags[MC::FRAG_FLOATS];
+    __shared__ __align__(16) float stage[4][MC::STAGE_FLOATS];
+    mlpmma::stage_frags<L>(frags, w1, b1, w2);
+    __syncthreads();
+    if (M_dev) M = min(M, (uint32_t)*M_dev);
+    const float ob0 = b2[0];
+    const uint32_t lane = threadIdx.x & 31, warp_g = blockIdx.x * 4 + (threadIdx.x >> 5), n_warps = gridDim.x * 4;
+    for (uint32_t base = warp_g * 32; base < M; base += n_warps * 32) {      // warp-uniform trip count
+        const uint32_t i = base + lane;
+        const bool live = i < M;
+        float x = 0.f, y = 0.f, z = 0.f;
+        float enc[R::IN];
+        if (live) {
+            x = xyz[(size_t)i * 3]; y = xyz[(size_t)i * 3 + 1]; z = xyz[(size_t)i * 3 + 2];
+            encode<L>(lv, table, (x + cfg.bound) * cfg.inv2b, (y + cfg.bound) * cfg.inv2b, (z + cfg.bound) * cfg.inv2b, enc);
+        } else {
+#pragma unroll
+            for (int q = 0; q < R::IN; q++) enc[q] = 0.f;
+        }
+        float o[4];
+        mlpmma::mlp_forward<L>(enc, stage[threadIdx.x >> 5], frags, o);
+        if (live) sigma[i] = __expf(o[0] + ob0 + blob_of(cfg, x, y, z));
     }
 }
 
@@ -323,10 +359,13 @@ int mve_field_forward(const float* xyz, uint32_t M, const int32_t* M_dev, const 
     const FieldCfg cfg = make_cfg(bound, blob_density, blob_radius, sigmoid_saturation);
     uint32_t grid = cdiv(M, 256);
     if (grid > (uint32_t)(8 * kNumSM)) grid = 8 * kNumSM;
+    uint32_t grid2 = cdiv(M, 128);
+    if (grid2 > (uint32_t)(8 * kNumSM)) grid2 = 8 * kNumSM;
     const float2* t2 = reinterpret_cast<const float2*>(table);
     cudaStream_t s = (cudaStream_t)stream;
 #define FWD(LL)                                                                                                                          \
-    if (density_only) k_field_fwd<LL, true><<<grid, 256, 0, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, sigma, rgb);                \
+    if (density_only == 2) k_field_density_mma<LL><<<grid2, 128, 0, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, sigma);             \
+    else if (density_only) k_field_fwd<LL, true><<<grid, 256, 0, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, sigma, rgb);           \
     else k_field_fwd<LL, false><<<grid, 256, 0, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, sigma, rgb);
     if (n_levels == 12) { FWD(12) } else if (n_levels == 14) { FWD(14) } else { FWD(16) }
 #undef FWD

@@ -18,12 +18,18 @@ struct FieldCfg {
     float bound, inv2b, blob_density, blob_k, sat_scale, sat_shift;
 };
 
+// grid.h grid_index: dense levels index linearly, hashed levels use the coherent prime hash; both end in `% size`.
+// A generic integer modulo costs ~20 instructions and there are 96 of them per sample, so it is specialised (same result):
+//   hashed: size is a power of two for every config the reference builds (2^19) -> mask;  otherwise the generic modulo;
+//   dense : idx <= res^3 + res^2 + res < 2 * size, so one conditional subtraction is the exact modulo.
 __device__ __forceinline__ uint32_t grid_index(const bool hashed, const uint32_t res, const uint32_t size, const uint32_t cx, const uint32_t cy,
                                                const uint32_t cz) {
-    uint32_t idx;
-    if (hashed) idx = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
-    else idx = cx + cy * res + cz * res * res;
-    return idx % size;
+    if (hashed) {
+        const uint32_t idx = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
+        return ((size & (size - 1)) == 0) ? (idx & (size - 1)) : (idx % size);
+    }
+    const uint32_t idx = cx + cy * res + cz * res * res;
+    return idx >= size ? idx - size : idx;
 }
 
 // positional part of one level: base cell, smoothstep weights and their derivatives

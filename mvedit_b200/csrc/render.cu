@@ -12,6 +12,7 @@
 //   keeps samples with weight > th, warp-per-ray ballot compaction, CTA scan + one atomic for the new offsets.
 #include "march_device.cuh"
 #include "field_device.cuh"
+#include "mlp_mma.cuh"
 #include "../../include/mvedit_b200.h"
 
 using namespace march;
@@ -53,61 +54,6 @@ struct RenderParams {
     const float* dt_gamma_per_view;  // [V] or null (then march.dt_gamma is used)
 };
 
-// Hash-grid gather with a per-thread cache of the last cell of every HASHED level (shared memory, [level][corner][thread]).
-// Consecutive samples along a ray are dt ~ 0.0034 apart while hashed cells are 0.006 .. 0.024 wide, so a thread re-enters the same
-// cell on 25-80 % of its steps; the 8 corner fetches of such a level are random 32-byte L2 sectors (no spatial locality after the
-// hash) and dominate the renderer's memory traffic.  Dense levels stay on the L1/L2 path (their corners are spatially coherent).
-constexpr int MAX_HASHED = 4;   // the 4 coarsest hashed levels (highest re-entry rate); 35 KB per CTA keeps 5 CTAs per SM
-struct CornerCache {
-    uint32_t* cell;   // [MAX_HASHED][threads]
-    float2* val;      // [MAX_HASHED][8][threads]
-    uint32_t nthreads, tid;
-};
-
-template <int L>
-__device__ __forceinline__ void encode_cached(const Levels& lv, const float2* __restrict__ table, const float x0, const float x1, const float x2,
-                                              float (&enc)[2 * L], const CornerCache& cc) {
-    int hl = 0;
-#pragma unroll
-    for (int l = 0; l < L; l++) {
-        const Cell c = locate(x0, x1, x2, lv.scale[l]);
-        const bool hashed = (lv.hashed >> l) & 1u;
-        const uint32_t res = lv.res[l], size = lv.size[l];
-        const float2* __restrict__ t = table + lv.off[l];
-        float2 v[8];
-        if (hashed && hl < MAX_HASHED) {
-            const uint32_t key = c.g[0] | (c.g[1] << 10) | (c.g[2] << 20);
-            uint32_t* ck = cc.cell + hl * cc.nthreads + cc.tid;
-            float2* cv = cc.val + (size_t)hl * 8 * cc.nthreads + cc.tid;
-            if (*ck == key) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = cv[k * cc.nthreads];
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; k++)
-                    v[k] = __ldg(t + grid_index(true, res, size, c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + (k >> 2)));
-#pragma unroll
-                for (int k = 0; k < 8; k++) cv[k * cc.nthreads] = v[k];
-                *ck = key;
-            }
-            hl++;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                v[k] = __ldg(t + grid_index(hashed, res, size, c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + (k >> 2)));
-        }
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const float wgt = ((k & 1) ? c.w[0] : 1.f - c.w[0]) * ((k & 2) ? c.w[1] : 1.f - c.w[1]) * ((k & 4) ? c.w[2] : 1.f - c.w[2]);
-            a0 = fmaf(wgt, v[k].x, a0);
-            a1 = fmaf(wgt, v[k].y, a1);
-        }
-        enc[2 * l] = a0;
-        enc[2 * l + 1] = a1;
-    }
-}
-
 // Round-based lane scheduling.  Every round (all steps converged except the bounded DDA loop):
 //   1. lanes without a ray fetch the next one with ONE warp-aggregated atomic,
 //   2. every lane without a sample advances its DDA by at most DDA_BUDGET voxel steps (retiring the ray if it ends); the loop
@@ -123,15 +69,10 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
                                                      const float* __restrict__ b2, const Levels lv, const FieldCfg cfg,
                                                      unsigned int* __restrict__ next_ray, unsigned long long* __restrict__ stats) {
     using R = Rec<L>;
-    __shared__ __align__(16) float rec[HID * R::STRIDE];
-    extern __shared__ __align__(16) uint8_t dyn_smem[];     // corner cache: [MAX_HASHED][8][128] float2 + [MAX_HASHED][128] u32
-    stage_mlp<L>(rec, w1, b1, w2);
-    CornerCache cc;
-    cc.val = reinterpret_cast<float2*>(dyn_smem);
-    cc.cell = reinterpret_cast<uint32_t*>(dyn_smem + (size_t)MAX_HASHED * 8 * 128 * sizeof(float2));
-    cc.nthreads = 128; cc.tid = threadIdx.x;
-#pragma unroll
-    for (int hl = 0; hl < MAX_HASHED; hl++) cc.cell[hl * 128 + threadIdx.x] = 0xFFFFFFFFu;
+    using MC = mlpmma::Cfg<L>;
+    __shared__ __align__(16) float frags[MC::FRAG_FLOATS];
+    __shared__ __align__(16) float stage[4][MC::STAGE_FLOATS];
+    mlpmma::stage_frags<L>(frags, w1, b1, w2);
     __syncthreads();
     const float ob0 = b2[0], ob1 = b2[1], ob2 = b2[2], ob3 = b2[3];
     const int lane = threadIdx.x & 31;
@@ -203,12 +144,18 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
         // ---------------- 3. shade
         if (__any_sync(0xffffffffu, has)) {
             shade_rounds++;
+            float enc[R::IN];
             if (has) {
                 t += dt;
-                float enc[R::IN];
-                encode_cached<L>(lv, table, (cx + cfg.bound) * cfg.inv2b, (cy + cfg.bound) * cfg.inv2b, (cz + cfg.bound) * cfg.inv2b, enc, cc);
-                float o0 = ob0, o1 = ob1, o2 = ob2, o3 = ob3;
-                mlp_forward<L, false>(rec, enc, o0, o1, o2, o3);
+                encode<L>(lv, table, (cx + cfg.bound) * cfg.inv2b, (cy + cfg.bound) * cfg.inv2b, (cz + cfg.bound) * cfg.inv2b, enc);
+            } else {
+#pragma unroll
+                for (int q = 0; q < R::IN; q++) enc[q] = 0.f;
+            }
+            float o[4];
+            mlpmma::mlp_forward<L>(enc, stage[threadIdx.x >> 5], frags, o);     // tensor cores, all 32 lanes participate
+            if (has) {
+                const float o0 = o[0] + ob0, o1 = o[1] + ob1, o2 = o[2] + ob2, o3 = o[3] + ob3;
                 const float sigma = __expf(o0 + blob_of(cfg, cx, cy, cz));
                 // kernel_composite_rays (raymarching.cu:878-903): T = 1 - weight_sum, the ray dies after accumulating the sample
                 const float alpha = 1.0f - __expf(-sigma * dt);
@@ -364,17 +311,9 @@ int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses
     MVE_CUDA(cudaMemsetAsync(g_render_scratch, 0, 32, s));
     unsigned int* next_ray = reinterpret_cast<unsigned int*>(g_render_scratch);
     unsigned long long* stats = reinterpret_cast<unsigned long long*>(g_render_scratch + 8);
-    constexpr size_t CACHE_SMEM = (size_t)MAX_HASHED * 128 * (8 * sizeof(float2) + sizeof(uint32_t));   // 35 KB
-    static bool configured = false;
-    if (!configured) {
-        MVE_CUDA(cudaFuncSetAttribute(k_render_rays<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CACHE_SMEM));
-        MVE_CUDA(cudaFuncSetAttribute(k_render_rays<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CACHE_SMEM));
-        MVE_CUDA(cudaFuncSetAttribute(k_render_rays<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CACHE_SMEM));
-        configured = true;
-    }
-    if (n_levels == 12) k_render_rays<12><<<grid, 128, CACHE_SMEM, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);
-    else if (n_levels == 14) k_render_rays<14><<<grid, 128, CACHE_SMEM, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);
-    else k_render_rays<16><<<grid, 128, CACHE_SMEM, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);
+    if (n_levels == 12) k_render_rays<12><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);
+    else if (n_levels == 14) k_render_rays<14><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);
+    else k_render_rays<16><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);
     MVE_CHECK_LAUNCH("mve_render_rays");
     return 0;
 }

@@ -267,7 +267,7 @@ class iNGPDecoder(nn.Module):
             counter1 = counter
             if self.weight_culling_th > 0:
                 with torch.no_grad():
-                    sig0, _, _ = self.point_decode([xyzs], None, code, density_only=True, m_dev=counter)
+                    sig0, _, _ = self.point_decode([xyzs], None, code, density_only=2, m_dev=counter)   # TF32 tensor-core MLP
                     w0 = torch.empty(cap1, dtype=torch.float32, device=xyzs.device)
                     scratch = torch.empty(N * 5, dtype=torch.float32, device=xyzs.device)
                     call('mve_composite_rays_train_forward', ptr(sig0), ptr(None), ptr(ts), ptr(rays), c_u32(cap1), ptr(counter), c_u32(N),

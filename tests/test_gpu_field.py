@@ -77,6 +77,21 @@ def test_field_forward_backward_vs_oracle(L, R):
     close(xg.grad, xo.grad, 5e-3)   # d/dxyz (DMTet stage)
 
 
+def test_density_prepass_tf32_tensor_core_mlp():
+    """density_only=2 (culling pre-pass): MLP via mma.sync TF32; vs the fp32 oracle within TF32 precision."""
+    from mvedit_b200.ingp_decoder import _FieldFn
+    dec, levels, params = make_decoder(table_scale=1.0)
+    g = torch.Generator().manual_seed(11)
+    xyz = (torch.rand(5000, 3, generator=g) * 2 - 1)
+    with torch.no_grad():
+        so, _ = fo.point_decode(xyz, *params, levels)
+        s2, _ = _FieldFn.apply(xyz.cuda(), *dec._field_params(), dec, 2)
+        s1, _ = _FieldFn.apply(xyz.cuda(), *dec._field_params(), dec, 1)
+    np.testing.assert_allclose(s1.cpu().numpy(), so.numpy(), rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(s2.cpu().numpy(), so.numpy(), rtol=5e-3, atol=1e-5)
+    assert np.abs(s2.cpu().numpy() / so.numpy() - 1).mean() < 1e-3
+
+
 def test_field_empty_and_tiny():
     dec, levels, params = make_decoder()
     s, r, n = dec.point_decode([torch.zeros(0, 3, device='cuda')], None, None)
@@ -118,16 +133,18 @@ def test_fused_render_vs_oracle_loop():
     out = dec(torch.from_numpy(ro).cuda()[None], torch.from_numpy(rd).cuda()[None], None, torch.from_numpy(bitfield).cuda()[None], H,
               dt_gamma=1 / f, perturb=False)
     assert ws.max() > 0.5
-    ok = np.abs(out['weights_sum'][0].cpu().numpy() - ws) < 2e-3
+    # The fused renderer evaluates the MLP on tensor cores in TF32 (10-bit mantissa) -- the reference's own matmul precision
+    # (allow_tf32=True) -- while the oracle is fp32: per-sample sigma/rgb differ by ~1e-3 relative, composited sums by less.
+    ok = np.abs(out['weights_sum'][0].cpu().numpy() - ws) < 5e-3
     assert ok.mean() > 0.995   # a march cell flipped by 1 ulp changes a whole ray; the rest must agree tightly
-    np.testing.assert_allclose(out['weights_sum'][0].cpu().numpy()[ok], ws[ok], rtol=1e-3, atol=2e-5)
-    np.testing.assert_allclose(out['image'][0].cpu().numpy()[ok], img[ok], rtol=1e-3, atol=2e-5)
-    np.testing.assert_allclose(out['depth'][0].cpu().numpy()[ok], d[ok], rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(out['weights_sum'][0].cpu().numpy()[ok], ws[ok], rtol=5e-3, atol=2e-4)
+    np.testing.assert_allclose(out['image'][0].cpu().numpy()[ok], img[ok], rtol=5e-3, atol=2e-4)
+    np.testing.assert_allclose(out['depth'][0].cpu().numpy()[ok], d[ok], rtol=5e-3, atol=2e-4)
     # camera mode == explicit rays
     size = int(round((N // poses.shape[0]) ** 0.5))
     K = torch.tensor([[f, f, size / 2, size / 2]] * poses.shape[0], device='cuda')
     ws_c, d_c, img_c = dec.render_cameras(torch.from_numpy(poses).cuda(), K, size, size, torch.from_numpy(bitfield).cuda(), H, dt_gamma=1 / f)
-    okc = (ws_c.reshape(-1) - out['weights_sum'][0]).abs() < 2e-3
+    okc = (ws_c.reshape(-1) - out['weights_sum'][0]).abs() < 5e-3
     assert okc.float().mean() > 0.99
     torch.testing.assert_close(img_c.reshape(-1, 3)[okc], out['image'][0][okc], rtol=1e-3, atol=1e-4)
 
