@@ -303,33 +303,66 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
     use_depth = tgt_depths is not None and depth_weight > 0
     ps = nerf.patch_size
     assert patch_size == ps
-    cam_weights_mean = cam_weights.mean()
+    V = camera_poses.shape[0]
+    n_sel = max(n_inverse_rays // (ps * ps), 1)
+    n_patches_total = V * (render_size // ps) ** 2
+    if prog.get('iteration') is None:
+        prog['iteration'] = iteration       # the closure the graph was (or will be) captured from
+    iteration = prog['iteration']
 
+    # ---- per-configuration "program": static input slots + the iteration closure (+ its captured CUDA graph).  It persists on the
+    # nerf object so that a graph is captured ONCE per configuration and replayed by every later nerf_optim call (the pipeline calls
+    # nerf_optim once per denoising step); inputs are copied into the static slots at the start of each call.
+    key = (V, render_size, ps, n_sel, bool(is_init), bool(init_shaded), use_normal, use_depth, fused, use_graph, float(dt_gamma_scale),
+           float(ambient_light), float(bg_width), float(intrinsics_size), float(patch_rgb_weight), float(patch_normal_weight),
+           float(depth_weight), id(optimizer), density_bitfield.data_ptr(), id(tonemapping), id(nerf_code), tuple(normal_bg))
+    cache = nerf.__dict__.setdefault('_recon_programs', {})
+    prog = cache.get(key) if use_graph else None
+    if prog is None:
+        f32 = dict(dtype=torch.float32, device=device)
+        prog = dict(
+            img=torch.empty(1, V, render_size, render_size, 3, **f32), msk=torch.empty(1, V, render_size, render_size, 1, **f32),
+            dirs=torch.empty(1, V, render_size, render_size, 3, **f32), R=torch.empty(V, 3, 3, **f32), Tr=torch.empty(V, 3, **f32),
+            camw=torch.empty(V, **f32), lights=torch.empty(V, 3, **f32), intr=torch.empty(V, 4, **f32),
+            nrm=torch.empty(1, V, render_size, render_size, 3, **f32) if use_normal else None,
+            dep=torch.empty(1, V, render_size, render_size, 1, **f32) if use_depth else None,
+            sc=dict(normal_reg=torch.zeros((), **f32), entropy=torch.zeros((), **f32), alpha_mul=torch.zeros((), **f32)),
+            inds=torch.zeros(min(n_sel, n_patches_total), dtype=torch.long, device=device), graph=None, vals=None)
+        if use_graph:
+            cache[key] = prog
     if alpha_blur_std > 0:
         kernel_size = int((alpha_blur_std * 6) // 2 * 2 + 1)
         tgt_masks_blur = gaussian_blur(tgt_masks.square().squeeze(0).permute(0, 3, 1, 2), kernel_size, alpha_blur_std
                                        ).permute(0, 2, 3, 1)[None].clamp(min=alpha_soften ** 2, max=(1 - alpha_soften) ** 2).sqrt()
     else:
         tgt_masks_blur = tgt_masks.clamp(min=alpha_soften ** 2, max=(1 - alpha_soften) ** 2).sqrt()
-    directions = get_ray_directions(render_size, render_size, intrinsics[None] * (render_size / intrinsics_size), norm=False,
-                                    device=intrinsics.device)
+    with torch.no_grad():
+        prog['img'].copy_(tgt_images); prog['msk'].copy_(tgt_masks_blur)
+        prog['dirs'].copy_(get_ray_directions(render_size, render_size, intrinsics[None] * (render_size / intrinsics_size), norm=False,
+                                              device=intrinsics.device))
+        prog['R'].copy_(camera_poses[:, :3, :3]); prog['Tr'].copy_(camera_poses[:, :3, 3])
+        prog['camw'].copy_(cam_weights); prog['lights'].copy_(cam_lights); prog['intr'].copy_(intrinsics)
+        if use_normal:
+            prog['nrm'].copy_(tgt_normals)
+        if use_depth:
+            prog['dep'].copy_(tgt_depths)
+        prog['sc']['normal_reg'].fill_(float(normal_reg_weight) * 10)
+        prog['sc']['entropy'].fill_(float(entropy_weight))
+        prog['sc']['alpha_mul'].fill_(5.0 if is_init else 1.0)
+    directions, R, Tr = prog['dirs'], prog['R'], prog['Tr']
+    cam_weights, cam_lights, intrinsics = prog['camw'], prog['lights'], prog['intr']     # static slots from here on
+    sc, inds_static = prog['sc'], prog['inds']
     normal_bg_t = tgt_images.new_tensor(normal_bg)
-    R, Tr = camera_poses[:, :3, :3].float(), camera_poses[:, :3, 3].float()
-    pv_img, pv_msk, pv_dir = _patch_view(tgt_images, ps), _patch_view(tgt_masks_blur, ps), _patch_view(directions, ps)
-    pv_nrm = _patch_view(tgt_normals, ps) if use_normal else None
-    pv_dep = _patch_view(tgt_depths, ps) if use_depth else None
-    n_patches_total = pv_img.shape[0] * pv_img.shape[1] * pv_img.shape[2]
-    n_sel = max(n_inverse_rays // (ps * ps), 1)
+    pv_img, pv_msk, pv_dir = _patch_view(prog['img'], ps), _patch_view(prog['msk'], ps), _patch_view(directions, ps)
+    pv_nrm = _patch_view(prog['nrm'], ps) if use_normal else None
+    pv_dep = _patch_view(prog['dep'], ps) if use_depth else None
     decoder_training_prev = nerf.decoder.training
     nerf.decoder.train(True)
     log = [] if debug else None
-    # schedule-dependent scalars live on the device so that a captured graph sees their current values
-    sc = dict(normal_reg=torch.tensor(float(normal_reg_weight) * 10, device=device), entropy=torch.tensor(float(entropy_weight), device=device),
-              alpha_mul=torch.tensor(5.0 if is_init else 1.0, device=device))
-    inds_static = torch.zeros(min(n_sel, n_patches_total), dtype=torch.long, device=device)
 
     def iteration():
         inds = inds_static
+        cam_weights_mean = cam_weights.mean()
         target_rgbs, target_cam_ids = _gather_patches(pv_img, inds)
         target_m_blur, _ = _gather_patches(pv_msk, inds)
         target_dir, _ = _gather_patches(pv_dir, inds)
@@ -405,11 +438,9 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
         optimizer.step()
         return torch.stack([loss.detach(), pixel_rgb_loss.detach(), alphas_loss.detach(), normal_reg_loss.detach(), entropy_loss.detach()])
 
-    # fused objective (4 kernels instead of ~300 eager ops + autograd) for the configuration it covers
-    fused = bool(getattr(nerf, 'fused_loss', True)) and tonemapping is None and not use_normal and not use_depth \
-        and not (patch_rgb_weight > 0 and nerf.patch_loss is not None) and nerf.decoder.sample_capacity > 0 and tgt_images.is_cuda
-    use_graph = bool(getattr(nerf, 'use_cuda_graph', False)) and bool(optimizer.defaults.get('capturable', False)) \
-        and nerf.decoder.sample_capacity > 0 and not debug
+    if prog.get('iteration') is None:
+        prog['iteration'] = iteration       # the closure the graph was (or will be) captured from
+    iteration = prog['iteration']
     with torch.enable_grad():
         if use_graph:
             if not isinstance(optimizer.param_groups[0]['lr'], torch.Tensor):
@@ -419,7 +450,7 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
             optimizer.param_groups[0]['lr'] = lr
         raybatch_inds, num_raybatch = nerf.get_raybatch_inds(tgt_images, n_inverse_rays)
         iter_density = 0
-        graph = None
+        graph, vals_static = prog['graph'], prog['vals']
         for inverse_step_id in range(inverse_steps):
             if inverse_step_id % nerf.update_extra_interval == 0:
                 for _ in range(nerf.update_extra_iters):
@@ -441,6 +472,7 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     vals_static = iteration()
+                prog['graph'], prog['vals'] = graph, vals_static
             else:
                 graph.replay()
                 vals = vals_static
