@@ -53,7 +53,7 @@ struct MarchParams {
     const uint8_t* __restrict__ grid;
     float bound, dt_gamma, dt_min, dt_max, rH, H3;
     uint32_t C, H;
-    bool contract;
+    bool contract, h_pow2;
 };
 
 // Visit the cell at t. Occupied: returns true with the (contracted) sample position and dt; t is not advanced.
@@ -67,8 +67,9 @@ __device__ __forceinline__ bool dda_step(const Ray& r, const MarchParams& p, flo
 
     dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
 
-    const int level = max(mip_from_pos(x, y, z, p.C), mip_from_dt(dt, H, p.C));
-    const float mip_bound = fminf(scalbnf(1.0f, level), bound);
+    // get mip level.  C == 1 (every VolumeRenderer call of the reference passes 1, base_volume_renderer.py:216,300) => level 0.
+    const int level = (p.C == 1) ? 0 : max(mip_from_pos(x, y, z, p.C), mip_from_dt(dt, H, p.C));
+    const float mip_bound = (p.C == 1) ? fminf(1.0f, bound) : fminf(scalbnf(1.0f, level), bound);
     const float mip_rbound = 1 / mip_bound;
 
     cx = x; cy = y; cz = z;
@@ -77,10 +78,20 @@ __device__ __forceinline__ bool dda_step(const Ray& r, const MarchParams& p, flo
         const float Linf_scale = (2 - 1 / mag) / mag;
         cx *= Linf_scale; cy *= Linf_scale; cz *= Linf_scale;
     }
-    // 0.5 is a double literal in the reference (:401-403): keep the promotion.
-    const int nx = clampf(0.5 * (cx * mip_rbound + 1) * H, 0.0f, (float)(H - 1));
-    const int ny = clampf(0.5 * (cy * mip_rbound + 1) * H, 0.0f, (float)(H - 1));
-    const int nz = clampf(0.5 * (cz * mip_rbound + 1) * H, 0.0f, (float)(H - 1));
+    int nx, ny, nz;
+    if (p.h_pow2) {
+        // 0.5 * v * H with H a power of two only rescales the exponent: the fp32 product is bit-identical to the reference's
+        // double-promoted expression (:401-403) and avoids 3 x (F2F, 2 DMUL, F2F) on the conversion pipe per step
+        const float hH = 0.5f * (float)H;
+        nx = clampf((cx * mip_rbound + 1) * hH, 0.0f, (float)(H - 1));
+        ny = clampf((cy * mip_rbound + 1) * hH, 0.0f, (float)(H - 1));
+        nz = clampf((cz * mip_rbound + 1) * hH, 0.0f, (float)(H - 1));
+    } else {
+        // 0.5 is a double literal in the reference (:401-403): keep the promotion.
+        nx = clampf(0.5 * (cx * mip_rbound + 1) * H, 0.0f, (float)(H - 1));
+        ny = clampf(0.5 * (cy * mip_rbound + 1) * H, 0.0f, (float)(H - 1));
+        nz = clampf(0.5 * (cz * mip_rbound + 1) * H, 0.0f, (float)(H - 1));
+    }
 
     const uint32_t index = level * p.H3 + morton3(nx, ny, nz);
     const bool occ = p.grid[index / 8] & (1 << (index % 8));
@@ -112,6 +123,7 @@ __host__ __device__ inline MarchParams make_params(const uint8_t* grid, float bo
     p.dt_min = 2 * 1.7320508075688772f / max_steps;
     p.dt_max = 2 * 1.7320508075688772f * bound / H;
     p.rH = 1 / (float)H;
+    p.h_pow2 = (H & (H - 1)) == 0;
     p.H3 = H * H * H;
     return p;
 }
