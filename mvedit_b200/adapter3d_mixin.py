@@ -110,7 +110,8 @@ class Adapter3DMixin:
 
     def get_noise_pred_p2(self, latent_batches, prompt_embeds_batches, dec_args, dec_kwargs, t, guidance_scale,
                           ctrl_images_batches, tile_weight, ctrl_depths_batches=None, depth_weight=None,
-                          added_cond_kwargs_batches=None, guess_mode=False, adapter_scale=None, ctrl_text_embedding=True):
+                          added_cond_kwargs_batches=None, guess_mode=False, adapter_scale=None, ctrl_text_embedding=True,
+                          ctrl_is_cfg_duplicate=False):
         """adapter3d_mixin.py:239-317: ControlNets on the fresh renders + decoder only."""
         assert added_cond_kwargs_batches is None and not guess_mode and ctrl_text_embedding
         latent_size = latent_batches[0].size(-1)
@@ -122,7 +123,9 @@ class Adapter3DMixin:
             ref = lat.shape[2] == 2 * lat.shape[3]
             cn_in = lat[:, :, -latent_size:] if ref else lat
             nets = MultiControlNet(self.controlnet.nets[:1 if cd is None else 2])
-            down, mid = nets(cn_in, t, pe, [ci] if cd is None else [ci, cd], [tile_weight] if cd is None else [tile_weight, depth_weight])
+            # ctrl_is_cfg_duplicate (extension): the caller built ctrl_* as torch.cat([x] * 2) for the CFG halves
+            down, mid = nets(cn_in, t, pe, [ci] if cd is None else [ci, cd], [tile_weight] if cd is None else [tile_weight, depth_weight],
+                             cond_repeat=2 if (ctrl_is_cfg_duplicate and not ref) else 1)
             if ref:
                 down, mid = [_interleave_zero(d) for d in down], _interleave_zero(mid)
             if dk['down_block_additional_residuals'] is not None:

@@ -143,9 +143,12 @@ __global__ void __launch_bounds__(BW_T) k_field_bwd(const float* __restrict__ xy
         for (int e = 0; e < IB; e++) aW1[c][e] = 0.f;
     }
 
-    const uint32_t n_tiles = (M + BW_T - 1) / BW_T;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t i = tile * BW_T + threadIdx.x;
+    // tiles are WARP-sized (32 samples): after culling a reconstruction iteration keeps only a few thousand samples, and the
+    // weight-gradient reduction is warp-cooperative anyway, so spreading 32-sample tiles over all resident warps (instead of
+    // 128-sample tiles over CTAs) turns a ~50-CTA latency-bound launch into one tile per warp.
+    const uint32_t n_tiles = (M + 31) / 32, total_warps = gridDim.x * (BW_T / 32);
+    for (uint32_t tile = blockIdx.x * (BW_T / 32) + warp; tile < n_tiles; tile += total_warps) {
+        const uint32_t i = tile * 32 + lane;
         const bool live = i < M;
         float x = 0.f, y = 0.f, z = 0.f, gs = 0.f, gr = 0.f, gg = 0.f, gb = 0.f;
         if (live) {
@@ -385,7 +388,7 @@ int mve_field_backward(const float* xyz, uint32_t M, const int32_t* M_dev, const
     MVE_ARG(workspace != nullptr, "field backward: workspace required (mve_field_backward_workspace_floats)");
     const FieldCfg cfg = make_cfg(bound, blob_density, blob_radius, sigmoid_saturation);
     uint32_t grid = cdiv(M > 0 ? M : 1, BW_T);
-    if (grid > (uint32_t)(2 * kNumSM)) grid = 2 * kNumSM;
+    if (grid > (uint32_t)(2 * kNumSM)) grid = 2 * kNumSM;     // M is the buffer capacity when M_dev is given: all CTAs launch
     const float2* t2 = reinterpret_cast<const float2*>(table);
     float2* gt2 = reinterpret_cast<float2*>(grad_table);
     cudaStream_t s = (cudaStream_t)stream;

@@ -153,7 +153,7 @@ class MVEdit3DStep(Adapter3DMixin):
         # ---- denoise P2 (:1413-1426)
         noise_pred = self.get_noise_pred_p2(latent_batches, prompt_batches, dec_args, dec_kwargs, t, guidance_scale,
                                             [torch.cat([ctrl_images] * 2, dim=0)], tile_weight, [torch.cat([ctrl_depths] * 2, dim=0)],
-                                            depth_weight)
+                                            depth_weight, ctrl_is_cfg_duplicate=True)
         # ---- solver step (:1438-1461, blend_weight 0)
         latents = sch.step(noise_pred.float(), i, latents, ancestral_noise)
         mark('denoise_p2+solver')

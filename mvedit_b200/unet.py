@@ -264,9 +264,14 @@ class ControlNet(_Net):
     """ControlNetModel (v1.1) forward, guess_mode=False.  Residuals come back NHWC bf16, already scaled; ``accumulate`` lets a
     second net add into the first one's buffers in its zero-conv epilogues (MultiControlNetModel's sum)."""
 
-    def cond_embedding(self, cond, base):
-        """cond [B,3,8L,8L]; base = conv_in(sample) NHWC.  Returns base + controlnet_cond_embedding(cond)."""
+    def cond_embedding(self, cond, base, cond_repeat=1):
+        """cond [B,3,8L,8L]; base = conv_in(sample) NHWC.  Returns base + controlnet_cond_embedding(cond).
+        cond_repeat = r: the caller guarantees cond = r stacked copies of the same images (the pipeline feeds
+        torch.cat([ctrl_images] * 2) for the CFG halves, mvedit_3d_pipeline.py:1417-1421): the 512^2 hint convolutions then run once
+        on B/r images and only the last (64^2) convolution sees all B."""
         w, ce = self.w, self.cfg.cond_embed_channels
+        if cond_repeat > 1:
+            cond = cond[:cond.shape[0] // cond_repeat]
         x = T.nchw_to_nhwc_pad(cond, 64)
 
         def conv(name, x, cin, cout, stride, act, residual=None):
@@ -297,14 +302,16 @@ class ControlNet(_Net):
         for a, b in zip(ce[:-1], ce[1:]):
             h = conv(f'controlnet_cond_embedding.blocks.{k}', h, a, a, 1, 'silu'); k += 1
             h = conv(f'controlnet_cond_embedding.blocks.{k}', h, a, b, 2, 'silu'); k += 1
+        if cond_repeat > 1:
+            h = h.repeat(cond_repeat, 1, 1, 1)
         return conv('controlnet_cond_embedding.conv_out', h, ce[-1], self.cfg.block_out_channels[0], 1, None, residual=base)
 
-    def __call__(self, sample, t, encoder_hidden_states, controlnet_cond, conditioning_scale=1.0, accumulate=None):
+    def __call__(self, sample, t, encoder_hidden_states, controlnet_cond, conditioning_scale=1.0, accumulate=None, cond_repeat=1):
         B = sample.shape[0]
         emb, proj = self.time_embed(t, B)
         x, wc, bc = self.conv_in(sample)
         x = T.conv3x3(x, wc, bias=bc)
-        x = self.cond_embedding(controlnet_cond, x)
+        x = self.cond_embedding(controlnet_cond, x, cond_repeat)
         ctx = encoder_hidden_states.to(torch.bfloat16).contiguous()
         res, s = self.encoder(x, proj, ctx)
         s = self.mid(s, proj, ctx)
@@ -329,8 +336,8 @@ class MultiControlNet:
     def __init__(self, nets):
         self.nets = list(nets)
 
-    def __call__(self, sample, t, encoder_hidden_states, controlnet_cond, conditioning_scale):
+    def __call__(self, sample, t, encoder_hidden_states, controlnet_cond, conditioning_scale, cond_repeat=1):
         acc = None
         for net, cond, sc in zip(self.nets, controlnet_cond, conditioning_scale):
-            acc = net(sample, t, encoder_hidden_states, cond, sc, accumulate=acc)
+            acc = net(sample, t, encoder_hidden_states, cond, sc, accumulate=acc, cond_repeat=cond_repeat)
         return acc

@@ -138,3 +138,19 @@ def test_unet_sd15_shapes_one_image():
         out = unet(x, 981, ctx)
     r2, rmax = rel(out, ref)
     assert r2 <= 3e-2 and rmax <= 8e-2, (r2, rmax)
+
+
+def test_controlnet_hint_dedupe_matches_full(tiny):
+    """cond_repeat=2 (hint convolutions once for both CFG halves) must equal running them on the duplicated batch."""
+    cfg = tiny['cfg']
+    g = torch.Generator(device='cuda').manual_seed(5)
+    N, L = 2, 16
+    lat = torch.randn(N, 4, L, L, device='cuda', generator=g)
+    pe = torch.randn(2 * N, 77, cfg.cross_attention_dim, device='cuda', generator=g)
+    ci = torch.rand(N, 3, 8 * L, 8 * L, device='cuda', generator=g)
+    x2, c2 = torch.cat([lat] * 2), torch.cat([ci] * 2)
+    with torch.no_grad():
+        d_a, m_a = tiny['cn'][0](x2, 300, pe, c2, 0.7)
+        d_b, m_b = tiny['cn'][0](x2, 300, pe, c2, 0.7, cond_repeat=2)
+    for a, b in zip(d_a + [m_a], d_b + [m_b]):
+        assert torch.equal(a, b)
