@@ -269,6 +269,11 @@ def run_ours(args):
                 occupied_cells=int((((bitfield.view(-1).to(torch.int32).unsqueeze(-1) >> torch.arange(8, device=device)) & 1).sum()).item()),
                 grid_cells=GRID ** 3)
     pipe.nerf.use_cuda_graph = graph_flag
+    dist = {}
+    for name, a, b, meta in prof:
+        dist.setdefault(name, []).append(a.elapsed_time(b))
+    tails = {k: dict(min=round(min(v), 3), med=round(float(np.median(v)), 3), p90=round(float(np.percentile(v, 90)), 3), max=round(max(v), 3))
+             for k, v in dist.items() if k in ('mve_field_backward', 'mve_field_forward', 'mve_march_rays_train', 'mve_attention_bf16')}
     cat = {}
     for name, a, b, meta in prof:
         c = cat.setdefault(name, dict(ms=0.0, n=0, flops=0.0))
@@ -303,7 +308,7 @@ def run_ours(args):
                       unit='TFLOP/s', frac=round(achieved / pk['tf_sustained'], 4), traffic=None, peak_source=pk['src'] + ' (sustained)',
                       launches_per_step=tc_n, share_of_step=round(tc_ms / total_prof_ms, 3) if total_prof_ms else None),
         phase_ms=phases, init_recon_640_iters_s=round(init_s, 2), work=work,
-        kernel_breakdown_ms=breakdown,
+        kernel_breakdown_ms=breakdown, per_call_ms=tails,
     )
     if world == 1:
         line['raster_hbm'] = raymarch_microbench(device, pk)
