@@ -132,6 +132,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
     if world > 1:
+        os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the single JSON line (NCCL prints its version banner there otherwise)
         dist.init_process_group('nccl', device_id=device)
     from mvedit_b200 import view_shard, _lib
     pipe = build(device, rank, world)
@@ -287,6 +288,9 @@ def run_ours(args):
     breakdown = {k: dict(ms=round(v['ms'], 3), launches=v['n'], tflops=round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1) if v['flops'] and v['ms'] else None)
                  for k, v in sorted(cat.items(), key=lambda kv: -kv[1]['ms'])}
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     steps_per_s = args.steps / (ms * 1e-3)
