@@ -266,7 +266,7 @@ def run_ours(args):
     rs = pipe.nerf.decoder.last_render_stats()
     lc = [int(c.item()) for c in pipe.nerf.decoder.last_counts]
     work = dict(render_samples_shaded=rs[0], render_lane_utilisation=round(rs[0] / max(rs[1] * 32, 1), 3), render_warp_rounds=rs[2],
-                render_shading_warp_rounds=rs[1], recon_last_iter_samples_marched=lc[0], recon_last_iter_samples_kept=lc[1],
+                render_shading_warp_rounds=rs[1], render_dda_warp_trips=rs[3], recon_last_iter_samples_marched=lc[0], recon_last_iter_samples_kept=lc[1],
                 occupied_cells=int((((bitfield.view(-1).to(torch.int32).unsqueeze(-1) >> torch.arange(8, device=device)) & 1).sum()).item()),
                 grid_cells=GRID ** 3)
     pipe.nerf.use_cuda_graph = graph_flag

@@ -178,8 +178,8 @@ int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses
                     float blob_density, float blob_radius, float sigmoid_saturation,
                     float* weights_sum, float* depth, float* image, void* stream);
 
-/* Statistics of the most recent mve_render_rays launch into host_out[3]: samples shaded, warp-rounds that shaded, warp-rounds total
- * (host-synchronous; diagnostics / bench only). */
+/* Statistics of the most recent mve_render_rays launch into host_out[4]: samples shaded, warp-rounds that shaded, warp-rounds total,
+ * warp-level trips of the occupancy-grid search loop (host-synchronous; diagnostics / bench only). */
 int mve_render_last_sample_count(uint64_t* host_out);
 
 /* Weight culling of the training branch (base_volume_renderer.py:222-246): keep samples with weight > th, compact xyzs/ts,

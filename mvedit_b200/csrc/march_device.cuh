@@ -56,8 +56,50 @@ struct MarchParams {
     bool contract, h_pow2;
 };
 
+// "step until next voxel" (raymarching.cu:452-455 / :818-821):  do { t += clamp(t * dt_gamma, dt_min, dt_max); } while (t < tt);
+// The same floating-point operations in the same order (so t is bit-identical), but unrolled: the original loop is one
+// dependent FMUL-FMNMX-FMNMX-FADD-FSETP-BRA chain per step (~50 cycles), and a ray crossing empty space takes hundreds of them,
+// which made the empty-space walk of the fused renderer latency-bound (7 search trips per shading round cost more than the
+// shading itself).  When tt * dt_gamma <= dt_min every step of this skip is exactly dt_min (rounding is monotone and t < tt
+// before each step), and the chain collapses to one FADD per step.
+__device__ __forceinline__ void step_until(float& t, const float tt, const MarchParams& p, float& dt) {
+    if (p.dt_gamma >= 0.0f && tt * p.dt_gamma <= p.dt_min && p.dt_min <= p.dt_max) {
+        dt = p.dt_min;
+        for (;;) {
+            const float t1 = t + dt, t2 = t1 + dt, t3 = t2 + dt, t4 = t3 + dt, t5 = t4 + dt, t6 = t5 + dt, t7 = t6 + dt, t8 = t7 + dt;
+            if (!(t8 < tt)) {
+                t = !(t1 < tt) ? t1 : !(t2 < tt) ? t2 : !(t3 < tt) ? t3 : !(t4 < tt) ? t4 : !(t5 < tt) ? t5 : !(t6 < tt) ? t6 : !(t7 < tt) ? t7 : t8;
+                return;
+            }
+            t = t8;
+        }
+    }
+    for (;;) {
+        const float d1 = clampf(t * p.dt_gamma, p.dt_min, p.dt_max), t1 = t + d1;
+        const float d2 = clampf(t1 * p.dt_gamma, p.dt_min, p.dt_max), t2 = t1 + d2;
+        const float d3 = clampf(t2 * p.dt_gamma, p.dt_min, p.dt_max), t3 = t2 + d3;
+        const float d4 = clampf(t3 * p.dt_gamma, p.dt_min, p.dt_max), t4 = t3 + d4;
+        if (!(t4 < tt)) {
+            if (!(t1 < tt)) { t = t1; dt = d1; }
+            else if (!(t2 < tt)) { t = t2; dt = d2; }
+            else if (!(t3 < tt)) { t = t3; dt = d3; }
+            else { t = t4; dt = d4; }
+            return;
+        }
+        t = t4;
+    }
+}
+
 // Visit the cell at t. Occupied: returns true with the (contracted) sample position and dt; t is not advanced.
 // Empty: advances t to the first step past the current voxel and returns false.
+//
+// BLOCK_SKIP (fused renderer only): 64 consecutive Morton cells are a 4x4x4 block and 8 aligned bytes of the bitfield, so ONE
+// 64-bit load answers "is the whole block empty"; if so the ray steps to the block's exit plane instead of the cell's.  The
+// t sequence (t += dt while t < exit) is the same sequence of increments the per-cell walk takes through those all-empty cells,
+// so the next sample is the same one up to the rounding of the exit distance (computed from another point of the same ray):
+// a sample that lies within an ulp of a cell face may move by one dt.  The training marcher keeps the per-cell walk and stays
+// bit-identical to the reference.
+template <bool BLOCK_SKIP = false>
 __device__ __forceinline__ bool dda_step(const Ray& r, const MarchParams& p, float& t, float& cx, float& cy, float& cz, float& dt) {
     const float bound = p.bound;
     const uint32_t H = p.H;
@@ -94,17 +136,30 @@ __device__ __forceinline__ bool dda_step(const Ray& r, const MarchParams& p, flo
     }
 
     const uint32_t index = level * p.H3 + morton3(nx, ny, nz);
-    const bool occ = p.grid[index / 8] & (1 << (index % 8));
-    if (occ) return true;
+    if (BLOCK_SKIP && p.h_pow2 && H >= 4 && !p.contract) {
+        const unsigned long long blk = *reinterpret_cast<const unsigned long long*>(p.grid + ((index >> 6) << 3));
+        if ((blk >> (index & 63u)) & 1ull) return true;
+        if (blk == 0ull) {
+            const float px = r.dx > 0 ? (float)((nx | 3) + 1) : (r.dx < 0 ? (float)(nx & ~3) : nx + 0.5f);
+            const float py = r.dy > 0 ? (float)((ny | 3) + 1) : (r.dy < 0 ? (float)(ny & ~3) : ny + 0.5f);
+            const float pz = r.dz > 0 ? (float)((nz | 3) + 1) : (r.dz < 0 ? (float)(nz & ~3) : nz + 0.5f);
+            const float tx = ((px * p.rH * 2 - 1) * mip_bound - cx) * r.rdx;
+            const float ty = ((py * p.rH * 2 - 1) * mip_bound - cy) * r.rdy;
+            const float tz = ((pz * p.rH * 2 - 1) * mip_bound - cz) * r.rdz;
+            const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+            step_until(t, tt, p, dt);
+            return false;
+        }
+    } else {
+        const bool occ = p.grid[index / 8] & (1 << (index % 8));
+        if (occ) return true;
+    }
     if (p.contract && mag > 1) { t += dt; return false; }
     const float tx = (((nx + 0.5f + 0.5f * sgnf(r.dx)) * p.rH * 2 - 1) * mip_bound - cx) * r.rdx;
     const float ty = (((ny + 0.5f + 0.5f * sgnf(r.dy)) * p.rH * 2 - 1) * mip_bound - cy) * r.rdy;
     const float tz = (((nz + 0.5f + 0.5f * sgnf(r.dz)) * p.rH * 2 - 1) * mip_bound - cz) * r.rdz;
     const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
-    do {
-        dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
-        t += dt;
-    } while (t < tt);
+    step_until(t, tt, p, dt);
     return false;
 }
 

@@ -64,16 +64,74 @@ __device__ __forceinline__ void stage_frags(float* __restrict__ fr, const float*
     for (int i = threadIdx.x; i < HID; i += blockDim.x) fr[C::B1_FLOATS + C::B2_FLOATS + i] = b1[i];
 }
 
+// Hash-grid encoding of one sample per lane written straight into the warp's [k][sample] staging tile (TF32), one level per
+// loop trip.  The level loop is deliberately NOT unrolled: the fully unrolled encoder is ~4 000 straight-line instructions
+// (64 KB) that every warp streams through once per round, and with the warps of an SM at different points of the
+// march/shade loop the fused renderer became instruction-fetch bound (ncu: stall_no_instruction 11 of 16 cycles per issue,
+// profiles/r01_ncu_k_render_rays_bench_state.txt).  A ~130-instruction loop body stays resident in the instruction caches.
+template <int L, int UNROLL>
+__device__ __forceinline__ void encode_staged(const field::Levels& lv, const float2* __restrict__ table, const float x0, const float x1,
+                                              const float x2, const bool live, float* __restrict__ stage) {
+    using C = Cfg<L>;
+    const int lane = threadIdx.x & 31;
+    uint32_t* st = reinterpret_cast<uint32_t*>(stage);
+#pragma unroll UNROLL
+    for (int l = 0; l < L; l++) {
+        float a0 = 0.f, a1 = 0.f;
+        if (live) {
+            const field::Cell c = field::locate(x0, x1, x2, lv.scale[l]);
+            const bool hashed = (lv.hashed >> l) & 1u;
+            const uint32_t res = lv.res[l], size = lv.size[l];
+            const float2* __restrict__ t = table + lv.off[l];
+            float2 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                v[k] = __ldg(t + field::grid_index(hashed, res, size, c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + (k >> 2)));
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float wgt = ((k & 1) ? c.w[0] : 1.f - c.w[0]) * ((k & 2) ? c.w[1] : 1.f - c.w[1]) * ((k & 4) ? c.w[2] : 1.f - c.w[2]);
+                a0 = fmaf(wgt, v[k].x, a0);
+                a1 = fmaf(wgt, v[k].y, a1);
+            }
+        }
+        st[(2 * l) * C::ENC_LD + lane] = to_tf32(a0);
+        st[(2 * l + 1) * C::ENC_LD + lane] = to_tf32(a1);
+    }
+}
+
+// zero the K-padding rows of a warp's staging tile (never written afterwards: the output exchange only touches floats 0..127)
+template <int L>
+__device__ __forceinline__ void zero_stage_pad(float* __restrict__ stage) {
+    using C = Cfg<L>;
+    const int lane = threadIdx.x & 31;
+    static_assert(C::IN * C::ENC_LD >= 128, "output exchange would overlap the padding rows");
+#pragma unroll
+    for (int k = C::IN; k < C::KS * 8; k++) stage[k * C::ENC_LD + lane] = 0.f;
+    __syncwarp();
+}
+
+template <int L>
+__device__ __forceinline__ void mlp_forward_staged(float* __restrict__ stage, const float* __restrict__ fr, float (&out)[4]);
+
 // All 32 lanes must call (mma.sync); lanes without a live sample pass zeros in enc.
 // out[0..3] = W2 relu(W1 enc + b1) for THIS lane's sample (the output bias b2 is added by the caller).
 template <int L>
 __device__ __forceinline__ void mlp_forward(const float (&enc)[2 * L], float* __restrict__ stage, const float* __restrict__ fr, float (&out)[4]) {
     using C = Cfg<L>;
-    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int lane = threadIdx.x & 31;
     uint32_t* st = reinterpret_cast<uint32_t*>(stage);
     // sample-major registers -> [k][sample] in shared memory
 #pragma unroll
     for (int k = 0; k < C::KS * 8; k++) st[k * C::ENC_LD + lane] = (k < C::IN) ? to_tf32(enc[k < C::IN ? k : 0]) : 0u;
+    mlp_forward_staged<L>(stage, fr, out);
+}
+
+// the MLP on an already staged [k][sample] tile (encode_staged); all 32 lanes must call
+template <int L>
+__device__ __forceinline__ void mlp_forward_staged(float* __restrict__ stage, const float* __restrict__ fr, float (&out)[4]) {
+    using C = Cfg<L>;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    uint32_t* st = reinterpret_cast<uint32_t*>(stage);
     __syncwarp();
     uint32_t a[2][C::KS][4];
 #pragma unroll

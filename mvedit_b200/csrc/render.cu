@@ -62,6 +62,11 @@ struct RenderParams {
 // A ray crossing empty space therefore never stalls its neighbours' shading for more than DDA_BUDGET steps, and finished /
 // missing / early-terminated rays are replaced immediately.
 constexpr int DDA_BUDGET = 8;
+constexpr int CHUNK = 64;
+#ifndef MVE_RENDER_ENC_UNROLL
+#define MVE_RENDER_ENC_UNROLL 1
+#endif
+constexpr int ENC_UNROLL = MVE_RENDER_ENC_UNROLL;
 
 template <int L>
 __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, MarchParams mp, const float2* __restrict__ table,
@@ -73,54 +78,74 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
     __shared__ __align__(16) float frags[MC::FRAG_FLOATS];
     __shared__ __align__(16) float stage[4][MC::STAGE_FLOATS];
     mlpmma::stage_frags<L>(frags, w1, b1, w2);
+    mlpmma::zero_stage_pad<L>(stage[threadIdx.x >> 5]);
     __syncthreads();
     const float ob0 = b2[0], ob1 = b2[1], ob2 = b2[2], ob3 = b2[3];
     const int lane = threadIdx.x & 31;
 
     bool have_ray = false;
     bool exhausted = false;      // warp-uniform
-    uint32_t n = 0, step = 0, shaded = 0, shade_rounds = 0, rounds = 0;
+    // Rays are handed out in chunks of CHUNK consecutive slots per warp; in camera mode a chunk is an 8x8 pixel tile, so the 32
+    // lanes of a warp march a narrow frustum in near lock-step and their hash-grid gathers share cache lines on the coarse
+    // levels (a single global ray counter leaves every lane on an unrelated ray: 20 L1 wavefronts per gather request,
+    // profiles/r01_ncu_k_render_rays.txt).
+    uint32_t chunk_cur = 0, chunk_end = 0;      // warp-uniform
+    const bool tiled = !rp.rays_o && (rp.h % 8 == 0) && (rp.w % 8 == 0);
+    const uint32_t tiles_x = rp.w / 8, tpv = tiles_x * (rp.h / 8);
+    uint32_t n = 0, step = 0, shaded = 0, shade_rounds = 0, rounds = 0, dda_trips = 0;
     Ray r;
     float t = 0.f, far = 0.f, ws = 0.f, dsum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
     bool terminated = false;
     float cx = 0.f, cy = 0.f, cz = 0.f, dt = 0.f;
 
     for (;;) {
-        // ---------------- 1. fetch
-        if (!exhausted) {
+        // ---------------- 1. fetch: lanes take consecutive slots of the warp's current chunk; an empty chunk is replaced with ONE atomic
+#pragma unroll 1
+        for (int rep = 0; rep < 2; rep++) {
             const uint32_t need = __ballot_sync(0xffffffffu, !have_ray);
-            if (need) {
+            if (!need || (exhausted && chunk_cur == chunk_end)) break;
+            if (chunk_cur == chunk_end) {
                 uint32_t base = 0;
-                if (lane == __ffs(need) - 1) base = atomicAdd(next_ray, (unsigned int)__popc(need));
-                base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
-                if (base >= rp.N) exhausted = true;
-                if (!have_ray) {
-                    const uint32_t mine = base + __popc(need & ((1u << lane) - 1u));
-                    if (mine < rp.N) {
-                        n = mine;
-                        if (rp.rays_o) {
-                            r = load_ray(rp.rays_o, rp.rays_d, n);
-                        } else {
-                            const uint32_t hw = rp.h * rp.w, v = n / hw, pix = n % hw;
-                            const float pi = (float)(pix % rp.w) + 0.5f, pj = (float)(pix / rp.w) + 0.5f;
-                            const float* K = rp.intrinsics + v * 4;
-                            const float* P = rp.poses + v * 16;
-                            const float cxd = (pi - K[2]) / K[0], cyd = (pj - K[3]) / K[1];
-                            const float dx = P[0] * cxd + P[1] * cyd + P[2], dy = P[4] * cxd + P[5] * cyd + P[6], dz = P[8] * cxd + P[9] * cyd + P[10];
-                            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-                            r.ox = P[3]; r.oy = P[7]; r.oz = P[11];
-                            r.dx = dx * inv; r.dy = dy * inv; r.dz = dz * inv;
-                            r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
-                            if (rp.dt_gamma_per_view) mp.dt_gamma = rp.dt_gamma_per_view[v];
-                        }
-                        float near;
-                        slab(r, rp.aabb, rp.min_near, near, far);
-                        t = near;
-                        ws = 0.f; dsum = 0.f; cr = 0.f; cg = 0.f; cb = 0.f; step = 0; terminated = false;
-                        have_ray = true;
-                    }
-                }
+                if (lane == 0) base = atomicAdd(next_ray, (unsigned int)CHUNK);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= rp.N) { exhausted = true; break; }
+                chunk_cur = base; chunk_end = min(base + (uint32_t)CHUNK, rp.N);
             }
+            const uint32_t rank = __popc(need & ((1u << lane) - 1u));
+            const uint32_t avail = chunk_end - chunk_cur;
+            if (!have_ray && rank < avail) {
+                const uint32_t slot = chunk_cur + rank;
+                if (rp.rays_o) {
+                    n = slot;
+                    r = load_ray(rp.rays_o, rp.rays_d, n);
+                } else {
+                    uint32_t v, px, py;
+                    if (tiled) {            // slot -> 8x8 pixel tile, row-major inside the tile
+                        const uint32_t tile = slot / CHUNK, j = slot % CHUNK, tt = tile % tpv, ty = tt / tiles_x, tx = tt % tiles_x;
+                        v = tile / tpv; py = ty * 8 + (j >> 3); px = tx * 8 + (j & 7);
+                    } else {
+                        const uint32_t hw = rp.h * rp.w, pix = slot % hw;
+                        v = slot / hw; py = pix / rp.w; px = pix % rp.w;
+                    }
+                    n = v * rp.h * rp.w + py * rp.w + px;
+                    const float pi = (float)px + 0.5f, pj = (float)py + 0.5f;
+                    const float* K = rp.intrinsics + v * 4;
+                    const float* P = rp.poses + v * 16;
+                    const float cxd = (pi - K[2]) / K[0], cyd = (pj - K[3]) / K[1];
+                    const float dx = P[0] * cxd + P[1] * cyd + P[2], dy = P[4] * cxd + P[5] * cyd + P[6], dz = P[8] * cxd + P[9] * cyd + P[10];
+                    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+                    r.ox = P[3]; r.oy = P[7]; r.oz = P[11];
+                    r.dx = dx * inv; r.dy = dy * inv; r.dz = dz * inv;
+                    r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+                    if (rp.dt_gamma_per_view) mp.dt_gamma = rp.dt_gamma_per_view[v];
+                }
+                float near;
+                slab(r, rp.aabb, rp.min_near, near, far);
+                t = near;
+                ws = 0.f; dsum = 0.f; cr = 0.f; cg = 0.f; cb = 0.f; step = 0; terminated = false;
+                have_ray = true;
+            }
+            chunk_cur += min(avail, (uint32_t)__popc(need));
         }
         if (!__any_sync(0xffffffffu, have_ray)) break;     // nothing in flight and nothing left to fetch
         rounds++;
@@ -130,9 +155,10 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
         for (int k = 0; k < DDA_BUDGET; k++) {
             const bool searching = have_ray && !has;
             if (!__any_sync(0xffffffffu, searching)) break;
+            dda_trips++;
             if (searching) {
                 if (!terminated && t < far && step < rp.max_steps) {
-                    has = dda_step(r, mp, t, cx, cy, cz, dt);
+                    has = dda_step<true>(r, mp, t, cx, cy, cz, dt);
                 } else {
                     rp.weights_sum[n] = ws;
                     rp.depth[n] = dsum;
@@ -144,16 +170,12 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
         // ---------------- 3. shade
         if (__any_sync(0xffffffffu, has)) {
             shade_rounds++;
-            float enc[R::IN];
-            if (has) {
-                t += dt;
-                encode<L>(lv, table, (cx + cfg.bound) * cfg.inv2b, (cy + cfg.bound) * cfg.inv2b, (cz + cfg.bound) * cfg.inv2b, enc);
-            } else {
-#pragma unroll
-                for (int q = 0; q < R::IN; q++) enc[q] = 0.f;
-            }
+            if (has) t += dt;
             float o[4];
-            mlpmma::mlp_forward<L>(enc, stage[threadIdx.x >> 5], frags, o);     // tensor cores, all 32 lanes participate
+            float* const stg = stage[threadIdx.x >> 5];
+            mlpmma::encode_staged<L, ENC_UNROLL>(lv, table, (cx + cfg.bound) * cfg.inv2b, (cy + cfg.bound) * cfg.inv2b, (cz + cfg.bound) * cfg.inv2b,
+                                                 has, stg);
+            mlpmma::mlp_forward_staged<L>(stg, frags, o);     // tensor cores, all 32 lanes participate
             if (has) {
                 const float o0 = o[0] + ob0, o1 = o[1] + ob1, o2 = o[2] + ob2, o3 = o[3] + ob3;
                 const float sigma = __expf(o0 + blob_of(cfg, cx, cy, cz));
@@ -178,6 +200,7 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
         if (shaded) atomicAdd(stats, (unsigned long long)shaded);
         atomicAdd(stats + 1, (unsigned long long)shade_rounds);     // warp-rounds that shaded (x32 = lane slots)
         atomicAdd(stats + 2, (unsigned long long)rounds);
+        atomicAdd(stats + 3, (unsigned long long)dda_trips);       // warp-level trips of the DDA search loop
     }
 }
 
@@ -279,9 +302,9 @@ extern "C" {
 
 int mve_render_last_sample_count(uint64_t* host_out) {
     MVE_ARG(host_out != nullptr, "render_last_sample_count: null output");
-    host_out[0] = host_out[1] = host_out[2] = 0;
+    host_out[0] = host_out[1] = host_out[2] = host_out[3] = 0;
     if (!g_render_scratch) return 0;
-    MVE_CUDA(cudaMemcpy(host_out, g_render_scratch + 8, 24, cudaMemcpyDeviceToHost));   // synchronises: statistics only
+    MVE_CUDA(cudaMemcpy(host_out, g_render_scratch + 8, 32, cudaMemcpyDeviceToHost));   // synchronises: statistics only
     return 0;
 }
 
@@ -293,6 +316,7 @@ int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses
                     float blob_radius, float sigmoid_saturation, float* weights_sum, float* depth, float* image, void* stream) {
     if (N == 0) return 0;
     MVE_ARG((rays_o && rays_d) || (poses && intrinsics && h && w), "render_rays: give rays_o/rays_d or poses/intrinsics/h/w");
+    MVE_ARG((reinterpret_cast<uintptr_t>(density_bitfield) & 7u) == 0, "render_rays: density_bitfield must be 8-byte aligned");
     Levels lv;
     MVE_ARG(fill_levels(lv, n_levels, level_scale, level_res, level_size, level_offset) == 0, "field: n_levels > 16");
     MVE_ARG(n_levels == 12 || n_levels == 14 || n_levels == 16, "field: n_levels must be 12, 14 or 16");
@@ -307,8 +331,8 @@ int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses
     const float2* t2 = reinterpret_cast<const float2*>(table);
     cudaStream_t s = (cudaStream_t)stream;
     // one process drives one GPU: process-wide scratch = [work counter (u32) | pad | samples shaded (u64)]
-    if (!g_render_scratch) MVE_CUDA(cudaMalloc(&g_render_scratch, 32));
-    MVE_CUDA(cudaMemsetAsync(g_render_scratch, 0, 32, s));
+    if (!g_render_scratch) MVE_CUDA(cudaMalloc(&g_render_scratch, 48));
+    MVE_CUDA(cudaMemsetAsync(g_render_scratch, 0, 48, s));
     unsigned int* next_ray = reinterpret_cast<unsigned int*>(g_render_scratch);
     unsigned long long* stats = reinterpret_cast<unsigned long long*>(g_render_scratch + 8);
     if (n_levels == 12) k_render_rays<12><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);

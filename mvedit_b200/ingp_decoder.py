@@ -327,11 +327,12 @@ class iNGPDecoder(nn.Module):
 
     @staticmethod
     def last_render_stats():
-        """(samples shaded, warp-rounds that shaded, warp-rounds) of the most recent fused render launch (synchronises)."""
+        """(samples shaded, warp-rounds that shaded, warp-rounds, warp-level DDA search trips) of the most recent fused render
+        launch (synchronises)."""
         import ctypes as _c
-        buf = (_c.c_uint64 * 3)()
+        buf = (_c.c_uint64 * 4)()
         call('mve_render_last_sample_count', buf)
-        return int(buf[0]), int(buf[1]), int(buf[2])
+        return int(buf[0]), int(buf[1]), int(buf[2]), int(buf[3])
 
     def render_cameras(self, poses, intrinsics, h, w, density_bitfield, grid_size, dt_gamma=0.0):
         """Fused BaseNeRF.render core (base_nerf.py:489-556): rays are generated inside the kernel from (pose, intrinsics, pixel).
