@@ -226,6 +226,20 @@ def run_ours(args):
         torch.cuda.synchronize()
         init_s = time.time() - t_init0
     snapshot()
+    if args.torch_profile:
+        # CUPTI kernel table of ONE warm step (graph mode as configured): where the time outside this library's kernels goes
+        from torch.profiler import profile, ProfilerActivity
+        with torch.no_grad():
+            for _ in range(2):
+                one_step(False)
+            torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof_t:
+                one_step(False)
+                torch.cuda.synchronize()
+        os.makedirs('gpurun_out', exist_ok=True)
+        with open('gpurun_out/torch_profile.txt', 'w') as f:
+            f.write(prof_t.key_averages().table(sort_by='cuda_time_total', row_limit=70, max_name_column_width=90))
+        return
     if args.profile_step:
         with torch.no_grad():
             one_step(False)
@@ -461,6 +475,7 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--torch-profile', action='store_true', help='write a CUPTI per-kernel table of one warm step to gpurun_out/torch_profile.txt')
     ap.add_argument('--profile-step', action='store_true', help='ncu helper: short init, 1 warm-up, ONE step between cudaProfilerStart/Stop, no JSON')
     ap.add_argument('--no-graph', action='store_true', help='run the recon iterations eagerly instead of as CUDA graphs')
     args = ap.parse_args()

@@ -136,8 +136,8 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t B, uint32_
  * lib/ops/activation.py:8-23).  level_* are HOST arrays of n_levels entries (scale, resolution, entries, entry offset);
  * table [n_entries,2] f32; w1 [64,2L], b1 [64], w2 [4,64], b2 [4] f32 (nn.Linear layout).
  * M_dev (optional, device): actual sample count <= M.
- * density_only: 0 = sigma+rgb (fp32 FFMA MLP), 1 = sigma only (fp32), 2 = sigma only with the MLP on tensor cores in TF32 -- the
- * reference's own matmul precision (allow_tf32) -- used for the culling pre-pass.
+ * density_only: 0 = sigma+rgb (fp32 FFMA MLP), 1 = sigma only (fp32); 2 = sigma only / 3 = sigma+rgb with the MLP on tensor
+ * cores in TF32 -- the reference's own matmul precision (torch allow_tf32, lib/apis/adapter3d.py:51-61).
  * ------------------------------------------------------------------------- */
 int mve_field_forward(const float* xyz, uint32_t M, const int32_t* M_dev, const float* table,
                       const float* w1, const float* b1, const float* w2, const float* b2,
@@ -149,7 +149,7 @@ int mve_field_forward(const float* xyz, uint32_t M, const int32_t* M_dev, const 
 /* Backward of mve_field_forward w.r.t. table (atomically ACCUMULATED into grad_table: caller zeroes / owns .grad),
  * MLP parameters (written, or added when accumulate_mlp != 0; deterministic two-stage reduction through `workspace`
  * of mve_field_backward_workspace_floats(n_levels) floats) and optionally xyz (grad_xyz [M,3] or NULL).
- * grad_rgb may be NULL (density-only graph). */
+ * grad_rgb may be NULL (density-only graph).  mlp_tf32 != 0: the MLP backward runs on tensor cores in TF32 (see above). */
 uint32_t mve_field_backward_workspace_floats(uint32_t n_levels);
 int mve_field_backward(const float* xyz, uint32_t M, const int32_t* M_dev, const float* table,
                        const float* w1, const float* b1, const float* w2, const float* b2,
@@ -158,7 +158,7 @@ int mve_field_backward(const float* xyz, uint32_t M, const int32_t* M_dev, const
                        float bound, float blob_density, float blob_radius, float sigmoid_saturation,
                        const float* grad_sigma, const float* grad_rgb,
                        float* grad_table, float* grad_w1, float* grad_b1, float* grad_w2, float* grad_b2,
-                       int accumulate_mlp, float* workspace, float* grad_xyz, void* stream);
+                       int accumulate_mlp, int mlp_tf32, float* workspace, float* grad_xyz, void* stream);
 
 /* ---------------------------------------------------------------------------
  * a-6 / a-9: fused NeRF-adapter kernels (no reference native counterpart: they replace Python loops)

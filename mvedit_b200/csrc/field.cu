@@ -14,6 +14,7 @@
 // Optionally d/d xyz (needed by the DMTet stage, base_mesh_renderer.py:277-283).
 #include "field_device.cuh"
 #include "mlp_mma.cuh"
+#include "field_bwd_mma.cuh"
 #include "../../include/mvedit_b200.h"
 
 using namespace field;
@@ -59,38 +60,41 @@ __global__ void __launch_bounds__(256) k_field_fwd(const float* __restrict__ xyz
     }
 }
 
-// Density-only decode of the training pre-pass (point_density_decode before weight culling, base_volume_renderer.py:222-227): the MLP
-// runs on tensor cores (mlp_mma.cuh, TF32 like the reference's matmuls); its output only decides which samples survive the cull.
-template <int L>
-__global__ void __launch_bounds__(128) k_field_density_mma(const float* __restrict__ xyz, uint32_t M, const int* __restrict__ M_dev,
-                                                           const float2* __restrict__ table, const float* __restrict__ w1,
-                                                           const float* __restrict__ b1, const float* __restrict__ w2,
-                                                           const float* __restrict__ b2, const Levels lv, const FieldCfg cfg,
-                                                           float* __restrict__ sigma) {
-    using R = Rec<L>;
+// Tensor-core forward: the MLP runs as per-warp TF32 mma.sync GEMMs (mlp_mma.cuh; TF32 is the reference's own matmul precision,
+// allow_tf32) and the hash-grid encoder is a rolled per-level loop that writes straight into the MMA staging tile.
+// DENSITY_ONLY: the culling pre-pass (point_density_decode before weight culling, base_volume_renderer.py:222-227).
+template <int L, bool DENSITY_ONLY>
+__global__ void __launch_bounds__(128) k_field_fwd_mma(const float* __restrict__ xyz, uint32_t M, const int* __restrict__ M_dev,
+                                                       const float2* __restrict__ table, const float* __restrict__ w1,
+                                                       const float* __restrict__ b1, const float* __restrict__ w2,
+                                                       const float* __restrict__ b2, const Levels lv, const FieldCfg cfg,
+                                                       float* __restrict__ sigma, float* __restrict__ rgb) {
     using MC = mlpmma::Cfg<L>;
     __shared__ __align__(16) float frags[MC::FRAG_FLOATS];
     __shared__ __align__(16) float stage[4][MC::STAGE_FLOATS];
     mlpmma::stage_frags<L>(frags, w1, b1, w2);
+    float* const stg = stage[threadIdx.x >> 5];
+    mlpmma::zero_stage_pad<L>(stg);
     __syncthreads();
     if (M_dev) M = min(M, (uint32_t)*M_dev);
-    const float ob0 = b2[0];
+    const float ob0 = b2[0], ob1 = b2[1], ob2 = b2[2], ob3 = b2[3];
     const uint32_t lane = threadIdx.x & 31, warp_g = blockIdx.x * 4 + (threadIdx.x >> 5), n_warps = gridDim.x * 4;
     for (uint32_t base = warp_g * 32; base < M; base += n_warps * 32) {      // warp-uniform trip count
         const uint32_t i = base + lane;
         const bool live = i < M;
         float x = 0.f, y = 0.f, z = 0.f;
-        float enc[R::IN];
-        if (live) {
-            x = xyz[(size_t)i * 3]; y = xyz[(size_t)i * 3 + 1]; z = xyz[(size_t)i * 3 + 2];
-            encode<L>(lv, table, (x + cfg.bound) * cfg.inv2b, (y + cfg.bound) * cfg.inv2b, (z + cfg.bound) * cfg.inv2b, enc);
-        } else {
-#pragma unroll
-            for (int q = 0; q < R::IN; q++) enc[q] = 0.f;
-        }
+        if (live) { x = xyz[(size_t)i * 3]; y = xyz[(size_t)i * 3 + 1]; z = xyz[(size_t)i * 3 + 2]; }
+        mlpmma::encode_staged<L, 1>(lv, table, (x + cfg.bound) * cfg.inv2b, (y + cfg.bound) * cfg.inv2b, (z + cfg.bound) * cfg.inv2b, live, stg);
         float o[4];
-        mlpmma::mlp_forward<L>(enc, stage[threadIdx.x >> 5], frags, o);
-        if (live) sigma[i] = __expf(o[0] + ob0 + blob_of(cfg, x, y, z));
+        mlpmma::mlp_forward_staged<L>(stg, frags, o);
+        if (live) {
+            sigma[i] = __expf(o[0] + ob0 + blob_of(cfg, x, y, z));
+            if (!DENSITY_ONLY) {
+                rgb[(size_t)i * 3] = fmaf(1.f / (1.f + __expf(-(o[1] + ob1))), cfg.sat_scale, cfg.sat_shift);
+                rgb[(size_t)i * 3 + 1] = fmaf(1.f / (1.f + __expf(-(o[2] + ob2))), cfg.sat_scale, cfg.sat_shift);
+                rgb[(size_t)i * 3 + 2] = fmaf(1.f / (1.f + __expf(-(o[3] + ob3))), cfg.sat_scale, cfg.sat_shift);
+            }
+        }
     }
 }
 
@@ -326,6 +330,131 @@ __global__ void __launch_bounds__(BW_T) k_field_bwd(const float* __restrict__ xy
     }
 }
 
+// Tensor-core backward (field_bwd_mma.cuh): rolled encoder -> per-warp TF32 MMA backward of the MLP -> rolled scatter of d(enc)
+// into the table gradient.  Same interface, workspace layout and two-stage deterministic MLP reduction as k_field_bwd.
+template <int L, bool WITH_DX>
+__global__ void __launch_bounds__(BW_T, 3) k_field_bwd_mma(const float* __restrict__ xyz, uint32_t M, const int* __restrict__ M_dev,
+                                                           const float2* __restrict__ table, const float* __restrict__ w1,
+                                                           const float* __restrict__ b1, const float* __restrict__ w2,
+                                                           const float* __restrict__ b2, const Levels lv, const FieldCfg cfg,
+                                                           const float* __restrict__ g_sigma, const float* __restrict__ g_rgb,
+                                                           float2* __restrict__ g_table, float* __restrict__ workspace,
+                                                           float* __restrict__ g_xyz) {
+    using B = mlpmma::BCfg<L>;
+    constexpr int IN = B::IN, LD = B::LD, WARP_FLOATS = B::STAGE_FLOATS + B::XCH_FLOATS;
+    extern __shared__ __align__(16) float smem[];
+    float* const fr = smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* const stage = smem + B::FRAG_FLOATS + warp * WARP_FLOATS;
+    float* const xch = stage + B::STAGE_FLOATS;
+    mlpmma::stage_bwd_frags<L>(fr, w1, b1, w2);
+    mlpmma::init_bwd_stage<L>(stage);
+    __syncthreads();
+    if (M_dev) M = min(M, (uint32_t)*M_dev);
+    const float ob0 = b2[0], ob1 = b2[1], ob2 = b2[2], ob3 = b2[3];
+    mlpmma::MlpGradAcc<L> acc;
+    acc.clear();
+
+    const uint32_t n_tiles = (M + 31) / 32, total_warps = gridDim.x * (BW_T / 32);
+    for (uint32_t tile = blockIdx.x * (BW_T / 32) + warp; tile < n_tiles; tile += total_warps) {
+        const uint32_t i = tile * 32 + lane;
+        const bool live = i < M;
+        float x = 0.f, y = 0.f, z = 0.f, gs = 0.f, gr = 0.f, gg = 0.f, gb = 0.f;
+        if (live) {
+            x = xyz[(size_t)i * 3]; y = xyz[(size_t)i * 3 + 1]; z = xyz[(size_t)i * 3 + 2];
+            gs = g_sigma[i];
+            if (g_rgb) { gr = g_rgb[(size_t)i * 3]; gg = g_rgb[(size_t)i * 3 + 1]; gb = g_rgb[(size_t)i * 3 + 2]; }
+        }
+        const float x0 = (x + cfg.bound) * cfg.inv2b, x1 = (y + cfg.bound) * cfg.inv2b, x2 = (z + cfg.bound) * cfg.inv2b;
+        mlpmma::encode_staged<L, 1>(lv, table, x0, x1, x2, live, stage);
+        const float blob = blob_of(cfg, x, y, z);
+        float d0 = 0.f;
+        mlpmma::mlp_backward_tile<L>(stage, xch, fr, acc, [&](const float (&o)[4], float (&d)[4]) {
+            // output activations backward (activation.py:18-22: clamp exp to [1e-6, 1e6] in the backward)
+            d[0] = d[1] = d[2] = d[3] = 0.f;
+            if (live) {
+                const float e = __expf(o[0] + ob0 + blob);
+                d[0] = gs * fminf(fmaxf(e, 1e-6f), 1e6f);
+                const float s1 = 1.f / (1.f + __expf(-(o[1] + ob1))), s2 = 1.f / (1.f + __expf(-(o[2] + ob2))),
+                            s3 = 1.f / (1.f + __expf(-(o[3] + ob3)));
+                d[1] = gr * cfg.sat_scale * s1 * (1.f - s1);
+                d[2] = gg * cfg.sat_scale * s2 * (1.f - s2);
+                d[3] = gb * cfg.sat_scale * s3 * (1.f - s3);
+            }
+            d0 = d[0];
+        });
+        // ---- scatter d(enc) into the table gradient (+ optional d/dx), one level per trip
+        float gx0 = 0.f, gx1 = 0.f, gx2 = 0.f;
+#pragma unroll 1
+        for (int l = 0; l < L; l++) {
+            const float ga = stage[(2 * l) * LD + lane], gb2 = stage[(2 * l + 1) * LD + lane];
+            if (live && (ga != 0.f || gb2 != 0.f)) {
+                const Cell cl = locate(x0, x1, x2, lv.scale[l]);
+                const bool hashed = (lv.hashed >> l) & 1u;
+                const uint32_t res = lv.res[l], size = lv.size[l];
+                float2* __restrict__ gt = g_table + lv.off[l];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float wx = (k & 1) ? cl.w[0] : 1.f - cl.w[0], wy = (k & 2) ? cl.w[1] : 1.f - cl.w[1], wz = (k & 4) ? cl.w[2] : 1.f - cl.w[2];
+                    const uint32_t idx = grid_index(hashed, res, size, cl.g[0] + (k & 1), cl.g[1] + ((k >> 1) & 1), cl.g[2] + (k >> 2));
+                    const float wgt = wx * wy * wz;
+                    red_add_v2(gt + idx, wgt * ga, wgt * gb2);
+                    if (WITH_DX) {
+                        const float2 v = __ldg(table + lv.off[l] + idx);
+                        const float gv = v.x * ga + v.y * gb2;
+                        const float sc = lv.scale[l];
+                        gx0 = fmaf(((k & 1) ? 1.f : -1.f) * cl.dw[0] * sc * wy * wz, gv, gx0);
+                        gx1 = fmaf(((k & 2) ? 1.f : -1.f) * cl.dw[1] * sc * wx * wz, gv, gx1);
+                        gx2 = fmaf(((k & 4) ? 1.f : -1.f) * cl.dw[2] * sc * wx * wy, gv, gx2);
+                    }
+                }
+            }
+        }
+        if (WITH_DX && live) {
+            // x01 = (x + bound) / (2 bound); blob(x) also depends on x where |x|^2 > 0.2 (ingp_decoder.py:101-104)
+            const float r2 = x * x + y * y + z * z;
+            const float gblob = (r2 > 0.2f) ? d0 * blob * (-2.f * cfg.blob_k) : 0.f;
+            g_xyz[(size_t)i * 3] = gx0 * cfg.inv2b + gblob * x;
+            g_xyz[(size_t)i * 3 + 1] = gx1 * cfg.inv2b + gblob * y;
+            g_xyz[(size_t)i * 3 + 2] = gx2 * cfg.inv2b + gblob * z;
+        }
+        __syncwarp();
+    }
+
+    // ---- CTA reduction of the MLP gradients in a fixed warp order, one workspace row per CTA
+    // layout of a row: [dW1 (HID x IN) | db1 (HID) | dW2 (4 x HID) | db2 (4)]
+    __syncthreads();
+    constexpr int NP = n_mlp<L>();
+    float* const s_acc = smem + B::FRAG_FLOATS;           // the staging tiles are free now
+    static_assert(NP <= (BW_T / 32) * WARP_FLOATS, "CTA accumulator does not fit in the staging area");
+    for (int t = threadIdx.x; t < NP; t += BW_T) s_acc[t] = 0.f;
+    __syncthreads();
+    const int g = lane >> 2, t4 = lane & 3;
+    for (int w = 0; w < BW_T / 32; w++) {
+        if (warp == w) {
+#pragma unroll
+            for (int mt = 0; mt < B::MT; mt++) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int hid = 16 * mt + g + 8 * (c >> 1);
+#pragma unroll
+                    for (int ft = 0; ft < B::WT; ft++) {
+                        const int f = 8 * ft + 2 * t4 + (c & 1);
+                        if (f < IN) s_acc[hid * IN + f] += acc.w1[mt][ft][c];
+                        else if (f == IN) s_acc[HID * IN + hid] += acc.w1[mt][ft][c];
+                    }
+                    const int o = 2 * t4 + (c & 1);
+                    if (o < 4) s_acc[HID * IN + HID + o * HID + hid] += acc.w2[mt][c];
+                }
+            }
+            if (lane < 4) s_acc[HID * IN + HID + 4 * HID + lane] += acc.b2;
+        }
+        __syncthreads();
+    }
+    float* row = workspace + (size_t)blockIdx.x * NP;
+    for (int t = threadIdx.x; t < NP; t += BW_T) row[t] = s_acc[t];
+}
+
 // sum the per-CTA rows in a fixed order -> g_w1, g_b1, g_w2, g_b2 (accumulate = add to existing .grad)
 template <int L>
 __global__ void k_field_reduce_mlp(const float* __restrict__ workspace, const uint32_t n_rows, float* __restrict__ g_w1,
@@ -348,7 +477,7 @@ __global__ void k_field_reduce_mlp(const float* __restrict__ workspace, const ui
 extern "C" {
 
 uint32_t mve_field_backward_workspace_floats(uint32_t n_levels) {
-    return (uint32_t)(2 * kNumSM) * (uint32_t)(HID * 2 * n_levels + HID + 4 * HID + 4);
+    return (uint32_t)(3 * kNumSM) * (uint32_t)(HID * 2 * n_levels + HID + 4 * HID + 4);
 }
 
 int mve_field_forward(const float* xyz, uint32_t M, const int32_t* M_dev, const float* table, const float* w1, const float* b1,
@@ -367,7 +496,8 @@ int mve_field_forward(const float* xyz, uint32_t M, const int32_t* M_dev, const 
     const float2* t2 = reinterpret_cast<const float2*>(table);
     cudaStream_t s = (cudaStream_t)stream;
 #define FWD(LL)                                                                                                                          \
-    if (density_only == 2) k_field_density_mma<LL><<<grid2, 128, 0, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, sigma);             \
+    if (density_only == 2) k_field_fwd_mma<LL, true><<<grid2, 128, 0, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, sigma, rgb);      \
+    else if (density_only == 3) k_field_fwd_mma<LL, false><<<grid2, 128, 0, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, sigma, rgb); \
     else if (density_only) k_field_fwd<LL, true><<<grid, 256, 0, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, sigma, rgb);           \
     else k_field_fwd<LL, false><<<grid, 256, 0, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, sigma, rgb);
     if (n_levels == 12) { FWD(12) } else if (n_levels == 14) { FWD(14) } else { FWD(16) }
@@ -380,29 +510,47 @@ int mve_field_backward(const float* xyz, uint32_t M, const int32_t* M_dev, const
                        const float* w2, const float* b2, uint32_t n_levels, const float* level_scale, const uint32_t* level_res,
                        const uint32_t* level_size, const uint32_t* level_offset, float bound, float blob_density, float blob_radius,
                        float sigmoid_saturation, const float* grad_sigma, const float* grad_rgb, float* grad_table, float* grad_w1,
-                       float* grad_b1, float* grad_w2, float* grad_b2, int accumulate_mlp, float* workspace, float* grad_xyz,
-                       void* stream) {
+                       float* grad_b1, float* grad_w2, float* grad_b2, int accumulate_mlp, int mlp_tf32, float* workspace,
+                       float* grad_xyz, void* stream) {
     Levels lv;
     MVE_ARG(fill_levels(lv, n_levels, level_scale, level_res, level_size, level_offset) == 0, "field: n_levels > 16");
     MVE_ARG(n_levels == 12 || n_levels == 14 || n_levels == 16, "field: n_levels must be 12, 14 or 16");
     MVE_ARG(workspace != nullptr, "field backward: workspace required (mve_field_backward_workspace_floats)");
     const FieldCfg cfg = make_cfg(bound, blob_density, blob_radius, sigmoid_saturation);
+    const int ctas_per_sm = mlp_tf32 ? 3 : 2;
     uint32_t grid = cdiv(M > 0 ? M : 1, BW_T);
-    if (grid > (uint32_t)(2 * kNumSM)) grid = 2 * kNumSM;     // M is the buffer capacity when M_dev is given: all CTAs launch
+    if (grid > (uint32_t)(ctas_per_sm * kNumSM)) grid = ctas_per_sm * kNumSM;   // M is the buffer capacity when M_dev is given: all CTAs launch
     const float2* t2 = reinterpret_cast<const float2*>(table);
     float2* gt2 = reinterpret_cast<float2*>(grad_table);
     cudaStream_t s = (cudaStream_t)stream;
+#define BWD_MMA(LL, DX)                                                                                                                  \
+    {                                                                                                                                    \
+        using BC = mlpmma::BCfg<LL>;                                                                                                     \
+        const size_t smem = sizeof(float) * (BC::FRAG_FLOATS + (BW_T / 32) * (BC::STAGE_FLOATS + BC::XCH_FLOATS));                       \
+        static bool attr_done = false;                                                                                                   \
+        if (!attr_done) {                                                                                                                \
+            MVE_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<LL, DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+            attr_done = true;                                                                                                            \
+        }                                                                                                                                \
+        k_field_bwd_mma<LL, DX><<<grid, BW_T, smem, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, grad_sigma, grad_rgb, gt2,          \
+                                                         workspace, grad_xyz);                                                           \
+    }
 #define BWD(LL)                                                                                                                          \
     {                                                                                                                                    \
-        if (grad_xyz) k_field_bwd<LL, true><<<grid, BW_T, 0, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, grad_sigma, grad_rgb, gt2, \
-                                                                  workspace, grad_xyz);                                                  \
-        else k_field_bwd<LL, false><<<grid, BW_T, 0, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, grad_sigma, grad_rgb, gt2,         \
-                                                          workspace, grad_xyz);                                                          \
+        if (mlp_tf32) {                                                                                                                  \
+            if (grad_xyz) BWD_MMA(LL, true) else BWD_MMA(LL, false)                                                                      \
+        } else if (grad_xyz)                                                                                                             \
+            k_field_bwd<LL, true><<<grid, BW_T, 0, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, grad_sigma, grad_rgb, gt2,           \
+                                                        workspace, grad_xyz);                                                            \
+        else                                                                                                                             \
+            k_field_bwd<LL, false><<<grid, BW_T, 0, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, grad_sigma, grad_rgb, gt2,          \
+                                                         workspace, grad_xyz);                                                           \
         k_field_reduce_mlp<LL><<<cdiv(n_mlp<LL>(), 256), 256, 0, s>>>(workspace, grid, grad_w1, grad_b1, grad_w2, grad_b2,               \
                                                                        accumulate_mlp != 0);                                             \
     }
     if (n_levels == 12) BWD(12) else if (n_levels == 14) BWD(14) else BWD(16)
 #undef BWD
+#undef BWD_MMA
     MVE_CHECK_LAUNCH("mve_field_backward");
     return 0;
 }

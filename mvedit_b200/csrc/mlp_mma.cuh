@@ -65,7 +65,8 @@ __device__ __forceinline__ void stage_frags(float* __restrict__ fr, const float*
 }
 
 // Hash-grid encoding of one sample per lane written straight into the warp's [k][sample] staging tile (TF32), one level per
-// loop trip.  The level loop is deliberately NOT unrolled: the fully unrolled encoder is ~4 000 straight-line instructions
+// loop trip (UNROLL = 1; two levels per trip measured 10 % slower in the renderer and 30 % slower in the field forward).
+// The level loop is deliberately NOT unrolled: the fully unrolled encoder is ~4 000 straight-line instructions
 // (64 KB) that every warp streams through once per round, and with the warps of an SM at different points of the
 // march/shade loop the fused renderer became instruction-fetch bound (ncu: stall_no_instruction 11 of 16 cycles per issue,
 // profiles/r01_ncu_k_render_rays_bench_state.txt).  A ~130-instruction loop body stays resident in the instruction caches.

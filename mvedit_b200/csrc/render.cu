@@ -63,10 +63,6 @@ struct RenderParams {
 // missing / early-terminated rays are replaced immediately.
 constexpr int DDA_BUDGET = 8;
 constexpr int CHUNK = 64;
-#ifndef MVE_RENDER_ENC_UNROLL
-#define MVE_RENDER_ENC_UNROLL 1
-#endif
-constexpr int ENC_UNROLL = MVE_RENDER_ENC_UNROLL;
 
 template <int L>
 __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, MarchParams mp, const float2* __restrict__ table,
@@ -173,7 +169,7 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
             if (has) t += dt;
             float o[4];
             float* const stg = stage[threadIdx.x >> 5];
-            mlpmma::encode_staged<L, ENC_UNROLL>(lv, table, (cx + cfg.bound) * cfg.inv2b, (cy + cfg.bound) * cfg.inv2b, (cz + cfg.bound) * cfg.inv2b,
+            mlpmma::encode_staged<L, 1>(lv, table, (cx + cfg.bound) * cfg.inv2b, (cy + cfg.bound) * cfg.inv2b, (cz + cfg.bound) * cfg.inv2b,
                                                  has, stg);
             mlpmma::mlp_forward_staged<L>(stg, frags, o);     // tensor cores, all 32 lanes participate
             if (has) {

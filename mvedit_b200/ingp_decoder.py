@@ -85,13 +85,17 @@ class _FieldFn(Function):
         alloc = torch.empty if m_dev is None else torch.zeros      # capacity buffers: the tail past *m_dev must read as 0
         sigma = alloc(M, dtype=torch.float32, device=xyz.device)
         rgb = None if density_only else alloc(M, 3, dtype=torch.float32, device=xyz.device)
+        # kernel mode: 0/1 = fp32 FFMA MLP (full / density), 2/3 = TF32 tensor-core MLP (density / full)
+        tf32 = bool(getattr(dec, 'mlp_tf32', True))
+        mode = (2 if tf32 or density_only == 2 else 1) if density_only else (3 if tf32 else 0)
         if M > 0:
             call('mve_field_forward', ptr(xyz), c_u32(M), ptr(m_dev), ptr(table), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
                  *dec.encoder._largs.args(), c_f32(dec.bound), c_f32(dec.blob_density), c_f32(dec.blob_radius),
-                 c_f32(dec.sigmoid_saturation), c_int(int(density_only)), ptr(sigma), ptr(rgb), stream())
+                 c_f32(dec.sigmoid_saturation), c_int(mode), ptr(sigma), ptr(rgb), stream())
         ctx.save_for_backward(xyz, table, w1, b1, w2, b2)
         ctx.dec = dec
         ctx.density_only = density_only
+        ctx.tf32 = tf32
         ctx.m_dev = m_dev
         if density_only:
             empty = sigma.new_zeros(0)
@@ -114,7 +118,7 @@ class _FieldFn(Function):
         call('mve_field_backward', ptr(xyz), c_u32(M), ptr(ctx.m_dev), ptr(table), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
              *dec.encoder._largs.args(), c_f32(dec.bound), c_f32(dec.blob_density), c_f32(dec.blob_radius),
              c_f32(dec.sigmoid_saturation), ptr(g_sigma), ptr(g_rgb), ptr(g_table), ptr(g_w1), ptr(g_b1), ptr(g_w2), ptr(g_b2),
-             c_int(0), ptr(ws), ptr(g_xyz), stream())
+             c_int(0), c_int(int(ctx.tf32)), ptr(ws), ptr(g_xyz), stream())
         return g_xyz, g_table, g_w1, g_b1, g_w2, g_b2, None, None, None
 
 
@@ -141,6 +145,9 @@ class iNGPDecoder(nn.Module):
         self.blob_radius = blob_radius
         self.state_dict_bak = None
         self.sample_capacity = 0      # > 0: sync-free training forward with capacity-sized sample buffers
+        # MLP matmuls on tensor cores in TF32 -- what the reference runs (torch.backends.cuda.matmul.allow_tf32 = True,
+        # lib/apis/adapter3d.py:51-61); False selects the fp32 FFMA kernels (exact-parity tests)
+        self.mlp_tf32 = True
         self._ws = None
         self._grid_cache = {}
         self.init_weights()

@@ -3,7 +3,8 @@ training forward against the CPU oracles (oracle/field_oracle.py -- tcnn algorit
 and oracle/raymarching_oracle.c).
 
 Tolerances: forward fp32 rtol 2e-4 (fast-math __expf + different summation order of 8 corners / 24-wide dot products);
-table / MLP gradients rtol 2e-3 relative to the gradient's max (atomic accumulation order)."""
+table / MLP gradients rtol 2e-3 relative to the gradient's max (atomic accumulation order).  With mlp_tf32 (the default, the
+reference's allow_tf32 matmul precision: 10-bit mantissa operands, fp32 accumulation) forward rtol 5e-3, gradients 5e-3 of max."""
 import numpy as np
 import pytest
 import torch
@@ -43,9 +44,11 @@ def test_level_table_matches_oracle_and_survey():
     assert level_table(14, 16, 512)['n_entries'] == 4594792
 
 
-@pytest.mark.parametrize('L,R', [(12, 320), (14, 512)])
-def test_field_forward_backward_vs_oracle(L, R):
+@pytest.mark.parametrize('L,R,tf32', [(12, 320, False), (14, 512, False), (12, 320, True), (14, 512, True), (16, 512, True)])
+def test_field_forward_backward_vs_oracle(L, R, tf32):
     dec, levels, (table, w1, b1, w2, b2) = make_decoder(L, R)
+    dec.mlp_tf32 = tf32
+    ftol, gtol = (5e-3, 5e-3) if tf32 else (2e-4, 2e-3)
     g = torch.Generator().manual_seed(3)
     M = 3001
     xyz = (torch.rand(M, 3, generator=g) * 2 - 1) * 0.999
@@ -59,28 +62,35 @@ def test_field_forward_backward_vs_oracle(L, R):
     # ours
     xg = xyz.cuda().requires_grad_(True)
     sig, rgb, _ = dec.point_decode([xg], None, None)
-    np.testing.assert_allclose(sig.detach().cpu().numpy(), sig_o.detach().numpy(), rtol=2e-4, atol=1e-6)
-    np.testing.assert_allclose(rgb.detach().cpu().numpy(), rgb_o.detach().numpy(), rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(sig.detach().cpu().numpy(), sig_o.detach().numpy(), rtol=ftol, atol=1e-6)
+    np.testing.assert_allclose(rgb.detach().cpu().numpy(), rgb_o.detach().numpy(), rtol=ftol, atol=1e-6)
     sd, _ = dec.point_density_decode([xyz.cuda()], None)
-    np.testing.assert_allclose(sd.detach().cpu().numpy(), sig_o.detach().numpy(), rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(sd.detach().cpu().numpy(), sig_o.detach().numpy(), rtol=ftol, atol=1e-6)
     torch.autograd.backward([sig, rgb], [gs.cuda(), gr.cuda()])
 
     def close(a, b, rel):
         a, b = a.detach().cpu().double().reshape(-1), b.detach().double().reshape(-1)
-        assert (a - b).abs().max().item() <= rel * b.abs().max().item() + 1e-7, ((a - b).abs().max().item(), b.abs().max().item())
+        if tf32:
+            # A TF32 forward flips the ReLU of the few hidden units with |h| < ~1e-4, and each flip moves one sample's whole
+            # contribution to dW1 / db1 / d(table) (measured: 2-9 % of max on single entries, dW2 / db2 -- which do not pass
+            # through the ReLU mask -- 5e-4): the TF32 mode is therefore checked in the L2 norm, the fp32 mode entry by entry.
+            assert (a - b).norm().item() <= 4 * rel * b.norm().item() + 1e-7, ((a - b).norm().item(), b.norm().item())
+        else:
+            assert (a - b).abs().max().item() <= rel * b.abs().max().item() + 1e-7, ((a - b).abs().max().item(), b.abs().max().item())
 
-    close(dec.encoder.params.grad, pt[0].grad, 2e-3)
-    close(dec.mlp.net[0].weight.grad, pt[1].grad, 2e-3)
-    close(dec.mlp.net[0].bias.grad, pt[2].grad, 2e-3)
-    close(dec.mlp.net[1].weight.grad, pt[3].grad, 2e-3)
-    close(dec.mlp.net[1].bias.grad, pt[4].grad, 2e-3)
-    close(xg.grad, xo.grad, 5e-3)   # d/dxyz (DMTet stage)
+    close(dec.encoder.params.grad, pt[0].grad, gtol)
+    close(dec.mlp.net[0].weight.grad, pt[1].grad, gtol)
+    close(dec.mlp.net[0].bias.grad, pt[2].grad, gtol)
+    close(dec.mlp.net[1].weight.grad, pt[3].grad, gtol)
+    close(dec.mlp.net[1].bias.grad, pt[4].grad, gtol)
+    close(xg.grad, xo.grad, 5e-3 if not tf32 else 1e-2)   # d/dxyz (DMTet stage)
 
 
 def test_density_prepass_tf32_tensor_core_mlp():
     """density_only=2 (culling pre-pass): MLP via mma.sync TF32; vs the fp32 oracle within TF32 precision."""
     from mvedit_b200.ingp_decoder import _FieldFn
     dec, levels, params = make_decoder(table_scale=1.0)
+    dec.mlp_tf32 = False          # so that mode 1 below is the fp32 kernel
     g = torch.Generator().manual_seed(11)
     xyz = (torch.rand(5000, 3, generator=g) * 2 - 1)
     with torch.no_grad():
@@ -94,6 +104,7 @@ def test_density_prepass_tf32_tensor_core_mlp():
 
 def test_field_empty_and_tiny():
     dec, levels, params = make_decoder()
+    dec.mlp_tf32 = False
     s, r, n = dec.point_decode([torch.zeros(0, 3, device='cuda')], None, None)
     assert s.numel() == 0 and r.shape == (0, 3) and n == [0]
     s, r, _ = dec.point_decode([torch.zeros(1, 3, device='cuda')], None, None)
@@ -149,9 +160,12 @@ def test_fused_render_vs_oracle_loop():
     torch.testing.assert_close(img_c.reshape(-1, 3)[okc], out['image'][0][okc], rtol=1e-3, atol=1e-4)
 
 
-def test_decoder_training_forward_backward_vs_oracle():
+@pytest.mark.parametrize('tf32', [False, True])
+def test_decoder_training_forward_backward_vs_oracle(tf32):
     """VolumeRenderer.forward training branch with weight culling (base_volume_renderer.py:207-262)."""
     dec, levels, params = make_decoder(table_scale=1.0, weight_culling_th=0.001)
+    dec.mlp_tf32 = tf32
+    tol = 3.0 if tf32 else 1.0
     dec.max_steps = 128
     dec.train()
     H, bitfield, poses, ro, rd, f = _scene(views=1, size=32)
@@ -177,10 +191,10 @@ def test_decoder_training_forward_backward_vs_oracle():
     out = dec(torch.from_numpy(ro).cuda()[None], torch.from_numpy(rd).cuda()[None], None, torch.from_numpy(bitfield).cuda()[None], H,
               dt_gamma=1 / f, perturb=True, noises=torch.from_numpy(noises).cuda())
     assert abs(out['ts'][0].shape[0] - x2.shape[0]) <= max(3, 0.002 * x2.shape[0])
-    ok = np.abs(out['weights_sum'][0].detach().cpu().numpy() - ws_o) < 2e-3
+    ok = np.abs(out['weights_sum'][0].detach().cpu().numpy() - ws_o) < 2e-3 * tol
     assert ok.mean() > 0.99
-    np.testing.assert_allclose(out['image'][0].detach().cpu().numpy()[ok], img_o[ok], rtol=2e-3, atol=5e-5)
-    np.testing.assert_allclose(out['depth'][0].detach().cpu().numpy()[ok], d_o[ok], rtol=2e-3, atol=5e-5)
+    np.testing.assert_allclose(out['image'][0].detach().cpu().numpy()[ok], img_o[ok], rtol=2e-3 * tol, atol=5e-5 * tol)
+    np.testing.assert_allclose(out['depth'][0].detach().cpu().numpy()[ok], d_o[ok], rtol=2e-3 * tol, atol=5e-5 * tol)
     gmask = torch.from_numpy(ok.astype(np.float32)).cuda()
     torch.autograd.backward([out['weights_sum'], out['depth'], out['image']],
                             [torch.from_numpy(gws).cuda()[None] , torch.from_numpy(gd).cuda()[None], torch.from_numpy(gi).cuda()[None]])
@@ -190,8 +204,10 @@ def test_decoder_training_forward_backward_vs_oracle():
     assert (a - b).abs().max() <= 2e-2 * b.abs().max()
 
 
-def test_update_extra_state_vs_oracle():
+@pytest.mark.parametrize('tf32', [False, True])
+def test_update_extra_state_vs_oracle(tf32):
     dec, levels, params = make_decoder(table_scale=1.0)
+    dec.mlp_tf32 = tf32
     H = 32
     g = torch.Generator().manual_seed(5)
     noise = torch.rand(H ** 3, 3, generator=g)
@@ -218,6 +234,6 @@ def test_update_extra_state_vs_oracle():
     bf_o = orc.packbits(new.float().numpy().reshape(-1), thresh)
     got = grid.cpu().float().numpy().reshape(-1)
     exp = new.float().numpy().reshape(-1)
-    np.testing.assert_allclose(got, exp, rtol=2e-3, atol=1e-4)    # fp16 grid: 1 ulp = 1e-3 relative
+    np.testing.assert_allclose(got, exp, rtol=6e-3 if tf32 else 2e-3, atol=1e-4)    # fp16 grid: 1 ulp = 1e-3 relative
     diff = np.unpackbits(bitfield.cpu().numpy().reshape(-1) ^ bf_o).sum()
-    assert diff <= 0.002 * H ** 3
+    assert diff <= (0.004 if tf32 else 0.002) * H ** 3
