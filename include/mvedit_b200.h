@@ -114,7 +114,9 @@ int mve_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int bi
 
 /* C[M,N] = act(A[M,K] . B[N,K]^T + bias[N] + row_bias[row / rows_per_group, N]) * alpha + residual[M,N]
  * A, B, C, residual bf16 (lda/ldb/ldc/ldr in elements, multiples of 8); bias/row_bias f32 or NULL (row_bias row stride ldrb, 0 = N); K % 64 == 0.
- * act: 0 none, 1 SiLU, 2 GELU(erf).  Replaces torch.nn.functional.linear / 1x1 conv (cuBLAS) on the UNet path. */
+ * act: 0 none, 1 SiLU, 2 GELU(erf), 3 GEGLU: every 256 columns of B hold [128 value | 128 gate] rows of a diffusers GEGLU
+ * projection and C gets the N/2 products value * gelu(gate) (ldc >= N/2; no row_bias / residual; N % 256 == 0).
+ * Replaces torch.nn.functional.linear / 1x1 conv (cuBLAS) on the UNet path. */
 int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N, uint32_t K,
                   uint32_t lda, uint32_t ldb, uint32_t ldc,
                   const float* bias, const float* row_bias, uint32_t rows_per_group, uint32_t ldrb,

@@ -102,7 +102,44 @@ __global__ void __launch_bounds__(GN_T) k_gn_apply(const bf16* __restrict__ x, b
     }
 }
 
-// ---------------------------------------------------------------- LayerNorm over the last dim, one warp per row
+// ---------------------------------------------------------------- LayerNorm over the last dim
+// Every width on the SD1.5 path is 320 * {1, 2, 4} = 40 * LPR vectors of 8: LPR = 8 / 16 / 32 lanes share a row with exactly 5
+// vectors each (no idle lanes, the row stays in registers between the statistics and the normalisation: one read, one write).
+template <int LPR>
+__global__ void __launch_bounds__(256) k_layernorm5(const bf16* __restrict__ x, bf16* __restrict__ y, const uint32_t rows, const uint32_t C,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta, const float eps) {
+    constexpr int RPW = 32 / LPR;                      // rows per warp
+    const uint32_t lane = threadIdx.x & 31, sub = lane % LPR;
+    const uint32_t row = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / LPR;
+    const bool ok = row < rows;
+    const bf16* xr = x + (size_t)(ok ? row : 0) * C;
+    float f[5][8];
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        unpack8(*reinterpret_cast<const uint4*>(xr + (sub + LPR * c) * 8), f[c]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { s += f[c][k]; q += f[c][k] * f[c][k]; }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    const float mean = s / C;
+    const float rstd = rsqrtf(fmaxf(q / C - mean * mean, 0.f) + eps);
+    if (!ok) return;
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        const uint32_t v = sub + LPR * c;
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8), b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = (f[c][k] - mean) * rstd * g[k] + b[k];
+        *reinterpret_cast<uint4*>(y + (size_t)row * C + v * 8) = pack8(o);
+    }
+}
+
+// generic width (C % 8 == 0, C <= 1280): one warp per row, up to 5 vectors per lane
 __global__ void __launch_bounds__(256) k_layernorm(const bf16* __restrict__ x, bf16* __restrict__ y, const uint32_t rows, const uint32_t C,
                                                    const float* __restrict__ gamma, const float* __restrict__ beta, const float eps) {
     const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -110,23 +147,28 @@ __global__ void __launch_bounds__(256) k_layernorm(const bf16* __restrict__ x, b
     const bf16* xr = x + (size_t)row * C;
     const uint32_t nvec = C / 8;
     float s = 0.f, q = 0.f;
-    // C <= 1280 on this path: at most 5 vectors per lane, kept in registers
     float f[5][8];
-    int cnt = 0;
-    for (uint32_t v = lane; v < nvec; v += 32, cnt++) {
-        unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f[cnt]);
 #pragma unroll
-        for (int k = 0; k < 8; k++) { s += f[cnt][k]; q += f[cnt][k] * f[cnt][k]; }
+    for (int c = 0; c < 5; c++) {
+        const uint32_t v = lane + 32 * c;
+        if (v < nvec) {
+            unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f[c]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) { s += f[c][k]; q += f[c][k] * f[c][k]; }
+        }
     }
     s = warp_sum(s); q = warp_sum(q);
     const float mean = s / C;
     const float rstd = rsqrtf(fmaxf(q / C - mean * mean, 0.f) + eps);
-    cnt = 0;
-    for (uint32_t v = lane; v < nvec; v += 32, cnt++) {
-        float o[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) o[k] = (f[cnt][k] - mean) * rstd * gamma[v * 8 + k] + beta[v * 8 + k];
-        *reinterpret_cast<uint4*>(y + (size_t)row * C + v * 8) = pack8(o);
+    for (int c = 0; c < 5; c++) {
+        const uint32_t v = lane + 32 * c;
+        if (v < nvec) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) o[k] = (f[c][k] - mean) * rstd * gamma[v * 8 + k] + beta[v * 8 + k];
+            *reinterpret_cast<uint4*>(y + (size_t)row * C + v * 8) = pack8(o);
+        }
     }
 }
 
@@ -220,7 +262,12 @@ int mve_groupnorm_bf16(const void* x, void* y, uint32_t B, uint32_t HW, uint32_t
 int mve_layernorm_bf16(const void* x, void* y, uint32_t rows, uint32_t C, const float* gamma, const float* beta, float eps, void* stream) {
     if (rows == 0) return 0;
     MVE_ARG(C % 8 == 0 && C <= 1280, "layernorm: C % 8 == 0 and C <= 1280 required");
-    k_layernorm<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, rows, C, gamma, beta, eps);
+    const bool al = (((uintptr_t)gamma | (uintptr_t)beta) & 15) == 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (al && C == 320) k_layernorm5<8><<<cdiv(rows, 32), 256, 0, s>>>((const bf16*)x, (bf16*)y, rows, C, gamma, beta, eps);
+    else if (al && C == 640) k_layernorm5<16><<<cdiv(rows, 16), 256, 0, s>>>((const bf16*)x, (bf16*)y, rows, C, gamma, beta, eps);
+    else if (al && C == 1280) k_layernorm5<32><<<cdiv(rows, 8), 256, 0, s>>>((const bf16*)x, (bf16*)y, rows, C, gamma, beta, eps);
+    else k_layernorm<<<cdiv(rows, 8), 256, 0, s>>>((const bf16*)x, (bf16*)y, rows, C, gamma, beta, eps);
     MVE_CHECK_LAUNCH("mve_layernorm_bf16");
     return 0;
 }

@@ -36,7 +36,7 @@ struct GemmParams {
     uint32_t rows_per_group, ldrb;
     const __nv_bfloat16* residual;  // [M, ldr] or null
     uint32_t ldr;
-    int act;                        // 0 none, 1 SiLU, 2 GELU(erf)
+    int act;                        // 0 none, 1 SiLU, 2 GELU(erf), 3 GEGLU (tile = [BN/2 value | BN/2 gate] columns -> BN/2 outputs)
     float alpha;                    // out = act(acc + bias + row_bias) * alpha + residual
     // conv geometry (MODE 1)
     uint32_t H, W, cin_chunks;
@@ -161,6 +161,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
             const bool row_ok = row < p.M;
             const float* rb = (p.row_bias && row_ok) ? p.row_bias + (size_t)(row / p.rows_per_group) * p.ldrb : nullptr;
             constexpr int CH = (BN >= 32) ? 32 : 16;
+            if (BN >= 64 && p.act == 3) {
+                // GEGLU fused into the feed-forward's first projection (diffusers GEGLU: hidden, gate = proj(x).chunk(2); hidden *
+                // gelu(gate)): the weight rows are pre-ordered so that this tile's first BN/2 columns are values and the last BN/2
+                // the matching gates; only the BN/2 products are written (the [M, 2F] intermediate never exists in HBM).
+                constexpr int HB = BN / 2;
+#pragma unroll 1
+                for (int c = half * 32; c < HB; c += 64) {
+                    uint32_t v[32], g[32];
+                    tc::tmem_ld32(t_row + c, v);
+                    tc::tmem_ld32(t_row + HB + c, g);
+                    tc::tmem_ld_wait();
+                    if (row_ok) {
+                        __nv_bfloat16* out = p.C + (size_t)row * p.ldc + nt * HB + c;
+#pragma unroll
+                        for (int gq = 0; gq < 4; gq++) {
+                            float f[8];
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                float a = __uint_as_float(v[gq * 8 + i]), b = __uint_as_float(g[gq * 8 + i]);
+                                if (p.bias) { a += p.bias[n0 + c + gq * 8 + i]; b += p.bias[n0 + HB + c + gq * 8 + i]; }
+                                f[i] = a * (0.5f * b * (1.0f + erff(b * 0.70710678118654752f))) * p.alpha;
+                            }
+                            uint4 o;
+                            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                            for (int i = 0; i < 4; i++) o2[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                            *reinterpret_cast<uint4*>(out + gq * 8) = o;
+                        }
+                    }
+                }
+            } else
 #pragma unroll 1
             for (int c = half * CH; c < BN; c += 2 * CH) {
                 uint32_t v[32];
@@ -312,6 +343,8 @@ int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N,
     MVE_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (16-byte TMA strides)");
     MVE_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "gemm: pointers must be 16-byte aligned");
     MVE_ARG(!row_bias || rows_per_group > 0, "gemm: rows_per_group must be > 0 with row_bias");
+    if (act == 3)
+        MVE_ARG(N % 256 == 0 && !row_bias && !residual, "gemm: GEGLU epilogue needs N % 256 == 0 (value/gate interleaved per 256 columns), no row_bias, no residual");
     const int bn = pick_bn(N);
     CUtensorMap tmA, tmB;
     {

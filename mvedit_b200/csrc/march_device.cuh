@@ -163,6 +163,51 @@ __device__ __forceinline__ bool dda_step(const Ray& r, const MarchParams& p, flo
     return false;
 }
 
+// Lean traversal step of the fused renderer for the configuration every VolumeRenderer call of the reference uses
+// (C == 1, no contraction, H a power of two, 4 <= H <= 256): same arithmetic as dda_step<true> on that path, expression by
+// expression, minus the per-step work that does not depend on the step (mip level, contraction, sign selects) and with the
+// Morton code taken from a 256-entry shared-memory table.  ~6 search trips run per shading round of the renderer, so the
+// trip's instruction count is a first-order term of the render time.
+// per-ray constants packed in one register: bits 0-2 direction component > 0 (x, y, z), bits 3-5 component != 0
+typedef uint32_t RayAux;
+__device__ __forceinline__ RayAux make_aux(const Ray& r) {
+    return (r.dx > 0.f ? 1u : 0u) | (r.dy > 0.f ? 2u : 0u) | (r.dz > 0.f ? 4u : 0u) | (r.dx != 0.f ? 8u : 0u) | (r.dy != 0.f ? 16u : 0u) |
+           (r.dz != 0.f ? 32u : 0u);
+}
+__device__ __forceinline__ bool dda_step_lean(const Ray& r, const RayAux a, const MarchParams& p, const uint32_t* __restrict__ lut,
+                                              float& t, float& cx, float& cy, float& cz, float& dt) {
+    const float bound = p.bound;
+    const float x = clampf(r.ox + t * r.dx, -bound, bound);
+    const float y = clampf(r.oy + t * r.dy, -bound, bound);
+    const float z = clampf(r.oz + t * r.dz, -bound, bound);
+    const float mip_bound = fminf(1.0f, bound);
+    const float mip_rbound = 1 / mip_bound;
+    const float hH = 0.5f * (float)p.H, top = (float)(p.H - 1);
+    const int nx = clampf((x * mip_rbound + 1) * hH, 0.0f, top);
+    const int ny = clampf((y * mip_rbound + 1) * hH, 0.0f, top);
+    const int nz = clampf((z * mip_rbound + 1) * hH, 0.0f, top);
+    const uint32_t index = lut[nx] | (lut[ny] << 1) | (lut[nz] << 2);
+    const unsigned long long blk = *reinterpret_cast<const unsigned long long*>(p.grid + ((index >> 6) << 3));
+    if ((blk >> (index & 63u)) & 1ull) {
+        cx = x; cy = y; cz = z;
+        dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
+        return true;
+    }
+    const bool e = blk == 0ull;      // the whole 4x4x4 block is empty: leave through the block's exit planes
+    // exit plane per axis: cell face nx + (d > 0) [+ 0.5 when d == 0: the reference's nx + 0.5 + 0.5 * sign(d)], block face when skipping
+    const int sx = a & 1u, sy = (a >> 1) & 1u, sz = (a >> 2) & 1u;
+    const bool nzx = a & 8u, nzy = a & 16u, nzz = a & 32u;
+    const float px = (float)((e && nzx) ? (nx & ~3) + 4 * sx : nx + sx) + (nzx ? 0.f : 0.5f);
+    const float py = (float)((e && nzy) ? (ny & ~3) + 4 * sy : ny + sy) + (nzy ? 0.f : 0.5f);
+    const float pz = (float)((e && nzz) ? (nz & ~3) + 4 * sz : nz + sz) + (nzz ? 0.f : 0.5f);
+    const float tx = ((px * p.rH * 2 - 1) * mip_bound - x) * r.rdx;
+    const float ty = ((py * p.rH * 2 - 1) * mip_bound - y) * r.rdy;
+    const float tz = ((pz * p.rH * 2 - 1) * mip_bound - z) * r.rdz;
+    const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+    step_until(t, tt, p, dt);
+    return false;
+}
+
 __device__ __forceinline__ Ray load_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const size_t n) {
     Ray r;
     r.ox = rays_o[n * 3]; r.oy = rays_o[n * 3 + 1]; r.oz = rays_o[n * 3 + 2];

@@ -64,8 +64,8 @@ struct RenderParams {
 constexpr int DDA_BUDGET = 8;
 constexpr int CHUNK = 64;
 
-template <int L>
-__global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, MarchParams mp, const float2* __restrict__ table,
+template <int L, bool LEAN>
+__global__ void __launch_bounds__(128, 4) k_render_rays(const RenderParams rp, MarchParams mp, const float2* __restrict__ table,
                                                      const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                                                      const float* __restrict__ b2, const Levels lv, const FieldCfg cfg,
                                                      unsigned int* __restrict__ next_ray, unsigned long long* __restrict__ stats) {
@@ -73,6 +73,9 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
     using MC = mlpmma::Cfg<L>;
     __shared__ __align__(16) float frags[MC::FRAG_FLOATS];
     __shared__ __align__(16) float stage[4][MC::STAGE_FLOATS];
+    __shared__ uint32_t s_lut[LEAN ? 256 : 1];      // Morton bit expansion of 0..255 (dda_step_lean)
+    if (LEAN)
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = expand_bits((uint32_t)i);
     mlpmma::stage_frags<L>(frags, w1, b1, w2);
     mlpmma::zero_stage_pad<L>(stage[threadIdx.x >> 5]);
     __syncthreads();
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
     const uint32_t tiles_x = rp.w / 8, tpv = tiles_x * (rp.h / 8);
     uint32_t n = 0, step = 0, shaded = 0, shade_rounds = 0, rounds = 0, dda_trips = 0;
     Ray r;
+    RayAux aux = 0;
     float t = 0.f, far = 0.f, ws = 0.f, dsum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
     bool terminated = false;
     float cx = 0.f, cy = 0.f, cz = 0.f, dt = 0.f;
@@ -135,6 +139,7 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
                     r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
                     if (rp.dt_gamma_per_view) mp.dt_gamma = rp.dt_gamma_per_view[v];
                 }
+                if (LEAN) aux = make_aux(r);
                 float near;
                 slab(r, rp.aabb, rp.min_near, near, far);
                 t = near;
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(128) k_render_rays(const RenderParams rp, Marc
             dda_trips++;
             if (searching) {
                 if (!terminated && t < far && step < rp.max_steps) {
-                    has = dda_step<true>(r, mp, t, cx, cy, cz, dt);
+                    has = LEAN ? dda_step_lean(r, aux, mp, s_lut, t, cx, cy, cz, dt) : dda_step<true>(r, mp, t, cx, cy, cz, dt);
                 } else {
                     rp.weights_sum[n] = ws;
                     rp.depth[n] = dsum;
@@ -331,9 +336,12 @@ int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses
     MVE_CUDA(cudaMemsetAsync(g_render_scratch, 0, 48, s));
     unsigned int* next_ray = reinterpret_cast<unsigned int*>(g_render_scratch);
     unsigned long long* stats = reinterpret_cast<unsigned long long*>(g_render_scratch + 8);
-    if (n_levels == 12) k_render_rays<12><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);
-    else if (n_levels == 14) k_render_rays<14><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);
-    else k_render_rays<16><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);
+    const bool lean = C == 1 && mp.h_pow2 && H >= 4 && H <= 256;      // what every VolumeRenderer call of the reference passes
+#define RENDER(LL)                                                                                                        \
+    if (lean) k_render_rays<LL, true><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);         \
+    else k_render_rays<LL, false><<<grid, 128, 0, s>>>(rp, mp, t2, w1, b1, w2, b2, lv, cfg, next_ray, stats);
+    if (n_levels == 12) { RENDER(12) } else if (n_levels == 14) { RENDER(14) } else { RENDER(16) }
+#undef RENDER
     MVE_CHECK_LAUNCH("mve_render_rays");
     return 0;
 }

@@ -9,17 +9,18 @@ import ctypes
 
 from ._lib import call, ptr, raw_ptr, stream, c_int, c_u32, c_f32
 
-ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2}
+ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2, 'geglu': 3}
 
 
 def gemm(a, w, bias=None, row_bias=None, rows_per_group=0, residual=None, act=None, alpha=1.0, out=None):
-    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias + row_bias[row // rows_per_group]) * alpha + residual.   bf16 in/out."""
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias + row_bias[row // rows_per_group]) * alpha + residual.   bf16 in/out.
+    act='geglu': w / bias must be ordered by geglu_interleave(); out[M, N/2] = value * gelu(gate)."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
     M, K = a.shape
     N = w.shape[0]
     if out is None:
-        out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+        out = torch.empty(M, N // 2 if act == 'geglu' else N, dtype=torch.bfloat16, device=a.device)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N
     if row_bias is not None:
@@ -31,6 +32,17 @@ def gemm(a, w, bias=None, row_bias=None, rows_per_group=0, residual=None, act=No
          c_u32(residual.stride(0) if residual is not None else 0), c_int(ACT[act]), c_f32(alpha), stream(),
          _meta=dict(flops=2.0 * M * N * K))
     return out
+
+
+def geglu_interleave(w, b, tile=256):
+    """Reorder a diffusers GEGLU projection ([2F, K] weight: rows 0..F-1 values, F..2F-1 gates) so that every `tile` rows hold
+    [tile/2 values | the tile/2 matching gates] -- the layout mve_gemm_bf16's act=3 epilogue expects."""
+    F = w.shape[0] // 2
+    h = tile // 2
+    assert w.shape[0] % tile == 0
+    idx = torch.arange(F, device=w.device).view(-1, h)
+    perm = torch.cat([idx, idx + F], dim=1).reshape(-1)
+    return w[perm].contiguous(), (None if b is None else b[perm].contiguous())
 
 
 def conv3x3(x, w, bias=None, row_bias=None, residual=None, act=None, alpha=1.0, out=None):

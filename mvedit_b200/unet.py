@@ -59,6 +59,14 @@ class _Weights:
             self.lin[name] = (_bf(w, self.dev), None if b is None else _f32(b, self.dev))
         return self.lin[name]
 
+    def geglu(self, name):
+        """GEGLU projection re-ordered for the fused value * gelu(gate) epilogue (tc_ops.geglu_interleave)."""
+        key = name + '#geglu'
+        if key not in self.lin:
+            w, b = self.linear(name)
+            self.lin[key] = T.geglu_interleave(w, b)
+        return self.lin[key]
+
     def fused(self, key, names):
         if key not in self.lin:
             ws = [self.sd[n + '.weight'].reshape(self.sd[n + '.weight'].shape[0], -1) for n in names]
@@ -166,9 +174,14 @@ class _Net:
         h = T.gemm(o.view(-1, C), wo2, bias=bo2, residual=h)
         # feed-forward (GEGLU)
         n3 = T.layernorm(h, *w.gn(b + '.norm3'))
-        wf1, bf1 = w.linear(b + '.ff.net.0.proj')
         wf2, bf2 = w.linear(b + '.ff.net.2')
-        h = T.gemm(T.geglu(T.gemm(n3, wf1, bias=bf1)), wf2, bias=bf2, residual=h)
+        if w.sd[b + '.ff.net.0.proj.weight'].shape[0] % 256 == 0:
+            wf1, bf1 = w.geglu(b + '.ff.net.0.proj')          # GEGLU inside the projection's epilogue
+            g = T.gemm(n3, wf1, bias=bf1, act='geglu')
+        else:
+            wf1, bf1 = w.linear(b + '.ff.net.0.proj')
+            g = T.geglu(T.gemm(n3, wf1, bias=bf1))
+        h = T.gemm(g, wf2, bias=bf2, residual=h)
         wp, bp = w.linear(p + '.proj_out')
         return T.gemm(h, wp, bias=bp, residual=x.view(-1, C)).view(B, H, W_, C)
 

@@ -72,9 +72,11 @@ def test_field_forward_backward_vs_oracle(L, R, tf32):
         a, b = a.detach().cpu().double().reshape(-1), b.detach().double().reshape(-1)
         if tf32:
             # A TF32 forward flips the ReLU of the few hidden units with |h| < ~1e-4, and each flip moves one sample's whole
-            # contribution to dW1 / db1 / d(table) (measured: 2-9 % of max on single entries, dW2 / db2 -- which do not pass
-            # through the ReLU mask -- 5e-4): the TF32 mode is therefore checked in the L2 norm, the fp32 mode entry by entry.
-            assert (a - b).norm().item() <= 4 * rel * b.norm().item() + 1e-7, ((a - b).norm().item(), b.norm().item())
+            # contribution to dW1 / db1 / d(table) / dxyz (measured: 2-9 % of max on single entries, 1.2-2.1 % in L2; dW2 / db2
+            # -- which do not pass through the ReLU mask -- 5e-4): the TF32 mode is therefore checked in the L2 norm here
+            # (5 %), entry by entry with an always-active ReLU in test_tf32_backward_without_relu_flips, and the fp32 mode
+            # entry by entry.
+            assert (a - b).norm().item() <= 10 * rel * b.norm().item() + 1e-7, ((a - b).norm().item(), b.norm().item())
         else:
             assert (a - b).abs().max().item() <= rel * b.abs().max().item() + 1e-7, ((a - b).abs().max().item(), b.abs().max().item())
 
@@ -83,7 +85,33 @@ def test_field_forward_backward_vs_oracle(L, R, tf32):
     close(dec.mlp.net[0].bias.grad, pt[2].grad, gtol)
     close(dec.mlp.net[1].weight.grad, pt[3].grad, gtol)
     close(dec.mlp.net[1].bias.grad, pt[4].grad, gtol)
-    close(xg.grad, xo.grad, 5e-3 if not tf32 else 1e-2)   # d/dxyz (DMTet stage)
+    close(xg.grad, xo.grad, 5e-3)   # d/dxyz (DMTet stage)
+
+
+def test_tf32_backward_without_relu_flips():
+    """TF32 tensor-core backward with every hidden unit active (b1 = +4): no ReLU decision can differ from the fp32 oracle, so
+    all gradients must agree entry by entry at TF32 precision (operands rounded to 10-bit mantissas, fp32 accumulation)."""
+    dec, levels, (table, w1, b1, w2, b2) = make_decoder(12, 320)
+    b1 = torch.full_like(b1, 4.0)
+    with torch.no_grad():
+        dec.mlp.net[0].bias.copy_(b1)
+    g = torch.Generator().manual_seed(5)
+    M = 4099
+    xyz = (torch.rand(M, 3, generator=g) * 2 - 1) * 0.999
+    pt = [t.clone().requires_grad_(True) for t in (table, w1, b1, w2, b2)]
+    xo = xyz.clone().requires_grad_(True)
+    sig_o, rgb_o = fo.point_decode(xo, *pt, levels)
+    assert float((torch.nn.functional.linear(fo.hash_encode((xyz + 1) / 2, table, levels), w1, b1)).min()) > 0.5
+    gs, gr = torch.randn(M, generator=g), torch.randn(M, 3, generator=g)
+    (sig_o * gs).sum().add((rgb_o * gr).sum()).backward()
+    xg = xyz.cuda().requires_grad_(True)
+    sig, rgb, _ = dec.point_decode([xg], None, None)
+    np.testing.assert_allclose(sig.detach().cpu().numpy(), sig_o.detach().numpy(), rtol=5e-3, atol=1e-6)
+    torch.autograd.backward([sig, rgb], [gs.cuda(), gr.cuda()])
+    for a, b in ((dec.encoder.params.grad, pt[0].grad), (dec.mlp.net[0].weight.grad, pt[1].grad), (dec.mlp.net[0].bias.grad, pt[2].grad),
+                 (dec.mlp.net[1].weight.grad, pt[3].grad), (dec.mlp.net[1].bias.grad, pt[4].grad), (xg.grad, xo.grad)):
+        a, b = a.detach().cpu().double().reshape(-1), b.detach().double().reshape(-1)
+        assert (a - b).abs().max().item() <= 1e-2 * b.abs().max().item() + 1e-7, ((a - b).abs().max().item(), b.abs().max().item())
 
 
 def test_density_prepass_tf32_tensor_core_mlp():
@@ -201,7 +229,10 @@ def test_decoder_training_forward_backward_vs_oracle(tf32):
     a, b = dec.mlp.net[1].weight.grad.cpu().double(), pt[3].grad.double()
     assert (a - b).abs().max() <= 2e-2 * b.abs().max()
     a, b = dec.encoder.params.grad.cpu().double(), pt[0].grad.double().reshape(-1)
-    assert (a - b).abs().max() <= 2e-2 * b.abs().max()
+    if tf32:      # ReLU flips of the TF32 forward (see test_field_forward_backward_vs_oracle): L2
+        assert (a - b).norm() <= 5e-2 * b.norm()
+    else:
+        assert (a - b).abs().max() <= 2e-2 * b.abs().max()
 
 
 @pytest.mark.parametrize('tf32', [False, True])

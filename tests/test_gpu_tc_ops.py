@@ -112,10 +112,28 @@ def test_groupnorm(B, HW, C, silu):
     assert (y.float() - ref).abs().mean().item() <= 4e-3 * ref.abs().mean().item() + 1e-4
 
 
+@pytest.mark.parametrize('M,F,K', [(300, 1280, 320), (4096 + 77, 2560, 640), (128, 128, 64)])
+def test_gemm_fused_geglu_epilogue(M, F, K):
+    """act='geglu': the feed-forward's first projection with GEGLU in the epilogue == unfused GEMM + GEGLU (torch fp32 reference)."""
+    from mvedit_b200 import tc_ops
+    g = torch.Generator(device='cuda').manual_seed(M + F)
+    x = (torch.randn(M, K, device='cuda', generator=g) * 0.5).bfloat16()
+    w = (torch.randn(2 * F, K, device='cuda', generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(2 * F, device='cuda', generator=g) * 0.1
+    h = x.float() @ w.float().t() + b
+    val, gate = h.chunk(2, dim=-1)
+    ref = val * torch.nn.functional.gelu(gate)
+    wi, bi = tc_ops.geglu_interleave(w, b)
+    out = tc_ops.gemm(x, wi, bias=bi, act='geglu')
+    assert out.shape == (M, F)
+    assert (out.float() - ref).abs().max().item() <= 1.5e-2 * ref.abs().max().item()
+    assert (out.float() - ref).abs().mean().item() <= 4e-3 * ref.abs().mean().item() + 1e-5
+
+
 def test_layernorm_geglu_upsample_im2col_layout():
     from mvedit_b200 import tc_ops
     g = torch.Generator(device='cuda').manual_seed(0)
-    for C in (64, 320, 640, 1280):
+    for C in (64, 320, 640, 1280, 960):
         x = torch.randn(777, C, device='cuda', generator=g).bfloat16()
         gamma, beta = torch.randn(C, device='cuda', generator=g), torch.randn(C, device='cuda', generator=g)
         ref = torch.nn.functional.layer_norm(x.float(), (C,), gamma, beta, 1e-5)

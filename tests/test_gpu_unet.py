@@ -154,4 +154,4 @@ def test_controlnet_hint_dedupe_matches_full(tiny):
         d_b, m_b = tiny['cn'][0](x2, 300, pe, c2, 0.7, cond_repeat=2)
     for a, b in zip(d_a + [m_a], d_b + [m_b]):
         # not bit-equal: GroupNorm statistics are accumulated with float atomics (order varies run to run)
-        assert rel(a, b)[0] <= 2e-3
+        assert rel(a, b)[0] <= 1e-2     # bf16 activations: one flipped rounding is 4e-3 relative on that element
