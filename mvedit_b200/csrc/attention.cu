@@ -272,6 +272,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// explicit shared-memory accesses (the exchange buffer is carved out of the dynamic allocation: plain dereferences compile to
+// generic LD/ST, which showed up as the second-largest stall of the softmax loop)
+__device__ __forceinline__ void sts_f32(float* p, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(tc::smem_u32(p)), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(const float* p) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(tc::smem_u32(p)) : "memory");
+    return v;
+}
+
 template <int DPAD>
 __global__ void __launch_bounds__(576, 1) k_attention_pp(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                          const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -288,12 +297,15 @@ __global__ void __launch_bounds__(576, 1) k_attention_pp(const __grid_constant__
     float* xch = reinterpret_cast<float*>(sP + 4 * ATOM_BYTES);   // [2 parity][2 tiles][2 halves][128] row-max exchange (+ final row sums)
     uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 2 * 2 * 128);
     uint64_t* bar_q = bars;               // 1
-    uint64_t* kv_full = bars + 1;         // [2]
-    uint64_t* kv_empty = bars + 3;        // [2]
-    uint64_t* s_full = bars + 5;          // [2 tiles]
-    uint64_t* p_full = bars + 7;          // [2 tiles], 256 arrivals
-    uint64_t* pv_done = bars + 9;         // [2 tiles]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+    uint64_t* k_full = bars + 1;          // [2]
+    uint64_t* k_empty = bars + 3;         // [2]
+    uint64_t* v_full = bars + 5;          // [2]
+    uint64_t* v_empty = bars + 7;         // [2]
+    uint64_t* s_full = bars + 9;          // [2 tiles]
+    uint64_t* s_free = bars + 11;         // [2 tiles], 256 arrivals: S(j) has been read into registers
+    uint64_t* p_full = bars + 13;         // [2 tiles], 256 arrivals
+    uint64_t* pv_done = bars + 15;        // [2 tiles]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t qb = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
@@ -303,8 +315,8 @@ __global__ void __launch_bounds__(576, 1) k_attention_pp(const __grid_constant__
         tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV);
         tc::mbar_init(bar_q, 1);
         for (int s = 0; s < 2; s++) {
-            tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1);
-            tc::mbar_init(&s_full[s], 1); tc::mbar_init(&p_full[s], 256); tc::mbar_init(&pv_done[s], 1);
+            tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1); tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 1);
+            tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_free[s], 256); tc::mbar_init(&p_full[s], 256); tc::mbar_init(&pv_done[s], 1);
         }
         tc::fence_barrier_init();
     }
@@ -320,11 +332,13 @@ __global__ void __launch_bounds__(576, 1) k_attention_pp(const __grid_constant__
             tc::tma_load_4d(sQ, &tmQ, bar_q, 0, head, qb * 256, batch);
             tc::tma_load_4d(sQ + ATOM_BYTES, &tmQ, bar_q, 0, head, qb * 256 + 128, batch);
             uint32_t stage = 0, phase = 0;
-            for (uint32_t j = 0; j < nblk; j++) {
-                tc::mbar_wait(&kv_empty[stage], phase ^ 1);
-                tc::mbar_arrive_expect_tx(&kv_full[stage], 2 * ATOM_BYTES);
-                tc::tma_load_4d(sK + stage * ATOM_BYTES, &tmK, &kv_full[stage], 0, head, j * BKV, batch);
-                tc::tma_load_4d(sV + stage * ATOM_BYTES, &tmV, &kv_full[stage], 0, head, j * BKV, batch);
+            for (uint32_t j = 0; j < nblk; j++) {       // K and V have their own rings: K(j+2) only waits for QK(j), V(j+2) for PV(j)
+                tc::mbar_wait(&k_empty[stage], phase ^ 1);
+                tc::mbar_arrive_expect_tx(&k_full[stage], ATOM_BYTES);
+                tc::tma_load_4d(sK + stage * ATOM_BYTES, &tmK, &k_full[stage], 0, head, j * BKV, batch);
+                tc::mbar_wait(&v_empty[stage], phase ^ 1);
+                tc::mbar_arrive_expect_tx(&v_full[stage], ATOM_BYTES);
+                tc::tma_load_4d(sV + stage * ATOM_BYTES, &tmV, &v_full[stage], 0, head, j * BKV, batch);
                 if (++stage == ST) { stage = 0; phase ^= 1; }
             }
         }
@@ -341,13 +355,29 @@ __global__ void __launch_bounds__(576, 1) k_attention_pp(const __grid_constant__
                                  idesc_qk, kk ? 1u : 0u);
                 tc::umma_commit(&s_full[tile]);
             };
+            // Software pipeline (FlashAttention-3 style): the softmax warps pull S(j) into registers and release the S columns at
+            // once (s_free), so QK(j+1) runs on the tensor pipe while the exponentials of block j are still being computed; PV(j)
+            // follows when P(j) is in shared memory.  The exp phase (the MUFU-bound part) never waits for an MMA round trip.
             tc::mbar_wait(bar_q, 0);
-            tc::mbar_wait(&kv_full[0], 0);
+            tc::mbar_wait(&k_full[0], 0);
             tc::tc_fence_after();
             issue_qk(0, 0);
             issue_qk(1, 0);
+            tc::umma_commit(&k_empty[0]);
             for (uint32_t j = 0; j < nblk; j++) {
                 const uint32_t st = j % ST;
+                if (j + 1 < nblk) {
+                    const uint32_t sn = (j + 1) % ST;
+                    tc::mbar_wait(&k_full[sn], ((j + 1) / ST) & 1);
+#pragma unroll
+                    for (uint32_t tile = 0; tile < 2; tile++) {
+                        tc::mbar_wait(&s_free[tile], j & 1);
+                        tc::tc_fence_after();
+                        issue_qk(tile, j + 1);
+                    }
+                    tc::umma_commit(&k_empty[sn]);
+                }
+                tc::mbar_wait(&v_full[st], (j / ST) & 1);
                 const uint32_t aV = tc::smem_u32(sV + st * ATOM_BYTES);
 #pragma unroll
                 for (uint32_t tile = 0; tile < 2; tile++) {
@@ -359,15 +389,8 @@ __global__ void __launch_bounds__(576, 1) k_attention_pp(const __grid_constant__
                         const uint64_t db = tc::make_desc_mn_sw128(aV + kk * 2048, ATOM_BYTES, 1024);
                         tc::umma_f16(tmem_base + (tile ? O_COL1 : O_COL0), da, db, idesc_pv, (j | kk) ? 1u : 0u);
                     }
-                    if (tile == 1) tc::umma_commit(&kv_empty[st]);
+                    if (tile == 1) tc::umma_commit(&v_empty[st]);
                     tc::umma_commit(&pv_done[tile]);
-                    if (j + 1 < nblk) {
-                        if (tile == 0) {
-                            tc::mbar_wait(&kv_full[(j + 1) % ST], ((j + 1) / ST) & 1);
-                            tc::tc_fence_after();
-                        }
-                        issue_qk(tile, j + 1);
-                    }
                 }
             }
         }
@@ -389,50 +412,58 @@ __global__ void __launch_bounds__(576, 1) k_attention_pp(const __grid_constant__
             const uint32_t kv_valid = min((uint32_t)BKV, p.kv_len - j * BKV);
             const bool full_blk = kv_valid == BKV;
             const uint32_t col0 = half * 64;
+            // S(j): this thread's 64 scores stay in registers for both passes; the TMEM columns are released immediately
+            uint32_t v0[32], v1[32];
+            tc::tmem_ld32(s_addr, v0);
+            tc::tmem_ld32(s_addr + 32, v1);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            tc::mbar_arrive(&s_free[tile]);
             float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 64; c += 32) {
-                uint32_t v[32];
-                tc::tmem_ld32(s_addr + c, v);
-                tc::tmem_ld_wait();
-                if (full_blk) {
+            if (full_blk) {
 #pragma unroll
-                    for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(v[i]));
-                } else {
+                for (int i = 0; i < 32; i++) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+            } else {
 #pragma unroll
-                    for (int i = 0; i < 32; i++)
-                        if (col0 + c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                for (int i = 0; i < 32; i++) {
+                    if (col0 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v0[i]));
+                    if (col0 + 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v1[i]));
                 }
             }
             float* xm = xch + (((j & 1) * 2 + tile) * 2) * 128;
-            xm[half * 128 + row] = mx;
+            sts_f32(xm + half * 128 + row, mx);
             asm volatile("bar.sync %0, 256;" ::"r"(1 + (int)tile) : "memory");
-            mx = fmaxf(mx, xm[(half ^ 1) * 128 + row]);
-            const float m_new = fmaxf(m, mx * p.scale_log2);
+            mx = fmaxf(mx, lds_f32(xm + (half ^ 1) * 128 + row));
+            // Lazy rescaling (FlashAttention-4): the running reference m only moves when the row maximum grows by more than 2^8;
+            // until then P = 2^(s - m) may exceed 1 (<= 256, exact in fp32 / fine in bf16) and O, l keep their scale -- the final
+            // O / l is unchanged, but the TMEM round trip that rescales O disappears from almost every block.
+            const float mx_s = mx * p.scale_log2;
+            const float m_new = (mx_s > m + 8.0f) ? mx_s : m;
             const float alpha = ex2_approx(m - m_new);
-            if (j > 0) {
+            // PV(j-1) must have finished before O is rescaled or P is overwritten: with lazy rescaling the rescale is rare, so
+            // the wait normally moves behind the exponentials (the MUFU-bound part) where PV(j-1) has long completed.
+            const bool resc = j > 0 && __any_sync(0xffffffffu, alpha != 1.0f);
+            if (resc) {
                 tc::mbar_wait(&pv_done[tile], (j - 1) & 1);
                 tc::tc_fence_after();
-                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
-                    for (int c = oc_lo; c < oc_hi; c++) {
-                        uint32_t v[16];
-                        tc::tmem_ld16(o_addr + c * 16, v);
-                        tc::tmem_ld_wait();
+                for (int c = oc_lo; c < oc_hi; c++) {
+                    uint32_t v[16];
+                    tc::tmem_ld16(o_addr + c * 16, v);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                        tmem_st16(o_addr + c * 16, v);
-                    }
-                    tmem_st_wait();
+                    for (int i = 0; i < 16; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                    tmem_st16(o_addr + c * 16, v);
                 }
+                tmem_st_wait();
             }
-            float lsum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 64; c += 32) {
-                uint32_t v[32];
-                tc::tmem_ld32(s_addr + c, v);
-                tc::tmem_ld_wait();
-                uint32_t pk[16];
+            float lsum0 = 0.f, lsum1 = 0.f;
+            uint32_t pk2[2][16];
+#pragma unroll
+            for (int cb = 0; cb < 2; cb++) {
+                const uint32_t* v = cb ? v1 : v0;
+                const int c = cb * 32;
+                uint32_t (&pk)[16] = pk2[cb];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                     float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
@@ -442,15 +473,22 @@ __global__ void __launch_bounds__(576, 1) k_attention_pp(const __grid_constant__
                         if (col0 + c + i + 1 >= kv_valid) p1 = 0.f;
                     }
                     const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-                    lsum += p0 + p1;
+                    lsum0 += p0; lsum1 += p1;
                     pk[i / 2] = *reinterpret_cast<const uint32_t*>(&b2);
                 }
+            }
+            if (j > 0 && !resc) {
+                tc::mbar_wait(&pv_done[tile], (j - 1) & 1);
+                tc::tc_fence_after();
+            }
+#pragma unroll
+            for (int cb = 0; cb < 2; cb++)
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const uint32_t chunk = (c / 8 + q) ^ sw;
-                    *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    const uint32_t chunk = (cb * 4 + q) ^ sw;
+                    *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk2[cb][4 * q], pk2[cb][4 * q + 1], pk2[cb][4 * q + 2], pk2[cb][4 * q + 3]);
                 }
-            }
+            const float lsum = lsum0 + lsum1;
             l = l * alpha + lsum;
             m = m_new;
             tc::fence_proxy_async_smem();
@@ -500,7 +538,7 @@ __global__ void __launch_bounds__(576, 1) k_attention_pp(const __grid_constant__
 template <int DPAD>
 int launch_attn_pp(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, uint32_t heads, uint32_t batch,
                    cudaStream_t s) {
-    constexpr int SMEM = ATOM_BYTES * (2 + 2 + 2 + 4) + 2 * 2 * 2 * 128 * 4 + 1024 + 256;
+    constexpr int SMEM = ATOM_BYTES * (2 + 2 + 2 + 4) + 2 * 2 * 2 * 128 * 4 + 1024 + 256;   // 256 B of barriers: 17 x 8 + 4
     static bool configured = false;
     if (!configured) {
         MVE_CUDA(cudaFuncSetAttribute(k_attention_pp<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
