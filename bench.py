@@ -376,7 +376,7 @@ def raymarch_microbench(device, pk):
     def march():
         counter.zero_()
         call('mve_march_rays_train', ptr(ro), ptr(rd), ptr(bf), c_f32(1.0), c_int(0), c_f32(1 / f), c_u32(1024), c_u32(N), c_u32(1), c_u32(H),
-             ptr(nears), ptr(fars), ptr(noises), ptr(xb), ptr(db), ptr(tb), c_u32(M + 16), ptr(rays2), ptr(counter), ptr(None), stream())
+             ptr(nears), ptr(fars), ptr(noises), ptr(xb), ptr(db), ptr(tb), c_u32(M + 16), ptr(rays2), ptr(counter), ptr(None), ptr(None), stream())
 
     fwd()
     tf, tbw, tm = t_of(fwd), t_of(bwd), t_of(march)

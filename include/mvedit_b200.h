@@ -57,13 +57,15 @@ int mve_packbits(const void* grid, int grid_is_half, uint32_t N, float density_t
  * offset+count > M as an empty ray, raymarching.cu:523).  If xyzs == NULL only rays/counter are written
  * (the reference's first pass).  noises [N] f32 may be NULL (= zeros, perturb=False).
  * dirs may be NULL (view-independent fields never read it).
- * dt_gamma_dev (optional, device, 1 float) overrides dt_gamma so a captured CUDA graph can change it between replays. */
+ * dt_gamma_dev (optional, device, 1 float) overrides dt_gamma so a captured CUDA graph can change it between replays.
+ * t_scratch (optional, device, N * max_steps floats): the counting pass records every sample's t there and the write pass
+ * becomes a coalesced warp-per-ray expansion instead of a second walk of the grid (two launches; same samples, bit for bit). */
 int mve_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* density_bitfield,
                          float bound, int contract, float dt_gamma, uint32_t max_steps,
                          uint32_t N, uint32_t C, uint32_t H,
                          const float* nears, const float* fars, const float* noises,
                          float* xyzs, float* dirs, float* ts, uint32_t max_M,
-                         int32_t* rays, int32_t* counter, const float* dt_gamma_dev, void* stream);
+                         int32_t* rays, int32_t* counter, const float* dt_gamma_dev, float* t_scratch, void* stream);
 /* second pass of the reference protocol: rays[n] already holds (offset,count); write the samples. */
 int mve_march_rays_train_write(const float* rays_o, const float* rays_d, const uint8_t* density_bitfield,
                                float bound, int contract, float dt_gamma, uint32_t max_steps,

@@ -174,6 +174,7 @@ __device__ __forceinline__ RayAux make_aux(const Ray& r) {
     return (r.dx > 0.f ? 1u : 0u) | (r.dy > 0.f ? 2u : 0u) | (r.dz > 0.f ? 4u : 0u) | (r.dx != 0.f ? 8u : 0u) | (r.dy != 0.f ? 16u : 0u) |
            (r.dz != 0.f ? 32u : 0u);
 }
+template <bool BLOCK = true>
 __device__ __forceinline__ bool dda_step_lean(const Ray& r, const RayAux a, const MarchParams& p, const uint32_t* __restrict__ lut,
                                               float& t, float& cx, float& cy, float& cz, float& dt) {
     const float bound = p.bound;
@@ -187,13 +188,19 @@ __device__ __forceinline__ bool dda_step_lean(const Ray& r, const RayAux a, cons
     const int ny = clampf((y * mip_rbound + 1) * hH, 0.0f, top);
     const int nz = clampf((z * mip_rbound + 1) * hH, 0.0f, top);
     const uint32_t index = lut[nx] | (lut[ny] << 1) | (lut[nz] << 2);
-    const unsigned long long blk = *reinterpret_cast<const unsigned long long*>(p.grid + ((index >> 6) << 3));
-    if ((blk >> (index & 63u)) & 1ull) {
+    bool occ, e = false;
+    if (BLOCK) {
+        const unsigned long long blk = *reinterpret_cast<const unsigned long long*>(p.grid + ((index >> 6) << 3));
+        occ = (blk >> (index & 63u)) & 1ull;
+        e = blk == 0ull;             // the whole 4x4x4 block is empty: leave through the block's exit planes
+    } else {
+        occ = p.grid[index >> 3] & (1 << (index & 7u));   // per-cell walk only: bit-identical to the reference (training marcher)
+    }
+    if (occ) {
         cx = x; cy = y; cz = z;
         dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
         return true;
     }
-    const bool e = blk == 0ull;      // the whole 4x4x4 block is empty: leave through the block's exit planes
     // exit plane per axis: cell face nx + (d > 0) [+ 0.5 when d == 0: the reference's nx + 0.5 + 0.5 * sign(d)], block face when skipping
     const int sx = a & 1u, sy = (a >> 1) & 1u, sz = (a >> 2) & 1u;
     const bool nzx = a & 8u, nzy = a & 16u, nzz = a & 32u;

@@ -161,6 +161,92 @@ __global__ void __launch_bounds__(MT_T) k_march_train(const float* __restrict__ 
     march_one<true>(r, p, near, far, noise, cnt, xyzs + (size_t)offset * 3, dirs ? dirs + (size_t)offset * 3 : nullptr, ts + (size_t)offset * 2);
 }
 
+// Single-march variant of the fused train marcher: the counting pass records every sample's t in a scratch row, so the write
+// pass no longer walks the occupancy grid a second time -- it is a warp-per-ray, coalesced expansion t -> (xyz, dirs, ts).
+// The march itself is one thread per ray (the t sequence of a ray is inherently sequential) and latency-bound: 16 384 rays are
+// 3.5 warps per SM, so halving the serial work is the lever.  LEAN: dda_step_lean<false> (same per-cell walk, cheaper steps).
+constexpr int MR_T = 64;
+template <bool LEAN>
+__global__ void __launch_bounds__(MR_T) k_march_record(const float* __restrict__ rays_o, const float* __restrict__ rays_d, MarchParams p,
+                                                       const float* __restrict__ dt_gamma_dev, const uint32_t max_steps, const uint32_t N,
+                                                       const float* __restrict__ nears, const float* __restrict__ fars,
+                                                       const float* __restrict__ noises, float* __restrict__ t_scratch,
+                                                       int* __restrict__ rays, int* __restrict__ counter) {
+    __shared__ uint32_t warp_tot[MR_T / 32];
+    __shared__ uint32_t cta_base;
+    __shared__ uint32_t s_lut[LEAN ? 256 : 1];
+    if (LEAN) {
+        for (int i = threadIdx.x; i < 256; i += MR_T) s_lut[i] = expand_bits((uint32_t)i);
+        __syncthreads();
+    }
+    const uint32_t n = threadIdx.x + blockIdx.x * MR_T;
+    const bool live = n < N;
+    if (dt_gamma_dev) p.dt_gamma = dt_gamma_dev[0];
+    uint32_t cnt = 0;
+    if (live) {
+        const Ray r = load_ray(rays_o, rays_d, n);
+        const RayAux aux = make_aux(r);
+        const float far = fars[n];
+        float t = nears[n];
+        t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * (noises ? noises[n] : 0.0f);
+        float* __restrict__ row = t_scratch + (size_t)n * max_steps;
+        float cx, cy, cz, dt;
+        while (t < far && cnt < max_steps) {
+            const bool hit = LEAN ? dda_step_lean<false>(r, aux, p, s_lut, t, cx, cy, cz, dt) : dda_step(r, p, t, cx, cy, cz, dt);
+            if (hit) {
+                row[cnt++] = t;
+                t += dt;
+            }
+        }
+    }
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < MR_T / 32; w++) { const uint32_t v = warp_tot[w]; warp_tot[w] = tot; tot += v; }
+        cta_base = tot ? (uint32_t)atomicAdd(counter, (int)tot) : 0u;
+    }
+    __syncthreads();
+    if (!live) return;
+    rays[n * 2] = (int)(cta_base + warp_tot[warp] + incl - cnt);
+    rays[n * 2 + 1] = (int)cnt;
+}
+
+// t -> sample: the expressions of dda_step's occupied branch and march_one's write (no contraction on this path)
+__global__ void __launch_bounds__(256) k_march_expand(const float* __restrict__ rays_o, const float* __restrict__ rays_d, MarchParams p,
+                                                      const float* __restrict__ dt_gamma_dev, const uint32_t max_steps, const uint32_t N,
+                                                      const float* __restrict__ t_scratch, const int* __restrict__ rays,
+                                                      float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ ts,
+                                                      const uint32_t max_M) {
+    const uint32_t n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    if (dt_gamma_dev) p.dt_gamma = dt_gamma_dev[0];
+    const uint32_t offset = rays[n * 2], cnt = rays[n * 2 + 1];
+    if (cnt == 0 || (uint64_t)offset + cnt > max_M) return;
+    const Ray r = load_ray(rays_o, rays_d, n);
+    const float bound = p.bound;
+    const float* __restrict__ row = t_scratch + (size_t)n * max_steps;
+    for (uint32_t s = lane; s < cnt; s += 32) {
+        const float t = row[s];
+        const float x = clampf(r.ox + t * r.dx, -bound, bound);
+        const float y = clampf(r.oy + t * r.dy, -bound, bound);
+        const float z = clampf(r.oz + t * r.dz, -bound, bound);
+        const float dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
+        const size_t o = (size_t)offset + s;
+        xyzs[o * 3] = x; xyzs[o * 3 + 1] = y; xyzs[o * 3 + 2] = z;
+        if (dirs) { dirs[o * 3] = r.dx; dirs[o * 3 + 1] = r.dy; dirs[o * 3 + 2] = r.dz; }
+        ts[o * 2] = t + dt; ts[o * 2 + 1] = dt;
+    }
+}
+
 // second pass only (reference protocol: offsets already in rays)
 __global__ void __launch_bounds__(MT_T) k_march_train_write(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const MarchParams p,
                                                             const uint32_t N, const float* __restrict__ nears, const float* __restrict__ fars,
@@ -453,10 +539,19 @@ int mve_packbits(const void* grid, int grid_is_half, uint32_t N, float density_t
 int mve_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* density_bitfield, float bound, int contract,
                          float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, const float* nears, const float* fars,
                          const float* noises, float* xyzs, float* dirs, float* ts, uint32_t max_M, int32_t* rays, int32_t* counter,
-                         const float* dt_gamma_dev, void* stream) {
+                         const float* dt_gamma_dev, float* t_scratch, void* stream) {
     if (N == 0) return 0;
     MVE_ARG(max_steps > 0 && H > 0 && C > 0, "march_rays_train: max_steps, H, C must be positive");
     const MarchParams p = make_params(density_bitfield, bound, contract != 0, dt_gamma, max_steps, C, H);
+    if (t_scratch && xyzs && !contract) {          // single march + coalesced expansion
+        cudaStream_t s = (cudaStream_t)stream;
+        const bool lean = C == 1 && p.h_pow2 && H >= 4 && H <= 256;
+        if (lean) k_march_record<true><<<cdiv(N, MR_T), MR_T, 0, s>>>(rays_o, rays_d, p, dt_gamma_dev, max_steps, N, nears, fars, noises, t_scratch, rays, counter);
+        else k_march_record<false><<<cdiv(N, MR_T), MR_T, 0, s>>>(rays_o, rays_d, p, dt_gamma_dev, max_steps, N, nears, fars, noises, t_scratch, rays, counter);
+        k_march_expand<<<cdiv(N, 8), 256, 0, s>>>(rays_o, rays_d, p, dt_gamma_dev, max_steps, N, t_scratch, rays, xyzs, dirs, ts, max_M);
+        MVE_CHECK_LAUNCH("mve_march_rays_train");
+        return 0;
+    }
     k_march_train<<<cdiv(N, MT_T), MT_T, 0, (cudaStream_t)stream>>>(rays_o, rays_d, p, dt_gamma_dev, max_steps, N, nears, fars, noises, xyzs, dirs, ts,
                                                                      max_M, rays, counter);
     MVE_CHECK_LAUNCH("mve_march_rays_train");

@@ -132,10 +132,12 @@ def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars,
         xyzs = alloc(max_points, 3, dtype=torch.float32, device=dev)
         dirs = torch.empty(max_points, 3, dtype=torch.float32, device=dev) if want_dirs else None
         ts = alloc(max_points, 2, dtype=torch.float32, device=dev)
+        # single march: the counting pass records each sample's t, the write pass is a coalesced expansion (no second grid walk)
+        t_scratch = None if (contract or N * max_steps > (1 << 27)) else torch.empty(N * max_steps, dtype=torch.float32, device=dev)
         call('mve_march_rays_train', *common, ptr(xyzs), ptr(dirs), ptr(ts), c_u32(max_points), ptr(rays), ptr(counter),
-             ptr(dt_gamma if isinstance(dt_gamma, torch.Tensor) else None), stream())
+             ptr(dt_gamma if isinstance(dt_gamma, torch.Tensor) else None), ptr(t_scratch), stream())
         return xyzs, dirs, ts, rays, counter
-    call('mve_march_rays_train', *common, ptr(None), ptr(None), ptr(None), c_u32(0), ptr(rays), ptr(counter), ptr(None), stream())
+    call('mve_march_rays_train', *common, ptr(None), ptr(None), ptr(None), c_u32(0), ptr(rays), ptr(counter), ptr(None), ptr(None), stream())
     M = int(counter.item())
     xyzs = torch.empty(M, 3, dtype=torch.float32, device=dev)
     dirs = torch.empty(M, 3, dtype=torch.float32, device=dev)

@@ -149,9 +149,16 @@ def test_controlnet_hint_dedupe_matches_full(tiny):
     pe = torch.randn(2 * N, 77, cfg.cross_attention_dim, device='cuda', generator=g)
     ci = torch.rand(N, 3, 8 * L, 8 * L, device='cuda', generator=g)
     x2, c2 = torch.cat([lat] * 2), torch.cat([ci] * 2)
+    cn = tiny['cn'][0]
     with torch.no_grad():
-        d_a, m_a = tiny['cn'][0](x2, 300, pe, c2, 0.7)
-        d_b, m_b = tiny['cn'][0](x2, 300, pe, c2, 0.7, cond_repeat=2)
+        # the de-duplicated part itself is deterministic (tcgen05 convolutions, no atomics): bit-equal
+        base, wc, bc = cn.conv_in(x2)
+        from mvedit_b200 import tc_ops as T
+        base = T.conv3x3(base, wc, bias=bc)
+        assert torch.equal(cn.cond_embedding(c2, base, 1), cn.cond_embedding(c2, base, 2))
+        d_a, m_a = cn(x2, 300, pe, c2, 0.7)
+        d_b, m_b = cn(x2, 300, pe, c2, 0.7, cond_repeat=2)
     for a, b in zip(d_a + [m_a], d_b + [m_b]):
-        # not bit-equal: GroupNorm statistics are accumulated with float atomics (order varies run to run)
-        assert rel(a, b)[0] <= 1e-2     # bf16 activations: one flipped rounding is 4e-3 relative on that element
+        # downstream the two runs are not bit-equal: GroupNorm statistics are accumulated with float atomics (order varies run to
+        # run) and a flipped bf16 rounding is amplified by the random-weight net; the exact check is the one above
+        assert rel(a, b)[0] <= 5e-2
