@@ -186,6 +186,15 @@ int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses
  * warp-level trips of the occupancy-grid search loop (host-synchronous; diagnostics / bench only). */
 int mve_render_last_sample_count(uint64_t* host_out);
 
+/* Post-render shading of denoise P2's hint images, two launches for all views (replaces ~40 elementwise torch kernels):
+ * BaseNeRF.render's tail (inverse-z depth, depth / alpha, depth_to_normal: base_nerf.py:536-556, geometry_utils.py:119-148),
+ * Lambert shading + background compositing (mvedit_3d_pipeline.py:1352-1380) and normalize_depth (geometry_utils.py:151-168).
+ * weights_sum / depth [V,h,w], image [V,h,w,3] are mve_render_rays' outputs; intrinsics [V,4] at the render size; lights [V,3].
+ * out_images / out_depths: bf16 [V,3,h,w] (NCHW), both clamped to [0,1]; reduce_scratch: [V,2] i32 of device scratch. */
+int mve_shade_views(const float* weights_sum, const float* depth, const float* image, const float* intrinsics, const float* lights,
+                    uint32_t V, uint32_t h, uint32_t w, float ambient, float bg_color, float far_depth, float alpha_clip, float eps,
+                    int32_t* reduce_scratch, void* out_images, void* out_depths, void* stream);
+
 /* Weight culling of the training branch (base_volume_renderer.py:222-246): keep samples with weight > th, compact xyzs/ts,
  * rebuild rays (offset,count); *counter (zeroed by the caller) receives the kept total.  Rays whose kept samples would not fit
  * in the M_out_cap-sample output buffers are emitted as empty. */

@@ -22,6 +22,7 @@ import torch
 from .adapter3d_mixin import Adapter3DMixin
 from .nerf import nerf_optim, normalize_depth
 from . import view_shard
+from ._lib import call, ptr, stream, c_u32, c_f32
 
 
 def get_noise_scales(alphas_bar, t, num_timesteps, dtype=torch.float32):
@@ -85,6 +86,27 @@ class MVEdit3DStep(Adapter3DMixin):
     # ------------------------------------------------------------------ render all (local) views, mvedit_3d_pipeline.py:1341-1395
     def render_views(self, density_bitfield, camera_poses, intrinsics, intrinsics_size, render_size, cam_lights, ambient_light,
                      testmode_dt_gamma_scale):
+        """-> (ctrl_images, ctrl_depths), bf16 [V,3,rs,rs] in [0,1].  One fused render launch + mve_shade_views (two launches) when no
+        tone mapping is configured; ``render_views_torch`` is the op-by-op restatement of the reference it is tested against."""
+        if self.tonemapping is not None:
+            return self.render_views_torch(density_bitfield, camera_poses, intrinsics, intrinsics_size, render_size, cam_lights,
+                                           ambient_light, testmode_dt_gamma_scale)
+        nerf = self.nerf
+        K = (intrinsics * (render_size / intrinsics_size)).float().contiguous()
+        dt_gamma = float(testmode_dt_gamma_scale * 2 / (K[:, 0] + K[:, 1]).mean())
+        ws, depth, image = nerf.decoder.render_cameras(camera_poses, K, render_size, render_size, density_bitfield, nerf.grid_size,
+                                                       dt_gamma=dt_gamma)
+        V, dev = K.shape[0], K.device
+        images = torch.empty(V, 3, render_size, render_size, dtype=torch.bfloat16, device=dev)
+        depths = torch.empty_like(images)
+        scratch = torch.empty(V, 2, dtype=torch.int32, device=dev)
+        call('mve_shade_views', ptr(ws), ptr(depth), ptr(image), ptr(K), ptr(cam_lights.float().contiguous()), c_u32(V), c_u32(render_size),
+             c_u32(render_size), c_f32(float(ambient_light)), c_f32(float(nerf.bg_color)), c_f32(0.25), c_f32(0.5), c_f32(1e-5),
+             ptr(scratch), ptr(images), ptr(depths), stream())
+        return images, depths
+
+    def render_views_torch(self, density_bitfield, camera_poses, intrinsics, intrinsics_size, render_size, cam_lights, ambient_light,
+                           testmode_dt_gamma_scale):
         nerf = self.nerf
         rgba, depth, normal, normal_fg = nerf.render(
             nerf.decoder, None, density_bitfield, render_size, render_size, intrinsics[None] * (render_size / intrinsics_size),

@@ -73,3 +73,37 @@ def test_nerf_optim_fits_targets(mode):
         nerf.decoder.encoder.params.zero_()
     nerf.decoder.restore_state_dict()
     assert nerf.decoder.encoder.params.abs().sum() > 0
+
+
+def test_fused_shade_views_matches_torch_restatement():
+    """mve_shade_views (inverse-z depth, depth_to_normal, Lambert shading, background compositing, normalize_depth in two launches)
+    == the op-by-op torch restatement of base_nerf.py:536-556 / geometry_utils.py:119-168 / mvedit_3d_pipeline.py:1352-1380.
+    Outputs are bf16 in [0,1]: a differently rounded fp32 intermediate may flip one bf16 rounding (2^-8 near 1)."""
+    from mvedit_b200.nerf import BaseNeRF, nerf_optim
+    from mvedit_b200.ingp_decoder import iNGPDecoder
+    from mvedit_b200.pipeline import MVEdit3DStep
+    torch.manual_seed(0)
+    V, size, ps = 4, 64, 32
+    poses = torch.from_numpy(synth.surround_poses(V, seed=3)).cuda()
+    f = 0.5 * size / math.tan(math.radians(15))
+    K = torch.tensor([[f, f, size / 2, size / 2]] * V, device='cuda')
+    tgt_images, tgt_masks = _targets(poses, K, size)
+    nerf = BaseNeRF(grid_size=64, decoder=iNGPDecoder(max_steps=256, weight_culling_th=0.001), patch_size=ps).cuda()
+    grid, bitfield = nerf.get_init_density_grid(1, 'cuda'), nerf.get_init_density_bitfield(1, 'cuda')
+    opt = torch.optim.Adam(nerf.decoder.parameters(), lr=0.01)
+    lights = torch.nn.functional.normalize(torch.randn(V, 3, device='cuda'), dim=-1)
+    nerf_optim(nerf, tgt_images, tgt_masks, None, optimizer=opt, lr=0.01, inverse_steps=120, n_inverse_rays=ps * ps * 2, patch_rgb_weight=0.0,
+               patch_normal_weight=0.0, alpha_soften=0.02, normal_reg_weight=0.1, entropy_weight=0.01, nerf_code=None, density_grid=grid,
+               density_bitfield=bitfield, render_size=size, intrinsics=K, intrinsics_size=size, camera_poses=poses,
+               cam_weights=torch.ones(V, device='cuda'), cam_lights=lights, patch_size=ps, is_init=True, bg_width=0.015, ambient_light=0.2,
+               dt_gamma_scale=0.5, init_shaded=False)
+    step = MVEdit3DStep(None, None, nerf, None)
+    with torch.no_grad():
+        for rs in (64, 96):       # 96: intrinsics rescaled, size not a multiple of the 32 x 8 pixel CTA tile
+            img_f, dep_f = step.render_views(bitfield, poses, K, size, rs, lights, 0.2, 0.5)
+            img_t, dep_t = step.render_views_torch(bitfield, poses, K, size, rs, lights, 0.2, 0.5)
+            assert img_f.shape == img_t.shape == (V, 3, rs, rs) and dep_f.shape == dep_t.shape
+            assert float(dep_t.float().max()) > 0.5 and float((img_t.float() < 0.99).float().mean()) > 0.05      # the object is there
+            for a, b in ((img_f, img_t), (dep_f, dep_t)):
+                d = (a.float() - b.float()).abs()
+                assert float(d.max()) <= 2.0 ** -7 and float((d > 0).float().mean()) < 0.02, (float(d.max()), float((d > 0).float().mean()))
