@@ -65,7 +65,7 @@ constexpr int DDA_BUDGET = 8;
 constexpr int CHUNK = 64;
 
 template <int L, bool LEAN>
-__global__ void __launch_bounds__(128, 4) k_render_rays(const RenderParams rp, MarchParams mp, const float2* __restrict__ table,
+__global__ void __launch_bounds__(128, 5) k_render_rays(const RenderParams rp, MarchParams mp, const float2* __restrict__ table,
                                                      const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                                                      const float* __restrict__ b2, const Levels lv, const FieldCfg cfg,
                                                      unsigned int* __restrict__ next_ray, unsigned long long* __restrict__ stats) {
