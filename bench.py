@@ -123,6 +123,17 @@ def build(device, rank, world):
     return pipe
 
 
+_JSON_FD = None
+
+
+def emit_json(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def run_ours(args):
     import torch.distributed as dist
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -132,7 +143,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the single JSON line (NCCL prints its version banner there otherwise)
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # keep stdout to the single JSON line (NCCL prints its version banner there otherwise)
         dist.init_process_group('nccl', device_id=device)
     from mvedit_b200 import view_shard, _lib
     pipe = build(device, rank, world)
@@ -221,7 +232,7 @@ def run_ours(args):
     from mvedit_b200.nerf import nerf_optim
     with torch.no_grad():
         t_init0 = time.time()
-        nerf_optim(pipe.nerf, tgt_img[None], tgt_msk[None], None, opt, 0.01, 64 if args.profile_step else 640, N_INVERSE_RAYS, 0.0, 0.0, 0.02, 0.1, 0.01, None, grid, bitfield,
+        nerf_optim(pipe.nerf, tgt_img[None], tgt_msk[None], None, opt, 0.01, 640, N_INVERSE_RAYS, 0.0, 0.0, 0.02, 0.1, 0.01, None, grid, bitfield,
                    IMG, K, IMG, poses, cam_w, lights, 128, True, 0.015, 0.2, 1.0, init_shaded=False)
         torch.cuda.synchronize()
         init_s = time.time() - t_init0
@@ -284,11 +295,11 @@ def run_ours(args):
                 occupied_cells=int((((bitfield.view(-1).to(torch.int32).unsqueeze(-1) >> torch.arange(8, device=device)) & 1).sum()).item()),
                 grid_cells=GRID ** 3)
     pipe.nerf.use_cuda_graph = graph_flag
-    dist = {}
+    per_call = {}
     for name, a, b, meta in prof:
-        dist.setdefault(name, []).append(a.elapsed_time(b))
+        per_call.setdefault(name, []).append(a.elapsed_time(b))
     tails = {k: dict(min=round(min(v), 3), med=round(float(np.median(v)), 3), p90=round(float(np.percentile(v, 90)), 3), max=round(max(v), 3))
-             for k, v in dist.items() if k in ('mve_field_backward', 'mve_field_forward', 'mve_march_rays_train', 'mve_attention_bf16')}
+             for k, v in per_call.items() if k in ('mve_field_backward', 'mve_field_forward', 'mve_march_rays_train', 'mve_attention_bf16')}
     cat = {}
     for name, a, b, meta in prof:
         c = cat.setdefault(name, dict(ms=0.0, n=0, flops=0.0))
@@ -331,7 +342,7 @@ def run_ours(args):
     if world == 1:
         line['raster_hbm'] = raymarch_microbench(device, pk)
         line['cpu_baseline'] = cpu_baseline()
-    print(json.dumps(line))
+    emit_json(line)
 
 
 # --------------------------------------------------------------------------------------------------------- config-5 microbench (HBM)
@@ -466,7 +477,7 @@ def run_reference(args):
                 ms_per_step=round(1e3 / cb['value'], 1), higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32', data='synthetic',
                 config=dict(workload='BASELINE configs[1] (bounded sample, extrapolated; see cpu_baseline.sample)', views=N_VIEWS, image=IMG),
                 cpu_baseline=cb, e2e=dict(value=cb['value'], unit='steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit_json(line)
 
 
 def main():
@@ -476,9 +487,15 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--torch-profile', action='store_true', help='write a CUPTI per-kernel table of one warm step to gpurun_out/torch_profile.txt')
-    ap.add_argument('--profile-step', action='store_true', help='ncu helper: short init, 1 warm-up, ONE step between cudaProfilerStart/Stop, no JSON')
+    ap.add_argument('--profile-step', action='store_true', help='ncu helper: 1 warm-up, ONE step between cudaProfilerStart/Stop, no JSON')
     ap.add_argument('--no-graph', action='store_true', help='run the recon iterations eagerly instead of as CUDA graphs')
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: libraries that chat on fd 1 (NCCL prints its version banner there from inside
+    # init_process_group, whatever NCCL_DEBUG_FILE says) are pointed at stderr for the whole run
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference(args)
     else:
