@@ -32,7 +32,8 @@ def test_encode_interpolates_grid_values_at_cell_corners():
 def test_point_decode_autograd_and_ranges():
     levels, n = fo.level_table(12, 16, 320)
     params = [p.double().requires_grad_(True) for p in fo.init_params(levels, n, table_scale=0.5)]
-    x = (torch.rand(64, 3, dtype=torch.float64) * 2 - 1).requires_grad_(True)
+    # seeded: an unlucky draw can put x[0] on a ReLU kink of the MLP, where the one-sided finite difference below disagrees
+    x = (torch.rand(64, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(7)) * 2 - 1).requires_grad_(True)
     sigma, rgb = fo.point_decode(x, *params, levels)
     assert sigma.min() > 0 and rgb.min() >= -0.001 and rgb.max() <= 1.001
     (sigma.sum() + rgb.sum()).backward()
