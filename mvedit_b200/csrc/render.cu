@@ -55,7 +55,7 @@ struct RenderParams {
 };
 
 // Round-based lane scheduling.  Every round (all steps converged except the bounded DDA loop):
-//   1. lanes without a ray fetch the next one with ONE warp-aggregated atomic,
+//   1. lanes without a ray take the next slots of the warp's current 8x8 pixel tile (one atomic per 64-ray tile, not per ray),
 //   2. every lane without a sample advances its DDA by at most DDA_BUDGET voxel steps (retiring the ray if it ends); the loop
 //      stops as soon as no lane is still searching, so a warp full of surface rays pays one DDA step per round,
 //   3. the lanes that hold a sample shade it together (96 hash-grid gathers + MLP + compositing) -- the expensive part stays converged.
