@@ -401,7 +401,7 @@ def raymarch_microbench(device, pk):
 
 
 # --------------------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_baseline(as_line=False, args=None):
+def cpu_baseline(reps_=(0, 1)):
     """The reference cannot run on CPU (raymarching.py:46-51 forces CUDA; tcnn / nvdiffrast are CUDA-only), so the CPU arm is the
     ORACLE PORT (kind 'port') on the host cores, on a bounded sample of the same workload, extrapolated linearly:
       UNet: 1 image through unet_enc + 2 x unet_dec and 2 ControlNets at latent 64 (x64 images per step),
@@ -418,14 +418,6 @@ def cpu_baseline(as_line=False, args=None):
     x = torch.randn(1, 4, LATENT, LATENT, generator=g)
     ctx = torch.randn(1, T_TOKENS, 768, generator=g)
     cond = torch.rand(1, 3, IMG, IMG, generator=g)
-    with torch.no_grad():
-        t0 = time.time()
-        emb, res, s = uo.unet_enc(usd, cfg, x, 500, ctx)
-        uo.unet_dec(usd, cfg, emb, res, s, ctx)
-        down, mid = uo.controlnet_forward(csd, cfg, x, 500, ctx, cond, 1.0)
-        d2, m2 = uo.controlnet_forward(csd, cfg, x, 500, ctx, cond, 1.0)
-        uo.unet_dec(usd, cfg, emb, res, s, ctx, None, [a + b for a, b in zip(down, d2)], mid + m2)
-        t_unet_img = time.time() - t0
     # recon iteration
     levels, n_entries = fo.level_table(12, 16, 320)
     params = [p.requires_grad_(True) for p in fo.init_params(levels, n_entries, table_scale=0.3)]
@@ -434,32 +426,52 @@ def cpu_baseline(as_line=False, args=None):
     poses = synth.surround_poses(4, seed=0)
     ro, rd, f = synth.camera_rays(poses[:1], 128)
     aabb = np.array([-1, -1, -1, 1, 1, 1], np.float32)
-    t0 = time.time()
-    nears, fars = orc.near_far_from_aabb(ro, rd, aabb, 0.2)
-    xs, _, ts, rays = orc.march_rays_train(ro, rd, 1.0, bitfield, 1, H, nears, fars, np.random.default_rng(0).random(ro.shape[0]).astype(np.float32),
-                                           dt_gamma=1 / f, max_steps=1024)
-    sig, rgb = fo.point_decode(torch.from_numpy(xs), *params, levels)
-    w, ws, dep, img = orc.composite_rays_train_forward(sig.detach().numpy(), rgb.detach().numpy(), ts, rays)
-    N = ro.shape[0]
-    gs, gc = orc.composite_rays_train_backward(np.zeros_like(w), np.ones(N, np.float32), np.ones(N, np.float32), np.ones((N, 3), np.float32),
-                                               sig.detach().numpy(), rgb.detach().numpy(), ts, rays, ws, dep, img)
-    torch.autograd.backward([sig, rgb], [torch.from_numpy(gs), torch.from_numpy(gc)])
-    t_recon_iter = time.time() - t0
-    # render one 128^2 view
-    t0 = time.time()
-    ws_, d_, im_ = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
-    alive, rt = np.arange(N, dtype=np.int32), nears.copy()
-    st = 0
-    with torch.no_grad():
-        while st < 1024 and alive.size:
-            n_alive = alive.size
-            n_step = min(max(N // n_alive, 1), 8)
-            xi, _, ti = orc.march_rays(n_alive, n_step, alive, rt, ro, rd, 1.0, bitfield, 1, H, nears, fars, None, dt_gamma=0.25 / f, max_steps=1024)
-            s_, c_ = fo.point_decode(torch.from_numpy(xi), *[p.detach() for p in params], levels)
-            orc.composite_rays(n_alive, n_step, alive, rt, s_.numpy(), c_.numpy(), ti, ws_, d_, im_, T_thresh=1e-2)
-            alive = np.ascontiguousarray(alive[alive >= 0])
-            st += n_step
-    t_render_view128 = time.time() - t0
+
+    def sample():
+        """one bounded sample of the step's three parts -> (s per UNet image, s per recon iteration, s per 128^2 view)"""
+        for p_ in params:
+            p_.grad = None
+        with torch.no_grad():
+            t0 = time.time()
+            emb, res, s = uo.unet_enc(usd, cfg, x, 500, ctx)
+            uo.unet_dec(usd, cfg, emb, res, s, ctx)
+            down, mid = uo.controlnet_forward(csd, cfg, x, 500, ctx, cond, 1.0)
+            d2, m2 = uo.controlnet_forward(csd, cfg, x, 500, ctx, cond, 1.0)
+            uo.unet_dec(usd, cfg, emb, res, s, ctx, None, [a + b for a, b in zip(down, d2)], mid + m2)
+            t_unet_img = time.time() - t0
+        t0 = time.time()
+        nears, fars = orc.near_far_from_aabb(ro, rd, aabb, 0.2)
+        xs, _, ts, rays = orc.march_rays_train(ro, rd, 1.0, bitfield, 1, H, nears, fars, np.random.default_rng(0).random(ro.shape[0]).astype(np.float32),
+                                               dt_gamma=1 / f, max_steps=1024)
+        sig, rgb = fo.point_decode(torch.from_numpy(xs), *params, levels)
+        w, ws, dep, img = orc.composite_rays_train_forward(sig.detach().numpy(), rgb.detach().numpy(), ts, rays)
+        N = ro.shape[0]
+        gs, gc = orc.composite_rays_train_backward(np.zeros_like(w), np.ones(N, np.float32), np.ones(N, np.float32), np.ones((N, 3), np.float32),
+                                                   sig.detach().numpy(), rgb.detach().numpy(), ts, rays, ws, dep, img)
+        torch.autograd.backward([sig, rgb], [torch.from_numpy(gs), torch.from_numpy(gc)])
+        t_recon_iter = time.time() - t0
+        # render one 128^2 view
+        t0 = time.time()
+        ws_, d_, im_ = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
+        alive, rt = np.arange(N, dtype=np.int32), nears.copy()
+        st = 0
+        with torch.no_grad():
+            while st < 1024 and alive.size:
+                n_alive = alive.size
+                n_step = min(max(N // n_alive, 1), 8)
+                xi, _, ti = orc.march_rays(n_alive, n_step, alive, rt, ro, rd, 1.0, bitfield, 1, H, nears, fars, None, dt_gamma=0.25 / f, max_steps=1024)
+                s_, c_ = fo.point_decode(torch.from_numpy(xi), *[p.detach() for p in params], levels)
+                orc.composite_rays(n_alive, n_step, alive, rt, s_.numpy(), c_.numpy(), ti, ws_, d_, im_, T_thresh=1e-2)
+                alive = np.ascontiguousarray(alive[alive >= 0])
+                st += n_step
+        t_render_view128 = time.time() - t0
+        return t_unet_img, t_recon_iter, t_render_view128
+
+    warm, reps = reps_
+    for _ in range(warm):
+        sample()
+    ts_ = np.array([sample() for _ in range(max(reps, 1))])
+    t_unet_img, t_recon_iter, t_render_view128 = (float(v) for v in ts_.mean(axis=0))
     step_s = 2 * N_VIEWS * t_unet_img + N_INVERSE_STEPS * t_recon_iter + N_VIEWS * 16 * t_render_view128
     out = dict(value=round(1.0 / step_s, 6), unit='steps/s', cores=cores, kind='port',
                sample='oracle port on host cores: 1 image of (unet_enc + 2x unet_dec + 2 ControlNets) @latent 64 = %.1f s (x64/step); '
@@ -472,7 +484,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cb = cpu_baseline()
+    cb = cpu_baseline((args.warmup, args.steps))       # W untimed + K timed bounded samples, averaged
     line = dict(impl='reference', metric=METRIC, value=cb['value'], unit='steps/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=round(1e3 / cb['value'], 1), higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32', data='synthetic',
                 config=dict(workload='BASELINE configs[1] (bounded sample, extrapolated; see cpu_baseline.sample)', views=N_VIEWS, image=IMG),
