@@ -190,10 +190,12 @@ int mve_render_last_sample_count(uint64_t* host_out);
  * BaseNeRF.render's tail (inverse-z depth, depth / alpha, depth_to_normal: base_nerf.py:536-556, geometry_utils.py:119-148),
  * Lambert shading + background compositing (mvedit_3d_pipeline.py:1352-1380) and normalize_depth (geometry_utils.py:151-168).
  * weights_sum / depth [V,h,w], image [V,h,w,3] are mve_render_rays' outputs; intrinsics [V,4] at the render size; lights [V,3].
- * out_images / out_depths: bf16 [V,3,h,w] (NCHW), both clamped to [0,1]; reduce_scratch: [V,2] i32 of device scratch. */
+ * out_images / out_depths: bf16 [V,3,h,w] (NCHW), both clamped to [0,1]; reduce_scratch: [V,2] i32 of device scratch.
+ * out_normals_fg (optional): f32 [V,h,w,3], depth_to_normal(depth_fg) in the opengl [0,1] encoding (BaseNeRF.render's
+ * compute_normal output, base_nerf.py:549-553).  With out_images == NULL only the normals are produced (lights / scratch unused). */
 int mve_shade_views(const float* weights_sum, const float* depth, const float* image, const float* intrinsics, const float* lights,
                     uint32_t V, uint32_t h, uint32_t w, float ambient, float bg_color, float far_depth, float alpha_clip, float eps,
-                    int32_t* reduce_scratch, void* out_images, void* out_depths, void* stream);
+                    int32_t* reduce_scratch, void* out_images, void* out_depths, float* out_normals_fg, void* stream);
 
 /* Weight culling of the training branch (base_volume_renderer.py:222-246): keep samples with weight > th, compact xyzs/ts,
  * rebuild rays (offset,count); *counter (zeroed by the caller) receives the kept total.  Rays whose kept samples would not fit
@@ -226,8 +228,13 @@ int mve_layernorm_bf16(const void* x, void* y, uint32_t rows, uint32_t C, const 
 /* h [M,2F] -> y [M,F] = h[:, :F] * gelu(h[:, F:]) */
 int mve_geglu_bf16(const void* h, void* y, uint64_t M, uint32_t F, void* stream);
 int mve_upsample2x_bf16(const void* x, void* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* stream);
-/* x [B,H,W,C] -> y [B*(H/2)*(W/2), 9*C] patches of a 3x3 stride-2 pad-1 conv (K index = tap*C + c) */
-int mve_im2col3x3s2_bf16(const void* x, void* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* stream);
+/* x [B,H,W,C] -> y [B*(H/2)*(W/2), 9*C] patches of a 3x3 stride-2 conv (K index = tap*C + c).  pad_lo = 1: pad 1 on every side
+ * (UNet Downsample2D); pad_lo = 0: zero pad on the right / bottom only (AutoencoderKL encoder Downsample2D, F.pad (0,1,0,1)). */
+int mve_im2col3x3s2_bf16(const void* x, void* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, int pad_lo, void* stream);
+/* y[r, :cols] = softmax(scale * x[r, :cols]) per row (bf16 in / out, fp32 inside; in place allowed).  The AutoencoderKL mid-block
+ * attention (one head, d = 512: lib/pipelines/mvedit_3d_pipeline.py:1119-1120,1258-1263 -> diffusers Attention) runs as
+ * score GEMM -> this -> value GEMM. */
+int mve_softmax_rows_bf16(const void* x, void* y, uint32_t rows, uint32_t cols, uint32_t ldx, uint32_t ldy, float scale, void* stream);
 /* x [B,C,HW] (f32 or bf16) -> y [B,HW,Cpad] bf16, channels >= C zero-filled */
 int mve_nchw_to_nhwc_pad_bf16(const void* x, int x_is_f32, void* y, uint32_t B, uint32_t C, uint32_t HW, uint32_t Cpad, void* stream);
 
@@ -241,6 +248,35 @@ int mve_nerf_patch_loss(const float* image, const float* alpha, const float* dep
                         int shaded, float ambient, float bg_color, float bg_width, float pixel_loss_weight,
                         const float* w_alpha_mul, const float* w_normal_reg, const float* w_entropy,
                         float* scratch, float* g_image, float* g_alpha, float* g_depth, float* loss5, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * a-5: glue of one nerf_optim iteration (lib/pipelines/mvedit_3d_pipeline.py:507-536, :631-633)
+ * ------------------------------------------------------------------------- */
+
+/* Rays and targets of the drawn patches in one launch: replaces BaseNeRF.ray_sample's whole-image patch reshuffle
+ * (lib/models/autoencoders/base_nerf.py:245-303), get_ray_directions / get_rays (lib/core/utils/geometry_utils.py:18-55) and the
+ * per-patch weight / light / dt_gamma ops (mvedit_3d_pipeline.py:516-536).
+ * patch_inds [P] int64: patch ids numbered (view, patch row, patch col) as ray_sample numbers them; poses_R [V,3,3], poses_T [V,3]
+ * (c2w), intrinsics [V,4] at intrinsics_size, intrinsics_scale = render_size / intrinsics_size; images [V,rs,rs,3], masks [V,rs,rs].
+ * Outputs for the FULL patches (n = P*ps*ps, patch-major, row-major inside a patch): dirs [n,3] camera-space directions (z = 1),
+ * tgt_rgb [n,3], tgt_mask [n], patch_w [P] = cam_w / mean(cam_w), patch_lights [P,3], dt_gamma [1] (first patch's view, as the
+ * one-scene reference uses only element 0: base_volume_renderer.py:212-218).
+ * rays_o / rays_d [P*(row_hi-row_lo)*ps, 3]: world-space rays of patch rows [row_lo, row_hi) only -- the strip this rank marches
+ * in the data-parallel reconstruction (row_lo = 0, row_hi = ps on one GPU). */
+int mve_patch_rays(const int64_t* patch_inds, uint32_t P, uint32_t V, uint32_t render_size, uint32_t patch_size,
+                   const float* poses_R, const float* poses_T, const float* intrinsics, float intrinsics_scale,
+                   const float* images, const float* masks, const float* cam_weights, const float* cam_lights,
+                   float dt_gamma_scale, uint32_t row_lo, uint32_t row_hi,
+                   float* rays_o, float* rays_d, float* dirs, float* tgt_rgb, float* tgt_mask,
+                   float* patch_w, float* patch_lights, float* dt_gamma, void* stream);
+
+/* torch.optim.Adam.step (defaults: no weight decay, no amsgrad) + optimizer.zero_grad for up to 8 tensors in one launch
+ * (mvedit_3d_pipeline.py:631-633): params / grads / exp_avg / exp_avg_sq / lr are HOST arrays of n_tensors DEVICE pointers
+ * (lr[i] points at a device float: schedulable inside a captured graph), numel a host array.  *step (device int32) is incremented
+ * first and used for the bias corrections.  grads are scaled by grad_scale before use and zeroed afterwards when zero_grad != 0. */
+int mve_adam_step(uint32_t n_tensors, void* const* params, void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                  const uint32_t* numel, const float* const* lr, float beta1, float beta2, float eps, float grad_scale,
+                  int32_t* step, int zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -188,6 +188,57 @@ __global__ void __launch_bounds__(256) k_geglu(const bf16* __restrict__ h, bf16*
     }
 }
 
+
+// ---------------------------------------------------------------- row softmax (the AutoencoderKL mid-block attention: one head, d = 512,
+// scores materialised by the GEMM).  One CTA of 128 threads per row, the row stays in registers: one read, one write.
+__global__ void __launch_bounds__(128) k_softmax_rows(const bf16* __restrict__ x, bf16* __restrict__ y, const uint32_t cols, const uint32_t ldx,
+                                                      const uint32_t ldy, const float scale_log2e) {
+    constexpr int MAXV = 8;                     // cols <= 128 * 8 * 8 = 8192
+    __shared__ float s_red[4];
+    const uint32_t row = blockIdx.x, nvec = cols / 8;
+    const bf16* xr = x + (size_t)row * ldx;
+    float f[MAXV][8];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < MAXV; c++) {
+        const uint32_t v = threadIdx.x + 128 * c;
+        if (v < nvec) {
+            unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f[c]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) m = fmaxf(m, f[c][k]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXV; c++) {
+        const uint32_t v = threadIdx.x + 128 * c;
+        if (v < nvec) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) { f[c][k] = exp2f((f[c][k] - m) * scale_log2e); s += f[c][k]; }
+        }
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    const float inv = 1.0f / (s_red[0] + s_red[1] + s_red[2] + s_red[3]);
+    bf16* yr = y + (size_t)row * ldy;
+#pragma unroll
+    for (int c = 0; c < MAXV; c++) {
+        const uint32_t v = threadIdx.x + 128 * c;
+        if (v < nvec) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) f[c][k] *= inv;
+            *reinterpret_cast<uint4*>(yr + v * 8) = pack8(f[c]);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- nearest x2 upsample NHWC
 __global__ void __launch_bounds__(256) k_upsample2x(const bf16* __restrict__ x, bf16* __restrict__ y, const uint32_t B, const uint32_t H,
                                                     const uint32_t W, const uint32_t C) {
@@ -206,7 +257,7 @@ __global__ void __launch_bounds__(256) k_upsample2x(const bf16* __restrict__ x, 
 
 // ---------------------------------------------------------------- im2col for 3x3 stride-2 pad-1 conv: out [B*Ho*Wo, 9*C], K index = tap*C + c
 __global__ void __launch_bounds__(256) k_im2col_s2(const bf16* __restrict__ x, bf16* __restrict__ y, const uint32_t B, const uint32_t H,
-                                                   const uint32_t W, const uint32_t C) {
+                                                   const uint32_t W, const uint32_t C, const int pad_lo) {
     const uint32_t Ho = H / 2, Wo = W / 2, vpp = C / 8;
     const size_t total = (size_t)B * Ho * Wo * 9 * vpp;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
@@ -216,7 +267,7 @@ __global__ void __launch_bounds__(256) k_im2col_s2(const bf16* __restrict__ x, b
         const uint32_t wo = (uint32_t)(r % Wo); r /= Wo;
         const uint32_t ho = (uint32_t)(r % Ho);
         const uint32_t b = (uint32_t)(r / Ho);
-        const int ih = (int)(2 * ho) + (int)(tap / 3) - 1, iw = (int)(2 * wo) + (int)(tap % 3) - 1;
+        const int ih = (int)(2 * ho) + (int)(tap / 3) - pad_lo, iw = (int)(2 * wo) + (int)(tap % 3) - pad_lo;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (ih >= 0 && ih < (int)H && iw >= 0 && iw < (int)W) v = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + ih) * W + iw) * C + cv * 8);
         *reinterpret_cast<uint4*>(y + i * 8) = v;
@@ -297,13 +348,22 @@ int mve_upsample2x_bf16(const void* x, void* y, uint32_t B, uint32_t H, uint32_t
     return 0;
 }
 
-int mve_im2col3x3s2_bf16(const void* x, void* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* stream) {
+int mve_im2col3x3s2_bf16(const void* x, void* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, int pad_lo, void* stream) {
     if (B == 0) return 0;
     MVE_ARG(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "im2col3x3s2: C % 8 == 0, even H and W required");
+    MVE_ARG(pad_lo == 0 || pad_lo == 1, "im2col3x3s2: pad_lo must be 1 (pad 1) or 0 (diffusers Downsample2D padding=0: F.pad (0,1,0,1))");
     const size_t total = (size_t)B * (H / 2) * (W / 2) * 9 * (C / 8);
     uint32_t grid = (uint32_t)((total + 255) / 256 < (size_t)(16 * kNumSM) ? (total + 255) / 256 : (size_t)(16 * kNumSM));
-    k_im2col_s2<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, C);
+    k_im2col_s2<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, C, pad_lo);
     MVE_CHECK_LAUNCH("mve_im2col3x3s2_bf16");
+    return 0;
+}
+
+int mve_softmax_rows_bf16(const void* x, void* y, uint32_t rows, uint32_t cols, uint32_t ldx, uint32_t ldy, float scale, void* stream) {
+    if (rows == 0) return 0;
+    MVE_ARG(cols % 8 == 0 && cols <= 8192 && ldx % 8 == 0 && ldy % 8 == 0, "softmax_rows: cols % 8 == 0, cols <= 8192, 16-byte aligned rows required");
+    k_softmax_rows<<<rows, 128, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, cols, ldx, ldy, scale * 1.4426950408889634f);
+    MVE_CHECK_LAUNCH("mve_softmax_rows_bf16");
     return 0;
 }
 

@@ -27,6 +27,7 @@ struct ShadeParams {
     int* red;               // [V,2] float bits: max inverse-z depth, min foreground depth
     __nv_bfloat16* out_img; // [V,3,h,w]
     __nv_bfloat16* out_dep; // [V,3,h,w]
+    float* out_nrm;         // [V,h,w,3] optional: normal_fg in the opengl [0,1] encoding
 };
 
 __device__ __forceinline__ float dir_norm(const float* K, const uint32_t x, const uint32_t y, float& dx, float& dy) {
@@ -98,10 +99,12 @@ __global__ void __launch_bounds__(256) k_shade_apply(const ShadeParams p) {
     n = {n.x * inv, n.y * inv, n.z * inv};
     // opengl [0,1] encoding and back to OpenCV, as the reference round-trips it (base_nerf.py:552, mvedit_3d_pipeline.py:1357)
     const float fx = n.x / 2 + 0.5f, fy = -n.y / 2 + 0.5f, fz = -n.z / 2 + 0.5f;
+    const size_t i = base + (size_t)y * p.w + x;
+    if (p.out_nrm) { p.out_nrm[i * 3] = fx; p.out_nrm[i * 3 + 1] = fy; p.out_nrm[i * 3 + 2] = fz; }
+    if (!p.out_img) return;
     const float ox = fx * 2 - 1, oy = -fy * 2 + 1, oz = -fz * 2 + 1;
     const float* Lg = p.lights + v * 3;
     const float shading = fmaxf(Lg[0] * ox + Lg[1] * oy + Lg[2] * oz, 0.f) * (1 - p.ambient) + p.ambient;
-    const size_t i = base + (size_t)y * p.w + x;
     const float a = p.ws[i];
     const size_t plane = (size_t)p.h * p.w, o = (size_t)v * 3 * plane + (size_t)y * p.w + x;
 #pragma unroll
@@ -123,13 +126,20 @@ __global__ void __launch_bounds__(256) k_shade_apply(const ShadeParams p) {
 
 extern "C" int mve_shade_views(const float* weights_sum, const float* depth, const float* image, const float* intrinsics, const float* lights,
                                uint32_t V, uint32_t h, uint32_t w, float ambient, float bg_color, float far_depth, float alpha_clip, float eps,
-                               int32_t* reduce_scratch, void* out_images, void* out_depths, void* stream) {
+                               int32_t* reduce_scratch, void* out_images, void* out_depths, float* out_normals_fg, void* stream) {
     if (V == 0) return 0;
     MVE_ARG(h >= 2 && w >= 2, "shade_views: h, w >= 2 required");
-    MVE_ARG(reduce_scratch != nullptr, "shade_views: reduce_scratch [V,2] i32 required");
+    MVE_ARG((out_images == nullptr) == (out_depths == nullptr), "shade_views: out_images and out_depths go together");
+    MVE_ARG(out_images != nullptr || out_normals_fg != nullptr, "shade_views: nothing to produce");
+    MVE_ARG(out_images == nullptr || (reduce_scratch != nullptr && lights != nullptr), "shade_views: reduce_scratch [V,2] i32 and lights required");
     cudaStream_t s = (cudaStream_t)stream;
     ShadeParams p{weights_sum, depth, image, intrinsics, lights, V, h, w, ambient, bg_color, far_depth, alpha_clip, eps, reduce_scratch,
-                  (__nv_bfloat16*)out_images, (__nv_bfloat16*)out_depths};
+                  (__nv_bfloat16*)out_images, (__nv_bfloat16*)out_depths, out_normals_fg};
+    if (out_images == nullptr) {
+        k_shade_apply<<<dim3(cdiv(w, 32), cdiv(h, 8), V), 256, 0, s>>>(p);
+        MVE_CHECK_LAUNCH("mve_shade_views");
+        return 0;
+    }
     const float init_min = 1.0f / eps;             // max starts at 0, the masked min at 1 / eps (geometry_utils.py:158)
     int min_bits;
     memcpy(&min_bits, &init_min, 4);

@@ -108,8 +108,13 @@ class _FieldFn(Function):
         xyz, table, w1, b1, w2, b2 = ctx.saved_tensors
         dec = ctx.dec
         M = xyz.shape[0]
-        g_table = torch.zeros_like(table)
-        g_w1, g_b1, g_w2, g_b2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
+        sink = dec.grad_sink            # FusedAdam: the kernels accumulate straight into the optimizer's flat gradient buffer
+        if sink is not None:
+            prm = dec._field_params()
+            g_table, g_w1, g_b1, g_w2, g_b2 = (sink.grad_sink(q) for q in prm)
+        else:
+            g_table = torch.zeros_like(table)
+            g_w1, g_b1, g_w2, g_b2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
         need_dx = ctx.needs_input_grad[0]
         g_xyz = torch.zeros_like(xyz) if need_dx else None
         ws = dec._workspace(xyz.device)
@@ -118,7 +123,9 @@ class _FieldFn(Function):
         call('mve_field_backward', ptr(xyz), c_u32(M), ptr(ctx.m_dev), ptr(table), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
              *dec.encoder._largs.args(), c_f32(dec.bound), c_f32(dec.blob_density), c_f32(dec.blob_radius),
              c_f32(dec.sigmoid_saturation), ptr(g_sigma), ptr(g_rgb), ptr(g_table), ptr(g_w1), ptr(g_b1), ptr(g_w2), ptr(g_b2),
-             c_int(0), c_int(int(ctx.tf32)), ptr(ws), ptr(g_xyz), stream())
+             c_int(int(sink is not None)), c_int(int(ctx.tf32)), ptr(ws), ptr(g_xyz), stream())
+        if sink is not None:
+            return g_xyz, None, None, None, None, None, None, None, None
         return g_xyz, g_table, g_w1, g_b1, g_w2, g_b2, None, None, None
 
 
@@ -150,6 +157,11 @@ class iNGPDecoder(nn.Module):
         self.mlp_tf32 = True
         self._ws = None
         self._grid_cache = {}
+        self.grad_sink = None          # set by nerf_optim to a FusedAdam: field backward accumulates into its flat gradient buffer
+        self._ov = None                # device max of the post-cull sample count over the iterations since the last check
+        self._ov_host = None
+        self._jitter_gen = None        # generator of the occupancy-refresh jitter (seeded identically on every rank)
+        self.test_noise = None         # parity tests: dict(march=[N] tensor, grid=[H^3,3] tensor) replaces the internal random draws
         self.init_weights()
 
     # ------------------------------------------------------------------ parameters / state
@@ -175,6 +187,39 @@ class iNGPDecoder(nn.Module):
             fn.restype = ctypes.c_uint32
             self._ws = torch.empty(int(fn(c_u32(self.n_levels))), dtype=torch.float32, device=device)
         return self._ws
+
+    # ------------------------------------------------------------------ capacity bookkeeping (sync-free training path)
+    def _track_overflow(self, counter):
+        """counter: device int32 [1] = TRUE number of samples that passed the cull in this forward (it keeps counting past the
+        capacity, mve_cull_samples).  A running device max is kept; nothing is read back here."""
+        if self._ov is None or self._ov.device != counter.device:
+            self._ov = torch.zeros(1, dtype=torch.int32, device=counter.device)
+            self._ov_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._ov_event = None
+        torch.maximum(self._ov, counter, out=self._ov)
+
+    def note_sample_overflow(self):
+        """End of a nerf_optim call: start an async copy of the running max to pinned host memory (no sync)."""
+        if self._ov is None:
+            return
+        self._ov_host.copy_(self._ov, non_blocking=True)
+        self._ov_event = torch.cuda.Event()
+        self._ov_event.record()
+
+    def check_sample_overflow(self, sync=False):
+        """Raises if an earlier training forward produced more samples than ``sample_capacity`` (rays were dropped: the reference
+        never drops samples).  Cheap: waits only on the event of the async copy issued by ``note_sample_overflow``.
+        Returns the largest post-cull sample count seen."""
+        if self._ov is None or self._ov_event is None:
+            return 0
+        if sync:
+            self.note_sample_overflow()
+        self._ov_event.synchronize()
+        m = int(self._ov_host[0])
+        if self.sample_capacity and m > self.sample_capacity:
+            raise RuntimeError('iNGPDecoder: %d samples survived the weight cull in one training forward but sample_capacity is %d -- '
+                               'rays were dropped; raise decoder.sample_capacity' % (m, self.sample_capacity))
+        return m
 
     def _field_params(self):
         return (self.encoder.params, self.mlp.net[0].weight, self.mlp.net[0].bias, self.mlp.net[1].weight, self.mlp.net[1].bias)
@@ -227,8 +272,13 @@ class iNGPDecoder(nn.Module):
                 raise NotImplementedError('partial occupancy update: not reachable from the MVEdit pipelines (iter_density stays 0)')
             centres, mesh_pos, scratch = self._morton_grid(grid_size, device)
             half_voxel_width = self.bound / grid_size
+            if noise is None and self.test_noise is not None and self.test_noise.get('grid') is not None:
+                noise = self.test_noise['grid']
             if noise is None:
-                u = torch.rand_like(centres)
+                if self._jitter_gen is None or self._jitter_gen.device != centres.device:
+                    self._jitter_gen = torch.Generator(device=centres.device)
+                    self._jitter_gen.manual_seed(0x5eed)        # the same stream on every rank: replicas refresh identical grids
+                u = torch.rand(centres.shape, generator=self._jitter_gen, device=centres.device)
             else:
                 u = noise.to(device=device, dtype=torch.float32).reshape(-1, 3)[mesh_pos]
             xyzs = centres + (u * (2 * half_voxel_width) - half_voxel_width)
@@ -260,6 +310,8 @@ class iNGPDecoder(nn.Module):
             dt_gamma = float(dt_gamma[0])
         ro, rd = rays_o[0], rays_d[0]
         bitfield = density_bitfield[0]
+        if noises is None and self.training and self.test_noise is not None:
+            noises = self.test_noise.get('march')
         if self.training and self.sample_capacity:
             # B200-native protocol: fixed-capacity sample buffers + device-side counts -> no host sync anywhere in the iteration
             # (the reference syncs three times here: raymarching.py:290, base_volume_renderer.py:235-241), CUDA-graph capturable.
@@ -286,6 +338,7 @@ class iNGPDecoder(nn.Module):
                     call('mve_cull_samples', ptr(w0), c_f32(self.weight_culling_th), ptr(rays), ptr(xyzs), ptr(ts), c_u32(N), c_u32(cap1),
                          ptr(counter), c_u32(cap), ptr(rays2), ptr(xyzs2), ptr(ts2), ptr(counter2), stream())
                     xyzs, ts, rays, counter = xyzs2, ts2, rays2, counter2
+                    self._track_overflow(counter2)
             sigmas, rgbs, num_points = self.point_decode([xyzs], None, code, m_dev=counter)
             weights, weights_sum, depth, image = rm.composite_rays_train(sigmas, rgbs, ts, rays, 1e-4, False, counter, fused_entropy)
             self.last_counts = (counter1, counter)       # device counters: marched / kept samples of the last training forward
@@ -341,7 +394,7 @@ class iNGPDecoder(nn.Module):
         call('mve_render_last_sample_count', buf)
         return int(buf[0]), int(buf[1]), int(buf[2]), int(buf[3])
 
-    def render_cameras(self, poses, intrinsics, h, w, density_bitfield, grid_size, dt_gamma=0.0):
+    def render_cameras(self, poses, intrinsics, h, w, density_bitfield, grid_size, dt_gamma=0.0, dt_gamma_per_view=None):
         """Fused BaseNeRF.render core (base_nerf.py:489-556): rays are generated inside the kernel from (pose, intrinsics, pixel).
         poses [V,4,4] (or [V,3,4]) c2w, intrinsics [V,4] at the render size.  -> weights_sum [V,h,w], depth [V,h,w] (sum w/t),
         image [V,h,w,3] (premultiplied, no background)."""
@@ -354,7 +407,10 @@ class iNGPDecoder(nn.Module):
         depth = torch.empty(N, dtype=torch.float32, device=poses.device)
         image = torch.empty(N, 3, dtype=torch.float32, device=poses.device)
         table, w1, b1, w2, b2 = self._field_params()
-        call('mve_render_rays', ptr(None), ptr(None), ptr(P), ptr(K), ptr(None), c_u32(h), c_u32(w), c_u32(N), ptr(self.aabb),
+        if dt_gamma_per_view is not None:
+            dt_gamma_per_view = dt_gamma_per_view.float().contiguous()
+            assert dt_gamma_per_view.numel() == V
+        call('mve_render_rays', ptr(None), ptr(None), ptr(P), ptr(K), ptr(dt_gamma_per_view), c_u32(h), c_u32(w), c_u32(N), ptr(self.aabb),
              c_f32(self.min_near), ptr(density_bitfield.reshape(-1).contiguous()), c_f32(self.bound), c_f32(float(dt_gamma)),
              c_u32(self.max_steps), c_u32(1), c_u32(grid_size), c_f32(1e-2), ptr(table), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
              *self.encoder._largs.args(), c_f32(self.blob_density), c_f32(self.blob_radius), c_f32(self.sigmoid_saturation),

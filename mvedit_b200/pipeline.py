@@ -6,13 +6,15 @@ What is and is not inside ``MVEdit3DStep.step``:
   * inside: scale_model_input, get_noise_pred_p1 (UNet enc+dec, all views one batch), pred_x0, nerf_optim (n_inverse_steps Adam
     iterations of march/field/composite fwd+bwd), nerf.render of all views + Lambert shading + normalize_depth, get_noise_pred_p2
     (tile+depth ControlNets on the fresh renders + UNet dec), Euler-ancestral solver step;
-  * hooks (neighbours of the path): ``decode_fn(pred_x0) -> (tgt_images, tgt_masks)`` stands where
-    vae.decode + TRACER masks are in the reference (:1258-1266); LPIPS ``patch_loss`` on the NeRF; the SRVGG enhancer (only
-    active below 512^2 renders).  bench.py passes a synthetic decode_fn and says so in its JSON.
+  * vae.decode of pred_x0 (:1258-1263) runs on the tcgen05 kernels (mvedit_b200.vae) when a ``vae`` is given; the target masks come
+    from a ``segmentation`` callable (TRACER in the reference: a neighbour that is not built).  A
+    ``decode_fn(pred_x0, lo, hi) -> (tgt_images, tgt_masks)`` overrides both (bench.py uses it to decode for real and then hand the
+    reconstruction analytic targets -- a random-init VAE decodes noise -- and says so in its JSON).  LPIPS and the SRVGG enhancer
+    (only active below 512^2 renders) are not built.
 
-View sharding: with ``torch.distributed`` initialised every rank denoises / renders its slice of the views and the
-decoded targets are exchanged with ONE all_gather per step (``view_shard.gather_views``); the reconstruction runs replicated and
-rank 0's field is broadcast afterwards so that replicas cannot drift through atomic-order noise.
+Sharding (mvedit_b200.view_shard): every rank denoises / decodes / renders its slice of the views; the decoded
+targets are exchanged with ONE all_gather per step; the reconstruction is data-parallel over rays (``nerf.data_parallel``: one
+all_gather of per-ray outputs + one all_reduce of the flat gradient per iteration) or, without it, replicated + one flat broadcast.
 """
 import math
 
@@ -20,24 +22,9 @@ import numpy as np
 import torch
 
 from .adapter3d_mixin import Adapter3DMixin
-from .nerf import nerf_optim, normalize_depth
+from .nerf import nerf_optim
 from . import view_shard
 from ._lib import call, ptr, stream, c_u32, c_f32
-
-
-def get_noise_scales(alphas_bar, t, num_timesteps, dtype=torch.float32):
-    """lib/core/diffusion.py:4-21."""
-    alphas_bar = t.new_tensor(alphas_bar, dtype=torch.float32)
-    if t.is_floating_point():
-        int_t = t.long()
-        frac_t = t - int_t
-        a0 = alphas_bar[int_t]
-        a1 = alphas_bar[(int_t + 1).clamp(max=num_timesteps - 1)]
-        s0, s1 = torch.sqrt((1 - a0) / a0), torch.sqrt((1 - a1) / a1)
-        ve = s0 * (1 - frac_t) + s1 * frac_t
-        return torch.sqrt(1 / (1 + ve ** 2)).to(dtype), torch.sqrt(ve ** 2 / (1 + ve ** 2)).to(dtype)
-    a = alphas_bar[t]
-    return torch.sqrt(a).to(dtype), torch.sqrt(1 - a).to(dtype)
 
 
 class EulerAncestralScheduler:
@@ -62,8 +49,26 @@ class EulerAncestralScheduler:
         self.init_noise_sigma = float(self.sigmas.max())
         self._step_index = 0
 
+    def noise_scales(self, t):
+        """(sqrt(alpha_bar_t), sqrt(1 - alpha_bar_t)) as 0-dim tensors on t's device; a fractional t (the 'trailing' / Karras
+        timesteps are floats) interpolates the VE sigma between the two neighbouring integer timesteps -- what the reference's
+        get_noise_scales does (lib/core/diffusion.py:4-21; checked against it in tests/test_reference_pins.py)."""
+        tf = float(t)
+        sig = np.sqrt((1 - self.alphas_cumprod) / self.alphas_cumprod)
+        lo = min(int(tf), self.num_train_timesteps - 1)
+        hi = min(lo + 1, self.num_train_timesteps - 1)
+        ve = sig[lo] + (sig[hi] - sig[lo]) * (tf - lo) if torch.is_floating_point(t) else sig[lo]
+        a = 1.0 / np.sqrt(1.0 + ve * ve)
+        return t.new_tensor(a, dtype=torch.float32), t.new_tensor(ve * a, dtype=torch.float32)
+
     def scale_model_input(self, sample, i):
         return sample / ((self.sigmas[i] ** 2 + 1) ** 0.5)
+
+    def add_noise(self, original_samples, noise, timesteps):
+        """diffusers EulerAncestralDiscreteScheduler.add_noise: x + noise * sigma(t), t looked up in the current schedule."""
+        idx = [int((self.timesteps == float(t)).nonzero()[0]) for t in timesteps.reshape(-1)]
+        sigma = self.sigmas[idx].to(original_samples.device)
+        return original_samples + noise * sigma.view(-1, *([1] * (original_samples.dim() - 1)))
 
     def step(self, model_output, i, sample, noise):
         sigma = self.sigmas[i]
@@ -78,51 +83,53 @@ class EulerAncestralScheduler:
 class MVEdit3DStep(Adapter3DMixin):
     """The loop body of MVEdit3DPipeline.__call__ (NeRF stage) on B200 components."""
 
-    def __init__(self, unet, controlnet, nerf, scheduler, tonemapping=None, normal_bg=(0.5, 0.5, 1.0)):
+    def __init__(self, unet, controlnet, nerf, scheduler, tonemapping=None, normal_bg=(0.5, 0.5, 1.0), vae=None, segmentation=None):
         self.unet, self.controlnet, self.nerf, self.scheduler = unet, controlnet, nerf, scheduler
-        self.tonemapping = tonemapping
+        self.vae, self.segmentation = vae, segmentation
+        if tonemapping is not None:
+            raise NotImplementedError('tone mapping (lib/core/utils/tonemapping.py) is not built: the fused shading kernels assume None')
+        self.tonemapping = None
         self.normal_bg = list(normal_bg)
+
+    # ------------------------------------------------------------------ decode + masks (mvedit_3d_pipeline.py:1258-1266)
+    def decode_targets(self, pred_x0, seg_padding=0):
+        """pred_x0 (n,4,L,L) -> (tgt_images (n,8L,8L,3), tgt_masks (n,8L,8L,1)) fp32.  vae.decode runs on the tcgen05 kernels
+        (mvedit_b200.vae); the masks come from ``self.segmentation`` (TRACER in the reference, adapter3d_mixin.py:14-19 -- a
+        neighbour that is not built: any callable images (n,3,H,W) in [0,1] -> masks (n,1,H,W))."""
+        if self.vae is None:
+            raise RuntimeError('MVEdit3DStep: no vae -- pass vae= (mvedit_b200.vae.AutoencoderKL) or a decode_fn')
+        imgs = self.vae.decode_images(pred_x0)
+        if self.segmentation is None:
+            raise RuntimeError('MVEdit3DStep: no segmentation callable for the target masks (TRACER is not built)')
+        masks = self.segmentation(imgs.permute(0, 3, 1, 2)).permute(0, 2, 3, 1).float()
+        return imgs, masks
 
     # ------------------------------------------------------------------ render all (local) views, mvedit_3d_pipeline.py:1341-1395
     def render_views(self, density_bitfield, camera_poses, intrinsics, intrinsics_size, render_size, cam_lights, ambient_light,
-                     testmode_dt_gamma_scale):
-        """-> (ctrl_images, ctrl_depths), bf16 [V,3,rs,rs] in [0,1].  One fused render launch + mve_shade_views (two launches) when no
-        tone mapping is configured; ``render_views_torch`` is the op-by-op restatement of the reference it is tested against."""
-        if self.tonemapping is not None:
-            return self.render_views_torch(density_bitfield, camera_poses, intrinsics, intrinsics_size, render_size, cam_lights,
-                                           ambient_light, testmode_dt_gamma_scale)
+                     testmode_dt_gamma_scale, render_bs=None, view_offset=0, all_intrinsics=None):
+        """-> (ctrl_images, ctrl_depths), bf16 [V,3,rs,rs] in [0,1]: one fused render launch + mve_shade_views (two launches).
+        The reference renders ``render_bs`` views per call and derives dt_gamma from the mean focal length OF THAT BATCH
+        (base_nerf.py:501-502); with ``render_bs`` set, every view gets the dt_gamma of its reference batch (batches are cut from the
+        GLOBAL view list: ``all_intrinsics`` / ``view_offset`` under view sharding), so the result does not depend on the shard layout."""
         nerf = self.nerf
-        K = (intrinsics * (render_size / intrinsics_size)).float().contiguous()
-        dt_gamma = float(testmode_dt_gamma_scale * 2 / (K[:, 0] + K[:, 1]).mean())
-        ws, depth, image = nerf.decoder.render_cameras(camera_poses, K, render_size, render_size, density_bitfield, nerf.grid_size,
-                                                       dt_gamma=dt_gamma)
+        scale = render_size / intrinsics_size
+        K = (intrinsics * scale).float().contiguous()
         V, dev = K.shape[0], K.device
+        if render_bs is None:
+            dt_gamma, per_view = float(testmode_dt_gamma_scale * 2 / (K[:, 0] + K[:, 1]).mean()), None
+        else:
+            Kg = (all_intrinsics if all_intrinsics is not None else intrinsics).float() * scale
+            f2 = Kg[:, 0] + Kg[:, 1]
+            batch_mean = torch.cat([c.mean().expand(c.numel()) for c in f2.split(render_bs)])
+            dt_gamma, per_view = 0.0, (testmode_dt_gamma_scale * 2 / batch_mean)[view_offset:view_offset + V].contiguous()
+        ws, depth, image = nerf.decoder.render_cameras(camera_poses, K, render_size, render_size, density_bitfield, nerf.grid_size,
+                                                       dt_gamma=dt_gamma, dt_gamma_per_view=per_view)
         images = torch.empty(V, 3, render_size, render_size, dtype=torch.bfloat16, device=dev)
         depths = torch.empty_like(images)
         scratch = torch.empty(V, 2, dtype=torch.int32, device=dev)
         call('mve_shade_views', ptr(ws), ptr(depth), ptr(image), ptr(K), ptr(cam_lights.float().contiguous()), c_u32(V), c_u32(render_size),
              c_u32(render_size), c_f32(float(ambient_light)), c_f32(float(nerf.bg_color)), c_f32(0.25), c_f32(0.5), c_f32(1e-5),
-             ptr(scratch), ptr(images), ptr(depths), stream())
-        return images, depths
-
-    def render_views_torch(self, density_bitfield, camera_poses, intrinsics, intrinsics_size, render_size, cam_lights, ambient_light,
-                           testmode_dt_gamma_scale):
-        nerf = self.nerf
-        rgba, depth, normal, normal_fg = nerf.render(
-            nerf.decoder, None, density_bitfield, render_size, render_size, intrinsics[None] * (render_size / intrinsics_size),
-            camera_poses[None], cfg=dict(return_rgba=True, compute_normal=True, dt_gamma_scale=testmode_dt_gamma_scale),
-            perturb=False, normal_bg=self.normal_bg)
-        normal_fg_opencv = torch.cat([normal_fg[..., :1] * 2 - 1, -normal_fg[..., 1:3] * 2 + 1], dim=-1)
-        shading = ((cam_lights[:, None, None, None, :] @ normal_fg_opencv[..., :, None]).clamp(min=0) * (1 - ambient_light)
-                   + ambient_light).squeeze(-1)
-        if self.tonemapping is None:
-            image = rgba[..., :3] * shading + nerf.bg_color * (1 - rgba[..., 3:])
-        else:
-            image = self.tonemapping.lut(self.tonemapping.inverse_lut(rgba[..., :3] / rgba[..., 3:].clamp(min=1e-6))
-                                         + shading.clamp(min=1e-6).log2()) * rgba[..., 3:] + nerf.bg_color * (1 - rgba[..., 3:])
-        images = image.squeeze(0).to(torch.bfloat16).permute(0, 3, 1, 2).clamp(min=0, max=1)
-        alphas = rgba[..., 3:].squeeze(0)
-        depths = normalize_depth(depth.squeeze(0), alphas).to(torch.bfloat16).unsqueeze(1).repeat(1, 3, 1, 1)
+             ptr(scratch), ptr(images), ptr(depths), ptr(None), stream())
         return images, depths
 
     # ------------------------------------------------------------------ one loop iteration (t != None)
@@ -130,7 +137,7 @@ class MVEdit3DStep(Adapter3DMixin):
              intrinsics_size, cam_weights, cam_lights, ancestral_noise, guidance_scale=7.0, render_size=512, n_inverse_steps=96,
              n_inverse_rays=2 ** 14, lr=0.01, alpha_soften=0.02, normal_reg_weight=0.1, entropy_weight=0.01, patch_rgb_weight=0.0,
              patch_normal_weight=0.0, bg_width=0.015, ambient_light=0.2, dt_gamma_scale=1.0, testmode_dt_gamma_scale=0.25,
-             is_init=False, tile_weight=1.0, depth_weight=1.0, phase_events=None):
+             is_init=False, tile_weight=1.0, depth_weight=1.0, phase_events=None, render_bs=None):
         """latents (n_local,4,L,L) fp32; prompt_embeds (2*n_local,T,D) as [neg ; pos]; cameras are the GLOBAL set (all views);
         with view sharding the local slice is ``view_shard.local_range``.  Returns (new latents, ctrl_images, ctrl_depths)."""
         def mark(name):
@@ -145,7 +152,7 @@ class MVEdit3DStep(Adapter3DMixin):
         lo, hi = view_shard.local_range(camera_poses.shape[0])
         n_local = hi - lo
         assert latents.shape[0] == n_local
-        sqrt_ab, sqrt_1mab = get_noise_scales(sch.alphas_cumprod, t, sch.num_train_timesteps)
+        sqrt_ab, sqrt_1mab = sch.noise_scales(t)
         # ---- denoise P1 (:1224-1256)
         latents_scaled = sch.scale_model_input(latents, i)
         latent_batches = [torch.cat([latents_scaled] * 2, dim=0)]
@@ -154,20 +161,26 @@ class MVEdit3DStep(Adapter3DMixin):
         pred_x0 = ((latents_scaled - sqrt_1mab * noise_pred.float()) / sqrt_ab)
         mark('denoise_p1')
         # ---- decode (neighbour hook) + exchange of the decoded views (:1258-1266)
-        tgt_images, tgt_masks = decode_fn(pred_x0, lo, hi)              # (n_local, rs, rs, 3), (n_local, rs, rs, 1) fp32
-        tgt_images = view_shard.gather_views(tgt_images)[None]
-        tgt_masks = view_shard.gather_views(tgt_masks)[None]
-        mark('decode_hook+gather')
+        if decode_fn is None:
+            tgt_images, tgt_masks = self.decode_targets(pred_x0)        # (n_local, rs, rs, 3), (n_local, rs, rs, 1) fp32
+        else:
+            tgt_images, tgt_masks = decode_fn(pred_x0, lo, hi)
+        mark('decode')
+        tgt_images, tgt_masks = view_shard.gather_views(tgt_images, tgt_masks, camera_poses.shape[0])     # ONE collective
+        tgt_images, tgt_masks = tgt_images[None], tgt_masks[None]
+        mark('gather')
         # ---- reconstruct (:1296-1305)
         nerf_optim(self.nerf, tgt_images, tgt_masks, None, optimizer, lr, n_inverse_steps, n_inverse_rays, patch_rgb_weight,
                    patch_normal_weight, alpha_soften, normal_reg_weight, entropy_weight, None, density_grid, density_bitfield,
                    render_size, intrinsics, intrinsics_size, camera_poses, cam_weights, cam_lights, self.nerf.patch_size, is_init,
                    bg_width, ambient_light, dt_gamma_scale, init_shaded=False, tonemapping=self.tonemapping)
-        view_shard.broadcast_field(self.nerf.decoder, density_grid, density_bitfield)
+        if not getattr(self.nerf, 'data_parallel', False):
+            view_shard.broadcast_field(self.nerf.decoder, density_grid, density_bitfield)    # replicated mode: rank 0's field wins
         mark('nerf_optim')
         # ---- render my views (:1341-1395)
         ctrl_images, ctrl_depths = self.render_views(density_bitfield, camera_poses[lo:hi], intrinsics[lo:hi], intrinsics_size,
-                                                     render_size, cam_lights[lo:hi], ambient_light, testmode_dt_gamma_scale)
+                                                     render_size, cam_lights[lo:hi], ambient_light, testmode_dt_gamma_scale,
+                                                     render_bs=render_bs, view_offset=lo, all_intrinsics=intrinsics)
         if render_size != 512:
             ctrl_images = torch.nn.functional.interpolate(ctrl_images.float(), size=(512, 512), mode='bilinear').clamp(0, 1).to(torch.bfloat16)
             ctrl_depths = torch.nn.functional.interpolate(ctrl_depths.float(), size=(512, 512), mode='bilinear').to(torch.bfloat16)

@@ -121,10 +121,19 @@ def upsample2x(x):
     return out
 
 
-def im2col3x3s2(x):
+def im2col3x3s2(x, pad_lo=1):
     B, H, W, C = x.shape
     out = torch.empty(B * (H // 2) * (W // 2), 9 * C, dtype=torch.bfloat16, device=x.device)
-    call('mve_im2col3x3s2_bf16', ptr(x), ptr(out), c_u32(B), c_u32(H), c_u32(W), c_u32(C), stream())
+    call('mve_im2col3x3s2_bf16', ptr(x), ptr(out), c_u32(B), c_u32(H), c_u32(W), c_u32(C), c_int(pad_lo), stream())
+    return out
+
+
+def softmax_rows(x, scale=1.0, out=None):
+    """x [rows, cols] bf16 (row stride may exceed cols) -> softmax(scale * x) per row; in place when out is None."""
+    assert x.dim() == 2 and x.dtype == torch.bfloat16 and x.stride(1) == 1
+    out = x if out is None else out
+    call('mve_softmax_rows_bf16', raw_ptr(x), raw_ptr(out), c_u32(x.shape[0]), c_u32(x.shape[1]), c_u32(x.stride(0)), c_u32(out.stride(0)),
+         c_f32(scale), stream())
     return out
 
 

@@ -81,13 +81,13 @@ def hash_encode(x01, table, levels):
                     wgt = wgt * (1 - w[:, d])
                     idx_c.append(g[:, d])
             # grid_index
-            stride, index = 1, torch.zeros(M, dtype=torch.int64)
+            stride, index = 1, torch.zeros(M, dtype=torch.int64, device=x01.device)
             for d in range(3):
                 if stride <= n:
                     index = index + idx_c[d] * stride
                     stride *= res
             if n < stride:   # hashed level
-                index = torch.zeros(M, dtype=torch.int64)
+                index = torch.zeros(M, dtype=torch.int64, device=x01.device)
                 for d in range(3):
                     index = index ^ ((idx_c[d] * PRIMES[d]) & 0xFFFFFFFF)
             index = (index & 0xFFFFFFFF) % n

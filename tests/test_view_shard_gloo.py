@@ -1,5 +1,6 @@
-"""N>1 path on CPU: world_size-2 gloo processes exercise the view partition, the single all_gather of decoded targets and the
-field broadcast."""
+"""N>1 path on CPU: world_size-2 gloo processes exercise the view partition, the single packed all_gather of decoded targets, the
+collectives of the data-parallel reconstruction (per-ray output gather, flat gradient all-reduce, patch-order broadcast) and the
+flat field broadcast of the replicated mode."""
 import os
 import sys
 
@@ -18,9 +19,27 @@ def _worker(rank, world, port, n_views, q):
     dist.init_process_group('gloo', rank=rank, world_size=world)
     from mvedit_b200 import view_shard
     lo, hi = view_shard.local_range(n_views)
-    full = torch.arange(n_views * 6, dtype=torch.float32).reshape(n_views, 2, 3)
-    got = view_shard.gather_views(full[lo:hi].clone())
-    ok = torch.equal(got, full)
+    # images + masks, bf16-exact values (the pack is bf16): small integers
+    full = (torch.arange(n_views * 2 * 3 * 3, dtype=torch.float32) % 251).reshape(n_views, 2, 3, 3)
+    msk = (torch.arange(n_views * 2 * 3, dtype=torch.float32) % 2).reshape(n_views, 2, 3, 1)
+    got, gotm = view_shard.gather_views(full[lo:hi].clone(), msk[lo:hi].clone(), n_views)
+    ok = torch.equal(got, full) and torch.equal(gotm, msk)
+    # data-parallel reconstruction: row strips of P patches -> full patches in patch-major order
+    P, ps, C = 3, 4, 5
+    rows = ps // world
+    patches = torch.arange(P * ps * ps * C, dtype=torch.float32).reshape(P, ps, ps, C)
+    mine = patches[:, rank * rows:(rank + 1) * rows].reshape(-1, C)
+    ok = ok and torch.equal(view_shard.gather_rays(mine, P), patches.reshape(-1, C))
+    ok = ok and torch.equal(view_shard.gather_rays(patches[0, rank * rows:(rank + 1) * rows].reshape(-1, C), 1), patches[0].reshape(-1, C))
+    flat = torch.full((7,), float(rank + 1))
+    view_shard.allreduce_flat(flat)
+    ok = ok and bool((flat == sum(range(1, world + 1))).all())
+    torch.manual_seed(100 + rank)
+    batches = torch.randperm(12)[None].split(4, dim=1)
+    b2 = view_shard.broadcast_patch_order(batches)
+    allb = [torch.zeros(1, 12, dtype=torch.long) for _ in range(world)]
+    dist.all_gather(allb, torch.cat(list(b2), dim=1))
+    ok = ok and all(torch.equal(a, allb[0]) for a in allb) and len(b2) == 3 and b2[0].shape == (1, 4)
     lin = torch.nn.Linear(4, 4)
     torch.manual_seed(rank)
     with torch.no_grad():
@@ -63,12 +82,12 @@ def test_partition_properties():
 
 
 def test_scheduler_matches_closed_form():
-    from mvedit_b200.pipeline import EulerAncestralScheduler, get_noise_scales
+    from mvedit_b200.pipeline import EulerAncestralScheduler
     s = EulerAncestralScheduler()
     s.set_timesteps(24)
     assert s.timesteps[0] == 999 and len(s.timesteps) == 24 and s.sigmas[-1] == 0
     assert abs(s.init_noise_sigma - 14.6146) < 1e-2                      # SD1.5 sigma_max
-    a, b = get_noise_scales(s.alphas_cumprod, s.timesteps[3], 1000)
+    a, b = s.noise_scales(s.timesteps[3])
     assert abs(float(a) ** 2 + float(b) ** 2 - 1) < 1e-5
     x = torch.randn(2, 4, 8, 8)
     eps = torch.randn(2, 4, 8, 8)
