@@ -5,8 +5,11 @@ reference.  The lists of ``diff_bs``-sized chunks the pipeline passes in are fus
 (the reference loops chunk by chunk only to bound VRAM, adapter3d.py:546); results are identical per sample.
 
 ``dec_args`` / ``dec_kwargs`` stay opaque to the caller (one entry per fused group instead of one per chunk).
-Not carried over in this round: ``cond_noisy_latent_batches`` (reference-only attention read/write modes), ``added_cond_kwargs``
-(SDXL-style conditioning, unused by SD1.5), IP-Adapter ``adapter_scale`` tokens -- they raise.
+IP-Adapter: ``unet.set_ip_adapter(...)`` / ``controlnet.set_cn_attn_processor()`` (mvedit_b200.unet) switch the cross-attentions to
+IPAttnProcessor2_0 / CNAttnProcessor2_0; prompt embeddings then carry the image tokens (T = 77 + 16) and ``adapter_scale`` selects the
+adapter-only guidance.  Extra ControlNets (ip2p, nets[2:]) take ``extra_control_batches`` with weight 1.0 as in the reference.
+Not carried over: ``cond_noisy_latent_batches`` (the texture pipelines' attention read/write modes) and ``added_cond_kwargs``
+(SDXL-style conditioning, unused by SD1.5) -- they raise.
 """
 from copy import copy
 
@@ -59,17 +62,21 @@ class Adapter3DMixin:
                        t, tile_weight, depth_weight, guidance_scale, extra_control_batches=None,
                        added_cond_kwargs_batches=None, adapter_scale=None):
         """adapter3d_mixin.py:68-135 (1-pass)."""
-        assert added_cond_kwargs_batches is None and not extra_control_batches
+        if added_cond_kwargs_batches is not None:
+            raise NotImplementedError('added_cond_kwargs (SDXL conditioning) is not built')
+        extra_control_batches = list(extra_control_batches or [])
         latent_size = latent_batches[0].size(-1)
         noise_pred = []
         for a, b in _groups(latent_batches):
             lat, pe = _cat(latent_batches, a, b), _cat(prompt_embeds_batches, a, b)
             ci = _cat(ctrl_images_batches, a, b)
             cd = _cat(ctrl_depths_batches, a, b) if ctrl_depths_batches is not None else None
+            extra = [_cat(e, a, b) for e in extra_control_batches]
             cak, unet_in, cn_in, unet_pe, cn_pe = self._split_ref(lat, latent_size, pe)
-            nets = MultiControlNet(self.controlnet.nets[:2] if cd is not None else self.controlnet.nets[:1])
-            down, mid = nets(cn_in, t, cn_pe, [ci, cd] if cd is not None else [ci],
-                             [tile_weight, depth_weight] if cd is not None else [tile_weight])
+            assert cd is not None or not extra, 'MultiControlNet order is [tile, depth, *extra]'
+            nets = MultiControlNet(self.controlnet.nets[:2 + len(extra)] if cd is not None else self.controlnet.nets[:1])
+            down, mid = nets(cn_in, t, cn_pe, ([ci, cd] if cd is not None else [ci]) + extra,
+                             ([tile_weight, depth_weight] if cd is not None else [tile_weight]) + [1.0] * len(extra))
             if cak is not None:
                 down, mid = [_interleave_zero(d) for d in down], _interleave_zero(mid)
             o = self.unet(unet_in, t, unet_pe, cak, down, mid)
@@ -82,18 +89,21 @@ class Adapter3DMixin:
                           ctrl_depths_batches=None, depth_weight=None, extra_control_batches=None,
                           cond_noisy_latent_batches=None, added_cond_kwargs_batches=None):
         """adapter3d_mixin.py:137-237: encoder once, decoder once without the tile ControlNet (depth / extra nets if given)."""
-        assert cond_noisy_latent_batches is None and added_cond_kwargs_batches is None and not extra_control_batches
+        if cond_noisy_latent_batches is not None or added_cond_kwargs_batches is not None:
+            raise NotImplementedError('cond_noisy_latent_batches (attention read/write modes) / added_cond_kwargs are not built')
+        extra_control_batches = list(extra_control_batches or [])
         latent_size = latent_batches[0].size(-1)
         noise_pred, dec_args, dec_kwargs = [], [], []
         for a, b in _groups(latent_batches):
             lat, pe = _cat(latent_batches, a, b), _cat(prompt_embeds_batches, a, b)
             cd = _cat(ctrl_depths_batches, a, b) if ctrl_depths_batches is not None else None
+            extra = [_cat(e, a, b) for e in extra_control_batches]
             cak, unet_in, cn_in, unet_pe, cn_pe = self._split_ref(lat, latent_size, pe)
             controlnet_skip = 2 if cd is None else 1
-            if len(self.controlnet.nets) > controlnet_skip:
-                nets = MultiControlNet(self.controlnet.nets[controlnet_skip:])
-                assert cd is not None, 'extra ControlNets (ip2p) are not wired in this round'
-                down, mid = nets(cn_in, t, cn_pe, [cd], [depth_weight])
+            if len(self.controlnet.nets) > controlnet_skip and (cd is not None or extra):
+                nets = MultiControlNet(self.controlnet.nets[controlnet_skip:controlnet_skip + (cd is not None) + len(extra)])
+                down, mid = nets(cn_in, t, cn_pe, ([cd] if cd is not None else []) + extra,
+                                 ([depth_weight] if cd is not None else []) + [1.0] * len(extra))
                 if cak is not None:
                     down, mid = [_interleave_zero(d) for d in down], _interleave_zero(mid)
             else:

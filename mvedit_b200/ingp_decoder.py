@@ -82,9 +82,10 @@ class _FieldFn(Function):
     def forward(ctx, xyz, table, w1, b1, w2, b2, dec, density_only, m_dev=None):
         xyz = xyz.float().contiguous()
         M = xyz.shape[0]
-        alloc = torch.empty if m_dev is None else torch.zeros      # capacity buffers: the tail past *m_dev must read as 0
-        sigma = alloc(M, dtype=torch.float32, device=xyz.device)
-        rgb = None if density_only else alloc(M, 3, dtype=torch.float32, device=xyz.device)
+        # capacity buffers (m_dev given): every consumer (composite fwd / bwd, cull, field backward) clamps to *m_dev, so the tail is
+        # never read and needs no fill
+        sigma = torch.empty(M, dtype=torch.float32, device=xyz.device)
+        rgb = None if density_only else torch.empty(M, 3, dtype=torch.float32, device=xyz.device)
         # kernel mode: 0/1 = fp32 FFMA MLP (full / density), 2/3 = TF32 tensor-core MLP (density / full)
         tf32 = bool(getattr(dec, 'mlp_tf32', True))
         mode = (2 if tf32 or density_only == 2 else 1) if density_only else (3 if tf32 else 0)
@@ -203,6 +204,8 @@ class iNGPDecoder(nn.Module):
         if self._ov is None:
             return
         self._ov_host.copy_(self._ov, non_blocking=True)
+        self._ov.zero_()                                   # the running max restarts: the next call may use another capacity
+        self._ov_cap = int(self.sample_capacity)
         self._ov_event = torch.cuda.Event()
         self._ov_event.record()
 
@@ -216,9 +219,10 @@ class iNGPDecoder(nn.Module):
             self.note_sample_overflow()
         self._ov_event.synchronize()
         m = int(self._ov_host[0])
-        if self.sample_capacity and m > self.sample_capacity:
-            raise RuntimeError('iNGPDecoder: %d samples survived the weight cull in one training forward but sample_capacity is %d -- '
-                               'rays were dropped; raise decoder.sample_capacity' % (m, self.sample_capacity))
+        cap = getattr(self, '_ov_cap', 0)
+        if cap and m > cap:
+            raise RuntimeError('iNGPDecoder: %d samples survived the weight cull in one training forward but sample_capacity was %d -- '
+                               'rays were dropped; raise decoder.sample_capacity' % (m, cap))
         return m
 
     def _field_params(self):
@@ -333,8 +337,8 @@ class iNGPDecoder(nn.Module):
                          c_f32(1e-4), c_int(0), ptr(w0), ptr(scratch[:N]), ptr(scratch[N:2 * N]), ptr(scratch[2 * N:]), stream())
                     counter2 = torch.zeros(1, dtype=torch.int32, device=xyzs.device)
                     rays2 = torch.empty_like(rays)
-                    xyzs2 = torch.zeros(cap, 3, dtype=torch.float32, device=xyzs.device)
-                    ts2 = torch.zeros(cap, 2, dtype=torch.float32, device=xyzs.device)
+                    xyzs2 = torch.empty(cap, 3, dtype=torch.float32, device=xyzs.device)
+                    ts2 = torch.empty(cap, 2, dtype=torch.float32, device=xyzs.device)
                     call('mve_cull_samples', ptr(w0), c_f32(self.weight_culling_th), ptr(rays), ptr(xyzs), ptr(ts), c_u32(N), c_u32(cap1),
                          ptr(counter), c_u32(cap), ptr(rays2), ptr(xyzs2), ptr(ts2), ptr(counter2), stream())
                     xyzs, ts, rays, counter = xyzs2, ts2, rays2, counter2

@@ -217,9 +217,12 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
     V = camera_poses.shape[0]
     n_sel = max(n_inverse_rays // (ps * ps), 1)
     n_patches_total = V * (render_size // ps) ** 2
-    if dec.sample_capacity <= 0:
-        dec.sample_capacity = n_sel * ps * ps * 160
     dec.check_sample_overflow()                       # result of the PREVIOUS call's iterations (no sync on the fast path)
+    if getattr(dec, 'auto_capacity', dec.sample_capacity <= 0):
+        # post-cull sample buffers: the initial fit starts from fog (hundreds of surviving samples per ray), later calls see a
+        # fitted field.  N * max_steps can never overflow; N * 256 is checked (check_sample_overflow raises if rays were dropped).
+        dec.auto_capacity = True
+        dec.sample_capacity = n_sel * ps * ps * (int(dec.max_steps) if is_init else min(256, int(dec.max_steps)))
     use_graph = bool(getattr(nerf, 'use_cuda_graph', False)) and bool(optimizer.defaults.get('capturable', False)) and not debug
     rank, world = view_shard.world() if getattr(nerf, 'data_parallel', False) else (0, 1)
     assert ps % world == 0, 'data-parallel reconstruction: the patch rows must divide by the world size'

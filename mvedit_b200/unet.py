@@ -104,6 +104,35 @@ class _Net:
             self._temb_slices[n] = (off, c)
             off += c
         self._temb_total = off
+        self.ip_tokens, self.ip_scale, self.drop_tokens = 0, 1.0, 0
+
+    # ---- IP-Adapter (lib/models/architecture/ip_adapter/ip_adapter.py:85-113)
+    def transformer_paths(self):
+        """Transformer blocks in diffusers ``attn_processors`` order (down, up, mid): block i owns processors 2i (attn1), 2i+1 (attn2)."""
+        cfg, paths = self.cfg, []
+        for i in range(len(cfg.block_out_channels)):
+            if cfg.attn_levels[i]:
+                paths += [f'down_blocks.{i}.attentions.{j}' for j in range(cfg.layers_per_block)]
+        rev = list(reversed(cfg.attn_levels))
+        for i in range(len(cfg.block_out_channels)):
+            if rev[i]:
+                paths += [f'up_blocks.{i}.attentions.{j}' for j in range(cfg.layers_per_block + 1)]
+        return paths + ['mid_block.attentions.0']
+
+    def set_ip_adapter(self, ip_state_dict, num_tokens=16, scale=1.0):
+        """UNet side of IPAdapter.set_ip_adapter: every cross-attention becomes IPAttnProcessor2_0 (attention_processor.py:283-396).
+        ``ip_state_dict`` is the ``ip_adapter`` section of an IP-Adapter checkpoint ("{2i+1}.to_k_ip.weight", "{2i+1}.to_v_ip.weight");
+        to_k_ip / to_v_ip are fused into one projection per block."""
+        for i, p in enumerate(self.transformer_paths()):
+            wk, wv = ip_state_dict[f'{2 * i + 1}.to_k_ip.weight'], ip_state_dict[f'{2 * i + 1}.to_v_ip.weight']
+            self.w.lin[p + '#ip_kv'] = (_bf(torch.cat([wk, wv], dim=0), self.device), None)
+        self.ip_tokens, self.ip_scale = int(num_tokens), float(scale)
+
+    def set_cn_attn_processor(self, num_tokens=4):
+        """ControlNet side (CNAttnProcessor2_0, attention_processor.py:466-556): cross-attention sees context[:, :-num_tokens].
+        The reference instantiates it with the DEFAULT num_tokens = 4 although the plus adapter appends 16 image tokens
+        (ip_adapter.py:104-110): 12 image tokens stay in the ControlNets' context.  Quirk kept for parity."""
+        self.drop_tokens = int(num_tokens)
 
     # ---- time embedding: emb [1|B, 4*C0] bf16 and ALL resnets' projections in one GEMM -> f32 [B, total]
     def time_embed(self, t, batch):
@@ -166,10 +195,18 @@ class _Net:
         q = T.gemm(n2, wq).view(Bj, Sj, C)
         if n_imgs > 1:
             ctx = ctx.view(Bj, n_imgs, *ctx.shape[1:]).float().mean(dim=1).to(torch.bfloat16)
+        if self.drop_tokens:
+            ctx = ctx[:, :ctx.shape[1] - self.drop_tokens]
+        ctx_ip = None
+        if self.ip_tokens and (p + '#ip_kv') in w.lin:
+            ctx, ctx_ip = ctx[:, :ctx.shape[1] - self.ip_tokens], ctx[:, ctx.shape[1] - self.ip_tokens:]
         Tn = ctx.shape[1]
         wkv, _ = w.fused(b + '.attn2.kv', [b + '.attn2.to_k', b + '.attn2.to_v'])
         kv = T.gemm(ctx.reshape(-1, ctx.shape[-1]), wkv).view(Bj, Tn, 2 * C)
         o = T.attention(q, kv[:, :, :C], kv[:, :, C:], heads)
+        if ctx_ip is not None:                      # IPAttnProcessor2_0: second attention over the image tokens, added with ``scale``
+            kv_ip = T.gemm(ctx_ip.reshape(-1, ctx_ip.shape[-1]), w.lin[p + '#ip_kv'][0]).view(Bj, self.ip_tokens, 2 * C)
+            o.add_(T.attention(q, kv_ip[:, :, :C], kv_ip[:, :, C:], heads), alpha=self.ip_scale)
         wo2, bo2 = w.linear(b + '.attn2.to_out.0')
         h = T.gemm(o.view(-1, C), wo2, bias=bo2, residual=h)
         # feed-forward (GEGLU)

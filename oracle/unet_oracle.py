@@ -147,6 +147,49 @@ def random_controlnet_state_dict(cfg=SD15, seed=1, zero_convs_nonzero=True):
     return sd
 
 
+# ------------------------------------------------------------------------------------------------ IP-Adapter (ip_adapter.py:85-113)
+IP_OPTS = {}          # id(state dict) -> dict(ip_tokens=.., ip_scale=..) for a UNet, dict(drop_tokens=..) for a ControlNet
+
+
+def transformer_paths(cfg=SD15):
+    """The UNet's transformer blocks in diffusers ``attn_processors`` order (down_blocks, up_blocks, mid_block -- the module
+    registration order of UNet2DConditionModel): processor 2i is attn1 of block i, 2i + 1 its attn2 -- the numbering of the
+    ``ip_adapter`` checkpoint section ("1.to_k_ip.weight", "3.to_k_ip.weight", ..., ip_adapter.py:61-62)."""
+    paths = []
+    for i in range(len(cfg.block_out_channels)):
+        if cfg.attn_levels[i]:
+            paths += [f'down_blocks.{i}.attentions.{j}' for j in range(cfg.layers_per_block)]
+    rev = list(reversed(cfg.attn_levels))
+    for i in range(len(cfg.block_out_channels)):
+        if rev[i]:
+            paths += [f'up_blocks.{i}.attentions.{j}' for j in range(cfg.layers_per_block + 1)]
+    return paths + ['mid_block.attentions.0']
+
+
+def random_ip_adapter_state_dict(cfg=SD15, seed=5):
+    """'ip_adapter' section of an IP-Adapter checkpoint: {2i+1}.to_k_ip.weight / to_v_ip.weight [hidden, cross_attention_dim]."""
+    g = torch.Generator().manual_seed(seed)
+    boc = cfg.block_out_channels
+    sd = {}
+    for i, p in enumerate(transformer_paths(cfg)):
+        blk = int(p.split('.')[1]) if not p.startswith('mid') else len(boc) - 1
+        c = boc[-1] if p.startswith('mid') else (boc[blk] if p.startswith('down') else list(reversed(boc))[blk])
+        for n in ('to_k_ip', 'to_v_ip'):
+            sd[f'{2 * i + 1}.{n}.weight'] = torch.randn(c, cfg.cross_attention_dim, generator=g) / math.sqrt(cfg.cross_attention_dim)
+    return sd
+
+
+def set_ip_adapter(unet_sd, ip_sd, cfg=SD15, num_tokens=16, scale=1.0, controlnet_sds=(), cn_num_tokens=4):
+    """IPAdapter.set_ip_adapter (ip_adapter.py:85-113) for the functional oracle: merges the adapter weights into the UNet state dict
+    under <block>.transformer_blocks.0.attn2.to_{k,v}_ip.weight and registers the processor options."""
+    for i, p in enumerate(transformer_paths(cfg)):
+        for n in ('to_k_ip', 'to_v_ip'):
+            unet_sd[f'{p}.transformer_blocks.0.attn2.{n}.weight'] = ip_sd[f'{2 * i + 1}.{n}.weight'].to(next(iter(unet_sd.values())))
+    IP_OPTS[id(unet_sd)] = dict(ip_tokens=num_tokens, ip_scale=scale)
+    for c in controlnet_sds:
+        IP_OPTS[id(c)] = dict(drop_tokens=cn_num_tokens)
+
+
 # ------------------------------------------------------------------------------------------------ layers
 def timestep_embedding(t, dim):
     """diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0)."""
@@ -177,25 +220,39 @@ def resnet(sd, p, x, emb, cfg):
     return x + h
 
 
-def attention(sd, p, x, ctx, heads, num_cross_attn_imgs=1):
+def attention(sd, p, x, ctx, heads, num_cross_attn_imgs=1, ip_tokens=0, ip_scale=1.0, drop_tokens=0):
     """Attention with AttnProcessor2_0 semantics; with num_cross_attn_imgs=2 the CrossImageAttnProcWrapper view
-    (joint_attn.py:13-33): self-attention spans the (ref, view) pair, text context is averaged over the pair."""
+    (joint_attn.py:13-33): self-attention spans the (ref, view) pair, text context is averaged over the pair.
+    Cross-attention variants of the IP-Adapter (pinned against the reference classes by tests/test_reference_pins.py):
+      ip_tokens > 0   IPAttnProcessor2_0 (ip_adapter/attention_processor.py:301-396): the last ip_tokens context tokens go through
+                      to_k_ip / to_v_ip (keys p + '.to_k_ip.weight' / '.to_v_ip.weight') in a second attention, added with ip_scale;
+      drop_tokens > 0 CNAttnProcessor2_0 (:472-556): the ControlNets attend to context[:, :-drop_tokens] only (NB num_tokens defaults
+                      to 4 there although the plus adapter appends 16 tokens: 12 image tokens stay in -- quirk kept)."""
     B, S, C = x.shape
     if num_cross_attn_imgs > 1:
         x = x.reshape(B // num_cross_attn_imgs, num_cross_attn_imgs * S, C)
         if ctx is not None:
             ctx = ctx.reshape(B // num_cross_attn_imgs, num_cross_attn_imgs, *ctx.shape[1:]).mean(dim=1)
+    ip_ctx = None
+    if ctx is not None and drop_tokens > 0:
+        ctx = ctx[:, :ctx.shape[1] - drop_tokens]
+    if ctx is not None and ip_tokens > 0:
+        ctx, ip_ctx = ctx[:, :ctx.shape[1] - ip_tokens], ctx[:, ctx.shape[1] - ip_tokens:]
     kv = x if ctx is None else ctx
     q, k, v = _l(sd, p + '.to_q', x), _l(sd, p + '.to_k', kv), _l(sd, p + '.to_v', kv)
     d = C // heads
     sh = lambda t: t.reshape(t.shape[0], t.shape[1], heads, d).transpose(1, 2)
     o = F.scaled_dot_product_attention(sh(q), sh(k), sh(v))
     o = o.transpose(1, 2).reshape(x.shape[0], x.shape[1], C)
+    if ip_ctx is not None:
+        o_ip = F.scaled_dot_product_attention(sh(q), sh(_l(sd, p + '.to_k_ip', ip_ctx)), sh(_l(sd, p + '.to_v_ip', ip_ctx)))
+        o = o + ip_scale * o_ip.transpose(1, 2).reshape(x.shape[0], x.shape[1], C)
     o = _l(sd, p + '.to_out.0', o)
     return o.reshape(B, S, C)
 
 
 def transformer(sd, p, x, ctx, heads, cfg, num_cross_attn_imgs=1):
+    ip = IP_OPTS.get(id(sd), {})
     B, C, H, W = x.shape
     res = x
     h = _c(sd, p + '.proj_in', _gn(sd, p + '.norm', x, cfg.norm_groups, 1e-6), padding=0)
@@ -203,7 +260,7 @@ def transformer(sd, p, x, ctx, heads, cfg, num_cross_attn_imgs=1):
     b = p + '.transformer_blocks.0'
     ln = lambda n, t: F.layer_norm(t, (C,), sd[b + f'.{n}.weight'], sd[b + f'.{n}.bias'], 1e-5)
     h = h + attention(sd, b + '.attn1', ln('norm1', h), None, heads, num_cross_attn_imgs)
-    h = h + attention(sd, b + '.attn2', ln('norm2', h), ctx, heads, num_cross_attn_imgs)
+    h = h + attention(sd, b + '.attn2', ln('norm2', h), ctx, heads, num_cross_attn_imgs, **ip)
     f = _l(sd, b + '.ff.net.0.proj', ln('norm3', h))
     a, gate = f.chunk(2, dim=-1)
     h = h + _l(sd, b + '.ff.net.2', a * F.gelu(gate))

@@ -95,6 +95,24 @@ def main():
                ja_self=wrap(None, hs, num_cross_attn_imgs=2).numpy(), ja_cross=wrap(None, hs, encoder_hidden_states=ctx, num_cross_attn_imgs=2).numpy(),
                ja_self_1=wrap(None, hs, num_cross_attn_imgs=1).numpy())
 
+    # ---- IPAttnProcessor2_0 / CNAttnProcessor2_0 (ip_adapter/attention_processor.py:283-396, :466-556) on a stand-in Attention module
+    ap = load_by_path('ref_ip_attn', 'lib/models/architecture/ip_adapter/attention_processor.py')
+    torch.manual_seed(3)
+    Ci, Di, Hh, Ti, Ni = 16, 8, 2, 9, 4            # hidden, cross dim, heads, context tokens (5 text + 4 image), image tokens
+    lin = lambda i, o, b: torch.nn.Linear(i, o, bias=b)
+    attn = types.SimpleNamespace(spatial_norm=None, group_norm=None, norm_cross=False, heads=Hh, residual_connection=False, rescale_output_factor=1.0,
+                                 to_q=lin(Ci, Ci, False), to_k=lin(Di, Ci, False), to_v=lin(Di, Ci, False),
+                                 to_out=[lin(Ci, Ci, True), torch.nn.Identity()])
+    ipp = ap.IPAttnProcessor2_0(hidden_size=Ci, cross_attention_dim=Di, scale=0.7, num_tokens=Ni)
+    cnp = ap.CNAttnProcessor2_0(num_tokens=2)
+    hs_i, ctx_i = torch.randn(3, 6, Ci, generator=g), torch.randn(3, Ti, Di, generator=g)
+    with torch.no_grad():
+        out.update(ip_hs=hs_i.numpy(), ip_ctx=ctx_i.numpy(), ip_out=ipp(attn, hs_i, encoder_hidden_states=ctx_i).numpy(),
+                   cn_out=cnp(attn, hs_i, encoder_hidden_states=ctx_i).numpy(),
+                   ip_wq=attn.to_q.weight.numpy(), ip_wk=attn.to_k.weight.numpy(), ip_wv=attn.to_v.weight.numpy(),
+                   ip_wo=attn.to_out[0].weight.numpy(), ip_bo=attn.to_out[0].bias.numpy(), ip_wk_ip=ipp.to_k_ip.weight.numpy(),
+                   ip_wv_ip=ipp.to_v_ip.weight.numpy())
+
     # ---- get_noise_scales (diffusion.py:4-21) on SD1.5's scaled_linear schedule
     dif = load_by_path('ref_diffusion', 'lib/core/diffusion.py')
     betas = np.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=np.float64) ** 2

@@ -1,5 +1,6 @@
 """Fused nerf_optim objective (mve_nerf_patch_loss + entropy folded into composite backward) vs the eager torch chain that restates
-mvedit_3d_pipeline.py:541-603 (mvedit_b200.nerf.nerf_optim's non-fused path is that restatement, used here as the checker)."""
+mvedit_3d_pipeline.py:541-603 with the oracle's loss modules (oracle/nerf_oracle.py; TVLoss / depth_to_normal pinned against the
+reference's own functions by tests/test_reference_pins.py)."""
 import math
 
 import pytest
@@ -9,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 def torch_chain(image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps, shaded, ambient, bg, bg_width, plw, alpha_mul, nreg, went):
-    from mvedit_b200.nerf import depth_to_normal, TVLoss, L1LossMod
+    from oracle.nerf_oracle import depth_to_normal, TVLoss, L1LossMod
     import torch.nn.functional as F
     P = alpha.numel() // (ps * ps)
     out_rgbs = image.reshape(P, ps, ps, 3)
@@ -37,7 +38,7 @@ def torch_chain(image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights, p
 @pytest.mark.parametrize('shaded', [False, True])
 @pytest.mark.parametrize('P,ps', [(1, 32), (3, 16)])
 def test_fused_patch_loss_matches_torch_chain(shaded, P, ps):
-    from mvedit_b200.nerf import _PatchLossFn
+    from mvedit_b200.nerf import patch_loss
     g = torch.Generator(device='cuda').manual_seed(P * ps + shaded)
     N = P * ps * ps
     R = lambda *s: torch.rand(*s, device='cuda', generator=g)
@@ -53,12 +54,10 @@ def test_fused_patch_loss_matches_torch_chain(shaded, P, ps):
     inp = [t.clone().requires_grad_(True) for t in (image, alpha, depth)]
     ref = torch_chain(*inp, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps, shaded, 0.2, 1.0, 0.015, 1.2, 5.0, 1.3, 0.02)
     ref[0].backward()
-    inp2 = [t.clone().requires_grad_(True) for t in (image, alpha, depth)]
-    out = _PatchLossFn.apply(*inp2, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps, shaded, 0.2, 1.0, 0.015, 1.2, *sc)
-    out[0].backward()
+    out, *grads = patch_loss(image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps, shaded, 0.2, 1.0, 0.015, 1.2, *sc)
     torch.testing.assert_close(out, ref.detach(), rtol=2e-4, atol=1e-6)
-    for a, b, name in zip(inp2, inp, ('image', 'alpha', 'depth')):
-        err = (a.grad - b.grad).abs().max().item()
+    for a, b, name in zip(grads, inp, ('image', 'alpha', 'depth')):
+        err = (a.view_as(b.grad) - b.grad).abs().max().item()
         assert err <= 2e-3 * b.grad.abs().max().item() + 1e-7, (name, err, b.grad.abs().max().item())
 
 

@@ -162,3 +162,71 @@ def test_controlnet_hint_dedupe_matches_full(tiny):
         # downstream the two runs are not bit-equal: GroupNorm statistics are accumulated with float atomics (order varies run to
         # run) and a flipped bf16 rounding is amplified by the random-weight net; the exact check is the one above
         assert rel(a, b)[0] <= 5e-2
+
+
+def test_ip_adapter_and_extra_control_and_benchmark_shape():
+    """(1) IP-Adapter mode as BASELINE configs[2] runs it on the denoise side: prompt embeddings carry 16 image tokens (T = 93), the UNet's
+    cross-attentions are IPAttnProcessor2_0, the ControlNets' CNAttnProcessor2_0 (drops 4 tokens), reference-image joint attention on
+    the cond half, adapter_scale guidance -- vs the oracle (processors pinned against the reference classes on CPU).
+    (2) an extra (ip2p-style) ControlNet through extra_control_batches.
+    (3) UNet parity at the BENCHMARKED shape family: SD-1.5 widths, latent 64, batch 8, ControlNet with cond_repeat=2."""
+    from mvedit_b200.unet import UNet, ControlNet, MultiControlNet
+    from mvedit_b200.adapter3d_mixin import Adapter3DMixin
+    cfg = uo.TINY
+    usd, csds = uo.random_unet_state_dict(cfg, 0), [uo.random_controlnet_state_dict(cfg, s) for s in (1, 2, 3)]
+    ipsd = uo.random_ip_adapter_state_dict(cfg, 5)
+    unet, cns = UNet(usd, cfg), [ControlNet(c, cfg) for c in csds]
+    unet.set_ip_adapter(ipsd, num_tokens=16, scale=0.8)
+    for c in cns:
+        c.set_cn_attn_processor()
+    usd_g, csd_g = _to(usd, 'cuda'), [_to(c, 'cuda') for c in csds]
+    uo.set_ip_adapter(usd_g, ipsd, cfg, num_tokens=16, scale=0.8, controlnet_sds=csd_g)
+    g = torch.Generator(device='cuda').manual_seed(11)
+    N, L = 2, 16
+    lat_u = torch.randn(N, 4, L, L, device='cuda', generator=g)
+    lat_c = torch.randn(N, 4, 2 * L, L, device='cuda', generator=g)
+    pe = torch.randn(2 * N, 93, cfg.cross_attention_dim, device='cuda', generator=g)
+    ci, cd, ce = (torch.rand(N, 3, 8 * L, 8 * L, device='cuda', generator=g) for _ in range(3))
+    pipe = Adapter3DMixin()
+    pipe.unet, pipe.controlnet = unet, MultiControlNet(cns)
+    with torch.no_grad():
+        ref = uo.get_noise_pred(usd_g, csd_g[:2], cfg, [lat_u, lat_c], list(pe.split(N)), [ci, ci], [cd, cd], 700, 0.5, 0.5, 5.0)
+        out = pipe.get_noise_pred([lat_u, lat_c], list(pe.split(N)), [ci, ci], [cd, cd], 700, 0.5, 0.5, 5.0)
+        assert rel(out, ref)[0] <= 1e-1, rel(out, ref)
+        # adapter_scale: a * (cond - uncond)
+        out_a = pipe.get_noise_pred([lat_u, lat_c], list(pe.split(N)), [ci, ci], [cd, cd], 700, 0.5, 0.5, 5.0, adapter_scale=2.0)
+        ref_c = uo.get_noise_pred(usd_g, csd_g[:2], cfg, [lat_u, lat_c], list(pe.split(N)), [ci, ci], [cd, cd], 700, 0.5, 0.5, 1.0)
+        ref_u = uo.get_noise_pred(usd_g, csd_g[:2], cfg, [lat_u, lat_c], list(pe.split(N)), [ci, ci], [cd, cd], 700, 0.5, 0.5, 0.0)
+        assert rel(out_a, 2.0 * (ref_c - ref_u))[0] <= 1.5e-1
+        # the IP tokens matter: zeroing the adapter scale changes the output
+        unet.ip_scale = 0.0
+        out0 = pipe.get_noise_pred([lat_u, lat_c], list(pe.split(N)), [ci, ci], [cd, cd], 700, 0.5, 0.5, 5.0)
+        unet.ip_scale = 0.8
+        assert rel(out0, out)[0] > 1e-3
+        # (2) extra ControlNet, weight 1.0 (adapter3d_mixin.py:101-109)
+        lb, pb = [lat_u, lat_u], list(pe.split(N))
+        down_o, mid_o = uo.multi_controlnet_forward(csd_g, cfg, lat_u, 300, pb[0], [ci, cd, ce], [0.6, 0.4, 1.0])
+        ref3 = uo.unet_forward(usd_g, cfg, lat_u, 300, pb[0], None, down_o, mid_o)
+        out3 = pipe.get_noise_pred(lb, pb, [ci, ci], [cd, cd], 300, 0.6, 0.4, 0.0, extra_control_batches=[[ce, ce]])
+        assert rel(out3, ref3)[0] <= 3e-2, rel(out3, ref3)
+    del unet, cns, usd_g, csd_g
+    torch.cuda.empty_cache()
+    # (3) benchmark shape family
+    cfg = uo.SD15
+    usd, csd = uo.random_unet_state_dict(cfg, 0), uo.random_controlnet_state_dict(cfg, 1)
+    unet, cn = UNet(usd, cfg), ControlNet(csd, cfg)
+    usd_g, csd_g = _to(usd, 'cuda'), _to(csd, 'cuda')
+    B, L = 8, 64
+    x = torch.randn(B, 4, L, L, device='cuda', generator=g)
+    ctx = torch.randn(B, 77, 768, device='cuda', generator=g)
+    cond = torch.rand(B // 2, 3, 8 * L, 8 * L, device='cuda', generator=g)
+    c2 = torch.cat([cond] * 2)
+    with torch.no_grad():
+        d_o, m_o = uo.controlnet_forward(csd_g, cfg, x, 500, ctx, c2, 1.0)
+        d, m = cn(x, 500, ctx, c2, 1.0, cond_repeat=2)
+        for a, b in zip(d + [m], d_o + [m_o]):
+            assert rel(a.permute(0, 3, 1, 2), b)[0] <= 3e-2
+        ref = uo.unet_forward(usd_g, cfg, x, 500, ctx, None, d_o, m_o)
+        out = unet(x, 500, ctx, None, d, m)
+    r2, rmax = rel(out, ref)
+    assert r2 <= 3e-2 and rmax <= 8e-2, (r2, rmax)

@@ -35,6 +35,16 @@ def test_cross_image_attention_oracle():
     np.testing.assert_allclose(uo.attention(sd2, 'a', hs, ctx, 2, 2).numpy(), PINS['ja_cross'], rtol=1e-5, atol=1e-6)
 
 
+def test_ip_adapter_attention_oracle():
+    """oracle/unet_oracle.attention(ip_tokens / drop_tokens) == IPAttnProcessor2_0 / CNAttnProcessor2_0 of the reference."""
+    from oracle import unet_oracle as uo
+    sd = {'a.to_q.weight': T('ip_wq'), 'a.to_k.weight': T('ip_wk'), 'a.to_v.weight': T('ip_wv'), 'a.to_out.0.weight': T('ip_wo'),
+          'a.to_out.0.bias': T('ip_bo'), 'a.to_k_ip.weight': T('ip_wk_ip'), 'a.to_v_ip.weight': T('ip_wv_ip')}
+    hs, ctx = T('ip_hs'), T('ip_ctx')
+    np.testing.assert_allclose(uo.attention(sd, 'a', hs, ctx, 2, ip_tokens=4, ip_scale=0.7).numpy(), PINS['ip_out'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(uo.attention(sd, 'a', hs, ctx, 2, drop_tokens=2).numpy(), PINS['cn_out'], rtol=1e-5, atol=1e-6)
+
+
 def test_noise_scales():
     from oracle import nerf_oracle as no
     from mvedit_b200.pipeline import EulerAncestralScheduler
