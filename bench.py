@@ -296,9 +296,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     _lib.PROFILE[0] = None
     pipe.nerf.use_cuda_graph = graph_flag
+    prof2 = []
+    _lib.PROFILE[0] = prof2                    # graph replays do not pass through call(): this records the eager launches only
     with torch.no_grad():
         one_step(False, phase_events)          # phases of a step as timed (graph mode as configured)
     torch.cuda.synchronize()
+    _lib.PROFILE[0] = None
+    render_ms_same_pass = sum(a.elapsed_time(b) for name, a, b, meta in prof2 if name == 'mve_render_rays')
     phases = {b[0]: round(a[1].elapsed_time(b[1]), 2) for a, b in zip(phase_events[:-1], phase_events[1:])}
     rs = pipe.nerf.decoder.last_render_stats()
     lc = [int(c.item()) for c in pipe.nerf.decoder.last_counts]
@@ -330,7 +334,7 @@ def run_ours(args):
     raster = raymarch_microbench(device, pk, rank, world, dist if world > 1 else None, with_ref=(rank == 0))
     extra = {}
     if world == 1:
-        extra['render_roofline'] = render_gather_roofline(device, pipe, rs[0], cat.get('mve_render_rays', dict(ms=0))['ms'])
+        extra['render_roofline'] = render_gather_roofline(device, pipe, rs[0], render_ms_same_pass)
         extra['field_precision'] = tf32_vs_fp32_render(pipe, bitfield, poses, K)
         extra['gpu_baseline'] = gpu_baseline(device, pipe, dict(grid=snap['grid'], bits=snap['bits']), poses, K, cam_w, lights, tgt_img, tgt_msk, phases,
                                              skip=args.no_gpu_baseline)
@@ -473,43 +477,58 @@ def raymarch_microbench(device, pk, rank=0, world=1, dist=None, with_ref=True):
 
 def render_gather_roofline(device, pipe, samples_shaded, render_ms):
     """The fused renderer moves ~0 HBM bytes per sample (table and occupancy grid stay in L2): HBM is the wrong roof.  Its roof is the
-    rate at which the SMs can pull random 8-byte entries of a 28.7 MB table out of L2.  Measured here with a bare gather kernel
-    (torch index_select of float2 rows from a table of the hash grid's size, 2^26 random indices) and compared with the renderer's
-    96 gathers per shaded sample."""
+    rate at which the SMs can pull random 8-byte entries of a 28.7 MB table out of L2 / L1: measured with mve_gather_ceiling (every
+    thread: in-register random indices, 8 independent 8-byte loads in flight, nothing else touches memory; 148 x 16 CTAs x 256 threads
+    x 4096 gathers) and compared with the renderer's 96 gathers per shaded sample (same pass as ``work.render_samples_shaded``)."""
+    from mvedit_b200._lib import call, ptr, stream, c_u32
     n_entries = pipe.nerf.decoder.encoder.levels['n_entries']
     table = torch.randn(n_entries, 2, device=device)
-    idx = torch.randint(0, n_entries, (1 << 26,), device=device)
-    out = torch.empty(1 << 26, 2, device=device)
+    blocks, per = 148 * 16, 4096
+    out = torch.empty(blocks * 256, device=device)
     ts = []
     for _ in range(6):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); torch.index_select(table, 0, idx, out=out); e1.record(); torch.cuda.synchronize()
+        e0.record()
+        call('mve_gather_ceiling', ptr(table), c_u32(n_entries), c_u32(blocks), c_u32(per), ptr(out), stream())
+        e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ms = float(np.median(ts[1:]))
-    ceil_g = (1 << 26) / ms / 1e6                  # G gathers / s (each 8 B) incl. the 4+8 B/gather of index read and result write
+    ceil_g = blocks * 256 * per / ms / 1e6                  # G gathers / s, 8 B each
     got_g = samples_shaded * 96 / max(render_ms, 1e-9) / 1e6
     return dict(bound='l2-gather', kernel='k_render_rays', gathers_per_sample=96, samples=samples_shaded, ms=round(render_ms, 3),
+                gsamples_s=round(samples_shaded / max(render_ms, 1e-9) / 1e6, 2),
                 achieved_ggathers_s=round(got_g, 1), achieved_gbs=round(got_g * 8, 1), ceiling_ggathers_s=round(ceil_g, 1),
                 ceiling_gbs=round(ceil_g * 8, 1), frac=round(got_g / ceil_g, 3),
-                how='ceiling = torch.index_select of 2^26 random float2 rows from a 28.7 MB table (L2 resident), median of 5; the renderer '
-                    'additionally runs the 24->64->4 MLP, the DDA and the compositing per sample')
+                how='ceiling = mve_gather_ceiling: random 8-byte gathers from a 28.7 MB table, in-register indices, 8 loads in flight per thread, '
+                    'median of 5; the renderer additionally runs the 24->64->4 MLP, the DDA and the compositing per sample, and its '
+                    'coarse levels hit L1')
 
 
 def tf32_vs_fp32_render(pipe, bitfield, poses, K):
-    """The field MLP runs in TF32 by default (what the reference runs: allow_tf32).  PSNR of the rendered views on the bench state
-    against the same render with the fp32 FFMA MLP kernels (VERDICT r1 weak #4: measure the ReLU-flip effect, do not assert it)."""
+    """The field MLP runs in TF32 by default (what the reference runs: allow_tf32).  PSNR of RGBA composited through the training-path
+    kernels (march -> field -> composite, perturb off) on camera rays of the bench state with the TF32 tensor-core MLP against the same
+    with the fp32 FFMA MLP kernels (VERDICT r1 weak #4: measure the ReLU-flip effect, do not assert it)."""
+    from mvedit_b200.nerf import pixel_directions
     dec = pipe.nerf.decoder
+    size = 128
+    Ks = (K[:4] * (size / IMG)).contiguous()
+    d = pixel_directions(Ks, size, size)
+    rd = torch.nn.functional.normalize(d @ poses[:4, None, :3, :3].transpose(-1, -2), dim=-1).reshape(1, -1, 3)
+    ro = poses[:4, None, None, :3, 3].expand(4, size, size, 3).reshape(1, -1, 3)
+    cap_prev, train_prev = dec.sample_capacity, dec.training
+    dec.sample_capacity = 0                    # reference protocol (host reads the counts): a diagnostic, not on the timed path
+    dec.train(True)
+    outs = []
     with torch.no_grad():
-        outs = []
         for flag in (True, False):
             dec.mlp_tf32 = flag
-            ws, depth, image = dec.render_cameras(poses[:4], (K[:4] * 0.5).contiguous(), IMG // 2, IMG // 2, bitfield, pipe.nerf.grid_size,
-                                                  dt_gamma=float(0.25 * 2 / (K[0, 0] + K[0, 1]) / 0.5))
-            outs.append(torch.cat([image, ws[..., None]], dim=-1))
-        dec.mlp_tf32 = True
+            o = dec(ro, rd, None, bitfield, pipe.nerf.grid_size, dt_gamma=float(2 / (Ks[0, 0] + Ks[0, 1])), perturb=False)
+            outs.append(torch.cat([o['image'][0], o['weights_sum'][0][:, None]], dim=-1))
+    dec.mlp_tf32, dec.sample_capacity = True, cap_prev
+    dec.train(train_prev)
     mse = float((outs[0] - outs[1]).square().mean())
-    return dict(views='4 x 256^2 of the bench state', rgba_psnr_db=round(10 * math.log10(1.0 / max(mse, 1e-20)), 1),
-                max_abs=round(float((outs[0] - outs[1]).abs().max()), 5))
+    return dict(views='4 x 128^2 camera rays of the bench state through march -> field -> composite', rgba_psnr_db=round(10 * math.log10(1.0 / max(mse, 1e-20)), 1),
+                max_abs=round(float((outs[0] - outs[1]).abs().max()), 5), mean_abs=float('%.3g' % float((outs[0] - outs[1]).abs().mean())))
 
 
 # --------------------------------------------------------------------------------------------------------- GPU reference leg
@@ -585,6 +604,34 @@ def gpu_baseline(device, pipe, state, poses, K, cam_w, lights, tgt_img, tgt_msk,
             out.update(recon_ms=round(ms_it / n_it * N_INVERSE_STEPS, 1), recon_sample='%d of %d iterations timed, scaled' % (n_it, N_INVERSE_STEPS),
                        render_ms=round(ms_r / nv * N_VIEWS, 1), render_sample='%d of %d views timed, scaled' % (nv, N_VIEWS),
                        field_note='hash grid = plain-PyTorch gathers (tiny-cuda-nn not installable offline): slower than the reference\'s tcnn')
+            # Variant B: the reference's execution plan (its Python loops, its ray-marching kernels, torch Adam, eager objective) with a
+            # FAST field standing in for tiny-cuda-nn -- this repo's fused hash-grid + MLP kernel called per point_decode.  It is at
+            # least as fast as tcnn's hash grid + two torch Linears, so this baseline is favourable to the reference: the ratio below
+            # isolates what the fused / sync-free execution plan buys, not the field kernel.
+            from mvedit_b200.ingp_decoder import iNGPDecoder
+
+            class FastFieldDecoder(no.OracleDecoder):
+                def point_decode(self, xyzs, dirs, code, density_only=False):
+                    return self.fast.point_decode(xyzs, dirs, code, density_only=density_only)
+
+            dec_b = FastFieldDecoder(ops, max_steps=1024, weight_culling_th=0.001).to(device)
+            fast = iNGPDecoder(max_resolution=320, n_levels=12, max_steps=1024, weight_culling_th=0.001).to(device)
+            fast.load_state_dict(pipe.nerf.decoder.state_dict(), strict=False)
+            object.__setattr__(dec_b, 'fast', fast)
+            nerf_b = no.OracleNeRF(dec_b, grid_size=GRID, patch_size=128)
+            grid_b, bits_b = state['grid'].clone(), state['bits'].clone()
+            opt_b = torch.optim.Adam(fast.parameters(), lr=0.01)
+            run_b = lambda k: no.nerf_optim(nerf_b, tgt_img[None], tgt_msk[None], None, opt_b, 0.01, k, N_INVERSE_RAYS, 0.0, 0.0, 0.02, 0.1, 0.01, None,
+                                            grid_b, bits_b, IMG, K, IMG, poses, cam_w, lights, 128, False, 0.015, 0.2, 1.0, False)
+            with torch.no_grad():
+                run_b(4)
+                ms_it_b, _ = timed(lambda: run_b(N_INVERSE_STEPS), warm=0)
+                ms_r_b, _ = timed(lambda: no.render_views(nerf_b, bits_b, poses, K, IMG, IMG, lights, 0.2, 0.25, render_bs=6), warm=0)
+            out['fast_field_variant'] = dict(
+                note='reference plan + reference ray-marching kernels + this repo\'s fused field kernel as a (favourable) stand-in for tcnn; '
+                     'full 96 iterations and 32 views timed',
+                recon_ms=round(ms_it_b, 1), render_ms=round(ms_r_b, 1),
+                step_ms=round(out['denoise_p1_ms'] + out['denoise_p2_ms'] + out['vae_decode_ms'] + ms_it_b + ms_r_b, 1))
         tot = sum(out.get(k, 0.0) for k in ('denoise_p1_ms', 'denoise_p2_ms', 'vae_decode_ms', 'recon_ms', 'render_ms'))
         out['step_ms'] = round(tot, 1)
         out['steps_per_s'] = round(1e3 / tot, 4) if tot else None
@@ -597,6 +644,10 @@ def gpu_baseline(device, pipe, state, poses, K, cam_w, lights, tgt_img, tgt_msk,
             denoise_plus_decode=ratio(sum(out.get(k, 0) for k in ('denoise_p1_ms', 'denoise_p2_ms', 'vae_decode_ms')),
                                       sum(ours.get(k, 0) for k in ('denoise_p1', 'decode', 'denoise_p2+solver'))),
             step=ratio(tot, sum(ours.values())))
+        if 'fast_field_variant' in out:
+            fv = out['fast_field_variant']
+            out['speedup_vs_gpu_baseline_fast_field'] = dict(recon=ratio(fv['recon_ms'], ours.get('nerf_optim')), render=ratio(fv['render_ms'], ours.get('render_views')),
+                                                             step=ratio(fv['step_ms'], sum(ours.values())))
     except Exception as e:             # a reported baseline must never take the bench line down
         out['error'] = repr(e)[:300]
     torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32_prev

@@ -182,6 +182,11 @@ int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses
                     float blob_density, float blob_radius, float sigmoid_saturation,
                     float* weights_sum, float* depth, float* image, void* stream);
 
+/* Diagnostic: the L2 gather ceiling the fused renderer is measured against.  blocks x 256 threads each issue per_thread (multiple of 8)
+ * random 8-byte gathers from table [n_entries,2] f32 (in-register LCG indices, 8 loads in flight) and write one float to out
+ * [blocks*256].  bench.py times it with CUDA events: gathers / s = blocks * 256 * per_thread / t. */
+int mve_gather_ceiling(const float* table, uint32_t n_entries, uint32_t blocks, uint32_t per_thread, float* out, void* stream);
+
 /* Statistics of the most recent mve_render_rays launch into host_out[4]: samples shaded, warp-rounds that shaded, warp-rounds total,
  * warp-level trips of the occupancy-grid search loop (host-synchronous; diagnostics / bench only). */
 int mve_render_last_sample_count(uint64_t* host_out);

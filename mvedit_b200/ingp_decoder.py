@@ -212,11 +212,9 @@ class iNGPDecoder(nn.Module):
     def check_sample_overflow(self, sync=False):
         """Raises if an earlier training forward produced more samples than ``sample_capacity`` (rays were dropped: the reference
         never drops samples).  Cheap: waits only on the event of the async copy issued by ``note_sample_overflow``.
-        Returns the largest post-cull sample count seen."""
+        Returns the largest post-cull sample count of the most recent nerf_optim call."""
         if self._ov is None or self._ov_event is None:
             return 0
-        if sync:
-            self.note_sample_overflow()
         self._ov_event.synchronize()
         m = int(self._ov_host[0])
         cap = getattr(self, '_ov_cap', 0)
