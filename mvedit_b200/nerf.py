@@ -12,6 +12,7 @@ Configurations of the objective that the fused kernels do not cover (target norm
 SURVEY.md §8f-2) raise ``NotImplementedError``: there is no eager fallback path.
 """
 import collections
+import os
 
 import torch
 import torch.nn as nn
@@ -225,6 +226,8 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
         dec.sample_capacity = n_sel * ps * ps * (int(dec.max_steps) if is_init else min(256, int(dec.max_steps)))
     use_graph = bool(getattr(nerf, 'use_cuda_graph', False)) and bool(optimizer.defaults.get('capturable', False)) and not debug
     rank, world = view_shard.world() if getattr(nerf, 'data_parallel', False) else (0, 1)
+    if world > 1 and os.environ.get('MVE_DP_GRAPH', '1') == '0':
+        use_graph = False                             # escape hatch: eager iterations around the collectives
     assert ps % world == 0, 'data-parallel reconstruction: the patch rows must divide by the world size'
 
     # ---- per-configuration "program": static input slots + the iteration closure (+ its captured CUDA graph).  It persists on the
@@ -356,7 +359,9 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
                     vals = iteration()
                 torch.cuda.current_stream().wait_stream(side)
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                # data-parallel: the captured iteration contains NCCL collectives; the process group's watchdog thread polls CUDA
+                # events concurrently, which the default ("global") capture mode turns into a capture error -> thread_local
+                with torch.cuda.graph(graph, capture_error_mode='thread_local' if world > 1 else 'global'):
                     vals_static = iteration()
                 prog['graph'], prog['vals'] = graph, vals_static
             else:
