@@ -341,8 +341,8 @@ def run_ours(args):
         extra['cpu_baseline'] = cpu_baseline()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
     if rank != 0:
+        _teardown(pipe, world)
         return
     steps_per_s = args.steps / (ms * 1e-3)
     e2e_steps_per_s = args.steps / (ms_e2e * 1e-3)
@@ -380,6 +380,20 @@ def run_ours(args):
     )
     line.update(extra)
     emit_json(line)
+    _teardown(pipe, world)
+
+
+def _teardown(pipe, world):
+    """Captured CUDA graphs hold NCCL collectives of the process group: release them before the communicator goes away, and leave
+    with os._exit so that a communicator teardown that blocks on a peer cannot hold the (already printed) result hostage."""
+    if world <= 1:
+        return
+    import gc
+    pipe.nerf.__dict__.get('_recon_programs', {}).clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(0)
 
 
 # --------------------------------------------------------------------------------------------------------- config-5 microbench (HBM)

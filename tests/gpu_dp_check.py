@@ -66,8 +66,13 @@ def main():
         print('DP_CHECK %s graph=%s replicas_identical=%s bitfields_identical=%s alpha_err=%.4f rgb_err=%.4f wall=%.2fs max_kept=%d' % (
             'ok' if ok else 'FAILED', graph, same, same_bits, a_err, c_err, dt, nerf.decoder.check_sample_overflow()), flush=True)
     dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    # captured graphs hold NCCL collectives of this process group: drop them before the communicator, and do not block on its teardown
+    import gc
+    nerf.__dict__.get('_recon_programs', {}).clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)
 
 
 if __name__ == '__main__':
