@@ -312,8 +312,8 @@ class iNGPDecoder(nn.Module):
             dt_gamma = float(dt_gamma[0])
         ro, rd = rays_o[0], rays_d[0]
         bitfield = density_bitfield[0]
-        if noises is None and self.training and self.test_noise is not None:
-            noises = self.test_noise.get('march')
+        if self.training and self.test_noise is not None and self.test_noise.get('march') is not None:
+            noises = self.test_noise['march']               # parity tests: supplied draws win over the caller's
         if self.training and self.sample_capacity:
             # B200-native protocol: fixed-capacity sample buffers + device-side counts -> no host sync anywhere in the iteration
             # (the reference syncs three times here: raymarching.py:290, base_volume_renderer.py:235-241), CUDA-graph capturable.

@@ -291,8 +291,13 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
              c_f32(render_size / intrinsics_size), ptr(prog['img']), ptr(prog['msk']), ptr(prog['camw']), ptr(prog['lights']),
              c_f32(float(dt_gamma_scale)), c_u32(row_lo), c_u32(row_hi), ptr(b['rays_o']), ptr(b['rays_d']), ptr(b['pdirs']), ptr(b['trgb']),
              ptr(b['tmsk']), ptr(b['pw']), ptr(b['pl']), ptr(b['dtg']), stream())
-        # 2. march -> cull -> field -> composite of the strip (autograd graph: composite <- field <- parameters)
-        out = dec(b['rays_o'], b['rays_d'], nerf_code, density_bitfield, nerf.grid_size, dt_gamma=b['dtg'], perturb=True,
+        # 2. march -> cull -> field -> composite of the strip (autograd graph: composite <- field <- parameters).  The perturbation
+        # noise is drawn for ALL rays of the iteration on every rank (the draw the reference makes, raymarching.py:279-282) and sliced,
+        # so the random stream -- and with it the training trajectory -- does not depend on the number of ranks
+        noise = torch.rand(n, device=device)
+        if world > 1:
+            noise = noise.view(P, ps, ps)[:, row_lo:row_hi].reshape(-1)
+        out = dec(b['rays_o'], b['rays_d'], nerf_code, density_bitfield, nerf.grid_size, dt_gamma=b['dtg'], perturb=True, noises=noise,
                   fused_entropy=(sc['entropy'], 1.0 / n))
         image, alpha, depth = out['image'][0], out['weights_sum'][0], out['depth'][0]
         if world > 1:        # 3. exchange the per-ray outputs (5 floats per ray): every rank sees the full patches
