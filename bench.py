@@ -258,8 +258,9 @@ def run_ours(args):
                 one_step(False)
                 torch.cuda.synchronize()
         os.makedirs('gpurun_out', exist_ok=True)
-        with open('gpurun_out/torch_profile.txt', 'w') as f:
+        with open('gpurun_out/torch_profile_w%d_r%d.txt' % (world, rank), 'w') as f:
             f.write(prof_t.key_averages().table(sort_by='cuda_time_total', row_limit=70, max_name_column_width=90))
+        _teardown(pipe, world)
         return
     if args.profile_step:
         with torch.no_grad():

@@ -283,6 +283,33 @@ int mve_adam_step(uint32_t n_tensors, void* const* params, void* const* grads, v
                   const uint32_t* numel, const float* const* lr, float beta1, float beta2, float eps, float grad_scale,
                   int32_t* step, int zero_grad, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * a-12: 3D Gaussian-splatting rasteriser -- tile binning + alpha blending.  The reference snapshot does not
+ * contain its 3DGS code (README.md:121 names ashawkey/diff-gaussian-rasterization as the upstream): these follow that public
+ * algorithm (restated in oracle/gs_oracle.py).  Per-Gaussian inputs come from the projection step (mvedit_b200.gs_renderer):
+ * xy [P,2] projected means in pixel-index coordinates, conic_opacity [P,4] = (A, B, C of the inverse 2-D covariance, opacity),
+ * feat [P,4] = (r, g, b, camera depth), rect [P,4] i32 = tile rect (x0, y0, x1, y1) of the 3-sigma radius (empty = culled).
+ * ------------------------------------------------------------------------- */
+
+/* One (tile << 32 | depth bits, gaussian id) pair per touched 16x16 tile.  offsets [P] = inclusive prefix sum of the tile counts
+ * (int64); keys / vals have offsets[P-1] entries.  grid_x = tiles per image row. */
+int mve_gs_duplicate_keys(const int32_t* rect, const float* depth, const int64_t* offsets, uint32_t P, uint32_t grid_x,
+                          int64_t* keys, int32_t* vals, void* stream);
+/* ranges [n_tiles,2] (zeroed by the caller) <- [start, end) of every tile in the SORTED key list. */
+int mve_gs_tile_ranges(const int64_t* keys_sorted, uint32_t L, int32_t* ranges, void* stream);
+/* Front-to-back blending, one 256-thread CTA per tile: alpha = min(0.99, o exp(-0.5 d^T conic d)), alpha < 1/255 skipped, stop before
+ * T < 1e-4.  bg_host3: HOST array of 3 floats.  Outputs: out_color [H,W,3] (background composited with the final T), out_depth [H,W]
+ * (sum alpha T depth), out_alpha [H,W] = 1 - T, final_T [H,W], n_contrib [H,W] (index of the last contributor, for the backward). */
+int mve_gs_blend_forward(const int32_t* ranges, const int32_t* point_list, const float* xy, const float* conic_opacity, const float* feat,
+                         const float* bg_host3, uint32_t W, uint32_t H, float* out_color, float* out_depth, float* out_alpha,
+                         float* final_T, int32_t* n_contrib, void* stream);
+/* Backward of the blend w.r.t. xy, conic_opacity, feat (ACCUMULATED with warp-reduced atomics into zeroed buffers).
+ * g_depth / g_alpha may be NULL. */
+int mve_gs_blend_backward(const int32_t* ranges, const int32_t* point_list, const float* xy, const float* conic_opacity, const float* feat,
+                          const float* bg_host3, uint32_t W, uint32_t H, const float* final_T, const int32_t* n_contrib,
+                          const float* g_color, const float* g_depth, const float* g_alpha,
+                          float* d_xy, float* d_conic_opacity, float* d_feat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
