@@ -246,6 +246,13 @@ def run_ours(args):
                    IMG, K, IMG, poses, cam_w, lights, 128, True, 0.015, 0.2, 1.0, init_shaded=False)
         torch.cuda.synchronize()
         init_s = time.time() - t_init0
+        # The timed step is a MID-schedule one (step_i = 8 of 24): by then the reference has run 8 further reconstruction calls of 96
+        # iterations on the field (mvedit_3d_pipeline.py:1296-1305).  Do those too, so that the snapshot is the field a mid-schedule
+        # step actually meets (a field fresh out of the 640-iteration init is foggier and its sample counts vary far more run to run).
+        for _ in range(step_i):
+            nerf_optim(pipe.nerf, tgt_img[None], tgt_msk[None], None, opt, 0.01, N_INVERSE_STEPS, N_INVERSE_RAYS, 0.0, 0.0, 0.02, 0.1, 0.01, None, grid,
+                       bitfield, IMG, K, IMG, poses, cam_w, lights, 128, False, 0.015, 0.2, 1.0, init_shaded=False)
+        torch.cuda.synchronize()
     snapshot()
     if args.torch_profile:
         # CUPTI kernel table of ONE warm step (graph mode as configured): where the time outside this library's kernels goes
@@ -337,6 +344,10 @@ def run_ours(args):
     if world == 1:
         extra['render_roofline'] = render_gather_roofline(device, pipe, rs[0], render_ms_same_pass)
         extra['field_precision'] = tf32_vs_fp32_render(pipe, bitfield, poses, K)
+        try:
+            extra['gs_raster'] = gs_microbench(device, pk)
+        except Exception as e:
+            extra['gs_raster'] = dict(error=repr(e)[:300])
         extra['gpu_baseline'] = gpu_baseline(device, pipe, dict(grid=snap['grid'], bits=snap['bits']), poses, K, cam_w, lights, tgt_img, tgt_msk, phases,
                                              skip=args.no_gpu_baseline)
         extra['cpu_baseline'] = cpu_baseline()
@@ -364,6 +375,7 @@ def run_ours(args):
                                 ('ray-data-parallel reconstruction (1 all_gather of per-ray outputs + 1 all_reduce of the 28.7 MB gradient per iteration)'
                                  if pipe.nerf.data_parallel else 'reconstruction on one replica set (+ 1 flat broadcast)' if world > 1 else 'single GPU'),
                     in_step='denoise P1, vae.decode (real, on pred_x0), gather, nerf_optim x96, render, denoise P2, solver',
+                    field_state='640-iteration init + 8 x 96 iterations (the reconstruction calls of the 8 steps before the timed mid-schedule step)',
                     not_in_step='TRACER masks, LPIPS patch loss, SRVGG enhancer (SURVEY.md §8f-2: not built). The reconstruction fits analytic '
                                 'targets + silhouettes because a random-init VAE decodes noise; the decoded tensor is reduced and read back in e2e',
                     l2='per-step working set (168 MB per UNet activation tensor, 2.1 GB per VAE activation, >5 GB live) >> 126 MB L2'),
@@ -544,6 +556,63 @@ def tf32_vs_fp32_render(pipe, bitfield, poses, K):
     mse = float((outs[0] - outs[1]).square().mean())
     return dict(views='4 x 128^2 camera rays of the bench state through march -> field -> composite', rgba_psnr_db=round(10 * math.log10(1.0 / max(mse, 1e-20)), 1),
                 max_abs=round(float((outs[0] - outs[1]).abs().max()), 5), mean_abs=float('%.3g' % float((outs[0] - outs[1]).abs().mean())))
+
+
+def gs_microbench(device, pk):
+    """BASELINE configs[2], rasteriser side (per GPU): 2^18 Gaussians ~N(0, 0.3^2), scales logU(-5,-3), random rotations, opacity
+    sigmoid(N(0,1)), SH degree 0; 4 views x 512^2.  Reported: ms per view of projection (torch), binning (key duplication
+    + device sort + ranges), blend forward, blend backward, tile instances, and algorithmic HBM GB/s of the blend kernels
+    (48 B staged per tile instance + 24 B per pixel out; backward + 28 B per pixel in and 40 B per Gaussian out)."""
+    from tests import synth
+    from mvedit_b200.gs_renderer import GaussianRasterizer, GaussianRasterizationSettings
+    P, HW, V = 1 << 18, IMG, 4
+    g = torch.Generator(device=device).manual_seed(0)
+    means = (torch.randn(P, 3, device=device, generator=g) * 0.3).requires_grad_(True)
+    scales = torch.exp(torch.rand(P, 3, device=device, generator=g) * 2 - 5).requires_grad_(True)
+    quats = torch.randn(P, 4, device=device, generator=g).requires_grad_(True)
+    opac = torch.sigmoid(torch.randn(P, device=device, generator=g)).requires_grad_(True)
+    cols = torch.rand(P, 3, device=device, generator=g).requires_grad_(True)
+    poses = torch.from_numpy(synth.surround_poses(V, seed=0)).to(device)
+    f = 0.5 * HW / math.tan(math.radians(15))
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    from mvedit_b200 import _lib
+    res = dict(fwd=[], bwd=[], blend_fwd=[], blend_bwd=[], inst=[])
+    for rep in range(2):
+        for v in range(V):
+            rast = GaussianRasterizer(GaussianRasterizationSettings(image_height=HW, image_width=HW, viewmatrix=torch.linalg.inv(poses[v]),
+                                                                    intrinsics=(f, f, HW / 2, HW / 2), bg=(1.0, 1.0, 1.0)))
+            prof = []
+            _lib.PROFILE[0] = prof
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record()
+            color, depth, alpha = rast(means, opac, cols, scales, quats)
+            e1.record()
+            (color.sum() + depth.sum() + alpha.sum()).backward()
+            e2.record()
+            torch.cuda.synchronize()
+            _lib.PROFILE[0] = None
+            if rep:
+                res['fwd'].append(e0.elapsed_time(e1)); res['bwd'].append(e1.elapsed_time(e2))
+                for name, a, b, meta in prof:
+                    if name == 'mve_gs_blend_forward': res['blend_fwd'].append(a.elapsed_time(b))
+                    if name == 'mve_gs_blend_backward': res['blend_bwd'].append(a.elapsed_time(b))
+                from mvedit_b200.gs_renderer import _BlendFn
+                res['inst'].append(int(getattr(_BlendFn, 'last_instances', 0)))
+            for t_ in (means, scales, quats, opac, cols):
+                t_.grad = None
+    m = lambda k: float(np.mean(res[k])) if res[k] else None
+    L = m('inst') or 0
+    out = dict(workload='BASELINE configs[2] rasteriser side: 2^18 Gaussians, %d views x %d^2, SH degree 0' % (V, HW), gaussians=P,
+               tile_instances_per_view=int(L), fwd_ms_per_view=round(m('fwd'), 3), bwd_ms_per_view=round(m('bwd'), 3),
+               blend_fwd_ms=round(m('blend_fwd'), 3), blend_bwd_ms=round(m('blend_bwd'), 3))
+    if L:
+        bf = L * 48 + HW * HW * 24
+        bb = L * 48 + HW * HW * 28 + P * 40
+        out.update(blend_fwd_gbs=round(bf / m('blend_fwd') / 1e6, 1), blend_bwd_gbs=round(bb / m('blend_bwd') / 1e6, 1),
+                   blend_fwd_frac_hbm=round(bf / m('blend_fwd') / 1e6 / pk['hbm_gbs'], 3), blend_bwd_frac_hbm=round(bb / m('blend_bwd') / 1e6 / pk['hbm_gbs'], 3),
+                   note='the blend loop itself is shared-memory / FMA bound (every pixel visits every Gaussian of its tile): HBM is the roof of the '
+                        'staging traffic only; views/s per GPU = %.1f fwd+bwd' % (1e3 / (m('fwd') + m('bwd'))))
+    return out
 
 
 # --------------------------------------------------------------------------------------------------------- GPU reference leg

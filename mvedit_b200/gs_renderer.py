@@ -98,6 +98,7 @@ class _BlendFn(torch.autograd.Function):
              ptr(alpha), ptr(final_T), ptr(n_contrib), stream())
         ctx.save_for_backward(ranges, point_list, xy_c, co, ft, final_T, n_contrib)
         ctx.bg, ctx.hw, ctx.n_instances = bg_h, (H, W), L
+        _BlendFn.last_instances = L
         return color, odepth, alpha
 
     @staticmethod

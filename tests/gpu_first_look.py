@@ -66,13 +66,22 @@ def main():
         tg = timeit(lambda: tc_ops.gemm(a, w, out=out))
         tt = timeit(lambda: torch.matmul(a, w.t(), out=out))
         print('gemm', Mm, Nn, Kk, 'ours ms', tg, 'TF/s', 2 * Mm * Nn * Kk / tg / 1e9, '| cublas ms', tt, 'TF/s', 2 * Mm * Nn * Kk / tt / 1e9)
-    for (B, Hh, C, Co) in [(64, 64, 320, 320), (64, 32, 640, 640), (64, 16, 1280, 1280)]:
+    for (B, Hh, C, Co) in [(64, 64, 320, 320), (64, 32, 640, 640), (64, 16, 1280, 1280), (8, 512, 128, 128), (8, 256, 256, 256), (16, 128, 512, 512)]:
         xx = torch.randn(B, Hh, Hh, C, device='cuda').bfloat16(); ww = torch.randn(Co, 3, 3, C, device='cuda').bfloat16()
         tg = timeit(lambda: tc_ops.conv3x3(xx, ww))
         xn = xx.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last); wn = ww.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
         tt = timeit(lambda: torch.nn.functional.conv2d(xn, wn, padding=1))
         fl = 2 * B * Hh * Hh * C * Co * 9
         print('conv3x3', B, Hh, C, Co, 'ours ms', tg, 'TF/s', fl / tg / 1e9, '| cudnn ms', tt, 'TF/s', fl / tt / 1e9)
+    # attention vs flash SDPA (torch picks the flash / cuDNN backend for bf16)
+    for (B, heads, S, d) in [(16, 8, 4096, 40), (16, 8, 1024, 80), (16, 8, 256, 160)]:
+        qkv = torch.randn(B, S, 3 * heads * d, device='cuda').bfloat16()
+        C = heads * d
+        tg = timeit(lambda: tc_ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads))
+        q, k, v = (qkv[:, :, i * C:(i + 1) * C].reshape(B, S, heads, d).transpose(1, 2) for i in range(3))
+        tt = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
+        fl = 4 * B * heads * S * S * d
+        print('attention', B, heads, S, d, 'ours ms', tg, 'TF/s', fl / tg / 1e9, '| torch SDPA ms', tt, 'TF/s', fl / tt / 1e9)
 
 
 if __name__ == '__main__':
