@@ -9,6 +9,13 @@
 //
 //   C[M,N] = epi( A[M,K] . B[N,K]^T )       A, B bf16 K-major (row-major with K contiguous), C bf16 row-major.
 //
+// MT = 2 ("tall" tiles): one CTA owns a 256 x BN output tile as TWO 128-row MMAs per K step that share the B stage in shared memory
+// (A stage = 32 KB, accumulators at TMEM columns [0,BN) and [BN,2BN)).  A 128 x BN tile needs 2*128*BN / (2*(128+BN)) FLOP per byte of
+// operands staged through shared memory -- 64 (BN=128) ... 71 (BN=160) -- and the ~100 B/clk an SM can pull from L2 then caps the
+// tensor pipe at 60-70 % (ncu: profiles/r02_ncu_kernels_summary.txt); 256 rows per B tile raise that to 85-98 FLOP/B.
+// ACC = number of accumulator stages in TMEM: 2 overlaps the epilogue of tile i with the main loop of tile i+1 (needs 2*MT*BN <= 512
+// columns); 1 is used for 256 x 160 tiles (320 columns), whose long K loops (3x3 convolutions) hide the un-overlapped epilogue.
+//
 // MODE 1 (conv3x3, stride 1, pad 1, NHWC): A is never materialised.  The producer walks K as 9 taps x (Cin/64) chunks and
 // fetches, for tap (dy,dx), the box {64 ch, BW, BH, BB} of the NHWC activation at (w0+dx-1, h0+dy-1, b0) with a 4-D tensor map;
 // TMA's out-of-bounds zero fill supplies the padding.  The 128 rows of the box are 128 consecutive output pixels.
@@ -16,6 +23,7 @@
 //
 // Replaces, on the reference's path, the cuDNN/cuBLAS calls under diffusers' UNet2DConditionModel / ControlNetModel
 // (SURVEY.md §8 a-1/a-2, Appendix A).
+#include <cstdlib>
 #include "tc_common.cuh"
 #include "../../include/mvedit_b200.h"
 
@@ -42,14 +50,19 @@ struct GemmParams {
     uint32_t H, W, cin_chunks;
 };
 
-template <int BN>
+constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+template <int BN, int MT = 1, int ACC = 2>
 struct Cfg {
     static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
-    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int ACC_STRIDE = (BN > 128) ? 256 : BN;  // column offset of accumulator stage 1
+    static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
+    static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (MT == 1 ? ((BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8)) : STAGES_RAW);
+    // column offset between accumulator stages; the MT sub-tiles of one stage are BN columns apart
+    static constexpr int ACC_STRIDE = (MT == 1) ? ((BN > 128) ? 256 : BN) : MT * BN;
+    static constexpr int TMEM_COLS = pow2_cols(ACC == 1 ? MT * BN : ACC_STRIDE + MT * BN);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(TMEM_COLS <= 512 && (ACC == 1 ? MT * BN : ACC_STRIDE + MT * BN) <= 512, "accumulators do not fit TMEM");
 };
 
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -58,10 +71,11 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     return v;
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int MT = 1, int ACC = 2>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                             const GemmParams p) {
-    using C_ = Cfg<BN>;
+    using C_ = Cfg<BN, MT, ACC>;
+    constexpr int BMT = BM * MT;            // rows of one CTA tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::STAGES * C_::STAGE_BYTES);
@@ -94,7 +108,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
             uint32_t stage = 0, phase = 0;
             for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const uint32_t mt = tile / p.n_tiles, nt = tile % p.n_tiles;
-                const int m0 = mt * BM, n0 = nt * BN;
+                const int m0 = mt * BMT, n0 = nt * BN;
                 int b0 = 0, h0 = 0, w0 = 0;
                 if (MODE == 1) {
                     const uint32_t hw = p.H * p.W;
@@ -106,7 +120,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
                 for (uint32_t kb = 0; kb < p.num_kb; kb++) {
                     tc::mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * C_::STAGE_BYTES;
-                    uint8_t* sb = sa + A_BYTES;
+                    uint8_t* sb = sa + MT * A_BYTES;
                     tc::mbar_arrive_expect_tx(&full[stage], C_::STAGE_BYTES);
                     if (MODE == 0) {
                         tc::tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
@@ -133,35 +147,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
                     tc::mbar_wait(&full[stage], phase);
                     tc::tc_fence_after();
                     const uint32_t sa = tc::smem_u32(smem + stage * C_::STAGE_BYTES);
-                    const uint64_t da = tc::make_desc_k_sw128(sa), db = tc::make_desc_k_sw128(sa + A_BYTES);
+                    const uint64_t da = tc::make_desc_k_sw128(sa), db = tc::make_desc_k_sw128(sa + MT * A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++) {
-                        // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
-                        tc::umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                        // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field;
+                        // the second 128-row sub-tile of A sits A_BYTES further on and accumulates BN columns further on
+#pragma unroll
+                        for (int s = 0; s < MT; s++)
+                            tc::umma_f16(d_tmem + s * BN, da + (uint64_t)(k * 2 + s * (A_BYTES >> 4)), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
                     }
                     tc::umma_commit(&empty[stage]);
                     if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc::umma_commit(&tfull[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
         // ------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;     // 0: even column chunks, 1: odd column chunks
+        const int half = (warp - 2) >> 2;     // MT == 1: 0 = even column chunks, 1 = odd column chunks; MT == 2: the 128-row sub-tile
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const uint32_t mt = tile / p.n_tiles, nt = tile % p.n_tiles;
-            const uint32_t row = mt * BM + q * 32 + lane;
+            const uint32_t row = mt * BMT + (MT == 2 ? half * BM : 0) + q * 32 + lane;
             const uint32_t n0 = nt * BN;
             tc::mbar_wait(&tfull[acc], acc_phase);
             tc::tc_fence_after();
-            const uint32_t t_row = tmem_base + acc * C_::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_row = tmem_base + acc * C_::ACC_STRIDE + (MT == 2 ? half * BN : 0) + ((uint32_t)(q * 32) << 16);
             const bool row_ok = row < p.M;
             const float* rb = (p.row_bias && row_ok) ? p.row_bias + (size_t)(row / p.rows_per_group) * p.ldrb : nullptr;
             constexpr int CH = (BN >= 32) ? 32 : 16;
-            if (BN >= 64 && p.act == 3) {
+            if (MT == 1 && BN >= 64 && p.act == 3) {
                 // GEGLU fused into the feed-forward's first projection (diffusers GEGLU: hidden, gate = proj(x).chunk(2); hidden *
                 // gelu(gate)): the weight rows are pre-ordered so that this tile's first BN/2 columns are values and the last BN/2
                 // the matching gates; only the BN/2 products are written (the [M, 2F] intermediate never exists in HBM).
@@ -193,7 +210,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
                 }
             } else
 #pragma unroll 1
-            for (int c = half * CH; c < BN; c += 2 * CH) {
+            for (int c = (MT == 2 ? 0 : half * CH); c < BN; c += (MT == 2 ? CH : 2 * CH)) {
                 uint32_t v[32];
                 if (CH == 32) {
                     tc::tmem_ld32(t_row + c, v);
@@ -249,7 +266,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tempty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
         }
     }
 
@@ -271,24 +288,42 @@ int pick_bn(uint32_t N) {
     return 16;
 }
 
-template <int BN, int MODE>
+// Tile shape for a problem: (BN, MT, ACC).  Tall (256-row) tiles when M is large and the shape has a tall configuration:
+//   N % 128 == 0 but not % 256 (128, 384, 640 ...) -> 256 x 128, two accumulator stages;
+//   N % 160 == 0 (320, 640 with long K)            -> 256 x 160, one accumulator stage (K >= 1024: the main loop hides the epilogue).
+// MVE_GEMM_TALL=0 in the environment disables them (A/B timing).
+struct TileCfg { int bn, mt, acc; };
+TileCfg pick_tile(uint32_t M, uint32_t N, uint32_t K, int act) {
+    static int tall = -1;
+    if (tall < 0) { const char* e = getenv("MVE_GEMM_TALL"); tall = (e && e[0] == '0') ? 0 : 1; }
+    const int bn = pick_bn(N);
+    if (!tall || act == 3 || M < 148u * 256u) return {bn, 1, 2};
+    if (bn == 128 && N % 128 == 0) return {128, 2, 2};
+    if (bn == 160 && K >= 1024) return {160, 2, 1};
+    return {bn, 1, 2};
+}
+
+template <int BN, int MODE, int MT = 1, int ACC = 2>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-    using C_ = Cfg<BN>;
-    static bool configured = false;
-    if (!configured) {
-        MVE_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
-        configured = true;
+    using C_ = Cfg<BN, MT, ACC>;
+    static bool configured[16] = {};
+    int dev = 0;
+    MVE_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 15]) {
+        MVE_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, MODE, MT, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
+        configured[dev & 15] = true;
     }
     const uint32_t tiles = p.m_tiles * p.n_tiles;
     const uint32_t grid = tiles < (uint32_t)kNumSM ? tiles : (uint32_t)kNumSM;
-    k_gemm_tc<BN, MODE><<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    k_gemm_tc<BN, MODE, MT, ACC><<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, p);
     MVE_CHECK_LAUNCH("k_gemm_tc");
     return 0;
 }
 
 template <int MODE>
-int dispatch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t s) {
-    switch (bn) {
+int dispatch(TileCfg t, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t s) {
+    if (t.mt == 2) return t.bn == 128 ? launch<128, MODE, 2, 2>(tmA, tmB, p, s) : launch<160, MODE, 2, 1>(tmA, tmB, p, s);
+    switch (t.bn) {
         case 256: return launch<256, MODE>(tmA, tmB, p, s);
         case 160: return launch<160, MODE>(tmA, tmB, p, s);
         case 128: return launch<128, MODE>(tmA, tmB, p, s);
@@ -345,11 +380,13 @@ int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N,
     MVE_ARG(!row_bias || rows_per_group > 0, "gemm: rows_per_group must be > 0 with row_bias");
     if (act == 3)
         MVE_ARG(N % 256 == 0 && !row_bias && !residual, "gemm: GEGLU epilogue needs N % 256 == 0 (value/gate interleaved per 256 columns), no row_bias, no residual");
-    const int bn = pick_bn(N);
+    const TileCfg tc_ = pick_tile(M, N, K, act);
+    const int bn = tc_.bn;
+    const uint32_t bm = BM * tc_.mt;
     CUtensorMap tmA, tmB;
     {
         const uint64_t dims[2] = {K, M}, str[1] = {(uint64_t)lda * 2};
-        const uint32_t box[2] = {BK, BM};
+        const uint32_t box[2] = {BK, bm};
         int r = mve_make_tmap_bf16(&tmA, A, 2, dims, str, box, "gemm A");
         if (r) return r;
     }
@@ -361,10 +398,10 @@ int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N,
     }
     GemmParams p{};
     p.C = (__nv_bfloat16*)C; p.M = M; p.N = N; p.ldc = ldc; p.num_kb = K / BK;
-    p.m_tiles = (M + BM - 1) / BM; p.n_tiles = (N + bn - 1) / bn;
+    p.m_tiles = (M + bm - 1) / bm; p.n_tiles = (N + bn - 1) / bn;
     p.bias = bias; p.row_bias = row_bias; p.rows_per_group = rows_per_group; p.ldrb = ldrb ? ldrb : N;
     p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act; p.alpha = alpha;
-    return dispatch<0>(bn, tmA, tmB, p, (cudaStream_t)stream);
+    return dispatch<0>(tc_, tmA, tmB, p, (cudaStream_t)stream);
 }
 
 int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32_t H, uint32_t W, uint32_t Cin, uint32_t Cout,
@@ -373,13 +410,22 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32
     if (Bn == 0) return 0;
     MVE_ARG(Cin % BK == 0, "conv3x3: Cin must be a multiple of 64 (pad channels)");
     MVE_ARG((W <= 128 && 128 % W == 0) || W % 128 == 0, "conv3x3: W must divide 128 or be a multiple of 128");
-    const uint32_t BW = W < 128 ? W : 128;
-    uint32_t BH = 128 / BW;
-    if (BH > H) BH = H;
-    const uint32_t BB = 128 / (BW * BH);
-    MVE_ARG(BW * BH * BB == 128 && (H % BH) == 0 && BB <= 256, "conv3x3: 128-pixel tile must cover whole rows / images");
     const uint32_t M = Bn * H * W;
-    const int bn = pick_bn(Cout);
+    TileCfg tc_ = pick_tile(M, Cout, 9 * Cin, act);
+    // the tile's pixels as a TMA box {64 ch, BW, BH, BB}: whole image rows / whole images (a tall tile falls back if it cannot)
+    uint32_t PIX, BW, BH, BB;
+    for (;;) {
+        PIX = BM * tc_.mt;
+        BW = W < PIX ? W : PIX;
+        BH = PIX / BW;
+        if (BH > H) BH = H;
+        BB = PIX / (BW * BH);
+        const bool ok = BW * BH * BB == PIX && (W % BW) == 0 && (H % BH) == 0 && BB <= 256 && BW <= 256 && BH <= 256;
+        if (ok || tc_.mt == 1) break;
+        tc_ = {pick_bn(Cout), 1, 2};
+    }
+    MVE_ARG(BW * BH * BB == PIX && (H % BH) == 0 && BB <= 256, "conv3x3: the pixel tile must cover whole rows / images");
+    const int bn = tc_.bn;
     CUtensorMap tmA, tmB;
     {
         const uint64_t dims[4] = {Cin, W, H, Bn};
@@ -396,11 +442,11 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32
     }
     GemmParams p{};
     p.C = (__nv_bfloat16*)Y; p.M = M; p.N = Cout; p.ldc = ldy; p.num_kb = 9 * (Cin / BK);
-    p.m_tiles = (M + BM - 1) / BM; p.n_tiles = (Cout + bn - 1) / bn;   // a last partial tile reads zero-filled images (TMA OOB)
+    p.m_tiles = (M + PIX - 1) / PIX; p.n_tiles = (Cout + bn - 1) / bn;   // a last partial tile reads zero-filled images (TMA OOB)
     p.bias = bias; p.row_bias = row_bias; p.rows_per_group = H * W; p.ldrb = ldrb ? ldrb : Cout;
     p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act; p.alpha = alpha;
     p.H = H; p.W = W; p.cin_chunks = Cin / BK;
-    return dispatch<1>(bn, tmA, tmB, p, (cudaStream_t)stream);
+    return dispatch<1>(tc_, tmA, tmB, p, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -152,3 +152,33 @@ def test_layernorm_geglu_upsample_im2col_layout():
     lat = torch.randn(2, 4, 8, 8, device='cuda', generator=g)
     nh = tc_ops.nchw_to_nhwc_pad(lat, 64)
     assert torch.equal(nh[..., :4].float(), lat.bfloat16().float().permute(0, 2, 3, 1)) and nh[..., 4:].abs().sum() == 0
+
+
+@pytest.mark.parametrize('M,N,K', [(40000, 128, 128), (65536, 640, 1280), (41000, 320, 1280), (38000, 384, 64)])
+def test_gemm_tall_tiles(M, N, K):
+    """256-row CTA tiles (two 128-row MMAs per B stage): 256 x 128 with two accumulator stages and 256 x 160 with one; M not a
+    multiple of 256 exercises the TMA zero fill / row guard of the second sub-tile; epilogue operands included."""
+    from mvedit_b200 import tc_ops
+    g = torch.Generator(device='cuda').manual_seed(M + N + K)
+    a = torch.randn(M, K, device='cuda', generator=g).bfloat16()
+    w = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device='cuda', generator=g)
+    res = torch.randn(M, N, device='cuda', generator=g).bfloat16()
+    out = tc_ops.gemm(a, w, bias=bias, residual=res, act='silu')
+    _check(out, torch.nn.functional.silu(a.float() @ w.float().t() + bias) + res.float(), K)
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', [(4, 128, 128, 128, 128), (16, 64, 64, 320, 320), (2, 256, 256, 64, 128), (3, 128, 128, 64, 640),
+                                            (40, 32, 32, 128, 320)])
+def test_conv3x3_tall_tiles(B, H, W, Cin, Cout):
+    from mvedit_b200 import tc_ops
+    g = torch.Generator(device='cuda').manual_seed(B + H + Cin + Cout)
+    x = torch.randn(B, H, W, Cin, device='cuda', generator=g).bfloat16()
+    w = (torch.randn(Cout, 3, 3, Cin, device='cuda', generator=g) / math.sqrt(9 * Cin)).bfloat16()
+    bias = torch.randn(Cout, device='cuda', generator=g)
+    rb = torch.randn(B, Cout, device='cuda', generator=g)
+    res = torch.randn(B, H, W, Cout, device='cuda', generator=g).bfloat16()
+    out = tc_ops.conv3x3(x, w, bias=bias, row_bias=rb, residual=res)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1)
+    ref = (ref + rb[:, :, None, None]).permute(0, 2, 3, 1) + res.float()
+    _check(out, ref, 9 * Cin)
