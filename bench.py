@@ -328,6 +328,13 @@ def run_ours(args):
     for name, a, b, meta in prof:
         c = cat.setdefault(name, dict(ms=0.0, n=0, flops=0.0))
         c['ms'] += a.elapsed_time(b); c['n'] += 1; c['flops'] += (meta or {}).get('flops', 0.0)
+    by_shape = {}
+    for name, a, b, meta in prof:
+        if meta and meta.get('shape'):
+            c = by_shape.setdefault(meta['shape'], dict(ms=0.0, n=0, flops=0.0))
+            c['ms'] += a.elapsed_time(b); c['n'] += 1; c['flops'] += meta.get('flops', 0.0)
+    top_shapes = {k: dict(ms=round(v['ms'], 2), launches=v['n'], tflops=round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1))
+                  for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1]['ms'])[:24]}
     pk = peaks()
     tc_ms = cat.get('mve_gemm_bf16', dict(ms=0))['ms'] + cat.get('mve_conv3x3_bf16', dict(ms=0))['ms']
     tc_fl = cat.get('mve_gemm_bf16', dict(flops=0))['flops'] + cat.get('mve_conv3x3_bf16', dict(flops=0))['flops']
@@ -389,7 +396,7 @@ def run_ours(args):
                       denoise_decode_phase_tflops=round(all_tc_fl / (denoise_ms * 1e-3) / 1e12, 1) if denoise_ms else None,
                       denoise_decode_phase_frac=round(all_tc_fl / (denoise_ms * 1e-3) / 1e12 / pk['tf_sustained'], 4) if denoise_ms else None),
         phase_ms=phases, init_recon_640_iters_s=round(init_s, 2), work=work,
-        kernel_breakdown_ms=breakdown, per_call_ms=tails, raster_hbm=raster,
+        kernel_breakdown_ms=breakdown, tensor_core_shapes_ms=top_shapes, per_call_ms=tails, raster_hbm=raster,
     )
     line.update(extra)
     emit_json(line)

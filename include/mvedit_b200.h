@@ -171,7 +171,8 @@ int mve_field_backward(const float* xyz, uint32_t M, const int32_t* M_dev, const
 /* Whole inference branch of VolumeRenderer.forward (lib/models/decoders/base_volume_renderer.py:264-329) + BaseNeRF.render's ray
  * generation (lib/models/autoencoders/base_nerf.py:489-556; lib/core/utils/geometry_utils.py:18-55) in one launch.
  * Rays: either rays_o/rays_d [N,3], or cameras (poses [V,4,4] c2w, intrinsics [V,4]=fx,fy,cx,cy at the render size, h, w; N = V*h*w,
- * optional dt_gamma_per_view [V]).  perturb=False semantics.  Outputs weights_sum [N], depth [N] (sum w/t), image [N,3]. */
+ * optional dt_gamma_per_view [V]).  perturb=False semantics.  Outputs weights_sum [N], depth [N] (sum w/t), image [N,3].
+ * One launch at a time per device (the work counter / statistics block is per device, zeroed stream-ordered by the launch). */
 int mve_render_rays(const float* rays_o, const float* rays_d, const float* poses, const float* intrinsics,
                     const float* dt_gamma_per_view, uint32_t h, uint32_t w, uint32_t N,
                     const float* aabb, float min_near, const uint8_t* density_bitfield, float bound, float dt_gamma,

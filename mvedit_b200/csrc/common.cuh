@@ -37,7 +37,16 @@ void mve_set_error(const char* fmt, ...);
 
 static inline unsigned int cdiv(unsigned long long a, unsigned int b) { return (unsigned int)((a + b - 1) / b); }
 
-constexpr int kNumSM = 148;  // B200
+// SM count of the current device, queried once per device (148 on a B200; grids are sized from it, nothing is hard-wired)
+static inline int mve_num_sms() {
+    static int cached[16] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int& c = cached[dev & 15];
+    if (c == 0 && (cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || c <= 0)) c = 148;
+    return c;
+}
+#define kNumSM (mve_num_sms())
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

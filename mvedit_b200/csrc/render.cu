@@ -295,7 +295,11 @@ __global__ void k_packbits_dev(const __half* __restrict__ grid, const uint32_t N
     bitfield[n] = (uint8_t)bits;
 }
 
-static unsigned char* g_render_scratch = nullptr;
+// work counter + statistics of the fused renderer: one 48-byte buffer PER DEVICE (a launch zeroes it stream-ordered; concurrent
+// mve_render_rays calls on two streams of the same device are not supported and documented so in the header)
+static unsigned char* g_render_scratch_dev[16] = {};
+#define g_render_scratch (g_render_scratch_dev[render_dev_index()])
+static inline int render_dev_index() { int d = 0; cudaGetDevice(&d); return d & 15; }
 
 }  // namespace
 

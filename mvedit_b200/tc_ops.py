@@ -30,7 +30,7 @@ def gemm(a, w, bias=None, row_bias=None, rows_per_group=0, residual=None, act=No
          c_u32(out.stride(0)), ptr(bias), raw_ptr(row_bias), c_u32(rows_per_group),
          c_u32(row_bias.stride(0) if row_bias is not None else 0), raw_ptr(residual),
          c_u32(residual.stride(0) if residual is not None else 0), c_int(ACT[act]), c_f32(alpha), stream(),
-         _meta=dict(flops=2.0 * M * N * K))
+         _meta=dict(flops=2.0 * M * N * K, shape='gemm M%d N%d K%d%s' % (M, N, K, ' geglu' if act == 'geglu' else '')))
     return out
 
 
@@ -57,7 +57,7 @@ def conv3x3(x, w, bias=None, row_bias=None, residual=None, act=None, alpha=1.0, 
     call('mve_conv3x3_bf16', ptr(x), ptr(w), ptr(out), c_u32(B), c_u32(H), c_u32(W), c_u32(Cin), c_u32(Cout), c_u32(out.stride(2)),
          ptr(bias), raw_ptr(row_bias), c_u32(row_bias.stride(0) if row_bias is not None else 0), ptr(residual),
          c_u32(residual.stride(2) if residual is not None else 0), c_int(ACT[act]),
-         c_f32(alpha), stream(), _meta=dict(flops=2.0 * B * H * W * Cout * 9 * Cin))
+         c_f32(alpha), stream(), _meta=dict(flops=2.0 * B * H * W * Cout * 9 * Cin, shape='conv B%d %dx%d Cin%d Cout%d' % (B, H, W, Cin, Cout)))
     return out
 
 
@@ -72,7 +72,7 @@ def attention(q, k, v, heads, scale=None, out=None):
         out = torch.empty(B, Sq, C, dtype=torch.bfloat16, device=q.device)
     call('mve_attention_bf16', raw_ptr(q), raw_ptr(k), raw_ptr(v), ptr(out), c_u32(B), c_u32(heads), c_u32(Sq), c_u32(Skv), c_u32(d),
          c_u32(q.stride(1)), c_u32(k.stride(1)), c_u32(v.stride(1)), c_u32(out.stride(1)), c_f32(scale if scale is not None else d ** -0.5),
-         stream(), _meta=dict(flops=4.0 * B * heads * Sq * Skv * d))
+         stream(), _meta=dict(flops=4.0 * B * heads * Sq * Skv * d, shape='attn B%d h%d Sq%d Skv%d d%d' % (B, heads, Sq, Skv, d)))
     return out
 
 
