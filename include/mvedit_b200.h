@@ -164,6 +164,15 @@ int mve_field_backward(const float* xyz, uint32_t M, const int32_t* M_dev, const
                        float* grad_table, float* grad_w1, float* grad_b1, float* grad_w2, float* grad_b2,
                        int accumulate_mlp, int mlp_tf32, float* workspace, float* grad_xyz, void* stream);
 
+/* The bare hash-grid encoding as a differentiable op: `tcnn.Encoding(n_input_dims=3, HashGrid ...)(x)` (seam B4; ingp_decoder.py:62-74,112,
+ * triplane_ingp_decoder.py:102-114,150).  x01 [M,3] in [0,1]; out [M, 2*n_levels] (feature 2l+f).  The backward ACCUMULATES into
+ * grad_table [n_entries,2] (atomics; may be NULL) and into grad_x [M,3] (zeroed by the caller; may be NULL). */
+int mve_hashgrid_forward(const float* x01, uint32_t M, const float* table, uint32_t n_levels, const float* level_scale,
+                         const uint32_t* level_res, const uint32_t* level_size, const uint32_t* level_offset, float* out, void* stream);
+int mve_hashgrid_backward(const float* x01, uint32_t M, const float* table, uint32_t n_levels, const float* level_scale,
+                          const uint32_t* level_res, const uint32_t* level_size, const uint32_t* level_offset,
+                          const float* grad_out, float* grad_table, float* grad_x, void* stream);
+
 /* ---------------------------------------------------------------------------
  * a-6 / a-9: fused NeRF-adapter kernels (no reference native counterpart: they replace Python loops)
  * ------------------------------------------------------------------------- */
@@ -276,7 +285,7 @@ int mve_patch_rays(const int64_t* patch_inds, uint32_t P, uint32_t V, uint32_t r
                    float* rays_o, float* rays_d, float* dirs, float* tgt_rgb, float* tgt_mask,
                    float* patch_w, float* patch_lights, float* dt_gamma, void* stream);
 
-/* torch.optim.Adam.step (defaults: no weight decay, no amsgrad) + optimizer.zero_grad for up to 8 tensors in one launch
+/* torch.optim.Adam.step (defaults: no weight decay, no amsgrad) + optimizer.zero_grad for up to 16 tensors in one launch
  * (mvedit_3d_pipeline.py:631-633): params / grads / exp_avg / exp_avg_sq / lr are HOST arrays of n_tensors DEVICE pointers
  * (lr[i] points at a device float: schedulable inside a captured graph), numel a host array.  *step (device int32) is incremented
  * first and used for the bias corrections.  grads are scaled by grad_scale before use and zeroed afterwards when zero_grad != 0. */

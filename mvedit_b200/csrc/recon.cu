@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) k_patch_rays(const PatchParams p) {
     }
 }
 
-constexpr int ADAM_MAX_SEG = 8;
+constexpr int ADAM_MAX_SEG = 16;
 struct AdamParams {
     float* p[ADAM_MAX_SEG]; float* g[ADAM_MAX_SEG]; float* m[ADAM_MAX_SEG]; float* v[ADAM_MAX_SEG];
     const float* lr[ADAM_MAX_SEG];
@@ -149,7 +149,7 @@ int mve_adam_step(uint32_t n_tensors, void* const* params, void* const* grads, v
                   const uint32_t* numel, const float* const* lr, float beta1, float beta2, float eps, float grad_scale, int32_t* step,
                   int zero_grad, void* stream) {
     if (n_tensors == 0) return 0;
-    MVE_ARG(n_tensors <= (uint32_t)ADAM_MAX_SEG, "adam_step: at most 8 tensors per launch");
+    MVE_ARG(n_tensors <= (uint32_t)ADAM_MAX_SEG, "adam_step: at most 16 tensors per launch");
     AdamParams a{};
     uint32_t blocks = 0;
     for (uint32_t s = 0; s < n_tensors; s++) {

@@ -53,8 +53,34 @@ class _LevelArgs:
         return (self.n, self.scale, self.res, self.size, self.off)
 
 
+class _HashGridFn(Function):
+    """enc = HashGrid(x01): differentiable w.r.t. the table and the positions (mve_hashgrid_forward / _backward)."""
+
+    @staticmethod
+    def forward(ctx, x01, params, enc):
+        x01 = x01.float().contiguous()
+        M = x01.shape[0]
+        out = torch.empty(M, enc.n_output_dims, dtype=torch.float32, device=x01.device)
+        call('mve_hashgrid_forward', ptr(x01), c_u32(M), ptr(params), *enc._largs.args(), ptr(out), stream())
+        ctx.save_for_backward(x01, params)
+        ctx.enc = enc
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x01, params = ctx.saved_tensors
+        g_table = torch.zeros_like(params) if ctx.needs_input_grad[1] else None
+        g_x = torch.zeros_like(x01) if ctx.needs_input_grad[0] else None
+        call('mve_hashgrid_backward', ptr(x01), c_u32(x01.shape[0]), ptr(params), *ctx.enc._largs.args(), ptr(g.float().contiguous()), ptr(g_table),
+             ptr(g_x), stream())
+        return g_x, g_table, None
+
+
 class HashGridEncoding(nn.Module):
-    """The slice of ``tinycudann.Encoding`` the reference uses: a flat fp32 ``params`` vector and ``n_output_dims``."""
+    """The slice of ``tinycudann.Encoding`` the reference uses (seam B4): a flat fp32 ``params`` vector, ``n_output_dims`` and the
+    call ``enc(x [M,3] in [0,1]) -> [M, 2 * n_levels]``, differentiable w.r.t. ``params`` and ``x`` (ingp_decoder.py:62-74,112;
+    triplane_ingp_decoder.py:102-114,150).  iNGPDecoder does not go through this call -- its encoding is fused with the MLP in
+    mve_field_forward / _backward -- TriPlaneiNGPDecoder does."""
 
     def __init__(self, n_levels=12, base_resolution=16, max_resolution=320, bound=1.0, log2_hashmap_size=19):
         super().__init__()
@@ -62,6 +88,11 @@ class HashGridEncoding(nn.Module):
         self.n_output_dims = 2 * n_levels
         self.params = nn.Parameter(torch.zeros(self.levels['n_entries'] * 2, dtype=torch.float32))
         self._largs = _LevelArgs(self.levels)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError('mvedit_b200 ops need CUDA tensors (no CPU fallback)')
+        return _HashGridFn.apply(x, self.params, self)
 
 
 class MLP(nn.Module):
@@ -368,7 +399,11 @@ class iNGPDecoder(nn.Module):
                     M2 = int(counter.item())
                     xyzs, ts, rays, dirs = xyzs2[:M2], ts2[:M2], rays2, None
             sigmas, rgbs, num_points = self.point_decode([xyzs], [dirs], code)
-            weights, weights_sum, depth, image = rm.batch_composite_rays_train(sigmas, rgbs, [ts], [rays], num_points)
+            if fused_entropy is not None:           # sample-entropy gradient folded into the composite backward (nerf_optim)
+                weights, weights_sum, depth, image = rm.composite_rays_train(sigmas, rgbs, ts, rays, 1e-4, False, None, fused_entropy)
+                weights_sum, depth, image = weights_sum[None], depth[None], image[None]
+            else:
+                weights, weights_sum, depth, image = rm.batch_composite_rays_train(sigmas, rgbs, [ts], [rays], num_points)
             results = dict(weights=weights, weights_sum=weights_sum, depth=depth, image=image, rays=[rays], normal=None, ts=[ts])
         else:
             N = ro.shape[0]

@@ -126,7 +126,8 @@ class BaseNeRF(nn.Module):
         assert intrinsics.dim() == 3 and intrinsics.size(0) == 1, 'one scene'
         K = intrinsics[0].float().contiguous()
         dt_gamma = float(cfg.get('dt_gamma_scale', 0.0) * 2 / (K[:, 0] + K[:, 1]).mean())
-        ws, depth, image = decoder.render_cameras(poses[0], K, h, w, density_bitfield, self.grid_size, dt_gamma=dt_gamma)
+        extra = dict(code=code) if not getattr(decoder, 'supports_capacity', True) else {}      # tri-plane decoders render from `code`
+        ws, depth, image = decoder.render_cameras(poses[0], K, h, w, density_bitfield, self.grid_size, dt_gamma=dt_gamma, **extra)
         return_rgba = cfg.get('return_rgba', False)
         if return_rgba:
             out_image = torch.cat([image, ws.unsqueeze(-1)], dim=-1)[None]
@@ -219,12 +220,13 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
     n_sel = max(n_inverse_rays // (ps * ps), 1)
     n_patches_total = V * (render_size // ps) ** 2
     dec.check_sample_overflow()                       # result of the PREVIOUS call's iterations (no sync on the fast path)
-    if getattr(dec, 'auto_capacity', dec.sample_capacity <= 0):
+    if getattr(dec, 'supports_capacity', True) and getattr(dec, 'auto_capacity', dec.sample_capacity <= 0):
         # post-cull sample buffers: the initial fit starts from fog (hundreds of surviving samples per ray), later calls see a
         # fitted field.  N * max_steps can never overflow; N * 256 is checked (check_sample_overflow raises if rays were dropped).
         dec.auto_capacity = True
         dec.sample_capacity = n_sel * ps * ps * (int(dec.max_steps) if is_init else min(256, int(dec.max_steps)))
-    use_graph = bool(getattr(nerf, 'use_cuda_graph', False)) and bool(optimizer.defaults.get('capturable', False)) and not debug
+    use_graph = bool(getattr(nerf, 'use_cuda_graph', False)) and bool(optimizer.defaults.get('capturable', False)) and not debug \
+        and getattr(dec, 'supports_capacity', True)
     rank, world = view_shard.world() if getattr(nerf, 'data_parallel', False) else (0, 1)
     if world > 1 and os.environ.get('MVE_DP_GRAPH', '1') == '0':
         use_graph = False                             # escape hatch: eager iterations around the collectives

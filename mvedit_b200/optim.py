@@ -50,7 +50,7 @@ class FusedAdam(torch.optim.Optimizer):
 
     def _build_args(self):
         n = len(self._params)
-        assert n <= 8, 'FusedAdam: at most 8 parameter tensors (mve_adam_step launches them together)'
+        assert n <= 16, 'FusedAdam: at most 16 parameter tensors (mve_adam_step launches them together)'
         arr = ctypes.c_void_p * n
         lrs = [g['lr'] for g in self.param_groups for _ in g['params']]
         self._c = dict(p=arr(*[p.data_ptr() for p in self._params]), g=arr(*[v[0].data_ptr() for v in self._views]),
@@ -68,14 +68,15 @@ class FusedAdam(torch.optim.Optimizer):
         raise KeyError('parameter is not managed by this optimizer')
 
     def zero_grad(self, set_to_none=False):
-        """Gradients are zeroed by ``step`` itself; only an explicit first call (or one after foreign writes) costs a memset."""
+        """``step`` zeroes the gradients it consumed, so inside a captured iteration this is free (nothing is recorded: the buffer is
+        zero by construction).  Outside a capture the buffer is cleared explicitly (a 28.7 MB memset, ~5 us) -- gradients written by
+        autograd between steps are not tracked."""
         for p, v in zip(self._params, self._views):
             if p.grad is None or p.grad.data_ptr() != v[0].data_ptr():
                 p.grad = v[0]
-                self._clean = False
-        if not self._clean and not torch.cuda.is_current_stream_capturing():
-            pass                     # inside nerf_optim the iteration starts right after a step (or a fresh buffer): nothing to do
-        return
+        if not torch.cuda.is_current_stream_capturing():
+            self.flat_grad.zero_()
+        self._clean = True
 
     def hard_zero_grad(self):
         self.flat_grad.zero_()

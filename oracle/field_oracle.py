@@ -124,3 +124,25 @@ def init_params(levels, n_entries, hidden=64, seed=0, table_scale=1e-4, dtype=to
     w1 = (torch.rand(hidden, in_dim, generator=g, dtype=dtype) * 2 - 1) * a1
     w2 = (torch.rand(4, hidden, generator=g, dtype=dtype) * 2 - 1) * a2
     return table, w1, torch.zeros(hidden, dtype=dtype), w2, torch.zeros(4, dtype=dtype)
+
+
+def triplane_point_decode(xyz, code, sd, levels, plane_cfg=('xy', 'xz', 'yz'), flip_z=False, bound=1.0, sigmoid_saturation=0.001, interp_mode='bilinear'):
+    """TriPlaneiNGPDecoder.point_decode (/root/reference/lib/models/decoders/triplane_ingp_decoder.py:142-212; xyz_transform:
+    triplane_decoder.py:106-130) for one scene without view directions (MVEdit disables them, lib/apis/adapter3d.py:1362).
+    xyz [M,3]; code (1,3,C,h,w); sd: state dict with the reference's keys (encoder.params, base_net.0.*, ingp_base_net.0.*,
+    density_net.0.*, color_net.0.*).  SiLU activation, trunc_exp density, saturated sigmoid colour."""
+    import torch.nn.functional as F
+    enc = hash_encode((xyz + bound) / (2 * bound), sd['encoder.params'].view(-1, 2), levels)
+    ax = dict(x=xyz[..., 0], y=xyz[..., 1], z=-xyz[..., 2] if flip_z else xyz[..., 2])
+    grid = torch.stack([torch.stack([ax[a] for a in plane], dim=-1) for plane in plane_cfg], dim=0).unsqueeze(1)       # (3,1,M,2)
+    C = code.shape[2]
+    pc = F.grid_sample(code[0].float(), grid, mode=interp_mode, padding_mode='border', align_corners=False).squeeze(-2)  # (3,C,M)
+    point_code = pc.permute(2, 1, 0).reshape(xyz.shape[0], C * 3)
+    lin = lambda n, t: F.linear(t, sd[n + '.0.weight'], sd[n + '.0.bias'])
+    base_x = lin('base_net', point_code) + lin('ingp_base_net', enc)
+    act = F.silu(base_x)
+    sigma = TruncExpFn.apply(lin('density_net', act).squeeze(-1))
+    rgb = torch.sigmoid(lin('color_net', act))
+    if sigmoid_saturation > 0:
+        rgb = rgb * (1 + sigmoid_saturation * 2) - sigmoid_saturation
+    return sigma, rgb
