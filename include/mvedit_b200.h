@@ -133,6 +133,14 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t B, uint32_
                      const float* bias, const float* row_bias, uint32_t ldrb, const void* residual, uint32_t ldr,
                      int act, float alpha, void* stream);
 
+/* 3x3 convolution (pad 1, stride 1 or 2) for FEW channels on the CUDA cores: the front of diffusers' ControlNetConditioningEmbedding
+ * (3->16, 16->16, 16->32 s2, 32->32, 32->96 s2 on the 512^2 condition images), where a tensor-core tile would be
+ * mostly channel padding.  x: x_format 0 = NHWC bf16 [B,H,W,Cin], 1 = NCHW f32, 2 = NCHW bf16 [B,Cin,H,W]; w_packed f32
+ * [9 taps][Cin][Cout]; y bf16 NHWC [B,H/stride,W/stride, ldy >= Cout] (columns >= Cout untouched); act 0 none / 1 SiLU.
+ * Instantiated (Cin, Cout, stride): (3,16,1) (16,16,1) (16,32,2) (32,32,1) (32,96,2) and the test sizes (3,8,1) (8,8,1) (8,16,2) (16,32,1). */
+int mve_conv3x3_direct_bf16(const void* x, int x_format, const float* w_packed, const float* bias, void* y, uint32_t B, uint32_t H,
+                            uint32_t W, uint32_t Cin, uint32_t Cout, uint32_t stride, uint32_t ldy, int act, void* stream);
+
 /* ---------------------------------------------------------------------------
  * B4: Instant-NGP field = tcnn-style HashGrid (Smoothstep, 2 features/level, fp32 table) + Linear(2L,64)+ReLU+Linear(64,4)
  * + trunc_exp(h0 + blob) / sigmoid saturation, fused.  Replaces tinycudann.Encoding fwd/bwd + torch Linear x2

@@ -147,3 +147,32 @@ def nchw_to_nhwc_pad(x, cpad):
     call('mve_nchw_to_nhwc_pad_bf16', ptr(x), c_int(int(x.dtype == torch.float32)), ptr(out), c_u32(B), c_u32(C), c_u32(H * W), c_u32(cpad),
          stream())
     return out
+
+
+DIRECT_CONV_CONFIGS = {(3, 16, 1), (16, 16, 1), (16, 32, 2), (32, 32, 1), (32, 96, 2), (3, 8, 1), (8, 8, 1), (8, 16, 2), (16, 32, 1)}
+
+
+def pack_direct_weight(w):
+    """[Cout, Cin, 3, 3] -> f32 [9, Cin, Cout] (tap = ky * 3 + kx), the layout mve_conv3x3_direct_bf16 stages into shared memory."""
+    return w.float().permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]).contiguous()
+
+
+def conv3x3_direct(x, w_packed, bias, cin, cout, stride=1, act=None, nchw=False, out_channels=None):
+    """Few-channel 3x3 convolution on the CUDA cores (pad 1).  x: NHWC bf16 [B,H,W,cin], or with nchw=True an NCHW f32 / bf16 image
+    [B,cin,H,W].  -> NHWC bf16 [B,H/stride,W/stride,out_channels or cout] (extra channels zero: the hand-off to a tensor-core layer)."""
+    if nchw:
+        B, _, H, W = x.shape
+        assert x.dtype in (torch.float32, torch.bfloat16)
+        fmt = 1 if x.dtype == torch.float32 else 2
+    else:
+        B, H, W, _ = x.shape
+        assert x.dtype == torch.bfloat16
+        fmt = 0
+    x = x.contiguous()
+    oc = out_channels or cout
+    alloc = torch.zeros if oc != cout else torch.empty
+    out = alloc(B, H // stride, W // stride, oc, dtype=torch.bfloat16, device=x.device)
+    call('mve_conv3x3_direct_bf16', ptr(x), c_int(fmt), ptr(w_packed), ptr(bias), ptr(out), c_u32(B), c_u32(H), c_u32(W), c_u32(cin), c_u32(cout),
+         c_u32(stride), c_u32(oc), c_int(ACT[act]), stream(), _meta=dict(flops=2.0 * B * (H // stride) * (W // stride) * cout * 9 * cin,
+                                                                        shape='direct conv B%d %dx%d Cin%d Cout%d s%d' % (B, H, W, cin, cout, stride)))
+    return out

@@ -322,8 +322,6 @@ class ControlNet(_Net):
         w, ce = self.w, self.cfg.cond_embed_channels
         if cond_repeat > 1:
             cond = cond[:cond.shape[0] // cond_repeat]
-        x = T.nchw_to_nhwc_pad(cond, 64)
-
         def conv(name, x, cin, cout, stride, act, residual=None):
             B, H, W_, cp = x.shape
             if stride == 1:
@@ -347,11 +345,30 @@ class ControlNet(_Net):
             T.gemm(cols, wd, bias=bd, act=act, out=out)
             return out.view(B, H // 2, W_ // 2, -1)
 
-        h = conv('controlnet_cond_embedding.conv_in', x, 3, ce[0], 1, 'silu')
+        # layer list of ControlNetConditioningEmbedding: conv_in, then (same-width stride 1, widening stride 2) pairs
+        layers = [('controlnet_cond_embedding.conv_in', 3, ce[0], 1)]
         k = 0
         for a, b in zip(ce[:-1], ce[1:]):
-            h = conv(f'controlnet_cond_embedding.blocks.{k}', h, a, a, 1, 'silu'); k += 1
-            h = conv(f'controlnet_cond_embedding.blocks.{k}', h, a, b, 2, 'silu'); k += 1
+            layers += [(f'controlnet_cond_embedding.blocks.{k}', a, a, 1), (f'controlnet_cond_embedding.blocks.{k + 1}', a, b, 2)]
+            k += 2
+        # the few-channel front (3->16->16->32->32->96 on 512^2 ... 128^2 images) runs on the CUDA cores at its true channel counts
+        # (mve_conv3x3_direct_bf16); from the first layer that is wide enough on, the tensor-core path takes over on 64-padded channels
+        h, direct, first = cond, True, True
+        for idx, (name, cin, cout, stride) in enumerate(layers):
+            if direct and (cin, cout, stride) in T.DIRECT_CONV_CONFIGS:
+                key = name + '#direct'
+                if key not in w.lin:
+                    w.lin[key] = (T.pack_direct_weight(w.sd[name + '.weight']).to(self.device), _f32(w.sd[name + '.bias'], self.device))
+                wp, bp = w.lin[key]
+                nxt = layers[idx + 1] if idx + 1 < len(layers) else None
+                hand_off = nxt is None or (nxt[1], nxt[2], nxt[3]) not in T.DIRECT_CONV_CONFIGS
+                h = T.conv3x3_direct(h, wp, bp, cin, cout, stride, act='silu', nchw=first, out_channels=_pad64(cout) if hand_off else None)
+            else:
+                if first:
+                    h = T.nchw_to_nhwc_pad(cond, 64)
+                direct = False
+                h = conv(name, h, cin, cout, stride, 'silu')
+            first = False
         if cond_repeat > 1:
             h = h.repeat(cond_repeat, 1, 1, 1)
         return conv('controlnet_cond_embedding.conv_out', h, ce[-1], self.cfg.block_out_channels[0], 1, None, residual=base)

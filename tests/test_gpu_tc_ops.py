@@ -182,3 +182,27 @@ def test_conv3x3_tall_tiles(B, H, W, Cin, Cout):
     ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1)
     ref = (ref + rb[:, :, None, None]).permute(0, 2, 3, 1) + res.float()
     _check(out, ref, 9 * Cin)
+
+
+@pytest.mark.parametrize('cin,cout,stride,nchw', [(3, 16, 1, True), (16, 16, 1, False), (16, 32, 2, False), (32, 32, 1, False), (32, 96, 2, False),
+                                                   (3, 16, 1, 'bf16')])
+def test_conv3x3_direct_small_channels(cin, cout, stride, nchw):
+    """mve_conv3x3_direct_bf16 (ControlNet hint front, CUDA cores, true channel counts) vs F.conv2d + SiLU."""
+    import torch.nn.functional as F
+    from mvedit_b200 import tc_ops as T
+    g = torch.Generator(device='cuda').manual_seed(cin * 100 + cout)
+    B, H, W = 3, 40, 56
+    w = torch.randn(cout, cin, 3, 3, device='cuda', generator=g) / math.sqrt(9 * cin)
+    bias = torch.randn(cout, device='cuda', generator=g)
+    x = torch.randn(B, cin, H, W, device='cuda', generator=g)
+    if nchw is True:
+        xin, xr = x, x
+    elif nchw == 'bf16':
+        xin = x.bfloat16(); xr = xin.float()
+    else:
+        xin = x.permute(0, 2, 3, 1).contiguous().bfloat16(); xr = xin.float().permute(0, 3, 1, 2)
+    out = T.conv3x3_direct(xin, T.pack_direct_weight(w), bias, cin, cout, stride, act='silu', nchw=bool(nchw), out_channels=(cout + 63) // 64 * 64)
+    ref = F.silu(F.conv2d(xr, w, bias, stride=stride, padding=1)).permute(0, 2, 3, 1)
+    assert out.shape == (B, H // stride, W // stride, (cout + 63) // 64 * 64)
+    _check(out[..., :cout], ref, 9 * cin)
+    assert float(out[..., cout:].abs().max()) == 0.0 if out.shape[-1] > cout else True
