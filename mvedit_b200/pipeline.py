@@ -24,60 +24,8 @@ import torch
 from .adapter3d_mixin import Adapter3DMixin
 from .nerf import nerf_optim
 from . import view_shard
+from .schedulers import EulerAncestralScheduler, DPMSolverMultistepScheduler, DDIMScheduler      # noqa: F401 (re-exported)
 from ._lib import call, ptr, stream, c_u32, c_f32
-
-
-class EulerAncestralScheduler:
-    """diffusers EulerAncestralDiscreteScheduler as the reference configures it for SD1.5 (scaled_linear betas 0.00085 -> 0.012,
-    1000 train steps, epsilon prediction, timestep_spacing='trailing': lib/apis/adapter3d.py:280-300).
-    The ancestral noise is an explicit argument of ``step`` so that oracle and kernels see identical draws."""
-
-    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
-        self.num_train_timesteps = num_train_timesteps
-        betas = np.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=np.float64) ** 2
-        self.alphas = 1.0 - betas
-        self.alphas_cumprod = np.cumprod(self.alphas)
-        self.init_noise_sigma = None
-
-    def set_timesteps(self, num_inference_steps, device='cpu'):
-        step_ratio = self.num_train_timesteps / num_inference_steps
-        ts = np.round(np.arange(self.num_train_timesteps, 0, -step_ratio)) - 1
-        sig = ((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5
-        sigmas = np.interp(ts, np.arange(len(sig)), sig)
-        self.sigmas = torch.tensor(np.concatenate([sigmas, [0.0]]), dtype=torch.float32, device=device)
-        self.timesteps = torch.tensor(ts, dtype=torch.float32, device=device)
-        self.init_noise_sigma = float(self.sigmas.max())
-        self._step_index = 0
-
-    def noise_scales(self, t):
-        """(sqrt(alpha_bar_t), sqrt(1 - alpha_bar_t)) as 0-dim tensors on t's device; a fractional t (the 'trailing' / Karras
-        timesteps are floats) interpolates the VE sigma between the two neighbouring integer timesteps -- what the reference's
-        get_noise_scales does (lib/core/diffusion.py:4-21; checked against it in tests/test_reference_pins.py)."""
-        tf = float(t)
-        sig = np.sqrt((1 - self.alphas_cumprod) / self.alphas_cumprod)
-        lo = min(int(tf), self.num_train_timesteps - 1)
-        hi = min(lo + 1, self.num_train_timesteps - 1)
-        ve = sig[lo] + (sig[hi] - sig[lo]) * (tf - lo) if torch.is_floating_point(t) else sig[lo]
-        a = 1.0 / np.sqrt(1.0 + ve * ve)
-        return t.new_tensor(a, dtype=torch.float32), t.new_tensor(ve * a, dtype=torch.float32)
-
-    def scale_model_input(self, sample, i):
-        return sample / ((self.sigmas[i] ** 2 + 1) ** 0.5)
-
-    def add_noise(self, original_samples, noise, timesteps):
-        """diffusers EulerAncestralDiscreteScheduler.add_noise: x + noise * sigma(t), t looked up in the current schedule."""
-        idx = [int((self.timesteps == float(t)).nonzero()[0]) for t in timesteps.reshape(-1)]
-        sigma = self.sigmas[idx].to(original_samples.device)
-        return original_samples + noise * sigma.view(-1, *([1] * (original_samples.dim() - 1)))
-
-    def step(self, model_output, i, sample, noise):
-        sigma = self.sigmas[i]
-        pred_original_sample = sample - sigma * model_output
-        sigma_to = self.sigmas[i + 1]
-        sigma_up = (sigma_to ** 2 * (sigma ** 2 - sigma_to ** 2) / sigma ** 2) ** 0.5
-        sigma_down = (sigma_to ** 2 - sigma_up ** 2) ** 0.5
-        derivative = (sample - pred_original_sample) / sigma
-        return sample + derivative * (sigma_down - sigma) + noise * sigma_up
 
 
 class MVEdit3DStep(Adapter3DMixin):
