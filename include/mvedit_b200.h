@@ -161,10 +161,7 @@ int mve_field_forward(const float* xyz, uint32_t M, const int32_t* M_dev, const 
 /* Backward of mve_field_forward w.r.t. table (atomically ACCUMULATED into grad_table: caller zeroes / owns .grad),
  * MLP parameters (written, or added when accumulate_mlp != 0; deterministic two-stage reduction through `workspace`
  * of mve_field_backward_workspace_floats(n_levels) floats) and optionally xyz (grad_xyz [M,3] or NULL).
- * grad_rgb may be NULL (density-only graph).  mlp_tf32 != 0: the MLP backward runs on tensor cores in TF32 (see above).
- * denc_scratch (NULL, or 2*n_levels*M floats; tensor-core path without grad_xyz only): the backward is split in two launches --
- * the MLP backward leaves d(enc) feature-major in the scratch, and a one-thread-per-(sample, level) kernel at full occupancy
- * turns it into the table-gradient reductions.  Same sums as the single launch; the order of the float atomics differs. */
+ * grad_rgb may be NULL (density-only graph).  mlp_tf32 != 0: the MLP backward runs on tensor cores in TF32 (see above). */
 uint32_t mve_field_backward_workspace_floats(uint32_t n_levels);
 int mve_field_backward(const float* xyz, uint32_t M, const int32_t* M_dev, const float* table,
                        const float* w1, const float* b1, const float* w2, const float* b2,
@@ -173,7 +170,7 @@ int mve_field_backward(const float* xyz, uint32_t M, const int32_t* M_dev, const
                        float bound, float blob_density, float blob_radius, float sigmoid_saturation,
                        const float* grad_sigma, const float* grad_rgb,
                        float* grad_table, float* grad_w1, float* grad_b1, float* grad_w2, float* grad_b2,
-                       int accumulate_mlp, int mlp_tf32, float* workspace, float* grad_xyz, float* denc_scratch, void* stream);
+                       int accumulate_mlp, int mlp_tf32, float* workspace, float* grad_xyz, void* stream);
 
 /* The bare hash-grid encoding as a differentiable op: `tcnn.Encoding(n_input_dims=3, HashGrid ...)(x)` (seam B4; ingp_decoder.py:62-74,112,
  * triplane_ingp_decoder.py:102-114,150).  x01 [M,3] in [0,1]; out [M, 2*n_levels] (feature 2l+f).  The backward ACCUMULATES into

@@ -58,7 +58,7 @@ def check(code, name):
 
 
 # kernels launched per C-ABI call (memsets not counted); used for the bench's "gpu_launches" claim
-KERNELS_PER_CALL = {'mve_groupnorm_bf16': 2, 'mve_field_backward': 3, 'mve_density_grid_update': 2, 'mve_march_rays_train': 2}
+KERNELS_PER_CALL = {'mve_groupnorm_bf16': 2, 'mve_field_backward': 2, 'mve_density_grid_update': 2, 'mve_march_rays_train': 2}
 LAUNCHES = [0]
 PROFILE = [None]      # set to a list to record (name, start_event, end_event, meta) per call (bench.py roofline pass)
 

@@ -332,14 +332,14 @@ __global__ void __launch_bounds__(BW_T) k_field_bwd(const float* __restrict__ xy
 
 // Tensor-core backward (field_bwd_mma.cuh): rolled encoder -> per-warp TF32 MMA backward of the MLP -> rolled scatter of d(enc)
 // into the table gradient.  Same interface, workspace layout and two-stage deterministic MLP reduction as k_field_bwd.
-template <int L, bool WITH_DX, bool SPLIT>
+template <int L, bool WITH_DX>
 __global__ void __launch_bounds__(BW_T, 3) k_field_bwd_mma(const float* __restrict__ xyz, uint32_t M, const int* __restrict__ M_dev,
                                                            const float2* __restrict__ table, const float* __restrict__ w1,
                                                            const float* __restrict__ b1, const float* __restrict__ w2,
                                                            const float* __restrict__ b2, const Levels lv, const FieldCfg cfg,
                                                            const float* __restrict__ g_sigma, const float* __restrict__ g_rgb,
                                                            float2* __restrict__ g_table, float* __restrict__ workspace,
-                                                           float* __restrict__ g_xyz, float* __restrict__ denc) {
+                                                           float* __restrict__ g_xyz) {
     using B = mlpmma::BCfg<L>;
     constexpr int IN = B::IN, LD = B::LD, WARP_FLOATS = B::STAGE_FLOATS + B::XCH_FLOATS;
     extern __shared__ __align__(16) float smem[];
@@ -350,7 +350,6 @@ __global__ void __launch_bounds__(BW_T, 3) k_field_bwd_mma(const float* __restri
     mlpmma::stage_bwd_frags<L>(fr, w1, b1, w2);
     mlpmma::init_bwd_stage<L>(stage);
     __syncthreads();
-    const uint32_t cap = M;          // row pitch of the feature-major d(enc) scratch (SPLIT)
     if (M_dev) M = min(M, (uint32_t)*M_dev);
     const float ob0 = b2[0], ob1 = b2[1], ob2 = b2[2], ob3 = b2[3];
     mlpmma::MlpGradAcc<L> acc;
@@ -384,15 +383,6 @@ __global__ void __launch_bounds__(BW_T, 3) k_field_bwd_mma(const float* __restri
             }
             d0 = d[0];
         });
-        if (SPLIT) {
-            // d(enc) leaves feature-major (coalesced 128 B rows); k_field_scatter turns it into table-gradient reds at full occupancy
-            if (live) {
-#pragma unroll 4
-                for (int f = 0; f < IN; f++) denc[(size_t)f * cap + i] = stage[f * LD + lane];
-            }
-            __syncwarp();
-            continue;
-        }
         // ---- scatter d(enc) into the table gradient (+ optional d/dx), one level per trip
         float gx0 = 0.f, gx1 = 0.f, gx2 = 0.f;
 #pragma unroll 1
@@ -465,38 +455,6 @@ __global__ void __launch_bounds__(BW_T, 3) k_field_bwd_mma(const float* __restri
     for (int t = threadIdx.x; t < NP; t += BW_T) row[t] = s_acc[t];
 }
 
-// Second half of the split backward: one thread per (sample, level), level = blockIdx.y so the CTAs resident at any moment work on
-// one level's slice of the table gradient (<= 4 MB: L2 resident).  ~40 registers -> full occupancy, which is what the reds want;
-// inside k_field_bwd_mma the same loop runs at 12 warps / SM behind the MLP accumulators.
-template <int L>
-__global__ void __launch_bounds__(256) k_field_scatter(const float* __restrict__ xyz, uint32_t M, const int* __restrict__ M_dev,
-                                                       const Levels lv, const FieldCfg cfg, const float* __restrict__ denc,
-                                                       float2* __restrict__ g_table) {
-    const uint32_t cap = M;
-    if (M_dev) M = min(M, (uint32_t)*M_dev);
-    const int l = blockIdx.y;
-    const float sc = lv.scale[l];
-    const bool hashed = (lv.hashed >> l) & 1u;
-    const uint32_t res = lv.res[l], size = lv.size[l];
-    float2* __restrict__ gt = g_table + lv.off[l];
-    const float* __restrict__ da = denc + (size_t)(2 * l) * cap;
-    const float* __restrict__ db = denc + (size_t)(2 * l + 1) * cap;
-    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < M; i += gridDim.x * 256) {
-        const float ga = da[i], gb = db[i];
-        if (ga == 0.f && gb == 0.f) continue;
-        const float x0 = (xyz[(size_t)i * 3] + cfg.bound) * cfg.inv2b, x1 = (xyz[(size_t)i * 3 + 1] + cfg.bound) * cfg.inv2b,
-                    x2 = (xyz[(size_t)i * 3 + 2] + cfg.bound) * cfg.inv2b;
-        const Cell cl = locate(x0, x1, x2, sc);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const float wx = (k & 1) ? cl.w[0] : 1.f - cl.w[0], wy = (k & 2) ? cl.w[1] : 1.f - cl.w[1], wz = (k & 4) ? cl.w[2] : 1.f - cl.w[2];
-            const uint32_t idx = grid_index(hashed, res, size, cl.g[0] + (k & 1), cl.g[1] + ((k >> 1) & 1), cl.g[2] + (k >> 2));
-            const float wgt = wx * wy * wz;
-            red_add_v2(gt + idx, wgt * ga, wgt * gb);
-        }
-    }
-}
-
 // sum the per-CTA rows in a fixed order -> g_w1, g_b1, g_w2, g_b2 (accumulate = add to existing .grad)
 template <int L>
 __global__ void k_field_reduce_mlp(const float* __restrict__ workspace, const uint32_t n_rows, float* __restrict__ g_w1,
@@ -553,7 +511,7 @@ int mve_field_backward(const float* xyz, uint32_t M, const int32_t* M_dev, const
                        const uint32_t* level_size, const uint32_t* level_offset, float bound, float blob_density, float blob_radius,
                        float sigmoid_saturation, const float* grad_sigma, const float* grad_rgb, float* grad_table, float* grad_w1,
                        float* grad_b1, float* grad_w2, float* grad_b2, int accumulate_mlp, int mlp_tf32, float* workspace,
-                       float* grad_xyz, float* denc_scratch, void* stream) {
+                       float* grad_xyz, void* stream) {
     Levels lv;
     MVE_ARG(fill_levels(lv, n_levels, level_scale, level_res, level_size, level_offset) == 0, "field: n_levels > 16");
     MVE_ARG(n_levels == 12 || n_levels == 14 || n_levels == 16, "field: n_levels must be 12, 14 or 16");
@@ -565,26 +523,22 @@ int mve_field_backward(const float* xyz, uint32_t M, const int32_t* M_dev, const
     const float2* t2 = reinterpret_cast<const float2*>(table);
     float2* gt2 = reinterpret_cast<float2*>(grad_table);
     cudaStream_t s = (cudaStream_t)stream;
-#define BWD_MMA(LL, DX, SP)                                                                                                              \
+#define BWD_MMA(LL, DX)                                                                                                                  \
     {                                                                                                                                    \
         using BC = mlpmma::BCfg<LL>;                                                                                                     \
         const size_t smem = sizeof(float) * (BC::FRAG_FLOATS + (BW_T / 32) * (BC::STAGE_FLOATS + BC::XCH_FLOATS));                       \
         static bool attr_done = false;                                                                                                   \
         if (!attr_done) {                                                                                                                \
-            MVE_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<LL, DX, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+            MVE_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<LL, DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
             attr_done = true;                                                                                                            \
         }                                                                                                                                \
-        k_field_bwd_mma<LL, DX, SP><<<grid, BW_T, smem, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, grad_sigma, grad_rgb, gt2,      \
-                                                             workspace, grad_xyz, denc_scratch);                                         \
-        if (SP) {                                                                                                                        \
-            const uint32_t gx0 = cdiv(M > 0 ? M : 1, 256), gx = gx0 < (uint32_t)(8 * kNumSM) ? gx0 : (uint32_t)(8 * kNumSM);                 \
-            k_field_scatter<LL><<<dim3(gx, LL), 256, 0, s>>>(xyz, M, M_dev, lv, cfg, denc_scratch, gt2);                                 \
-        }                                                                                                                                \
+        k_field_bwd_mma<LL, DX><<<grid, BW_T, smem, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, grad_sigma, grad_rgb, gt2,          \
+                                                         workspace, grad_xyz);                                                           \
     }
 #define BWD(LL)                                                                                                                          \
     {                                                                                                                                    \
         if (mlp_tf32) {                                                                                                                  \
-            if (grad_xyz) BWD_MMA(LL, true, false) else if (denc_scratch) BWD_MMA(LL, false, true) else BWD_MMA(LL, false, false)        \
+            if (grad_xyz) BWD_MMA(LL, true) else BWD_MMA(LL, false)                                                                      \
         } else if (grad_xyz)                                                                                                             \
             k_field_bwd<LL, true><<<grid, BW_T, 0, s>>>(xyz, M, M_dev, t2, w1, b1, w2, b2, lv, cfg, grad_sigma, grad_rgb, gt2,           \
                                                         workspace, grad_xyz);                                                            \

@@ -11,7 +11,6 @@ returns the same dict.  The arithmetic is libmvedit_b200.so: hash grid + MLP + a
 """
 import ctypes
 import math
-import os
 from copy import deepcopy
 
 import numpy as np
@@ -21,8 +20,6 @@ from torch.autograd import Function
 
 from . import raymarching as rm
 from ._lib import call, ptr, stream, get_lib, c_int, c_u32, c_f32
-
-_FIELD_SPLIT = os.environ.get('MVE_FIELD_SPLIT', '1') != '0'
 
 
 def level_table(n_levels=12, base_resolution=16, max_resolution=320, bound=1.0, log2_hashmap_size=19):
@@ -155,14 +152,10 @@ class _FieldFn(Function):
         ws = dec._workspace(xyz.device)
         g_sigma = g_sigma.float().contiguous()
         g_rgb = None if (ctx.density_only or g_rgb is None) else g_rgb.float().contiguous()
-        # split backward (MLP backward -> feature-major d(enc) -> full-occupancy scatter kernel); MVE_FIELD_SPLIT=0 keeps one launch
-        denc = None
-        if ctx.tf32 and not need_dx and M > 0 and _FIELD_SPLIT:
-            denc = torch.empty(dec.encoder.n_output_dims * M, dtype=torch.float32, device=xyz.device)
         call('mve_field_backward', ptr(xyz), c_u32(M), ptr(ctx.m_dev), ptr(table), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
              *dec.encoder._largs.args(), c_f32(dec.bound), c_f32(dec.blob_density), c_f32(dec.blob_radius),
              c_f32(dec.sigmoid_saturation), ptr(g_sigma), ptr(g_rgb), ptr(g_table), ptr(g_w1), ptr(g_b1), ptr(g_w2), ptr(g_b2),
-             c_int(int(sink is not None)), c_int(int(ctx.tf32)), ptr(ws), ptr(g_xyz), ptr(denc), stream())
+             c_int(int(sink is not None)), c_int(int(ctx.tf32)), ptr(ws), ptr(g_xyz), stream())
         if sink is not None:
             return g_xyz, None, None, None, None, None, None, None, None
         return g_xyz, g_table, g_w1, g_b1, g_w2, g_b2, None, None, None

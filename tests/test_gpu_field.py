@@ -114,37 +114,6 @@ def test_tf32_backward_without_relu_flips():
         assert (a - b).abs().max().item() <= 1e-2 * b.abs().max().item() + 1e-7, ((a - b).abs().max().item(), b.abs().max().item())
 
 
-@pytest.mark.parametrize('L,R', [(12, 320), (16, 512)])
-def test_split_backward_equals_single_launch(L, R):
-    """mve_field_backward with a d(enc) scratch (MLP backward + full-occupancy scatter kernel, the default of the training loop)
-    against the single launch: the same products summed in another atomic order -> 1e-5 of the gradient's max; MLP gradients (same
-    kernel, deterministic reduction) bit-identical.  M = 70001 makes the scatter kernel's grid-stride loop and ragged tail run."""
-    import mvedit_b200.ingp_decoder as ing
-    dec, levels, _ = make_decoder(L, R)
-    dec.mlp_tf32 = True
-    g = torch.Generator().manual_seed(9)
-    M = 70001
-    xyz = ((torch.rand(M, 3, generator=g) * 2 - 1) * 0.999).cuda()
-    gs, gr = torch.randn(M, generator=g).cuda(), torch.randn(M, 3, generator=g).cuda()
-    gs[::5] = 0; gr[::5] = 0                     # samples past a ray's termination carry exact zeros
-    grads = {}
-    for split in (True, False):
-        ing._FIELD_SPLIT = split
-        try:
-            for p in dec.parameters():
-                p.grad = None
-            sig, rgb, _ = dec.point_decode([xyz], None, None)
-            torch.autograd.backward([sig, rgb], [gs, gr])
-            grads[split] = [p.grad.detach().clone() for p in dec._field_params()]
-        finally:
-            ing._FIELD_SPLIT = True
-    a, b = grads[True][0], grads[False][0]
-    assert float(b.abs().max()) > 0
-    assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
-    for x, y in zip(grads[True][1:], grads[False][1:]):
-        assert torch.equal(x, y)
-
-
 def test_density_prepass_tf32_tensor_core_mlp():
     """density_only=2 (culling pre-pass): MLP via mma.sync TF32; vs the fp32 oracle within TF32 precision."""
     from mvedit_b200.ingp_decoder import _FieldFn

@@ -68,13 +68,24 @@ def _schedulers():
                 dpm_karras=lambda: DPMSolverMultistepScheduler(use_karras_sigmas=True, timestep_spacing='leading'))
 
 
-@pytest.mark.parametrize('sched,mode,blend', [('euler', '2-pass', 0.0), ('dpm', '2-pass', 0.0), ('dpm_karras', '1-pass', 'dynamic'),
-                                              ('ddim', '1-pass', 0.0)])
-def test_call_runs_nerf_stage(parts, sched, mode, blend):
+@pytest.mark.parametrize('sched,mode,blend,ref', [('euler', '2-pass', 0.0, False), ('dpm', '2-pass', 0.0, False),
+                                                  ('dpm_karras', '1-pass', 'dynamic', False), ('ddim', '1-pass', 0.0, False),
+                                                  ('euler', '2-pass', 0.0, True), ('dpm', '1-pass', 'dynamic', 'cond'),
+                                                  ('euler', '2-pass', 0.0, 'extra')])
+def test_call_runs_nerf_stage(parts, sched, mode, blend, ref):
+    """ref: False = plain CFG batch; True = cross-image attention against the view's own input image (the reference's default,
+    latents (N,4,128,64)); 'cond' = against separate conditioning images; 'extra' = a third ControlNet fed the input images."""
     sch = _schedulers()[sched]()
     pipe, dec = make_pipe(parts, sch)
     before = {k: v.detach().clone() for k, v in dec.state_dict().items()}
-    mesh, state = call(pipe, parts, mode=mode, blend_weight=blend)
+    kw = dict(use_reference=bool(ref) and ref != 'extra')
+    if ref == 'cond':
+        g = torch.Generator(device='cuda').manual_seed(5)
+        kw['cond_images'] = [torch.rand(3, 256, 256, device='cuda', generator=g) for _ in range(N)]
+    if ref == 'extra':
+        from mvedit_b200.unet import MultiControlNet
+        pipe.controlnet = MultiControlNet(parts['cns'] + [parts['cns'][0]])
+    mesh, state = call(pipe, parts, mode=mode, blend_weight=blend, **kw)
     assert mesh is None and state is not None, 'the run raised inside __call__ (traceback printed above)'
     assert all(torch.isfinite(v).all() for v in state.values() if torch.is_floating_point(v))
     moved = max(float((state[k].float() - before[k].float()).abs().max()) for k in before if torch.is_floating_point(before[k]))
@@ -94,6 +105,6 @@ def test_unbuilt_stages_raise_and_restore(parts):
         call(pipe, parts, progress_to_dmtet=0.3)                    # DMTet / mesh stage
     assert all(torch.equal(dec.state_dict()[k], before[k]) for k in before)
     with pytest.raises(NotImplementedError):
-        call(pipe, parts, use_reference=True)
+        call(pipe, parts, use_normal=True)
     with pytest.raises(NotImplementedError):
         call(pipe, parts, init_images=None)
