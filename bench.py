@@ -117,8 +117,12 @@ def build(device, rank, world):
     cns = [ControlNet(uc.random_controlnet_state_dict(cfg, 1, device), cfg, device),
            ControlNet(uc.random_controlnet_state_dict(cfg, 2, device), cfg, device)]
     torch.manual_seed(0)
+    from mvedit_b200.lpips import LPIPSLoss, random_lpips_state_dict
+    from mvedit_b200.nerf import L1LossMod
+    # pixel_loss / patch_loss as the pipelines build them (lib/pipelines/utils.py:231-232): L1LossMod(1.2), LPIPSLoss('vgg', 1.2)
     nerf = BaseNeRF(grid_size=GRID, decoder=iNGPDecoder(max_resolution=320, n_levels=12, max_steps=1024, weight_culling_th=0.001),
-                    patch_size=128).to(device)
+                    pixel_loss=L1LossMod(loss_weight=1.2),
+                    patch_loss=LPIPSLoss(random_lpips_state_dict(5, device), loss_weight=1.2, device=device), patch_size=128).to(device)
     sch = EulerAncestralScheduler()
     sch.set_timesteps(24, device=device)
     from mvedit_b200.vae import AutoencoderKL, random_vae_state_dict
@@ -185,9 +189,12 @@ def run_ours(args):
         decoded_mean.copy_(pipe.vae.decode_images(pred_x0).mean().reshape(1))
         return tgt_img_h.to(device, non_blocking=True), tgt_msk_h.to(device, non_blocking=True)
 
+    # LPIPS patch term with the reference's default schedule (mvedit_3d_pipeline.py:65-66: 0.3 -> 1.5 over the run), at this step's progress
+    from mvedit_b200.mvedit_3d_pipeline import default_patch_rgb_weight
+    prw = (lambda i: 0.0) if args.no_lpips else (lambda i: float(default_patch_rgb_weight(i / 24)))
     kw = dict(density_grid=grid, density_bitfield=bitfield, optimizer=opt, camera_poses=poses, intrinsics=K, intrinsics_size=IMG,
               cam_weights=cam_w, cam_lights=lights, ancestral_noise=noise, guidance_scale=7.0, render_size=IMG,
-              n_inverse_steps=N_INVERSE_STEPS, n_inverse_rays=N_INVERSE_RAYS)
+              n_inverse_steps=N_INVERSE_STEPS, n_inverse_rays=N_INVERSE_RAYS, patch_rgb_weight=prw(step_i))
 
     snap = {}
 
@@ -242,15 +249,15 @@ def run_ours(args):
     from mvedit_b200.nerf import nerf_optim
     with torch.no_grad():
         t_init0 = time.time()
-        nerf_optim(pipe.nerf, tgt_img[None], tgt_msk[None], None, opt, 0.01, 640, N_INVERSE_RAYS, 0.0, 0.0, 0.02, 0.1, 0.01, None, grid, bitfield,
+        nerf_optim(pipe.nerf, tgt_img[None], tgt_msk[None], None, opt, 0.01, 640, N_INVERSE_RAYS, prw(0), 0.0, 0.02, 0.1, 0.01, None, grid, bitfield,
                    IMG, K, IMG, poses, cam_w, lights, 128, True, 0.015, 0.2, 1.0, init_shaded=False)
         torch.cuda.synchronize()
         init_s = time.time() - t_init0
         # The timed step is a MID-schedule one (step_i = 8 of 24): by then the reference has run 8 further reconstruction calls of 96
         # iterations on the field (mvedit_3d_pipeline.py:1296-1305).  Do those too, so that the snapshot is the field a mid-schedule
         # step actually meets (a field fresh out of the 640-iteration init is foggier and its sample counts vary far more run to run).
-        for _ in range(step_i):
-            nerf_optim(pipe.nerf, tgt_img[None], tgt_msk[None], None, opt, 0.01, N_INVERSE_STEPS, N_INVERSE_RAYS, 0.0, 0.0, 0.02, 0.1, 0.01, None, grid,
+        for j in range(step_i):
+            nerf_optim(pipe.nerf, tgt_img[None], tgt_msk[None], None, opt, 0.01, N_INVERSE_STEPS, N_INVERSE_RAYS, prw(j), 0.0, 0.02, 0.1, 0.01, None, grid,
                        bitfield, IMG, K, IMG, poses, cam_w, lights, 128, False, 0.015, 0.2, 1.0, init_shaded=False)
         torch.cuda.synchronize()
     snapshot()
@@ -356,7 +363,7 @@ def run_ours(args):
         except Exception as e:
             extra['gs_raster'] = dict(error=repr(e)[:300])
         extra['gpu_baseline'] = gpu_baseline(device, pipe, dict(grid=snap['grid'], bits=snap['bits']), poses, K, cam_w, lights, tgt_img, tgt_msk, phases,
-                                             skip=args.no_gpu_baseline)
+                                             skip=args.no_gpu_baseline, patch_rgb_weight=prw(step_i))
         extra['cpu_baseline'] = cpu_baseline()
     if world > 1:
         dist.barrier()
@@ -374,16 +381,18 @@ def run_ours(args):
         metric=METRIC, value=round(steps_per_s, 4), unit='steps/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=round(ms / args.steps, 2), higher_is_better=True, scaling='strong', vs_baseline=None, dtype='bf16', data='synthetic',
         config=dict(workload='BASELINE configs[1]: 32-view 512^2 SD1.5 UNet + ControlNet tile+depth (2-pass, CFG: 64 UNet images/pass) '
-                             '+ vae.decode of 32 latents + NeRF adapter (96 iters x 16384 rays, 12-level hash grid) + render 32x512^2 '
+                             '+ vae.decode of 32 latents + NeRF adapter (96 iters x 16384 rays, 12-level hash grid, objective incl. the LPIPS-VGG16 '
+                             'patch term) + render 32x512^2 '
                              '+ Euler-ancestral step',
                     views=N_VIEWS, image=IMG, latent=LATENT, recon_iters=N_INVERSE_STEPS, rays_per_iter=N_INVERSE_RAYS,
                     weights='random-init SD1.5 / ControlNet v1.1 / SD1.5-VAE shapes',
                     parallelism=('view-shard x%d (denoise, decode, render) + ' % world) +
                                 ('ray-data-parallel reconstruction (1 all_gather of per-ray outputs + 1 all_reduce of the 28.7 MB gradient per iteration)'
                                  if pipe.nerf.data_parallel else 'reconstruction on one replica set (+ 1 flat broadcast)' if world > 1 else 'single GPU'),
-                    in_step='denoise P1, vae.decode (real, on pred_x0), gather, nerf_optim x96, render, denoise P2, solver',
+                    in_step='denoise P1, vae.decode (real, on pred_x0), gather, nerf_optim x96 (L1 + alpha + TV-normal + entropy' +
+                            ('' if args.no_lpips else ' + LPIPS(VGG16, bf16) on the 128^2 patch, weight %.2f' % prw(step_i)) + '), render, denoise P2, solver',
                     field_state='640-iteration init + 8 x 96 iterations (the reconstruction calls of the 8 steps before the timed mid-schedule step)',
-                    not_in_step='TRACER masks, LPIPS patch loss, SRVGG enhancer (SURVEY.md §8f-2: not built). The reconstruction fits analytic '
+                    not_in_step='TRACER masks, SRVGG enhancer' + (', LPIPS patch loss (--no-lpips)' if args.no_lpips else '') + ' (SURVEY.md §8f-2: not built). The reconstruction fits analytic '
                                 'targets + silhouettes because a random-init VAE decodes noise; the decoded tensor is reduced and read back in e2e',
                     l2='per-step working set (168 MB per UNet activation tensor, 2.1 GB per VAE activation, >5 GB live) >> 126 MB L2'),
         e2e=dict(value=round(e2e_steps_per_s, 4), unit='steps/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(out_h.numel() * 4 + 4)),
@@ -623,7 +632,7 @@ def gs_microbench(device, pk):
 
 
 # --------------------------------------------------------------------------------------------------------- GPU reference leg
-def gpu_baseline(device, pipe, state, poses, K, cam_w, lights, tgt_img, tgt_msk, our_phases, skip=False):
+def gpu_baseline(device, pipe, state, poses, K, cam_w, lights, tgt_img, tgt_msk, our_phases, skip=False, patch_rgb_weight=0.0):
     """BASELINE.md §3 row 2 -- what the reference executes for one step, on THIS GPU, as far as it can be run offline:
       * denoiser: the SD-1.5 UNet / ControlNets / VAE decoder as stock PyTorch modules-equivalent functional code (oracle/unet_oracle.py,
         oracle/vae_oracle.py: F.conv2d -> cuDNN, F.linear -> cuBLAS, F.scaled_dot_product_attention -> flash SDPA) in bf16 with TF32
@@ -682,10 +691,18 @@ def gpu_baseline(device, pipe, state, poses, K, cam_w, lights, tgt_img, tgt_msk,
             dec = no.OracleDecoder(ops, max_steps=1024, weight_culling_th=0.001).to(device)
             dec.load_state_dict(pipe.nerf.decoder.state_dict(), strict=False)
             nerf = no.OracleNeRF(dec, grid_size=GRID, patch_size=128)
+            prw = float(patch_rgb_weight)
+            if prw > 0:
+                # the reference's LPIPSLoss: lpips.LPIPS(net='vgg') in bf16 through stock PyTorch (cuDNN) + autograd (lpips_loss.py:28-43)
+                from oracle import lpips_oracle as lo
+                from mvedit_b200.lpips import random_lpips_state_dict
+                lsd = {k: v.to(torch.bfloat16) for k, v in random_lpips_state_dict(5, device).items()}
+                lpips_ref = lambda pred, tgt, weight=None: lo.lpips_loss(lsd, pred.to(torch.bfloat16), tgt.to(torch.bfloat16), weight, 1.2).float()
+                nerf.patch_loss = lpips_ref
             grid, bits = state['grid'].clone(), state['bits'].clone()
             opt = torch.optim.Adam(dec.parameters(), lr=0.01)
             n_it = 24                                                  # bounded sample of the 96 iterations (each is the same work)
-            run = lambda k: no.nerf_optim(nerf, tgt_img[None], tgt_msk[None], None, opt, 0.01, k, N_INVERSE_RAYS, 0.0, 0.0, 0.02, 0.1, 0.01, None,
+            run = lambda k: no.nerf_optim(nerf, tgt_img[None], tgt_msk[None], None, opt, 0.01, k, N_INVERSE_RAYS, prw, 0.0, 0.02, 0.1, 0.01, None,
                                           grid, bits, IMG, K, IMG, poses, cam_w, lights, 128, False, 0.015, 0.2, 1.0, False)
             with torch.no_grad():
                 run(2)
@@ -710,9 +727,11 @@ def gpu_baseline(device, pipe, state, poses, K, cam_w, lights, tgt_img, tgt_msk,
             fast.load_state_dict(pipe.nerf.decoder.state_dict(), strict=False)
             object.__setattr__(dec_b, 'fast', fast)
             nerf_b = no.OracleNeRF(dec_b, grid_size=GRID, patch_size=128)
+            if prw > 0:
+                nerf_b.patch_loss = lpips_ref
             grid_b, bits_b = state['grid'].clone(), state['bits'].clone()
             opt_b = torch.optim.Adam(fast.parameters(), lr=0.01)
-            run_b = lambda k: no.nerf_optim(nerf_b, tgt_img[None], tgt_msk[None], None, opt_b, 0.01, k, N_INVERSE_RAYS, 0.0, 0.0, 0.02, 0.1, 0.01, None,
+            run_b = lambda k: no.nerf_optim(nerf_b, tgt_img[None], tgt_msk[None], None, opt_b, 0.01, k, N_INVERSE_RAYS, prw, 0.0, 0.02, 0.1, 0.01, None,
                                             grid_b, bits_b, IMG, K, IMG, poses, cam_w, lights, 128, False, 0.015, 0.2, 1.0, False)
             with torch.no_grad():
                 run_b(4)
@@ -751,10 +770,11 @@ def cpu_baseline(reps_=(0, 1)):
     ORACLE PORT (kind 'port') on the host cores, on a bounded sample of the same workload, extrapolated linearly:
       UNet: 1 image through unet_enc + 2 x unet_dec and 2 ControlNets at latent 64 (x64 images per step),
       VAE: 1 latent through the decoder at latent 64 (x32 per step),
-      recon: 1 iteration (16 384 rays: C march + composite, torch field fwd/bwd)           (x96 per step),
+      recon: 1 iteration (16 384 rays: C march + composite, torch field fwd/bwd, LPIPS-VGG16 fwd/bwd on the patch)   (x96 per step),
       render: 1 view at 128^2 through the inference loop (x32 views x16 for 512^2)."""
-    from oracle import unet_oracle as uo, field_oracle as fo, raymarching_oracle as orc, vae_oracle as vo
+    from oracle import unet_oracle as uo, field_oracle as fo, raymarching_oracle as orc, vae_oracle as vo, lpips_oracle as lo_
     from tests import synth
+    lsd = lo_.random_lpips_state_dict(5)
     cores = min(len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1), 32)
     torch.set_num_threads(cores)
     os.environ.setdefault('OMP_NUM_THREADS', str(cores))
@@ -799,6 +819,9 @@ def cpu_baseline(reps_=(0, 1)):
         gs, gc = orc.composite_rays_train_backward(np.zeros_like(w), np.ones(N, np.float32), np.ones(N, np.float32), np.ones((N, 3), np.float32),
                                                    sig.detach().numpy(), rgb.detach().numpy(), ts, rays, ws, dep, img)
         torch.autograd.backward([sig, rgb], [torch.from_numpy(gs), torch.from_numpy(gc)])
+        # LPIPS patch term of the iteration: VGG16 over the rendered and the target 128^2 patch + backward to the rendered one
+        pr = torch.from_numpy(img.reshape(1, 128, 128, 3)).permute(0, 3, 1, 2).clamp(0, 1).requires_grad_(True)
+        lo_.lpips_loss(lsd, pr, torch.rand(1, 3, 128, 128, generator=g), None, 1.2).backward()
         t_recon_iter = time.time() - t0
         # render one 128^2 view
         t0 = time.time()
@@ -853,6 +876,7 @@ def main():
     ap.add_argument('--profile-step', action='store_true', help='ncu helper: 1 warm-up, ONE step between cudaProfilerStart/Stop, no JSON')
     ap.add_argument('--no-graph', action='store_true', help='run the recon iterations eagerly instead of as CUDA graphs')
     ap.add_argument('--recon', default='dp', choices=['dp', 'replicated'], help='N > 1: ray-data-parallel reconstruction (default) or replicated + broadcast')
+    ap.add_argument('--no-lpips', action='store_true', help='A/B: drop the LPIPS patch term from the reconstruction objective (patch_rgb_weight 0)')
     ap.add_argument('--no-gpu-baseline', action='store_true', help='skip the stock-PyTorch + reference-kernel GPU baseline leg (saves ~1 min)')
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON: libraries that chat on fd 1 (NCCL prints its version banner there from inside

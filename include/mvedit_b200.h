@@ -117,7 +117,8 @@ int mve_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int bi
 /* C[M,N] = act(A[M,K] . B[N,K]^T + bias[N] + row_bias[row / rows_per_group, N]) * alpha + residual[M,N]
  * A, B, C, residual bf16 (lda/ldb/ldc/ldr in elements, multiples of 8); bias/row_bias f32 or NULL (row_bias row stride ldrb, 0 = N); K % 64 == 0.
  * act: 0 none, 1 SiLU, 2 GELU(erf), 3 GEGLU: every 256 columns of B hold [128 value | 128 gate] rows of a diffusers GEGLU
- * projection and C gets the N/2 products value * gelu(gate) (ldc >= N/2; no row_bias / residual; N % 256 == 0).
+ * projection and C gets the N/2 products value * gelu(gate) (ldc >= N/2; no row_bias / residual; N % 256 == 0);
+ * 4 ReLU; 5 ReLU backward gate: C = residual > 0 ? (acc + bias) * alpha : 0 (residual = the forward activation, not added).
  * Replaces torch.nn.functional.linear / 1x1 conv (cuBLAS) on the UNet path. */
 int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N, uint32_t K,
                   uint32_t lda, uint32_t ldb, uint32_t ldc,
@@ -258,19 +259,45 @@ int mve_im2col3x3s2_bf16(const void* x, void* y, uint32_t B, uint32_t H, uint32_
  * attention (one head, d = 512: lib/pipelines/mvedit_3d_pipeline.py:1119-1120,1258-1263 -> diffusers Attention) runs as
  * score GEMM -> this -> value GEMM. */
 int mve_softmax_rows_bf16(const void* x, void* y, uint32_t rows, uint32_t cols, uint32_t ldx, uint32_t ldy, float scale, void* stream);
+/* ---- LPIPS(net='vgg') patch loss of the reconstruction objective, forward AND gradient w.r.t. the rendered patch
+ * (lib/models/losses/lpips_loss.py:14-43 -> lpips==0.1.4 LPIPS.forward; lib/pipelines/mvedit_3d_pipeline.py:611-617,796-801).
+ * The 13 VGG16 convolutions and their 13 input-gradient convolutions are mve_conv3x3_bf16 calls (act 4 = ReLU; act 5 = ReLU
+ * backward gate: out = residual > 0 ? acc * alpha : 0, residual = the forward activation); the rest of the graph is these kernels.
+ *   prep:        pred / target [n_pix_each,3] f32 in [0,1] -> out [2*n_pix_each,64] bf16 = ((2x-1) - shift) / scale, channels 3.. zero
+ *   input_grad:  g64 [n_pix,64] bf16 (gradient of prep's output, pred half) -> g_pred [n_pix,3] f32 (times 2 / scale)
+ *   maxpool2x2:  x [B,H,W,C] -> y [B,H/2,W/2,C]
+ *   maxpool2x2_relu_backward: g_x [B,H,W,C] = (x > 0) ? g_x + (g_y routed to each window's first maximum) : 0   (in place)
+ *   lpips_layer: feat [2P,HW,C] bf16 (pred images then target images), lin_w [C] f32 >= 0, gscale [P] f32 (d total / d lpips[img]):
+ *                loss[img] += mean_pixels sum_c lin_w[c] (f_p/(|f_p|+1e-10) - f_t/(|f_t|+1e-10))_c^2   (atomicAdd; caller zeroes),
+ *                g_feat [P,HW,C] bf16 = gscale[img] * d loss[img] / d f_p, gated by f_p > 0. */
+int mve_lpips_prep(const float* pred, const float* target, uint32_t n_pix_each, void* out, void* stream);
+int mve_lpips_input_grad(const void* g64, uint32_t n_pix, float* g_pred, void* stream);
+int mve_maxpool2x2_bf16(const void* x, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* y, void* stream);
+int mve_maxpool2x2_relu_backward_bf16(const void* x, const void* g_y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* g_x,
+                                      void* stream);
+int mve_lpips_layer(const void* feat, uint32_t P, uint32_t HW, uint32_t C, const float* lin_w, const float* gscale, float* loss,
+                    void* g_feat, void* stream);
 /* x [B,C,HW] (f32 or bf16) -> y [B,HW,Cpad] bf16, channels >= C zero-filled */
 int mve_nchw_to_nhwc_pad_bf16(const void* x, int x_is_f32, void* y, uint32_t B, uint32_t C, uint32_t HW, uint32_t Cpad, void* stream);
 
 /* Fused objective of one nerf_optim iteration on P patches of ps x ps rays (mvedit_3d_pipeline.py:541-603 without target normals /
  * depths / tonemapping): depth->normals, Lambert shading, L1 rgb, L1 alpha, TV^1.5 normal regulariser, background entropy.
  * Produces the 5 loss terms (total, rgb, alpha, normal_reg, bg-entropy) and d/d(image, weights_sum, depth).
- * w_* are device scalars (schedule dependent).  scratch: mve_nerf_patch_loss_scratch_floats(N) floats. */
+ * w_* are device scalars (schedule dependent).  scratch: mve_nerf_patch_loss_scratch_floats(N) floats.
+ * g_out_extra [N,3] or NULL: the gradient of further terms w.r.t. the shaded, composited rgb (out = image * shading + bg (1 - alpha))
+ * -- the LPIPS patch term (:611-617), evaluated by the caller on mve_nerf_patch_out_rgb's output -- chained through shading /
+ * compositing together with the L1 term. */
 uint32_t mve_nerf_patch_loss_scratch_floats(uint32_t n_rays);
 int mve_nerf_patch_loss(const float* image, const float* alpha, const float* depth, const float* tgt_rgb, const float* tgt_mask,
                         const float* dirs, const float* patch_w, const float* lights, uint32_t n_patches, uint32_t patch_size,
                         int shaded, float ambient, float bg_color, float bg_width, float pixel_loss_weight,
                         const float* w_alpha_mul, const float* w_normal_reg, const float* w_entropy,
-                        float* scratch, float* g_image, float* g_alpha, float* g_depth, float* loss5, void* stream);
+                        float* scratch, float* g_image, float* g_alpha, float* g_depth, float* loss5, const float* g_out_extra,
+                        void* stream);
+/* out_rgb [N,3]: what the pixel and patch losses compare with the target (mvedit_3d_pipeline.py:558-571); same scratch. */
+int mve_nerf_patch_out_rgb(const float* image, const float* alpha, const float* depth, const float* dirs, const float* lights,
+                           uint32_t n_patches, uint32_t patch_size, int shaded, float ambient, float bg_color, float* scratch,
+                           float* out_rgb, void* stream);
 
 /* ---------------------------------------------------------------------------
  * a-5: glue of one nerf_optim iteration (lib/pipelines/mvedit_3d_pipeline.py:507-536, :631-633)

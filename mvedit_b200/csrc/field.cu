@@ -385,8 +385,12 @@ __global__ void __launch_bounds__(BW_T, 3) k_field_bwd_mma(const float* __restri
         });
         // ---- scatter d(enc) into the table gradient (+ optional d/dx), one level per trip
         float gx0 = 0.f, gx1 = 0.f, gx2 = 0.f;
+        // warps start at different levels: the coarse levels have few entries (17^3 at level 0) and the L2 atomic unit serialises
+        // per address, so warps that walk the levels in lockstep queue up on the same lines
+        const int rot = (int)(tile % (uint32_t)L);
 #pragma unroll 1
-        for (int l = 0; l < L; l++) {
+        for (int lq = 0; lq < L; lq++) {
+            const int l = lq + rot < L ? lq + rot : lq + rot - L;
             const float ga = stage[(2 * l) * LD + lane], gb2 = stage[(2 * l + 1) * LD + lane];
             if (live && (ga != 0.f || gb2 != 0.f)) {
                 const Cell cl = locate(x0, x1, x2, lv.scale[l]);

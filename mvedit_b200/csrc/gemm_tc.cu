@@ -44,7 +44,9 @@ struct GemmParams {
     uint32_t rows_per_group, ldrb;
     const __nv_bfloat16* residual;  // [M, ldr] or null
     uint32_t ldr;
-    int act;                        // 0 none, 1 SiLU, 2 GELU(erf), 3 GEGLU (tile = [BN/2 value | BN/2 gate] columns -> BN/2 outputs)
+    int act;                        // 0 none, 1 SiLU, 2 GELU(erf), 3 GEGLU (tile = [BN/2 value | BN/2 gate] columns -> BN/2 outputs),
+                                    // 4 ReLU, 5 ReLU-backward gate: out = residual > 0 ? (acc + bias) * alpha : 0 (residual = the forward
+                                    // activation; nothing is added)
     float alpha;                    // out = act(acc + bias + row_bias) * alpha + residual
     // conv geometry (MODE 1)
     uint32_t H, W, cin_chunks;
@@ -68,6 +70,7 @@ struct Cfg {
 __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == 1) return v / (1.0f + __expf(-v));
     if (act == 2) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    if (act == 4) return fmaxf(v, 0.0f);
     return v;
 }
 
@@ -241,7 +244,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
                                 const uint4 r4 = *reinterpret_cast<const uint4*>(res + g * 8);
                                 const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r4);
 #pragma unroll
-                                for (int i = 0; i < 4; i++) { const float2 t = __bfloat1622float2(r2[i]); f[2 * i] += t.x; f[2 * i + 1] += t.y; }
+                                for (int i = 0; i < 4; i++) {
+                                    const float2 t = __bfloat1622float2(r2[i]);
+                                    if (p.act == 5) { f[2 * i] = t.x > 0.f ? f[2 * i] : 0.f; f[2 * i + 1] = t.y > 0.f ? f[2 * i + 1] : 0.f; }
+                                    else { f[2 * i] += t.x; f[2 * i + 1] += t.y; }
+                                }
                             }
                             uint4 o;
                             __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
                             if (p.bias) x += p.bias[col0 + i];
                             if (rb) x += rb[col0 + i];
                             x = act_apply(x, p.act) * p.alpha;
-                            if (res) x += __bfloat162float(res[i]);
+                            if (res) x = p.act == 5 ? (__bfloat162float(res[i]) > 0.f ? x : 0.f) : x + __bfloat162float(res[i]);
                             out[i] = __float2bfloat16(x);
                         }
                     }
@@ -298,7 +305,13 @@ struct TileCfg { int bn, mt, acc; };
 TileCfg pick_tile(uint32_t M, uint32_t N, uint32_t K, int act) {
     static int tall = -1;
     if (tall < 0) { const char* e = getenv("MVE_GEMM_TALL"); tall = (e && e[0] == '0') ? 0 : 1; }
-    const int bn = pick_bn(N);
+    int bn = pick_bn(N);
+    if (act != 3) {
+        // few-tile problems (the 8^2 .. 32^2 levels of the LPIPS VGG, a patch at a time): narrower tiles put more SMs to work
+        const uint32_t mt_ = (M + BM - 1) / BM;
+        if (bn == 256 && mt_ * ((N + 255) / 256) * 4 <= (uint32_t)kNumSM) bn = 128;
+        if (bn == 128 && N % 64 == 0 && mt_ * ((N + 127) / 128) * 4 <= (uint32_t)kNumSM) bn = 64;
+    }
     if (!tall || act == 3 || M < 148u * 256u) return {bn, 1, 2};
     if (bn == 128 && N % 128 == 0) return {128, 2, 2};
     if (bn == 160 && K >= 1024) return {160, 2, 1};

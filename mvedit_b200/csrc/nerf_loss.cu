@@ -45,6 +45,8 @@ struct LossParams {
     float* g_alpha;      // [N]
     float* g_depth;      // [N]
     float* loss;         // [5] total, pixel_rgb, alpha, normal_reg, entropy(background part)   (zeroed by the launcher)
+    const float* g_out_extra;   // [N,3] or NULL: gradient of further terms w.r.t. the composited / shaded rgb (the LPIPS patch loss)
+    float* out_rgb;             // [N,3] (k_out_rgb only): image * shading + bg_color (1 - alpha), what pixel and patch losses see
 };
 
 struct V3 { float x, y, z; };
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(256) k_terms(const LossParams p) {
             const float out = C * s + p.bg_color * (1 - A);
             const float diff = out - p.tgt_rgb[i * 3 + c];
             l_pix += fabsf(diff) * w * c_pix;
-            const float g = sgn(diff) * w * c_pix;
+            const float g = sgn(diff) * w * c_pix + (p.g_out_extra ? p.g_out_extra[i * 3 + c] : 0.f);
             p.g_image[i * 3 + c] = g * s;
             ds += g * C;
             dsum += g;
@@ -185,6 +187,22 @@ __global__ void __launch_bounds__(256) k_terms(const LossParams p) {
         atomicAdd(&p.loss[1], l_pix); atomicAdd(&p.loss[2], l_alpha); atomicAdd(&p.loss[3], l_tv); atomicAdd(&p.loss[4], l_ent);
         atomicAdd(&p.loss[0], l_pix + l_alpha + l_tv + l_ent);
     }
+}
+
+// the rendered rgb the losses compare with the target (mvedit_3d_pipeline.py:558-571): the input of the LPIPS patch term
+__global__ void __launch_bounds__(256) k_out_rgb(const LossParams p) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x, N = p.P * p.ps * p.ps;
+    if (i >= N) return;
+    const uint32_t patch = i / (p.ps * p.ps);
+    float s = 1.0f;
+    if (p.shaded) {
+        const float lcv = p.lights[patch * 3] * (p.normals[i * 3] * 2 - 1) + p.lights[patch * 3 + 1] * (-p.normals[i * 3 + 1] * 2 + 1) +
+                          p.lights[patch * 3 + 2] * (-p.normals[i * 3 + 2] * 2 + 1);
+        s = fmaxf(lcv, 0.f) * (1 - p.ambient) + p.ambient;
+    }
+    const float bg = p.bg_color * (1 - p.alpha[i]);
+#pragma unroll
+    for (int c = 0; c < 3; c++) p.out_rgb[i * 3 + c] = p.image[i * 3 + c] * s + bg;
 }
 
 __device__ __forceinline__ void add3(float* dst, uint32_t i, V3 g) {
@@ -251,7 +269,7 @@ int mve_nerf_patch_loss(const float* image, const float* alpha, const float* dep
                         const float* dirs, const float* patch_w, const float* lights, uint32_t n_patches, uint32_t patch_size, int shaded,
                         float ambient, float bg_color, float bg_width, float pixel_loss_weight, const float* w_alpha_mul,
                         const float* w_normal_reg, const float* w_entropy, float* scratch, float* g_image, float* g_alpha, float* g_depth,
-                        float* loss5, void* stream) {
+                        float* loss5, const float* g_out_extra, void* stream) {
     const uint32_t N = n_patches * patch_size * patch_size;
     if (N == 0) return 0;
     MVE_ARG(patch_size >= 2, "nerf_patch_loss: patch_size must be >= 2");
@@ -261,7 +279,7 @@ int mve_nerf_patch_loss(const float* image, const float* alpha, const float* dep
     p.lights = lights; p.P = n_patches; p.ps = patch_size; p.shaded = shaded; p.ambient = ambient; p.bg_color = bg_color; p.bg_width = bg_width;
     p.w_alpha_mul = w_alpha_mul; p.w_normal_reg = w_normal_reg; p.w_entropy = w_entropy; p.pixel_loss_weight = pixel_loss_weight;
     p.normals = scratch; p.fgw = scratch + (size_t)N * 3; p.d_normals = scratch + (size_t)N * 4; p.d_xyz = scratch + (size_t)N * 7;
-    p.g_image = g_image; p.g_alpha = g_alpha; p.g_depth = g_depth; p.loss = loss5;
+    p.g_image = g_image; p.g_alpha = g_alpha; p.g_depth = g_depth; p.loss = loss5; p.g_out_extra = g_out_extra;
     MVE_CUDA(cudaMemsetAsync(p.d_normals, 0, (size_t)N * 6 * sizeof(float), s));
     MVE_CUDA(cudaMemsetAsync(loss5, 0, 5 * sizeof(float), s));
     const uint32_t grid = cdiv(N, 256);
@@ -270,6 +288,24 @@ int mve_nerf_patch_loss(const float* image, const float* alpha, const float* dep
     k_normal_bwd<<<grid, 256, 0, s>>>(p);
     k_finish<<<grid, 256, 0, s>>>(p);
     MVE_CHECK_LAUNCH("mve_nerf_patch_loss");
+    return 0;
+}
+
+int mve_nerf_patch_out_rgb(const float* image, const float* alpha, const float* depth, const float* dirs, const float* lights,
+                           uint32_t n_patches, uint32_t patch_size, int shaded, float ambient, float bg_color, float* scratch,
+                           float* out_rgb, void* stream) {
+    const uint32_t N = n_patches * patch_size * patch_size;
+    if (N == 0) return 0;
+    MVE_ARG(patch_size >= 2, "nerf_patch_out_rgb: patch_size must be >= 2");
+    cudaStream_t s = (cudaStream_t)stream;
+    LossParams p{};
+    p.image = image; p.alpha = alpha; p.depth = depth; p.dirs = dirs; p.lights = lights; p.P = n_patches; p.ps = patch_size;
+    p.shaded = shaded; p.ambient = ambient; p.bg_color = bg_color;
+    p.normals = scratch; p.fgw = scratch + (size_t)N * 3; p.out_rgb = out_rgb;
+    const uint32_t grid = cdiv(N, 256);
+    if (shaded) k_normals<<<grid, 256, 0, s>>>(p);
+    k_out_rgb<<<grid, 256, 0, s>>>(p);
+    MVE_CHECK_LAUNCH("mve_nerf_patch_out_rgb");
     return 0;
 }
 

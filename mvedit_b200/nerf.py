@@ -164,7 +164,7 @@ def patch_loss(image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps
     call('mve_nerf_patch_loss', ptr(f(image).view(N, 3)), ptr(f(alpha).view(N)), ptr(f(depth).view(N)), ptr(f(tgt_rgb)), ptr(f(tgt_mask)),
          ptr(f(dirs)), ptr(f(patch_w)), ptr(f(lights)), c_u32(P), c_u32(ps), c_int(int(shaded)), c_f32(ambient), c_f32(bg_color),
          c_f32(bg_width), c_f32(pixel_loss_weight), ptr(w_alpha_mul), ptr(w_normal_reg), ptr(w_entropy), ptr(scratch), ptr(g_image),
-         ptr(g_alpha), ptr(g_depth), ptr(loss5), stream())
+         ptr(g_alpha), ptr(g_depth), ptr(loss5), ptr(None), stream())
     return loss5, g_image, g_alpha, g_depth
 
 
@@ -209,8 +209,12 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
     if tgt_normals is not None or (tgt_depths is not None and depth_weight > 0) or tonemapping is not None:
         raise NotImplementedError('nerf_optim: target normals / depths and tone mapping are not covered by the fused objective kernels '
                                   '(mve_nerf_patch_loss); there is no eager fallback')
-    if patch_rgb_weight > 0 and nerf.patch_loss is not None:
-        raise NotImplementedError('nerf_optim: the LPIPS patch loss (SURVEY.md §8f-2) is not built; pass patch_rgb_weight=0 or patch_loss=None')
+    lpips = nerf.patch_loss if patch_rgb_weight > 0 else None
+    if lpips is not None and not hasattr(lpips, 'loss_and_grad'):
+        raise NotImplementedError('nerf_optim: nerf.patch_loss must be a mvedit_b200.lpips.LPIPSLoss (kernels, no autograd graph); got %r'
+                                  % type(lpips).__name__)
+    if patch_normal_weight > 0 and tgt_normals is not None:
+        raise NotImplementedError('nerf_optim: the high-passed normal patch term needs target normals (normal_model: not built)')
     if not tgt_images.is_cuda:
         raise RuntimeError('mvedit_b200 ops need CUDA tensors (no CPU fallback)')
     ps = nerf.patch_size
@@ -238,7 +242,7 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
     key = (V, render_size, ps, n_sel, bool(is_init), bool(init_shaded), use_graph, float(dt_gamma_scale),
            float(ambient_light), float(bg_width), float(intrinsics_size), id(optimizer), density_bitfield.data_ptr(), id(nerf_code),
            float(nerf.bg_color), float(nerf.pixel_loss.loss_weight), int(dec.sample_capacity), int(dec.max_steps),
-           float(dec.weight_culling_th), bool(dec.mlp_tf32), int(nerf.grid_size), rank, world)
+           float(dec.weight_culling_th), bool(dec.mlp_tf32), int(nerf.grid_size), rank, world, id(lpips))
     cache = nerf.__dict__.setdefault('_recon_programs', collections.OrderedDict())
     prog = cache.get(key) if use_graph else None
     if prog is None:
@@ -247,7 +251,8 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
             img=torch.empty(1, V, render_size, render_size, 3, **f32), msk=torch.empty(1, V, render_size, render_size, 1, **f32),
             R=torch.empty(V, 3, 3, **f32), Tr=torch.empty(V, 3, **f32),
             camw=torch.empty(V, **f32), lights=torch.empty(V, 3, **f32), intr=torch.empty(V, 4, **f32),
-            sc=dict(normal_reg=torch.zeros((), **f32), entropy=torch.zeros((), **f32), alpha_mul=torch.zeros((), **f32)),
+            sc=dict(normal_reg=torch.zeros((), **f32), entropy=torch.zeros((), **f32), alpha_mul=torch.zeros((), **f32),
+                    patch_rgb=torch.zeros((), **f32)),
             inds=torch.zeros(min(n_sel, n_patches_total), dtype=torch.long, device=device), graph=None, vals=None)
         if use_graph:
             cache[key] = prog
@@ -268,6 +273,7 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
         prog['sc']['normal_reg'].fill_(float(normal_reg_weight) * 10)
         prog['sc']['entropy'].fill_(float(entropy_weight))
         prog['sc']['alpha_mul'].fill_(5.0 if is_init else 1.0)
+        prog['sc']['patch_rgb'].fill_(float(patch_rgb_weight))
     R, Tr = prog['R'], prog['Tr']
     sc, inds_static = prog['sc'], prog['inds']
     decoder_training_prev = dec.training
@@ -284,7 +290,8 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
         prog.update(rays_o=torch.empty(1, n_loc, 3, **f32), rays_d=torch.empty(1, n_loc, 3, **f32), pdirs=torch.empty(n, 3, **f32),
                     trgb=torch.empty(n, 3, **f32), tmsk=torch.empty(n, **f32), pw=torch.empty(P, **f32), pl=torch.empty(P, 3, **f32),
                     dtg=torch.empty(1, **f32), scratch=torch.empty(n * 10, **f32), g_img=torch.empty(n, 3, **f32),
-                    g_a=torch.empty(n, **f32), g_d=torch.empty(n, **f32), loss5=torch.empty(5, **f32))
+                    g_a=torch.empty(n, **f32), g_d=torch.empty(n, **f32), loss5=torch.empty(5, **f32), out_rgb=torch.empty(n, 3, **f32),
+                    lp=torch.zeros((), **f32))
     b = prog
 
     def iteration():
@@ -307,11 +314,20 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
             f_img, f_a, f_d = full[:, :3].contiguous(), full[:, 3].contiguous(), full[:, 4].contiguous()
         else:
             f_img, f_a, f_d = image.detach(), alpha.detach(), depth.detach()
-        # 4. objective on the full patches: loss terms and d/d(image, alpha, depth) in four launches (replicated: 16 384 pixels)
+        shaded = int((not is_init) or init_shaded)
+        # 4a. LPIPS patch term (:611-617) on the shaded, composited rgb: VGG16 forward over [rendered ; target] patches and the
+        # gradient back to the rendered pixels, ~42 launches of the conv / lpips kernels (mvedit_b200.lpips), no autograd graph
+        g_extra = None
+        if lpips is not None:
+            call('mve_nerf_patch_out_rgb', ptr(f_img), ptr(f_a), ptr(f_d), ptr(b['pdirs']), ptr(b['pl']), c_u32(P), c_u32(ps), c_int(shaded),
+                 c_f32(ambient_light), c_f32(float(nerf.bg_color)), ptr(b['scratch']), ptr(b['out_rgb']), stream())
+            lp, g_extra, _ = lpips.loss_and_grad(b['out_rgb'].view(P, ps, ps, 3), b['trgb'].view(P, ps, ps, 3), b['pw'], sc['patch_rgb'])
+            b['lp'].copy_(lp)
+        # 4b. objective on the full patches: loss terms and d/d(image, alpha, depth) in four launches (replicated: 16 384 pixels)
         call('mve_nerf_patch_loss', ptr(f_img), ptr(f_a), ptr(f_d), ptr(b['trgb']), ptr(b['tmsk']), ptr(b['pdirs']), ptr(b['pw']), ptr(b['pl']),
-             c_u32(P), c_u32(ps), c_int(int((not is_init) or init_shaded)), c_f32(ambient_light), c_f32(float(nerf.bg_color)), c_f32(bg_width),
+             c_u32(P), c_u32(ps), c_int(shaded), c_f32(ambient_light), c_f32(float(nerf.bg_color)), c_f32(bg_width),
              c_f32(float(nerf.pixel_loss.loss_weight)), ptr(sc['alpha_mul']), ptr(sc['normal_reg']), ptr(sc['entropy']), ptr(b['scratch']),
-             ptr(b['g_img']), ptr(b['g_a']), ptr(b['g_d']), ptr(b['loss5']), stream())
+             ptr(b['g_img']), ptr(b['g_a']), ptr(b['g_d']), ptr(b['loss5']), ptr(g_extra), stream())
         if world > 1:
             sel = lambda t: t.view(P, ps, ps, -1)[:, row_lo:row_hi].reshape(n_loc, -1)
             g_img, g_a, g_d = sel(b['g_img']), sel(b['g_a']).view(-1), sel(b['g_d']).view(-1)
@@ -376,7 +392,8 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
                 vals = vals_static
             if debug:
                 v = [float(x) for x in vals]
-                log.append(dict(loss=v[0], pixel_rgb=v[1], alpha=v[2], normal_reg=v[3], entropy=v[4]))
+                lpv = float(prog['lp']) if lpips is not None else 0.0
+                log.append(dict(loss=v[0] + lpv, pixel_rgb=v[1], alpha=v[2], normal_reg=v[3], entropy=v[4], patch_rgb=lpv))
     dec.grad_sink = None
     dec.note_sample_overflow()
     dec.train(decoder_training_prev)

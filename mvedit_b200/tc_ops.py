@@ -9,7 +9,7 @@ import ctypes
 
 from ._lib import call, ptr, raw_ptr, stream, c_int, c_u32, c_f32
 
-ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2, 'geglu': 3}
+ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2, 'geglu': 3, 'relu': 4, 'relu_gate': 5}
 
 
 def gemm(a, w, bias=None, row_bias=None, rows_per_group=0, residual=None, act=None, alpha=1.0, out=None):
