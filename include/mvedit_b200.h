@@ -216,10 +216,14 @@ int mve_render_last_sample_count(uint64_t* host_out);
  * weights_sum / depth [V,h,w], image [V,h,w,3] are mve_render_rays' outputs; intrinsics [V,4] at the render size; lights [V,3].
  * out_images / out_depths: bf16 [V,3,h,w] (NCHW), both clamped to [0,1]; reduce_scratch: [V,2] i32 of device scratch.
  * out_normals_fg (optional): f32 [V,h,w,3], depth_to_normal(depth_fg) in the opengl [0,1] encoding (BaseNeRF.render's
- * compute_normal output, base_nerf.py:549-553).  With out_images == NULL only the normals are produced (lights / scratch unused). */
+ * compute_normal output, base_nerf.py:549-553).  With out_images == NULL only the normals are produced (lights / scratch unused).
+ * tonemap_knots (HOST array [lut_x (n) | lut_y (n)], 2 <= n <= 32, or NULL): the reference's Tonemapping module
+ * (lib/models/decoders/tonemapping.py:5-52) -- shading is then applied in tone-mapped space,
+ * lut(inverse_lut(rgb / alpha) + log2(shading)) * alpha + bg (1 - alpha) (mvedit_3d_pipeline.py:1377-1384). */
 int mve_shade_views(const float* weights_sum, const float* depth, const float* image, const float* intrinsics, const float* lights,
                     uint32_t V, uint32_t h, uint32_t w, float ambient, float bg_color, float far_depth, float alpha_clip, float eps,
-                    int32_t* reduce_scratch, void* out_images, void* out_depths, float* out_normals_fg, void* stream);
+                    int32_t* reduce_scratch, void* out_images, void* out_depths, float* out_normals_fg,
+                    const float* tonemap_knots, uint32_t tonemap_n, void* stream);
 
 /* Weight culling of the training branch (base_volume_renderer.py:222-246): keep samples with weight > th, compact xyzs/ts,
  * rebuild rays (offset,count); *counter (zeroed by the caller) receives the kept total.  Rays whose kept samples would not fit
@@ -286,18 +290,20 @@ int mve_nchw_to_nhwc_pad_bf16(const void* x, int x_is_f32, void* y, uint32_t B, 
  * w_* are device scalars (schedule dependent).  scratch: mve_nerf_patch_loss_scratch_floats(N) floats.
  * g_out_extra [N,3] or NULL: the gradient of further terms w.r.t. the shaded, composited rgb (out = image * shading + bg (1 - alpha))
  * -- the LPIPS patch term (:611-617), evaluated by the caller on mve_nerf_patch_out_rgb's output -- chained through shading /
- * compositing together with the L1 term. */
+ * compositing together with the L1 term.
+ * tonemap_knots / tonemap_n as in mve_shade_views: with shading on, the shaded colour is lut(inverse_lut(image / alpha) + log2(shading))
+ * (mvedit_3d_pipeline.py:564-570) and the gradients follow the piecewise-linear curve. */
 uint32_t mve_nerf_patch_loss_scratch_floats(uint32_t n_rays);
 int mve_nerf_patch_loss(const float* image, const float* alpha, const float* depth, const float* tgt_rgb, const float* tgt_mask,
                         const float* dirs, const float* patch_w, const float* lights, uint32_t n_patches, uint32_t patch_size,
                         int shaded, float ambient, float bg_color, float bg_width, float pixel_loss_weight,
                         const float* w_alpha_mul, const float* w_normal_reg, const float* w_entropy,
                         float* scratch, float* g_image, float* g_alpha, float* g_depth, float* loss5, const float* g_out_extra,
-                        void* stream);
+                        const float* tonemap_knots, uint32_t tonemap_n, void* stream);
 /* out_rgb [N,3]: what the pixel and patch losses compare with the target (mvedit_3d_pipeline.py:558-571); same scratch. */
 int mve_nerf_patch_out_rgb(const float* image, const float* alpha, const float* depth, const float* dirs, const float* lights,
                            uint32_t n_patches, uint32_t patch_size, int shaded, float ambient, float bg_color, float* scratch,
-                           float* out_rgb, void* stream);
+                           float* out_rgb, const float* tonemap_knots, uint32_t tonemap_n, void* stream);
 
 /* ---------------------------------------------------------------------------
  * a-5: glue of one nerf_optim iteration (lib/pipelines/mvedit_3d_pipeline.py:507-536, :631-633)

@@ -13,6 +13,7 @@
 // Covered configuration: tgt_normals None, tgt_depths None, tonemapping None (the text-to-3D recipe benchmarked here); the host
 // keeps the torch chain for the other options.
 #include "common.cuh"
+#include "tonemap.cuh"
 #include "../../include/mvedit_b200.h"
 
 namespace {
@@ -47,6 +48,7 @@ struct LossParams {
     float* loss;         // [5] total, pixel_rgb, alpha, normal_reg, entropy(background part)   (zeroed by the launcher)
     const float* g_out_extra;   // [N,3] or NULL: gradient of further terms w.r.t. the composited / shaded rgb (the LPIPS patch loss)
     float* out_rgb;             // [N,3] (k_out_rgb only): image * shading + bg_color (1 - alpha), what pixel and patch losses see
+    ToneLut tone;               // n > 0 (and shaded): out = lut(inverse_lut(image / alpha) + log2(shading)) * alpha + bg (1 - alpha) (:564-570)
 };
 
 struct V3 { float x, y, z; };
@@ -128,15 +130,32 @@ __global__ void __launch_bounds__(256) k_terms(const LossParams p) {
         }
         const float c_pix = p.pixel_loss_weight * 4.5f / (float)(N * 3);
         float ds = 0.f, dsum = 0.f;
+        const bool tone = p.shaded && p.tone.n > 0;
+        const float Ac = fmaxf(A, 1e-6f), sc = fmaxf(s, 1e-6f), l2s = tone ? log2f(sc) : 0.f;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const float C = p.image[i * 3 + c];
-            const float out = C * s + p.bg_color * (1 - A);
+            float out, k_inv = 0.f, k_lut = 0.f, t = 0.f;
+            if (tone) {
+                t = tone_lut(p.tone, tone_inverse_lut(p.tone, C / Ac, &k_inv) + l2s, &k_lut);
+                out = t * A + p.bg_color * (1 - A);
+            } else {
+                out = C * s + p.bg_color * (1 - A);
+            }
             const float diff = out - p.tgt_rgb[i * 3 + c];
             l_pix += fabsf(diff) * w * c_pix;
             const float g = sgn(diff) * w * c_pix + (p.g_out_extra ? p.g_out_extra[i * 3 + c] : 0.f);
-            p.g_image[i * 3 + c] = g * s;
-            ds += g * C;
+            if (tone) {
+                // out = lut(inv(C / Ac) + log2(sc)) A + bg (1 - A)
+                const float gz = g * A * k_lut;                      // d / d (inverse_lut(.) + log2 s)
+                p.g_image[i * 3 + c] = gz * k_inv / Ac;
+                if (s > 1e-6f) ds += gz / (sc * 0.6931471805599453f);
+                gA += g * t;
+                if (A > 1e-6f) gA += -gz * k_inv * C / (Ac * Ac);
+            } else {
+                p.g_image[i * 3 + c] = g * s;
+                ds += g * C;
+            }
             dsum += g;
         }
         gA += -p.bg_color * dsum;
@@ -200,9 +219,14 @@ __global__ void __launch_bounds__(256) k_out_rgb(const LossParams p) {
                           p.lights[patch * 3 + 2] * (-p.normals[i * 3 + 2] * 2 + 1);
         s = fmaxf(lcv, 0.f) * (1 - p.ambient) + p.ambient;
     }
-    const float bg = p.bg_color * (1 - p.alpha[i]);
+    const float A = p.alpha[i], bg = p.bg_color * (1 - A);
 #pragma unroll
-    for (int c = 0; c < 3; c++) p.out_rgb[i * 3 + c] = p.image[i * 3 + c] * s + bg;
+    for (int c = 0; c < 3; c++) {
+        const float C = p.image[i * 3 + c];
+        p.out_rgb[i * 3 + c] = (p.shaded && p.tone.n > 0)
+            ? tone_lut(p.tone, tone_inverse_lut(p.tone, C / fmaxf(A, 1e-6f)) + log2f(fmaxf(s, 1e-6f))) * A + bg
+            : C * s + bg;
+    }
 }
 
 __device__ __forceinline__ void add3(float* dst, uint32_t i, V3 g) {
@@ -269,7 +293,7 @@ int mve_nerf_patch_loss(const float* image, const float* alpha, const float* dep
                         const float* dirs, const float* patch_w, const float* lights, uint32_t n_patches, uint32_t patch_size, int shaded,
                         float ambient, float bg_color, float bg_width, float pixel_loss_weight, const float* w_alpha_mul,
                         const float* w_normal_reg, const float* w_entropy, float* scratch, float* g_image, float* g_alpha, float* g_depth,
-                        float* loss5, const float* g_out_extra, void* stream) {
+                        float* loss5, const float* g_out_extra, const float* tonemap_knots, uint32_t tonemap_n, void* stream) {
     const uint32_t N = n_patches * patch_size * patch_size;
     if (N == 0) return 0;
     MVE_ARG(patch_size >= 2, "nerf_patch_loss: patch_size must be >= 2");
@@ -280,6 +304,7 @@ int mve_nerf_patch_loss(const float* image, const float* alpha, const float* dep
     p.w_alpha_mul = w_alpha_mul; p.w_normal_reg = w_normal_reg; p.w_entropy = w_entropy; p.pixel_loss_weight = pixel_loss_weight;
     p.normals = scratch; p.fgw = scratch + (size_t)N * 3; p.d_normals = scratch + (size_t)N * 4; p.d_xyz = scratch + (size_t)N * 7;
     p.g_image = g_image; p.g_alpha = g_alpha; p.g_depth = g_depth; p.loss = loss5; p.g_out_extra = g_out_extra;
+    MVE_ARG(fill_tone_lut(p.tone, tonemap_knots, tonemap_n) == 0, "nerf_patch_loss: tone curve needs 2..32 knots");
     MVE_CUDA(cudaMemsetAsync(p.d_normals, 0, (size_t)N * 6 * sizeof(float), s));
     MVE_CUDA(cudaMemsetAsync(loss5, 0, 5 * sizeof(float), s));
     const uint32_t grid = cdiv(N, 256);
@@ -293,7 +318,7 @@ int mve_nerf_patch_loss(const float* image, const float* alpha, const float* dep
 
 int mve_nerf_patch_out_rgb(const float* image, const float* alpha, const float* depth, const float* dirs, const float* lights,
                            uint32_t n_patches, uint32_t patch_size, int shaded, float ambient, float bg_color, float* scratch,
-                           float* out_rgb, void* stream) {
+                           float* out_rgb, const float* tonemap_knots, uint32_t tonemap_n, void* stream) {
     const uint32_t N = n_patches * patch_size * patch_size;
     if (N == 0) return 0;
     MVE_ARG(patch_size >= 2, "nerf_patch_out_rgb: patch_size must be >= 2");
@@ -302,6 +327,7 @@ int mve_nerf_patch_out_rgb(const float* image, const float* alpha, const float* 
     p.image = image; p.alpha = alpha; p.depth = depth; p.dirs = dirs; p.lights = lights; p.P = n_patches; p.ps = patch_size;
     p.shaded = shaded; p.ambient = ambient; p.bg_color = bg_color;
     p.normals = scratch; p.fgw = scratch + (size_t)N * 3; p.out_rgb = out_rgb;
+    MVE_ARG(fill_tone_lut(p.tone, tonemap_knots, tonemap_n) == 0, "nerf_patch_out_rgb: tone curve needs 2..32 knots");
     const uint32_t grid = cdiv(N, 256);
     if (shaded) k_normals<<<grid, 256, 0, s>>>(p);
     k_out_rgb<<<grid, 256, 0, s>>>(p);

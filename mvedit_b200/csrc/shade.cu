@@ -11,6 +11,7 @@
 // and the normalised depth as bf16 NCHW -- the layout the denoiser's hint path takes).
 #include <cstring>
 #include "common.cuh"
+#include "tonemap.cuh"
 #include "../../include/mvedit_b200.h"
 
 namespace {
@@ -28,6 +29,7 @@ struct ShadeParams {
     __nv_bfloat16* out_img; // [V,3,h,w]
     __nv_bfloat16* out_dep; // [V,3,h,w]
     float* out_nrm;         // [V,h,w,3] optional: normal_fg in the opengl [0,1] encoding
+    ToneLut tone;           // n == 0: linear shading; else shading in tone-mapped space (mvedit_3d_pipeline.py:1377-1384)
 };
 
 __device__ __forceinline__ float dir_norm(const float* K, const uint32_t x, const uint32_t y, float& dx, float& dy) {
@@ -109,7 +111,12 @@ __global__ void __launch_bounds__(256) k_shade_apply(const ShadeParams p) {
     const size_t plane = (size_t)p.h * p.w, o = (size_t)v * 3 * plane + (size_t)y * p.w + x;
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
-        const float val = p.image[i * 3 + ch] * shading + p.bg * (1 - a);
+        float val;
+        if (p.tone.n)
+            val = tone_lut(p.tone, tone_inverse_lut(p.tone, p.image[i * 3 + ch] / fmaxf(a, 1e-6f)) + log2f(fmaxf(shading, 1e-6f))) * a +
+                  p.bg * (1 - a);
+        else
+            val = p.image[i * 3 + ch] * shading + p.bg * (1 - a);
         p.out_img[o + ch * plane] = __float2bfloat16(fminf(fmaxf(__bfloat162float(__float2bfloat16(val)), 0.f), 1.f));
     }
     // normalize_depth
@@ -126,7 +133,8 @@ __global__ void __launch_bounds__(256) k_shade_apply(const ShadeParams p) {
 
 extern "C" int mve_shade_views(const float* weights_sum, const float* depth, const float* image, const float* intrinsics, const float* lights,
                                uint32_t V, uint32_t h, uint32_t w, float ambient, float bg_color, float far_depth, float alpha_clip, float eps,
-                               int32_t* reduce_scratch, void* out_images, void* out_depths, float* out_normals_fg, void* stream) {
+                               int32_t* reduce_scratch, void* out_images, void* out_depths, float* out_normals_fg,
+                               const float* tonemap_knots, uint32_t tonemap_n, void* stream) {
     if (V == 0) return 0;
     MVE_ARG(h >= 2 && w >= 2, "shade_views: h, w >= 2 required");
     MVE_ARG((out_images == nullptr) == (out_depths == nullptr), "shade_views: out_images and out_depths go together");
@@ -134,7 +142,8 @@ extern "C" int mve_shade_views(const float* weights_sum, const float* depth, con
     MVE_ARG(out_images == nullptr || (reduce_scratch != nullptr && lights != nullptr), "shade_views: reduce_scratch [V,2] i32 and lights required");
     cudaStream_t s = (cudaStream_t)stream;
     ShadeParams p{weights_sum, depth, image, intrinsics, lights, V, h, w, ambient, bg_color, far_depth, alpha_clip, eps, reduce_scratch,
-                  (__nv_bfloat16*)out_images, (__nv_bfloat16*)out_depths, out_normals_fg};
+                  (__nv_bfloat16*)out_images, (__nv_bfloat16*)out_depths, out_normals_fg, {}};
+    MVE_ARG(fill_tone_lut(p.tone, tonemap_knots, tonemap_n) == 0, "shade_views: tone curve needs 2..32 knots");
     if (out_images == nullptr) {
         k_shade_apply<<<dim3(cdiv(w, 32), cdiv(h, 8), V), 256, 0, s>>>(p);
         MVE_CHECK_LAUNCH("mve_shade_views");

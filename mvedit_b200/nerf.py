@@ -8,8 +8,9 @@ Same names / arguments / return values; torch is the plumbing, the arithmetic of
 shading is libmvedit_b200.  The op-by-op torch restatements of the reference (geometry helpers, loss modules, the eager objective)
 live in ``oracle/nerf_oracle.py`` as test infrastructure; nothing here falls back to them.
 
-Configurations of the objective that the fused kernels do not cover (target normals / depths, tone mapping, LPIPS patch loss --
-SURVEY.md §8f-2) raise ``NotImplementedError``: there is no eager fallback path.
+The objective covers L1 rgb / alpha, TV-normal, entropy, the LPIPS patch term (``nerf.patch_loss`` = mvedit_b200.lpips.LPIPSLoss) and
+shading in tone-mapped space (``tonemapping``).  Target normals / depths (they need the normal model, a neighbour that is not built)
+raise ``NotImplementedError``: there is no eager fallback path.
 """
 import collections
 import os
@@ -21,6 +22,7 @@ import torch.nn.functional as F
 from .ingp_decoder import iNGPDecoder
 from . import view_shard
 from .optim import FusedAdam
+from .tonemapping import tone_args
 from ._lib import call, ptr, stream, c_int, c_u32, c_f32
 
 
@@ -141,7 +143,8 @@ class BaseNeRF(nn.Module):
             V = K.shape[0]
             nfg = torch.empty(V, h, w, 3, dtype=torch.float32, device=K.device)
             call('mve_shade_views', ptr(ws), ptr(depth), ptr(image), ptr(K), ptr(None), c_u32(V), c_u32(h), c_u32(w), c_f32(0.0),
-                 c_f32(float(bg_color)), c_f32(0.25), c_f32(0.5), c_f32(1e-5), ptr(None), ptr(None), ptr(None), ptr(nfg), stream())
+                 c_f32(float(bg_color)), c_f32(0.25), c_f32(0.5), c_f32(1e-5), ptr(None), ptr(None), ptr(None), ptr(nfg), None, c_u32(0),
+                 stream())
             out_normal_fg = nfg[None]
             a = out_image[..., 3:]
             out_normal = out_normal_fg * a + out_normal_fg.new_tensor(normal_bg) * (1 - a)
@@ -150,7 +153,7 @@ class BaseNeRF(nn.Module):
 
 
 def patch_loss(image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps, shaded, ambient, bg_color, bg_width,
-               pixel_loss_weight, w_alpha_mul, w_normal_reg, w_entropy):
+               pixel_loss_weight, w_alpha_mul, w_normal_reg, w_entropy, tonemapping=None, g_out_extra=None):
     """Fused objective of one nerf_optim iteration on P patches of ps x ps rays (mve_nerf_patch_loss, four launches):
     -> (loss5 = [total, rgb, alpha, normal_reg, background-entropy], d total / d image [N,3], / d alpha [N], / d depth [N]).
     w_* are device scalars (schedule dependent; they must stay valid inside a captured graph)."""
@@ -164,7 +167,7 @@ def patch_loss(image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps
     call('mve_nerf_patch_loss', ptr(f(image).view(N, 3)), ptr(f(alpha).view(N)), ptr(f(depth).view(N)), ptr(f(tgt_rgb)), ptr(f(tgt_mask)),
          ptr(f(dirs)), ptr(f(patch_w)), ptr(f(lights)), c_u32(P), c_u32(ps), c_int(int(shaded)), c_f32(ambient), c_f32(bg_color),
          c_f32(bg_width), c_f32(pixel_loss_weight), ptr(w_alpha_mul), ptr(w_normal_reg), ptr(w_entropy), ptr(scratch), ptr(g_image),
-         ptr(g_alpha), ptr(g_depth), ptr(loss5), ptr(None), stream())
+         ptr(g_alpha), ptr(g_depth), ptr(loss5), ptr(g_out_extra), *tone_args(tonemapping), stream())
     return loss5, g_image, g_alpha, g_depth
 
 
@@ -206,9 +209,10 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
         are all-reduced once per iteration (view_shard.allreduce_grads).
     Returns the per-iteration loss log when ``debug`` else None."""
     device = tgt_images.device
-    if tgt_normals is not None or (tgt_depths is not None and depth_weight > 0) or tonemapping is not None:
-        raise NotImplementedError('nerf_optim: target normals / depths and tone mapping are not covered by the fused objective kernels '
+    if tgt_normals is not None or (tgt_depths is not None and depth_weight > 0):
+        raise NotImplementedError('nerf_optim: target normals / depths are not covered by the fused objective kernels '
                                   '(mve_nerf_patch_loss); there is no eager fallback')
+    tone = tone_args(tonemapping)                     # knots by value into the kernels (static: safe inside the captured graph)
     lpips = nerf.patch_loss if patch_rgb_weight > 0 else None
     if lpips is not None and not hasattr(lpips, 'loss_and_grad'):
         raise NotImplementedError('nerf_optim: nerf.patch_loss must be a mvedit_b200.lpips.LPIPSLoss (kernels, no autograd graph); got %r'
@@ -242,7 +246,8 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
     key = (V, render_size, ps, n_sel, bool(is_init), bool(init_shaded), use_graph, float(dt_gamma_scale),
            float(ambient_light), float(bg_width), float(intrinsics_size), id(optimizer), density_bitfield.data_ptr(), id(nerf_code),
            float(nerf.bg_color), float(nerf.pixel_loss.loss_weight), int(dec.sample_capacity), int(dec.max_steps),
-           float(dec.weight_culling_th), bool(dec.mlp_tf32), int(nerf.grid_size), rank, world, id(lpips))
+           float(dec.weight_culling_th), bool(dec.mlp_tf32), int(nerf.grid_size), rank, world, id(lpips),
+           None if tonemapping is None else tuple(tonemapping.knots()[0]))
     cache = nerf.__dict__.setdefault('_recon_programs', collections.OrderedDict())
     prog = cache.get(key) if use_graph else None
     if prog is None:
@@ -320,14 +325,14 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
         g_extra = None
         if lpips is not None:
             call('mve_nerf_patch_out_rgb', ptr(f_img), ptr(f_a), ptr(f_d), ptr(b['pdirs']), ptr(b['pl']), c_u32(P), c_u32(ps), c_int(shaded),
-                 c_f32(ambient_light), c_f32(float(nerf.bg_color)), ptr(b['scratch']), ptr(b['out_rgb']), stream())
+                 c_f32(ambient_light), c_f32(float(nerf.bg_color)), ptr(b['scratch']), ptr(b['out_rgb']), *tone, stream())
             lp, g_extra, _ = lpips.loss_and_grad(b['out_rgb'].view(P, ps, ps, 3), b['trgb'].view(P, ps, ps, 3), b['pw'], sc['patch_rgb'])
             b['lp'].copy_(lp)
         # 4b. objective on the full patches: loss terms and d/d(image, alpha, depth) in four launches (replicated: 16 384 pixels)
         call('mve_nerf_patch_loss', ptr(f_img), ptr(f_a), ptr(f_d), ptr(b['trgb']), ptr(b['tmsk']), ptr(b['pdirs']), ptr(b['pw']), ptr(b['pl']),
              c_u32(P), c_u32(ps), c_int(shaded), c_f32(ambient_light), c_f32(float(nerf.bg_color)), c_f32(bg_width),
              c_f32(float(nerf.pixel_loss.loss_weight)), ptr(sc['alpha_mul']), ptr(sc['normal_reg']), ptr(sc['entropy']), ptr(b['scratch']),
-             ptr(b['g_img']), ptr(b['g_a']), ptr(b['g_d']), ptr(b['loss5']), ptr(g_extra), stream())
+             ptr(b['g_img']), ptr(b['g_a']), ptr(b['g_d']), ptr(b['loss5']), ptr(g_extra), *tone, stream())
         if world > 1:
             sel = lambda t: t.view(P, ps, ps, -1)[:, row_lo:row_hi].reshape(n_loc, -1)
             g_img, g_a, g_d = sel(b['g_img']), sel(b['g_a']).view(-1), sel(b['g_d']).view(-1)

@@ -26,6 +26,7 @@ from .nerf import nerf_optim
 from . import view_shard
 from .schedulers import EulerAncestralScheduler, DPMSolverMultistepScheduler, DDIMScheduler      # noqa: F401 (re-exported)
 from ._lib import call, ptr, stream, c_u32, c_f32
+from .tonemapping import tone_args
 
 
 class MVEdit3DStep(Adapter3DMixin):
@@ -34,9 +35,14 @@ class MVEdit3DStep(Adapter3DMixin):
     def __init__(self, unet, controlnet, nerf, scheduler, tonemapping=None, normal_bg=(0.5, 0.5, 1.0), vae=None, segmentation=None):
         self.unet, self.controlnet, self.nerf, self.scheduler = unet, controlnet, nerf, scheduler
         self.vae, self.segmentation = vae, segmentation
-        if tonemapping is not None:
-            raise NotImplementedError('tone mapping (lib/core/utils/tonemapping.py) is not built: the fused shading kernels assume None')
-        self.tonemapping = None
+        # a mvedit_b200.tonemapping.Tonemapping (or any module with its lut_x / lut_y buffers): shading then happens in tone-mapped
+        # space inside the fused objective and shading kernels (mvedit_3d_pipeline.py:564-570, :1377-1384)
+        if tonemapping is not None and not hasattr(tonemapping, 'knots'):
+            from .tonemapping import Tonemapping
+            tm = Tonemapping(lut_steps=tonemapping.lut_x.numel())
+            tm.load_state_dict({'lut_x': tonemapping.lut_x.detach().float().cpu(), 'lut_y': tonemapping.lut_y.detach().float().cpu()})
+            tonemapping = tm
+        self.tonemapping = tonemapping
         self.normal_bg = list(normal_bg)
 
     # ------------------------------------------------------------------ decode + masks (mvedit_3d_pipeline.py:1258-1266)
@@ -77,7 +83,7 @@ class MVEdit3DStep(Adapter3DMixin):
         scratch = torch.empty(V, 2, dtype=torch.int32, device=dev)
         call('mve_shade_views', ptr(ws), ptr(depth), ptr(image), ptr(K), ptr(cam_lights.float().contiguous()), c_u32(V), c_u32(render_size),
              c_u32(render_size), c_f32(float(ambient_light)), c_f32(float(nerf.bg_color)), c_f32(0.25), c_f32(0.5), c_f32(1e-5),
-             ptr(scratch), ptr(images), ptr(depths), ptr(None), stream())
+             ptr(scratch), ptr(images), ptr(depths), ptr(None), *tone_args(self.tonemapping), stream())
         return images, depths
 
     # ------------------------------------------------------------------ one loop iteration (t != None)

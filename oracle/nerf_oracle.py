@@ -109,6 +109,43 @@ def _weighted(loss, weight=None, avg_factor=None):
     return loss.mean() if avg_factor is None else loss.sum() / avg_factor
 
 
+class Tonemapping(nn.Module):
+    """lib/models/decoders/tonemapping.py:5-52: 16 knots of x -> sigmoid(c (x + e)) g_s + c (x + e) g_l + b on a log2-exposure axis;
+    ``lut`` / ``inverse_lut`` interpolate linearly between the knots (bucketize right=True, index clamped to [1, n-1])."""
+
+    def __init__(self, exposure=0.0, contrast=0.953, bias=0.088, sigmoid_gain=0.943, log_gain=0.011, lut_logx_min=-9, lut_logx_max=3,
+                 lut_steps=16):
+        super().__init__()
+        self.p = (exposure, contrast, bias, sigmoid_gain, log_gain)
+        self.register_buffer('lut_x', torch.linspace(lut_logx_min, lut_logx_max, lut_steps))
+        self.register_buffer('lut_y', self.smooth_forward(self.lut_x))
+
+    def smooth_forward(self, x, input_mode='log'):
+        e, c, b, gs, gl = self.p
+        if input_mode == 'linear':
+            x = x.clamp(min=1e-6).log2()
+        x = (x + e) * c
+        return x.sigmoid() * gs + x * gl + b
+
+    @staticmethod
+    def _pw(v, a, b):
+        i = torch.bucketize(v, a, right=True).clamp(min=1, max=len(a) - 1)
+        t = (v - a[i - 1]) / (a[i] - a[i - 1])
+        return b[i - 1] + (b[i] - b[i - 1]) * t
+
+    def lut(self, x, input_mode='log'):
+        dt = x.dtype
+        x = x.to(self.lut_x.dtype)
+        if input_mode == 'linear':
+            x = x.clamp(min=1e-6).log2()
+        return self._pw(x, self.lut_x, self.lut_y).to(dt)
+
+    def inverse_lut(self, y, output_mode='log'):
+        dt = y.dtype
+        x = self._pw(y.to(self.lut_y.dtype), self.lut_y, self.lut_x)
+        return (torch.exp2(x) if output_mode == 'linear' else x).to(dt)
+
+
 class L1LossMod(nn.Module):
     """pixelwise_loss.py:9-35."""
 
@@ -492,7 +529,7 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
                patch_normal_weight, alpha_soften, normal_reg_weight, entropy_weight, nerf_code, density_grid, density_bitfield,
                render_size, intrinsics, intrinsics_size, camera_poses, cam_weights, cam_lights, patch_size, is_init, bg_width,
                ambient_light, dt_gamma_scale, init_shaded, alpha_blur_std=1.5, debug=False, tgt_depths=None, depth_weight=0.0,
-               normal_bg=(0.5, 0.5, 1.0), raybatch_inds=None, march_noises=None, grid_noises=None):
+               normal_bg=(0.5, 0.5, 1.0), raybatch_inds=None, march_noises=None, grid_noises=None, tonemapping=None):
     """The reference's reconstruction loop, term by term.  ``raybatch_inds`` / ``march_noises`` /
     ``grid_noises`` (lists, one entry per iteration / occupancy refresh) replace the internal random draws for parity runs."""
     loss_tv = TVLoss(loss_weight=1.0, power=1.5)
@@ -562,7 +599,11 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
                 out_normals_fg_opencv = torch.cat([out_normals_fg[..., :1] * 2 - 1, -out_normals_fg[..., 1:3] * 2 + 1], dim=-1)
                 nerf_shading = ((target_lights[..., None, :] @ out_normals_fg_opencv[..., :, None]).clamp(min=0)
                                 * (1 - ambient_light) + ambient_light).squeeze(-1)
-                out_rgbs = out_rgbs * nerf_shading + nerf.bg_color * (1 - out_alphas)
+                if tonemapping is None:
+                    out_rgbs = out_rgbs * nerf_shading + nerf.bg_color * (1 - out_alphas)
+                else:                                                                             # :564-570
+                    out_rgbs = tonemapping.lut(tonemapping.inverse_lut(out_rgbs / out_alphas.clamp(min=1e-6))
+                                               + nerf_shading.clamp(min=1e-6).log2()) * out_alphas + nerf.bg_color * (1 - out_alphas)
             else:
                 out_rgbs = out_rgbs + nerf.bg_color * (1 - out_alphas)
             pixel_rgb_loss = nerf.pixel_loss(out_rgbs.reshape(target_rgbs.size()), target_rgbs, weight=target_w / cam_weights_mean) * 4.5
@@ -596,7 +637,7 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
 
 # ------------------------------------------------------------------------------------------------ render for denoise P2 (:1341-1395)
 def render_views(nerf, density_bitfield, camera_poses, intrinsics, intrinsics_size, render_size, cam_lights, ambient_light,
-                 testmode_dt_gamma_scale, render_bs=6, normal_bg=(0.5, 0.5, 1.0), out_dtype=torch.bfloat16):
+                 testmode_dt_gamma_scale, render_bs=6, normal_bg=(0.5, 0.5, 1.0), out_dtype=torch.bfloat16, tonemapping=None):
     images, alphas, depths = [], [], []
     for pose_batch, intr_batch, light_batch in zip(camera_poses.split(render_bs, dim=0), intrinsics.split(render_bs, dim=0),
                                                    cam_lights.split(render_bs, dim=0)):
@@ -607,7 +648,11 @@ def render_views(nerf, density_bitfield, camera_poses, intrinsics, intrinsics_si
         normal_fg_opencv = torch.cat([normal_fg[..., :1] * 2 - 1, -normal_fg[..., 1:3] * 2 + 1], dim=-1)
         shading = ((light_batch[:, None, None, None, :] @ normal_fg_opencv[..., :, None]).clamp(min=0) * (1 - ambient_light)
                    + ambient_light).squeeze(-1)
-        image = rgba[..., :3] * shading + nerf.bg_color * (1 - rgba[..., 3:])
+        if tonemapping is None:
+            image = rgba[..., :3] * shading + nerf.bg_color * (1 - rgba[..., 3:])
+        else:                                                                                     # :1377-1384
+            image = tonemapping.lut(tonemapping.inverse_lut(rgba[..., :3] / rgba[..., 3:].clamp(min=1e-6))
+                                    + shading.clamp(min=1e-6).log2()) * rgba[..., 3:] + nerf.bg_color * (1 - rgba[..., 3:])
         images.append(image.squeeze(0)); alphas.append(rgba[..., 3:].squeeze(0)); depths.append(depth.squeeze(0))
     images = torch.cat(images, dim=0).to(out_dtype).permute(0, 3, 1, 2).clamp(min=0, max=1)
     alphas, depths = torch.cat(alphas, dim=0), torch.cat(depths, dim=0)

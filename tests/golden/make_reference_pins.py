@@ -4,6 +4,8 @@
 Loaded by path (``import lib`` itself is impossible here: mmcv / mmgen / diffusers / trimesh are absent):
   lib/ops/activation.py                    trunc_exp fwd / bwd                       -> pins oracle/field_oracle.TruncExpFn
   lib/models/architecture/joint_attn.py    CrossImageAttnProcWrapper                 -> pins oracle/unet_oracle.attention(num_cross_attn_imgs=2)
+  lib/models/decoders/tonemapping.py       Tonemapping (lut / inverse_lut / smooth_forward) -> pins oracle/nerf_oracle.Tonemapping and
+                                           mvedit_b200.tonemapping.Tonemapping
   lib/core/diffusion.py                    get_noise_scales                          -> pins oracle/nerf_oracle.get_noise_scales,
                                                                                         mvedit_b200.pipeline scheduler.noise_scales
   lib/core/utils/geometry_utils.py         get_ray_directions / get_rays / depth_to_normal / normalize_depth   (mcubes, skimage stubbed)
@@ -189,6 +191,18 @@ def main():
     dw = torch.rand(2, 1, 6, 6, generator=g)
     out.update(tv_pred=pred.numpy(), tv_tgt=tgt.numpy(), tv_w=dw.numpy(), tv_plain=tv(pred, None, dims=[-2, -1], power=1.5).numpy(),
                tv_full=tv(pred, tgt, dims=[-2, -1], power=1.5, dense_weight=dw).numpy())
+
+    # ---- Tonemapping (lib/models/decoders/tonemapping.py:5-52): the module itself (torch only)
+    tmod = load_by_path('ref_tonemapping', 'lib/models/decoders/tonemapping.py')
+    tm = tmod.Tonemapping()
+    xs = torch.cat([torch.linspace(-11, 5, 97), tm.lut_x, tm.lut_x + 1e-4])            # beyond both ends, and on / next to the knots
+    ys = torch.cat([torch.linspace(-0.1, 1.25, 83), tm.lut_y])
+    alb, shd = torch.rand(5, 7, 3, generator=g), torch.rand(5, 7, 1, generator=g) * 0.8 + 0.2
+    out.update(tm_lut_x=tm.lut_x.numpy(), tm_lut_y=tm.lut_y.numpy(), tm_xs=xs.numpy(), tm_ys=ys.numpy(),
+               tm_lut=tm.lut(xs).numpy(), tm_lut_lin=tm.lut(torch.exp2(xs), input_mode='linear').numpy(),
+               tm_inv=tm.inverse_lut(ys).numpy(), tm_inv_lin=tm.inverse_lut(ys, output_mode='linear').numpy(),
+               tm_smooth=tm.smooth_forward(xs).numpy(), tm_alb=alb.numpy(), tm_shd=shd.numpy(),
+               tm_shaded=tm.lut(tm.inverse_lut(alb) + shd.clamp(min=1e-6).log2()).numpy())       # mvedit_3d_pipeline.py:418-422
 
     np.savez_compressed(OUT, **out)
     print('wrote', OUT, len(out), 'arrays', os.path.getsize(OUT), 'bytes')

@@ -101,7 +101,7 @@ def test_lpips_value_and_gradient_vs_oracle(P, S):
     # the module-style call (NCHW in [0,1], as the reference calls nerf.patch_loss) and the bare distance agree with loss_and_grad
     torch.testing.assert_close(m(pred.permute(0, 3, 1, 2), tgt.permute(0, 3, 1, 2), weight=w) * 0.9, loss, rtol=1e-5, atol=1e-8)
     torch.testing.assert_close(LPIPS(sd)(pred, tgt), d)
-    assert float(LPIPS(sd)(tgt, tgt).abs().max()) == 0.0
+    assert float(LPIPS(sd)(tgt, tgt).abs().max()) < 1e-9
 
 
 def test_gradient_descends_the_oracle_distance():
@@ -158,7 +158,7 @@ def test_objective_with_lpips_term_matches_torch_chain(shaded):
     f32 = dict(dtype=torch.float32, device='cuda')
     scratch, out_rgb = torch.empty(N * 10, **f32), torch.empty(N, 3, **f32)
     call('mve_nerf_patch_out_rgb', ptr(image), ptr(alpha), ptr(depth), ptr(dirs), ptr(lights), c_u32(P), c_u32(ps), c_int(int(shaded)),
-         c_f32(0.2), c_f32(1.0), ptr(scratch), ptr(out_rgb), stream())
+         c_f32(0.2), c_f32(1.0), ptr(scratch), ptr(out_rgb), None, c_u32(0), stream())
     torch.testing.assert_close(out_rgb.view(P, ps, ps, 3), out.detach(), rtol=1e-4, atol=1e-5)
     lp, g_extra, _ = LPIPSLoss(sd, loss_weight=1.2).loss_and_grad(out_rgb.view(P, ps, ps, 3), tgt, patch_w, prw)
     assert abs(float(lp) / float(l_lp) - 1) < 3e-2
@@ -166,7 +166,7 @@ def test_objective_with_lpips_term_matches_torch_chain(shaded):
     g_i, g_a, g_d, loss5 = torch.empty(N, 3, **f32), torch.empty(N, **f32), torch.empty(N, **f32), torch.empty(5, **f32)
     call('mve_nerf_patch_loss', ptr(image), ptr(alpha), ptr(depth), ptr(tgt), ptr(tgt_mask), ptr(dirs), ptr(patch_w), ptr(lights), c_u32(P),
          c_u32(ps), c_int(int(shaded)), c_f32(0.2), c_f32(1.0), c_f32(0.015), c_f32(1.2), ptr(sc[0]), ptr(sc[1]), ptr(sc[2]), ptr(scratch),
-         ptr(g_i), ptr(g_a), ptr(g_d), ptr(loss5), ptr(g_extra), stream())
+         ptr(g_i), ptr(g_a), ptr(g_d), ptr(loss5), ptr(g_extra), None, c_u32(0), stream())
     torch.testing.assert_close(loss5, ref.detach(), rtol=2e-4, atol=1e-6)
     for a, b, name in zip((g_i, g_a, g_d), inp, ('image', 'alpha', 'depth')):
         r = rel(a.view_as(b.grad), b.grad)

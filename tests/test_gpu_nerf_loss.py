@@ -9,7 +9,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def torch_chain(image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps, shaded, ambient, bg, bg_width, plw, alpha_mul, nreg, went):
+def torch_chain(image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps, shaded, ambient, bg, bg_width, plw, alpha_mul, nreg, went,
+                tone=None):
     from oracle.nerf_oracle import depth_to_normal, TVLoss, L1LossMod
     import torch.nn.functional as F
     P = alpha.numel() // (ps * ps)
@@ -22,7 +23,11 @@ def torch_chain(image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights, p
     if shaded:
         ncv = torch.cat([n_fg[..., :1] * 2 - 1, -n_fg[..., 1:3] * 2 + 1], dim=-1)
         sh = ((lights[:, None, None, None, :] @ ncv[..., :, None]).clamp(min=0) * (1 - ambient) + ambient).squeeze(-1)
-        out_rgbs = out_rgbs * sh + bg * (1 - out_alphas)
+        if tone is None:
+            out_rgbs = out_rgbs * sh + bg * (1 - out_alphas)
+        else:        # mvedit_3d_pipeline.py:564-570
+            out_rgbs = tone.lut(tone.inverse_lut(out_rgbs / out_alphas.clamp(min=1e-6)) + sh.clamp(min=1e-6).log2()) * out_alphas \
+                + bg * (1 - out_alphas)
     else:
         out_rgbs = out_rgbs + bg * (1 - out_alphas)
     w = patch_w[:, None, None, None].expand(-1, ps, ps, 1)
@@ -35,11 +40,16 @@ def torch_chain(image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights, p
     return torch.stack([l_rgb + l_a + l_tv + l_e, l_rgb, l_a, l_tv, l_e])
 
 
-@pytest.mark.parametrize('shaded', [False, True])
+@pytest.mark.parametrize('shaded', [False, True, 'tone'])
 @pytest.mark.parametrize('P,ps', [(1, 32), (3, 16)])
 def test_fused_patch_loss_matches_torch_chain(shaded, P, ps):
+    """shaded == 'tone': Lambert shading applied in tone-mapped space (the runner always passes a Tonemapping, adapter3d.py:88,780)."""
     from mvedit_b200.nerf import patch_loss
-    g = torch.Generator(device='cuda').manual_seed(P * ps + shaded)
+    from mvedit_b200.tonemapping import Tonemapping
+    from oracle.nerf_oracle import Tonemapping as OracleTonemapping
+    tone_o, tone_p = (OracleTonemapping().cuda(), Tonemapping()) if shaded == 'tone' else (None, None)
+    shaded = bool(shaded)
+    g = torch.Generator(device='cuda').manual_seed(P * ps + int(shaded))
     N = P * ps * ps
     R = lambda *s: torch.rand(*s, device='cuda', generator=g)
     alpha = (R(N) * 1.1).clamp(0, 1)
@@ -52,9 +62,9 @@ def test_fused_patch_loss_matches_torch_chain(shaded, P, ps):
     patch_w, lights = 0.5 + R(P), torch.nn.functional.normalize(torch.randn(P, 3, device='cuda', generator=g), dim=-1)
     sc = [torch.tensor(v, device='cuda') for v in (5.0, 1.3, 0.02)]
     inp = [t.clone().requires_grad_(True) for t in (image, alpha, depth)]
-    ref = torch_chain(*inp, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps, shaded, 0.2, 1.0, 0.015, 1.2, 5.0, 1.3, 0.02)
+    ref = torch_chain(*inp, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps, shaded, 0.2, 1.0, 0.015, 1.2, 5.0, 1.3, 0.02, tone=tone_o)
     ref[0].backward()
-    out, *grads = patch_loss(image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps, shaded, 0.2, 1.0, 0.015, 1.2, *sc)
+    out, *grads = patch_loss(image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps, shaded, 0.2, 1.0, 0.015, 1.2, *sc, tonemapping=tone_p)
     torch.testing.assert_close(out, ref.detach(), rtol=2e-4, atol=1e-6)
     for a, b, name in zip(grads, inp, ('image', 'alpha', 'depth')):
         err = (a.view_as(b.grad) - b.grad).abs().max().item()

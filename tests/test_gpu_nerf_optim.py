@@ -101,9 +101,10 @@ def test_fused_shade_views_matches_torch_restatement():
                density_bitfield=bitfield, render_size=size, intrinsics=K, intrinsics_size=size, camera_poses=poses,
                cam_weights=torch.ones(V, device='cuda'), cam_lights=lights, patch_size=ps, is_init=True, bg_width=0.015, ambient_light=0.2,
                dt_gamma_scale=0.5, init_shaded=False)
-    step = MVEdit3DStep(None, None, nerf, None)
+    tone_o = no.Tonemapping().cuda()
     with torch.no_grad():
-        for rs in (64, 96):       # 96: intrinsics rescaled, size not a multiple of the 32 x 8 pixel CTA tile
+        for rs, tone in ((64, None), (96, None), (64, tone_o)):     # 96: intrinsics rescaled, size not a multiple of the 32 x 8 pixel CTA tile
+            step = MVEdit3DStep(None, None, nerf, None, tonemapping=tone)       # an external module with lut_x / lut_y buffers is adopted
             for render_bs in (None, 3):
                 img_f, dep_f = step.render_views(bitfield, poses, K, size, rs, lights, 0.2, 0.5, render_bs=render_bs)
                 # oracle chain on the product's raw render, batch by batch as the reference renders (render_bs views per call)
@@ -116,7 +117,11 @@ def test_fused_shade_views_matches_torch_restatement():
                     assert float((normal_fg - nfg_o).abs().max()) < 2e-4
                     ncv = torch.cat([normal_fg[..., :1] * 2 - 1, -normal_fg[..., 1:3] * 2 + 1], dim=-1)
                     sh = ((lb[:, None, None, None, :] @ ncv[..., :, None]).clamp(min=0) * 0.8 + 0.2).squeeze(-1)
-                    imgs.append((rgba[..., :3] * sh + nerf.bg_color * (1 - rgba[..., 3:])).squeeze(0))
+                    if tone is None:
+                        imgs.append((rgba[..., :3] * sh + nerf.bg_color * (1 - rgba[..., 3:])).squeeze(0))
+                    else:         # shading in tone-mapped space (mvedit_3d_pipeline.py:1377-1384)
+                        imgs.append((tone.lut(tone.inverse_lut(rgba[..., :3] / rgba[..., 3:].clamp(min=1e-6)) + sh.clamp(min=1e-6).log2())
+                                     * rgba[..., 3:] + nerf.bg_color * (1 - rgba[..., 3:])).squeeze(0))
                     alphas.append(rgba[..., 3:].squeeze(0)); depths.append(depth.squeeze(0))
                 img_t = torch.cat(imgs).to(torch.bfloat16).permute(0, 3, 1, 2).clamp(0, 1)
                 al = torch.cat(alphas)

@@ -41,15 +41,20 @@ def parts():
                 pe=torch.randn(2 * N, 77, 768, device=dev, generator=g))
 
 
-def make_pipe(parts, scheduler):
+def make_pipe(parts, scheduler, tonemapping=None, lpips=False):
     from mvedit_b200.mvedit_3d_pipeline import MVEdit3DPipeline
     from mvedit_b200.nerf import BaseNeRF
     from mvedit_b200.ingp_decoder import iNGPDecoder
     torch.manual_seed(0)
     dec = iNGPDecoder(max_steps=256)
-    nerf = BaseNeRF(grid_size=128, decoder=dec, patch_size=64).cuda()
+    patch_loss = None
+    if lpips:            # the reference's patch_loss = LPIPSLoss(net='vgg', loss_weight=1.2) (lib/pipelines/utils.py:232)
+        from mvedit_b200.lpips import LPIPSLoss, random_lpips_state_dict
+        patch_loss = LPIPSLoss(random_lpips_state_dict(0, 'cuda'), loss_weight=1.2)
+    nerf = BaseNeRF(grid_size=128, decoder=dec, patch_loss=patch_loss, patch_size=64).cuda()
     seg = lambda x: (x.amax(dim=1, keepdim=True) > 0.5).float()          # TRACER stand-in: any images -> masks callable
-    return MVEdit3DPipeline(parts['vae'], None, None, parts['unet'], parts['cns'], scheduler, nerf, segmentation=seg), dec
+    return MVEdit3DPipeline(parts['vae'], None, None, parts['unet'], parts['cns'], scheduler, nerf, segmentation=seg,
+                            tonemapping=tonemapping), dec
 
 
 def call(pipe, parts, **kw):
@@ -71,14 +76,22 @@ def _schedulers():
 @pytest.mark.parametrize('sched,mode,blend,ref', [('euler', '2-pass', 0.0, False), ('dpm', '2-pass', 0.0, False),
                                                   ('dpm_karras', '1-pass', 'dynamic', False), ('ddim', '1-pass', 0.0, False),
                                                   ('euler', '2-pass', 0.0, True), ('dpm', '1-pass', 'dynamic', 'cond'),
-                                                  ('euler', '2-pass', 0.0, 'extra')])
+                                                  ('euler', '2-pass', 0.0, 'extra'), ('euler', '2-pass', 0.0, 'runner')])
 def test_call_runs_nerf_stage(parts, sched, mode, blend, ref):
     """ref: False = plain CFG batch; True = cross-image attention against the view's own input image (the reference's default,
-    latents (N,4,128,64)); 'cond' = against separate conditioning images; 'extra' = a third ControlNet fed the input images."""
+    latents (N,4,128,64)); 'cond' = against separate conditioning images; 'extra' = a third ControlNet fed the input images;
+    'runner' = what Adapter3DRunner builds (adapter3d.py:88,780; lib/pipelines/utils.py:231-232): reference attention, the Tonemapping
+    module, the LPIPS patch loss with the default weight schedule."""
     sch = _schedulers()[sched]()
-    pipe, dec = make_pipe(parts, sch)
+    if ref == 'runner':
+        from mvedit_b200.tonemapping import Tonemapping
+        pipe, dec = make_pipe(parts, sch, tonemapping=Tonemapping(), lpips=True)
+    else:
+        pipe, dec = make_pipe(parts, sch)
     before = {k: v.detach().clone() for k, v in dec.state_dict().items()}
     kw = dict(use_reference=bool(ref) and ref != 'extra')
+    if ref != 'runner':
+        kw['patch_rgb_weight'] = lambda p: 0.0
     if ref == 'cond':
         g = torch.Generator(device='cuda').manual_seed(5)
         kw['cond_images'] = [torch.rand(3, 256, 256, device='cuda', generator=g) for _ in range(N)]

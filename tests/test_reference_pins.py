@@ -131,3 +131,24 @@ def test_camera_pruning_schedules_lights():
     wl, cl = mp.light_sampling(T('geo_poses'))
     np.testing.assert_allclose(cl.numpy(), PINS['light_cam'], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(wl.numpy(), PINS['light_world'], rtol=1e-5, atol=1e-6)
+
+
+def test_tonemapping_module_and_oracle():
+    """The tone curve (tonemapping.py:5-52): knots, lut / inverse_lut in both modes (incl. the extrapolating end segments and values on
+    the knots), smooth_forward, and shading in tone-mapped space (mvedit_3d_pipeline.py:418-422) -- product module and oracle."""
+    from oracle.nerf_oracle import Tonemapping as OT
+    from mvedit_b200.tonemapping import Tonemapping as PT
+    t = lambda k: torch.from_numpy(PINS[k])
+    for cls in (OT, PT):
+        tm = cls()
+        np.testing.assert_allclose(tm.lut_x.numpy(), PINS['tm_lut_x'], rtol=0, atol=0)
+        np.testing.assert_allclose(tm.lut_y.numpy(), PINS['tm_lut_y'], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(tm.lut(t('tm_xs')).numpy(), PINS['tm_lut'], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(tm.lut(torch.exp2(t('tm_xs')), input_mode='linear').numpy(), PINS['tm_lut_lin'], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(tm.inverse_lut(t('tm_ys')).numpy(), PINS['tm_inv'], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(tm.inverse_lut(t('tm_ys'), output_mode='linear').numpy(), PINS['tm_inv_lin'], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(tm.smooth_forward(t('tm_xs')).numpy(), PINS['tm_smooth'], rtol=1e-6, atol=1e-7)
+        shaded = tm.lut(tm.inverse_lut(t('tm_alb')) + t('tm_shd').clamp(min=1e-6).log2())
+        np.testing.assert_allclose(shaded.numpy(), PINS['tm_shaded'], rtol=1e-5, atol=1e-6)
+    arr, n = PT().knots()
+    assert n == 16 and np.allclose(np.array(arr[:16]), PINS['tm_lut_x']) and np.allclose(np.array(arr[16:]), PINS['tm_lut_y'], atol=1e-7)
