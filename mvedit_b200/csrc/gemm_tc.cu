@@ -50,6 +50,10 @@ struct GemmParams {
     float alpha;                    // out = act(acc + bias + row_bias) * alpha + residual
     // conv geometry (MODE 1)
     uint32_t H, W, cin_chunks;
+    // split-K (few-tile problems with a long K: the 8^2 / 16^2 levels of the LPIPS VGG): `splits` CTAs share one output tile, each
+    // reduces a slice of K and adds its fp32 partial into ws [M, N] (zero on entry); k_splitk_finish applies the epilogue and re-zeroes
+    uint32_t splits;
+    float* ws;
 };
 
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
@@ -103,14 +107,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const uint32_t num_tiles = p.m_tiles * p.n_tiles;
+    const uint32_t num_tiles = p.m_tiles * p.n_tiles * p.splits;
+    // tile -> (m tile, n tile, first and one-past-last k block of this CTA's K slice)
+    auto decode = [&](const uint32_t tile, uint32_t& mt, uint32_t& nt, uint32_t& kb0, uint32_t& kb1) {
+        const uint32_t sp = tile % p.splits, t2 = tile / p.splits;
+        mt = t2 / p.n_tiles; nt = t2 % p.n_tiles;
+        kb0 = sp * p.num_kb / p.splits; kb1 = (sp + 1) * p.num_kb / p.splits;
+    };
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const uint32_t mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+                uint32_t mt, nt, kb0, kb1;
+                decode(tile, mt, nt, kb0, kb1);
                 const int m0 = mt * BMT, n0 = nt * BN;
                 int b0 = 0, h0 = 0, w0 = 0;
                 if (MODE == 1) {
@@ -120,7 +131,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
                     h0 = rem / p.W;
                     w0 = rem % p.W;
                 }
-                for (uint32_t kb = 0; kb < p.num_kb; kb++) {
+                for (uint32_t kb = kb0; kb < kb1; kb++) {
                     tc::mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * C_::STAGE_BYTES;
                     uint8_t* sb = sa + MT * A_BYTES;
@@ -143,10 +154,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
             constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                uint32_t mt_, nt_, kb0, kb1;
+                decode(tile, mt_, nt_, kb0, kb1);
                 tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * C_::ACC_STRIDE;
-                for (uint32_t kb = 0; kb < p.num_kb; kb++) {
+                for (uint32_t kb = kb0; kb < kb1; kb++) {
                     tc::mbar_wait(&full[stage], phase);
                     tc::tc_fence_after();
                     const uint32_t sa = tc::smem_u32(smem + stage * C_::STAGE_BYTES);
@@ -157,7 +170,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
                         // the second 128-row sub-tile of A sits A_BYTES further on and accumulates BN columns further on
 #pragma unroll
                         for (int s = 0; s < MT; s++)
-                            tc::umma_f16(d_tmem + s * BN, da + (uint64_t)(k * 2 + s * (A_BYTES >> 4)), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                            tc::umma_f16(d_tmem + s * BN, da + (uint64_t)(k * 2 + s * (A_BYTES >> 4)), db + (uint64_t)(k * 2), idesc, ((kb - kb0) | k) ? 1u : 0u);
                     }
                     tc::umma_commit(&empty[stage]);
                     if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
@@ -172,7 +185,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
         const int half = (warp - 2) >> 2;     // MT == 1: 0 = even column chunks, 1 = odd column chunks; MT == 2: the 128-row sub-tile
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const uint32_t mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+            uint32_t mt, nt, kb0_, kb1_;
+            decode(tile, mt, nt, kb0_, kb1_);
             const uint32_t row = mt * BMT + (MT == 2 ? half * BM : 0) + q * 32 + lane;
             const uint32_t n0 = nt * BN;
             tc::mbar_wait(&tfull[acc], acc_phase);
@@ -225,7 +239,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
                 }
                 tc::tmem_ld_wait();
                 const uint32_t col0 = n0 + c;
-                if (row_ok && col0 < p.N) {
+                if (p.splits > 1) {
+                    if (row_ok) {
+                        float* wrow = p.ws + (size_t)row * p.N + col0;
+#pragma unroll
+                        for (int i = 0; i < CH; i++)
+                            if (col0 + i < p.N) atomicAdd(wrow + i, __uint_as_float(v[i]));
+                    }
+                } else if (row_ok && col0 < p.N) {
                     __nv_bfloat16* out = p.C + (size_t)row * p.ldc + col0;
                     const __nv_bfloat16* res = p.residual ? p.residual + (size_t)row * p.ldr + col0 : nullptr;
                     const bool full_chunk = (col0 + CH <= p.N) && ((p.ldc & 7) == 0) && (!res || (p.ldr & 7) == 0);
@@ -285,6 +306,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
     }
 }
 
+// epilogue of a split-K launch: ws [M,N] fp32 sums -> act(sum + bias) * alpha (+ residual / gated by it) -> bf16, and ws back to zero
+__global__ void __launch_bounds__(256) k_splitk_finish(const GemmParams p) {
+    const uint32_t n8 = p.N / 8;
+    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= (size_t)p.M * n8) return;
+    const uint32_t row = t / n8, col0 = (t % n8) * 8;
+    float4* w4 = reinterpret_cast<float4*>(p.ws + (size_t)row * p.N + col0);
+    const float4 a = w4[0], b = w4[1];
+    w4[0] = make_float4(0.f, 0.f, 0.f, 0.f); w4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const float* rb = p.row_bias ? p.row_bias + (size_t)(row / p.rows_per_group) * p.ldrb : nullptr;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float x = f[i];
+        if (p.bias) x += p.bias[col0 + i];
+        if (rb) x += rb[col0 + i];
+        x = act_apply(x, p.act) * p.alpha;
+        if (p.residual) {
+            const float r = __bfloat162float(p.residual[(size_t)row * p.ldr + col0 + i]);
+            x = p.act == 5 ? (r > 0.f ? x : 0.f) : x + r;
+        }
+        p.C[(size_t)row * p.ldc + col0 + i] = __float2bfloat16(x);
+    }
+}
+
+// per-device fp32 workspace of the split-K path (zero between launches by construction).  Never allocated under stream capture.
+constexpr size_t SPLITK_WS_FLOATS = 2u << 20;      // 8 MB: M * N <= 2 Mi elements
+float* splitk_workspace(cudaStream_t s) {
+    static float* ws[16] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    float*& w = ws[dev & 15];
+    if (!w) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+        if (cudaMalloc(&w, SPLITK_WS_FLOATS * sizeof(float)) != cudaSuccess) { w = nullptr; return nullptr; }
+        if (cudaMemset(w, 0, SPLITK_WS_FLOATS * sizeof(float)) != cudaSuccess) return nullptr;
+    }
+    return w;
+}
+
 int pick_bn(uint32_t N) {
     if (N % 256 == 0) return 256;
     if (N % 160 == 0) return 160;
@@ -328,10 +390,14 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
         MVE_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, MODE, MT, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
         configured[dev & 15] = true;
     }
-    const uint32_t tiles = p.m_tiles * p.n_tiles;
+    const uint32_t tiles = p.m_tiles * p.n_tiles * p.splits;
     const uint32_t grid = tiles < (uint32_t)kNumSM ? tiles : (uint32_t)kNumSM;
     k_gemm_tc<BN, MODE, MT, ACC><<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, p);
     MVE_CHECK_LAUNCH("k_gemm_tc");
+    if (p.splits > 1) {
+        k_splitk_finish<<<cdiv((size_t)p.M * (p.N / 8), 256), 256, 0, stream>>>(p);
+        MVE_CHECK_LAUNCH("k_splitk_finish");
+    }
     return 0;
 }
 
@@ -418,6 +484,7 @@ int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N,
     p.m_tiles = (M + bm - 1) / bm; p.n_tiles = (N + bn - 1) / bn;
     p.bias = bias; p.row_bias = row_bias; p.rows_per_group = rows_per_group; p.ldrb = ldrb ? ldrb : N;
     p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act; p.alpha = alpha;
+    p.splits = 1;
     return dispatch<0>(tc_, tmA, tmB, p, (cudaStream_t)stream);
 }
 
@@ -463,6 +530,20 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32
     p.bias = bias; p.row_bias = row_bias; p.rows_per_group = H * W; p.ldrb = ldrb ? ldrb : Cout;
     p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act; p.alpha = alpha;
     p.H = H; p.W = W; p.cin_chunks = Cin / BK;
+    // split-K: a handful of tiles each looping over >= 16 k blocks is latency-bound (28 us for the 512 -> 512 convolutions of an 8^2 or
+    // 16^2 feature map whatever the tile count) -- spread K over idle SMs, >= 8 k blocks per CTA
+    p.splits = 1;
+    {
+        static int enabled = -1;
+        if (enabled < 0) { const char* e = getenv("MVE_CONV_SPLITK"); enabled = (e && e[0] == '0') ? 0 : 1; }
+        const uint32_t tiles = p.m_tiles * p.n_tiles;
+        if (enabled && tc_.mt == 1 && act != 3 && Cout % 8 == 0 && (ldy % 8) == 0 && tiles * 4 <= (uint32_t)kNumSM && p.num_kb >= 16 &&
+            (size_t)M * Cout <= SPLITK_WS_FLOATS) {
+            uint32_t sp = p.num_kb / 8;
+            if (sp > (uint32_t)kNumSM / tiles) sp = (uint32_t)kNumSM / tiles;
+            if (sp >= 2 && (p.ws = splitk_workspace((cudaStream_t)stream)) != nullptr) p.splits = sp;
+        }
+    }
     return dispatch<1>(tc_, tmA, tmB, p, (cudaStream_t)stream);
 }
 

@@ -112,42 +112,61 @@ template <int CPL>
 __global__ void __launch_bounds__(256) k_lpips_layer(const __nv_bfloat16* __restrict__ feat, uint32_t P, uint32_t HW,
                                                      const float* __restrict__ lin_w, const float* __restrict__ gscale,
                                                      float* __restrict__ loss, __nv_bfloat16* __restrict__ g_feat) {
-    constexpr int C = CPL * 32;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= P * HW) return;
-    const uint32_t img = warp / HW;
-    const __nv_bfloat16* fp = feat + (size_t)warp * C + lane * CPL;
-    const __nv_bfloat16* ft = feat + ((size_t)P * HW + warp) * C + lane * CPL;
-    float p[CPL], t[CPL], w[CPL];
-    float sp = 0.f, st = 0.f;
+    constexpr int C = CPL * 32, PIX_PER_WARP = 8;
+    // a CTA covers 64 consecutive pixels of ONE image (HW is a multiple of 64 or the grid is per image): one loss atomic per CTA --
+    // 16 384 same-address atomics, one per pixel, serialise in L2 and cost 27 us on the 128^2 level
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t blocks_per_img = (HW + 63) / 64, img = blockIdx.x / blocks_per_img;
+    const uint32_t pix0 = (blockIdx.x % blocks_per_img) * 64 + wib * PIX_PER_WARP;
+    float w[CPL];
 #pragma unroll
-    for (int j = 0; j < CPL; j += 2) {
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(fp + j));
-        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ft + j));
-        p[j] = a.x; p[j + 1] = a.y; t[j] = b.x; t[j + 1] = b.y;
-        w[j] = lin_w[lane * CPL + j]; w[j + 1] = lin_w[lane * CPL + j + 1];
-        sp += a.x * a.x + a.y * a.y; st += b.x * b.x + b.y * b.y;
-    }
-    sp = warp_sum(sp); st = warp_sum(st);
-    const float np_ = sqrtf(sp), nt_ = sqrtf(st), ip = 1.f / (np_ + 1e-10f), it = 1.f / (nt_ + 1e-10f);
-    float val = 0.f, dot = 0.f, q[CPL];
-#pragma unroll
-    for (int j = 0; j < CPL; j++) {
-        const float d = p[j] * ip - t[j] * it;
-        val += w[j] * d * d;
-        q[j] = 2.f * w[j] * d;
-        dot += q[j] * p[j];
-    }
-    val = warp_sum(val); dot = warp_sum(dot);
-    if (lane == 0) atomicAdd(loss + img, val / (float)HW);
+    for (int j = 0; j < CPL; j++) w[j] = lin_w[lane * CPL + j];
     const float gs = gscale[img] / (float)HW;
-    const float k2 = np_ > 0.f ? dot * ip * ip / np_ : 0.f;
-    __nv_bfloat16* g = g_feat + (size_t)warp * C + lane * CPL;
+    float acc = 0.f;
+    for (uint32_t k = 0; k < PIX_PER_WARP; k++) {
+        const uint32_t pix = pix0 + k;
+        if (pix >= HW) break;
+        const size_t row = (size_t)img * HW + pix;
+        const __nv_bfloat16* fp = feat + row * C + lane * CPL;
+        const __nv_bfloat16* ft = feat + ((size_t)P * HW + row) * C + lane * CPL;
+        float p[CPL], t[CPL];
+        float sp = 0.f, st = 0.f;
 #pragma unroll
-    for (int j = 0; j < CPL; j += 2) {
-        const float g0 = p[j] > 0.f ? gs * (q[j] * ip - p[j] * k2) : 0.f;
-        const float g1 = p[j + 1] > 0.f ? gs * (q[j + 1] * ip - p[j + 1] * k2) : 0.f;
-        *reinterpret_cast<__nv_bfloat162*>(g + j) = __floats2bfloat162_rn(g0, g1);
+        for (int j = 0; j < CPL; j += 2) {
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(fp + j));
+            const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ft + j));
+            p[j] = a.x; p[j + 1] = a.y; t[j] = b.x; t[j + 1] = b.y;
+            sp += a.x * a.x + a.y * a.y; st += b.x * b.x + b.y * b.y;
+        }
+        sp = warp_sum(sp); st = warp_sum(st);
+        const float np_ = sqrtf(sp), nt_ = sqrtf(st), ip = 1.f / (np_ + 1e-10f), it = 1.f / (nt_ + 1e-10f);
+        float val = 0.f, dot = 0.f, q[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; j++) {
+            const float d = p[j] * ip - t[j] * it;
+            val += w[j] * d * d;
+            q[j] = 2.f * w[j] * d;
+            dot += q[j] * p[j];
+        }
+        val = warp_sum(val); dot = warp_sum(dot);
+        acc += val;
+        const float k2 = np_ > 0.f ? dot * ip * ip / np_ : 0.f;
+        __nv_bfloat16* g = g_feat + row * C + lane * CPL;
+#pragma unroll
+        for (int j = 0; j < CPL; j += 2) {
+            const float g0 = p[j] > 0.f ? gs * (q[j] * ip - p[j] * k2) : 0.f;
+            const float g1 = p[j + 1] > 0.f ? gs * (q[j + 1] * ip - p[j + 1] * k2) : 0.f;
+            *reinterpret_cast<__nv_bfloat162*>(g + j) = __floats2bfloat162_rn(g0, g1);
+        }
+    }
+    __shared__ float s_acc[8];
+    if (lane == 0) s_acc[wib] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) tot += s_acc[i];
+        atomicAdd(loss + img, tot / (float)HW);
     }
 }
 
@@ -193,7 +212,7 @@ int mve_lpips_layer(const void* feat, uint32_t P, uint32_t HW, uint32_t C, const
                     void* g_feat, void* stream) {
     MVE_ARG(C == 64 || C == 128 || C == 256 || C == 512, "lpips layer: C must be 64, 128, 256 or 512 (VGG16)");
     if (P * HW == 0) return 0;
-    const uint32_t blocks = cdiv((size_t)P * HW * 32, 256);
+    const uint32_t blocks = P * cdiv(HW, 64);
     cudaStream_t s = (cudaStream_t)stream;
     const __nv_bfloat16* f = (const __nv_bfloat16*)feat;
     __nv_bfloat16* g = (__nv_bfloat16*)g_feat;
