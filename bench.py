@@ -373,10 +373,11 @@ def run_ours(args):
     steps_per_s = args.steps / (ms * 1e-3)
     e2e_steps_per_s = args.steps / (ms_e2e * 1e-3)
     h2d = lat_h.numel() * 4 + pe_h.numel() * 2 + tgt_img_h.numel() * 4 + tgt_msk_h.numel() * 4
-    traffic = None
+    traffic = traffic_shape = None
     tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json')       # dram bytes per launch of the dominant kernel family from the committed ncu capture
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get('k_gemm_tc_dram_bytes_per_launch')
+        tj = json.load(open(tpath))
+        traffic, traffic_shape = tj.get('k_gemm_tc_dram_bytes_per_launch'), tj.get('k_gemm_tc_dram_bytes_shape')
     line = dict(
         metric=METRIC, value=round(steps_per_s, 4), unit='steps/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=round(ms / args.steps, 2), higher_is_better=True, scaling='strong', vs_baseline=None, dtype='bf16', data='synthetic',
@@ -399,7 +400,7 @@ def run_ours(args):
         gpu_launches=int(launches),
         clocks=clocks,
         roofline=dict(bound='tensor', kernel='k_gemm_tc (mve_gemm_bf16 + mve_conv3x3_bf16: UNet, ControlNets, VAE)', achieved=round(achieved, 1),
-                      peak=pk['tf_sustained'], unit='TFLOP/s', frac=round(achieved / pk['tf_sustained'], 4), traffic=traffic,
+                      peak=pk['tf_sustained'], unit='TFLOP/s', frac=round(achieved / pk['tf_sustained'], 4), traffic=traffic, traffic_shape=traffic_shape,
                       peak_source=pk['src'] + ' (sustained)', launches_per_step=tc_n,
                       share_of_step=round(tc_ms / total_prof_ms, 3) if total_prof_ms else None,
                       denoise_decode_phase_tflops=round(all_tc_fl / (denoise_ms * 1e-3) / 1e12, 1) if denoise_ms else None,

@@ -25,6 +25,8 @@
 // (SURVEY.md §8 a-1/a-2, Appendix A).
 #include <cstdlib>
 #include "tc_common.cuh"
+#include <mutex>
+#include <string.h>
 #include "../../include/mvedit_b200.h"
 
 namespace {
@@ -433,6 +435,25 @@ PFN_tmapEncodeTiled mve_get_tmap_encode() {
 
 int mve_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                        const uint32_t* box, const char* what) {
+    // Descriptors are pure functions of (base, dims, strides, box): a step issues ~650 GEMM / conv / attention launches over a few dozen
+    // distinct operand layouts at recurring addresses (weights; activations at the caching allocator's recycled pointers), so a small
+    // direct-mapped cache removes the driver call from the launch path.
+    struct Entry { uint64_t key[14]; CUtensorMap map; bool valid; };
+    static Entry cache[512];
+    static std::mutex mu;
+    uint64_t key[14] = {(uint64_t)(uintptr_t)base, (uint64_t)rank};
+    for (int i = 0; i < 4; i++) {
+        key[2 + i] = i < rank ? dims[i] : 0;
+        key[6 + i] = i + 1 < rank ? strides_bytes[i] : 0;
+        key[10 + i] = i < rank ? box[i] : 0;
+    }
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < 14; i++) { h ^= key[i]; h *= 1099511628211ull; }
+    Entry& e = cache[(h >> 20) & 511];
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (e.valid && memcmp(e.key, key, sizeof(key)) == 0) { *out = e.map; return 0; }
+    }
     PFN_tmapEncodeTiled enc = mve_get_tmap_encode();
     if (!enc) { mve_set_error("%s: cuTensorMapEncodeTiled entry point not available (no CUDA driver?)", what); return -2; }
     cuuint64_t gdim[5], gstr[5];
@@ -447,6 +468,10 @@ int mve_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint6
                       (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), (unsigned long long)(rank > 2 ? dims[2] : 0),
                       (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
         return -3;
+    }
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        memcpy(e.key, key, sizeof(key)); e.map = *out; e.valid = true;
     }
     return 0;
 }
