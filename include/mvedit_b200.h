@@ -118,12 +118,13 @@ int mve_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int bi
  * A, B, C, residual bf16 (lda/ldb/ldc/ldr in elements, multiples of 8); bias/row_bias f32 or NULL (row_bias row stride ldrb, 0 = N); K % 64 == 0.
  * act: 0 none, 1 SiLU, 2 GELU(erf), 3 GEGLU: every 256 columns of B hold [128 value | 128 gate] rows of a diffusers GEGLU
  * projection and C gets the N/2 products value * gelu(gate) (ldc >= N/2; no row_bias / residual; N % 256 == 0);
- * 4 ReLU; 5 ReLU backward gate: C = residual > 0 ? (acc + bias) * alpha : 0 (residual = the forward activation, not added).
+ * 4 ReLU; 5 ReLU backward gate: C = residual > 0 ? (acc + bias) * alpha : 0 (residual = the forward activation, not added);
+ * 6 PReLU with per-column slopes act_param [N] (f32; NULL otherwise).
  * Replaces torch.nn.functional.linear / 1x1 conv (cuBLAS) on the UNet path. */
 int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N, uint32_t K,
                   uint32_t lda, uint32_t ldb, uint32_t ldc,
                   const float* bias, const float* row_bias, uint32_t rows_per_group, uint32_t ldrb,
-                  const void* residual, uint32_t ldr, int act, float alpha, void* stream);
+                  const void* residual, uint32_t ldr, int act, float alpha, const float* act_param, void* stream);
 
 /* 3x3 convolution, stride 1, pad 1, as an implicit GEMM (no im2col buffer): X [B,H,W,Cin] bf16 NHWC,
  * Wt [Cout,3,3,Cin] bf16, Y [B*H*W, ldy] bf16.  Epilogue as mve_gemm_bf16 with rows_per_group = H*W
@@ -132,7 +133,7 @@ int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N,
 int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t B, uint32_t H, uint32_t W,
                      uint32_t Cin, uint32_t Cout, uint32_t ldy,
                      const float* bias, const float* row_bias, uint32_t ldrb, const void* residual, uint32_t ldr,
-                     int act, float alpha, void* stream);
+                     int act, float alpha, const float* act_param, void* stream);
 
 /* 3x3 convolution (pad 1, stride 1 or 2) for FEW channels on the CUDA cores: the front of diffusers' ControlNetConditioningEmbedding
  * (3->16, 16->16, 16->32 s2, 32->32, 32->96 s2 on the 512^2 condition images), where a tensor-core tile would be
@@ -281,6 +282,12 @@ int mve_maxpool2x2_relu_backward_bf16(const void* x, const void* g_y, uint32_t B
                                       void* stream);
 int mve_lpips_layer(const void* feat, uint32_t P, uint32_t HW, uint32_t C, const float* lin_w, const float* gscale, float* loss,
                     void* g_feat, void* stream);
+/* Tail of SRVGGNetCompact.forward, the render enhancer below 512^2 (lib/models/decoders/image_space_ss.py:66-75;
+ * mvedit_3d_pipeline.py:1398-1401): out [B,C,rH,rW] bf16 NCHW = PixelShuffle(r)(y) + nearest-upsampled x, with y [B,H,W,ldy] bf16 NHWC
+ * holding channel c r^2 + i r + j of the last convolution and x [B,H,W,ldx] bf16 NHWC the network input (first C channels).  The 34
+ * convolutions before it are mve_conv3x3_bf16 calls with the PReLU epilogue (act 6). */
+int mve_pixel_shuffle_add_bf16(const void* y, const void* x, uint32_t B, uint32_t H, uint32_t W, uint32_t C, uint32_t r,
+                               uint32_t ldy, uint32_t ldx, void* out, void* stream);
 /* x [B,C,HW] (f32 or bf16) -> y [B,HW,Cpad] bf16, channels >= C zero-filled */
 int mve_nchw_to_nhwc_pad_bf16(const void* x, int x_is_f32, void* y, uint32_t B, uint32_t C, uint32_t HW, uint32_t Cpad, void* stream);
 

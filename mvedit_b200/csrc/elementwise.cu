@@ -438,3 +438,32 @@ int mve_nchw_to_nhwc_pad_bf16(const void* x, int x_is_f32, void* y, uint32_t B, 
 }
 
 }  // extern "C"
+
+
+// ---- tail of SRVGGNetCompact.forward (lib/models/decoders/image_space_ss.py:66-75): PixelShuffle(r) of the last conv's output plus the
+// nearest-upsampled input.  y [B,H,W,ldy >= C r^2] bf16 NHWC (channel c r^2 + i r + j), x [B,H,W,ldx >= C] bf16 NHWC ->
+// out [B,C,rH,rW] bf16 NCHW: out[b,c,h r + i,w r + j] = y[b,h,w,c r^2 + i r + j] + x[b,h,w,c].  One thread per output pixel pair row.
+namespace {
+__global__ void __launch_bounds__(256) k_pixel_shuffle_add(const bf16* __restrict__ y, const bf16* __restrict__ x, uint32_t B, uint32_t H,
+                                                           uint32_t W, uint32_t C, uint32_t r, uint32_t ldy, uint32_t ldx,
+                                                           bf16* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;                 // over (b, c, oh, ow), ow fastest: coalesced NCHW writes
+    const uint32_t OW = W * r, OH = H * r;
+    if (t >= (size_t)B * C * OH * OW) return;
+    const uint32_t ow = t % OW, oh = (t / OW) % OH, c = (t / ((size_t)OW * OH)) % C, b = t / ((size_t)OW * OH * C);
+    const uint32_t w = ow / r, j = ow % r, h = oh / r, i = oh % r;
+    const size_t pix = ((size_t)b * H + h) * W + w;
+    const float v = __bfloat162float(y[pix * ldy + c * r * r + i * r + j]) + __bfloat162float(x[pix * ldx + c]);
+    out[t] = __float2bfloat16(v);
+}
+}  // namespace
+
+extern "C" int mve_pixel_shuffle_add_bf16(const void* y, const void* x, uint32_t B, uint32_t H, uint32_t W, uint32_t C, uint32_t r,
+                                          uint32_t ldy, uint32_t ldx, void* out, void* stream) {
+    const size_t n = (size_t)B * C * H * r * W * r;
+    if (n == 0) return 0;
+    MVE_ARG(ldy >= C * r * r && ldx >= C, "pixel_shuffle_add: ldy >= C r^2 and ldx >= C");
+    k_pixel_shuffle_add<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)y, (const bf16*)x, B, H, W, C, r, ldy, ldx, (bf16*)out);
+    MVE_CHECK_LAUNCH("mve_pixel_shuffle_add_bf16");
+    return 0;
+}

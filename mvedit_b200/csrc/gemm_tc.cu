@@ -49,7 +49,9 @@ struct GemmParams {
     int act;                        // 0 none, 1 SiLU, 2 GELU(erf), 3 GEGLU (tile = [BN/2 value | BN/2 gate] columns -> BN/2 outputs),
                                     // 4 ReLU, 5 ReLU-backward gate: out = residual > 0 ? (acc + bias) * alpha : 0 (residual = the forward
                                     // activation; nothing is added)
+                                    // 6 PReLU with per-column slopes act_param[N]
     float alpha;                    // out = act(acc + bias + row_bias) * alpha + residual
+    const float* act_param;         // [N] for act 6, else unused
     // conv geometry (MODE 1)
     uint32_t H, W, cin_chunks;
     // split-K (few-tile problems with a long K: the 8^2 / 16^2 levels of the LPIPS VGG): `splits` CTAs share one output tile, each
@@ -261,6 +263,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
                                 float x = __uint_as_float(v[g * 8 + i]);
                                 if (p.bias) x += p.bias[col0 + g * 8 + i];
                                 if (rb) x += rb[col0 + g * 8 + i];
+                                if (p.act == 6) x = x > 0.f ? x : x * p.act_param[col0 + g * 8 + i];
                                 f[i] = act_apply(x, p.act) * p.alpha;
                             }
                             if (res) {
@@ -286,6 +289,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
                             float x = __uint_as_float(v[i]);
                             if (p.bias) x += p.bias[col0 + i];
                             if (rb) x += rb[col0 + i];
+                            if (p.act == 6) x = x > 0.f ? x : x * p.act_param[col0 + i];
                             x = act_apply(x, p.act) * p.alpha;
                             if (res) x = p.act == 5 ? (__bfloat162float(res[i]) > 0.f ? x : 0.f) : x + __bfloat162float(res[i]);
                             out[i] = __float2bfloat16(x);
@@ -324,6 +328,7 @@ __global__ void __launch_bounds__(256) k_splitk_finish(const GemmParams p) {
         float x = f[i];
         if (p.bias) x += p.bias[col0 + i];
         if (rb) x += rb[col0 + i];
+        if (p.act == 6) x = x > 0.f ? x : x * p.act_param[col0 + i];
         x = act_apply(x, p.act) * p.alpha;
         if (p.residual) {
             const float r = __bfloat162float(p.residual[(size_t)row * p.ldr + col0 + i]);
@@ -480,8 +485,9 @@ extern "C" {
 
 int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N, uint32_t K, uint32_t lda, uint32_t ldb, uint32_t ldc,
                   const float* bias, const float* row_bias, uint32_t rows_per_group, uint32_t ldrb, const void* residual, uint32_t ldr,
-                  int act, float alpha, void* stream) {
+                  int act, float alpha, const float* act_param, void* stream) {
     if (M == 0 || N == 0) return 0;
+    MVE_ARG(act != 6 || act_param != nullptr, "gemm: act 6 (PReLU) needs act_param [N]");
     MVE_ARG(K % BK == 0 && K > 0, "gemm: K must be a positive multiple of 64");
     MVE_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (16-byte TMA strides)");
     MVE_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "gemm: pointers must be 16-byte aligned");
@@ -508,15 +514,16 @@ int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N,
     p.C = (__nv_bfloat16*)C; p.M = M; p.N = N; p.ldc = ldc; p.num_kb = K / BK;
     p.m_tiles = (M + bm - 1) / bm; p.n_tiles = (N + bn - 1) / bn;
     p.bias = bias; p.row_bias = row_bias; p.rows_per_group = rows_per_group; p.ldrb = ldrb ? ldrb : N;
-    p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act; p.alpha = alpha;
+    p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act; p.alpha = alpha; p.act_param = act_param;
     p.splits = 1;
     return dispatch<0>(tc_, tmA, tmB, p, (cudaStream_t)stream);
 }
 
 int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32_t H, uint32_t W, uint32_t Cin, uint32_t Cout,
                      uint32_t ldy, const float* bias, const float* row_bias, uint32_t ldrb, const void* residual, uint32_t ldr, int act,
-                     float alpha, void* stream) {
+                     float alpha, const float* act_param, void* stream) {
     if (Bn == 0) return 0;
+    MVE_ARG(act != 6 || act_param != nullptr, "conv3x3: act 6 (PReLU) needs act_param [Cout]");
     MVE_ARG(Cin % BK == 0, "conv3x3: Cin must be a multiple of 64 (pad channels)");
     MVE_ARG((W <= 128 && 128 % W == 0) || W % 128 == 0, "conv3x3: W must divide 128 or be a multiple of 128");
     const uint32_t M = Bn * H * W;
@@ -553,7 +560,7 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32
     p.C = (__nv_bfloat16*)Y; p.M = M; p.N = Cout; p.ldc = ldy; p.num_kb = 9 * (Cin / BK);
     p.m_tiles = (M + PIX - 1) / PIX; p.n_tiles = (Cout + bn - 1) / bn;   // a last partial tile reads zero-filled images (TMA OOB)
     p.bias = bias; p.row_bias = row_bias; p.rows_per_group = H * W; p.ldrb = ldrb ? ldrb : Cout;
-    p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act; p.alpha = alpha;
+    p.residual = (const __nv_bfloat16*)residual; p.ldr = ldr; p.act = act; p.alpha = alpha; p.act_param = act_param;
     p.H = H; p.W = W; p.cin_chunks = Cin / BK;
     // split-K: a handful of tiles each looping over >= 16 k blocks is latency-bound (28 us for the 512 -> 512 convolutions of an 8^2 or
     // 16^2 feature map whatever the tile count) -- spread K over idle SMs, >= 8 k blocks per CTA

@@ -9,10 +9,10 @@ import ctypes
 
 from ._lib import call, ptr, raw_ptr, stream, c_int, c_u32, c_f32
 
-ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2, 'geglu': 3, 'relu': 4, 'relu_gate': 5}
+ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2, 'geglu': 3, 'relu': 4, 'relu_gate': 5, 'prelu': 6}
 
 
-def gemm(a, w, bias=None, row_bias=None, rows_per_group=0, residual=None, act=None, alpha=1.0, out=None):
+def gemm(a, w, bias=None, row_bias=None, rows_per_group=0, residual=None, act=None, alpha=1.0, out=None, act_param=None):
     """out[M,N] = act(a[M,K] @ w[N,K]^T + bias + row_bias[row // rows_per_group]) * alpha + residual.   bf16 in/out.
     act='geglu': w / bias must be ordered by geglu_interleave(); out[M, N/2] = value * gelu(gate)."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
@@ -29,7 +29,7 @@ def gemm(a, w, bias=None, row_bias=None, rows_per_group=0, residual=None, act=No
     call('mve_gemm_bf16', raw_ptr(a), raw_ptr(w), raw_ptr(out), c_u32(M), c_u32(N), c_u32(K), c_u32(a.stride(0)), c_u32(w.stride(0)),
          c_u32(out.stride(0)), ptr(bias), raw_ptr(row_bias), c_u32(rows_per_group),
          c_u32(row_bias.stride(0) if row_bias is not None else 0), raw_ptr(residual),
-         c_u32(residual.stride(0) if residual is not None else 0), c_int(ACT[act]), c_f32(alpha), stream(),
+         c_u32(residual.stride(0) if residual is not None else 0), c_int(ACT[act]), c_f32(alpha), ptr(act_param), stream(),
          _meta=dict(flops=2.0 * M * N * K, shape='gemm M%d N%d K%d%s' % (M, N, K, ' geglu' if act == 'geglu' else '')))
     return out
 
@@ -45,7 +45,7 @@ def geglu_interleave(w, b, tile=256):
     return w[perm].contiguous(), (None if b is None else b[perm].contiguous())
 
 
-def conv3x3(x, w, bias=None, row_bias=None, residual=None, act=None, alpha=1.0, out=None):
+def conv3x3(x, w, bias=None, row_bias=None, residual=None, act=None, alpha=1.0, out=None, act_param=None):
     """x [B,H,W,Cin] bf16 NHWC, w [Cout,3,3,Cin] bf16 -> [B,H,W,Cout] bf16.  stride 1, pad 1.
     row_bias [B,Cout] f32 is added per image (time embedding); residual [B,H,W,Cout] is added after scaling."""
     assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.is_contiguous() and w.is_contiguous()
@@ -57,7 +57,7 @@ def conv3x3(x, w, bias=None, row_bias=None, residual=None, act=None, alpha=1.0, 
     call('mve_conv3x3_bf16', ptr(x), ptr(w), ptr(out), c_u32(B), c_u32(H), c_u32(W), c_u32(Cin), c_u32(Cout), c_u32(out.stride(2)),
          ptr(bias), raw_ptr(row_bias), c_u32(row_bias.stride(0) if row_bias is not None else 0), ptr(residual),
          c_u32(residual.stride(2) if residual is not None else 0), c_int(ACT[act]),
-         c_f32(alpha), stream(), _meta=dict(flops=2.0 * B * H * W * Cout * 9 * Cin, shape='conv B%d %dx%d Cin%d Cout%d' % (B, H, W, Cin, Cout)))
+         c_f32(alpha), ptr(act_param), stream(), _meta=dict(flops=2.0 * B * H * W * Cout * 9 * Cin, shape='conv B%d %dx%d Cin%d Cout%d' % (B, H, W, Cin, Cout)))
     return out
 
 

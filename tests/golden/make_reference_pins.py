@@ -6,6 +6,7 @@ Loaded by path (``import lib`` itself is impossible here: mmcv / mmgen / diffuse
   lib/models/architecture/joint_attn.py    CrossImageAttnProcWrapper                 -> pins oracle/unet_oracle.attention(num_cross_attn_imgs=2)
   lib/models/decoders/tonemapping.py       Tonemapping (lut / inverse_lut / smooth_forward) -> pins oracle/nerf_oracle.Tonemapping and
                                            mvedit_b200.tonemapping.Tonemapping
+  lib/models/decoders/image_space_ss.py    SRVGGNetCompact (class cut out by AST)     -> pins oracle/enhancer_oracle.srvgg_forward
   lib/core/diffusion.py                    get_noise_scales                          -> pins oracle/nerf_oracle.get_noise_scales,
                                                                                         mvedit_b200.pipeline scheduler.noise_scales
   lib/core/utils/geometry_utils.py         get_ray_directions / get_rays / depth_to_normal / normalize_depth   (mcubes, skimage stubbed)
@@ -203,6 +204,23 @@ def main():
                tm_inv=tm.inverse_lut(ys).numpy(), tm_inv_lin=tm.inverse_lut(ys, output_mode='linear').numpy(),
                tm_smooth=tm.smooth_forward(xs).numpy(), tm_alb=alb.numpy(), tm_shd=shd.numpy(),
                tm_shaded=tm.lut(tm.inverse_lut(alb) + shd.clamp(min=1e-6).log2()).numpy())       # mvedit_3d_pipeline.py:418-422
+
+    # ---- SRVGGNetCompact (image_space_ss.py:8-75): the class cut out of its file (mmgen / mmcv imports are not needed by it)
+    src = open(os.path.join(REF, 'lib/models/decoders/image_space_ss.py')).read()
+    tree = ast.parse(src)
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == 'SRVGGNetCompact'][0]
+    cls.decorator_list = []
+    env = dict(nn=torch.nn, F=torch.nn.functional, torch=torch)
+    exec(compile(ast.Module(body=[cls], type_ignores=[]), 'image_space_ss.py', 'exec'), env)
+    torch.manual_seed(21)
+    net = env['SRVGGNetCompact'](num_in_ch=3, num_out_ch=3, num_feat=8, num_conv=3, upscale=4, act_type='prelu').eval()
+    with torch.no_grad():
+        for m in net.body:
+            if isinstance(m, torch.nn.PReLU):
+                m.weight.uniform_(0.05, 0.4)
+        xin = torch.rand(2, 3, 6, 5, generator=g)
+        yout = net(xin)
+    out.update(sr_x=xin.numpy(), sr_y=yout.numpy(), **{'sr_sd.' + k: v.numpy() for k, v in net.state_dict().items()})
 
     np.savez_compressed(OUT, **out)
     print('wrote', OUT, len(out), 'arrays', os.path.getsize(OUT), 'bytes')

@@ -41,7 +41,7 @@ def parts():
                 pe=torch.randn(2 * N, 77, 768, device=dev, generator=g))
 
 
-def make_pipe(parts, scheduler, tonemapping=None, lpips=False):
+def make_pipe(parts, scheduler, tonemapping=None, lpips=False, enhancer=False):
     from mvedit_b200.mvedit_3d_pipeline import MVEdit3DPipeline
     from mvedit_b200.nerf import BaseNeRF
     from mvedit_b200.ingp_decoder import iNGPDecoder
@@ -53,8 +53,12 @@ def make_pipe(parts, scheduler, tonemapping=None, lpips=False):
         patch_loss = LPIPSLoss(random_lpips_state_dict(0, 'cuda'), loss_weight=1.2)
     nerf = BaseNeRF(grid_size=128, decoder=dec, patch_loss=patch_loss, patch_size=64).cuda()
     seg = lambda x: (x.amax(dim=1, keepdim=True) > 0.5).float()          # TRACER stand-in: any images -> masks callable
-    return MVEdit3DPipeline(parts['vae'], None, None, parts['unet'], parts['cns'], scheduler, nerf, segmentation=seg,
-                            tonemapping=tonemapping), dec
+    image_enhancer = None
+    if enhancer:         # init_mvedit: SRVGGNetCompact(3, 3, 64, num_conv=32, upscale=4, 'prelu') (lib/pipelines/utils.py:212-215)
+        from mvedit_b200.enhancer import SRVGGNetCompact, random_srvgg_state_dict
+        image_enhancer = SRVGGNetCompact(random_srvgg_state_dict(0, num_conv=32, device='cuda'), num_conv=32)
+    return MVEdit3DPipeline(parts['vae'], None, None, parts['unet'], parts['cns'], scheduler, nerf, image_enhancer=image_enhancer,
+                            segmentation=seg, tonemapping=tonemapping), dec
 
 
 def call(pipe, parts, **kw):
@@ -81,11 +85,11 @@ def test_call_runs_nerf_stage(parts, sched, mode, blend, ref):
     """ref: False = plain CFG batch; True = cross-image attention against the view's own input image (the reference's default,
     latents (N,4,128,64)); 'cond' = against separate conditioning images; 'extra' = a third ControlNet fed the input images;
     'runner' = what Adapter3DRunner builds (adapter3d.py:88,780; lib/pipelines/utils.py:231-232): reference attention, the Tonemapping
-    module, the LPIPS patch loss with the default weight schedule."""
+    module, the LPIPS patch loss with the default weight schedule, the SRVGG enhancer on the 128^2 renders."""
     sch = _schedulers()[sched]()
     if ref == 'runner':
         from mvedit_b200.tonemapping import Tonemapping
-        pipe, dec = make_pipe(parts, sch, tonemapping=Tonemapping(), lpips=True)
+        pipe, dec = make_pipe(parts, sch, tonemapping=Tonemapping(), lpips=True, enhancer=True)
     else:
         pipe, dec = make_pipe(parts, sch)
     before = {k: v.detach().clone() for k, v in dec.state_dict().items()}

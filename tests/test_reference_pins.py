@@ -152,3 +152,12 @@ def test_tonemapping_module_and_oracle():
         np.testing.assert_allclose(shaded.numpy(), PINS['tm_shaded'], rtol=1e-5, atol=1e-6)
     arr, n = PT().knots()
     assert n == 16 and np.allclose(np.array(arr[:16]), PINS['tm_lut_x']) and np.allclose(np.array(arr[16:]), PINS['tm_lut_y'], atol=1e-7)
+
+
+def test_srvgg_enhancer_oracle():
+    """oracle/enhancer_oracle.srvgg_forward against the reference's SRVGGNetCompact (image_space_ss.py:8-75) on seeded weights."""
+    from oracle.enhancer_oracle import srvgg_forward
+    sd = {k[len('sr_sd.'):]: torch.from_numpy(PINS[k]) for k in PINS.files if k.startswith('sr_sd.')}
+    assert len(sd) == 5 * 2 + 4                                       # 5 convolutions (weight + bias), 4 PReLUs
+    y = srvgg_forward(sd, torch.from_numpy(PINS['sr_x']), num_conv=3, upscale=4)
+    np.testing.assert_allclose(y.numpy(), PINS['sr_y'], rtol=1e-5, atol=1e-6)
