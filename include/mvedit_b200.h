@@ -129,6 +129,9 @@ int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N,
 /* 3x3 convolution, stride 1, pad 1, as an implicit GEMM (no im2col buffer): X [B,H,W,Cin] bf16 NHWC,
  * Wt [Cout,3,3,Cin] bf16, Y [B*H*W, ldy] bf16.  Epilogue as mve_gemm_bf16 with rows_per_group = H*W
  * (row_bias [B,Cout] = the time-embedding projection of a ResnetBlock2D).  Cin % 64 == 0.
+ * act | 0x100 allows split-K for few-tile problems with K >= 1024 (the 8^2 / 16^2 levels of the LPIPS VGG: one CTA per output tile
+ * is bound by what a single SM pulls from L2): CTAs reduce K slices into an fp32 workspace with atomics and a second kernel applies
+ * the epilogue -- the sums are then not bit-reproducible run to run, which is why it is opt-in.
  * Replaces torch.nn.functional.conv2d (cuDNN) on the UNet path. */
 int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t B, uint32_t H, uint32_t W,
                      uint32_t Cin, uint32_t Cout, uint32_t ldy,

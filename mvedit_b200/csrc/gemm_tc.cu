@@ -523,6 +523,8 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32
                      uint32_t ldy, const float* bias, const float* row_bias, uint32_t ldrb, const void* residual, uint32_t ldr, int act,
                      float alpha, const float* act_param, void* stream) {
     if (Bn == 0) return 0;
+    const bool allow_split_k = (act & 0x100) != 0;      // opt-in: fp32 partial sums meet in atomic order -> not bit-reproducible
+    act &= 0xff;
     MVE_ARG(act != 6 || act_param != nullptr, "conv3x3: act 6 (PReLU) needs act_param [Cout]");
     MVE_ARG(Cin % BK == 0, "conv3x3: Cin must be a multiple of 64 (pad channels)");
     MVE_ARG((W <= 128 && 128 % W == 0) || W % 128 == 0, "conv3x3: W must divide 128 or be a multiple of 128");
@@ -569,7 +571,7 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32
         static int enabled = -1;
         if (enabled < 0) { const char* e = getenv("MVE_CONV_SPLITK"); enabled = (e && e[0] == '0') ? 0 : 1; }
         const uint32_t tiles = p.m_tiles * p.n_tiles;
-        if (enabled && tc_.mt == 1 && act != 3 && Cout % 8 == 0 && (ldy % 8) == 0 && tiles * 4 <= (uint32_t)kNumSM && p.num_kb >= 16 &&
+        if (enabled && allow_split_k && tc_.mt == 1 && act != 3 && Cout % 8 == 0 && (ldy % 8) == 0 && tiles * 4 <= (uint32_t)kNumSM && p.num_kb >= 16 &&
             (size_t)M * Cout <= SPLITK_WS_FLOATS) {
             uint32_t sp = p.num_kb / 8;
             if (sp > (uint32_t)kNumSM / tiles) sp = (uint32_t)kNumSM / tiles;
