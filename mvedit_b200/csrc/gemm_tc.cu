@@ -113,10 +113,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
 
     const uint32_t num_tiles = p.m_tiles * p.n_tiles * p.splits;
     // tile -> (m tile, n tile, first and one-past-last k block of this CTA's K slice)
-    auto decode = [&](const uint32_t tile, uint32_t& mt, uint32_t& nt, uint32_t& kb0, uint32_t& kb1) {
-        const uint32_t sp = tile % p.splits, t2 = tile / p.splits;
-        mt = t2 / p.n_tiles; nt = t2 % p.n_tiles;
-        kb0 = sp * p.num_kb / p.splits; kb1 = (sp + 1) * p.num_kb / p.splits;
+    // (scalars captured BY VALUE: a reference capture of the kernel parameter struct would force it into local memory and turn every
+    //  p.field read of the epilogue into a local load -- measured: the whole GEMM family 2x slower)
+    const uint32_t d_splits = p.splits, d_n_tiles = p.n_tiles, d_num_kb = p.num_kb;
+    auto decode = [d_splits, d_n_tiles, d_num_kb](const uint32_t tile, uint32_t& mt, uint32_t& nt, uint32_t& kb0, uint32_t& kb1) {
+        if (d_splits == 1) {
+            mt = tile / d_n_tiles; nt = tile % d_n_tiles; kb0 = 0; kb1 = d_num_kb;
+            return;
+        }
+        const uint32_t sp = tile % d_splits, t2 = tile / d_splits;
+        mt = t2 / d_n_tiles; nt = t2 % d_n_tiles;
+        kb0 = sp * d_num_kb / d_splits; kb1 = (sp + 1) * d_num_kb / d_splits;
     };
 
     if (warp == 0) {

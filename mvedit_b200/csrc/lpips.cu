@@ -111,13 +111,14 @@ __global__ void k_maxpool2x2_bwd(const __nv_bfloat16* __restrict__ x, const __nv
 template <int CPL>
 __global__ void __launch_bounds__(256) k_lpips_layer(const __nv_bfloat16* __restrict__ feat, uint32_t P, uint32_t HW,
                                                      const float* __restrict__ lin_w, const float* __restrict__ gscale,
-                                                     float* __restrict__ loss, __nv_bfloat16* __restrict__ g_feat) {
-    constexpr int C = CPL * 32, PIX_PER_WARP = 8;
-    // a CTA covers 64 consecutive pixels of ONE image (HW is a multiple of 64 or the grid is per image): one loss atomic per CTA --
-    // 16 384 same-address atomics, one per pixel, serialise in L2 and cost 27 us on the 128^2 level
-    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t blocks_per_img = (HW + 63) / 64, img = blockIdx.x / blocks_per_img;
-    const uint32_t pix0 = (blockIdx.x % blocks_per_img) * 64 + wib * PIX_PER_WARP;
+                                                     float* __restrict__ loss, __nv_bfloat16* __restrict__ g_feat,
+                                                     const uint32_t PIX_PER_WARP) {
+    constexpr int C = CPL * 32;
+    // a CTA covers 8 * PIX_PER_WARP consecutive pixels of ONE image and issues one loss atomic -- 16 384 same-address atomics, one
+    // per pixel, serialise in L2 and cost 27 us on the 128^2 level; the small levels keep one pixel per warp (latency, not atomics)
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, per_block = 8 * PIX_PER_WARP;
+    const uint32_t blocks_per_img = (HW + per_block - 1) / per_block, img = blockIdx.x / blocks_per_img;
+    const uint32_t pix0 = (blockIdx.x % blocks_per_img) * per_block + wib * PIX_PER_WARP;
     float w[CPL];
 #pragma unroll
     for (int j = 0; j < CPL; j++) w[j] = lin_w[lane * CPL + j];
@@ -212,14 +213,16 @@ int mve_lpips_layer(const void* feat, uint32_t P, uint32_t HW, uint32_t C, const
                     void* g_feat, void* stream) {
     MVE_ARG(C == 64 || C == 128 || C == 256 || C == 512, "lpips layer: C must be 64, 128, 256 or 512 (VGG16)");
     if (P * HW == 0) return 0;
-    const uint32_t blocks = P * cdiv(HW, 64);
+    uint32_t ppw = (uint32_t)((size_t)P * HW / (8u * (uint32_t)kNumSM));       // >= one CTA per SM before warps take several pixels
+    ppw = ppw < 1 ? 1 : (ppw > 8 ? 8 : ppw);
+    const uint32_t blocks = P * cdiv(HW, 8 * ppw);
     cudaStream_t s = (cudaStream_t)stream;
     const __nv_bfloat16* f = (const __nv_bfloat16*)feat;
     __nv_bfloat16* g = (__nv_bfloat16*)g_feat;
-    if (C == 64) k_lpips_layer<2><<<blocks, 256, 0, s>>>(f, P, HW, lin_w, gscale, loss, g);
-    else if (C == 128) k_lpips_layer<4><<<blocks, 256, 0, s>>>(f, P, HW, lin_w, gscale, loss, g);
-    else if (C == 256) k_lpips_layer<8><<<blocks, 256, 0, s>>>(f, P, HW, lin_w, gscale, loss, g);
-    else k_lpips_layer<16><<<blocks, 256, 0, s>>>(f, P, HW, lin_w, gscale, loss, g);
+    if (C == 64) k_lpips_layer<2><<<blocks, 256, 0, s>>>(f, P, HW, lin_w, gscale, loss, g, ppw);
+    else if (C == 128) k_lpips_layer<4><<<blocks, 256, 0, s>>>(f, P, HW, lin_w, gscale, loss, g, ppw);
+    else if (C == 256) k_lpips_layer<8><<<blocks, 256, 0, s>>>(f, P, HW, lin_w, gscale, loss, g, ppw);
+    else k_lpips_layer<16><<<blocks, 256, 0, s>>>(f, P, HW, lin_w, gscale, loss, g, ppw);
     MVE_CHECK_LAUNCH("mve_lpips_layer");
     return 0;
 }
