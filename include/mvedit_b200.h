@@ -119,7 +119,7 @@ int mve_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int bi
  * act: 0 none, 1 SiLU, 2 GELU(erf), 3 GEGLU: every 256 columns of B hold [128 value | 128 gate] rows of a diffusers GEGLU
  * projection and C gets the N/2 products value * gelu(gate) (ldc >= N/2; no row_bias / residual; N % 256 == 0);
  * 4 ReLU; 5 ReLU backward gate: C = residual > 0 ? (acc + bias) * alpha : 0 (residual = the forward activation, not added);
- * 6 PReLU with per-column slopes act_param [N] (f32; NULL otherwise).
+ * 6 PReLU with per-column slopes act_param [N] (f32; NULL otherwise) -- mve_conv3x3_bf16 only.
  * Replaces torch.nn.functional.linear / 1x1 conv (cuBLAS) on the UNet path. */
 int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N, uint32_t K,
                   uint32_t lda, uint32_t ldb, uint32_t ldc,

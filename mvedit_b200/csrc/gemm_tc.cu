@@ -82,7 +82,10 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     return v;
 }
 
-template <int BN, int MODE, int MT = 1, int ACC = 2>
+// RARE = true: the instantiation that also carries the split-K reduction and the PReLU epilogue (64-wide conv tiles only: the LPIPS VGG
+// and the SRVGG enhancer).  The hot instantiations (RARE = false) do not contain that code: with it inlined the generic epilogue -- the
+// bottleneck of the short-K GEMMs and of the 256-row tiles -- ran 1.4-2.4x slower (profiles/r02_bench_*: 74 -> 143 ms of GEMM per step).
+template <int BN, int MODE, int MT = 1, int ACC = 2, bool RARE = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                             const GemmParams p) {
     using C_ = Cfg<BN, MT, ACC>;
@@ -111,13 +114,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const uint32_t num_tiles = p.m_tiles * p.n_tiles * p.splits;
+    const uint32_t num_tiles = p.m_tiles * p.n_tiles * (RARE ? p.splits : 1u);
     // tile -> (m tile, n tile, first and one-past-last k block of this CTA's K slice)
-    // (scalars captured BY VALUE: a reference capture of the kernel parameter struct would force it into local memory and turn every
-    //  p.field read of the epilogue into a local load -- measured: the whole GEMM family 2x slower)
-    const uint32_t d_splits = p.splits, d_n_tiles = p.n_tiles, d_num_kb = p.num_kb;
+    const uint32_t d_splits = RARE ? p.splits : 1u, d_n_tiles = p.n_tiles, d_num_kb = p.num_kb;
     auto decode = [d_splits, d_n_tiles, d_num_kb](const uint32_t tile, uint32_t& mt, uint32_t& nt, uint32_t& kb0, uint32_t& kb1) {
-        if (d_splits == 1) {
+        if (!RARE || d_splits == 1) {
             mt = tile / d_n_tiles; nt = tile % d_n_tiles; kb0 = 0; kb1 = d_num_kb;
             return;
         }
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
                 }
                 tc::tmem_ld_wait();
                 const uint32_t col0 = n0 + c;
-                if (p.splits > 1) {
+                if (RARE && p.splits > 1) {
                     if (row_ok) {
                         float* wrow = p.ws + (size_t)row * p.N + col0;
 #pragma unroll
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
                                 float x = __uint_as_float(v[g * 8 + i]);
                                 if (p.bias) x += p.bias[col0 + g * 8 + i];
                                 if (rb) x += rb[col0 + g * 8 + i];
-                                if (p.act == 6) x = x > 0.f ? x : x * p.act_param[col0 + g * 8 + i];
+                                if (RARE && p.act == 6) x = x > 0.f ? x : x * p.act_param[col0 + g * 8 + i];
                                 f[i] = act_apply(x, p.act) * p.alpha;
                             }
                             if (res) {
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const __grid_constan
                             float x = __uint_as_float(v[i]);
                             if (p.bias) x += p.bias[col0 + i];
                             if (rb) x += rb[col0 + i];
-                            if (p.act == 6) x = x > 0.f ? x : x * p.act_param[col0 + i];
+                            if (RARE && p.act == 6) x = x > 0.f ? x : x * p.act_param[col0 + i];
                             x = act_apply(x, p.act) * p.alpha;
                             if (res) x = p.act == 5 ? (__bfloat162float(res[i]) > 0.f ? x : 0.f) : x + __bfloat162float(res[i]);
                             out[i] = __float2bfloat16(x);
@@ -394,19 +395,19 @@ TileCfg pick_tile(uint32_t M, uint32_t N, uint32_t K, int act) {
     return {bn, 1, 2};
 }
 
-template <int BN, int MODE, int MT = 1, int ACC = 2>
+template <int BN, int MODE, int MT = 1, int ACC = 2, bool RARE = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
     using C_ = Cfg<BN, MT, ACC>;
     static bool configured[16] = {};
     int dev = 0;
     MVE_CUDA(cudaGetDevice(&dev));
     if (!configured[dev & 15]) {
-        MVE_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, MODE, MT, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
+        MVE_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, MODE, MT, ACC, RARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
         configured[dev & 15] = true;
     }
     const uint32_t tiles = p.m_tiles * p.n_tiles * p.splits;
     const uint32_t grid = tiles < (uint32_t)kNumSM ? tiles : (uint32_t)kNumSM;
-    k_gemm_tc<BN, MODE, MT, ACC><<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    k_gemm_tc<BN, MODE, MT, ACC, RARE><<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, p);
     MVE_CHECK_LAUNCH("k_gemm_tc");
     if (p.splits > 1) {
         k_splitk_finish<<<cdiv((size_t)p.M * (p.N / 8), 256), 256, 0, stream>>>(p);
@@ -417,6 +418,10 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
 
 template <int MODE>
 int dispatch(TileCfg t, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t s) {
+    if (p.splits > 1 || p.act == 6) {
+        if (MODE != 1 || t.bn != 64 || t.mt != 1) { mve_set_error("split-K / PReLU epilogues exist for 64-wide convolution tiles only"); return -1; }
+        return launch<64, 1, 1, 2, true>(tmA, tmB, p, s);
+    }
     if (t.mt == 2)
         return t.bn == 128 ? launch<128, MODE, 2, 2>(tmA, tmB, p, s)
                            : (t.bn == 160 ? launch<160, MODE, 2, 1>(tmA, tmB, p, s) : launch<256, MODE, 2, 1>(tmA, tmB, p, s));
@@ -462,7 +467,9 @@ int mve_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint6
     uint64_t h = 1469598103934665603ull;
     for (int i = 0; i < 14; i++) { h ^= key[i]; h *= 1099511628211ull; }
     Entry& e = cache[(h >> 20) & 511];
-    {
+    static int use_cache = -1;
+    if (use_cache < 0) { const char* ev = getenv("MVE_TMAP_CACHE"); use_cache = (ev && ev[0] == '0') ? 0 : 1; }
+    if (use_cache) {
         std::lock_guard<std::mutex> lock(mu);
         if (e.valid && memcmp(e.key, key, sizeof(key)) == 0) { *out = e.map; return 0; }
     }
@@ -494,7 +501,7 @@ int mve_gemm_bf16(const void* A, const void* B, void* C, uint32_t M, uint32_t N,
                   const float* bias, const float* row_bias, uint32_t rows_per_group, uint32_t ldrb, const void* residual, uint32_t ldr,
                   int act, float alpha, const float* act_param, void* stream) {
     if (M == 0 || N == 0) return 0;
-    MVE_ARG(act != 6 || act_param != nullptr, "gemm: act 6 (PReLU) needs act_param [N]");
+    MVE_ARG(act != 6, "gemm: the PReLU epilogue (act 6) exists for mve_conv3x3_bf16 only");
     MVE_ARG(K % BK == 0 && K > 0, "gemm: K must be a positive multiple of 64");
     MVE_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (16-byte TMA strides)");
     MVE_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "gemm: pointers must be 16-byte aligned");
@@ -537,6 +544,7 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32
     MVE_ARG((W <= 128 && 128 % W == 0) || W % 128 == 0, "conv3x3: W must divide 128 or be a multiple of 128");
     const uint32_t M = Bn * H * W;
     TileCfg tc_ = pick_tile(M, Cout, 9 * Cin, act);
+    if (act == 6) tc_ = {64, 1, 2};            // the PReLU epilogue lives in the 64-wide instantiation (SRVGG: Cout = 64 / 48)
     // the tile's pixels as a TMA box {64 ch, BW, BH, BB}: whole image rows / whole images (a tall tile falls back if it cannot)
     uint32_t PIX, BW, BH, BB;
     for (;;) {
@@ -578,7 +586,7 @@ int mve_conv3x3_bf16(const void* X, const void* Wt, void* Y, uint32_t Bn, uint32
         static int enabled = -1;
         if (enabled < 0) { const char* e = getenv("MVE_CONV_SPLITK"); enabled = (e && e[0] == '0') ? 0 : 1; }
         const uint32_t tiles = p.m_tiles * p.n_tiles;
-        if (enabled && allow_split_k && tc_.mt == 1 && act != 3 && Cout % 8 == 0 && (ldy % 8) == 0 && tiles * 4 <= (uint32_t)kNumSM && p.num_kb >= 16 &&
+        if (enabled && allow_split_k && tc_.mt == 1 && tc_.bn == 64 && act != 3 && Cout % 8 == 0 && (ldy % 8) == 0 && tiles * 4 <= (uint32_t)kNumSM && p.num_kb >= 16 &&
             (size_t)M * Cout <= SPLITK_WS_FLOATS) {
             uint32_t sp = p.num_kb / 8;
             if (sp > (uint32_t)kNumSM / tiles) sp = (uint32_t)kNumSM / tiles;

@@ -106,7 +106,7 @@ def test_lpips_value_and_gradient_vs_oracle(P, S):
     # (two separate evaluations: the split-K convolutions of the deep levels sum their fp32 partials in atomic order)
     torch.testing.assert_close(m(pred.permute(0, 3, 1, 2), tgt.permute(0, 3, 1, 2), weight=w) * 0.9, loss, rtol=1e-3, atol=1e-7)
     torch.testing.assert_close(LPIPS(sd)(pred, tgt), d, rtol=1e-3, atol=1e-7)
-    assert float(LPIPS(sd)(tgt, tgt).abs().max()) < 1e-6 * float(d.max())
+    assert float(LPIPS(sd)(tgt, tgt).abs().max()) < 1e-4 * float(d.max())        # ~1e-8 vs ~2e-3: the two halves of the batch sum in different orders
 
 
 def test_gradient_descends_the_oracle_distance():
