@@ -74,7 +74,7 @@ class LPIPS:
                 pooled = torch.empty(B, H // 2, W // 2, C, dtype=torch.bfloat16, device=cur.device)
                 call('mve_maxpool2x2_bf16', ptr(cur), c_u32(B), c_u32(H), c_u32(W), c_u32(C), ptr(pooled), stream())
                 cur = pooled
-            cur = T.conv3x3(cur, L['w'], bias=L['b'], act='relu', split_k=True)
+            cur = T.conv3x3(cur, L['w'], bias=L['b'], act='relu', split_k=True, family='lpips')
             acts.append(cur)
         feats.append(cur)
         return x, acts, feats
@@ -116,15 +116,15 @@ class LPIPS:
             first_of_slice = k == 0 or self.layers[k - 1]['slice'] != L['slice']
             if not first_of_slice:
                 # d / d (previous conv's output), gated by that ReLU: its pre-activation gradient
-                g = T.conv3x3(g, L['wT'], act='relu_gate', residual=acts[k - 1][:P], split_k=True)
+                g = T.conv3x3(g, L['wT'], act='relu_gate', residual=acts[k - 1][:P], split_k=True, family='lpips')
             elif k > 0:
-                gp = T.conv3x3(g, L['wT'], split_k=True)           # gradient w.r.t. the pooled features of the slice below
+                gp = T.conv3x3(g, L['wT'], split_k=True, family='lpips')           # gradient w.r.t. the pooled features of the slice below
                 below = feats[L['slice'] - 2]
                 _, H, W, C = below.shape
                 g = grads[L['slice'] - 2]
                 call('mve_maxpool2x2_relu_backward_bf16', ptr(below), ptr(gp), c_u32(P), c_u32(H), c_u32(W), c_u32(C), ptr(g), stream())
             else:
-                g64 = T.conv3x3(g, L['wT'], split_k=True)          # gradient of the normalised, padded input
+                g64 = T.conv3x3(g, L['wT'], split_k=True, family='lpips')          # gradient of the normalised, padded input
                 g_pred = torch.empty(P, h, w, 3, dtype=torch.float32, device=dev)
                 call('mve_lpips_input_grad', ptr(g64), c_u32(P * h * w), ptr(g_pred), stream())
         return loss, g_pred, per_img

@@ -45,7 +45,7 @@ def geglu_interleave(w, b, tile=256):
     return w[perm].contiguous(), (None if b is None else b[perm].contiguous())
 
 
-def conv3x3(x, w, bias=None, row_bias=None, residual=None, act=None, alpha=1.0, out=None, act_param=None, split_k=False):
+def conv3x3(x, w, bias=None, row_bias=None, residual=None, act=None, alpha=1.0, out=None, act_param=None, split_k=False, family=None):
     """x [B,H,W,Cin] bf16 NHWC, w [Cout,3,3,Cin] bf16 -> [B,H,W,Cout] bf16.  stride 1, pad 1.
     row_bias [B,Cout] f32 is added per image (time embedding); residual [B,H,W,Cout] is added after scaling.
     split_k: allow the split-K path for few-tile, long-K problems (fp32 atomics: not bit-reproducible run to run)."""
@@ -58,7 +58,8 @@ def conv3x3(x, w, bias=None, row_bias=None, residual=None, act=None, alpha=1.0, 
     call('mve_conv3x3_bf16', ptr(x), ptr(w), ptr(out), c_u32(B), c_u32(H), c_u32(W), c_u32(Cin), c_u32(Cout), c_u32(out.stride(2)),
          ptr(bias), raw_ptr(row_bias), c_u32(row_bias.stride(0) if row_bias is not None else 0), ptr(residual),
          c_u32(residual.stride(2) if residual is not None else 0), c_int(ACT[act] | (0x100 if split_k else 0)),
-         c_f32(alpha), ptr(act_param), stream(), _meta=dict(flops=2.0 * B * H * W * Cout * 9 * Cin, shape='conv B%d %dx%d Cin%d Cout%d' % (B, H, W, Cin, Cout)))
+         c_f32(alpha), ptr(act_param), stream(), _meta=dict(flops=2.0 * B * H * W * Cout * 9 * Cin, family=family,
+                                                            shape='conv B%d %dx%d Cin%d Cout%d' % (B, H, W, Cin, Cout)))
     return out
 
 
