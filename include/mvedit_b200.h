@@ -371,6 +371,43 @@ int mve_gs_blend_backward(const int32_t* ranges, const int32_t* point_list, cons
                           const float* g_color, const float* g_depth, const float* g_alpha,
                           float* d_xy, float* d_conic_opacity, float* d_feat, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * B5: triangle-mesh rasteriser -- the nvdiffrast.torch ops MeshRenderer uses
+ * (lib/models/decoders/mesh_renderer/base_mesh_renderer.py:204 RasterizeCudaContext, :241-242 dr.rasterize, :247-278 dr.interpolate,
+ * :296-298 dr.antialias; texture-space rasterisation :407-410, :442, :521).  nvdiffrast is an un-vendored dependency
+ * (requirements.txt:3): semantics per SURVEY.md Appendix C, restated in oracle/raster_oracle.py.  Instance mode only
+ * (one topology, B views; the reference's "range mode" needs num_scenes > 1, which MVEdit never uses).
+ * pos [B,V,4] (pos_batched != 0) or [V,4] clip-space f32; tri [F,3] i32; images are [B,H,W,*] f32, row y <-> NDC y = (2y+1)/H - 1.
+ * ------------------------------------------------------------------------- */
+
+/* dr.rasterize: rast [B,H,W,4] = (u, v, z/w, triangle id + 1; 0 = empty), u / v = perspective-correct barycentrics of vertex 0 / 1;
+ * rast_db [B,H,W,4] = (du/dX, du/dY, dv/dX, dv/dY) per pixel, or NULL (grad_db=False).  Nearest z/w in [-1, 1] wins, ties go to the
+ * lower triangle id (deterministic).  Triangles with a vertex at w <= 0 are dropped (no near-plane clipping).
+ * Scratch (caller-allocated, contents irrelevant): zbuf [B*H*W] u64, queue [1 + B*F] u32.  Three launches, no host sync. */
+int mve_rasterize_fwd(const float* pos, const int32_t* tri, uint32_t B, uint32_t V, uint32_t F, uint32_t H, uint32_t W,
+                      int pos_batched, void* zbuf, uint32_t* queue, float* rast, float* rast_db, void* stream);
+/* d rast (u, v, z/w; the id channel and rast_db carry no gradient) -> g_pos [B or 1, V, 4], ACCUMULATED into a zeroed buffer. */
+int mve_rasterize_bwd(const float* pos, const int32_t* tri, uint32_t B, uint32_t V, uint32_t F, uint32_t H, uint32_t W,
+                      int pos_batched, const float* rast, const float* g_rast, float* g_pos, void* stream);
+
+/* dr.interpolate: out [B,H,W,C] = u a0 + v a1 + (1-u-v) a2 over attr [B or 1, Va, C] with the attribute triangles tri [F,3]
+ * (zeros on empty pixels); out_da [B,H,W,2C] = (d/dX, d/dY) of every attribute (diff_attrs='all'; needs rast_db) or NULL. */
+int mve_interpolate_fwd(const float* attr, const int32_t* tri, const float* rast, const float* rast_db, uint32_t B, uint32_t H,
+                        uint32_t W, uint32_t Va, uint32_t F, uint32_t C, int attr_batched, float* out, float* out_da, void* stream);
+/* g_out -> g_attr (ACCUMULATED into a zeroed buffer) and g_rast [B,H,W,4] = (d/du, d/dv, 0, 0) (written; may be NULL). */
+int mve_interpolate_bwd(const float* attr, const int32_t* tri, const float* rast, uint32_t B, uint32_t H, uint32_t W, uint32_t Va,
+                        uint32_t F, uint32_t C, int attr_batched, const float* g_out, float* g_attr, float* g_rast, void* stream);
+
+/* dr.antialias: out = color + silhouette blends.  opp [F,3] i32: for edge k of a triangle (the edge facing its vertex k) the vertex
+ * opposite to that edge in the adjacent triangle, -1 on an open edge (mvedit_b200.mesh_raster.edge_opposites; it stands in for
+ * nvdiffrast's internal edge hash). */
+int mve_antialias_fwd(const float* color, const float* rast, const float* pos, const int32_t* tri, const int32_t* opp, uint32_t B,
+                      uint32_t H, uint32_t W, uint32_t C, uint32_t V, uint32_t F, int pos_batched, float* out, void* stream);
+/* g_out -> g_color [B,H,W,C] (written) and g_pos [B or 1, V, 4] (ACCUMULATED into a zeroed buffer; may be NULL). */
+int mve_antialias_bwd(const float* color, const float* rast, const float* pos, const int32_t* tri, const int32_t* opp, uint32_t B,
+                      uint32_t H, uint32_t W, uint32_t C, uint32_t V, uint32_t F, int pos_batched, const float* g_out,
+                      float* g_color, float* g_pos, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

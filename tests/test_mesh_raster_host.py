@@ -1,0 +1,219 @@
+"""CPU checks of the mesh rasteriser (seam B5) without a GPU: the kernel source compiled as plain C++ (tests/host_harness.py) runs
+the same per-triangle / per-pixel code and is compared with oracle/raster_oracle.py -- ids and barycentrics bit for bit, gradients
+against the oracle's autograd -- through the product's Python mirror (mvedit_b200/mesh_raster.py) routed to the harness."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import raster_oracle as ro
+from tests import host_harness, synth_mesh
+from mvedit_b200 import mesh_raster as dr
+
+
+@pytest.fixture(autouse=True)
+def _route():
+    with host_harness.routed(dr):
+        yield
+
+
+def _scene(kind, seed=0):
+    rng = np.random.default_rng(seed)
+    if kind == 'sphere':
+        v, f = synth_mesh.icosphere(2)
+        pos = synth_mesh.project(v * 0.6, synth_mesh.surround_poses(3, seed), fov_deg=30.0)
+        return pos.astype(np.float32), f.astype(np.int32), (48, 40)
+    if kind == 'soup':                       # random small triangles at random depths, both windings, some behind the camera / off screen
+        n = 300
+        c = rng.uniform(-1.2, 1.2, (n, 1, 2))
+        xy = c + rng.normal(0, 0.08, (n, 3, 2))
+        z = rng.uniform(-1.3, 1.3, (n, 1, 1)) + rng.normal(0, 0.05, (n, 3, 1))
+        w = rng.uniform(0.5, 2.0, (n, 3, 1))
+        w[:5] = -w[:5]
+        w[5:8, 0] = 0.0
+        v = np.concatenate([xy * w, z * w, w], axis=-1).reshape(1, n * 3, 4)
+        f = np.arange(n * 3).reshape(n, 3)
+        f[10] = f[10][[0, 0, 1]]            # zero-area
+        return v.astype(np.float32), f.astype(np.int32), (37, 53)
+    if kind == 'large':                      # screen-filling, overlapping, interpenetrating triangles -> the queued path
+        v = np.array([[[-1.5, -1.5, 0.2, 1], [1.5, -1.5, 0.2, 1], [1.5, 1.5, 0.2, 1], [-1.5, 1.5, 0.2, 1],
+                       [-0.9, -0.8, -0.5, 1], [0.9, -0.7, 0.9, 1], [0.0, 0.95, 0.1, 1],
+                       [-3, -3, 0.5, 2], [3, -3, 0.5, 2], [0, 3, -0.5, 2]]], np.float32)
+        f = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [7, 8, 9], [0, 1, 2]], np.int32)   # the last duplicates the first: tie -> lower id
+        return v, f, (64, 64)
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize('kind', ['sphere', 'soup', 'large'])
+def test_rasterize_matches_oracle_bit_for_bit(kind):
+    pos, tri, res = _scene(kind)
+    r_o, db_o = ro.rasterize(pos, tri, res)
+    rast, db = dr.rasterize(dr.RasterizeCudaContext(), torch.from_numpy(pos), torch.from_numpy(tri), res)
+    rast, db = rast.numpy(), db.numpy()
+    assert (rast[..., 3] == r_o[..., 3]).all()
+    assert (rast[..., 3] > 0).sum() > 50
+    np.testing.assert_array_equal(rast.view(np.uint32), r_o.view(np.uint32))
+    np.testing.assert_array_equal(db.view(np.uint32), db_o.view(np.uint32))
+    fg = rast[..., 3] > 0
+    assert (rast[fg][:, :2] >= 0).all() and (rast[fg][:, 0] + rast[fg][:, 1] <= 1 + 1e-6).all()
+    assert (np.abs(rast[fg][:, 2]) <= 1).all()
+    r2, db2 = dr.rasterize(dr.RasterizeCudaContext(), torch.from_numpy(pos), torch.from_numpy(tri), res, grad_db=False)
+    assert db2.shape[-1] == 0 and (r2.numpy() == rast).all()
+
+
+def test_closed_mesh_is_watertight():
+    """Shared edges are exactly negated edge functions: no pixel inside the silhouette of a closed mesh is left empty."""
+    v, f = synth_mesh.icosphere(3)
+    pos = synth_mesh.project(v * 0.6, synth_mesh.surround_poses(2, 1), fov_deg=30.0).astype(np.float32)
+    H = W = 96
+    rast, _ = dr.rasterize(dr.RasterizeCudaContext(), torch.from_numpy(pos), torch.from_numpy(f.astype(np.int32)), (H, W))
+    fg = (rast[..., 3] > 0).numpy()
+    for b in range(fg.shape[0]):
+        for y in range(H):
+            xs = np.nonzero(fg[b, y])[0]
+            if len(xs):
+                assert fg[b, y, xs[0]:xs[-1] + 1].all()     # a convex silhouette: every row is one run
+        assert 0.1 < fg[b].mean() < 0.6
+    # nearest surface wins: all winners face the camera
+    ids = (rast[..., 3].long() - 1).numpy()
+    for b in range(fg.shape[0]):
+        t = np.unique(ids[b][fg[b]])
+        p = pos[b][f[t]]
+        s = p[..., :2] / p[..., 3:]
+        area = (s[:, 1, 0] - s[:, 0, 0]) * (s[:, 2, 1] - s[:, 0, 1]) - (s[:, 2, 0] - s[:, 0, 0]) * (s[:, 1, 1] - s[:, 0, 1])
+        assert (np.sign(area) == np.sign(area[0])).all()
+
+
+def test_rasterize_depth_matches_analytic_sphere():
+    v, f = synth_mesh.icosphere(4)
+    poses = synth_mesh.surround_poses(1, 0)
+    pos, vcam = synth_mesh.project(v * 0.5, poses, fov_deg=30.0, return_cam=True)
+    H = W = 64
+    rast, _ = dr.rasterize(dr.RasterizeCudaContext(), torch.from_numpy(pos.astype(np.float32)), torch.from_numpy(f.astype(np.int32)), (H, W))
+    depth_attr = torch.from_numpy((-vcam[..., 2:3]).astype(np.float32))
+    inv_d, _ = dr.interpolate(depth_attr, rast, torch.from_numpy(f.astype(np.int32)))
+    fg = rast[..., 3] > 0
+    d = inv_d[..., 0][fg].numpy()
+    dist = np.linalg.norm(poses[0, :3, 3])
+    assert abs(d.min() - (dist - 0.5)) < 5e-3            # nearest point of the sphere of radius 0.5
+    assert d.max() < dist
+
+
+def _rand_like(shape, seed):
+    return torch.from_numpy(np.random.default_rng(seed).normal(size=shape).astype(np.float32))
+
+
+def test_interpolate_forward_backward_vs_oracle():
+    pos, tri, res = _scene('sphere')
+    pos_t, tri_t = torch.from_numpy(pos), torch.from_numpy(tri)
+    rast, db = dr.rasterize(dr.RasterizeCudaContext(), pos_t, tri_t, res)
+    B, V = pos.shape[:2]
+    for batched in (False, True):
+        attr = _rand_like((B if batched else 1, V, 5), 3).requires_grad_(True)
+        rast_l = rast.clone().requires_grad_(True)
+        out, da = dr.interpolate(attr, rast_l, tri_t, rast_db=db, diff_attrs='all')
+        attr_o = attr.detach().double().requires_grad_(True)
+        rast_o = rast.double().requires_grad_(True)
+        out_o, da_o = ro.interpolate(attr_o, rast_o, tri_t, rast_db=db.double(), diff_attrs='all')
+        torch.testing.assert_close(out, out_o.float(), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(da, da_o.float(), rtol=1e-4, atol=1e-6)
+        g = _rand_like(out.shape, 4)
+        out.backward(g)
+        out_o.backward(g.double())
+        torch.testing.assert_close(attr.grad, attr_o.grad.float(), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(rast_l.grad[..., :2], rast_o.grad[..., :2].float(), rtol=1e-4, atol=1e-5)
+        assert (rast_l.grad[..., 2:] == 0).all()
+    out2, da2 = dr.interpolate(attr, rast, tri_t)
+    assert da2.shape[-1] == 0
+
+
+def test_rasterize_backward_vs_oracle_autograd():
+    pos, tri, res = _scene('sphere')
+    tri_t = torch.from_numpy(tri)
+    pos_t = torch.from_numpy(pos).requires_grad_(True)
+    rast, _ = dr.rasterize(dr.RasterizeCudaContext(), pos_t, tri_t, res)
+    g = _rand_like(rast.shape, 5)
+    g[..., 3] = 0
+    rast.backward(g)
+    pos_o = torch.from_numpy(pos).double().requires_grad_(True)
+    ids = rast[..., 3].long() - 1
+    uvz = ro.barycentrics(pos_o, tri_t, ids)
+    torch.testing.assert_close(rast[..., :3].detach(), uvz.float(), rtol=1e-4, atol=2e-5)
+    uvz.backward(g[..., :3].double())
+    scale = pos_o.grad.abs().max()
+    assert scale > 0
+    assert (pos_t.grad - pos_o.grad.float()).abs().max() <= 2e-3 * scale
+
+
+def test_gradient_flows_from_interpolated_attribute_to_positions():
+    """The chain mesh_optim relies on: loss(interpolate(attr, rasterize(pos))) -> d pos (finite-difference check, fp64 oracle chain)."""
+    pos, tri, res = _scene('sphere')
+    tri_t = torch.from_numpy(tri)
+    pos_t = torch.from_numpy(pos).requires_grad_(True)
+    attr = _rand_like((1, pos.shape[1], 3), 7)
+    rast, _ = dr.rasterize(dr.RasterizeCudaContext(), pos_t, tri_t, res)
+    out, _ = dr.interpolate(attr, rast, tri_t)
+    wgt = _rand_like(out.shape, 8)
+    (out * wgt).sum().backward()
+    ids = rast[..., 3].long() - 1
+    pos_o = torch.from_numpy(pos).double().requires_grad_(True)
+    uvz = ro.barycentrics(pos_o, tri_t, ids)
+    rast_o = torch.cat([uvz, rast.detach()[..., 3:].double()], dim=-1)
+    out_o, _ = ro.interpolate(attr.double(), rast_o, tri_t)
+    (out_o * wgt.double()).sum().backward()
+    scale = pos_o.grad.abs().max()
+    assert (pos_t.grad - pos_o.grad.float()).abs().max() <= 2e-3 * scale
+
+
+def test_edge_opposites_matches_oracle():
+    v, f = synth_mesh.icosphere(1)
+    f = np.concatenate([f[:-3], [[0, 1, 2]]]).astype(np.int32)      # open edges and an extra user of some edges
+    opp = dr.edge_opposites(torch.from_numpy(f)).numpy()
+    np.testing.assert_array_equal(opp, ro.edge_opposites(f))
+    closed = dr.edge_opposites(torch.from_numpy(synth_mesh.icosphere(1)[1].astype(np.int32))).numpy()
+    assert (closed >= 0).all()
+
+
+@pytest.mark.parametrize('kind', ['sphere', 'large'])
+def test_antialias_forward_backward_vs_oracle(kind):
+    pos, tri, res = _scene(kind)
+    tri_t = torch.from_numpy(tri)
+    pos_t = torch.from_numpy(pos).requires_grad_(True)
+    rast, _ = dr.rasterize(dr.RasterizeCudaContext(), pos_t.detach(), tri_t, res)
+    B, H, W, _ = rast.shape
+    fg = (rast[..., 3:] > 0).float()
+    color = (torch.cat([_rand_like((B, H, W, 3), 9).abs() * fg, fg, _rand_like((B, H, W, 4), 10)], dim=-1)).requires_grad_(True)
+    out = dr.antialias(color, rast, pos_t, tri_t)
+    color_o = color.detach().double().requires_grad_(True)
+    pos_o = pos_t.detach().double().requires_grad_(True)
+    out_o = ro.antialias(color_o, rast.double(), pos_o, tri)
+    changed = ((out.detach() - color.detach()).abs().sum(-1) > 1e-6)
+    assert changed.float().mean() > 0.004                   # silhouettes were found
+    if kind == 'sphere':                                    # fractional coverage on the alpha channel along the outline
+        assert ((out.detach()[..., 3] > 0.02) & (out.detach()[..., 3] < 0.98)).sum() > 10
+    torch.testing.assert_close(out, out_o.float(), rtol=1e-4, atol=1e-5)
+    interior = ~changed
+    torch.testing.assert_close(out[interior], color[interior])
+    g = _rand_like(out.shape, 11)
+    out.backward(g)
+    out_o.backward(g.double())
+    torch.testing.assert_close(color.grad, color_o.grad.float(), rtol=1e-4, atol=1e-5)
+    scale = pos_o.grad.abs().max()
+    assert scale > 0
+    assert (pos_t.grad - pos_o.grad.float()).abs().max() <= 2e-3 * scale
+
+
+def test_antialias_alpha_tracks_subpixel_motion():
+    """Moving a silhouette by a fraction of a pixel changes the antialiased coverage by about that fraction of the edge length --
+    the property that makes the alpha loss differentiable w.r.t. geometry."""
+    H = W = 32
+    tri = torch.tensor([[0, 1, 2], [0, 2, 3]], dtype=torch.int32)
+
+    def cover(x_edge):
+        v = torch.tensor([[[-0.5, -0.5, 0, 1], [x_edge, -0.5, 0, 1], [x_edge, 0.5, 0, 1], [-0.5, 0.5, 0, 1]]], dtype=torch.float32)
+        rast, _ = dr.rasterize(dr.RasterizeCudaContext(), v, tri, (H, W))
+        a = (rast[..., 3:] > 0).float()
+        return dr.antialias(a, rast, v, tri).sum().item()
+
+    px = 2.0 / W
+    c0, c1 = cover(0.25 + 0.1 * px), cover(0.25 + 0.6 * px)
+    assert abs((c1 - c0) - 0.5 * 16) < 0.3             # the edge is 16 pixels long; it moved half a pixel
