@@ -1,0 +1,92 @@
+"""Mesh-stage host logic vs the reference's own code (fixtures made by tests/golden/make_mesh_pins.py, which RUNS the reference's
+DMTet / auto_normal / regularisers in the build container): same vertices in the same order, same faces in the same order, same losses
+and gradients.  CPU (these pieces are index arithmetic in torch; the rasteriser kernels have their own tests)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mvedit_b200.mesh_renderer import DMTet, Mesh, compute_edge_to_face_mapping, interpolate_hwc, laplacian_smooth_loss, make_tet_grid, normal_consistency
+
+PINS = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'mesh_pins.npz'))
+T = lambda k: torch.from_numpy(PINS[k])
+
+
+def test_dmtet_matches_reference_class():
+    pos, sdf, tets = T('dm_pos').requires_grad_(True), T('dm_sdf').requires_grad_(True), T('dm_tets')
+    dm = DMTet('cpu')
+    verts, faces = dm(pos, sdf, tets)
+    assert (faces.numpy() == PINS['dm_faces']).all()
+    np.testing.assert_allclose(verts.detach().numpy(), PINS['dm_verts'], rtol=0, atol=1e-7)
+    (verts * T('dm_wv')).sum().backward()
+    np.testing.assert_allclose(pos.grad.numpy(), PINS['dm_g_pos'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sdf.grad.numpy(), PINS['dm_g_sdf'], rtol=1e-4, atol=1e-5)
+    # a second extraction with a changed field re-uses the cached grid topology and still agrees with a fresh object
+    sdf2 = (sdf.detach() - 0.12)
+    v_a, f_a = dm(pos.detach(), sdf2, tets)
+    v_b, f_b = DMTet('cpu')(pos.detach(), sdf2, tets)
+    assert (f_a == f_b).all() and (v_a == v_b).all() and f_a.shape[0] != faces.shape[0]
+
+
+def test_dmtet_mesh_is_closed_and_consistently_oriented():
+    pos, sdf, tets = T('dm_pos'), T('dm_sdf'), T('dm_tets')
+    verts, faces = DMTet('cpu')(pos, sdf, tets)
+    e = torch.cat([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]])
+    directed = set(map(tuple, e.tolist()))
+    assert all((b, a) in directed for a, b in directed)          # every edge is used once in each direction
+    assert len(directed) == e.shape[0]
+
+
+def test_make_tet_grid_is_conforming():
+    g = make_tet_grid(3)
+    v, t = g['vertices'], g['indices']
+    assert v.shape == (64, 3) and t.shape == (6 * 27, 4)
+    p = v[t]
+    vol = torch.linalg.det(p[:, 1:] - p[:, :1]) / 6                     # signed: every tet positively oriented (like demo/tets/*.npz)
+    assert torch.allclose(vol.sum(), torch.tensor(1.0), atol=1e-5) and (vol > 1e-6).all()
+    # interior faces are shared by exactly two tets, boundary faces by one
+    fcs = torch.cat([t[:, [0, 1, 2]], t[:, [0, 1, 3]], t[:, [0, 2, 3]], t[:, [1, 2, 3]]]).sort(dim=1).values
+    _, cnt = torch.unique(fcs, dim=0, return_counts=True)
+    assert set(cnt.tolist()) == {1, 2} and (cnt == 1).sum() == 2 * 6 * 9
+
+
+def test_auto_normal_and_regularisers_match_reference():
+    v = T('dm_verts').requires_grad_(True)
+    m = Mesh(v=v, f=T('dm_faces').int())
+    m.auto_normal()
+    np.testing.assert_allclose(m.vn.detach().numpy(), PINS['an_vn'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m.face_normals.detach().numpy(), PINS['an_face_normals'], rtol=1e-5, atol=1e-6)
+    assert m.fn.dtype == torch.int32 and (m.fn == m.f).all()
+    lap = laplacian_smooth_loss(m.v, m.f)
+    nc = normal_consistency(m.face_normals, m.f)
+    np.testing.assert_allclose(lap.item(), PINS['reg_lap'], rtol=1e-5)
+    np.testing.assert_allclose(nc.item(), PINS['reg_nc'], rtol=1e-5)
+    assert (compute_edge_to_face_mapping(m.f).numpy() == PINS['reg_e2f']).all()
+    (lap * 3 + nc * 2 + (m.vn * T('dm_wv')).sum()).backward()
+    np.testing.assert_allclose(v.grad.numpy(), PINS['reg_g_v'], rtol=1e-4, atol=1e-5)
+
+
+def test_interpolate_hwc_matches_reference():
+    np.testing.assert_allclose(interpolate_hwc(T('hwc_x'), 0.5).numpy(), PINS['hwc_y'], rtol=1e-6, atol=1e-7)
+
+
+def test_dmtet_on_the_reference_tet_grid():
+    """The 128-resolution grid the reference ships (demo/tets/128_tets.npz, 1.5 M tets): same vertex / face counts, sums and face
+    checksum as the reference class produced on it.  Needs the reference checkout (build container only)."""
+    path = '/root/reference/demo/tets/128_tets.npz'
+    if 'big_counts' not in PINS.files or not os.path.exists(path):
+        pytest.skip('reference tet grid not available')
+    t = np.load(path)
+    pos = -torch.tensor(t['vertices'], dtype=torch.float32) * 2
+    tets = torch.tensor(t['indices'], dtype=torch.long)
+    p = pos * float(PINS['big_sdf_scale'])
+    sdf = 0.31 - p.norm(dim=-1) + 0.04 * torch.sin(9 * p[:, 0]) * torch.sin(7 * p[:, 1]) * torch.sin(8 * p[:, 2])
+    with torch.no_grad():
+        v, f = DMTet('cpu')(pos, sdf, tets)
+    assert [v.shape[0], f.shape[0]] == PINS['big_counts'].tolist()
+    np.testing.assert_allclose(v.double().sum(0).numpy(), PINS['big_vsum'], rtol=1e-9, atol=1e-6)
+    np.testing.assert_allclose(v.double().abs().sum(0).numpy(), PINS['big_vabs'], rtol=1e-9, atol=1e-6)
+    dig = np.frombuffer(hashlib.sha256(np.ascontiguousarray(f.numpy().astype(np.int64)).tobytes()).digest()[:8], np.int64)[0]
+    assert dig == PINS['big_face_digest']
