@@ -1,0 +1,265 @@
+"""DMTet / mesh stage of the reconstruction loop: ``init_tet``, the NeRF-field shading function of the mesh
+renderer and ``mesh_optim`` -- argument for argument the reference's ``MVEdit3DPipeline.mesh_optim``
+(``lib/pipelines/mvedit_3d_pipeline.py:658-872``; ``init_tet``: ``lib/pipelines/utils.py:156-184``; shading functions ``:425-450``).
+
+One iteration = render ``render_bs`` full views of the current DMTet mesh through ``MeshRenderer`` (rasterize / interpolate / antialias
+kernels, the hash-grid field kernel at the visible surface points), the objective of Appendix F's mesh column, backward through the same
+kernels, one fused Adam step over (field parameters | sdf, deform), marching-tets re-extraction.  The objective's elementwise glue is
+torch autograd over those kernels (the NeRF stage has it fused in ``nerf_loss.cu``; the mesh stage's version is not fused yet).
+
+Not built (raise): target normals (``use_normal``: the normal model is absent), mesh simplification at the last step
+(``mesh_reduction < 1`` needs open3d's quadric decimation, ``:829-844``).
+"""
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .mesh_renderer import DMTet, Mesh, laplacian_smooth_loss, make_tet_grid, normal_consistency   # noqa: F401  (re-exported)
+from .nerf import blur_masks, pixel_directions
+
+
+def init_tet(nerf_model, nerf_code=None, density_thresh=5.0, resolution=128, tets=None):
+    """Tet grid fitted to the NeRF's occupied box, SDF initialised from its density (``lib/pipelines/utils.py:156-184``).
+
+    ``tets``: a dict / npz path with ``vertices`` [N,3] in [-0.5, 0.5] and ``indices`` [F,4] (the format of the reference's
+    ``demo/tets/{resolution}_tets.npz``, which it downloads when missing); default: ``$MVEDIT_TETS_DIR/{resolution}_tets.npz`` if that
+    exists, else the regular grid of ``make_tet_grid(resolution)``.  -> (verts [N,3], indices [F,4] int64, sdf [N])."""
+    device = next(nerf_model.decoder.parameters()).device
+    if tets is None:
+        path = os.path.join(os.environ.get('MVEDIT_TETS_DIR', ''), '%d_tets.npz' % resolution)
+        tets = path if os.path.exists(path) else make_tet_grid(resolution, device=device)
+    if isinstance(tets, str):
+        tets = np.load(tets)
+    verts = -torch.as_tensor(np.asarray(tets['vertices']) if not torch.is_tensor(tets['vertices']) else tets['vertices'],
+                             dtype=torch.float32, device=device) * 2                       # covers [-1, 1]
+    indices = torch.as_tensor(np.asarray(tets['indices']) if not torch.is_tensor(tets['indices']) else tets['indices'],
+                              dtype=torch.long, device=device)
+    if nerf_code is None:
+        nerf_code = [None]
+    with torch.no_grad():
+        sigma = nerf_model.decoder.point_density_decode([verts], nerf_code)[0]
+        valid = verts[sigma > density_thresh]
+        if valid.shape[0] == 0:
+            raise RuntimeError('init_tet: the field has no density above %g -- nothing to extract' % density_thresh)
+        vmax, vmin = valid.amax(dim=0) + 0.1, valid.amin(dim=0) - 0.1
+        verts = verts * ((vmax - vmin).max() / 2) + (vmax + vmin) / 2
+        sigma = nerf_model.decoder.point_density_decode([verts], nerf_code)[0]
+        sdf = (sigma - density_thresh).clamp(-1, 1)
+        sdf[(verts < -1).any(dim=-1) | (verts > 1).any(dim=-1)] = -1
+    return verts.contiguous(), indices, sdf.contiguous()
+
+
+def make_nerf_shading_fun(decoder, nerf_code, worldspace_point_lights, ambient_light, tonemapping=None):
+    """Lambert shading of the field's albedo at the visible surface points by one point light per view (``:425-442``)."""
+    def shading_fun(world_pos=None, albedo=None, world_normal=None, fg_mask=None, **kwargs):
+        if len(world_pos) == 0:
+            return world_pos if albedo is None else albedo
+        base_albedo = decoder.point_decode([world_pos], None, nerf_code)[1]
+        fg_lights = worldspace_point_lights[fg_mask.squeeze(0)]
+        shading = (fg_lights * world_normal).sum(-1, keepdim=True).clamp(min=0) * (1 - ambient_light) + ambient_light
+        if tonemapping is None:
+            return base_albedo * shading
+        return tonemapping.lut(tonemapping.inverse_lut(base_albedo) + shading.clamp(min=1e-6).log2())
+    return shading_fun
+
+
+def make_nerf_albedo_shading_fun(decoder, nerf_code):
+    """Unshaded albedo (``:444-450``; used when baking the texture)."""
+    def shading_fun(world_pos=None, albedo=None, **kwargs):
+        if len(world_pos) == 0:
+            return world_pos if albedo is None else albedo
+        return decoder.point_decode([world_pos], None, nerf_code)[1]
+    return shading_fun
+
+
+def _min_pool(x_nhwc, k=5):
+    return -F.max_pool2d(-x_nhwc.permute(0, 3, 1, 2), k, stride=1, padding=k // 2).permute(0, 2, 3, 1)
+
+
+@torch.no_grad()
+def view_cosine_gate(inv_depth, dirs):
+    """How frontal the surface is to the camera, per pixel in [0, 1], eroded by a 5x5 window (``:750-756``): the geometric normal is
+    taken from the back-projected inverse-depth map (mean of the four unit cross products of neighbouring finite differences, edges
+    replicated -- ``geometry_utils.depth_to_normal``), the gate is max(-n . unit ray, 0)."""
+    xyz = dirs / inv_depth.unsqueeze(-1).clamp(min=1e-6)
+    dx = xyz[:, :, 1:] - xyz[:, :, :-1]
+    dy = xyz[:, 1:] - xyz[:, :-1]
+    right, left = torch.cat([dx, dx[:, :, -1:]], dim=2), -torch.cat([dx[:, :, :1], dx], dim=2)
+    down, up = torch.cat([dy, dy[:, -1:]], dim=1), -torch.cat([dy[:, :1], dy], dim=1)
+    unit_cross = lambda a, b: F.normalize(torch.cross(a, b, dim=-1), dim=-1)
+    n = F.normalize(unit_cross(right, up) + unit_cross(up, left) + unit_cross(left, down) + unit_cross(down, right), dim=-1)
+    cos = -(n * F.normalize(dirs, dim=-1)).sum(-1, keepdim=True)
+    return _min_pool(cos.clamp(min=0))
+
+
+def tv_normal_loss(pred, weight, power=1.5, target=None):
+    """``TVLoss(power=1.5)`` on NCHW maps (``lib/models/losses/tv_loss.py:7-42``): forward differences along h and w (zero at the far
+    border), each weighted by the smaller weight of its two pixels, ``||(dh, dw)||_2 ** power`` averaged over everything."""
+    def fdiff(t, dim):
+        return F.pad(torch.diff(t, dim=dim), (0, 1) if dim == -1 else (0, 0, 0, 1))
+
+    def wmin(t, dim):
+        n = t.size(dim) - 1
+        return F.pad(torch.minimum(t.narrow(dim, 0, n), t.narrow(dim, 1, n)), (0, 1) if dim == -1 else (0, 0, 0, 1))
+    dh, dw = fdiff(pred, -2), fdiff(pred, -1)
+    if target is not None:
+        dh, dw = dh - fdiff(target, -2), dw - fdiff(target, -1)
+    dh, dw = dh * wmin(weight, -2), dw * wmin(weight, -1)
+    return torch.stack([dh, dw], dim=0).norm(dim=0).pow(power).mean()      # norm: zero sub-gradient on the flat background
+
+
+class _LpipsFn(torch.autograd.Function):
+    """Bridges ``LPIPSLoss.loss_and_grad`` (forward and input gradient in one call, no autograd graph) into the mesh objective."""
+
+    @staticmethod
+    def forward(ctx, pred_nhwc, target_nhwc, weight, patch_loss):
+        loss, g, _ = patch_loss.loss_and_grad(pred_nhwc.detach().float().contiguous(), target_nhwc.detach().float().contiguous(), weight, 1.0)
+        ctx.save_for_backward(g)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        (g,) = ctx.saved_tensors
+        return g * g_loss, None, None, None
+
+
+def lpips_patch_loss(patch_loss, pred_nchw, target_nchw, weight):
+    """``self.nerf.patch_loss(pred, target, weight=...)`` with gradient to ``pred`` (NCHW in [0,1] as the reference passes them)."""
+    if hasattr(patch_loss, 'loss_and_grad'):
+        return _LpipsFn.apply(pred_nchw.permute(0, 2, 3, 1), target_nchw.permute(0, 2, 3, 1), weight, patch_loss)
+    return patch_loss(pred_nchw, target_nchw, weight=weight)
+
+
+def normalize_depth(depths, alphas, far_depth=0.25, alpha_clip=0.5, eps=1e-5):
+    """Inverse depth [n,h,w] + alpha [n,h,w,1] -> the ControlNet depth image in [0,1] (``geometry_utils.normalize_depth``): per view,
+    foreground inverse depth rescaled so that the farthest confident (alpha >= alpha_clip) pixel maps to ``far_depth`` and the nearest to 1."""
+    a = alphas.squeeze(-1)
+    d_max = depths.flatten(1).amax(dim=1)[:, None, None]
+    d_fg = depths / a.clamp(min=eps)
+    d_min = d_fg.masked_fill(a < alpha_clip, 1 / eps).flatten(1).amin(dim=1)[:, None, None]
+    d_fg = (d_fg - d_min) / (d_max - d_min).clamp(min=eps) * (1 - far_depth) + far_depth
+    return (d_fg * a).clamp(min=0, max=1)
+
+
+def render_mesh_views(self, in_mesh, nerf_code, camera_poses, intrinsics, intrinsics_size, render_size, lights, ambient_light, render_bs):
+    """The mesh branch of the per-step render (``mvedit_3d_pipeline.py:1341-1360,1391-1396``) -> (ctrl_images, ctrl_depths) bf16
+    [n,3,rs,rs] like ``MVEdit3DStep.render_views``."""
+    images, alphas, depths = [], [], []
+    for pose_b, intr_b, light_b in zip(camera_poses.split(render_bs), intrinsics.split(render_bs), lights.split(render_bs)):
+        out = self.mesh_renderer(
+            [in_mesh], pose_b[None], intr_b[None] * (render_size / intrinsics_size), render_size, render_size,
+            make_nerf_shading_fun(self.nerf.decoder, nerf_code, light_b[:, None, None, :].expand(-1, render_size, render_size, -1),
+                                  ambient_light, self.tonemapping), normal_bg=self.normal_bg)
+        rgba = out['rgba'].squeeze(0).detach()
+        images.append(rgba[..., :3] + self.nerf.bg_color * (1 - rgba[..., 3:]))
+        alphas.append(rgba[..., 3:])
+        depths.append(out['depth'].squeeze(0).detach())
+    images = torch.cat(images, dim=0).permute(0, 3, 1, 2).clamp(min=0, max=1).to(torch.bfloat16)
+    alphas, depths = torch.cat(alphas, dim=0), torch.cat(depths, dim=0)
+    depths = normalize_depth(depths, alphas).to(torch.bfloat16).unsqueeze(1).repeat(1, 3, 1, 1)
+    return images.contiguous(), depths.contiguous()
+
+
+def _patches(x_nhwc, render_size, patch_size):
+    """[n, rs, rs, C] -> [n * (rs/ps)^2, C, ps, ps] (``:784-792``)."""
+    g = render_size // patch_size
+    c = x_nhwc.shape[-1]
+    return x_nhwc.reshape(-1, g, patch_size, g, patch_size, c).permute(0, 1, 3, 5, 2, 4).reshape(-1, c, patch_size, patch_size)
+
+
+def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                                                   # input images
+               optimizer, lr, lr_multiplier, inverse_steps, render_bs, patch_bs, mesh_simplify_texture_steps,  # optimisation settings
+               patch_rgb_weight, patch_normal_weight, alpha_soften, normal_reg_weight, mesh_normal_reg_weight,  # loss weights
+               nerf_code, tet_verts, deform, tet_sdf, tet_indices, dmtet, in_mesh,                          # mesh model
+               render_size, intrinsics, intrinsics_size, camera_poses, cam_weights, lights, patch_size,     # cameras
+               is_end, ambient_light, mesh_reduction, debug=False, perturb=True, noise=None):
+    """``self``: the pipeline (``nerf``, ``mesh_renderer``, ``normal_bg``, ``tonemapping``).  ``noise`` (extension, for parity tests):
+    dict with ``camera_perm`` [n], ``jitter`` [steps, render_bs, 2] in [0,1), ``patch_perm`` [steps, n_patches] replacing the draws."""
+    if tgt_normals is not None:
+        raise NotImplementedError('mesh_optim: target normals need the normal model, which is not built')
+    if mesh_reduction < 1 and is_end:
+        raise NotImplementedError('mesh_optim: mesh simplification (open3d quadric decimation) is not built; use mesh_reduction=1')
+    nerf, dec = self.nerf, self.nerf.decoder
+    device = tet_verts.device
+    noise = noise or {}
+    cam_weights_mean = cam_weights.mean()
+    n_views = camera_poses.size(0)
+    tgt_masks_blur = blur_masks(tgt_masks.square().squeeze(0).permute(0, 3, 1, 2), 9, 1.5).permute(0, 2, 3, 1).clamp(
+        min=alpha_soften ** 2, max=(1 - alpha_soften) ** 2).sqrt()
+    directions = pixel_directions(intrinsics * (render_size / intrinsics_size), render_size, render_size)      # [n, h, w, 3]
+    normal_bg = tgt_images.new_tensor(self.normal_bg)
+    decoder_training_prev = dec.training
+    dec.train(True)
+    fused = hasattr(optimizer, 'set_lr')
+    sink_prev = dec.grad_sink
+    dec.grad_sink = optimizer if fused and hasattr(optimizer, 'grad_sink') else None
+    try:
+        with torch.enable_grad():
+            if fused:
+                optimizer.set_lr(lr, group=0)
+                optimizer.set_lr(lr * 0.04 * lr_multiplier, group=1)
+            else:
+                optimizer.param_groups[0]['lr'] = lr
+                optimizer.param_groups[1]['lr'] = lr * 0.04 * lr_multiplier
+            camera_perm = noise['camera_perm'].to(device) if 'camera_perm' in noise else torch.randperm(n_views, device=device)
+            split = lambda x: x[camera_perm].split(render_bs, dim=0)
+            pose_b, intr_b = split(camera_poses), split(intrinsics)
+            img_b, mask_b, blur_b = split(tgt_images.squeeze(0)), split(tgt_masks.squeeze(0)), split(tgt_masks_blur)
+            dir_b, w_b, light_b = split(directions), split(cam_weights), split(lights)
+            nb = len(pose_b)
+            if is_end:
+                inverse_steps = max(inverse_steps, mesh_simplify_texture_steps)
+            for step in range(inverse_steps):
+                k = step % nb
+                target_rgbs, target_m, target_m_blur, target_dir = img_b[k], mask_b[k], blur_b[k], dir_b[k]
+                bs = target_rgbs.shape[0]
+                target_m_erode = _min_pool(target_m)
+                target_w = w_b[k][:, None, None, None].expand(-1, render_size, render_size, 1)
+                target_lights = light_b[k][:, None, None, :].expand(-1, render_size, render_size, 3)
+                intrinsics_batch = intr_b[k] * (render_size / intrinsics_size)
+                if perturb:                                  # +-0.5 px principal-point jitter (:733-735)
+                    u = noise['jitter'][step, :bs].to(device) if 'jitter' in noise else torch.rand_like(intrinsics_batch[:, 2:])
+                    intrinsics_batch = torch.cat([intrinsics_batch[:, :2], intrinsics_batch[:, 2:] + (u - 0.5) / self.mesh_renderer.ssaa], dim=1)
+
+                render_out = self.mesh_renderer(
+                    [in_mesh], pose_b[k][None], intrinsics_batch[None], render_size, render_size,
+                    make_nerf_shading_fun(dec, nerf_code, target_lights, ambient_light, self.tonemapping), normal_bg=self.normal_bg)
+                rgba = render_out['rgba'].squeeze(0)
+                out_alphas = rgba[..., 3:]
+                out_rgbs = rgba[..., :3] / out_alphas.clamp(min=1e-3)
+                out_rgbs = out_rgbs * target_m_erode + target_rgbs * (1 - target_m_erode)
+                out_normals = render_out['normal'].squeeze(0)
+                gate = view_cosine_gate(render_out['depth'].squeeze(0).detach(), target_dir)
+                out_normals = out_normals * gate + out_normals.detach() * (1 - gate)      # value unchanged, gradient scaled by the gate
+                out_normals_fg = (out_normals - normal_bg * (1 - out_alphas)) / out_alphas.clamp(min=1e-3)
+                wgt = target_w / cam_weights_mean
+
+                loss = nerf.pixel_loss(out_rgbs, target_rgbs, weight=wgt) * 4.5
+                loss = loss + nerf.pixel_loss(out_alphas, target_m_blur, weight=wgt) * 2.0
+                loss = loss + tv_normal_loss(out_normals_fg.permute(0, 3, 1, 2), out_alphas.detach().permute(0, 3, 1, 2)) * (normal_reg_weight * 2)
+                loss = loss + laplacian_smooth_loss(in_mesh.v, in_mesh.f) * mesh_normal_reg_weight
+                loss = loss + normal_consistency(in_mesh.face_normals, in_mesh.f) * mesh_normal_reg_weight
+
+                if patch_rgb_weight > 0:
+                    out_p, tgt_p = _patches(out_rgbs, render_size, patch_size), _patches(target_rgbs, render_size, patch_size)
+                    w_p = _patches(target_w, render_size, patch_size)
+                    perm = noise['patch_perm'][step].to(device) if 'patch_perm' in noise else torch.randperm(out_p.size(0), device=device)
+                    pick = perm[:patch_bs]
+                    loss = loss + lpips_patch_loss(nerf.patch_loss, out_p[pick], tgt_p[pick], w_p[pick, 0, 0, 0] / cam_weights_mean) * patch_rgb_weight
+
+                optimizer.zero_grad()
+                loss.backward()
+                optimizer.step()
+
+                with torch.enable_grad():
+                    mesh_verts, mesh_faces = dmtet(tet_verts + deform, tet_sdf, tet_indices)
+                    in_mesh = Mesh(v=mesh_verts, f=mesh_faces.int(), device=device)
+                    in_mesh.auto_normal()
+                if debug:
+                    print('mesh_optim step %d: loss %.5f, %d vertices, %d faces' % (step, float(loss), mesh_verts.shape[0], mesh_faces.shape[0]))
+    finally:
+        dec.grad_sink = sink_prev
+        dec.train(decoder_training_prev)
+    return in_mesh

@@ -1,0 +1,254 @@
+"""CPU oracle of the mesh stage -- TEST INFRASTRUCTURE ONLY (tests/, smoke(), bench.py's cpu_baseline).
+
+The reference's Python restated op by op, on top of oracle/raster_oracle.py for the four nvdiffrast ops:
+  ``DMTetOracle``             lib/models/decoders/mesh_renderer/base_mesh_renderer.py:104-188 (per-call torch.unique, as the reference)
+  ``auto_normal``             mesh_utils.py:359-382
+  ``laplacian_smooth_loss``   base_mesh_renderer.py:71-101 (sparse uniform Laplacian), ``normal_consistency`` :22-68
+  ``mesh_renderer_forward``   base_mesh_renderer.py:207-299, 383-395 (single-scene branch)
+  ``mesh_optim``              lib/pipelines/mvedit_3d_pipeline.py:658-872, every random draw supplied
+Pinned by: tests/golden/mesh_pins.npz for DMTet / auto_normal / the regularisers (the reference's own classes run in the build
+container); the renderer / rasteriser part is a restatement of an absent dependency (nvdiffrast) -- **parity unpinned**.
+"""
+import types
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import raster_oracle as ro
+from .nerf_oracle import L1LossMod, TVLoss, depth_to_normal, gaussian_blur, get_ray_directions
+
+
+class DMTetOracle:
+    def __init__(self, device='cpu'):
+        self.device = device
+        self.triangle_table = torch.tensor([
+            [-1, -1, -1, -1, -1, -1], [1, 0, 2, -1, -1, -1], [4, 0, 3, -1, -1, -1], [1, 4, 2, 1, 3, 4], [3, 1, 5, -1, -1, -1],
+            [2, 3, 0, 2, 5, 3], [1, 4, 0, 1, 5, 4], [4, 2, 5, -1, -1, -1], [4, 5, 2, -1, -1, -1], [4, 1, 0, 4, 5, 1],
+            [3, 2, 0, 3, 5, 2], [1, 3, 5, -1, -1, -1], [4, 1, 2, 4, 3, 1], [3, 0, 4, -1, -1, -1], [2, 0, 1, -1, -1, -1],
+            [-1, -1, -1, -1, -1, -1]], dtype=torch.long, device=device)
+        self.num_triangles_table = torch.tensor([0, 1, 1, 2, 1, 2, 2, 1, 1, 2, 2, 1, 2, 1, 1, 0], dtype=torch.long, device=device)
+        self.base_tet_edges = torch.tensor([0, 1, 0, 2, 0, 3, 1, 2, 1, 3, 2, 3], dtype=torch.long, device=device)
+
+    def __call__(self, pos_nx3, sdf_n, tet_fx4):
+        with torch.no_grad():
+            occ_n = sdf_n > 0
+            occ_fx4 = occ_n[tet_fx4.reshape(-1)].reshape(-1, 4)
+            occ_sum = torch.sum(occ_fx4, -1)
+            valid_tets = (occ_sum > 0) & (occ_sum < 4)
+            all_edges = tet_fx4[valid_tets][:, self.base_tet_edges].reshape(-1, 2)
+            order = (all_edges[:, 0] > all_edges[:, 1]).long().unsqueeze(1)
+            all_edges = torch.stack([torch.gather(all_edges, 1, order), torch.gather(all_edges, 1, 1 - order)], -1).reshape(-1, 2)
+            unique_edges, idx_map = torch.unique(all_edges, dim=0, return_inverse=True)
+            unique_edges = unique_edges.long()
+            mask_edges = occ_n[unique_edges.reshape(-1)].reshape(-1, 2).sum(-1) == 1
+            mapping = torch.ones((unique_edges.shape[0]), dtype=torch.long, device=self.device) * -1
+            mapping[mask_edges] = torch.arange(mask_edges.sum(), dtype=torch.long, device=self.device)
+            idx_map = mapping[idx_map]
+            interp_v = unique_edges[mask_edges]
+        edges_to_interp = pos_nx3[interp_v.reshape(-1)].reshape(-1, 2, 3)
+        edges_to_interp_sdf = sdf_n[interp_v.reshape(-1)].reshape(-1, 2, 1)
+        edges_to_interp_sdf = torch.cat([edges_to_interp_sdf[:, :1], -edges_to_interp_sdf[:, 1:]], dim=1)
+        denominator = edges_to_interp_sdf.sum(1, keepdim=True)
+        edges_to_interp_sdf = torch.flip(edges_to_interp_sdf, [1]) / denominator
+        verts = (edges_to_interp * edges_to_interp_sdf).sum(1)
+        idx_map = idx_map.reshape(-1, 6)
+        v_id = torch.pow(2, torch.arange(4, dtype=torch.long, device=self.device))
+        tetindex = (occ_fx4[valid_tets] * v_id.unsqueeze(0)).sum(-1)
+        num_triangles = self.num_triangles_table[tetindex]
+        faces = torch.cat((
+            torch.gather(input=idx_map[num_triangles == 1], dim=1, index=self.triangle_table[tetindex[num_triangles == 1]][:, :3]).reshape(-1, 3),
+            torch.gather(input=idx_map[num_triangles == 2], dim=1, index=self.triangle_table[tetindex[num_triangles == 2]][:, :6]).reshape(-1, 3),
+        ), dim=0)
+        return verts, faces
+
+
+def make_mesh(v, f):
+    m = types.SimpleNamespace(v=v, f=f, vn=None, fn=None, vt=None, ft=None, vc=None, albedo=None, face_normals=None)
+    auto_normal(m)
+    return m
+
+
+def auto_normal(mesh):
+    i0, i1, i2 = mesh.f[:, 0].long(), mesh.f[:, 1].long(), mesh.f[:, 2].long()
+    v0, v1, v2 = mesh.v[i0, :], mesh.v[i1, :], mesh.v[i2, :]
+    face_normals = F.normalize(torch.cross(v1 - v0, v2 - v0, dim=-1), dim=-1)
+    vn = torch.zeros_like(mesh.v)
+    vn = vn.scatter_add(0, i0[:, None].repeat(1, 3), face_normals)
+    vn = vn.scatter_add(0, i1[:, None].repeat(1, 3), face_normals)
+    vn = vn.scatter_add(0, i2[:, None].repeat(1, 3), face_normals)
+    mesh.vn = F.normalize(vn, dim=-1)
+    mesh.fn = mesh.f.to(torch.int32)
+    mesh.face_normals = face_normals
+
+
+def compute_edge_to_face_mapping(attr_idx):
+    with torch.no_grad():
+        all_edges = torch.cat((torch.stack((attr_idx[:, 0], attr_idx[:, 1]), dim=-1), torch.stack((attr_idx[:, 1], attr_idx[:, 2]), dim=-1),
+                               torch.stack((attr_idx[:, 2], attr_idx[:, 0]), dim=-1)), dim=-1).view(-1, 2)
+        order = (all_edges[:, 0] > all_edges[:, 1]).long().unsqueeze(dim=1)
+        sorted_edges = torch.cat((torch.gather(all_edges, 1, order), torch.gather(all_edges, 1, 1 - order)), dim=-1)
+        unique_edges, idx_map = torch.unique(sorted_edges, dim=0, return_inverse=True)
+        tris = torch.arange(attr_idx.shape[0]).repeat_interleave(3)
+        tris_per_edge = torch.zeros((unique_edges.shape[0], 2), dtype=torch.int64)
+        mask0, mask1 = order[:, 0] == 0, order[:, 0] == 1
+        tris_per_edge[idx_map[mask0], 0] = tris[mask0]
+        tris_per_edge[idx_map[mask1], 1] = tris[mask1]
+        return tris_per_edge
+
+
+def normal_consistency(face_normals, t_pos_idx):
+    tris_per_edge = compute_edge_to_face_mapping(t_pos_idx.long())
+    n0, n1 = face_normals[tris_per_edge[:, 0], :], face_normals[tris_per_edge[:, 1], :]
+    term = 1.0 - torch.clamp(torch.sum(n0 * n1, -1, keepdim=True), min=-1.0, max=1.0)
+    return torch.mean(torch.abs(term))
+
+
+def laplacian_smooth_loss(verts, faces):
+    with torch.no_grad():
+        faces = faces.long()
+        V = verts.shape[0]
+        ii, jj = faces[:, [1, 2, 0]].flatten(), faces[:, [2, 0, 1]].flatten()
+        adj = torch.stack([torch.cat([ii, jj]), torch.cat([jj, ii])], dim=0).unique(dim=1)
+        adj_values = torch.ones(adj.shape[1], dtype=verts.dtype)
+        idx = torch.cat((adj, torch.stack((adj[0], adj[0]), dim=0)), dim=1)
+        L = torch.sparse_coo_tensor(idx, torch.cat((-adj_values, adj_values)), (V, V)).coalesce()
+    return L.mm(verts).norm(dim=1).mean()
+
+
+# ---- the four rasteriser ops with autograd, built from raster_oracle ---------------------------------------------------------------
+
+def dr_rasterize(pos, tri, resolution, grad_db=True):
+    """ids / coverage from the fp32 numpy rasteriser (the discrete decision), (u, v, z/w) re-evaluated differentiably in pos's dtype."""
+    rast_np, db_np = ro.rasterize(pos.detach().float().numpy(), np.asarray(tri), resolution, grad_db=grad_db)
+    ids = torch.from_numpy(rast_np[..., 3]).long() - 1
+    uvz = ro.barycentrics(pos, torch.as_tensor(np.asarray(tri)), ids)
+    rast = torch.cat([uvz, torch.from_numpy(rast_np[..., 3:]).to(pos.dtype)], dim=-1)
+    return rast, torch.from_numpy(db_np).to(pos.dtype)
+
+
+def mesh_renderer_forward(mesh, poses, intrinsics, h, w, shading_fun=None, normal_bg=(0.5, 0.5, 1.0), aa=True, near=0.01, far=100.0, ssaa=1):
+    """base_mesh_renderer.py:207-299,383-395 for num_scenes == 1.  poses [1,n,3|4,4], intrinsics [1,n,4]."""
+    num_scenes, num_images = poses.shape[:2]
+    if ssaa > 1:
+        h, w, intrinsics = h * ssaa, w * ssaa, intrinsics * ssaa
+    r_mat_c2w = torch.cat([poses[..., :3, :1], -poses[..., :3, 1:3]], dim=-1)
+    proj = poses.new_zeros([num_scenes, num_images, 4, 4])
+    proj[..., 0, 0] = 2 * intrinsics[..., 0] / w
+    proj[..., 0, 2] = -2 * intrinsics[..., 2] / w + 1
+    proj[..., 1, 1] = -2 * intrinsics[..., 1] / h
+    proj[..., 1, 2] = -2 * intrinsics[..., 3] / h + 1
+    proj[..., 2, 2] = -(far + near) / (far - near)
+    proj[..., 2, 3] = -(2 * far * near) / (far - near)
+    proj[..., 3, 2] = -1
+    v_cam = (mesh.v - poses[0, :, :3, 3].unsqueeze(-2)) @ r_mat_c2w[0]
+    v_clip = F.pad(v_cam, pad=(0, 1), mode='constant', value=1.0) @ proj[0].transpose(-1, -2)
+    tri = mesh.f
+    rast, rast_db = dr_rasterize(v_clip, tri, (h, w))
+    fg = (rast[..., 3] > 0).unsqueeze(0)
+    alpha = fg.to(v_clip.dtype).unsqueeze(-1)
+    depth = 1 / ro.interpolate(-v_cam[..., 2:3], rast, tri)[0].reshape(num_scenes, num_images, h, w)
+    depth = depth.masked_fill(~fg, 0)
+    normal = ro.interpolate(mesh.vn.unsqueeze(0), rast, mesh.fn)[0].reshape(num_scenes, num_images, h, w, 3)
+    normal = F.normalize(normal, dim=-1)
+    rot_normal = (normal @ r_mat_c2w.unsqueeze(2)) / 2 + 0.5
+    rot_normal = torch.where(fg.unsqueeze(-1), rot_normal, rot_normal.new_tensor(list(normal_bg)))
+    if mesh.vc is not None:
+        rgba = ro.interpolate(mesh.vc if mesh.vc.dim() == 3 else mesh.vc[None], rast, tri)[0].reshape(num_scenes, num_images, h, w, 4)
+        alpha = alpha * rgba[..., 3:4]
+        albedo = rgba[..., :3] * alpha
+    else:
+        albedo = torch.zeros_like(rot_normal)
+    if shading_fun is not None:
+        xyz = ro.interpolate(mesh.v.unsqueeze(0), rast, tri)[0].reshape(num_scenes, num_images, h, w, 3)
+        rgb_reshade = shading_fun(world_pos=xyz[fg], albedo=albedo[fg], world_normal=normal[fg], fg_mask=fg)
+        albedo = torch.zeros_like(albedo).masked_scatter(fg.unsqueeze(-1).expand_as(albedo), rgb_reshade.to(albedo.dtype))
+    rgba = torch.cat([albedo, alpha], dim=-1)
+    if aa:
+        rgba, depth, rot_normal = ro.antialias(torch.cat([rgba, depth.unsqueeze(-1), rot_normal], dim=-1).squeeze(0), rast, v_clip,
+                                               np.asarray(tri)).unsqueeze(0).split([4, 1, 3], dim=-1)
+        depth = depth.squeeze(-1)
+    if ssaa > 1:
+        def down(x):
+            b = x.shape[:-3]
+            y = F.interpolate(x.reshape(b.numel(), *x.shape[-3:]).permute(0, 3, 1, 2), scale_factor=1 / ssaa, mode='area').permute(0, 2, 3, 1)
+            return y.reshape(*b, *y.shape[1:])
+        rgba, depth, rot_normal = down(rgba), down(depth.unsqueeze(-1)).squeeze(-1), down(rot_normal)
+    return dict(rgba=rgba, depth=depth, normal=rot_normal)
+
+
+def mesh_optim(decoder, tgt_images, tgt_masks, optimizer, lr, lr_multiplier, inverse_steps, render_bs, patch_bs, patch_rgb_weight,
+               alpha_soften, normal_reg_weight, mesh_normal_reg_weight, nerf_code, tet_verts, deform, tet_sdf, tet_indices, dmtet, in_mesh,
+               render_size, intrinsics, intrinsics_size, camera_poses, cam_weights, lights, patch_size, ambient_light, noise,
+               pixel_loss=None, patch_loss=None, normal_bg=(0.5, 0.5, 1.0), tonemapping=None, near=0.01, far=100.0):
+    """mvedit_3d_pipeline.py:658-872 without target normals / simplification; ``noise``: camera_perm, jitter [steps, bs, 2], patch_perm."""
+    pixel_loss = pixel_loss or L1LossMod(loss_weight=1.2)
+    loss_tv = TVLoss(loss_weight=1.0, power=1.5)
+    cam_weights_mean = cam_weights.mean()
+    tgt_masks_blur = gaussian_blur(tgt_masks.square().squeeze(0).permute(0, 3, 1, 2), 9, 1.5).permute(0, 2, 3, 1)[None].clamp(
+        min=alpha_soften ** 2, max=(1 - alpha_soften) ** 2).sqrt()
+    directions = get_ray_directions(render_size, render_size, intrinsics[None] * (render_size / intrinsics_size), norm=False)
+    normal_bg_t = tgt_images.new_tensor(list(normal_bg))
+    optimizer.param_groups[0]['lr'] = lr
+    optimizer.param_groups[1]['lr'] = lr * 0.04 * lr_multiplier
+    camera_perm = noise['camera_perm']
+    sp = lambda x: x[camera_perm].split(render_bs, dim=0)
+    pose_batches, intrinsics_batches = sp(camera_poses), sp(intrinsics)
+    tgt_image_batches, tgt_mask_batches = sp(tgt_images.squeeze(0)), sp(tgt_masks.squeeze(0))
+    tgt_mask_blur_batches, tgt_dir_batches = sp(tgt_masks_blur.squeeze(0)), sp(directions.squeeze(0))
+    cam_weights_batches, lights_batches = sp(cam_weights), sp(lights)
+    nb = len(pose_batches)
+    losses = []
+    for step in range(inverse_steps):
+        k = step % nb
+        pose_batch, intrinsics_batch = pose_batches[k], intrinsics_batches[k]
+        target_rgbs, target_m, target_m_blur = tgt_image_batches[k], tgt_mask_batches[k], tgt_mask_blur_batches[k]
+        target_m_erode = -F.max_pool2d(-target_m.permute(0, 3, 1, 2), 5, stride=1, padding=2).permute(0, 2, 3, 1)
+        target_dir = tgt_dir_batches[k]
+        target_w = cam_weights_batches[k][:, None, None, None].expand(-1, render_size, render_size, 1)
+        target_lights = lights_batches[k][:, None, None, :].expand(-1, render_size, render_size, 3)
+        intrinsics_batch = intrinsics_batch * (render_size / intrinsics_size)
+        intrinsics_batch = torch.cat([intrinsics_batch[:, :2], intrinsics_batch[:, 2:] + (noise['jitter'][step, :len(pose_batch)] - 0.5)], dim=1)
+
+        def shading_fun(world_pos=None, albedo=None, world_normal=None, fg_mask=None, **kwargs):
+            if len(world_pos) == 0:
+                return world_pos if albedo is None else albedo
+            base_albedo = decoder.point_decode([world_pos], None, nerf_code)[1]
+            fg_lights = target_lights[fg_mask.squeeze(0)]
+            shading = ((fg_lights[:, None, :] @ world_normal[:, :, None]).clamp(min=0) * (1 - ambient_light) + ambient_light).squeeze(-1)
+            if tonemapping is None:
+                return base_albedo * shading
+            return tonemapping.lut(tonemapping.inverse_lut(base_albedo) + shading.clamp(min=1e-6).log2())
+
+        render_out = mesh_renderer_forward(in_mesh, pose_batch[None], intrinsics_batch[None], render_size, render_size, shading_fun,
+                                           normal_bg=normal_bg, near=near, far=far)
+        out_alphas = render_out['rgba'][..., 3:].squeeze(0)
+        out_rgbs = (render_out['rgba'][..., :3] / render_out['rgba'][..., 3:].clamp(min=1e-3)).squeeze(0)
+        out_rgbs = out_rgbs * target_m_erode + target_rgbs * (1 - target_m_erode)
+        out_normals = render_out['normal'].squeeze(0)
+        out_normals_opencv = depth_to_normal(render_out['depth'].squeeze(0).detach(), target_dir, format='opencv') * 2 - 1
+        out_normals_cos = (out_normals_opencv[..., None, :] @ F.normalize(target_dir[..., :, None], dim=-2)).squeeze(-1).neg().clamp(min=0)
+        out_normals_cos = -F.max_pool2d(-out_normals_cos.permute(0, 3, 1, 2), 5, stride=1, padding=2).permute(0, 2, 3, 1)
+        out_normals = out_normals * out_normals_cos + out_normals.detach() * (1 - out_normals_cos)
+        out_normals_fg = (out_normals - normal_bg_t * (1 - out_alphas)) / out_alphas.clamp(min=1e-3)
+        out_normals_fg_weight = out_alphas.detach()
+        loss = pixel_loss(out_rgbs.reshape(target_rgbs.size()), target_rgbs, weight=target_w / cam_weights_mean) * 4.5
+        alphas_loss = pixel_loss(out_alphas.reshape(target_m_blur.size()), target_m_blur, weight=target_w / cam_weights_mean) * 2.0
+        normal_reg_loss = loss_tv(out_normals_fg.permute(0, 3, 1, 2), None, weight=out_normals_fg_weight.permute(0, 3, 1, 2)) * (normal_reg_weight * 2)
+        lapsmth_loss = laplacian_smooth_loss(in_mesh.v, in_mesh.f) * mesh_normal_reg_weight
+        norm_const_loss = normal_consistency(in_mesh.face_normals, in_mesh.f) * mesh_normal_reg_weight
+        loss = loss + alphas_loss + normal_reg_loss + lapsmth_loss + norm_const_loss
+        if patch_rgb_weight > 0:
+            g = render_size // patch_size
+            pt = lambda x: x.reshape(-1, g, patch_size, g, patch_size, x.shape[-1]).permute(0, 1, 3, 5, 2, 4).reshape(-1, x.shape[-1], patch_size, patch_size)
+            out_rgb_patch, tgt_rgb_patch, target_w_patch = pt(out_rgbs), pt(target_rgbs), pt(target_w)
+            patch_batch = noise['patch_perm'][step][:patch_bs]
+            loss = loss + patch_loss(out_rgb_patch[patch_batch], tgt_rgb_patch[patch_batch],
+                                     weight=target_w_patch[patch_batch, 0, 0, 0] / cam_weights_mean) * patch_rgb_weight
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        losses.append(float(loss))
+        mesh_verts, mesh_faces = dmtet(tet_verts + deform, tet_sdf, tet_indices)
+        in_mesh = make_mesh(mesh_verts, mesh_faces.int())
+    return in_mesh, losses

@@ -141,7 +141,7 @@ def barycentrics(pos, tri, tri_id):
     w = p[0][..., 3] * a0 + p[1][..., 3] * a1 + p[2][..., 3] * a2
     w = torch.where(tri_id >= 0, w, torch.ones_like(w))
     out = torch.stack([a0 / at, a1 / at, z / w], dim=-1)
-    return out * (tri_id >= 0)[..., None].to(out.dtype)
+    return torch.where((tri_id >= 0)[..., None], out, torch.zeros_like(out))     # where, not *: empty pixels pass no gradient (not even NaN)
 
 
 def interpolate(attr, rast, tri, rast_db=None, diff_attrs=None):
@@ -156,14 +156,16 @@ def interpolate(attr, rast, tri, rast_db=None, diff_attrs=None):
     bidx = torch.arange(B)[:, None, None].expand(B, H, W)
     a = [ab[bidx, tri[t, k].long()] for k in range(3)]                    # [B,H,W,C]
     u, v = rast[..., 0:1], rast[..., 1:2]
-    out = (u * a[0] + v * a[1] + (1 - u - v) * a[2]) * fg[..., None].to(attr.dtype)
+    out = u * a[0] + v * a[1] + (1 - u - v) * a[2]
+    out = torch.where(fg[..., None], out, torch.zeros_like(out))          # empty pixels neither produce nor receive anything
     out_da = None
     if diff_attrs is not None:
         assert diff_attrs == 'all' and rast_db is not None
         e0, e1 = a[0] - a[2], a[1] - a[2]
         dX = e0 * rast_db[..., 0:1] + e1 * rast_db[..., 2:3]
         dY = e0 * rast_db[..., 1:2] + e1 * rast_db[..., 3:4]
-        out_da = torch.stack([dX, dY], dim=-1).reshape(B, H, W, -1) * fg[..., None].to(attr.dtype)
+        out_da = torch.stack([dX, dY], dim=-1).reshape(B, H, W, -1)
+        out_da = torch.where(fg[..., None], out_da, torch.zeros_like(out_da))
     return out, out_da
 
 

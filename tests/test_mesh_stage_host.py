@@ -1,0 +1,156 @@
+"""CPU checks of the mesh stage against oracle/mesh_oracle.py: ``MeshRenderer.forward`` and a few ``mesh_optim``
+iterations, with the rasteriser kernels' code running through tests/host_harness.py and an analytic stand-in for the hash-grid field
+(the field kernel is CUDA-only; its own parity tests are tests/test_gpu_field.py).  The GPU version of the same comparison with the
+real field is tests/test_gpu_zmesh.py."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import mesh_oracle as mo
+from oracle.nerf_oracle import L1LossMod
+from tests import host_harness, synth_mesh
+from mvedit_b200 import mesh_raster as dr
+from mvedit_b200 import mesh_optim as mopt
+from mvedit_b200.mesh_renderer import DMTet, Mesh, MeshRenderer, make_tet_grid
+from types import SimpleNamespace
+
+
+@pytest.fixture(autouse=True)
+def _route():
+    with host_harness.routed(dr):
+        yield
+
+
+class ToyField(nn.Module):
+    """Stand-in for iNGPDecoder on the CPU: a smooth density blob and an albedo that depends on position through two parameters."""
+
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(0)
+        self.w = nn.Parameter(torch.randn(3, 3, generator=g))
+        self.b = nn.Parameter(torch.randn(3, generator=g) * 0.1)
+        self.grad_sink = None
+
+    def point_decode(self, xyzs, dirs, code, density_only=False, **kw):
+        x = xyzs[0]
+        sigma = 40 * (0.45 - x.norm(dim=-1)) + 4 * torch.sin(5 * x[:, 0]) * torch.sin(4 * x[:, 1])
+        rgb = None if density_only else torch.sigmoid(x @ self.w + self.b)
+        return sigma, rgb, [len(x)]
+
+    def point_density_decode(self, xyzs, code, **kw):
+        s, _, n = self.point_decode(xyzs, None, code, density_only=True)
+        return s, n
+
+
+def _cameras(n, size, seed=0):
+    poses = torch.from_numpy(synth_mesh.surround_poses(n, seed)).float()
+    intr = torch.from_numpy(synth_mesh.intrinsics(size)).float()[None].expand(n, -1).contiguous()
+    return poses, intr
+
+
+def test_mesh_renderer_forward_and_gradients_match_oracle():
+    v, f = synth_mesh.icosphere(2)
+    size, n = 40, 3
+    poses, intr = _cameras(n, size)
+    field = ToyField()
+    lights = torch.nn.functional.normalize(torch.randn(n, 3, generator=torch.Generator().manual_seed(1)), dim=-1)
+    lights_px = lights[:, None, None, :].expand(-1, size, size, -1)
+    out = {}
+    for name in ('product', 'oracle'):
+        vt = (torch.from_numpy(v).float() * 0.55).requires_grad_(True)
+        field.zero_grad()
+        if name == 'product':
+            mesh = Mesh(v=vt, f=torch.from_numpy(f).int())
+            mesh.auto_normal()
+            r = MeshRenderer(near=0.01, far=100)([mesh], poses[None], intr[None], size, size,
+                                                 mopt.make_nerf_shading_fun(field, None, lights_px, 0.2), normal_bg=[0.5, 0.5, 1.0])
+        else:
+            mesh = mo.make_mesh(vt, torch.from_numpy(f).int())
+            r = mo.mesh_renderer_forward(mesh, poses[None], intr[None], size, size,
+                                         mopt.make_nerf_shading_fun(field, None, lights_px, 0.2), normal_bg=(0.5, 0.5, 1.0))
+        g = torch.Generator().manual_seed(2)
+        loss = sum((r[k] * torch.randn(r[k].shape, generator=g)).sum() for k in ('rgba', 'depth', 'normal'))
+        loss.backward()
+        out[name] = dict(r={k: x.detach() for k, x in r.items()}, gv=vt.grad.clone(), gw=field.w.grad.clone())
+    p, o = out['product'], out['oracle']
+    for k in ('rgba', 'depth', 'normal'):
+        assert p['r'][k].shape == o['r'][k].shape
+        torch.testing.assert_close(p['r'][k], o['r'][k], rtol=1e-4, atol=2e-5)
+    assert p['r']['rgba'].shape == (1, n, size, size, 4) and 0.05 < p['r']['rgba'][..., 3].mean() < 0.6
+    assert (p['gv'] - o['gv']).abs().max() <= 2e-3 * o['gv'].abs().max()
+    assert (p['gw'] - o['gw']).abs().max() <= 2e-3 * o['gw'].abs().max()
+
+
+def test_vertex_colour_path_and_no_grad_render():
+    v, f = synth_mesh.icosphere(1)
+    poses, intr = _cameras(2, 32)
+    vt = torch.from_numpy(v).float() * 0.5
+    vc = torch.rand(1, vt.shape[0], 4, generator=torch.Generator().manual_seed(3))
+    mesh = Mesh(v=vt, f=torch.from_numpy(f).int(), vc=vc)
+    mesh.auto_normal()
+    with torch.no_grad():
+        r = MeshRenderer(near=0.01, far=100)([mesh], poses[None], intr[None], 32, 32)
+    om = mo.make_mesh(vt, torch.from_numpy(f).int())
+    om.vc = vc
+    ro_ = mo.mesh_renderer_forward(om, poses[None], intr[None], 32, 32)
+    for k in ('rgba', 'depth', 'normal'):
+        torch.testing.assert_close(r[k], ro_[k], rtol=1e-4, atol=2e-5)
+
+
+def test_unbuilt_branches_raise():
+    v, f = synth_mesh.icosphere(0)
+    poses, intr = _cameras(1, 16)
+    mesh = Mesh(v=torch.from_numpy(v).float() * 0.5, f=torch.from_numpy(f).int(), vt=torch.zeros(3, 2), albedo=torch.zeros(4, 4, 4))
+    mesh.auto_normal()
+    with pytest.raises(NotImplementedError):
+        MeshRenderer()([mesh], poses[None], intr[None], 16, 16)
+    with pytest.raises(NotImplementedError):
+        MeshRenderer()([mesh, mesh], poses[None].expand(2, -1, -1, -1), intr[None].expand(2, -1, -1), 16, 16)
+
+
+def test_init_tet_and_mesh_optim_match_oracle():
+    torch.manual_seed(0)
+    n, size, steps = 4, 32, 3
+    poses, intr = _cameras(n, size, seed=2)
+    lights = torch.nn.functional.normalize(torch.randn(n, 3, generator=torch.Generator().manual_seed(4)), dim=-1)
+    cam_weights = torch.tensor([1.0, 0.5, 1.0, 2.0])
+    yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing='ij')
+    disc = (((xx - 15.5) ** 2 + (yy - 15.5) ** 2).float().sqrt() < 9).float()
+    tgt_masks = disc[None, None, :, :, None].expand(1, n, -1, -1, -1).contiguous()
+    tgt_images = (torch.rand(1, n, size, size, 3, generator=torch.Generator().manual_seed(5)) * 0.5 + 0.25) * tgt_masks + (1 - tgt_masks)
+    noise = dict(camera_perm=torch.tensor([2, 0, 3, 1]), jitter=torch.rand(steps, 2, 2, generator=torch.Generator().manual_seed(6)))
+    grid = make_tet_grid(12)
+    results = {}
+    for name in ('product', 'oracle'):
+        field = ToyField()
+        nerf = SimpleNamespace(decoder=field, pixel_loss=L1LossMod(loss_weight=1.2), patch_loss=None)
+        tet_verts, tet_indices, tet_sdf = mopt.init_tet(nerf, None, density_thresh=5.0, tets=grid)
+        assert (tet_sdf > 0).sum() > 20 and (tet_sdf < 0).sum() > 20
+        deform = torch.zeros_like(tet_verts).requires_grad_(True)
+        tet_sdf.requires_grad_(True)
+        opt = torch.optim.Adam([{'params': list(field.parameters())}, {'params': [tet_sdf, deform], 'lr': 1e-3}], lr=0.01)
+        if name == 'product':
+            dm = DMTet('cpu')
+            with torch.enable_grad():
+                mv, mf = dm(tet_verts + deform, tet_sdf, tet_indices)
+                mesh = Mesh(v=mv, f=mf.int())
+                mesh.auto_normal()
+            pipe = SimpleNamespace(nerf=nerf, mesh_renderer=MeshRenderer(near=0.01, far=100), normal_bg=[0.5, 0.5, 1.0], tonemapping=None)
+            mesh = mopt.mesh_optim(pipe, tgt_images, tgt_masks, None, opt, 0.01, 0.8, steps, 2, 8, 24, 0.0, 0.0, 0.02, 0.1, 5.0, None,
+                                   tet_verts, deform, tet_sdf, tet_indices, dm, mesh, size, intr, size, poses, cam_weights, lights, 16,
+                                   False, 0.2, 1.0, noise=noise)
+        else:
+            dm = mo.DMTetOracle()
+            mv, mf = dm(tet_verts + deform, tet_sdf, tet_indices)
+            mesh, _ = mo.mesh_optim(field, tgt_images, tgt_masks, opt, 0.01, 0.8, steps, 2, 8, 0.0, 0.02, 0.1, 5.0, None, tet_verts, deform,
+                                    tet_sdf, tet_indices, dm, mo.make_mesh(mv, mf.int()), size, intr, size, poses, cam_weights, lights, 16,
+                                    0.2, noise)
+        results[name] = dict(sdf=tet_sdf.detach().clone(), deform=deform.detach().clone(), w=field.w.detach().clone(), f=mesh.f.clone(),
+                             v=mesh.v.detach().clone())
+    p, o = results['product'], results['oracle']
+    assert (p['sdf'] - o['sdf']).abs().max() < 2e-5 and (p['deform'] - o['deform']).abs().max() < 2e-5
+    assert (p['w'] - o['w']).abs().max() < 2e-5
+    assert (p['deform'].abs().max() > 1e-4) and (p['w'] - ToyField().w.detach()).abs().max() > 1e-3      # everything moved
+    assert p['f'].shape == o['f'].shape and (p['f'] == o['f']).all()
+    torch.testing.assert_close(p['v'], o['v'], rtol=1e-4, atol=2e-5)
