@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) k_field_fwd(const float* __restrict__ xyz
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
         const float x = xyz[(size_t)i * 3], y = xyz[(size_t)i * 3 + 1], z = xyz[(size_t)i * 3 + 2];
         float enc[R::IN];
-        encode<L>(lv, table, (x + cfg.bound) * cfg.inv2b, (y + cfg.bound) * cfg.inv2b, (z + cfg.bound) * cfg.inv2b, enc);
+        encode<L>(lv, table, unit_coord(cfg, x), unit_coord(cfg, y), unit_coord(cfg, z), enc);
         float o0 = ob0, o1 = ob1, o2 = ob2, o3 = ob3;
 #pragma unroll 4
         for (int j = 0; j < HID; j++) {
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128) k_field_fwd_mma(const float* __restrict__
         const bool live = i < M;
         float x = 0.f, y = 0.f, z = 0.f;
         if (live) { x = xyz[(size_t)i * 3]; y = xyz[(size_t)i * 3 + 1]; z = xyz[(size_t)i * 3 + 2]; }
-        mlpmma::encode_staged<L, 1>(lv, table, (x + cfg.bound) * cfg.inv2b, (y + cfg.bound) * cfg.inv2b, (z + cfg.bound) * cfg.inv2b, live, stg);
+        mlpmma::encode_staged<L, 1>(lv, table, unit_coord(cfg, x), unit_coord(cfg, y), unit_coord(cfg, z), live, stg);
         float o[4];
         mlpmma::mlp_forward_staged<L>(stg, frags, o);
         if (live) {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(BW_T) k_field_bwd(const float* __restrict__ xy
             gs = g_sigma[i];
             if (g_rgb) { gr = g_rgb[(size_t)i * 3]; gg = g_rgb[(size_t)i * 3 + 1]; gb = g_rgb[(size_t)i * 3 + 2]; }
         }
-        const float x0 = (x + cfg.bound) * cfg.inv2b, x1 = (y + cfg.bound) * cfg.inv2b, x2 = (z + cfg.bound) * cfg.inv2b;
+        const float x0 = unit_coord(cfg, x), x1 = unit_coord(cfg, y), x2 = unit_coord(cfg, z);
         float enc[IN];
         encode<L>(lv, table, x0, x1, x2, enc);
         // ---- forward recompute of the 4 outputs
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(BW_T, 3) k_field_bwd_mma(const float* __restri
             gs = g_sigma[i];
             if (g_rgb) { gr = g_rgb[(size_t)i * 3]; gg = g_rgb[(size_t)i * 3 + 1]; gb = g_rgb[(size_t)i * 3 + 2]; }
         }
-        const float x0 = (x + cfg.bound) * cfg.inv2b, x1 = (y + cfg.bound) * cfg.inv2b, x2 = (z + cfg.bound) * cfg.inv2b;
+        const float x0 = unit_coord(cfg, x), x1 = unit_coord(cfg, y), x2 = unit_coord(cfg, z);
         mlpmma::encode_staged<L, 1>(lv, table, x0, x1, x2, live, stage);
         const float blob = blob_of(cfg, x, y, z);
         float d0 = 0.f;

@@ -32,6 +32,13 @@ __device__ __forceinline__ uint32_t grid_index(const bool hashed, const uint32_t
     return idx >= size ? idx - size : idx;
 }
 
+// World coordinate -> the hash grid's [0, 1] input (ingp_decoder.py:112), clamped to the box.  Ray-marched samples never leave the
+// aabb, but the mesh stage queries arbitrary points (init_tet's rescaled tet grid, lib/pipelines/utils.py:177-183; surface points of a
+// drifting mesh): outside [0, 1] the dense-level index of grid_index() would leave the table.  tcnn wraps such indices (`% size` on a
+// value that no longer fits the one-subtraction shortcut below); here the query is evaluated at the nearest point of the box instead --
+// the reference discards those values anyway (init_tet overwrites the SDF outside [-1, 1]).
+__device__ __forceinline__ float unit_coord(const FieldCfg& c, const float x) { return fminf(fmaxf((x + c.bound) * c.inv2b, 0.f), 1.f); }
+
 // positional part of one level: base cell, smoothstep weights and their derivatives
 struct Cell {
     uint32_t g[3];
