@@ -420,6 +420,12 @@ def run_ours(args):
         kernel_breakdown_ms=breakdown, tensor_core_shapes_ms=top_shapes, per_call_ms=tails, raster_hbm=raster,
     )
     line.update(extra)
+    if world == 1 and not getattr(args, 'no_mesh', False):
+        # last, after every other number is final: these kernels are the newest in the tree
+        try:
+            line['mesh_raster'] = mesh_microbench(device, pk)
+        except Exception as e:
+            line['mesh_raster'] = dict(error=repr(e)[:300])
     emit_json(line)
     _teardown(pipe, world)
 
@@ -640,6 +646,61 @@ def gs_microbench(device, pk):
                    blend_fwd_frac_hbm=round(bf / m('blend_fwd') / 1e6 / pk['hbm_gbs'], 3), blend_bwd_frac_hbm=round(bb / m('blend_bwd') / 1e6 / pk['hbm_gbs'], 3),
                    note='the blend loop itself is shared-memory / FMA bound (every pixel visits every Gaussian of its tile): HBM is the roof of the '
                         'staging traffic only; views/s per GPU = %.1f fwd+bwd' % (1e3 / (m('fwd') + m('bwd'))))
+    return out
+
+
+def mesh_microbench(device, pk, V=6, S=1024, R=96):
+    """BASELINE configs[3], rasteriser side: a DMTet mesh (marching tets over a 96^3 6-tets-per-cell grid, rippled-sphere SDF) rendered
+    by MeshRenderer.forward at 6 views x 1024^2 with vertex colours (no field), forward + backward to the vertices.  Reported: ms of the
+    extraction, of the whole forward / backward, per C-ABI call (CUDA events), and algorithmic HBM GB/s of the three rasterize launches
+    (8 B z-buffer clear + 8 B read + 16 B rast + 16 B rast_db per pixel, 60 B per triangle and view)."""
+    from tests import synth_mesh
+    from mvedit_b200 import _lib
+    from mvedit_b200.mesh_renderer import DMTet, Mesh, MeshRenderer, make_tet_grid
+    grid = make_tet_grid(R, device=device)
+    tv, ti = (-grid['vertices'] * 2 * 0.9).contiguous(), grid['indices']
+    sdf = (0.6 - tv.norm(dim=-1) + 0.05 * torch.sin(8 * tv[:, 0]) * torch.sin(8 * tv[:, 1]) * torch.sin(8 * tv[:, 2])).requires_grad_(True)
+    deform = torch.zeros_like(tv).requires_grad_(True)
+    dm = DMTet(device)
+    poses = torch.from_numpy(synth_mesh.surround_poses(V, 0)).float().to(device)
+    K = torch.from_numpy(synth_mesh.intrinsics(S)).float().to(device)[None].expand(V, -1).contiguous()
+    renderer = MeshRenderer(near=0.01, far=100)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    res = dict(extract=[], fwd=[], bwd=[])
+    calls = {}
+    for rep in range(4):
+        e = [ev() for _ in range(4)]
+        prof = []
+        e[0].record()
+        mv, mf = dm(tv + deform, sdf, ti)
+        mesh = Mesh(v=mv, f=mf.int(), vc=torch.cat([mv.detach() * 0.5 + 0.5, torch.ones_like(mv[:, :1])], dim=-1)[None].contiguous())
+        mesh.auto_normal()
+        e[1].record()
+        _lib.PROFILE[0] = prof
+        out = renderer([mesh], poses[None], K[None], S, S)
+        e[2].record()
+        (out['rgba'].sum() + out['depth'].sum() + out['normal'].sum()).backward()
+        e[3].record()
+        torch.cuda.synchronize()
+        _lib.PROFILE[0] = None
+        sdf.grad = deform.grad = None
+        if rep:
+            res['extract'].append(e[0].elapsed_time(e[1])); res['fwd'].append(e[1].elapsed_time(e[2])); res['bwd'].append(e[2].elapsed_time(e[3]))
+            for name, a, b, _m in prof:
+                calls.setdefault(name, []).append(a.elapsed_time(b))
+    m = lambda x: float(np.mean(x))
+    F_, npx = int(mf.shape[0]), V * S * S
+    per_call = {k: dict(ms=round(m(v_), 4), calls_per_pass=len(v_) // 3) for k, v_ in calls.items()}
+    out = dict(workload='BASELINE configs[3] rasteriser side: DMTet mesh from a %d^3 tet grid, %d views x %d^2, vertex colours' % (R, V, S),
+               triangles=F_, vertices=int(mv.shape[0]), coverage=round(float((out['rgba'][..., 3] > 0).float().mean()), 3),
+               dmtet_extract_ms=round(m(res['extract']), 3), render_fwd_ms=round(m(res['fwd']), 3), render_bwd_ms=round(m(res['bwd']), 3), per_call=per_call)
+    if 'mve_rasterize_fwd' in calls:
+        b_r = npx * 48 + V * F_ * 60
+        gbs = b_r / m(calls['mve_rasterize_fwd']) / 1e6
+        out.update(rasterize_gbs=round(gbs, 1), rasterize_frac_hbm=round(gbs / pk['hbm_gbs'], 3))
+    if 'mve_antialias_fwd' in calls:
+        gbs = npx * (3 * 8 * 4 + 16) / m(calls['mve_antialias_fwd']) / 1e6
+        out.update(antialias_gbs=round(gbs, 1), antialias_frac_hbm=round(gbs / pk['hbm_gbs'], 3))
     return out
 
 
@@ -889,6 +950,7 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='run the recon iterations eagerly instead of as CUDA graphs')
     ap.add_argument('--recon', default='dp', choices=['dp', 'replicated'], help='N > 1: ray-data-parallel reconstruction (default) or replicated + broadcast')
     ap.add_argument('--no-lpips', action='store_true', help='A/B: drop the LPIPS patch term from the reconstruction objective (patch_rgb_weight 0)')
+    ap.add_argument('--no-mesh', action='store_true', help='skip the config-4 mesh rasteriser microbench')
     ap.add_argument('--no-gpu-baseline', action='store_true', help='skip the stock-PyTorch + reference-kernel GPU baseline leg (saves ~1 min)')
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON: libraries that chat on fd 1 (NCCL prints its version banner there from inside
