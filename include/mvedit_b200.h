@@ -381,7 +381,7 @@ int mve_gs_blend_backward(const int32_t* ranges, const int32_t* point_list, cons
  * ------------------------------------------------------------------------- */
 
 /* dr.rasterize: rast [B,H,W,4] = (u, v, z/w, triangle id + 1; 0 = empty), u / v = perspective-correct barycentrics of vertex 0 / 1;
- * rast_db [B,H,W,4] = (du/dX, du/dY, dv/dX, dv/dY) per pixel, or NULL (grad_db=False).  Nearest z/w in [-1, 1] wins, ties go to the
+ * rast_db [B,H,W,4] = (du/dX, du/dY, dv/dX, dv/dY) per pixel, or NULL to skip it.  Nearest z/w in [-1, 1] wins, ties go to the
  * lower triangle id (deterministic).  Triangles with a vertex at w <= 0 are dropped (no near-plane clipping).
  * Scratch (caller-allocated, contents irrelevant): zbuf [B*H*W] u64, queue [1 + B*F] u32.  Three launches, no host sync. */
 int mve_rasterize_fwd(const float* pos, const int32_t* tri, uint32_t B, uint32_t V, uint32_t F, uint32_t H, uint32_t W,
@@ -407,6 +407,23 @@ int mve_antialias_fwd(const float* color, const float* rast, const float* pos, c
 int mve_antialias_bwd(const float* color, const float* rast, const float* pos, const int32_t* tri, const int32_t* opp, uint32_t B,
                       uint32_t H, uint32_t W, uint32_t C, uint32_t V, uint32_t F, int pos_batched, const float* g_out,
                       float* g_color, float* g_pos, void* stream);
+
+/* dr.texture(tex, uv, uv_da=, filter_mode='linear-mipmap-linear' | 'linear'), boundary mode 'wrap' (nvdiffrast's default; the reference
+ * never passes another): base_mesh_renderer.py:263-264 (albedo), :470-475 / :547-552 (coverage of a ones map through the texture
+ * GRADIENT), :499-500 / :576-577 (images resampled into texture space).  The mip pyramid is ONE flat f32 buffer: level l holds
+ * [Bt, th >> l, tw >> l, C] at the offset mve_texture_pyramid_floats(Bt, th, tw, C, l) (2x2 box averages; every halved level needs
+ * even dimensions).  The caller copies the texture into level 0 and calls mve_texture_mip_build once per texture. */
+unsigned long long mve_texture_pyramid_floats(uint32_t Bt, uint32_t th, uint32_t tw, uint32_t C, uint32_t n_levels);
+int mve_texture_mip_build(float* pyr, uint32_t Bt, uint32_t th, uint32_t tw, uint32_t C, uint32_t n_levels, void* stream);
+/* out [B,H,W,C]; uv [B,H,W,2] in texture units ((0,0) = corner of texel (0,0)); uv_da [B,H,W,4] = (du/dX, du/dY, dv/dX, dv/dY) from
+ * mve_interpolate_fwd's out_da, or NULL (level 0 only).  Level = clamp(0.5 log2(major axis^2 of the pixel footprint in texels), 0,
+ * n_levels - 1), trilinear between floor(level) and the next.  Bt = 1 (one texture for all images) or B. */
+int mve_texture_fwd(const float* pyr, uint32_t Bt, uint32_t th, uint32_t tw, uint32_t C, uint32_t n_levels, const float* uv,
+                    const float* uv_da, uint32_t B, uint32_t H, uint32_t W, float* out, void* stream);
+/* g_out -> g_pyr (same layout as the pyramid, zeroed by the caller): taps scattered with atomics, then the coarse levels' gradients
+ * folded down so that level 0 of g_pyr is d/d(texture).  No gradient to uv / uv_da (MVEdit optimises either geometry or texture). */
+int mve_texture_bwd(uint32_t Bt, uint32_t th, uint32_t tw, uint32_t C, uint32_t n_levels, const float* uv, const float* uv_da,
+                    uint32_t B, uint32_t H, uint32_t W, const float* g_out, float* g_pyr, void* stream);
 
 #ifdef __cplusplus
 }

@@ -435,6 +435,118 @@ MVE_HD void aa_bwd_pixel(const AaP& p, uint32_t i) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// texture: bilinear fetch with wrap addressing from a mip pyramid, trilinear between the two levels chosen by the screen-space
+// footprint of (u, v) (dr.texture(..., uv_da=, filter_mode='linear-mipmap-linear'), base_mesh_renderer.py:263-264,473-474,499-500,576-577).
+constexpr int kMaxMip = 16;
+
+struct TexP {
+    const float* pyr;           // level l at offset off[l]: [Bt, th >> l, tw >> l, C]
+    float* g_pyr;               // backward: same layout, accumulated
+    uint32_t off[kMaxMip];
+    uint32_t Bt, th, tw, C, n_levels, tex_stride;   // tex_stride: 1 if the texture is batched, 0 if one texture serves all images
+    const float2* uv;           // [B, H, W]
+    const float4* uv_da;        // [B, H, W] (du/dX, du/dY, dv/dX, dv/dY) or NULL (level 0 only)
+    uint32_t n_pix_per_image;
+    float* out;                 // [B, H, W, C]
+    const float* g_out;
+    uint32_t level;             // mip build / fold kernels: the level being written
+};
+
+struct TexTap { uint32_t i00, i01, i10, i11; float w00, w01, w10, w11; };
+
+MVE_HD uint32_t wrap_i(int i, uint32_t n) { int m = i % (int)n; return (uint32_t)(m < 0 ? m + (int)n : m); }
+
+// the four texels and weights of a bilinear fetch at (u, v) on level l of image bt (element offsets of channel 0)
+MVE_HD TexTap tex_tap(const TexP& p, uint32_t bt, uint32_t l, float u, float v) {
+    uint32_t wl = p.tw >> l, hl = p.th >> l;
+    float x = u * (float)wl - 0.5f, y = v * (float)hl - 0.5f;
+    float fx0 = floorf(x), fy0 = floorf(y);
+    float fx = x - fx0, fy = y - fy0;
+    if (!(fx0 > -1e9f && fx0 < 1e9f && fy0 > -1e9f && fy0 < 1e9f)) { fx0 = fy0 = 0.f; fx = fy = 0.f; }      // NaN / huge uv
+    uint32_t x0 = wrap_i((int)fx0, wl), x1 = wrap_i((int)fx0 + 1, wl), y0 = wrap_i((int)fy0, hl), y1 = wrap_i((int)fy0 + 1, hl);
+    uint32_t base = p.off[l] + bt * hl * wl * p.C;
+    TexTap t;
+    t.i00 = base + (y0 * wl + x0) * p.C; t.i01 = base + (y0 * wl + x1) * p.C;
+    t.i10 = base + (y1 * wl + x0) * p.C; t.i11 = base + (y1 * wl + x1) * p.C;
+    t.w00 = (1.f - fx) * (1.f - fy); t.w01 = fx * (1.f - fy); t.w10 = (1.f - fx) * fy; t.w11 = fx * fy;
+    return t;
+}
+
+// mip level from the footprint: half the log2 of the squared major axis of the pixel's ellipse in texel units
+MVE_HD void tex_level(const TexP& p, uint32_t i, uint32_t& l0, uint32_t& l1, float& f) {
+    l0 = l1 = 0; f = 0.f;
+    if (!p.uv_da || p.n_levels <= 1) return;
+    float4 d = p.uv_da[i];
+    float dsdx = d.x * (float)p.tw, dsdy = d.y * (float)p.tw, dtdx = d.z * (float)p.th, dtdy = d.w * (float)p.th;
+    float A = dsdx * dsdx + dtdx * dtdx, Bq = dsdy * dsdy + dtdy * dtdy, Cq = dsdx * dsdy + dtdx * dtdy;
+    float l2b = 0.5f * (A + Bq), l2n = 0.25f * (A - Bq) * (A - Bq) + Cq * Cq;
+    float major = l2b + sqrtf(l2n);
+    float level = major > 0.f ? 0.5f * log2f(major) : 0.f;
+    float top = (float)(p.n_levels - 1);
+    level = level > 0.f ? (level < top ? level : top) : 0.f;             // also maps NaN to 0
+    float fl = floorf(level);
+    l0 = (uint32_t)fl; f = level - fl;
+    l1 = l0 + 1 < p.n_levels ? l0 + 1 : l0;
+    if (l1 == l0) f = 0.f;
+}
+
+MVE_HD void tex_fwd_pixel(const TexP& p, uint32_t i) {
+    float2 uv = p.uv[i];
+    uint32_t bt = (i / p.n_pix_per_image) * p.tex_stride;
+    uint32_t l0, l1; float f;
+    tex_level(p, i, l0, l1, f);
+    TexTap a = tex_tap(p, bt, l0, uv.x, uv.y);
+    float* o = p.out + (size_t)i * p.C;
+    for (uint32_t c = 0; c < p.C; ++c)
+        o[c] = ((a.w00 * p.pyr[a.i00 + c] + a.w01 * p.pyr[a.i01 + c]) + a.w10 * p.pyr[a.i10 + c]) + a.w11 * p.pyr[a.i11 + c];
+    if (f > 0.f) {
+        TexTap b = tex_tap(p, bt, l1, uv.x, uv.y);
+        for (uint32_t c = 0; c < p.C; ++c) {
+            float s1 = ((b.w00 * p.pyr[b.i00 + c] + b.w01 * p.pyr[b.i01 + c]) + b.w10 * p.pyr[b.i10 + c]) + b.w11 * p.pyr[b.i11 + c];
+            o[c] = o[c] + f * (s1 - o[c]);
+        }
+    }
+}
+
+MVE_HD void tex_scatter(const TexP& p, const TexTap& t, const float* g, float scale) {
+    for (uint32_t c = 0; c < p.C; ++c) {
+        float gc = g[c] * scale;
+        if (gc == 0.f) continue;
+        atomic_add_f(p.g_pyr + t.i00 + c, gc * t.w00); atomic_add_f(p.g_pyr + t.i01 + c, gc * t.w01);
+        atomic_add_f(p.g_pyr + t.i10 + c, gc * t.w10); atomic_add_f(p.g_pyr + t.i11 + c, gc * t.w11);
+    }
+}
+
+MVE_HD void tex_bwd_pixel(const TexP& p, uint32_t i) {
+    float2 uv = p.uv[i];
+    uint32_t bt = (i / p.n_pix_per_image) * p.tex_stride;
+    uint32_t l0, l1; float f;
+    tex_level(p, i, l0, l1, f);
+    const float* g = p.g_out + (size_t)i * p.C;
+    tex_scatter(p, tex_tap(p, bt, l0, uv.x, uv.y), g, 1.f - f);
+    if (f > 0.f) tex_scatter(p, tex_tap(p, bt, l1, uv.x, uv.y), g, f);
+}
+
+// level `p.level` (>= 1) <- 2x2 box average of the level below; one element per (bt, y, x, c)
+MVE_HD void tex_mip_down(const TexP& p, uint32_t i) {
+    uint32_t l = p.level, wl = p.tw >> l, hl = p.th >> l, wf = wl * 2;
+    uint32_t c = i % p.C, x = (i / p.C) % wl, y = (i / (p.C * wl)) % hl, bt = i / (p.C * wl * hl);
+    const float* src = p.pyr + p.off[l - 1] + ((size_t)bt * hl * 2 * wf) * p.C;
+    float s = (src[((2 * y) * wf + 2 * x) * p.C + c] + src[((2 * y) * wf + 2 * x + 1) * p.C + c])
+            + (src[((2 * y + 1) * wf + 2 * x) * p.C + c] + src[((2 * y + 1) * wf + 2 * x + 1) * p.C + c]);
+    ((float*)p.pyr)[p.off[l] + i] = 0.25f * s;
+}
+
+// gradient of level `p.level` (>= 1) folded into the level below: every fine texel takes a quarter of its parent's gradient
+MVE_HD void tex_mip_fold(const TexP& p, uint32_t i) {
+    uint32_t l = p.level, wl = p.tw >> l, hl = p.th >> l, wf = wl * 2, hf = hl * 2;
+    uint32_t c = i % p.C, x = (i / p.C) % wf, y = (i / (p.C * wf)) % hf, bt = i / (p.C * wf * hf);
+    float g = p.g_pyr[p.off[l] + (((size_t)bt * hl + y / 2) * wl + x / 2) * p.C + c];
+    p.g_pyr[p.off[l - 1] + i] += 0.25f * g;
+}
+
 // ------------------------------------------------------------------------------------------------------------------------------
 MVE_ELEMENT_KERNEL(k_raster_tris, RasterP, raster_tri)
 MVE_ELEMENT_KERNEL(k_raster_resolve, RasterP, raster_resolve)
@@ -443,6 +555,10 @@ MVE_ELEMENT_KERNEL(k_interp_fwd, InterpP, interp_fwd_pixel)
 MVE_ELEMENT_KERNEL(k_interp_bwd, InterpP, interp_bwd_pixel)
 MVE_ELEMENT_KERNEL(k_antialias_fwd, AaP, aa_fwd_pixel)
 MVE_ELEMENT_KERNEL(k_antialias_bwd, AaP, aa_bwd_pixel)
+MVE_ELEMENT_KERNEL(k_texture_fwd, TexP, tex_fwd_pixel)
+MVE_ELEMENT_KERNEL(k_texture_bwd, TexP, tex_bwd_pixel)
+MVE_ELEMENT_KERNEL(k_texture_mip_down, TexP, tex_mip_down)
+MVE_ELEMENT_KERNEL(k_texture_mip_fold, TexP, tex_mip_fold)
 
 #ifdef MVE_HOST_HARNESS
 static void k_raster_large(const RasterP& p) {
@@ -456,6 +572,20 @@ __global__ void __launch_bounds__(kLargeLanes) k_raster_large(const RasterP p) {
     for (uint32_t q = blockIdx.x; q < n; q += gridDim.x) raster_large_lane(p, q, threadIdx.x);
 }
 #endif
+
+
+// level offsets (in floats) of the pyramid of a [Bt, th, tw, C] texture; returns the total, 0 on a bad level count
+static inline unsigned long long tex_fill(TexP& p, uint32_t Bt, uint32_t th, uint32_t tw, uint32_t C, uint32_t n_levels) {
+    unsigned long long o = 0;
+    if (n_levels < 1 || n_levels > (uint32_t)kMaxMip) return 0;
+    for (uint32_t l = 0; l < n_levels; ++l) {
+        if ((th >> l) == 0 || (tw >> l) == 0 || (l > 0 && ((((th >> (l - 1)) | (tw >> (l - 1))) & 1u) != 0))) return 0;
+        p.off[l] = (uint32_t)o;
+        o += (unsigned long long)Bt * (th >> l) * (tw >> l) * C;
+    }
+    p.Bt = Bt; p.th = th; p.tw = tw; p.C = C; p.n_levels = n_levels;
+    return o < (1ull << 31) ? o : 0;
+}
 
 }  // namespace
 
@@ -530,5 +660,49 @@ MVE_EXPORT int mve_antialias_bwd(const float* color, const float* rast, const fl
     p.V = V; p.F = F; p.pos_stride = pos_batched ? V : 0; p.g_out = g_out; p.g_color = g_color; p.g_pos = g_pos;
     MVE_MEMCPY(g_color, g_out, (size_t)B * H * W * C * 4, stream);
     MVE_LAUNCH(k_antialias_bwd, p, B * H * W, stream);
+    return 0;
+}
+
+/* ---- texture ---------------------------------------------------------------------------------------------------------------- */
+MVE_EXPORT unsigned long long mve_texture_pyramid_floats(uint32_t Bt, uint32_t th, uint32_t tw, uint32_t C, uint32_t n_levels) {
+    TexP p = {};
+    return tex_fill(p, Bt, th, tw, C, n_levels);
+}
+
+MVE_EXPORT int mve_texture_mip_build(float* pyr, uint32_t Bt, uint32_t th, uint32_t tw, uint32_t C, uint32_t n_levels, void* stream) {
+    MVE_ARG(pyr, "mve_texture_mip_build: NULL pointer");
+    TexP p = {};
+    MVE_ARG(tex_fill(p, Bt, th, tw, C, n_levels) > 0, "mve_texture_mip_build: bad level count (every halved level needs even dimensions; total < 2^31 floats)");
+    p.pyr = pyr;
+    for (uint32_t l = 1; l < n_levels; ++l) {
+        p.level = l;
+        MVE_LAUNCH(k_texture_mip_down, p, Bt * (th >> l) * (tw >> l) * C, stream);
+    }
+    return 0;
+}
+
+MVE_EXPORT int mve_texture_fwd(const float* pyr, uint32_t Bt, uint32_t th, uint32_t tw, uint32_t C, uint32_t n_levels, const float* uv,
+                               const float* uv_da, uint32_t B, uint32_t H, uint32_t W, float* out, void* stream) {
+    MVE_ARG(pyr && uv && out, "mve_texture_fwd: NULL pointer");
+    MVE_ARG(Bt == 1 || Bt == B, "mve_texture_fwd: texture batch must be 1 or B");
+    TexP p = {};
+    MVE_ARG(tex_fill(p, Bt, th, tw, C, n_levels) > 0, "mve_texture_fwd: bad level count");
+    p.pyr = pyr; p.uv = (const float2*)uv; p.uv_da = (const float4*)uv_da; p.n_pix_per_image = H * W; p.tex_stride = Bt == 1 ? 0 : 1; p.out = out;
+    MVE_LAUNCH(k_texture_fwd, p, B * H * W, stream);
+    return 0;
+}
+
+MVE_EXPORT int mve_texture_bwd(uint32_t Bt, uint32_t th, uint32_t tw, uint32_t C, uint32_t n_levels, const float* uv, const float* uv_da,
+                               uint32_t B, uint32_t H, uint32_t W, const float* g_out, float* g_pyr, void* stream) {
+    MVE_ARG(uv && g_out && g_pyr, "mve_texture_bwd: NULL pointer");
+    MVE_ARG(Bt == 1 || Bt == B, "mve_texture_bwd: texture batch must be 1 or B");
+    TexP p = {};
+    MVE_ARG(tex_fill(p, Bt, th, tw, C, n_levels) > 0, "mve_texture_bwd: bad level count");
+    p.g_pyr = g_pyr; p.uv = (const float2*)uv; p.uv_da = (const float4*)uv_da; p.n_pix_per_image = H * W; p.tex_stride = Bt == 1 ? 0 : 1; p.g_out = g_out;
+    MVE_LAUNCH(k_texture_bwd, p, B * H * W, stream);
+    for (uint32_t l = n_levels - 1; l >= 1; --l) {
+        p.level = l;
+        MVE_LAUNCH(k_texture_mip_fold, p, Bt * (th >> (l - 1)) * (tw >> (l - 1)) * C, stream);
+    }
     return 0;
 }

@@ -16,7 +16,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .mesh_renderer import DMTet, Mesh, laplacian_smooth_loss, make_tet_grid, normal_consistency   # noqa: F401  (re-exported)
+from .mesh_renderer import (DMTet, Mesh, laplacian_smooth_loss, make_tet_grid, min_pool, normal_consistency,   # noqa: F401  (re-exported)
+                            view_cosine)
 from .nerf import blur_masks, pixel_directions
 
 
@@ -74,24 +75,9 @@ def make_nerf_albedo_shading_fun(decoder, nerf_code):
     return shading_fun
 
 
-def _min_pool(x_nhwc, k=5):
-    return -F.max_pool2d(-x_nhwc.permute(0, 3, 1, 2), k, stride=1, padding=k // 2).permute(0, 2, 3, 1)
-
-
-@torch.no_grad()
 def view_cosine_gate(inv_depth, dirs):
-    """How frontal the surface is to the camera, per pixel in [0, 1], eroded by a 5x5 window (``:750-756``): the geometric normal is
-    taken from the back-projected inverse-depth map (mean of the four unit cross products of neighbouring finite differences, edges
-    replicated -- ``geometry_utils.depth_to_normal``), the gate is max(-n . unit ray, 0)."""
-    xyz = dirs / inv_depth.unsqueeze(-1).clamp(min=1e-6)
-    dx = xyz[:, :, 1:] - xyz[:, :, :-1]
-    dy = xyz[:, 1:] - xyz[:, :-1]
-    right, left = torch.cat([dx, dx[:, :, -1:]], dim=2), -torch.cat([dx[:, :, :1], dx], dim=2)
-    down, up = torch.cat([dy, dy[:, -1:]], dim=1), -torch.cat([dy[:, :1], dy], dim=1)
-    unit_cross = lambda a, b: F.normalize(torch.cross(a, b, dim=-1), dim=-1)
-    n = F.normalize(unit_cross(right, up) + unit_cross(up, left) + unit_cross(left, down) + unit_cross(down, right), dim=-1)
-    cos = -(n * F.normalize(dirs, dim=-1)).sum(-1, keepdim=True)
-    return _min_pool(cos.clamp(min=0))
+    """``view_cosine`` eroded by a 5x5 window (``mvedit_3d_pipeline.py:750-756``)."""
+    return min_pool(view_cosine(inv_depth, dirs))
 
 
 def tv_normal_loss(pred, weight, power=1.5, target=None):
@@ -215,7 +201,7 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
                 k = step % nb
                 target_rgbs, target_m, target_m_blur, target_dir = img_b[k], mask_b[k], blur_b[k], dir_b[k]
                 bs = target_rgbs.shape[0]
-                target_m_erode = _min_pool(target_m)
+                target_m_erode = min_pool(target_m)
                 target_w = w_b[k][:, None, None, None].expand(-1, render_size, render_size, 1)
                 target_lights = light_b[k][:, None, None, :].expand(-1, render_size, render_size, 3)
                 intrinsics_batch = intr_b[k] * (render_size / intrinsics_size)
@@ -263,3 +249,59 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
         dec.grad_sink = sink_prev
         dec.train(decoder_training_prev)
     return in_mesh
+
+
+def texture_optim(self, tgt_images,                                                   # input images
+                  optimizer, lr, inverse_steps, render_bs, patch_bs,                  # optimisation settings
+                  patch_rgb_weight,                                                   # loss weights
+                  nerf_code, in_mesh,                                                 # mesh model
+                  render_size, intrinsics, intrinsics_size, camera_poses, cam_weights_dense, patch_size,
+                  debug=False, perturb=True, noise=None):
+    """Fit the field's albedo on a FIXED mesh to the target views (``MVEditTexturePipeline.texture_optim``,
+    ``lib/pipelines/mvedit_texture_pipeline.py:93-172``; the super-resolution pipeline's copy is identical,
+    ``mvedit_texture_superres_pipeline.py:89-168``): render ``render_bs`` views through ``MeshRenderer`` with the unshaded field albedo at the
+    surface points, composite on ``self.bg_color``, L1 x 2 with dense per-pixel camera weights [n,h,w,1] + the LPIPS patch term.
+    ``noise`` (extension, parity tests): ``camera_perm``, ``jitter`` [steps, render_bs, 2], ``patch_perm`` [steps, n_patches]."""
+    nerf, dec = self.nerf, self.nerf.decoder
+    device = camera_poses.device
+    noise = noise or {}
+    decoder_training_prev = dec.training
+    dec.train(True)
+    fused = hasattr(optimizer, 'set_lr')
+    sink_prev = dec.grad_sink
+    dec.grad_sink = optimizer if fused and hasattr(optimizer, 'grad_sink') else None
+    shading = make_nerf_albedo_shading_fun(dec, nerf_code)
+    try:
+        with torch.enable_grad():
+            if fused:
+                optimizer.set_lr(lr, group=0)
+            else:
+                optimizer.param_groups[0]['lr'] = lr
+            camera_perm = noise['camera_perm'].to(device) if 'camera_perm' in noise else torch.randperm(camera_poses.size(0), device=device)
+            split = lambda x: x[camera_perm].split(render_bs, dim=0)
+            pose_b, intr_b, img_b, w_b = split(camera_poses), split(intrinsics), split(tgt_images.squeeze(0)), split(cam_weights_dense)
+            nb = len(pose_b)
+            for step in range(inverse_steps):
+                k = step % nb
+                target_rgbs, target_w = img_b[k], w_b[k]
+                intrinsics_batch = intr_b[k] * (render_size / intrinsics_size)
+                if perturb:
+                    u = noise['jitter'][step, :target_rgbs.shape[0]].to(device) if 'jitter' in noise else torch.rand_like(intrinsics_batch[:, 2:])
+                    intrinsics_batch = torch.cat([intrinsics_batch[:, :2], intrinsics_batch[:, 2:] + (u - 0.5) / self.mesh_renderer.ssaa], dim=1)
+                rgba = self.mesh_renderer([in_mesh], pose_b[k][None], intrinsics_batch[None], render_size, render_size, shading)['rgba'].squeeze(0)
+                out_rgbs = rgba[..., :3] + (1 - rgba[..., 3:].clamp(min=1e-3)) * self.bg_color
+                loss = nerf.pixel_loss(out_rgbs, target_rgbs, weight=target_w) * 2
+                if patch_rgb_weight > 0:
+                    out_p, tgt_p = _patches(out_rgbs, render_size, patch_size), _patches(target_rgbs, render_size, patch_size)
+                    w_p = _patches(target_w, render_size, patch_size)
+                    perm = noise['patch_perm'][step].to(device) if 'patch_perm' in noise else torch.randperm(out_p.size(0), device=device)
+                    pick = perm[:patch_bs]
+                    loss = loss + lpips_patch_loss(nerf.patch_loss, out_p[pick], tgt_p[pick], w_p[pick].amax(dim=(1, 2, 3))) * patch_rgb_weight
+                optimizer.zero_grad()
+                loss.backward()
+                optimizer.step()
+                if debug:
+                    print('texture_optim step %d: loss %.5f' % (step, float(loss)))
+    finally:
+        dec.grad_sink = sink_prev
+        dec.train(decoder_training_prev)

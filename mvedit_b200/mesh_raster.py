@@ -4,6 +4,7 @@ argument order and return conventions, so that module reads ``from mvedit_b200 i
 
     glctx = dr.RasterizeCudaContext()
     rast, rast_db = dr.rasterize(glctx, pos[B,V,4], tri[F,3] int32, resolution=(h, w), ranges=None, grad_db=True)
+    tex_out       = dr.texture(tex[B or 1,th,tw,C], uv[B,h,w,2], uv_da=out_da, filter_mode='linear-mipmap-linear')
     out, out_da   = dr.interpolate(attr[B or 1,V,C], rast, tri, rast_db=None, diff_attrs=None)
     color_aa      = dr.antialias(color[B,h,w,C], rast, pos, tri)
 
@@ -86,12 +87,10 @@ class _RasterizeFn(torch.autograd.Function):
         pos_c, tri_c = _f32c(pos), _i32c(tri)
         zbuf, queue = glctx.scratch(B * H * W, B * F, pos.device)
         rast = torch.empty(B, H, W, 4, dtype=torch.float32, device=pos.device)
-        rast_db = torch.empty(B, H, W, 4, dtype=torch.float32, device=pos.device) if grad_db else None
+        rast_db = torch.empty(B, H, W, 4, dtype=torch.float32, device=pos.device)
         call('mve_rasterize_fwd', ptr(pos_c), ptr(tri_c), c_u32(B), c_u32(V), c_u32(F), c_u32(H), c_u32(W), c_int(1), ptr(zbuf), ptr(queue),
              ptr(rast), ptr(rast_db), stream())
         ctx.save_for_backward(pos_c, tri_c, rast)
-        if rast_db is None:
-            rast_db = torch.zeros(B, H, W, 0, dtype=torch.float32, device=pos.device)     # nvdiffrast's "no db" return
         ctx.mark_non_differentiable(rast_db)
         return rast, rast_db
 
@@ -106,7 +105,10 @@ class _RasterizeFn(torch.autograd.Function):
 
 
 def rasterize(glctx, pos, tri, resolution, ranges=None, grad_db=True):
-    """``dr.rasterize`` -> (rast [B,h,w,4] = (u, v, z/w, triangle id + 1), rast_db [B,h,w,4] or [B,h,w,0])."""
+    """``dr.rasterize`` -> (rast [B,h,w,4] = (u, v, z/w, triangle id + 1), rast_db [B,h,w,4] = (du/dX, du/dY, dv/dX, dv/dY)).
+    Like nvdiffrast's CUDA context, ``rast_db`` is produced whatever ``grad_db`` says (the flag only governs gradient flow THROUGH
+    rast_db, which is not carried here at all): the reference rasterises texture space with ``grad_db=False`` and still feeds
+    ``tex_rast_db`` to ``interpolate`` (base_mesh_renderer.py:442,496-497)."""
     if ranges is not None or pos.dim() != 3:
         raise NotImplementedError('mesh_raster.rasterize: range mode (2-D pos + ranges) is not built; MVEdit uses instance mode')
     if pos.shape[-1] != 4 or tri.dim() != 2 or tri.shape[1] != 3:
@@ -193,3 +195,67 @@ def antialias(color, rast, pos, tri, topology_hash=None, pos_gradient_boost=1.0)
 
 def antialias_construct_topology_hash(tri):
     return edge_opposites(tri)
+
+
+def _n_mip_levels(th, tw, max_mip_level=None):
+    n = 1
+    while th % 2 == 0 and tw % 2 == 0 and n < 16 and (max_mip_level is None or n <= max_mip_level):
+        th, tw, n = th // 2, tw // 2, n + 1
+    return n
+
+
+class _TextureFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tex, uv, uv_da, n_levels):
+        Bt, th, tw, C = tex.shape
+        B, H, W, _ = uv.shape
+        uv_c = _f32c(uv)
+        da_c = _f32c(uv_da) if uv_da is not None else None
+        lib_total = _pyramid_floats(Bt, th, tw, C, n_levels)
+        pyr = torch.empty(lib_total, dtype=torch.float32, device=tex.device)
+        pyr[:Bt * th * tw * C].copy_(tex.detach().to(torch.float32).reshape(-1))
+        if n_levels > 1:
+            call('mve_texture_mip_build', ptr(pyr), c_u32(Bt), c_u32(th), c_u32(tw), c_u32(C), c_u32(n_levels), stream())
+        out = torch.empty(B, H, W, C, dtype=torch.float32, device=tex.device)
+        call('mve_texture_fwd', ptr(pyr), c_u32(Bt), c_u32(th), c_u32(tw), c_u32(C), c_u32(n_levels), ptr(uv_c), ptr(da_c), c_u32(B), c_u32(H),
+             c_u32(W), ptr(out), stream())
+        ctx.save_for_backward(uv_c, da_c)
+        ctx.dims = (Bt, th, tw, C, n_levels, lib_total)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        uv_c, da_c = ctx.saved_tensors
+        Bt, th, tw, C, n_levels, total = ctx.dims
+        B, H, W, _ = uv_c.shape
+        g_pyr = torch.zeros(total, dtype=torch.float32, device=uv_c.device)
+        call('mve_texture_bwd', c_u32(Bt), c_u32(th), c_u32(tw), c_u32(C), c_u32(n_levels), ptr(uv_c), ptr(da_c), c_u32(B), c_u32(H), c_u32(W),
+             ptr(_f32c(g_out)), ptr(g_pyr), stream())
+        return g_pyr[:Bt * th * tw * C].view(Bt, th, tw, C), None, None, None
+
+
+def _pyramid_floats(Bt, th, tw, C, n_levels):
+    total = sum(Bt * (th >> l) * (tw >> l) * C for l in range(n_levels))
+    if total >= 2 ** 31:
+        raise ValueError('texture: the mip pyramid exceeds 2^31 floats')
+    return total
+
+
+def texture(tex, uv, uv_da=None, mip_level_bias=None, mip=None, filter_mode='auto', boundary_mode='wrap', max_mip_level=None):
+    """``dr.texture``: tex [B or 1, th, tw, C], uv [B,h,w,2], uv_da [B,h,w,4] (``interpolate(..., diff_attrs='all')``'s second output)
+    -> [B,h,w,C].  ``filter_mode`` 'linear' or 'linear-mipmap-linear' ('auto' = the latter when uv_da is given); boundary mode 'wrap'.
+    Differentiable w.r.t. ``tex`` (the reference bakes textures through exactly that gradient, base_mesh_renderer.py:470-475); uv and
+    uv_da receive no gradient."""
+    if filter_mode == 'auto':
+        filter_mode = 'linear-mipmap-linear' if uv_da is not None else 'linear'
+    if filter_mode not in ('linear', 'linear-mipmap-linear') or boundary_mode != 'wrap' or mip is not None or mip_level_bias is not None:
+        raise NotImplementedError("texture: only filter_mode 'linear' / 'linear-mipmap-linear' with boundary_mode='wrap' is built")
+    if tex.dim() != 4 or uv.dim() != 4 or uv.shape[-1] != 2 or tex.shape[0] not in (1, uv.shape[0]):
+        raise ValueError('texture: tex must be [B or 1, th, tw, C] and uv [B, h, w, 2]')
+    if uv.requires_grad or (uv_da is not None and uv_da.requires_grad):
+        raise NotImplementedError('texture: gradients w.r.t. uv / uv_da are not built (MVEdit optimises either geometry or texture)')
+    use_mip = filter_mode == 'linear-mipmap-linear'
+    if use_mip and (uv_da is None or uv_da.shape[-1] != 4):
+        raise ValueError("texture: 'linear-mipmap-linear' needs uv_da [B,h,w,4]")
+    n_levels = _n_mip_levels(tex.shape[1], tex.shape[2], max_mip_level) if use_mip else 1
+    return _TextureFn.apply(tex, uv, uv_da if use_mip else None, n_levels)

@@ -11,8 +11,12 @@ What runs where:
     work + prefix sums (no per-call ``torch.unique`` over ~10 M edges as in ``base_mesh_renderer.py:153-161``) and produces the SAME
     vertex order and face order as the reference (checked against the reference class, ``tests/test_mesh_pins.py``).
 
-Not built (raise): textured meshes (``dr.texture`` mip-mapped fetch, ``:258-265``; the texture-baking row a-11), range mode for
-``num_scenes > 1`` (``:301-381``), ``dilate_edges`` (``lib/ops/edge_dilation.py``, only used when baking).
+Texture side (row a-11, ``:397-603``): the textured branch of ``forward`` (mip-mapped ``dr.texture`` fetch), ``edge_dilation``
+(``lib/ops/edge_dilation.py``), ``bake_xyz_shading_fun``, ``get_cam_weights_uv`` and ``bake_multiview`` -- the two bakers share one
+per-batch routine here (the reference repeats it).  ``Mesh.auto_uv`` is a per-triangle atlas, NOT xatlas (absent offline): enough to
+bake and export, but its charts are single triangles.
+
+Not built (raise): range mode for ``num_scenes > 1`` (``:301-381``).
 """
 import math
 
@@ -56,6 +60,26 @@ class Mesh:
         self.vn = F.normalize(vn, dim=-1)
         self.fn = faces.to(torch.int32)
         self.face_normals = face_normals
+
+
+    def auto_uv(self, cache_path=None, vmap=True):
+        """A UV atlas with one chart per triangle (the reference unwraps with xatlas, ``mesh_utils.py:384-414``, which is not available
+        offline): triangles are packed two per square cell of an n x n grid, each shrunk towards its centroid so that neighbouring
+        charts keep a gutter for ``edge_dilation``.  Sets ``vt`` [3F,2] and ``ft`` [F,3]; vertices are not split (``vmap`` is moot)."""
+        F_ = self.f.shape[0]
+        dev = self.v.device
+        n = int(math.ceil(math.sqrt((F_ + 1) // 2)))
+        idx = torch.arange(F_, device=dev)
+        cell, upper = idx // 2, (idx % 2).bool()
+        cx, cy = (cell % n).float(), (cell // n).float()
+        lower_tri = torch.tensor([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]], device=dev)
+        upper_tri = torch.tensor([[1.0, 1.0], [0.0, 1.0], [1.0, 0.0]], device=dev)
+        corners = torch.where(upper[:, None, None], upper_tri[None], lower_tri[None])              # [F,3,2] in the unit cell
+        centroid = corners.mean(dim=1, keepdim=True)
+        corners = centroid + (corners - centroid) * 0.8                                            # gutter between the two halves / cells
+        vt = (corners + torch.stack([cx, cy], dim=-1)[:, None, :]) / n
+        self.vt = vt.reshape(-1, 2).contiguous()
+        self.ft = torch.arange(3 * F_, device=dev, dtype=torch.int32).reshape(F_, 3)
 
 
 # ---- regularisers (base_mesh_renderer.py:22-101) -------------------------------------------------------------------------------
@@ -193,6 +217,51 @@ def interpolate_hwc(x, scale_factor, mode='area'):
     return y.reshape(*batch_dim, *y.shape[1:])
 
 
+def min_pool(x_nhwc, k=5):
+    """k x k erosion of an NHWC map (``-max_pool2d(-x)``: "alleviate edge effect", ``:488-489``)."""
+    return -F.max_pool2d(-x_nhwc.permute(0, 3, 1, 2), k, stride=1, padding=k // 2).permute(0, 2, 3, 1)
+
+
+@torch.no_grad()
+def view_cosine(inv_depth, dirs):
+    """How frontal the visible surface is to the camera, per pixel in [0, 1] (``:482-485``; ``mvedit_3d_pipeline.py:750-754``): the
+    geometric normal of the back-projected inverse-depth map (mean of the four unit cross products of neighbouring finite differences,
+    borders replicated -- ``geometry_utils.depth_to_normal``) against the unit ray: max(-n . ray, 0).  inv_depth [n,h,w], dirs [n,h,w,3]."""
+    xyz = dirs / inv_depth.unsqueeze(-1).clamp(min=1e-6)
+    dx = xyz[:, :, 1:] - xyz[:, :, :-1]
+    dy = xyz[:, 1:] - xyz[:, :-1]
+    right, left = torch.cat([dx, dx[:, :, -1:]], dim=2), -torch.cat([dx[:, :, :1], dx], dim=2)
+    down, up = torch.cat([dy, dy[:, -1:]], dim=1), -torch.cat([dy[:, :1], dy], dim=1)
+    unit_cross = lambda a, b: F.normalize(torch.cross(a, b, dim=-1), dim=-1)
+    n = F.normalize(unit_cross(right, up) + unit_cross(up, left) + unit_cross(left, down) + unit_cross(down, right), dim=-1)
+    return (-(n * F.normalize(dirs, dim=-1)).sum(-1, keepdim=True)).clamp(min=0)
+
+
+def edge_dilation(img, mask, radius=3, iters=7):
+    """Grow the valid region of ``img`` [n,c,h,w] (``mask`` [n,1,h,w] in {0,1}) by ``radius`` pixels per iteration: every newly covered
+    pixel copies its nearest valid pixel of the previous iteration (``lib/ops/edge_dilation.py:5-49``; ties broken by the first
+    window position, like the reference's argmax over the unfolded window)."""
+    if radius == 0 or iters == 0:
+        return img
+    n, c, h, w = img.shape
+    r = round(radius)
+    k = 2 * r + 1
+    off = torch.arange(-r, r + 1, device=img.device, dtype=img.dtype)
+    dist = (off[None, :].square() + off[:, None].square()).sqrt()
+    score = (dist.max() - dist + 1).reshape(-1)                    # larger = nearer; zero never wins against a valid pixel
+    for _ in range(iters):
+        grown = F.max_pool2d(mask, k, stride=1, padding=r)
+        fill = ((grown - mask) > 0.5).squeeze(1)
+        at = fill.nonzero()
+        window = F.unfold(mask, k, padding=r).reshape(n, k * k, h, w).permute(0, 2, 3, 1)[fill]
+        best = (window * score).argmax(dim=-1)
+        src_y, src_x = at[:, 1] + best // k - r, at[:, 2] + best % k - r
+        out = img.clone()
+        out[at[:, 0], :, at[:, 1], at[:, 2]] = img[at[:, 0], :, src_y, src_x]
+        img, mask = out, grown
+    return img
+
+
 class MeshRenderer(nn.Module):
     def __init__(self, near=0.1, far=10, ssaa=1, texture_filter='linear-mipmap-linear', opengl=False):
         super().__init__()
@@ -224,8 +293,6 @@ class MeshRenderer(nn.Module):
         num_scenes, num_images, _, _ = poses.size()
         if num_scenes != 1 or len(meshes) != 1:
             raise NotImplementedError('MeshRenderer: range mode (num_scenes > 1) is not built')
-        if dilate_edges > 0:
-            raise NotImplementedError('MeshRenderer: dilate_edges is not built')
         mesh = meshes[0]
         if self.ssaa > 1:
             h, w = h * self.ssaa, w * self.ssaa
@@ -249,7 +316,9 @@ class MeshRenderer(nn.Module):
         rot_normal = torch.where(fg.unsqueeze(-1), rot_normal, rot_normal.new_tensor(normal_bg))
 
         if mesh.vt is not None and mesh.albedo is not None:
-            raise NotImplementedError('MeshRenderer: textured meshes need dr.texture (row a-11), which is not built')
+            texc, texc_db = dr.interpolate(mesh.vt.unsqueeze(0).contiguous(), rast, mesh.ft, rast_db=rast_db, diff_attrs='all')
+            albedo = dr.texture(mesh.albedo.unsqueeze(0)[..., :3].contiguous(), texc.detach(), uv_da=texc_db, filter_mode=self.texture_filter).unsqueeze(0)
+            albedo = torch.where(fg.unsqueeze(-1), albedo, torch.zeros_like(albedo))
         elif mesh.vc is not None:
             rgba = dr.interpolate(mesh.vc.contiguous()[None] if mesh.vc.dim() == 2 else mesh.vc.contiguous(), rast, tri)[0].reshape(
                 num_scenes, num_images, h, w, 4)
@@ -266,6 +335,9 @@ class MeshRenderer(nn.Module):
                 rgb_reshade = shading_fun(world_pos=xyz[fg], albedo=albedo[fg], world_normal=normal[fg], fg_mask=fg)
                 albedo = torch.zeros_like(albedo).masked_scatter(fg.unsqueeze(-1).expand_as(albedo), rgb_reshade.to(albedo.dtype))
             rgba = torch.cat([albedo, alpha], dim=-1)
+            if dilate_edges > 0:
+                rgba = rgba.reshape(num_scenes * num_images, h, w, 4).permute(0, 3, 1, 2)
+                rgba = edge_dilation(rgba, rgba[:, 3:], dilate_edges).permute(0, 2, 3, 1).reshape(num_scenes, num_images, h, w, 4)
             if aa:
                 rgba, depth, rot_normal = dr.antialias(
                     torch.cat([rgba, depth.unsqueeze(-1), rot_normal], dim=-1).squeeze(0).contiguous(), rast, v_clip, tri
@@ -278,3 +350,101 @@ class MeshRenderer(nn.Module):
         finally:
             torch.set_grad_enabled(prev_grad_enabled)
         return dict(rgba=rgba, depth=depth, normal=rot_normal)
+
+    # ---- texture baking (base_mesh_renderer.py:397-603) --------------------------------------------------------------------------
+    def _texture_space(self, mesh, map_size):
+        """Rasterise the UV layout itself: every texel learns which triangle covers it (``:405-408,441-443,520-522``)."""
+        vt_clip = torch.cat([mesh.vt * 2 - 1, mesh.vt.new_tensor([[0.0, 1.0]]).expand(mesh.vt.size(0), -1)], dim=-1)
+        tex_rast, tex_rast_db = dr.rasterize(self.glctx, vt_clip[None].contiguous(), mesh.ft, (map_size, map_size), grad_db=False)
+        return tex_rast, tex_rast_db, (tex_rast[..., 3] > 0).reshape(map_size, map_size)
+
+    def bake_xyz_shading_fun(self, meshes, shading_fun, map_size=1024, force_auto_uv=False, dilation_iters=7):
+        """Evaluate ``shading_fun(world_pos=...)`` at the surface point under every texel and store it as the albedo map (``:397-423``)."""
+        assert len(meshes) == 1, 'only support one mesh'
+        mesh = meshes[0]
+        if mesh.vt is None or force_auto_uv:
+            mesh.auto_uv()
+        assert len(mesh.ft) == len(mesh.f)
+        tex_rast, _, valid = self._texture_space(mesh, map_size)
+        xyz = dr.interpolate(mesh.v[None].contiguous(), tex_rast, mesh.f)[0].reshape(map_size, map_size, 3)
+        albedo = xyz.new_zeros((map_size, map_size, 3))
+        albedo[valid] = shading_fun(world_pos=xyz[valid]).to(albedo.dtype)
+        albedo = edge_dilation(albedo.permute(2, 0, 1)[None], valid[None, None].float(), iters=dilation_iters).squeeze(0).permute(1, 2, 0)
+        mesh.albedo = torch.cat([albedo.clamp(min=0, max=1), torch.ones_like(albedo[..., :1])], dim=-1)
+        mesh.textureless = False
+        return [mesh]
+
+    def _bake_batch(self, mesh, poses, intrinsics, alphas, payload, h, w, tex_rast, tex_rast_db, map_size, cos_weight_pow):
+        """One ``render_bs`` batch of views resampled into texture space (the body both bakers share, ``:447-502`` = ``:524-579``):
+        -> (tex [bs,ms,ms,C+1]: payload channels + the image-space confidence, visibility [bs,ms,ms,1]: how much of each texel the view's
+        pixels fetch -- the gradient of a mip-mapped fetch of a ones map w.r.t. that map)."""
+        bs = poses.size(0)
+        r_mat_c2w, proj = self.projection(poses[..., :3, :], intrinsics, h, w)
+        v_cam = (mesh.v.detach() - poses[:, :3, 3].unsqueeze(-2)) @ r_mat_c2w
+        v_clip = (F.pad(v_cam, pad=(0, 1), mode='constant', value=1.0) @ proj.transpose(-1, -2)).contiguous()
+        rast, rast_db = dr.rasterize(self.glctx, v_clip, mesh.f, (h, w), grad_db=False)
+        texc, texc_db = dr.interpolate(mesh.vt.unsqueeze(0).contiguous(), rast, mesh.ft, rast_db=rast_db, diff_attrs='all')
+        with torch.enable_grad():
+            ones = torch.ones((bs, map_size, map_size, 1), device=poses.device, dtype=poses.dtype).requires_grad_(True)
+            seen = dr.texture(ones, texc, uv_da=texc_db, filter_mode=self.texture_filter)
+            visibility = torch.autograd.grad(seen.sum(), ones)[0]
+        fg = rast[..., 3] > 0
+        depth = (1 / dr.interpolate(-v_cam[..., 2:3].contiguous(), rast, mesh.f)[0].reshape(bs, h, w)).masked_fill(~fg, 0)
+        from .nerf import pixel_directions
+        dirs = F.normalize(pixel_directions(intrinsics, h, w), dim=-1)
+        weight = min_pool((view_cosine(depth, dirs) ** cos_weight_pow) * alphas)
+        v_img = v_clip[..., :2] / v_clip[..., 3:] * 0.5 + 0.5
+        imgc, imgc_db = dr.interpolate(v_img.contiguous(), tex_rast.expand(bs, -1, -1, -1).contiguous(), mesh.f,
+                                       rast_db=tex_rast_db.expand(bs, -1, -1, -1).contiguous(), diff_attrs='all')
+        src = weight if payload is None else torch.cat([payload, weight], dim=-1)
+        return dr.texture(src.contiguous(), imgc, uv_da=imgc_db, filter_mode=self.texture_filter), visibility
+
+    @torch.no_grad()
+    def get_cam_weights_uv(self, meshes, poses, intrinsics, alphas=None, render_size=512, map_size=1024, render_bs=8, cos_weight_pow=1.0):
+        """Per-view blending weights in texture space (``:425-505``) -> (weights [1,n,ms,ms,1], valid [1,ms,ms])."""
+        assert len(meshes) == 1, 'only support one mesh'
+        mesh = meshes[0]
+        n = max(poses.size(-3), intrinsics.size(-2))
+        poses, intrinsics = poses[0].expand(n, -1, -1), intrinsics[0].expand(n, -1)
+        if alphas is not None:
+            _, h, w, _ = alphas.size()
+            assert render_size == h == w
+        else:
+            h = w = render_size
+            alphas = torch.ones((n, h, w, 1), device=poses.device, dtype=poses.dtype)
+        tex_rast, tex_rast_db, valid = self._texture_space(mesh, map_size)
+        out = []
+        for a_b, p_b, i_b in zip(alphas.split(render_bs), poses.split(render_bs), intrinsics.split(render_bs)):
+            tex, vis = self._bake_batch(mesh, p_b, i_b, a_b, None, h, w, tex_rast, tex_rast_db, map_size, cos_weight_pow)
+            out.append(tex * vis)
+        return torch.cat(out, dim=0)[None], valid[None]
+
+    @torch.no_grad()
+    def bake_multiview(self, meshes, images, alphas, poses, intrinsics, map_size=1024, cos_weight_pow=8.0, base_weight=0.0, render_bs=8):
+        """Blend the views into one albedo map, each weighted by (frontalness ** cos_weight_pow) x alpha x visibility (``:507-603``)."""
+        assert len(meshes) == 1, 'only support one mesh'
+        mesh = meshes[0]
+        images, alphas = images[0], alphas[0]
+        n, h, w, _ = images.size()
+        poses, intrinsics = poses[0].expand(n, -1, -1), intrinsics[0].expand(n, -1)
+        acc = torch.zeros((map_size, map_size, 3), device=images.device, dtype=images.dtype)
+        wsum = torch.zeros((map_size, map_size, 1), device=images.device, dtype=images.dtype)
+        tex_rast, tex_rast_db, valid = self._texture_space(mesh, map_size)
+        for im_b, a_b, p_b, i_b in zip(images.split(render_bs), alphas.split(render_bs), poses.split(render_bs), intrinsics.split(render_bs)):
+            tex, vis = self._bake_batch(mesh, p_b, i_b, a_b, im_b, h, w, tex_rast, tex_rast_db, map_size, cos_weight_pow)
+            weight = tex[..., 3:4] * vis
+            acc += (tex[..., :3] * weight).sum(dim=0)
+            wsum += weight.sum(dim=0)
+        if base_weight > 0 and (mesh.albedo is not None or mesh.vc is not None):
+            if mesh.albedo is not None:
+                tex = F.interpolate(mesh.albedo.permute(2, 0, 1)[None], size=map_size, mode='bilinear').squeeze(0).permute(1, 2, 0)
+            else:
+                tex = dr.interpolate(mesh.vc[None].contiguous() if mesh.vc.dim() == 2 else mesh.vc.contiguous(), tex_rast.contiguous(), mesh.f)[0].squeeze(0)
+            weight = (tex[..., 3:4] * valid[..., None] if tex.size(-1) == 4 else valid[..., None]) * (base_weight ** cos_weight_pow)
+            acc += tex[..., :3] * weight
+            wsum += weight
+        albedo = acc / wsum.clamp(min=1e-8)
+        albedo = edge_dilation(albedo.permute(2, 0, 1)[None], valid[None, None].float()).squeeze(0).permute(1, 2, 0)
+        mesh.albedo = torch.cat([albedo.clamp(min=0, max=1), torch.ones_like(albedo[..., :1])], dim=-1)
+        mesh.textureless = False
+        return [mesh]

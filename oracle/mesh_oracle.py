@@ -153,7 +153,11 @@ def mesh_renderer_forward(mesh, poses, intrinsics, h, w, shading_fun=None, norma
     normal = F.normalize(normal, dim=-1)
     rot_normal = (normal @ r_mat_c2w.unsqueeze(2)) / 2 + 0.5
     rot_normal = torch.where(fg.unsqueeze(-1), rot_normal, rot_normal.new_tensor(list(normal_bg)))
-    if mesh.vc is not None:
+    if mesh.vt is not None and mesh.albedo is not None:
+        texc, texc_db = ro.interpolate(mesh.vt.unsqueeze(0), rast, mesh.ft, rast_db=rast_db, diff_attrs='all')
+        albedo = ro.texture(mesh.albedo.unsqueeze(0)[..., :3], texc.detach(), texc_db, filter_mode='linear-mipmap-linear').unsqueeze(0)
+        albedo = torch.where(fg.unsqueeze(-1), albedo, torch.zeros_like(albedo))
+    elif mesh.vc is not None:
         rgba = ro.interpolate(mesh.vc if mesh.vc.dim() == 3 else mesh.vc[None], rast, tri)[0].reshape(num_scenes, num_images, h, w, 4)
         alpha = alpha * rgba[..., 3:4]
         albedo = rgba[..., :3] * alpha
@@ -252,3 +256,136 @@ def mesh_optim(decoder, tgt_images, tgt_masks, optimizer, lr, lr_multiplier, inv
         mesh_verts, mesh_faces = dmtet(tet_verts + deform, tet_sdf, tet_indices)
         in_mesh = make_mesh(mesh_verts, mesh_faces.int())
     return in_mesh, losses
+
+
+# ---- texture baking (base_mesh_renderer.py:397-603), restated on the raster oracle ------------------------------------------------------
+
+def edge_dilation(img, mask, radius=3, iters=7):
+    """lib/ops/edge_dilation.py:5-49 (pinned by tests/golden/mesh_pins.npz through the product's copy of the same semantics)."""
+    if radius == 0 or iters == 0:
+        return img
+    n, c, h, w = img.size()
+    int_radius = round(radius)
+    kernel_size = int(int_radius * 2 + 1)
+    distance1d_sq = torch.linspace(-int_radius, int_radius, kernel_size, dtype=img.dtype).square()
+    kernel_distance = (distance1d_sq.reshape(1, -1) + distance1d_sq.reshape(-1, 1)).sqrt()
+    kernel_neg_distance = kernel_distance.max() - kernel_distance + 1
+    for _ in range(iters):
+        mask_out = F.max_pool2d(mask, kernel_size, stride=1, padding=int_radius)
+        do_fill_mask = ((mask_out - mask) > 0.5).squeeze(1)
+        do_fill = do_fill_mask.nonzero()
+        mask_unfold = F.unfold(mask, kernel_size, padding=int_radius).reshape(n, kernel_size * kernel_size, h, w).permute(0, 2, 3, 1)
+        fill_ind = (mask_unfold[do_fill_mask] * kernel_neg_distance.flatten()).argmax(dim=-1)
+        do_fill_h = do_fill[:, 1] + fill_ind // kernel_size - int_radius
+        do_fill_w = do_fill[:, 2] + fill_ind % kernel_size - int_radius
+        img_out = img.clone()
+        img_out[do_fill[:, 0], :, do_fill[:, 1], do_fill[:, 2]] = img[do_fill[:, 0], :, do_fill_h, do_fill_w]
+        img, mask = img_out, mask_out
+    return img
+
+
+def _proj(poses_batch, intrinsics_batch, h, w, near, far):
+    bs = poses_batch.size(0)
+    r_mat_c2w = torch.cat([poses_batch[:, :3, :1], -poses_batch[:, :3, 1:3]], dim=-1)
+    proj = poses_batch.new_zeros([bs, 4, 4])
+    proj[:, 0, 0] = 2 * intrinsics_batch[:, 0] / w
+    proj[:, 0, 2] = -2 * intrinsics_batch[:, 2] / w + 1
+    proj[:, 1, 1] = -2 * intrinsics_batch[:, 1] / h
+    proj[:, 1, 2] = -2 * intrinsics_batch[:, 3] / h + 1
+    proj[:, 2, 2] = -(far + near) / (far - near)
+    proj[:, 2, 3] = -(2 * far * near) / (far - near)
+    proj[:, 3, 2] = -1
+    return r_mat_c2w, proj
+
+
+def bake_multiview(mesh, images, alphas, poses, intrinsics, map_size=64, cos_weight_pow=8.0, render_bs=8, near=0.01, far=100.0,
+                   weights_only=False):
+    """base_mesh_renderer.py:507-603 (``weights_only``: get_cam_weights_uv, :425-505, which runs the same loop on the weight alone).
+    images [1,n,h,w,3], alphas [1,n,h,w,1], poses [1,n,3|4,4], intrinsics [1,n,4]."""
+    images, alphas = images[0], alphas[0]
+    n, h, w, _ = images.size()
+    poses, intrinsics = poses[0].expand(n, -1, -1), intrinsics[0].expand(n, -1)
+    new_albedo_map_sum = torch.zeros((map_size, map_size, 3), dtype=images.dtype)
+    weights_sum = torch.zeros((map_size, map_size, 1), dtype=images.dtype)
+    vt_clip = torch.cat([mesh.vt * 2 - 1, mesh.vt.new_tensor([[0., 1.]]).expand(mesh.vt.size(0), -1)], dim=-1)
+    tex_rast, tex_rast_db = dr_rasterize(vt_clip[None], mesh.ft, (map_size, map_size))
+    valid = (tex_rast[..., 3] > 0).reshape(map_size, map_size)
+    out_weights = []
+    for images_batch, alphas_batch, poses_batch, intrinsics_batch in zip(images.split(render_bs), alphas.split(render_bs),
+                                                                         poses.split(render_bs), intrinsics.split(render_bs)):
+        bs = images_batch.size(0)
+        r_mat_c2w, proj = _proj(poses_batch, intrinsics_batch, h, w, near, far)
+        v_cam = (mesh.v.detach() - poses_batch[:, :3, 3].unsqueeze(-2)) @ r_mat_c2w
+        v_clip = F.pad(v_cam, pad=(0, 1), mode='constant', value=1.0) @ proj.transpose(-1, -2)
+        rast, rast_db = dr_rasterize(v_clip, mesh.f, (h, w))
+        texc, texc_db = ro.interpolate(mesh.vt.unsqueeze(0), rast, mesh.ft, rast_db=rast_db, diff_attrs='all')
+        with torch.enable_grad():
+            dummy_maps = torch.ones((bs, map_size, map_size, 1), dtype=images.dtype).requires_grad_(True)
+            albedo = ro.texture(dummy_maps, texc, texc_db, filter_mode='linear-mipmap-linear')
+            visibility_grad = torch.autograd.grad(albedo.sum(), dummy_maps, create_graph=False)[0]
+        fg = rast[..., 3] > 0
+        depth = 1 / ro.interpolate(-v_cam[..., 2:3], rast, mesh.f)[0].reshape(bs, h, w)
+        depth = depth.masked_fill(~fg, 0)
+        directions = get_ray_directions(h, w, intrinsics_batch, norm=True)
+        normals_opencv = depth_to_normal(depth, directions, format='opencv') * 2 - 1
+        normals_cos_weight = (normals_opencv[..., None, :] @ directions[..., :, None]).squeeze(-1).neg().clamp(min=0)
+        img_space_weight = (normals_cos_weight ** cos_weight_pow) * alphas_batch
+        img_space_weight = -F.max_pool2d(-img_space_weight.permute(0, 3, 1, 2), 5, stride=1, padding=2).permute(0, 2, 3, 1)
+        v_img = v_clip[..., :2] / v_clip[..., 3:] * 0.5 + 0.5
+        imgc, imgc_db = ro.interpolate(v_img, tex_rast.expand(bs, -1, -1, -1), mesh.f, rast_db=tex_rast_db.expand(bs, -1, -1, -1), diff_attrs='all')
+        if weights_only:
+            tex = ro.texture(img_space_weight, imgc, imgc_db, filter_mode='linear-mipmap-linear')
+            out_weights.append(tex * visibility_grad)
+            continue
+        tex = ro.texture(torch.cat([images_batch, img_space_weight], dim=-1), imgc, imgc_db, filter_mode='linear-mipmap-linear')
+        weight = tex[..., 3:4] * visibility_grad
+        new_albedo_map_sum += (tex[..., :3] * weight).sum(dim=0)
+        weights_sum += weight.sum(dim=0)
+    if weights_only:
+        return torch.cat(out_weights, dim=0)[None], valid[None]
+    new_albedo_map = new_albedo_map_sum / weights_sum.clamp(min=1e-8)
+    new_albedo_map = edge_dilation(new_albedo_map.permute(2, 0, 1)[None], valid[None, None].float()).squeeze(0).permute(1, 2, 0)
+    return torch.cat([new_albedo_map.clamp(min=0, max=1), torch.ones_like(new_albedo_map[..., :1])], dim=-1)
+
+
+def bake_xyz_shading_fun(mesh, shading_fun, map_size=64, dilation_iters=7):
+    """base_mesh_renderer.py:397-423 for a mesh that already has vt / ft."""
+    vt_clip = torch.cat([mesh.vt * 2 - 1, mesh.vt.new_tensor([[0., 1.]]).expand(mesh.vt.size(0), -1)], dim=-1)
+    rast, _ = dr_rasterize(vt_clip[None], mesh.ft, (map_size, map_size))
+    valid = (rast[..., 3] > 0).reshape(map_size, map_size)
+    xyz = ro.interpolate(mesh.v[None], rast, mesh.f)[0].reshape(map_size, map_size, 3)
+    new_albedo_map = xyz.new_zeros((map_size, map_size, 3))
+    new_albedo_map[valid] = shading_fun(world_pos=xyz[valid])
+    new_albedo_map = edge_dilation(new_albedo_map.permute(2, 0, 1)[None], valid[None, None].float(), iters=dilation_iters).squeeze(0).permute(1, 2, 0)
+    return torch.cat([new_albedo_map.clamp(min=0, max=1), torch.ones_like(new_albedo_map[..., :1])], dim=-1)
+
+
+def texture_optim(decoder, tgt_images, optimizer, lr, inverse_steps, render_bs, nerf_code, in_mesh, render_size, intrinsics, intrinsics_size,
+                  camera_poses, cam_weights_dense, noise, bg_color=0.5, pixel_loss=None, near=0.01, far=100.0):
+    """lib/pipelines/mvedit_texture_pipeline.py:93-172 without the patch term, every random draw supplied."""
+    pixel_loss = pixel_loss or L1LossMod(loss_weight=1.2)
+    optimizer.param_groups[0]['lr'] = lr
+    camera_perm = noise['camera_perm']
+    pose_batches = camera_poses[camera_perm].split(render_bs, dim=0)
+    intrinsics_batches = intrinsics[camera_perm].split(render_bs, dim=0)
+    tgt_image_batches = tgt_images.squeeze(0)[camera_perm].split(render_bs, dim=0)
+    cam_weights_batches = cam_weights_dense[camera_perm].split(render_bs, dim=0)
+    num_pose_batches = len(pose_batches)
+
+    def shading_fun(world_pos=None, albedo=None, **kwargs):
+        if len(world_pos) == 0:
+            return world_pos if albedo is None else albedo
+        return decoder.point_decode([world_pos], None, nerf_code)[1]
+
+    for inverse_step_id in range(inverse_steps):
+        pose_batch = pose_batches[inverse_step_id % num_pose_batches]
+        intrinsics_batch = intrinsics_batches[inverse_step_id % num_pose_batches] * (render_size / intrinsics_size)
+        target_rgbs = tgt_image_batches[inverse_step_id % num_pose_batches]
+        target_w = cam_weights_batches[inverse_step_id % num_pose_batches]
+        intrinsics_batch = torch.cat([intrinsics_batch[:, :2], intrinsics_batch[:, 2:] + (noise['jitter'][inverse_step_id, :len(pose_batch)] - 0.5)], dim=1)
+        render_out = mesh_renderer_forward(in_mesh, pose_batch[None], intrinsics_batch[None], render_size, render_size, shading_fun, near=near, far=far)
+        out_rgbs = (render_out['rgba'][..., :3] + (1 - render_out['rgba'][..., 3:].clamp(min=1e-3)) * bg_color).squeeze(0)
+        loss = pixel_loss(out_rgbs.reshape(target_rgbs.size()), target_rgbs, weight=target_w) * 2
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()

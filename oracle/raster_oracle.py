@@ -285,3 +285,55 @@ def antialias(color, rast, pos, tri, opp=None):
         flat = flat.index_add(0, idx, delta)
         out = flat.reshape(B, H, W, C)
     return out
+
+
+def n_mip_levels(th, tw, max_mip_level=None):
+    """Levels of the 2x2-average pyramid: a level is halved while both of its dimensions are even."""
+    n = 1
+    while th % 2 == 0 and tw % 2 == 0 and (max_mip_level is None or n <= max_mip_level):
+        th, tw, n = th // 2, tw // 2, n + 1
+    return n
+
+
+def texture(tex, uv, uv_da=None, filter_mode='linear-mipmap-linear', max_mip_level=None):
+    """``dr.texture`` restated (boundary mode 'wrap', nvdiffrast's default): tex [Bt,th,tw,C] (Bt = 1 or B), uv [B,H,W,2] with (0,0) the
+    corner of texel (0,0), uv_da [B,H,W,4] = (du/dX, du/dY, dv/dX, dv/dY).  Bilinear taps on the two pyramid levels around
+    ``0.5 log2(major axis^2 of the pixel footprint in texels)`` (clamped to the pyramid), linear blend between them; without uv_da or
+    with filter_mode='linear': level 0.  Differentiable w.r.t. ``tex`` (torch ops)."""
+    B, H, W, _ = uv.shape
+    Bt, th, tw, C = tex.shape
+    use_mip = filter_mode == 'linear-mipmap-linear' and uv_da is not None
+    n_levels = n_mip_levels(th, tw, max_mip_level) if use_mip else 1
+    pyr = [tex]
+    for _ in range(1, n_levels):
+        pyr.append(torch.nn.functional.avg_pool2d(pyr[-1].permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1))
+    bidx = (torch.arange(B)[:, None, None].expand(B, H, W) if Bt == B and B > 1 else torch.zeros(B, H, W, dtype=torch.long))
+
+    def tap(level):
+        t = pyr[level]
+        hl, wl = t.shape[1], t.shape[2]
+        x, y = uv[..., 0] * wl - 0.5, uv[..., 1] * hl - 0.5
+        x0, y0 = torch.floor(x), torch.floor(y)
+        fx, fy = (x - x0)[..., None], (y - y0)[..., None]
+        x0, y0 = x0.long(), y0.long()
+        g = lambda yy, xx: t[bidx, yy % hl, xx % wl]
+        return ((1 - fx) * (1 - fy) * g(y0, x0) + fx * (1 - fy) * g(y0, x0 + 1)) + (1 - fx) * fy * g(y0 + 1, x0) + fx * fy * g(y0 + 1, x0 + 1)
+
+    if n_levels == 1:
+        return tap(0)
+    dsdx, dsdy, dtdx, dtdy = uv_da[..., 0] * tw, uv_da[..., 1] * tw, uv_da[..., 2] * th, uv_da[..., 3] * th
+    A, Bq, Cq = dsdx ** 2 + dtdx ** 2, dsdy ** 2 + dtdy ** 2, dsdx * dsdy + dtdx * dtdy
+    major = 0.5 * (A + Bq) + torch.sqrt(0.25 * (A - Bq) ** 2 + Cq ** 2)
+    level = torch.where(major > 0, 0.5 * torch.log2(major.clamp(min=1e-30)), torch.zeros_like(major)).clamp(0, n_levels - 1)
+    l0 = torch.floor(level).long()
+    f = (level - l0)[..., None]
+    l1 = (l0 + 1).clamp(max=n_levels - 1)
+    out = torch.zeros(B, H, W, C, dtype=tex.dtype)
+    for l in range(n_levels):
+        s = None
+        m0, m1 = (l0 == l)[..., None], ((l1 == l) & (l1 != l0))[..., None]
+        if m0.any() or m1.any():
+            s = tap(l)
+            out = out + torch.where(m0, (1 - torch.where(l1[..., None] != l0[..., None], f, torch.zeros_like(f))) * s, torch.zeros_like(s))
+            out = out + torch.where(m1, f * s, torch.zeros_like(s))
+    return out

@@ -262,3 +262,54 @@ def test_init_tet_from_field():
     assert sdf.min() >= -1 and sdf.max() <= 1 and (sdf > 0).any() and (sdf < 0).any()
     outside = (verts.abs() > 1).any(dim=-1)
     assert (sdf[outside] == -1).all()
+
+
+# ---- texture side (row a-11) -------------------------------------------------------------------------------------------------------------
+
+def test_texture_fetch_and_gradient_vs_oracle():
+    from oracle import raster_oracle as ro
+    from mvedit_b200 import mesh_raster as dr
+    v = np.array([[[-0.9, -0.7, 0.3, 1.0], [0.9, -0.8, 0.6, 1.6], [0.8, 0.9, 0.9, 2.6], [-0.8, 0.8, 0.2, 1.2]]], np.float32)
+    v[..., :3] *= v[..., 3:]
+    tri = torch.tensor([[0, 1, 2], [0, 2, 3]], dtype=torch.int32).cuda()
+    vt = torch.tensor([[[0.05, 0.1], [2.3, 0.0], [2.1, 1.7], [-0.4, 1.2]]]).cuda()
+    rast, db = dr.rasterize(dr.RasterizeCudaContext(), torch.from_numpy(v).cuda(), tri, (40, 48))
+    uv, uv_da = dr.interpolate(vt, rast, tri, rast_db=db, diff_attrs='all')
+    for mode in ('linear', 'linear-mipmap-linear'):
+        tex = _rand((1, 32, 64, 3), 21)
+        tex_g = tex.clone().cuda().requires_grad_(True)
+        out = dr.texture(tex_g, uv, uv_da=uv_da if mode != 'linear' else None, filter_mode=mode)
+        tex_o = tex.detach().double().requires_grad_(True)
+        out_o = ro.texture(tex_o, uv.cpu().double(), uv_da.cpu().double() if mode != 'linear' else None, filter_mode=mode)
+        # log2 of the footprint is not bit-identical between the GPU and the CPU: the blend weight between two mip levels may differ by ~1e-6
+        torch.testing.assert_close(out.detach().cpu(), out_o.detach().float(), rtol=1e-4, atol=5e-5)
+        g = _rand(out.shape, 22)
+        out.backward(g.cuda())
+        out_o.backward(g.double())
+        torch.testing.assert_close(tex_g.grad.cpu(), tex_o.grad.float(), rtol=1e-3, atol=2e-4)
+
+
+def test_bake_and_textured_render_vs_oracle():
+    from oracle import mesh_oracle as mo
+    from mvedit_b200.mesh_renderer import Mesh, MeshRenderer
+    v, f = synth_mesh.icosphere(2)
+    mesh = Mesh(v=(torch.from_numpy(v).float() * 0.5).cuda(), f=torch.from_numpy(f).int().cuda())
+    mesh.auto_normal()
+    mesh.auto_uv()
+    om = mo.make_mesh(mesh.v.cpu(), mesh.f.cpu())
+    om.vt, om.ft = mesh.vt.cpu(), mesh.ft.cpu()
+    n, size, ms = 3, 32, 64
+    poses, intr = _cameras(n, size, seed=3)
+    g = torch.Generator().manual_seed(9)
+    images = torch.rand(1, n, size, size, 3, generator=g)
+    alphas = (torch.rand(1, n, size, size, 1, generator=g) > 0.1).float()
+    r = MeshRenderer(near=0.01, far=100)
+    baked = r.bake_multiview([mesh], images.cuda(), alphas.cuda(), poses[None].cuda(), intr[None].cuda(), map_size=ms, cos_weight_pow=8.0, render_bs=2)[0]
+    albedo_o = mo.bake_multiview(om, images, alphas, poses[None], intr[None], map_size=ms, cos_weight_pow=8.0, render_bs=2)
+    d = (baked.albedo.cpu() - albedo_o).abs()
+    assert d.mean() < 2e-4 and (d > 1e-2).float().mean() < 5e-3
+    with torch.no_grad():
+        out = r([baked], poses[None].cuda(), intr[None].cuda(), size, size)
+    om.albedo = baked.albedo.cpu()
+    out_o = mo.mesh_renderer_forward(om, poses[None], intr[None], size, size)
+    torch.testing.assert_close(out['rgba'].cpu(), out_o['rgba'], rtol=1e-3, atol=1e-3)

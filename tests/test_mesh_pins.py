@@ -90,3 +90,11 @@ def test_dmtet_on_the_reference_tet_grid():
     np.testing.assert_allclose(v.double().abs().sum(0).numpy(), PINS['big_vabs'], rtol=1e-9, atol=1e-6)
     dig = np.frombuffer(hashlib.sha256(np.ascontiguousarray(f.numpy().astype(np.int64)).tobytes()).digest()[:8], np.int64)[0]
     assert dig == PINS['big_face_digest']
+
+
+def test_edge_dilation_matches_reference():
+    from mvedit_b200.mesh_renderer import edge_dilation
+    img, mask = T('ed_img'), T('ed_mask')
+    np.testing.assert_array_equal(edge_dilation(img, mask).numpy(), PINS['ed_out_default'])
+    np.testing.assert_array_equal(edge_dilation(img, mask, radius=2, iters=3).numpy(), PINS['ed_out_r2_i3'])
+    assert edge_dilation(img, mask, radius=0) is img

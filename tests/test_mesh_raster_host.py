@@ -57,7 +57,7 @@ def test_rasterize_matches_oracle_bit_for_bit(kind):
     assert (rast[fg][:, :2] >= 0).all() and (rast[fg][:, 0] + rast[fg][:, 1] <= 1 + 1e-6).all()
     assert (np.abs(rast[fg][:, 2]) <= 1).all()
     r2, db2 = dr.rasterize(dr.RasterizeCudaContext(), torch.from_numpy(pos), torch.from_numpy(tri), res, grad_db=False)
-    assert db2.shape[-1] == 0 and (r2.numpy() == rast).all()
+    assert (db2.numpy() == db).all() and (r2.numpy() == rast).all()      # rast_db is produced whatever grad_db says (as nvdiffrast's CUDA context)
 
 
 def test_closed_mesh_is_watertight():
@@ -217,3 +217,56 @@ def test_antialias_alpha_tracks_subpixel_motion():
     px = 2.0 / W
     c0, c1 = cover(0.25 + 0.1 * px), cover(0.25 + 0.6 * px)
     assert abs((c1 - c0) - 0.5 * 16) < 0.3             # the edge is 16 pixels long; it moved half a pixel
+
+
+def _uv_scene(seed=0):
+    """uv / uv_da of a textured quad seen at a grazing angle: footprints from sub-texel to many texels."""
+    v = np.array([[[-0.9, -0.7, 0.3, 1.0], [0.9, -0.8, 0.6, 1.6], [0.8, 0.9, 0.9, 2.6], [-0.8, 0.8, 0.2, 1.2]]], np.float32)
+    v[..., :3] *= v[..., 3:]
+    tri = torch.tensor([[0, 1, 2], [0, 2, 3]], dtype=torch.int32)
+    vt = torch.tensor([[[0.05, 0.1], [2.3, 0.0], [2.1, 1.7], [-0.4, 1.2]]])         # beyond [0,1]: wrap addressing
+    rast, db = dr.rasterize(dr.RasterizeCudaContext(), torch.from_numpy(v), tri, (40, 48))
+    uv, uv_da = dr.interpolate(vt, rast, tri, rast_db=db, diff_attrs='all')
+    return uv, uv_da
+
+
+@pytest.mark.parametrize('mode', ['linear', 'linear-mipmap-linear'])
+@pytest.mark.parametrize('batched', [False, True])
+def test_texture_forward_backward_vs_oracle(mode, batched):
+    uv, uv_da = _uv_scene()
+    uv, uv_da = uv.expand(2, -1, -1, -1).contiguous(), uv_da.expand(2, -1, -1, -1).contiguous()
+    tex = _rand_like((2 if batched else 1, 32, 64, 3), 21).requires_grad_(True)
+    out = dr.texture(tex, uv, uv_da=uv_da if mode != 'linear' else None, filter_mode=mode)
+    tex_o = tex.detach().double().requires_grad_(True)
+    out_o = ro.texture(tex_o, uv.double(), uv_da.double() if mode != 'linear' else None, filter_mode=mode)
+    torch.testing.assert_close(out, out_o.float(), rtol=1e-4, atol=2e-5)
+    g = _rand_like(out.shape, 22)
+    out.backward(g)
+    out_o.backward(g.double())
+    torch.testing.assert_close(tex.grad, tex_o.grad.float(), rtol=1e-4, atol=1e-4)
+    if mode != 'linear':
+        lv = 0.5 * torch.log2((uv_da[..., [0, 2]] * torch.tensor([64.0, 32.0])).square().sum(-1).clamp(min=1e-12))
+        assert (lv > 1).any() and (lv < 0).any()             # the scene exercises several pyramid levels and the clamp at level 0
+
+
+def test_texture_of_ones_map_gradient_is_a_coverage_map():
+    """The reference's baking trick (base_mesh_renderer.py:470-475): d(sum of fetches) / d(texture of ones) = how much every texel is
+    seen; the weights of every fetch sum to one on every level, so the total equals the pixel count."""
+    uv, uv_da = _uv_scene()
+    ones = torch.ones(1, 64, 64, 1, requires_grad=True)
+    out = dr.texture(ones, uv, uv_da=uv_da, filter_mode='linear-mipmap-linear')
+    torch.testing.assert_close(out, torch.ones_like(out), rtol=0, atol=1e-6)
+    (g,) = torch.autograd.grad(out.sum(), ones)
+    assert abs(g.sum().item() - out.numel()) < 1e-2 * out.numel() and (g >= 0).all()
+
+
+def test_texture_rejects_what_is_not_built():
+    uv, uv_da = _uv_scene()
+    tex = torch.ones(1, 8, 8, 1)
+    with pytest.raises(NotImplementedError):
+        dr.texture(tex, uv, filter_mode='nearest')
+    with pytest.raises(NotImplementedError):
+        dr.texture(tex, uv, boundary_mode='clamp')
+    with pytest.raises(NotImplementedError):
+        dr.texture(tex, uv.clone().requires_grad_(True))
+    assert dr.texture(torch.ones(1, 6, 10, 1), uv, uv_da=uv_da).shape[-1] == 1       # odd halves: the pyramid stops at 3 x 5

@@ -98,13 +98,35 @@ def test_vertex_colour_path_and_no_grad_render():
         torch.testing.assert_close(r[k], ro_[k], rtol=1e-4, atol=2e-5)
 
 
-def test_unbuilt_branches_raise():
+def test_textured_mesh_forward_matches_oracle_and_gradient_reaches_the_texture():
+    v, f = synth_mesh.icosphere(2)
+    poses, intr = _cameras(2, 40)
+    vt_v = torch.from_numpy(v).float() * 0.5
+    mesh = Mesh(v=vt_v, f=torch.from_numpy(f).int())
+    mesh.auto_normal()
+    mesh.auto_uv()
+    assert mesh.vt.shape == (3 * len(f), 2) and mesh.ft.shape == (len(f), 3) and mesh.vt.min() >= 0 and mesh.vt.max() <= 1
+    albedo = torch.rand(32, 32, 4, generator=torch.Generator().manual_seed(7)).requires_grad_(True)
+    mesh.albedo = albedo
+    r = MeshRenderer(near=0.01, far=100)([mesh], poses[None], intr[None], 40, 40)
+    om = mo.make_mesh(vt_v, torch.from_numpy(f).int())
+    om.vt, om.ft = mesh.vt, mesh.ft
+    om.albedo = albedo.detach().clone().requires_grad_(True)
+    r_o = mo.mesh_renderer_forward(om, poses[None], intr[None], 40, 40)
+    for k in ('rgba', 'depth', 'normal'):
+        torch.testing.assert_close(r[k].detach(), r_o[k].detach(), rtol=1e-4, atol=2e-5)
+    w = torch.randn(r['rgba'].shape, generator=torch.Generator().manual_seed(8))
+    (r['rgba'] * w).sum().backward()
+    (r_o['rgba'] * w).sum().backward()
+    assert albedo.grad[..., :3].abs().sum() > 0 and (albedo.grad[..., 3] == 0).all()
+    torch.testing.assert_close(albedo.grad, om.albedo.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_range_mode_raises():
     v, f = synth_mesh.icosphere(0)
     poses, intr = _cameras(1, 16)
-    mesh = Mesh(v=torch.from_numpy(v).float() * 0.5, f=torch.from_numpy(f).int(), vt=torch.zeros(3, 2), albedo=torch.zeros(4, 4, 4))
+    mesh = Mesh(v=torch.from_numpy(v).float() * 0.5, f=torch.from_numpy(f).int())
     mesh.auto_normal()
-    with pytest.raises(NotImplementedError):
-        MeshRenderer()([mesh], poses[None], intr[None], 16, 16)
     with pytest.raises(NotImplementedError):
         MeshRenderer()([mesh, mesh], poses[None].expand(2, -1, -1, -1), intr[None].expand(2, -1, -1), 16, 16)
 
@@ -154,3 +176,75 @@ def test_init_tet_and_mesh_optim_match_oracle():
     assert (p['deform'].abs().max() > 1e-4) and (p['w'] - ToyField().w.detach()).abs().max() > 1e-3      # everything moved
     assert p['f'].shape == o['f'].shape and (p['f'] == o['f']).all()
     torch.testing.assert_close(p['v'], o['v'], rtol=1e-4, atol=2e-5)
+
+
+def _textured_sphere(subdiv=2):
+    v, f = synth_mesh.icosphere(subdiv)
+    mesh = Mesh(v=torch.from_numpy(v).float() * 0.5, f=torch.from_numpy(f).int())
+    mesh.auto_normal()
+    mesh.auto_uv()
+    om = mo.make_mesh(mesh.v, mesh.f)
+    om.vt, om.ft = mesh.vt, mesh.ft
+    return mesh, om
+
+
+def test_bake_multiview_and_cam_weights_match_oracle():
+    mesh, om = _textured_sphere()
+    n, size, ms = 3, 32, 64
+    poses, intr = _cameras(n, size, seed=3)
+    g = torch.Generator().manual_seed(9)
+    images = torch.rand(1, n, size, size, 3, generator=g)
+    alphas = (torch.rand(1, n, size, size, 1, generator=g) > 0.1).float()
+    r = MeshRenderer(near=0.01, far=100)
+    wts, valid = r.get_cam_weights_uv([mesh], poses[None], intr[None], alphas=alphas[0], render_size=size, map_size=ms, render_bs=2, cos_weight_pow=1.0)
+    wts_o, valid_o = mo.bake_multiview(om, images, alphas, poses[None], intr[None], map_size=ms, cos_weight_pow=1.0, render_bs=2, weights_only=True)
+    assert wts.shape == (1, n, ms, ms, 1) and (valid == valid_o).all() and 0.2 < valid.float().mean() < 0.9
+    torch.testing.assert_close(wts, wts_o, rtol=1e-3, atol=1e-4)
+    assert wts.sum() > 1
+    baked = r.bake_multiview([mesh], images, alphas, poses[None], intr[None], map_size=ms, cos_weight_pow=8.0, render_bs=2)[0]
+    albedo_o = mo.bake_multiview(om, images, alphas, poses[None], intr[None], map_size=ms, cos_weight_pow=8.0, render_bs=2)
+    assert baked.albedo.shape == (ms, ms, 4) and baked.textureless is False
+    d = (baked.albedo - albedo_o).abs()
+    assert d.mean() < 1e-4 and (d > 1e-2).float().mean() < 2e-3        # a texel whose total weight is ~1e-8 may round differently
+
+
+def test_bake_xyz_shading_fun_matches_oracle_and_renders_back():
+    mesh, om = _textured_sphere(1)
+    field = ToyField()
+    fun = mopt.make_nerf_albedo_shading_fun(field, None)
+    r = MeshRenderer(near=0.01, far=100)
+    with torch.no_grad():
+        baked = r.bake_xyz_shading_fun([mesh], fun, map_size=256)[0]
+        albedo_o = mo.bake_xyz_shading_fun(om, fun, map_size=256)
+    torch.testing.assert_close(baked.albedo, albedo_o, rtol=1e-4, atol=2e-5)
+    # rendering the baked texture reproduces the field's albedo at the visible surface points
+    poses, intr = _cameras(2, 48, seed=5)
+    with torch.no_grad():
+        out = r([baked], poses[None], intr[None], 48, 48, aa=False)
+        ref = r([Mesh(v=mesh.v, f=mesh.f, vn=mesh.vn, fn=mesh.fn)], poses[None], intr[None], 48, 48, shading_fun=lambda world_pos=None, **kw: fun(world_pos=world_pos), aa=False)
+    fg = out['rgba'][..., 3] > 0
+    assert (out['rgba'][..., :3][fg] - ref['rgba'][..., :3][fg]).abs().mean() < 0.03
+
+
+def test_texture_optim_matches_oracle():
+    mesh, om = _textured_sphere(2)
+    n, size, steps = 4, 32, 3
+    poses, intr = _cameras(n, size, seed=4)
+    g = torch.Generator().manual_seed(12)
+    tgt = torch.rand(1, n, size, size, 3, generator=g)
+    w_dense = torch.rand(n, size, size, 1, generator=g)
+    noise = dict(camera_perm=torch.tensor([1, 3, 0, 2]), jitter=torch.rand(steps, 2, 2, generator=g))
+    res = {}
+    for name in ('product', 'oracle'):
+        field = ToyField()
+        opt = torch.optim.Adam(field.parameters(), lr=0.01)
+        if name == 'product':
+            nerf = SimpleNamespace(decoder=field, pixel_loss=L1LossMod(loss_weight=1.2), patch_loss=None)
+            pipe = SimpleNamespace(nerf=nerf, mesh_renderer=MeshRenderer(near=0.01, far=100), bg_color=0.5)
+            mopt.texture_optim(pipe, tgt, opt, 0.02, steps, 2, 8, 0.0, None, mesh, size, intr, size, poses, w_dense, 16, noise=noise)
+        else:
+            mo.texture_optim(field, tgt, opt, 0.02, steps, 2, None, om, size, intr, size, poses, w_dense, noise)
+        res[name] = (field.w.detach().clone(), field.b.detach().clone())
+    for a, b in zip(res['product'], res['oracle']):
+        assert (a - b).abs().max() < 2e-5
+    assert (res['product'][0] - ToyField().w.detach()).abs().max() > 1e-2
