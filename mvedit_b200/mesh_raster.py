@@ -99,8 +99,9 @@ class _RasterizeFn(torch.autograd.Function):
         pos_c, tri_c, rast = ctx.saved_tensors
         B, H, W, _ = rast.shape
         g_pos = torch.zeros_like(pos_c)
+        g_rast_c = _f32c(g_rast)          # a named reference: a temporary passed as ptr(...) would be freed before the kernel reads it
         call('mve_rasterize_bwd', ptr(pos_c), ptr(tri_c), c_u32(B), c_u32(pos_c.shape[1]), c_u32(tri_c.shape[0]), c_u32(H), c_u32(W), c_int(1),
-             ptr(rast), ptr(_f32c(g_rast)), ptr(g_pos), stream())
+             ptr(rast), ptr(g_rast_c), ptr(g_pos), stream())
         return None, g_pos, None, None, None, None
 
 
@@ -143,8 +144,9 @@ class _InterpolateFn(torch.autograd.Function):
         Ba, Va, C = attr_c.shape
         g_attr = torch.zeros_like(attr_c)
         g_rast = torch.empty_like(rast_c) if ctx.needs_input_grad[1] else None
+        g_out_c = _f32c(g_out)
         call('mve_interpolate_bwd', ptr(attr_c), ptr(tri_c), ptr(rast_c), c_u32(B), c_u32(H), c_u32(W), c_u32(Va), c_u32(tri_c.shape[0]), c_u32(C),
-             c_int(0 if Ba == 1 else 1), ptr(_f32c(g_out)), ptr(g_attr), ptr(g_rast), stream())
+             c_int(0 if Ba == 1 else 1), ptr(g_out_c), ptr(g_attr), ptr(g_rast), stream())
         return g_attr, g_rast, None, None, None
 
 
@@ -178,8 +180,9 @@ class _AntialiasFn(torch.autograd.Function):
         B, H, W, C = color_c.shape
         g_color = torch.empty_like(color_c)
         g_pos = torch.zeros_like(pos_c) if ctx.needs_input_grad[2] else None
+        g_out_c = _f32c(g_out)
         call('mve_antialias_bwd', ptr(color_c), ptr(rast_c), ptr(pos_c), ptr(tri_c), ptr(opp_c), c_u32(B), c_u32(H), c_u32(W), c_u32(C),
-             c_u32(pos_c.shape[1]), c_u32(tri_c.shape[0]), c_int(1), ptr(_f32c(g_out)), ptr(g_color), ptr(g_pos), stream())
+             c_u32(pos_c.shape[1]), c_u32(tri_c.shape[0]), c_int(1), ptr(g_out_c), ptr(g_color), ptr(g_pos), stream())
         return g_color, None, g_pos, None, None
 
 
@@ -229,8 +232,9 @@ class _TextureFn(torch.autograd.Function):
         Bt, th, tw, C, n_levels, total = ctx.dims
         B, H, W, _ = uv_c.shape
         g_pyr = torch.zeros(total, dtype=torch.float32, device=uv_c.device)
+        g_out_c = _f32c(g_out)
         call('mve_texture_bwd', c_u32(Bt), c_u32(th), c_u32(tw), c_u32(C), c_u32(n_levels), ptr(uv_c), ptr(da_c), c_u32(B), c_u32(H), c_u32(W),
-             ptr(_f32c(g_out)), ptr(g_pyr), stream())
+             ptr(g_out_c), ptr(g_pyr), stream())
         return g_pyr[:Bt * th * tw * C].view(Bt, th, tw, C), None, None, None
 
 
