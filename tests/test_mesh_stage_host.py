@@ -248,3 +248,30 @@ def test_texture_optim_matches_oracle():
     for a, b in zip(res['product'], res['oracle']):
         assert (a - b).abs().max() < 2e-5
     assert (res['product'][0] - ToyField().w.detach()).abs().max() > 1e-2
+
+
+def test_render_mesh_views_matches_oracle_composition():
+    """The mesh branch of the per-step render (mvedit_3d_pipeline.py:1341-1360,1391-1396): shaded rgb over the background colour and the
+    normalised inverse depth, as bf16 NCHW ControlNet inputs."""
+    from oracle.nerf_oracle import normalize_depth
+    v, f = synth_mesh.icosphere(2)
+    n, size = 3, 32
+    poses, intr = _cameras(n, size, seed=6)
+    lights = torch.nn.functional.normalize(torch.randn(n, 3, generator=torch.Generator().manual_seed(1)), dim=-1)
+    field = ToyField()
+    vt = torch.from_numpy(v).float() * 0.5
+    mesh = Mesh(v=vt, f=torch.from_numpy(f).int())
+    mesh.auto_normal()
+    pipe = SimpleNamespace(nerf=SimpleNamespace(decoder=field, bg_color=1.0), mesh_renderer=MeshRenderer(near=0.01, far=100),
+                           normal_bg=[0.5, 0.5, 1.0], tonemapping=None)
+    with torch.no_grad():
+        images, depths = mopt.render_mesh_views(pipe, mesh, None, poses, intr, size * 2, size, lights, 0.2, render_bs=2)
+        lp = lights[:, None, None, :].expand(-1, size, size, -1)
+        r_o = mo.mesh_renderer_forward(mo.make_mesh(vt, torch.from_numpy(f).int()), poses[None], intr[None] * 0.5, size, size,
+                                       mopt.make_nerf_shading_fun(field, None, lp, 0.2))
+    assert images.shape == depths.shape == (n, 3, size, size) and images.dtype == depths.dtype == torch.bfloat16
+    rgba = r_o['rgba'].squeeze(0)
+    img_o = (rgba[..., :3] + 1.0 * (1 - rgba[..., 3:])).permute(0, 3, 1, 2).clamp(0, 1)
+    dep_o = normalize_depth(r_o['depth'].squeeze(0), rgba[..., 3:]).unsqueeze(1).repeat(1, 3, 1, 1)
+    assert (images.float() - img_o).abs().max() < 1e-2 and (depths.float() - dep_o).abs().max() < 1e-2     # bf16 storage
+    assert depths.float().max() > 0.9 and (depths.float()[:, 0][rgba[..., 3] == 0] == 0).all()

@@ -1,0 +1,116 @@
+"""Host logic of ``MVEdit3DPipeline.__call__`` past ``progress_to_dmtet`` (mvedit_3d_pipeline.py:1306-1334,1480-1487 of the reference):
+NeRF stage -> ``init_tet`` -> two-group optimiser -> ``mesh_optim`` per step -> baked, textured mesh + state dict, and the state-dict
+restore.  CPU: ``optim_only=True`` (no denoiser), the NeRF fit stubbed out, an analytic field instead of the CUDA hash grid, the
+rasteriser through tests/host_harness.py.  What it checks is the control flow and the argument plumbing of the mesh branch."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+
+from tests import host_harness, synth_mesh
+from mvedit_b200 import mesh_raster as dr
+from mvedit_b200 import mvedit_3d_pipeline as P
+from mvedit_b200.mesh_renderer import MeshRenderer, make_tet_grid
+from mvedit_b200.nerf import L1LossMod
+
+
+@pytest.fixture(autouse=True)
+def _route():
+    with host_harness.routed(dr):
+        yield
+
+
+class ToyDecoder(nn.Module):
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(0)
+        self.w = nn.Parameter(torch.randn(3, 3, generator=g))
+        self.b = nn.Parameter(torch.randn(3, generator=g) * 0.1)
+        self.grad_sink = None
+        self.state_dict_bak = None
+
+    def backup_state_dict(self):
+        self.state_dict_bak = copy.deepcopy(self.state_dict())
+
+    def restore_state_dict(self):
+        self.load_state_dict(self.state_dict_bak)
+
+    def point_decode(self, xyzs, dirs, code, density_only=False, **kw):
+        x = xyzs[0]
+        sigma = 40 * (0.45 - x.norm(dim=-1))
+        return sigma, (None if density_only else torch.sigmoid(x @ self.w + self.b)), [len(x)]
+
+    def point_density_decode(self, xyzs, code, **kw):
+        s, _, n = self.point_decode(xyzs, None, code, density_only=True)
+        return s, n
+
+
+class AdamLike(torch.optim.Adam):
+    def __init__(self, params, lr=1e-3, **kw):
+        super().__init__(params, lr=lr)
+
+    def set_lr(self, lr, group=None):
+        for i, g in enumerate(self.param_groups):
+            if group is None or group == i:
+                g['lr'] = float(lr)
+
+
+def test_call_runs_the_dmtet_stage_and_returns_a_baked_mesh(monkeypatch):
+    n, size = 4, 32
+    calls = dict(nerf=0, mesh=[])
+    monkeypatch.setattr(P, 'FusedAdam', AdamLike)
+    monkeypatch.setattr(P, 'nerf_optim', lambda *a, **k: calls.__setitem__('nerf', calls['nerf'] + 1))
+    real_mesh_optim = P.mesh_optim
+
+    def spy(self, *a, **k):
+        calls['mesh'].append((a[6], a[5]))              # (inverse_steps, lr_multiplier)
+        return real_mesh_optim(self, *a, **k)
+    monkeypatch.setattr(P, 'mesh_optim', spy)
+
+    dec = ToyDecoder()
+    w0 = dec.w.detach().clone()
+    nerf = nn.Module()
+    nerf.decoder, nerf.bg_color, nerf.grid_size, nerf.pixel_loss, nerf.patch_loss = dec, 1.0, 8, L1LossMod(loss_weight=1.2), None
+    nerf.get_init_density_grid = lambda ns, device=None: torch.zeros(ns, 8 ** 3, dtype=torch.float16)
+    nerf.get_init_density_bitfield = lambda ns, device=None: torch.zeros(ns, 8 ** 3 // 8, dtype=torch.uint8)
+    unet = nn.Module()
+    unet.device = torch.device('cpu')
+    pipe = P.MVEdit3DPipeline(None, None, None, unet, None, None, nerf, mesh_renderer=MeshRenderer(near=0.01, far=100))
+    poses = torch.from_numpy(synth_mesh.surround_poses(n, 1)).float()
+    intr = torch.from_numpy(synth_mesh.intrinsics(size)).float()
+    yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing='ij')
+    disc = (((xx - 15.5) ** 2 + (yy - 15.5) ** 2).float().sqrt() < 9).float()
+    init = torch.cat([torch.rand(n, 3, size, size, generator=torch.Generator().manual_seed(2)), disc[None, None].expand(n, -1, -1, -1)], dim=1)
+    mesh, state = pipe(init_images=init, camera_poses=poses, intrinsics=intr, intrinsics_size=size, use_reference=False, use_normal=False,
+                       optim_only=True, num_inference_steps=4, progress_to_dmtet=0.4, tet_resolution=12, tets=make_tet_grid(12),
+                       n_inverse_steps=2, init_inverse_steps=2, tet_init_inverse_steps=3, render_bs=2, patch_size=16,
+                       render_size_p=lambda p: size, patch_rgb_weight=lambda p: 0.0, mesh_simplify_texture_steps=0,
+                       bake_texture=True, bake_texture_kwargs=dict(map_size=64))
+    # progress = i / 4 for i = 0..4: NeRF stage at 0, 0.25; DMTet at 0.5 (init: tet_init_inverse_steps), 0.75, 1.0
+    assert calls['nerf'] == 2
+    assert [c[0] for c in calls['mesh']] == [3, 2, 2]
+    assert calls['mesh'][0][1] == pytest.approx(min((1 - 0.5) / (1 - 0.4), 1)) and calls['mesh'][2][1] == pytest.approx(0.0)
+    assert mesh is not None and mesh.v.shape[0] > 50 and mesh.f.shape[1] == 3 and not mesh.v.requires_grad
+    assert mesh.albedo.shape == (64, 64, 4) and mesh.vt is not None and mesh.textureless is False
+    assert set(state.keys()) == {'w', 'b'} and (state['w'] - w0).abs().max() > 1e-4        # the returned state is the optimised field ...
+    assert torch.equal(dec.w.detach(), w0)                                                # ... and the module's own weights are restored
+
+
+def test_call_without_mesh_renderer_raises_cleanly(monkeypatch):
+    monkeypatch.setattr(P, 'FusedAdam', AdamLike)
+    monkeypatch.setattr(P, 'nerf_optim', lambda *a, **k: None)
+    dec = ToyDecoder()
+    nerf = nn.Module()
+    nerf.decoder, nerf.bg_color, nerf.grid_size, nerf.pixel_loss, nerf.patch_loss = dec, 1.0, 8, L1LossMod(loss_weight=1.2), None
+    nerf.get_init_density_grid = lambda ns, device=None: torch.zeros(ns, 8 ** 3, dtype=torch.float16)
+    nerf.get_init_density_bitfield = lambda ns, device=None: torch.zeros(ns, 8 ** 3 // 8, dtype=torch.uint8)
+    unet = nn.Module()
+    unet.device = torch.device('cpu')
+    pipe = P.MVEdit3DPipeline(None, None, None, unet, None, None, nerf, mesh_renderer=None)
+    poses = torch.from_numpy(synth_mesh.surround_poses(2, 1)).float()
+    init = torch.rand(2, 4, 16, 16)
+    mesh, state = pipe(init_images=init, camera_poses=poses, intrinsics=torch.tensor([30.0, 30.0, 8.0, 8.0]), intrinsics_size=16,
+                       use_reference=False, use_normal=False, optim_only=True, num_inference_steps=2, progress_to_dmtet=0.4)
+    assert mesh is None and state is None               # the reference's behaviour on any failure: print the traceback, return (None, None)
+    assert dec.state_dict_bak is not None
