@@ -19,6 +19,7 @@ import torch.nn.functional as F
 from .mesh_renderer import (DMTet, Mesh, laplacian_smooth_loss, make_tet_grid, min_pool, normal_consistency,   # noqa: F401  (re-exported)
                             view_cosine)
 from .nerf import blur_masks, pixel_directions
+from . import view_shard
 
 
 def init_tet(nerf_model, nerf_code=None, density_thresh=5.0, resolution=128, tets=None):
@@ -148,6 +149,14 @@ def render_mesh_views(self, in_mesh, nerf_code, camera_poses, intrinsics, intrin
     return images.contiguous(), depths.contiguous()
 
 
+def _from_rank0(t):
+    """Rank 0's draw on every rank (random permutations / jitter must agree across the data-parallel replicas)."""
+    import torch.distributed as dist
+    t = t.contiguous()
+    dist.broadcast(t, 0)
+    return t
+
+
 def _patches(x_nhwc, render_size, patch_size):
     """[n, rs, rs, C] -> [n * (rs/ps)^2, C, ps, ps] (``:784-792``)."""
     g = render_size // patch_size
@@ -162,7 +171,12 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
                render_size, intrinsics, intrinsics_size, camera_poses, cam_weights, lights, patch_size,     # cameras
                is_end, ambient_light, mesh_reduction, debug=False, perturb=True, noise=None):
     """``self``: the pipeline (``nerf``, ``mesh_renderer``, ``normal_bg``, ``tonemapping``).  ``noise`` (extension, for parity tests):
-    dict with ``camera_perm`` [n], ``jitter`` [steps, render_bs, 2] in [0,1), ``patch_perm`` [steps, n_patches] replacing the draws."""
+    dict with ``camera_perm`` [n], ``jitter`` [steps, render_bs, 2] in [0,1), ``patch_perm`` [steps, n_patches] replacing the draws.
+
+    Multi-GPU (``nerf.data_parallel`` with torch.distributed up; the reference is single-GPU): data-parallel over VIEWS -- every rank
+    renders its block of the iteration's ``render_bs`` views, the per-view loss terms are weighted by the block's share and the
+    replicated regularisers by 1 / world, so that ONE all-reduce (sum) of the gradients reproduces the single-GPU gradient; the fused
+    Adam step and the marching-tets extraction then run replicated and bit-identical.  Random draws are rank 0's (one small broadcast)."""
     if tgt_normals is not None:
         raise NotImplementedError('mesh_optim: target normals need the normal model, which is not built')
     if mesh_reduction < 1 and is_end:
@@ -181,6 +195,8 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
     fused = hasattr(optimizer, 'set_lr')
     sink_prev = dec.grad_sink
     dec.grad_sink = optimizer if fused and hasattr(optimizer, 'grad_sink') else None
+    rank, world = view_shard.world() if getattr(nerf, 'data_parallel', False) else (0, 1)
+    shared = (lambda t: _from_rank0(t)) if world > 1 else (lambda t: t)
     try:
         with torch.enable_grad():
             if fused:
@@ -189,7 +205,7 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
             else:
                 optimizer.param_groups[0]['lr'] = lr
                 optimizer.param_groups[1]['lr'] = lr * 0.04 * lr_multiplier
-            camera_perm = noise['camera_perm'].to(device) if 'camera_perm' in noise else torch.randperm(n_views, device=device)
+            camera_perm = noise['camera_perm'].to(device) if 'camera_perm' in noise else shared(torch.randperm(n_views, device=device))
             split = lambda x: x[camera_perm].split(render_bs, dim=0)
             pose_b, intr_b = split(camera_poses), split(intrinsics)
             img_b, mask_b, blur_b = split(tgt_images.squeeze(0)), split(tgt_masks.squeeze(0)), split(tgt_masks_blur)
@@ -199,44 +215,54 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
                 inverse_steps = max(inverse_steps, mesh_simplify_texture_steps)
             for step in range(inverse_steps):
                 k = step % nb
-                target_rgbs, target_m, target_m_blur, target_dir = img_b[k], mask_b[k], blur_b[k], dir_b[k]
-                bs = target_rgbs.shape[0]
-                target_m_erode = min_pool(target_m)
-                target_w = w_b[k][:, None, None, None].expand(-1, render_size, render_size, 1)
-                target_lights = light_b[k][:, None, None, :].expand(-1, render_size, render_size, 3)
+                bs = img_b[k].shape[0]
+                lo, hi = view_shard.local_range(bs, rank, world) if world > 1 else (0, bs)
+                share = (hi - lo) / bs                       # this rank's share of the per-view means
                 intrinsics_batch = intr_b[k] * (render_size / intrinsics_size)
                 if perturb:                                  # +-0.5 px principal-point jitter (:733-735)
-                    u = noise['jitter'][step, :bs].to(device) if 'jitter' in noise else torch.rand_like(intrinsics_batch[:, 2:])
+                    u = noise['jitter'][step, :bs].to(device) if 'jitter' in noise else shared(torch.rand_like(intrinsics_batch[:, 2:]))
                     intrinsics_batch = torch.cat([intrinsics_batch[:, :2], intrinsics_batch[:, 2:] + (u - 0.5) / self.mesh_renderer.ssaa], dim=1)
-
-                render_out = self.mesh_renderer(
-                    [in_mesh], pose_b[k][None], intrinsics_batch[None], render_size, render_size,
-                    make_nerf_shading_fun(dec, nerf_code, target_lights, ambient_light, self.tonemapping), normal_bg=self.normal_bg)
-                rgba = render_out['rgba'].squeeze(0)
-                out_alphas = rgba[..., 3:]
-                out_rgbs = rgba[..., :3] / out_alphas.clamp(min=1e-3)
-                out_rgbs = out_rgbs * target_m_erode + target_rgbs * (1 - target_m_erode)
-                out_normals = render_out['normal'].squeeze(0)
-                gate = view_cosine_gate(render_out['depth'].squeeze(0).detach(), target_dir)
-                out_normals = out_normals * gate + out_normals.detach() * (1 - gate)      # value unchanged, gradient scaled by the gate
-                out_normals_fg = (out_normals - normal_bg * (1 - out_alphas)) / out_alphas.clamp(min=1e-3)
-                wgt = target_w / cam_weights_mean
-
-                loss = nerf.pixel_loss(out_rgbs, target_rgbs, weight=wgt) * 4.5
-                loss = loss + nerf.pixel_loss(out_alphas, target_m_blur, weight=wgt) * 2.0
-                loss = loss + tv_normal_loss(out_normals_fg.permute(0, 3, 1, 2), out_alphas.detach().permute(0, 3, 1, 2)) * (normal_reg_weight * 2)
-                loss = loss + laplacian_smooth_loss(in_mesh.v, in_mesh.f) * mesh_normal_reg_weight
-                loss = loss + normal_consistency(in_mesh.face_normals, in_mesh.f) * mesh_normal_reg_weight
-
-                if patch_rgb_weight > 0:
-                    out_p, tgt_p = _patches(out_rgbs, render_size, patch_size), _patches(target_rgbs, render_size, patch_size)
-                    w_p = _patches(target_w, render_size, patch_size)
-                    perm = noise['patch_perm'][step].to(device) if 'patch_perm' in noise else torch.randperm(out_p.size(0), device=device)
-                    pick = perm[:patch_bs]
-                    loss = loss + lpips_patch_loss(nerf.patch_loss, out_p[pick], tgt_p[pick], w_p[pick, 0, 0, 0] / cam_weights_mean) * patch_rgb_weight
+                loss = (laplacian_smooth_loss(in_mesh.v, in_mesh.f) + normal_consistency(in_mesh.face_normals, in_mesh.f)) * (mesh_normal_reg_weight / world)
+                if hi > lo:
+                    target_rgbs, target_m, target_m_blur, target_dir = img_b[k][lo:hi], mask_b[k][lo:hi], blur_b[k][lo:hi], dir_b[k][lo:hi]
+                    target_m_erode = min_pool(target_m)
+                    target_w = w_b[k][lo:hi, None, None, None].expand(-1, render_size, render_size, 1)
+                    target_lights = light_b[k][lo:hi, None, None, :].expand(-1, render_size, render_size, 3)
+                    render_out = self.mesh_renderer(
+                        [in_mesh], pose_b[k][lo:hi][None], intrinsics_batch[lo:hi][None], render_size, render_size,
+                        make_nerf_shading_fun(dec, nerf_code, target_lights, ambient_light, self.tonemapping), normal_bg=self.normal_bg)
+                    rgba = render_out['rgba'].squeeze(0)
+                    out_alphas = rgba[..., 3:]
+                    out_rgbs = rgba[..., :3] / out_alphas.clamp(min=1e-3)
+                    out_rgbs = out_rgbs * target_m_erode + target_rgbs * (1 - target_m_erode)
+                    out_normals = render_out['normal'].squeeze(0)
+                    gate = view_cosine_gate(render_out['depth'].squeeze(0).detach(), target_dir)
+                    out_normals = out_normals * gate + out_normals.detach() * (1 - gate)      # value unchanged, gradient scaled by the gate
+                    out_normals_fg = (out_normals - normal_bg * (1 - out_alphas)) / out_alphas.clamp(min=1e-3)
+                    wgt = target_w / cam_weights_mean
+                    views = nerf.pixel_loss(out_rgbs, target_rgbs, weight=wgt) * 4.5
+                    views = views + nerf.pixel_loss(out_alphas, target_m_blur, weight=wgt) * 2.0
+                    views = views + tv_normal_loss(out_normals_fg.permute(0, 3, 1, 2), out_alphas.detach().permute(0, 3, 1, 2)) * (normal_reg_weight * 2)
+                    if patch_rgb_weight > 0:
+                        out_p, tgt_p = _patches(out_rgbs, render_size, patch_size), _patches(target_rgbs, render_size, patch_size)
+                        w_p = _patches(target_w, render_size, patch_size)
+                        if world > 1:                        # each rank draws its share of the patches among its own views
+                            perm = torch.randperm(out_p.size(0), device=device)
+                            pick = perm[:max(patch_bs * (hi - lo) // bs, 1)]
+                        else:
+                            perm = noise['patch_perm'][step].to(device) if 'patch_perm' in noise else torch.randperm(out_p.size(0), device=device)
+                            pick = perm[:patch_bs]
+                        views = views + lpips_patch_loss(nerf.patch_loss, out_p[pick], tgt_p[pick], w_p[pick, 0, 0, 0] / cam_weights_mean) * patch_rgb_weight
+                    loss = loss + views * share
 
                 optimizer.zero_grad()
                 loss.backward()
+                if world > 1:
+                    if fused and hasattr(optimizer, 'flat_grad'):
+                        optimizer.fold_grads()
+                        view_shard.allreduce_flat(optimizer.flat_grad)
+                    else:
+                        view_shard.allreduce_grads([p_ for g_ in optimizer.param_groups for p_ in g_['params']])
                 optimizer.step()
 
                 with torch.enable_grad():

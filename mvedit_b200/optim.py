@@ -83,14 +83,20 @@ class FusedAdam(torch.optim.Optimizer):
         self._clean = True
 
     @torch.no_grad()
+    def fold_grads(self):
+        """Make ``flat_grad`` hold every gradient: a ``p.grad`` that autograd attached as a fresh tensor is added into its slot of the flat
+        buffer (``step`` does this itself; a data-parallel caller does it before all-reducing ``flat_grad``)."""
+        for p, v in zip(self._params, self._views):
+            if p.grad is not None and p.grad.data_ptr() != v[0].data_ptr():
+                v[0].add_(p.grad)
+                p.grad = v[0]
+
+    @torch.no_grad()
     def step(self, closure=None, grad_scale=1.0):
         assert closure is None
         if tuple(p.data_ptr() for p in self._params) != self._ptrs:
             self._build_args()       # a parameter was re-allocated (load_state_dict copies in place, so this is rare)
-        for p, v in zip(self._params, self._views):
-            if p.grad is not None and p.grad.data_ptr() != v[0].data_ptr():        # autograd attached a fresh tensor: fold it in
-                v[0].add_(p.grad)
-                p.grad = v[0]
+        self.fold_grads()
         g0 = self.param_groups[0]
         c = self._c
         call('mve_adam_step', c_u32(len(self._params)), c['p'], c['g'], c['m'], c['v'], c['n'], c['lr'], c_f32(g0['betas'][0]),
