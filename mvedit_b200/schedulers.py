@@ -7,7 +7,10 @@ the published update rules of diffusers==0.27.2 (requirements.txt:13; not instal
   * ``DPMSolverMultistepScheduler``  -- image-to-3D (lib/core/webui/tab_img_to_3d.py:54): DPM-Solver++(2M), epsilon prediction,
                                         midpoint, ``lower_order_final``, ``final_sigmas_type='zero'``
 
-``DPMSolverSDE`` (one scheduler object per view and a torchsde Brownian tree, mvedit_3d_pipeline.py:1176-1177,1456-1459) is not built.
+  * ``DPMSolverSDEScheduler``        -- DPM-Solver++ SDE (k-diffusion's ``sample_dpmpp_sde``); the reference keeps one scheduler object per
+                                        view because each owns a torchsde Brownian tree (mvedit_3d_pipeline.py:1176-1177,1456-1459);
+                                        here the Brownian increments are built from the explicit noise tensors, one object for all views
+  * ``DDIMScheduler``
 
 Interface: what the loop body calls on ``self.scheduler`` (mvedit_3d_pipeline.py:1101-1109,1209-1213,1225,1461,1466,1478):
 ``betas``, ``order``, ``set_timesteps``, ``timesteps``, ``init_noise_sigma``, ``scale_model_input(sample, t)``,
@@ -236,4 +239,81 @@ class DPMSolverMultistepScheduler(_SigmaSchedule):
             out = (s_t / s_s) * sample.float() + c * x0 + (0.5 * c) * d1
         if self.lower_order_nums < self.solver_order:
             self.lower_order_nums += 1
+        return out.to(sample.dtype)
+
+
+class DPMSolverSDEScheduler(_SigmaSchedule):
+    """DPM-Solver++ SDE, the stochastic second-order sampler of Karras et al. / k-diffusion's ``sample_dpmpp_sde`` as diffusers 0.27.2
+    packages it (``DPMSolverSDEScheduler``: epsilon prediction, midpoint ratio 1/2, eta = s_noise = 1).  The reference keeps ONE
+    scheduler object per view because each owns a seeded torchsde Brownian tree (mvedit_3d_pipeline.py:1176-1177,1456-1459); here the
+    Brownian increments are built from the explicit per-call ``noise`` tensor, so one object steps all views and ``prune`` drops the
+    state of pruned views.
+
+    Every sampler step is two model evaluations, so ``timesteps`` has 2n - 1 entries: t_0, m_0, t_1, m_1, ..., t_{n-1} with m_k the
+    training timestep of the geometric-mean sigma sqrt(sigma_k sigma_{k+1}) (the midpoint in t = -log sigma); ``order`` = 2 as in
+    diffusers (the pipeline's denoising-strength cut keeps that alignment, mvedit_3d_pipeline.py:1109).  With x0 = x - sigma eps:
+        stage 1 (at t_k):  ancestral split of sigma_k -> sigma_mid into (down, up);  x_mid = (down / sigma_k) x + (1 - down / sigma_k) x0 + up * n1
+        stage 2 (at m_k):  x0' from the model at x_mid;  split of sigma_k -> sigma_{k+1};  x_next = (down / sigma_k) x + (1 - down / sigma_k) x0' + up * n
+    where n is the normalised Brownian increment over [sigma_{k+1}, sigma_k], which CONTAINS stage 1's interval:
+    n = (sqrt(a) n1 + sqrt(b) n2) / sqrt(a + b), a = sigma_k - sigma_mid, b = sigma_mid - sigma_{k+1} (the tree's time is sigma itself).
+    The last step (sigma_next = 0) is one Euler step to x0."""
+    order = 2
+
+    def set_timesteps(self, num_inference_steps, device='cpu'):
+        ts, sigmas = self._schedule(num_inference_steps, round_karras_t=False)
+        self._sig = np.concatenate([sigmas, [0.0]])
+        mid = np.sqrt(self._sig[:-2] * self._sig[1:-1])                               # n - 1 midpoints (none for the final Euler step)
+        self._mid = mid
+        mts = self._sigma_to_t(mid)
+        full = np.empty(2 * len(ts) - 1)
+        full[0::2], full[1::2] = ts, mts
+        per_index = np.empty(2 * len(ts) - 1)
+        per_index[0::2], per_index[1::2] = sigmas, mid
+        self.timesteps = torch.tensor(full, dtype=torch.float32, device=device)
+        self.sigmas = torch.tensor(np.concatenate([per_index, [0.0]]), dtype=torch.float32, device=device)   # sigma the model sees at index i
+        sm = float(sigmas.max())
+        self.init_noise_sigma = sm if self.timestep_spacing in ('linspace', 'trailing') else (sm * sm + 1) ** 0.5
+        self._sample = self._n1 = None
+        self._cursor = 0
+
+    def scale_model_input(self, sample, t):
+        return sample / ((self.sigmas[self.index_of(t)] ** 2 + 1) ** 0.5)
+
+    def add_noise(self, original_samples, noise, timesteps):
+        idx = [self.index_of(t) for t in timesteps.reshape(-1)]
+        sigma = self.sigmas[idx].to(original_samples.device)
+        return original_samples + noise * sigma.view(-1, *([1] * (original_samples.dim() - 1)))
+
+    def prune(self, keep_ids):
+        if self._sample is not None:
+            self._sample, self._n1 = self._sample[keep_ids], self._n1[keep_ids]
+
+    @staticmethod
+    def _split(sigma_from, sigma_to):
+        """Ancestral split (eta = 1): the step lands on sigma_down and sigma_up of fresh noise restores the marginal at sigma_to."""
+        up = min(sigma_to, (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5)
+        return (sigma_to ** 2 - up ** 2) ** 0.5, up
+
+    def step(self, model_output, t, sample, noise):
+        i = self.index_of(t)
+        self._cursor = i + 1
+        k, second = i // 2, i % 2 == 1
+        s_k, s_next = float(self._sig[k]), float(self._sig[k + 1])
+        if s_next == 0.0:                                      # final step: Euler to x0
+            return (sample.float() - s_k * model_output.float()).to(sample.dtype)
+        s_mid = float(self._mid[k])
+        if not second:
+            x0 = sample.float() - s_k * model_output.float()
+            down, up = self._split(s_k, s_mid)
+            self._sample, self._n1 = sample.float(), noise.float()
+            out = (down / s_k) * self._sample + (1 - down / s_k) * x0 + up * self._n1
+        else:
+            if self._sample is None:
+                raise RuntimeError('DPMSolverSDEScheduler: second-stage step without its first stage (timesteps must be walked in order)')
+            x0 = sample.float() - s_mid * model_output.float()         # the model saw x_mid at sigma_mid
+            down, up = self._split(s_k, s_next)
+            a, b = s_k - s_mid, s_mid - s_next
+            n = (a ** 0.5 * self._n1 + b ** 0.5 * noise.float()) / (a + b) ** 0.5
+            out = (down / s_k) * self._sample + (1 - down / s_k) * x0 + up * n
+            self._sample = self._n1 = None
         return out.to(sample.dtype)

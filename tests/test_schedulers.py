@@ -150,3 +150,91 @@ def test_prune_keeps_history_aligned():
             d.prune(keep); part = part[keep]
         part = d.step(eps[i] if i < 2 else eps[i][keep], d.timesteps[i], part)
     np.testing.assert_allclose(part.numpy(), full[keep].numpy(), rtol=1e-6, atol=1e-6)
+
+
+def _sde(n=16, **kw):
+    from mvedit_b200.schedulers import DPMSolverSDEScheduler
+    s = DPMSolverSDEScheduler(**kw)
+    s.set_timesteps(n)
+    return s
+
+
+def test_dpm_sde_schedule_layout():
+    s = _sde(12)
+    assert len(s.timesteps) == 23 and s.order == 2 and len(s.sigmas) == 24 and float(s.sigmas[-1]) == 0
+    sig = s.sigmas[:-1].numpy()
+    assert (np.diff(sig) < 0).all()                                         # t_0 > m_0 > t_1 > ... in sigma
+    np.testing.assert_allclose(sig[1::2], np.sqrt(sig[0:-1:2] * sig[2::2]), rtol=1e-5)      # midpoints in log sigma
+    assert (np.diff(s.timesteps.numpy()) < 0).all()
+    assert abs(s.init_noise_sigma - float(s.sigmas[0])) < 1e-6
+
+
+def _dpmpp_sde_direct(sig, denoiser, x, noises):
+    """k-diffusion's ``sample_dpmpp_sde`` loop (r = 1/2, eta = s_noise = 1) written out directly; the Brownian path lives on the sigma
+    axis: noises[2k] drives [sigma_mid, sigma_k], noises[2k+1] drives [sigma_{k+1}, sigma_mid]."""
+    split = lambda s_from, s_to: ((s_to ** 2 - min(s_to, (s_to ** 2 * (s_from ** 2 - s_to ** 2) / s_from ** 2) ** 0.5) ** 2) ** 0.5,
+                                  min(s_to, (s_to ** 2 * (s_from ** 2 - s_to ** 2) / s_from ** 2) ** 0.5))
+    for k in range(len(sig) - 1):
+        s, sn = sig[k], sig[k + 1]
+        den = denoiser(x, s)
+        if sn == 0:
+            x = den
+            continue
+        sm = (s * sn) ** 0.5
+        n1, n2 = noises[2 * k], noises[2 * k + 1]
+        down, up = split(s, sm)
+        x2 = (down / s) * x + (1 - down / s) * den + up * n1
+        den2 = denoiser(x2, sm)
+        down, up = split(s, sn)
+        w = ((s - sm) ** 0.5 * n1 + (sm - sn) ** 0.5 * n2) / (s - sn) ** 0.5            # W(sigma_k) - W(sigma_next), normalised
+        x = (down / s) * x + (1 - down / s) * den2 + up * w
+    return x
+
+
+def test_dpm_sde_equals_the_direct_loop_and_converges_on_a_gaussian():
+    """Data ~ N(0, c^2): exact denoiser x c^2 / (c^2 + sigma^2).  (i) The two-calls-per-step scheduler reproduces the directly written
+    k-diffusion loop given the same unit normals (which checks that stage 2's Brownian increment contains stage 1's); (ii) the final
+    variance approaches c^2 as the step count grows; (iii) breaking the correlation between the stages makes it worse."""
+    c = 0.6
+    den = lambda x, s: x * (c * c / (c * c + s * s))
+    errs = {}
+    for n in (16, 32):
+        s = _sde(n)
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(100000, generator=g).double() * (c * c + s.init_noise_sigma ** 2) ** 0.5
+        noises = [torch.randn(x.shape, generator=g).double() for _ in range(len(s.timesteps))]
+        ref = _dpmpp_sde_direct([float(v) for v in s._sig], den, x.clone(), noises)
+        y = x.clone()
+        for i, t in enumerate(s.timesteps):
+            sigma = float(s.sigmas[i])
+            y = s.step((y - den(y, sigma)) / sigma, t, y, noises[i])
+        assert float((y - ref).abs().max()) < 1e-4
+        errs[n] = abs(float(y.var()) / (c * c) - 1)
+        if n == 32:                                                # (iii) independent stage-2 noise: a different, worse sampler
+            s2 = _sde(n)
+            z = x.clone()
+            for i, t in enumerate(s2.timesteps):
+                sigma = float(s2.sigmas[i])
+                if i % 2 == 1 and s2._n1 is not None:
+                    s2._n1 = torch.randn(x.shape, generator=g)
+                z = s2.step((z - den(z, sigma)) / sigma, t, z, noises[i])
+            assert abs(float(z.var()) / (c * c) - 1) > 1.5 * errs[32]
+    assert errs[32] < 0.6 * errs[16] and errs[32] < 0.1, errs
+
+
+def test_dpm_sde_point_mass_and_pruning():
+    s = _sde(8)
+    x0 = torch.tensor([[0.7], [-1.3], [0.2]])
+    x = torch.tensor([[0.3], [-0.5], [1.1]]) * s.init_noise_sigma
+    keep = torch.tensor([0, 2])
+    g = torch.Generator().manual_seed(3)
+    for i, t in enumerate(s.timesteps):
+        if i == 5:                                   # prune between a first and a second stage: the stored state follows the views
+            x, x0 = x[keep], x0[keep]
+            s.prune(keep)
+        eps = (x - x0) / float(s.sigmas[i])
+        x = s.step(eps, t, x, torch.randn(x.shape, generator=g) * 0.0)
+    assert x.shape == (2, 1) and float((x - x0).abs().max()) < 1e-5
+    with pytest.raises(RuntimeError):
+        s2 = _sde(4)
+        s2.step(torch.zeros(1), s2.timesteps[1], torch.zeros(1), torch.zeros(1))
