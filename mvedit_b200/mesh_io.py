@@ -1,0 +1,133 @@
+"""On-disk formats of the mesh stage's result: ``Mesh.write(path)`` for ``.obj`` (+ ``.mtl`` + albedo PNG), ``.ply``
+(geometry only) and ``.glb`` (geometry + UVs + normals + embedded albedo PNG), what the runner hands back to the web UI
+(``lib/models/decoders/mesh_renderer/mesh_utils.py:461-692``).  Host-side I/O, no GPU work: tensors are copied to the CPU once.
+
+The reference goes through trimesh (``.ply``), pygltflib (``.glb``) and cv2 (PNG); none of the first two is installed here, so the
+containers are written by hand: binary little-endian PLY, and glTF 2.0 binary (12-byte header, JSON chunk, BIN chunk, 4-byte aligned)
+with the same accessor layout the reference builds (indices, POSITION, TEXCOORD_0, NORMAL, one embedded ``image/png``; linear /
+mip-mapped sampler, REPEAT wrap, metallic 0 / roughness 1, double sided).  Like the reference, ``.obj`` flips v to ``1 - v``.
+"""
+import io
+import json
+import os
+import struct
+
+import numpy as np
+import torch
+
+
+def _np(t, dtype=None):
+    a = t.detach().cpu().numpy()
+    return a if dtype is None else a.astype(dtype)
+
+
+def _png_bytes(albedo_hwc_float):
+    from PIL import Image
+    img = (np.clip(albedo_hwc_float[..., :3], 0, 1) * 255).astype(np.uint8)
+    buf = io.BytesIO()
+    Image.fromarray(img, 'RGB').save(buf, format='PNG')
+    return buf.getvalue()
+
+
+def align_to_vt(mesh):
+    """One vertex per UV vertex (``Mesh.align_v_to_vt`` / ``align_vn_to_vt``, mesh_utils.py:416-438): glTF has a single index buffer, so
+    positions / normals are re-indexed by the texture topology (a position shared by several UV vertices is duplicated)."""
+    ft, f = mesh.ft.reshape(-1).long(), mesh.f.reshape(-1).long()
+    vmap = torch.zeros(mesh.vt.shape[0], dtype=torch.long, device=mesh.v.device)
+    vmap[ft] = f
+    nmap = torch.zeros_like(vmap)
+    nmap[ft] = mesh.fn.reshape(-1).long()
+    return mesh.v[vmap], mesh.vn[nmap], mesh.vt, mesh.ft
+
+
+def write_obj(mesh, path):
+    mtl_path, albedo_path = path.replace('.obj', '.mtl'), path.replace('.obj', '_albedo.png')
+    v, f = _np(mesh.v), _np(mesh.f)
+    vt, vn = (None if mesh.vt is None else _np(mesh.vt)), (None if mesh.vn is None else _np(mesh.vn))
+    ft, fn = (None if mesh.ft is None else _np(mesh.ft)), (None if mesh.fn is None else _np(mesh.fn))
+    textured = (not mesh.textureless) and mesh.albedo is not None
+    lines = ['mtllib %s' % os.path.basename(mtl_path)]
+    lines += ['v %.6f %.6f %.6f' % tuple(p) for p in v]
+    if vt is not None:
+        lines += ['vt %.4f %.4f' % (p[0], 1 - p[1]) for p in vt]
+    if vn is not None:
+        lines += ['vn %.4f %.4f %.4f' % tuple(p) for p in vn]
+    lines.append('usemtl defaultMat')
+    corner = lambda i, k: '%d/%s/%s' % (f[i, k] + 1, '' if ft is None else ft[i, k] + 1, '' if fn is None else fn[i, k] + 1)
+    lines += ['f %s %s %s' % (corner(i, 0), corner(i, 1), corner(i, 2)) for i in range(len(f))]
+    with open(path, 'w') as fp:
+        fp.write('\n'.join(lines) + '\n')
+    with open(mtl_path, 'w') as fp:
+        fp.write('newmtl defaultMat\nKa 1 1 1\nKd 1 1 1\nKs 0 0 0\nTr 1\nillum 1\nNs 0\n' + ('map_Kd %s\n' % os.path.basename(albedo_path) if textured else ''))
+    if textured:
+        with open(albedo_path, 'wb') as fp:
+            fp.write(_png_bytes(_np(mesh.albedo)))
+
+
+def write_ply(mesh, path):
+    v, f = _np(mesh.v, np.float32), _np(mesh.f, np.int32)
+    header = ('ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n'
+              'element face %d\nproperty list uchar int vertex_indices\nend_header\n' % (len(v), len(f)))
+    rec = np.empty(len(f), dtype=[('n', 'u1'), ('i', '<i4', 3)])
+    rec['n'], rec['i'] = 3, f
+    with open(path, 'wb') as fp:
+        fp.write(header.encode('ascii'))
+        fp.write(v.astype('<f4').tobytes())
+        fp.write(rec.tobytes())
+
+
+def write_glb(mesh, path):
+    assert mesh.vn is not None, 'write_glb needs vertex normals (auto_normal)'
+    if mesh.vt is None:
+        v, vn, vt, f = mesh.v, mesh.vn, mesh.v.new_zeros((mesh.v.size(0), 2)), mesh.f
+    else:
+        v, vn, vt, f = align_to_vt(mesh)
+    blobs = [_np(f, np.uint32).reshape(-1).tobytes(), _np(v, np.float32).tobytes(), _np(vt, np.float32).tobytes(), _np(vn, np.float32).tobytes(),
+             _png_bytes(_np(mesh.albedo) if mesh.albedo is not None else np.full((1024, 1024, 3), 0.5, np.float32))]
+    views, off = [], 0
+    for k, b in enumerate(blobs):
+        view = dict(buffer=0, byteOffset=off, byteLength=len(b))
+        if k == 0:
+            view['target'] = 34963                      # ELEMENT_ARRAY_BUFFER
+        elif k < 4:
+            view['target'] = 34962                      # ARRAY_BUFFER
+            view['byteStride'] = (12, 8, 12)[k - 1]
+        views.append(view)
+        off += len(b) + (-len(b)) % 4
+    vmin, vmax = _np(v, np.float32).min(0).tolist(), _np(v, np.float32).max(0).tolist()
+    n_v, n_i = int(v.shape[0]), int(f.numel())
+    gltf = dict(
+        asset=dict(version='2.0', generator='mvedit_b200'), scene=0, scenes=[dict(nodes=[0])], nodes=[dict(mesh=0)],
+        meshes=[dict(primitives=[dict(attributes=dict(POSITION=1, TEXCOORD_0=2, NORMAL=3), indices=0, material=0)])],
+        materials=[dict(pbrMetallicRoughness=dict(baseColorTexture=dict(index=0, texCoord=0), metallicFactor=0.0, roughnessFactor=1.0),
+                        alphaCutoff=0, doubleSided=True)],
+        textures=[dict(sampler=0, source=0)], samplers=[dict(magFilter=9729, minFilter=9987, wrapS=10497, wrapT=10497)],
+        images=[dict(bufferView=4, mimeType='image/png')], buffers=[dict(byteLength=off)], bufferViews=views,
+        accessors=[dict(bufferView=0, componentType=5125, count=n_i, type='SCALAR', max=[int(_np(f).max())], min=[int(_np(f).min())]),
+                   dict(bufferView=1, componentType=5126, count=n_v, type='VEC3', max=vmax, min=vmin),
+                   dict(bufferView=2, componentType=5126, count=n_v, type='VEC2', max=_np(vt, np.float32).max(0).tolist(), min=_np(vt, np.float32).min(0).tolist()),
+                   dict(bufferView=3, componentType=5126, count=n_v, type='VEC3', max=_np(vn, np.float32).max(0).tolist(), min=_np(vn, np.float32).min(0).tolist())])
+    js = json.dumps(gltf, separators=(',', ':')).encode('utf-8')
+    js += b' ' * ((-len(js)) % 4)
+    bin_chunk = b''.join(b + b'\x00' * ((-len(b)) % 4) for b in blobs)
+    total = 12 + 8 + len(js) + 8 + len(bin_chunk)
+    with open(path, 'wb') as fp:
+        fp.write(struct.pack('<4sII', b'glTF', 2, total))
+        fp.write(struct.pack('<I4s', len(js), b'JSON') + js)
+        fp.write(struct.pack('<I4s', len(bin_chunk), b'BIN\x00') + bin_chunk)
+
+
+def write(mesh, path, flip_yz=False):
+    """``Mesh.write`` (mesh_utils.py:461-477): ``flip_yz`` swaps to a y-up frame (y <- z, z <- -y)."""
+    if flip_yz:
+        mesh = mesh.copy()
+        flip = lambda t: torch.stack([t[..., 0], t[..., 2], -t[..., 1]], dim=-1)
+        mesh.v, mesh.vn = flip(mesh.v), (None if mesh.vn is None else flip(mesh.vn))
+    if path.endswith('.ply'):
+        write_ply(mesh, path)
+    elif path.endswith('.obj'):
+        write_obj(mesh, path)
+    elif path.endswith('.glb') or path.endswith('.gltf'):
+        write_glb(mesh, path)
+    else:
+        raise NotImplementedError('format %s not supported!' % path)

@@ -46,6 +46,23 @@ class Mesh:
             setattr(self, k, t.detach() if t is not None else None)
         return self
 
+    def to(self, device):
+        self.device = device
+        for k in ('v', 'f', 'vn', 'fn', 'vt', 'ft', 'albedo', 'vc', 'face_normals'):
+            t = getattr(self, k)
+            if t is not None:
+                setattr(self, k, t.to(device))
+        return self
+
+    def copy(self):
+        return Mesh(v=self.v, f=self.f, vn=self.vn, fn=self.fn, vt=self.vt, ft=self.ft, vc=self.vc, albedo=self.albedo, device=self.device,
+                    textureless=self.textureless)
+
+    def write(self, path, flip_yz=False):
+        """``.obj`` (+ .mtl + albedo PNG) / ``.ply`` / ``.glb`` (``mesh_utils.py:461-692``; containers written by ``mesh_io``)."""
+        from . import mesh_io
+        mesh_io.write(self, path, flip_yz=flip_yz)
+
     def auto_normal(self, seamless=False):
         """Area-unweighted vertex normals: unit face normals splatted to the vertices (``mesh_utils.py:359-382``)."""
         if seamless:

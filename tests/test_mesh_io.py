@@ -1,0 +1,79 @@
+"""Mesh.write: .obj / .ply / .glb containers parsed back on the CPU."""
+import io
+import json
+import struct
+
+import numpy as np
+import torch
+
+from tests import synth_mesh
+from mvedit_b200.mesh_renderer import Mesh
+
+
+def _mesh(textured=True):
+    v, f = synth_mesh.icosphere(1)
+    m = Mesh(v=torch.from_numpy(v).float() * 0.5, f=torch.from_numpy(f).int())
+    m.auto_normal()
+    if textured:
+        m.auto_uv()
+        m.albedo = torch.rand(16, 16, 4, generator=torch.Generator().manual_seed(0))
+    return m
+
+
+def test_obj_round_trip(tmp_path):
+    m = _mesh()
+    p = str(tmp_path / 'a.obj')
+    m.write(p)
+    lines = open(p).read().splitlines()
+    vs = np.array([[float(x) for x in l.split()[1:]] for l in lines if l.startswith('v ')])
+    vts = np.array([[float(x) for x in l.split()[1:]] for l in lines if l.startswith('vt ')])
+    fs = [l.split()[1:] for l in lines if l.startswith('f ')]
+    np.testing.assert_allclose(vs, m.v.numpy(), atol=1e-6)
+    np.testing.assert_allclose(vts, np.stack([m.vt[:, 0].numpy(), 1 - m.vt[:, 1].numpy()], -1), atol=1e-4)      # v flipped, as the reference
+    assert len(fs) == m.f.shape[0] and fs[0][0] == '%d/%d/%d' % (m.f[0, 0] + 1, m.ft[0, 0] + 1, m.fn[0, 0] + 1)
+    assert 'map_Kd a_albedo.png' in open(str(tmp_path / 'a.mtl')).read()
+    from PIL import Image
+    img = np.asarray(Image.open(str(tmp_path / 'a_albedo.png')))
+    assert img.shape == (16, 16, 3) and np.abs(img.astype(np.float32) / 255 - m.albedo[..., :3].numpy()).max() < 1 / 255 + 1e-6
+    # untextured: no vt, no texture reference
+    m2 = _mesh(False)
+    m2.write(str(tmp_path / 'b.obj'))
+    assert 'map_Kd' not in open(str(tmp_path / 'b.mtl')).read() and '//' in open(str(tmp_path / 'b.obj')).read()
+
+
+def test_ply_and_yz_flip(tmp_path):
+    m = _mesh(False)
+    p = str(tmp_path / 'a.ply')
+    m.write(p, flip_yz=True)
+    raw = open(p, 'rb').read()
+    head, body = raw.split(b'end_header\n', 1)
+    assert b'element vertex %d' % m.v.shape[0] in head and b'element face %d' % m.f.shape[0] in head
+    v = np.frombuffer(body[:m.v.shape[0] * 12], '<f4').reshape(-1, 3)
+    np.testing.assert_allclose(v, np.stack([m.v[:, 0], m.v[:, 2], -m.v[:, 1]], -1), atol=1e-7)
+    faces = np.frombuffer(body[m.v.shape[0] * 12:], dtype=[('n', 'u1'), ('i', '<i4', 3)])
+    assert (faces['n'] == 3).all() and (faces['i'] == m.f.numpy()).all()
+    assert torch.equal(m.v, _mesh(False).v)                   # the flip works on a copy
+
+
+def test_glb_container(tmp_path):
+    m = _mesh()
+    p = str(tmp_path / 'a.glb')
+    m.write(p)
+    raw = open(p, 'rb').read()
+    magic, version, total = struct.unpack('<4sII', raw[:12])
+    assert magic == b'glTF' and version == 2 and total == len(raw)
+    jlen, jtype = struct.unpack('<I4s', raw[12:20])
+    gltf = json.loads(raw[20:20 + jlen])
+    blen, btype = struct.unpack('<I4s', raw[20 + jlen:28 + jlen])
+    assert jtype == b'JSON' and btype == b'BIN\x00' and jlen % 4 == 0 and blen % 4 == 0 and 28 + jlen + blen == len(raw)
+    bin_ = raw[28 + jlen:]
+    acc, views = gltf['accessors'], gltf['bufferViews']
+    n_uv = m.vt.shape[0]
+    assert acc[0]['count'] == m.f.numel() and acc[1]['count'] == acc[2]['count'] == acc[3]['count'] == n_uv
+    idx = np.frombuffer(bin_[views[0]['byteOffset']:views[0]['byteOffset'] + views[0]['byteLength']], '<u4').reshape(-1, 3)
+    pos = np.frombuffer(bin_[views[1]['byteOffset']:views[1]['byteOffset'] + views[1]['byteLength']], '<f4').reshape(-1, 3)
+    np.testing.assert_allclose(pos[idx], m.v.numpy()[m.f.numpy()], atol=1e-7)          # re-indexed by the UV topology, same triangles
+    from PIL import Image
+    png = bin_[views[4]['byteOffset']:views[4]['byteOffset'] + views[4]['byteLength']]
+    assert np.asarray(Image.open(io.BytesIO(png))).shape == (16, 16, 3)
+    assert gltf['images'][0]['mimeType'] == 'image/png' and gltf['materials'][0]['doubleSided'] is True
