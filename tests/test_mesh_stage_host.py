@@ -275,3 +275,64 @@ def test_render_mesh_views_matches_oracle_composition():
     dep_o = normalize_depth(r_o['depth'].squeeze(0), rgba[..., 3:]).unsqueeze(1).repeat(1, 3, 1, 1)
     assert (images.float() - img_o).abs().max() < 1e-2 and (depths.float() - dep_o).abs().max() < 1e-2     # bf16 storage
     assert depths.float().max() > 0.9 and (depths.float()[:, 0][rgba[..., 3] == 0] == 0).all()
+
+
+class _FakePatchLoss:
+    """Stands in for ``LPIPSLoss`` (CUDA-only) with the same two entry points: ``loss_and_grad`` on NHWC patches (what the product
+    calls, gradient returned instead of recorded) and the reference-style ``__call__`` on NCHW with autograd (what the oracle calls).
+    The metric is a weighted MSE, so both sides must agree exactly."""
+    loss_weight = 1.2
+
+    def loss_and_grad(self, pred, target, weight=None, scale=1.0):
+        P = pred.shape[0]
+        w = torch.ones(P) if weight is None else weight
+        per = (pred - target).square().flatten(1).mean(1)
+        loss = (per * w).mean() * scale * self.loss_weight
+        g = 2 * (pred - target) / pred[0].numel() * (w * scale * self.loss_weight / P)[:, None, None, None]
+        return loss, g, per
+
+    def __call__(self, pred, target, weight=None, avg_factor=None):
+        per = (pred - target).square().flatten(1).mean(1)
+        return ((per if weight is None else per * weight).mean() * self.loss_weight)
+
+
+def test_mesh_optim_patch_term_plumbing_matches_oracle():
+    n, size, steps, ps = 2, 32, 2, 16
+    poses, intr = _cameras(n, size, seed=2)
+    lights = torch.nn.functional.normalize(torch.randn(n, 3, generator=torch.Generator().manual_seed(4)), dim=-1)
+    cam_weights = torch.tensor([1.0, 2.0])
+    yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing='ij')
+    disc = (((xx - 15.5) ** 2 + (yy - 15.5) ** 2).float().sqrt() < 9).float()
+    tgt_masks = disc[None, None, :, :, None].expand(1, n, -1, -1, -1).contiguous()
+    tgt_images = (torch.rand(1, n, size, size, 3, generator=torch.Generator().manual_seed(5)) * 0.5 + 0.25) * tgt_masks + (1 - tgt_masks)
+    g = torch.Generator().manual_seed(6)
+    noise = dict(camera_perm=torch.tensor([1, 0]), jitter=torch.rand(steps, 2, 2, generator=g),
+                 patch_perm=torch.stack([torch.randperm(n * (size // ps) ** 2, generator=g) for _ in range(steps)]))
+    grid = make_tet_grid(10)
+    res = {}
+    for name in ('product', 'oracle'):
+        field = ToyField()
+        nerf = SimpleNamespace(decoder=field, pixel_loss=L1LossMod(loss_weight=1.2), patch_loss=_FakePatchLoss())
+        tet_verts, tet_indices, tet_sdf = mopt.init_tet(nerf, None, density_thresh=5.0, tets=grid)
+        deform = torch.zeros_like(tet_verts).requires_grad_(True)
+        tet_sdf.requires_grad_(True)
+        opt = torch.optim.Adam([{'params': list(field.parameters())}, {'params': [tet_sdf, deform], 'lr': 1e-3}], lr=0.01)
+        if name == 'product':
+            dm = DMTet('cpu')
+            with torch.enable_grad():
+                mv, mf = dm(tet_verts + deform, tet_sdf, tet_indices)
+                mesh = Mesh(v=mv, f=mf.int())
+                mesh.auto_normal()
+            pipe = SimpleNamespace(nerf=nerf, mesh_renderer=MeshRenderer(near=0.01, far=100), normal_bg=[0.5, 0.5, 1.0], tonemapping=None)
+            mopt.mesh_optim(pipe, tgt_images, tgt_masks, None, opt, 0.01, 0.8, steps, 2, 3, 24, 0.7, 0.0, 0.02, 0.1, 5.0, None,
+                            tet_verts, deform, tet_sdf, tet_indices, dm, mesh, size, intr, size, poses, cam_weights, lights, ps,
+                            False, 0.2, 1.0, noise=noise)
+        else:
+            dm = mo.DMTetOracle()
+            mv, mf = dm(tet_verts + deform, tet_sdf, tet_indices)
+            mo.mesh_optim(field, tgt_images, tgt_masks, opt, 0.01, 0.8, steps, 2, 3, 0.7, 0.02, 0.1, 5.0, None, tet_verts, deform, tet_sdf,
+                          tet_indices, dm, mo.make_mesh(mv, mf.int()), size, intr, size, poses, cam_weights, lights, ps, 0.2, noise,
+                          patch_loss=nerf.patch_loss)
+        res[name] = (tet_sdf.detach().clone(), deform.detach().clone(), field.w.detach().clone())
+    for a, b in zip(res['product'], res['oracle']):
+        assert (a - b).abs().max() < 2e-5
