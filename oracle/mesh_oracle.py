@@ -127,7 +127,8 @@ def dr_rasterize(pos, tri, resolution, grad_db=True):
     return rast, torch.from_numpy(db_np).to(pos.dtype)
 
 
-def mesh_renderer_forward(mesh, poses, intrinsics, h, w, shading_fun=None, normal_bg=(0.5, 0.5, 1.0), aa=True, near=0.01, far=100.0, ssaa=1):
+def mesh_renderer_forward(mesh, poses, intrinsics, h, w, shading_fun=None, normal_bg=(0.5, 0.5, 1.0), aa=True, near=0.01, far=100.0, ssaa=1,
+                          dilate_edges=0):
     """base_mesh_renderer.py:207-299,383-395 for num_scenes == 1.  poses [1,n,3|4,4], intrinsics [1,n,4]."""
     num_scenes, num_images = poses.shape[:2]
     if ssaa > 1:
@@ -168,6 +169,9 @@ def mesh_renderer_forward(mesh, poses, intrinsics, h, w, shading_fun=None, norma
         rgb_reshade = shading_fun(world_pos=xyz[fg], albedo=albedo[fg], world_normal=normal[fg], fg_mask=fg)
         albedo = torch.zeros_like(albedo).masked_scatter(fg.unsqueeze(-1).expand_as(albedo), rgb_reshade.to(albedo.dtype))
     rgba = torch.cat([albedo, alpha], dim=-1)
+    if dilate_edges > 0:
+        rgba = rgba.reshape(num_scenes * num_images, h, w, 4).permute(0, 3, 1, 2)
+        rgba = edge_dilation(rgba, rgba[:, 3:], dilate_edges).permute(0, 2, 3, 1).reshape(num_scenes, num_images, h, w, 4)
     if aa:
         rgba, depth, rot_normal = ro.antialias(torch.cat([rgba, depth.unsqueeze(-1), rot_normal], dim=-1).squeeze(0), rast, v_clip,
                                                np.asarray(tri)).unsqueeze(0).split([4, 1, 3], dim=-1)

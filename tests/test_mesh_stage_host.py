@@ -336,3 +336,27 @@ def test_mesh_optim_patch_term_plumbing_matches_oracle():
         res[name] = (tet_sdf.detach().clone(), deform.detach().clone(), field.w.detach().clone())
     for a, b in zip(res['product'], res['oracle']):
         assert (a - b).abs().max() < 2e-5
+
+
+def test_ssaa_and_edge_dilation_branches_match_oracle():
+    v, f = synth_mesh.icosphere(1)
+    poses, intr = _cameras(2, 24)
+    vt = torch.from_numpy(v).float() * 0.5
+    vc = torch.rand(1, vt.shape[0], 4, generator=torch.Generator().manual_seed(3)) * 0.5 + 0.5
+    mesh = Mesh(v=vt, f=torch.from_numpy(f).int(), vc=vc)
+    mesh.auto_normal()
+    om = mo.make_mesh(vt, torch.from_numpy(f).int())
+    om.vc = vc
+    with torch.no_grad():
+        r = MeshRenderer(near=0.01, far=100, ssaa=2)([mesh], poses[None], intr[None], 24, 24)
+        r_o = mo.mesh_renderer_forward(om, poses[None], intr[None], 24, 24, ssaa=2)
+        d = MeshRenderer(near=0.01, far=100)([mesh], poses[None], intr[None], 24, 24, dilate_edges=2, aa=False)
+        d_o = mo.mesh_renderer_forward(om, poses[None], intr[None], 24, 24, dilate_edges=2, aa=False)
+        plain = MeshRenderer(near=0.01, far=100)([mesh], poses[None], intr[None], 24, 24, aa=False)
+    for k in ('rgba', 'depth', 'normal'):
+        assert r[k].shape[2:4] == (24, 24)
+        torch.testing.assert_close(r[k], r_o[k], rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(d[k], d_o[k], rtol=1e-4, atol=2e-5)
+    assert ((r['rgba'][..., 3] > 0.05) & (r['rgba'][..., 3] < 0.95)).sum() > 8        # area-averaged 2x2 supersamples: soft outline
+    grown = (d['rgba'][..., 3] > 0).sum() - (plain['rgba'][..., 3] > 0).sum()
+    assert grown > 20                                                               # the coverage grew by the dilation ring
