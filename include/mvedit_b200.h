@@ -381,7 +381,9 @@ int mve_gs_blend_backward(const int32_t* ranges, const int32_t* point_list, cons
  * ------------------------------------------------------------------------- */
 
 /* dr.rasterize: rast [B,H,W,4] = (u, v, z/w, triangle id + 1; 0 = empty), u / v = perspective-correct barycentrics of vertex 0 / 1;
- * rast_db [B,H,W,4] = (du/dX, du/dY, dv/dX, dv/dY) per pixel, or NULL to skip it.  Nearest z/w in [-1, 1] wins, ties go to the
+ * rast_db [B,H,W,4] = (du/dX, du/dY, dv/dX, dv/dY) per pixel, or NULL to skip it.  A pixel is covered when its centre is inside or on
+ * the triangle (homogeneous edge functions, both windings) AND inside the triangle's fp32 screen bounding box padded by one pixel (this
+ * pins down zero-area triangles, whose edge functions are rounding noise).  Nearest z/w in [-1, 1] wins, ties go to the
  * lower triangle id (deterministic).  Triangles with a vertex at w <= 0 are dropped (no near-plane clipping).
  * Scratch (caller-allocated, contents irrelevant): zbuf [B*H*W] u64, queue [1 + B*F] u32.  Three launches, no host sync. */
 int mve_rasterize_fwd(const float* pos, const int32_t* tri, uint32_t B, uint32_t V, uint32_t F, uint32_t H, uint32_t W,

@@ -9,7 +9,8 @@ are its call sites: argument layout, the (u, v, z/w, id + 1) output convention (
 
 Conventions restated:
   * clip-space positions ``pos [B,V,4]``; pixel (row y, col x) has its centre at NDC ``((2x+1)/W - 1, (2y+1)/H - 1)``;
-  * a pixel is covered when its centre is inside or on the triangle (both windings, no culling); nearest ``z/w`` within [-1, 1] wins,
+  * a pixel is covered when its centre is inside or on the triangle (both windings, no culling) and within the triangle's fp32 screen
+    bounding box padded by one pixel (which pins down zero-area triangles, whose edge functions are rounding noise); nearest ``z/w`` within [-1, 1] wins,
     ties go to the lower triangle index; a triangle with a vertex at ``w <= 0`` is dropped (no near-plane clipping);
   * ``rast = (u, v, z/w, id + 1)`` with (u, v) the perspective-correct barycentrics of the triangle's vertices 0 and 1;
     ``rast_db = (du/dX, du/dY, dv/dX, dv/dY)`` per pixel;
@@ -57,13 +58,18 @@ def rasterize(pos, tri, resolution, grad_db=True):
                 p0, p1, p2 = pos[b, i0], pos[b, i1], pos[b, i2]
                 if not (p0[3] > 0 and p1[3] > 0 and p2[3] > 0):
                     continue
-                # generous pixel box (the decision itself is the edge-function test)
-                sx = np.array([p[0] / p[3] for p in (p0, p1, p2)], np.float64) * 0.5 * W + 0.5 * W
-                sy = np.array([p[1] / p[3] for p in (p0, p1, p2)], np.float64) * 0.5 * H + 0.5 * H
-                if not (np.isfinite(sx).all() and np.isfinite(sy).all()):
+                # candidate pixels: the triangle's screen bounding box in fp32, one pixel of slack (part of the specification: a
+                # zero-area triangle has rounding noise for edge functions, so WHERE they are evaluated must be pinned down too)
+                hw_, hh_ = f32(0.5) * f32(W), f32(0.5) * f32(H)
+                sx = np.array([p[0] / p[3] * hw_ + hw_ for p in (p0, p1, p2)], f32)
+                sy = np.array([p[1] / p[3] * hh_ + hh_ for p in (p0, p1, p2)], f32)
+                mnx, mxx = np.fmin.reduce(sx), np.fmax.reduce(sx)          # fmin / fmax ignore NaN, like fminf / fmaxf
+                mny, mxy = np.fmin.reduce(sy), np.fmax.reduce(sy)
+                if not (mxx >= 0 and mnx <= f32(W) and mxy >= 0 and mny <= f32(H)):
                     continue
-                x0, x1 = int(max(np.floor(sx.min()) - 2, 0)), int(min(np.ceil(sx.max()) + 2, W))
-                y0, y1 = int(max(np.floor(sy.min()) - 2, 0)), int(min(np.ceil(sy.max()) + 2, H))
+                x0 = int(np.floor(np.fmax(mnx, f32(0)) - f32(0.5))); x1 = int(np.ceil(np.fmin(mxx, f32(W)) - f32(0.5)))
+                y0 = int(np.floor(np.fmax(mny, f32(0)) - f32(0.5))); y1 = int(np.ceil(np.fmin(mxy, f32(H)) - f32(0.5)))
+                x0, y0, x1, y1 = max(x0, 0), max(y0, 0), min(x1, W - 1) + 1, min(y1, H - 1) + 1      # [x0, x1) x [y0, y1)
                 if x1 <= x0 or y1 <= y0:
                     continue
                 fx, fy = np.meshgrid(xs[x0:x1], ys[y0:y1])
