@@ -42,6 +42,28 @@ class Adapter3DMixin:
     unet = None
     controlnet = None
 
+    def load_init_mesh(self, in_model, camera_poses, intrinsics, intrinsics_size, render_bs, shading_fun=None, diff_size=512):
+        """Render an input mesh from every camera at 2x supersampling (adapter3d_mixin.py:21-66) -> (mesh, images [N,s,s,3] composited on
+        ``self.bg_color``, alphas [N,s,s,1], inverse depths [N,s,s]).  ``in_model`` is a ``mesh_renderer.Mesh`` (file loading -- trimesh /
+        pygltflib in the reference's ``Mesh.load`` -- is not built)."""
+        if isinstance(in_model, str):
+            raise NotImplementedError('load_init_mesh: pass a mesh_renderer.Mesh; loading mesh files is not built')
+        in_mesh = in_model.detach().to(camera_poses.device)
+        if in_mesh.vn is None:
+            in_mesh.auto_normal()
+        renderer = copy(self.mesh_renderer)
+        renderer.ssaa = 2
+        pose_b, intr_b = camera_poses.split(render_bs, dim=0), intrinsics.split(render_bs, dim=0)
+        funs = shading_fun if isinstance(shading_fun, list) else [shading_fun] * len(pose_b)
+        images, alphas, depths = [], [], []
+        for p_b, i_b, fun in zip(pose_b, intr_b, funs):
+            out = renderer([in_mesh], p_b[None], i_b[None] * (diff_size / intrinsics_size), diff_size, diff_size, fun)
+            rgba = out['rgba'].squeeze(0)
+            images.append(rgba[..., :3] + (1 - rgba[..., 3:]) * self.bg_color)
+            alphas.append(rgba[..., 3:])
+            depths.append(out['depth'].squeeze(0))
+        return in_mesh, torch.cat(images, dim=0).clamp(min=0, max=1), torch.cat(alphas, dim=0), torch.cat(depths, dim=0)
+
     @staticmethod
     def _split_ref(lat, latent_size, pe):
         shp = lat.shape

@@ -98,3 +98,13 @@ def test_edge_dilation_matches_reference():
     np.testing.assert_array_equal(edge_dilation(img, mask).numpy(), PINS['ed_out_default'])
     np.testing.assert_array_equal(edge_dilation(img, mask, radius=2, iters=3).numpy(), PINS['ed_out_r2_i3'])
     assert edge_dilation(img, mask, radius=0) is img
+
+
+def test_camera_dense_weighting_and_texture_schedules_match_reference():
+    from mvedit_b200 import mvedit_texture_pipeline as tp
+    out = tp.camera_dense_weighting(T('cdw_intr'), 32, 32, T('cdw_alpha'), T('cdw_depth'))
+    np.testing.assert_allclose(out.numpy(), PINS['cdw_out'], rtol=1e-4, atol=1e-5)
+    out2 = tp.camera_dense_weighting(T('cdw_intr'), 64, 32, T('cdw_alpha'), T('cdw_depth'), cos_weight_pow=2.0)
+    np.testing.assert_allclose(out2.numpy(), PINS['cdw_out_pow2'], rtol=1e-4, atol=1e-5)
+    sched = np.array([[tp.default_patch_rgb_weight(p), tp.default_max_num_views(p)] for p in np.linspace(0, 1, 9)])
+    np.testing.assert_allclose(sched, PINS['tex_sched'], rtol=1e-12)
