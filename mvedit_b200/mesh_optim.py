@@ -282,12 +282,14 @@ def texture_optim(self, tgt_images,                                             
                   patch_rgb_weight,                                                   # loss weights
                   nerf_code, in_mesh,                                                 # mesh model
                   render_size, intrinsics, intrinsics_size, camera_poses, cam_weights_dense, patch_size,
-                  debug=False, perturb=True, noise=None):
+                  debug=False, perturb=True, noise=None, patch_views=None):
     """Fit the field's albedo on a FIXED mesh to the target views (``MVEditTexturePipeline.texture_optim``,
     ``lib/pipelines/mvedit_texture_pipeline.py:93-172``; the super-resolution pipeline's copy is identical,
     ``mvedit_texture_superres_pipeline.py:89-168``): render ``render_bs`` views through ``MeshRenderer`` with the unshaded field albedo at the
     surface points, composite on ``self.bg_color``, L1 x 2 with dense per-pixel camera weights [n,h,w,1] + the LPIPS patch term.
-    ``noise`` (extension, parity tests): ``camera_perm``, ``jitter`` [steps, render_bs, 2], ``patch_perm`` [steps, n_patches]."""
+    ``noise`` (extension, parity tests): ``camera_perm``, ``jitter`` [steps, render_bs, 2], ``patch_perm`` [steps, n_patches].
+    ``patch_views``: the super-resolution variant's ``num_cameras`` -- its patch term only looks at the first ``num_cameras`` views of every
+    rendered batch (``mvedit_texture_superres_pipeline.py:139-148``, "ignore regularization views")."""
     nerf, dec = self.nerf, self.nerf.decoder
     device = camera_poses.device
     noise = noise or {}
@@ -318,8 +320,9 @@ def texture_optim(self, tgt_images,                                             
                 out_rgbs = rgba[..., :3] + (1 - rgba[..., 3:].clamp(min=1e-3)) * self.bg_color
                 loss = nerf.pixel_loss(out_rgbs, target_rgbs, weight=target_w) * 2
                 if patch_rgb_weight > 0:
-                    out_p, tgt_p = _patches(out_rgbs, render_size, patch_size), _patches(target_rgbs, render_size, patch_size)
-                    w_p = _patches(target_w, render_size, patch_size)
+                    pv = slice(None, patch_views)
+                    out_p, tgt_p = _patches(out_rgbs[pv], render_size, patch_size), _patches(target_rgbs[pv], render_size, patch_size)
+                    w_p = _patches(target_w[pv], render_size, patch_size)
                     perm = noise['patch_perm'][step].to(device) if 'patch_perm' in noise else torch.randperm(out_p.size(0), device=device)
                     pick = perm[:patch_bs]
                     loss = loss + lpips_patch_loss(nerf.patch_loss, out_p[pick], tgt_p[pick], w_p[pick].amax(dim=(1, 2, 3))) * patch_rgb_weight

@@ -223,3 +223,152 @@ class MVEditTexturePipeline(MVEdit3DPipeline):
             torch.set_grad_enabled(grad_mode)
         dec.restore_state_dict()
         return out_mesh, output_state
+
+
+class MVEditTextureSuperResPipeline(MVEditTexturePipeline):
+    """The texture super-resolution pipeline (``lib/pipelines/mvedit_texture_superres_pipeline.py``; BASELINE configs[3]'s second half):
+    the views rendered from the input mesh are re-noised and denoised with the tile ControlNet at full weight on the ORIGINAL renders
+    (the condition never changes: no per-step baking, no pruning, 1-pass only), the last step's prediction plus a set of
+    regulariser views (``reg_camera_poses``: plain renders of the input, weight 0.5) are fitted by ``texture_optim``, and the baked
+    field is blended with the original texture by per-texel camera confidence (``get_cam_weights_uv``, cos^4, original weight 0.2^4).
+    Returns the mesh only, as the reference (``:493-496``)."""
+
+    def __call__(self, prompt='', negative_prompt='', in_model=None, ingp_states=None, init_images=None, cond_images=None,
+                 extra_control_images=None, nerf_code=None, camera_poses=None, reg_camera_poses=None, intrinsics=None, intrinsics_size=256,
+                 use_reference=True, cam_weights=None, reg_cam_weights=None, guidance_scale=7, num_inference_steps=26, denoising_strength=0.5,
+                 diff_size=512, patch_size=512, patch_bs=1, diff_bs=12, render_bs=8, n_inverse_steps=512, ip_adapter=None,
+                 ip_adapter_use_cond_idx=None, lr=0.01, patch_rgb_weight=default_patch_rgb_weight, optim_only=False, debug=False,
+                 out_dir=None, save_interval=None, save_all_interval=None,
+                 default_prompt='best quality, sharp focus, photorealistic, extremely detailed',
+                 default_neg_prompt='worst quality, low quality, depth of field, blurry, out of focus, low-res, illustration, painting, drawing',
+                 bake_texture_kwargs=None, prog_bar=None, prompt_embeds=None):
+        if ip_adapter is not None:
+            raise NotImplementedError('MVEditTextureSuperResPipeline: ip_adapter image prompts are not built on the B200 path')
+        assert in_model is not None
+        from .mesh_renderer import edge_dilation
+        nerf, dec, sch = self.nerf, self.nerf.decoder, self.scheduler
+        device = next(dec.parameters()).device
+        grad_mode = torch.is_grad_enabled()
+        torch.set_grad_enabled(False)
+        render_size = diff_size
+        patch_size = render_size // round(render_size / patch_size)               # make sure patch_size divides render_size (:219)
+        if dec.state_dict_bak is None:
+            dec.backup_state_dict()
+        out_mesh = None
+        try:
+            if ingp_states is not None:
+                dec.load_state_dict(ingp_states if isinstance(ingp_states, dict) else torch.load(ingp_states, map_location='cpu'), strict=False)
+            to_poses = lambda p: (p if torch.is_tensor(p) else torch.from_numpy(np.stack(p, axis=0))).to(device=device, dtype=torch.float32)
+            camera_poses = to_poses(camera_poses)
+            num_cameras = len(camera_poses)
+            reg_camera_poses = to_poses(reg_camera_poses) if reg_camera_poses is not None else camera_poses.new_zeros((0,) + tuple(camera_poses.shape[1:]))
+            num_reg = len(reg_camera_poses)
+            all_poses = torch.cat([camera_poses, reg_camera_poses], dim=0)
+            intrinsics = intrinsics.to(device=device, dtype=torch.float32)
+            if intrinsics.dim() == 1:
+                intrinsics = intrinsics[None].expand(len(all_poses), -1)
+            albedo_fun = make_nerf_albedo_shading_fun(dec, nerf_code)
+            in_mesh, images, alphas, depths = self.load_init_mesh(in_model, all_poses, intrinsics, intrinsics_size, render_bs,
+                                                                  None if ingp_states is None else albedo_fun, diff_size=diff_size)
+            if init_images is None:
+                in_images, reg_images = images[:num_cameras].permute(0, 3, 1, 2).float(), images[num_cameras:]
+            else:
+                init = self.load_init_images(init_images, ret_masks=False, diff_size=diff_size)
+                in_images, reg_images = init[:num_cameras], init[num_cameras:].permute(0, 2, 3, 1).float()
+            ctrl_images = in_images.to(torch.bfloat16)
+            ctrl_depths = normalize_depth(depths[:num_cameras], alphas[:num_cameras]).unsqueeze(1).repeat(1, 3, 1, 1).to(torch.bfloat16)
+            cam_weights = camera_poses.new_tensor(list(cam_weights if cam_weights is not None else [1.0] * num_cameras)
+                                                  + list(reg_cam_weights if reg_cam_weights is not None else [0.5] * num_reg))
+            cam_weights_dense = cam_weights[:, None, None, None] * camera_dense_weighting(intrinsics, intrinsics_size, render_size, alphas, depths)
+            prompt = prompt if isinstance(prompt, list) else [prompt] * num_cameras
+            negative_prompt = negative_prompt if isinstance(negative_prompt, list) else [negative_prompt] * num_cameras
+            cond_images, extra_control_images = self.load_cond_images(in_images, cond_images, extra_control_images)
+            if not optim_only:
+                sch.set_timesteps(num_inference_steps, device=device)
+                timesteps = sch.timesteps
+                if denoising_strength is not None:
+                    timesteps = timesteps[min(int(round(len(timesteps) * (1 - denoising_strength) / sch.order)) * sch.order,
+                                              len(timesteps) - 1):]
+                pe = self.get_prompt_embeds([join_prompts(p, default_prompt) for p in prompt],
+                                            [join_prompts(p, default_neg_prompt) for p in negative_prompt], prompt_embeds)
+                encode = lambda x: torch.cat([self.vae.encode(b * 2 - 1).latent_dist.sample() * self.vae.config.scaling_factor
+                                              for b in x.split(diff_bs, dim=0)], dim=0)
+                init_latents = encode(in_images)
+                ref_latents = None
+                if use_reference:
+                    ref_latents = init_latents if cond_images is None else encode(
+                        torch.cat([F.interpolate(c, size=(diff_size, diff_size), mode='bilinear') for c in cond_images], dim=0))
+                L = init_latents.shape[-1]
+            optimizer = FusedAdam(dec.parameters(), lr=0.01)
+            total_steps = num_inference_steps if optim_only else len(timesteps)
+            steps = [None] * (num_inference_steps + 1) if optim_only else [None] + list(timesteps)
+            latents = None
+            tgt_images = None
+            for i, t in enumerate(prog_bar(steps) if prog_bar is not None else steps):
+                progress = i / total_steps
+                if not optim_only:
+                    sqrt_ab, sqrt_1mab = sch.noise_scales(timesteps[0] if t is None else t)
+                if t is not None and not optim_only:
+                    latents_scaled = sch.scale_model_input(latents, t)
+                    if use_reference:
+                        lat_b, pe_b = [latents_scaled[:, :, -L:], latents_scaled], [pe[:num_cameras], pe[-num_cameras:]]
+                        dup = lambda x: [x, x]
+                    else:
+                        lat_b, pe_b = [torch.cat([latents_scaled] * 2, dim=0)], [pe]
+                        dup = lambda x: [torch.cat([x] * 2, dim=0)]
+                    noise_pred = self.get_noise_pred(lat_b, pe_b, dup(ctrl_images), dup(ctrl_depths), t, 1.0, 1.0, guidance_scale,
+                                                     extra_control_batches=[dup(e.to(torch.bfloat16)) for e in extra_control_images])
+                    if i == total_steps:
+                        pred_x0 = (latents_scaled[:, :, -L:] - sqrt_1mab * noise_pred.float()) / sqrt_ab
+                        tgt_images = torch.cat([(self.vae.decode(b / self.vae.config.scaling_factor, return_dict=False)[0].float() / 2 + 0.5
+                                                 ).clamp(min=0, max=1).permute(0, 2, 3, 1) for b in pred_x0.split(diff_bs, dim=0)], dim=0)[None]
+                elif i == total_steps:
+                    tgt_images = in_images.permute(0, 2, 3, 1)[None].float()
+                if i == total_steps:                                   # optimisation only at the final step (:398-406)
+                    tgt_images = torch.cat([tgt_images, reg_images[None].float()], dim=1)
+                    self.texture_optim(tgt_images, optimizer, lr, n_inverse_steps, render_bs, patch_bs, patch_rgb_weight(progress), nerf_code,
+                                       in_mesh, render_size, intrinsics, intrinsics_size, all_poses, cam_weights_dense, patch_size, debug=debug,
+                                       patch_views=num_cameras)
+                if i >= total_steps or optim_only:
+                    continue
+                if t is not None:
+                    merged = noise_pred.float()
+                    if use_reference:
+                        merged = torch.cat([(latents_scaled[:, :, :L] - ref_latents * sqrt_ab) / sqrt_1mab, merged], dim=2)
+                    latents = sch.step(merged, t, latents, torch.randn(latents.shape, device=device))
+                elif denoising_strength is None:
+                    shared = lambda: torch.randn_like(init_latents[0]).expand(init_latents.size(0), -1, -1, -1) * sch.init_noise_sigma
+                    latents = shared()
+                    if use_reference:
+                        latents = torch.cat([shared(), latents], dim=2)
+                else:
+                    latents = torch.cat([ref_latents, init_latents], dim=2) if use_reference else init_latents
+                    latents = sch.add_noise(latents, torch.randn_like(latents[0]).expand(latents.size(0), -1, -1, -1), timesteps[0:1])
+            kw = dict(map_size=2048, force_auto_uv=False)
+            kw.update(bake_texture_kwargs or {})
+            ori_albedo = in_mesh.albedo
+            keep_original = not (ori_albedo is None or in_mesh.textureless)
+            if keep_original:
+                kw.update(dilation_iters=0)
+            out_mesh = self.mesh_renderer.bake_xyz_shading_fun([in_mesh], albedo_fun, **kw)[0]
+            if keep_original:                                          # blend with the input texture where the cameras saw little (:468-487)
+                cos_weight_pow, map_size = 4.0, kw['map_size']
+                ori_weight = 0.2 ** cos_weight_pow
+                ori = F.interpolate(ori_albedo.permute(2, 0, 1)[None], size=map_size, mode='bilinear').squeeze(0).permute(1, 2, 0)
+                w_uv, valid = self.mesh_renderer.get_cam_weights_uv([in_mesh], all_poses[None], intrinsics[None] * (render_size / intrinsics_size),
+                                                                    render_size=render_size, map_size=map_size, render_bs=render_bs,
+                                                                    cos_weight_pow=cos_weight_pow)
+                w_uv = (w_uv.squeeze(0) * cam_weights[:, None, None, None]).sum(dim=0)
+                albedo = (ori[..., :3] * ori_weight + out_mesh.albedo[..., :3] * w_uv) / (ori_weight + w_uv).clamp(min=1e-6)
+                out_mesh.albedo = edge_dilation(albedo.permute(2, 0, 1)[None], valid[None].float()).squeeze(0).permute(1, 2, 0)
+                out_mesh.textureless = False
+        except NotImplementedError:
+            dec.restore_state_dict()
+            raise
+        except Exception:
+            print(traceback.format_exc())
+            out_mesh = None
+        finally:
+            torch.set_grad_enabled(grad_mode)
+        dec.restore_state_dict()
+        return out_mesh

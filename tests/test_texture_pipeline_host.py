@@ -120,3 +120,31 @@ def test_camera_dense_weighting_shape_and_range():
     w = TP.camera_dense_weighting(intr[None].expand(n, -1), size, size, out['rgba'].squeeze(0)[..., 3:], out['depth'].squeeze(0))
     assert w.shape == (n, size, size, 1) and w.min() >= 0 and 0.3 < w.max() <= 1.0 + 1e-5
     assert (w[out['rgba'].squeeze(0)[..., 3:] == 0] == 0).all()
+
+
+def test_superres_pipeline_runs_and_keeps_unseen_texels_of_the_original(monkeypatch):
+    monkeypatch.setattr(TP, 'FusedAdam', AdamLike)
+    n, size = 3, 32
+    base, dec, mesh, poses, intr, _ = _pipeline(DDIMScheduler(), n, size)
+    pipe = TP.MVEditTextureSuperResPipeline(base.vae, None, None, base.unet, None, base.scheduler, base.nerf, base.mesh_renderer)
+    calls = []
+
+    def fake(lat_b, pe_b, ci_b, cd_b, t, tile_w, depth_w, g, extra_control_batches=None):
+        calls.append((lat_b[0].shape[0], ci_b[0].shape, float(tile_w)))
+        return 0.1 * lat_b[0][: lat_b[0].shape[0] // 2].float()
+    pipe.get_noise_pred = fake
+    seen = {}
+    real_optim = pipe.texture_optim
+    pipe.texture_optim = lambda *a, **k: (seen.update(n_tgt=a[0].shape[1], n_poses=a[12].shape[0], patch_views=k.get('patch_views')), real_optim(*a, **k))[1]
+    mesh.albedo = torch.rand(64, 64, 4, generator=torch.Generator().manual_seed(1))
+    ori = mesh.albedo.clone()
+    reg_poses = torch.from_numpy(synth_mesh.surround_poses(2, 9)).float()
+    out = pipe(in_model=mesh, camera_poses=poses, reg_camera_poses=reg_poses, intrinsics=intr, intrinsics_size=size, use_reference=False,
+               diff_size=size, patch_size=20, render_bs=2, n_inverse_steps=2, num_inference_steps=4, denoising_strength=0.5,
+               patch_rgb_weight=lambda p: 0.0, prompt_embeds=torch.zeros(2 * n, 77, 8), bake_texture_kwargs=dict(map_size=64))
+    assert isinstance(out, Mesh) and out.albedo.shape[:2] == (64, 64)
+    assert len(calls) >= 2 and all(c[0] == 2 * n and c[1] == (2 * n, 3, size, size) and c[2] == 1.0 for c in calls)     # fixed tile condition, weight 1
+    assert seen == dict(n_tgt=n + 2, n_poses=n + 2, patch_views=n)                     # regulariser views join the fit, not the patch term
+    # texels no camera looks at frontally keep (a dilated copy of) the original texture; well-seen texels moved to the fitted field
+    d = (out.albedo[..., :3] - ori[..., :3]).abs().max(dim=-1).values
+    assert (d < 0.02).float().mean() > 0.1 and (d > 0.05).float().mean() > 0.05
