@@ -114,3 +114,31 @@ def test_call_without_mesh_renderer_raises_cleanly(monkeypatch):
                        use_reference=False, use_normal=False, optim_only=True, num_inference_steps=2, progress_to_dmtet=0.4)
     assert mesh is None and state is None               # the reference's behaviour on any failure: print the traceback, return (None, None)
     assert dec.state_dict_bak is not None
+
+
+def test_call_initialises_from_an_input_mesh(monkeypatch):
+    """3D-to-3D: without init_images the targets of the initial fit are renders of ``in_model`` shaded by the sampled lights
+    (mvedit_3d_pipeline.py:1052-1066), with ``init_shaded`` set."""
+    from mvedit_b200.mesh_renderer import Mesh
+    monkeypatch.setattr(P, 'FusedAdam', AdamLike)
+    seen = []
+    monkeypatch.setattr(P, 'nerf_optim', lambda nerf, tgt_images, tgt_masks, *a, **k: seen.append((tgt_images, tgt_masks, a[24])))    # a[24] = init_shaded
+    dec = ToyDecoder()
+    nerf = nn.Module()
+    nerf.decoder, nerf.bg_color, nerf.grid_size, nerf.pixel_loss, nerf.patch_loss = dec, 1.0, 8, L1LossMod(loss_weight=1.2), None
+    nerf.get_init_density_grid = lambda ns, device=None: torch.zeros(ns, 8 ** 3, dtype=torch.float16)
+    nerf.get_init_density_bitfield = lambda ns, device=None: torch.zeros(ns, 8 ** 3 // 8, dtype=torch.uint8)
+    unet = nn.Module()
+    unet.device = torch.device('cpu')
+    pipe = P.MVEdit3DPipeline(None, None, None, unet, None, None, nerf, mesh_renderer=MeshRenderer(near=0.01, far=100))
+    v, f = synth_mesh.icosphere(1)
+    mesh = Mesh(v=torch.from_numpy(v).float() * 0.5, f=torch.from_numpy(f).int(), vc=torch.cat([torch.rand(1, len(v), 3), torch.ones(1, len(v), 1)], dim=-1))
+    poses = torch.from_numpy(synth_mesh.surround_poses(2, 1)).float()
+    pipe(in_model=mesh, camera_poses=poses, intrinsics=torch.from_numpy(synth_mesh.intrinsics(32)).float(), intrinsics_size=32,
+         use_reference=False, use_normal=False, optim_only=True, num_inference_steps=1, progress_to_dmtet=0.9, tet_resolution=8, render_bs=2,
+         render_size_p=lambda p: 512, max_num_views=lambda p, q: 2, bake_texture=False, tet_init_inverse_steps=0, n_inverse_steps=0)
+    tgt_images, tgt_masks, init_shaded = seen[0]
+    assert tgt_images.shape == (1, 2, 512, 512, 3) and tgt_masks.shape == (1, 2, 512, 512, 1) and init_shaded is True
+    fg = tgt_masks[0, ..., 0] > 0.99
+    assert 0.05 < fg.float().mean() < 0.5 and (tgt_images[0][~(tgt_masks[0, ..., 0] > 0)] == 1.0).all()       # composited on the background colour
+    assert tgt_images[0][fg].std() > 0.02                                                                   # shaded vertex colours, not flat
