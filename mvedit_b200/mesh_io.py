@@ -131,3 +131,82 @@ def write(mesh, path, flip_yz=False):
         write_glb(mesh, path)
     else:
         raise NotImplementedError('format %s not supported!' % path)
+
+
+# ---- loading (mesh_utils.py:80-260): .obj with face uvs / normals and a map_Kd texture, and the binary .ply written above ------------------
+
+def load_obj(path, device=None):
+    from .mesh_renderer import Mesh
+    v, vt, vn, f, ft, fn, mtl = [], [], [], [], [], [], None
+    with open(path) as fp:
+        for line in fp:
+            tok = line.split()
+            if not tok:
+                continue
+            if tok[0] == 'v':
+                v.append([float(x) for x in tok[1:4]])
+            elif tok[0] == 'vt':
+                vt.append([float(tok[1]), 1.0 - float(tok[2])])                 # stored as 1 - v (write_obj)
+            elif tok[0] == 'vn':
+                vn.append([float(x) for x in tok[1:4]])
+            elif tok[0] == 'mtllib':
+                mtl = tok[1]
+            elif tok[0] == 'f':
+                corners = [(c.split('/') + ['', ''])[:3] for c in tok[1:]]
+                idx = [[int(c[k]) - 1 if c[k] else -1 for c in corners] for k in range(3)]
+                for j in range(1, len(corners) - 1):                            # fan triangulation of polygons
+                    f.append([idx[0][0], idx[0][j], idx[0][j + 1]])
+                    ft.append([idx[1][0], idx[1][j], idx[1][j + 1]])
+                    fn.append([idx[2][0], idx[2][j], idx[2][j + 1]])
+    t = lambda a, dt: torch.tensor(a, dtype=dt, device=device)
+    mesh = Mesh(v=t(v, torch.float32), f=t(f, torch.int32), device=device)
+    if vt and min(min(r) for r in ft) >= 0:
+        mesh.vt, mesh.ft = t(vt, torch.float32), t(ft, torch.int32)
+    if vn and min(min(r) for r in fn) >= 0:
+        mesh.vn, mesh.fn = t(vn, torch.float32), t(fn, torch.int32)
+    if mtl is not None:
+        mtl_path = os.path.join(os.path.dirname(path), mtl)
+        if os.path.exists(mtl_path):
+            for line in open(mtl_path):
+                tok = line.split()
+                if tok and tok[0] == 'map_Kd':
+                    from PIL import Image
+                    img = np.asarray(Image.open(os.path.join(os.path.dirname(path), tok[1])).convert('RGB')).astype(np.float32) / 255
+                    mesh.albedo = torch.cat([torch.from_numpy(img), torch.ones(img.shape[0], img.shape[1], 1)], dim=-1).to(device)
+    mesh.textureless = mesh.albedo is None
+    return mesh
+
+
+def load_ply(path, device=None):
+    from .mesh_renderer import Mesh
+    raw = open(path, 'rb').read()
+    head, body = raw.split(b'end_header\n', 1)
+    if b'binary_little_endian' not in head:
+        raise NotImplementedError('load_ply: only the binary little-endian layout written by write_ply is read')
+    nv = int([l for l in head.split(b'\n') if l.startswith(b'element vertex')][0].split()[-1])
+    nf = int([l for l in head.split(b'\n') if l.startswith(b'element face')][0].split()[-1])
+    v = np.frombuffer(body[:nv * 12], '<f4').reshape(nv, 3)
+    faces = np.frombuffer(body[nv * 12:nv * 12 + nf * 13], dtype=[('n', 'u1'), ('i', '<i4', 3)])
+    return Mesh(v=torch.from_numpy(v.copy()).to(device), f=torch.from_numpy(faces['i'].copy()).to(device), device=device, textureless=True)
+
+
+def load(path, resize=False, auto_uv=True, flip_yz=False, force_auto_normal=False, device=None):
+    """``Mesh.load`` (mesh_utils.py:80-113): read, fix normals / UVs, optional y-up -> z-up flip (the inverse of ``write``'s)."""
+    if path.endswith('.obj'):
+        mesh = load_obj(path, device)
+    elif path.endswith('.ply'):
+        mesh = load_ply(path, device)
+    else:
+        raise NotImplementedError('Mesh.load: %s -- only .obj and the binary .ply of Mesh.write are read (.glb needs a glTF reader)' % path)
+    if resize:
+        vmin, vmax = mesh.v.min(dim=0).values, mesh.v.max(dim=0).values
+        mesh.ori_center, mesh.ori_scale = (vmax + vmin) / 2, 1.2 / float((vmax - vmin).max())
+        mesh.v = (mesh.v - mesh.ori_center) * mesh.ori_scale
+    if mesh.vn is None or force_auto_normal:
+        mesh.auto_normal()
+    if mesh.vt is None and auto_uv:
+        mesh.auto_uv()
+    if flip_yz:
+        flip = lambda t: torch.stack([t[..., 0], -t[..., 2], t[..., 1]], dim=-1)
+        mesh.v, mesh.vn = flip(mesh.v), flip(mesh.vn)
+    return mesh

@@ -77,3 +77,22 @@ def test_glb_container(tmp_path):
     png = bin_[views[4]['byteOffset']:views[4]['byteOffset'] + views[4]['byteLength']]
     assert np.asarray(Image.open(io.BytesIO(png))).shape == (16, 16, 3)
     assert gltf['images'][0]['mimeType'] == 'image/png' and gltf['materials'][0]['doubleSided'] is True
+
+
+def test_obj_and_ply_load_back(tmp_path):
+    m = _mesh()
+    p = str(tmp_path / 'a.obj')
+    m.write(p, flip_yz=True)
+    r = Mesh.load(p, flip_yz=True)                                     # the load-side flip undoes the write-side one
+    np.testing.assert_allclose(r.v.numpy(), m.v.numpy(), atol=2e-6)
+    np.testing.assert_allclose(r.vt.numpy(), m.vt.numpy(), atol=1e-4)
+    np.testing.assert_allclose(r.vn.numpy(), m.vn.numpy(), atol=1e-4)
+    assert torch.equal(r.f, m.f) and torch.equal(r.ft, m.ft) and torch.equal(r.fn, m.fn) and r.textureless is False
+    assert r.albedo.shape == (16, 16, 4) and (r.albedo[..., :3] - m.albedo[..., :3]).abs().max() < 1 / 255 + 1e-6
+    q = str(tmp_path / 'b.ply')
+    m.write(q)
+    g = Mesh.load(q)
+    assert torch.equal(g.f, m.f) and torch.allclose(g.v, m.v) and g.vn is not None and g.vt is not None      # normals / atlas rebuilt
+    (tmp_path / 'quad.obj').write_text('v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n')
+    quad = Mesh.load(str(tmp_path / 'quad.obj'), auto_uv=False)
+    assert quad.f.tolist() == [[0, 1, 2], [0, 2, 3]] and quad.vt is None
