@@ -255,8 +255,9 @@ MVE_HD void interp_fwd_pixel(const InterpP& p, uint32_t i) {
     int t = (int)r.w - 1;
     float* o = p.out + (size_t)i * p.C;
     float* oda = p.out_da ? p.out_da + (size_t)i * 2 * p.C : nullptr;
-    const int32_t* tv = p.tri + (size_t)(t < 0 ? 0 : t) * 3;
-    bool ok = t >= 0 && (uint32_t)t < p.F && (uint32_t)tv[0] < p.Va && (uint32_t)tv[1] < p.Va && (uint32_t)tv[2] < p.Va;
+    bool ok = t >= 0 && (uint32_t)t < p.F;                     // nothing is read from tri for an empty pixel (the face list may be empty)
+    const int32_t* tv = p.tri + (size_t)(ok ? t : 0) * 3;
+    ok = ok && (uint32_t)tv[0] < p.Va && (uint32_t)tv[1] < p.Va && (uint32_t)tv[2] < p.Va;
     if (!ok) {
         for (uint32_t c = 0; c < p.C; ++c) o[c] = 0.f;
         if (oda) for (uint32_t c = 0; c < 2 * p.C; ++c) oda[c] = 0.f;
@@ -281,8 +282,9 @@ MVE_HD void interp_bwd_pixel(const InterpP& p, uint32_t i) {
     float4 r = p.rast[i];
     int t = (int)r.w - 1;
     float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int32_t* tv = p.tri + (size_t)(t < 0 ? 0 : t) * 3;
-    bool ok = t >= 0 && (uint32_t)t < p.F && (uint32_t)tv[0] < p.Va && (uint32_t)tv[1] < p.Va && (uint32_t)tv[2] < p.Va;
+    bool ok = t >= 0 && (uint32_t)t < p.F;
+    const int32_t* tv = p.tri + (size_t)(ok ? t : 0) * 3;
+    ok = ok && (uint32_t)tv[0] < p.Va && (uint32_t)tv[1] < p.Va && (uint32_t)tv[2] < p.Va;
     if (ok) {
         size_t boff = (size_t)(i / p.n_pix_per_image) * p.attr_stride * p.C;
         const float* a0 = p.attr + boff + (size_t)tv[0] * p.C; const float* a1 = p.attr + boff + (size_t)tv[1] * p.C; const float* a2 = p.attr + boff + (size_t)tv[2] * p.C;
@@ -591,7 +593,7 @@ static inline unsigned long long tex_fill(TexP& p, uint32_t Bt, uint32_t th, uin
 
 MVE_EXPORT int mve_rasterize_fwd(const float* pos, const int32_t* tri, uint32_t B, uint32_t V, uint32_t F, uint32_t H, uint32_t W,
                                  int pos_batched, void* zbuf, uint32_t* queue, float* rast, float* rast_db, void* stream) {
-    MVE_ARG(pos && tri && zbuf && queue && rast, "mve_rasterize_fwd: NULL pointer");
+    MVE_ARG(pos && (tri || F == 0) && zbuf && queue && rast, "mve_rasterize_fwd: NULL pointer");
     MVE_ARG(B > 0 && H > 0 && W > 0 && (unsigned long long)B * H * W < (1ull << 31) && (unsigned long long)B * (F ? F : 1) < (1ull << 31),
             "mve_rasterize_fwd: B*H*W and B*F must be below 2^31");
     RasterP p = {};
@@ -611,7 +613,7 @@ MVE_EXPORT int mve_rasterize_fwd(const float* pos, const int32_t* tri, uint32_t 
 
 MVE_EXPORT int mve_rasterize_bwd(const float* pos, const int32_t* tri, uint32_t B, uint32_t V, uint32_t F, uint32_t H, uint32_t W,
                                  int pos_batched, const float* rast, const float* g_rast, float* g_pos, void* stream) {
-    MVE_ARG(pos && tri && rast && g_rast && g_pos, "mve_rasterize_bwd: NULL pointer");
+    MVE_ARG(pos && (tri || F == 0) && rast && g_rast && g_pos, "mve_rasterize_bwd: NULL pointer");
     RasterP p = {};
     p.pos = (const float4*)pos; p.tri = tri; p.B = B; p.V = V; p.F = F; p.H = H; p.W = W; p.pos_stride = pos_batched ? V : 0;
     p.rast = (float4*)rast; p.g_rast = (const float4*)g_rast; p.g_pos = g_pos;
@@ -621,7 +623,7 @@ MVE_EXPORT int mve_rasterize_bwd(const float* pos, const int32_t* tri, uint32_t 
 
 MVE_EXPORT int mve_interpolate_fwd(const float* attr, const int32_t* tri, const float* rast, const float* rast_db, uint32_t B, uint32_t H,
                                    uint32_t W, uint32_t Va, uint32_t F, uint32_t C, int attr_batched, float* out, float* out_da, void* stream) {
-    MVE_ARG(attr && tri && rast && out, "mve_interpolate_fwd: NULL pointer");
+    MVE_ARG(attr && (tri || F == 0) && rast && out, "mve_interpolate_fwd: NULL pointer");
     MVE_ARG(out_da == nullptr || rast_db != nullptr, "mve_interpolate_fwd: out_da needs rast_db");
     InterpP p = {};
     p.attr = attr; p.tri = tri; p.rast = (const float4*)rast; p.rast_db = (const float4*)rast_db; p.n_pix_per_image = H * W; p.Va = Va; p.F = F;
@@ -632,7 +634,7 @@ MVE_EXPORT int mve_interpolate_fwd(const float* attr, const int32_t* tri, const 
 
 MVE_EXPORT int mve_interpolate_bwd(const float* attr, const int32_t* tri, const float* rast, uint32_t B, uint32_t H, uint32_t W, uint32_t Va,
                                    uint32_t F, uint32_t C, int attr_batched, const float* g_out, float* g_attr, float* g_rast, void* stream) {
-    MVE_ARG(attr && tri && rast && g_out && g_attr, "mve_interpolate_bwd: NULL pointer");
+    MVE_ARG(attr && (tri || F == 0) && rast && g_out && g_attr, "mve_interpolate_bwd: NULL pointer");
     InterpP p = {};
     p.attr = attr; p.tri = tri; p.rast = (const float4*)rast; p.n_pix_per_image = H * W; p.Va = Va; p.F = F; p.C = C;
     p.attr_stride = attr_batched ? Va : 0; p.g_out = g_out; p.g_attr = g_attr; p.g_rast = (float4*)g_rast;
@@ -642,7 +644,7 @@ MVE_EXPORT int mve_interpolate_bwd(const float* attr, const int32_t* tri, const 
 
 MVE_EXPORT int mve_antialias_fwd(const float* color, const float* rast, const float* pos, const int32_t* tri, const int32_t* opp, uint32_t B,
                                  uint32_t H, uint32_t W, uint32_t C, uint32_t V, uint32_t F, int pos_batched, float* out, void* stream) {
-    MVE_ARG(color && rast && pos && tri && opp && out, "mve_antialias_fwd: NULL pointer");
+    MVE_ARG(color && rast && pos && ((tri && opp) || F == 0) && out, "mve_antialias_fwd: NULL pointer");
     AaP p = {};
     p.color = color; p.rast = (const float4*)rast; p.pos = (const float4*)pos; p.tri = tri; p.opp = opp; p.B = B; p.H = H; p.W = W; p.C = C;
     p.V = V; p.F = F; p.pos_stride = pos_batched ? V : 0; p.out = out;
@@ -654,7 +656,7 @@ MVE_EXPORT int mve_antialias_fwd(const float* color, const float* rast, const fl
 MVE_EXPORT int mve_antialias_bwd(const float* color, const float* rast, const float* pos, const int32_t* tri, const int32_t* opp, uint32_t B,
                                  uint32_t H, uint32_t W, uint32_t C, uint32_t V, uint32_t F, int pos_batched, const float* g_out,
                                  float* g_color, float* g_pos, void* stream) {
-    MVE_ARG(color && rast && pos && tri && opp && g_out && g_color, "mve_antialias_bwd: NULL pointer");
+    MVE_ARG(color && rast && pos && ((tri && opp) || F == 0) && g_out && g_color, "mve_antialias_bwd: NULL pointer");
     AaP p = {};
     p.color = color; p.rast = (const float4*)rast; p.pos = (const float4*)pos; p.tri = tri; p.opp = opp; p.B = B; p.H = H; p.W = W; p.C = C;
     p.V = V; p.F = F; p.pos_stride = pos_batched ? V : 0; p.g_out = g_out; p.g_color = g_color; p.g_pos = g_pos;

@@ -270,3 +270,19 @@ def test_texture_rejects_what_is_not_built():
     with pytest.raises(NotImplementedError):
         dr.texture(tex, uv.clone().requires_grad_(True))
     assert dr.texture(torch.ones(1, 6, 10, 1), uv, uv_da=uv_da).shape[-1] == 1       # odd halves: the pyramid stops at 3 x 5
+
+
+def test_empty_face_list_is_rendered_as_an_empty_image():
+    """A DMTet field that lost its zero crossing yields no triangles: every op must pass that through (empty raster, zero attributes,
+    colours untouched, zero gradients) instead of reading a face that does not exist."""
+    pos = torch.randn(2, 5, 4).abs().requires_grad_(True)
+    tri = torch.zeros(0, 3, dtype=torch.int32)
+    rast, db = dr.rasterize(dr.RasterizeCudaContext(), pos, tri, (6, 7))
+    assert rast.shape == (2, 6, 7, 4) and (rast == 0).all() and (db == 0).all()
+    attr = torch.randn(1, 5, 3, requires_grad=True)
+    out, _ = dr.interpolate(attr, rast, tri)
+    col = torch.rand(2, 6, 7, 4, requires_grad=True)
+    aa = dr.antialias(col, rast, pos, tri)
+    assert (out == 0).all() and torch.equal(aa, col)
+    (out.sum() + aa.sum() + rast.sum()).backward()
+    assert (attr.grad == 0).all() and (pos.grad == 0).all() and (col.grad == 1).all()
