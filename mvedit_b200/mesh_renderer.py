@@ -69,6 +69,14 @@ class Mesh:
         from . import mesh_io
         mesh_io.write(self, path, flip_yz=flip_yz)
 
+    def edge_topology(self):
+        """``mesh_raster.edge_opposites(f)`` cached on the mesh (one stable sort, ~0.5 ms at 300 k faces: every ``render_bs`` batch and every
+        step of a fixed mesh re-uses it; a DMTet re-extraction makes a new Mesh and hence a new cache)."""
+        key = (self.f.data_ptr(), tuple(self.f.shape))
+        if getattr(self, '_edge_topology', None) is None or self._edge_topology[0] != key:
+            self._edge_topology = (key, dr.edge_opposites(self.f))
+        return self._edge_topology[1]
+
     def auto_normal(self, seamless=False):
         """Area-unweighted vertex normals: unit face normals splatted to the vertices (``mesh_utils.py:359-382``)."""
         if seamless:
@@ -179,20 +187,21 @@ class DMTet:
             occ_n = sdf_n > 0
             occ_fx4 = occ_n[tet_fx4.reshape(-1)].reshape(-1, 4)
             occ_sum = occ_fx4.sum(-1)
-            valid = (occ_sum > 0) & (occ_sum < 4)
-            cross = occ_n[edges[:, 0]] != occ_n[edges[:, 1]]
+            valid_ids = ((occ_sum > 0) & (occ_sum < 4)).nonzero().reshape(-1)                  # every data-dependent size costs one host
+            cross = occ_n[edges[:, 0]] != occ_n[edges[:, 1]]                                   # read: four in all (the reference's
+            cross_ids = cross.nonzero().reshape(-1)                                            # boolean indexing makes about a dozen)
             edge_vid = torch.cumsum(cross.long(), 0) - 1
             edge_vid = torch.where(cross, edge_vid, torch.full_like(edge_vid, -1))
-            interp_v = edges[cross]
-            idx_map = edge_vid[tet_edges[valid]]                                       # [Fv,6]
+            interp_v = edges[cross_ids]
+            idx_map = edge_vid[tet_edges[valid_ids]]                                           # [Fv,6]
             v_id = torch.pow(2, torch.arange(4, dtype=torch.long, device=sdf_n.device))
-            tetindex = (occ_fx4[valid] * v_id.unsqueeze(0)).sum(-1)
+            tetindex = (occ_fx4[valid_ids] * v_id.unsqueeze(0)).sum(-1)
             num_triangles = self.num_triangles_table[tetindex]
+            one, two = (num_triangles == 1).nonzero().reshape(-1), (num_triangles == 2).nonzero().reshape(-1)
         p = pos_nx3[interp_v.reshape(-1)].reshape(-1, 2, 3)
         s = sdf_n[interp_v.reshape(-1)].reshape(-1, 2)
         den = s[:, 0] - s[:, 1]
         verts = p[:, 0] * (-s[:, 1] / den)[:, None] + p[:, 1] * (s[:, 0] / den)[:, None]
-        one, two = num_triangles == 1, num_triangles == 2
         faces = torch.cat((
             torch.gather(idx_map[one], 1, self.triangle_table[tetindex[one]][:, :3]).reshape(-1, 3),
             torch.gather(idx_map[two], 1, self.triangle_table[tetindex[two]][:, :6]).reshape(-1, 3)), dim=0)
@@ -363,8 +372,8 @@ class MeshRenderer(nn.Module):
                 rgba = edge_dilation(rgba, rgba[:, 3:], dilate_edges).permute(0, 2, 3, 1).reshape(num_scenes, num_images, h, w, 4)
             if aa:
                 rgba, depth, rot_normal = dr.antialias(
-                    torch.cat([rgba, depth.unsqueeze(-1), rot_normal], dim=-1).squeeze(0).contiguous(), rast, v_clip, tri
-                ).unsqueeze(0).split([4, 1, 3], dim=-1)
+                    torch.cat([rgba, depth.unsqueeze(-1), rot_normal], dim=-1).squeeze(0).contiguous(), rast, v_clip, tri,
+                    topology_hash=mesh.edge_topology()).unsqueeze(0).split([4, 1, 3], dim=-1)
                 depth = depth.squeeze(-1)
             if self.ssaa > 1:
                 rgba = interpolate_hwc(rgba, 1 / self.ssaa)
