@@ -427,6 +427,24 @@ int mve_texture_fwd(const float* pyr, uint32_t Bt, uint32_t th, uint32_t tw, uin
 int mve_texture_bwd(uint32_t Bt, uint32_t th, uint32_t tw, uint32_t C, uint32_t n_levels, const float* uv, const float* uv_da,
                     uint32_t B, uint32_t H, uint32_t W, const float* g_out, float* g_pyr, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * a-10: the per-pixel part of mesh_optim's objective (lib/pipelines/mvedit_3d_pipeline.py:745-774), loss and gradient in two calls
+ * (three launches).  Images are [bs,h,w,*] f32: rgba = the antialiased render (premultiplied rgb, alpha), normal = its camera-space
+ * normal map, tgt_rgb / m_erode / m_blur the target colours, the 5x5-eroded target mask and the softened target alpha, w_view [bs] =
+ * camera weight / mean weight, nbg_host3 = HOST array of the 3 background-normal values.  c_* = term weight / element count
+ * (x the data-parallel share): L1LossMod(1.2) * 4.5 / (n*3), 1.2 * 2 / n, normal_reg_weight * 2 / (n*3).
+ * ------------------------------------------------------------------------- */
+/* out_rgb [n,3] = rgb' (what the LPIPS patch term looks at), nfg [n,3] (kept for the backward), loss[0..1] += the rgb / alpha sums. */
+int mve_mesh_loss_forward(const float* rgba, const float* normal, const float* tgt_rgb, const float* m_erode, const float* m_blur,
+                          const float* w_view, const float* nbg_host3, uint32_t bs, uint32_t h, uint32_t w, float c_rgb, float c_alpha,
+                          float* out_rgb, float* nfg, float* loss, void* stream);
+/* loss[2] += the TV-normal sum; g_rgba [n,4], g_normal [n,3] written.  gate [n] (view-cosine gate of the normal gradient) and
+ * g_rgb_extra [n,3] (d patch term / d rgb') may be NULL; g_nfg [n,3] is scratch. */
+int mve_mesh_loss_backward(const float* rgba, const float* tgt_rgb, const float* m_erode, const float* m_blur, const float* w_view,
+                           const float* gate, const float* nbg_host3, uint32_t bs, uint32_t h, uint32_t w, float c_rgb, float c_alpha,
+                           float c_tv, const float* nfg, const float* g_rgb_extra, float* g_nfg, float* loss, float* g_rgba,
+                           float* g_normal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

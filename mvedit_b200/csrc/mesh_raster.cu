@@ -20,47 +20,7 @@
 // The file also compiles as plain C++ (-DMVE_HOST_HARNESS, tests/host_harness.py): the per-element functions below are then driven
 // by serial loops so that the CPU test-suite exercises the very same arithmetic and the Python autograd mirror without a GPU.
 // That harness is test infrastructure only; the product library contains the CUDA build and nothing else.
-#ifdef MVE_HOST_HARNESS
-#include <math.h>
-#include <stdarg.h>
-#include <stdint.h>
-#include <stdio.h>
-#include <string.h>
-#define MVE_HD static inline
-struct float4 { float x, y, z, w; };
-struct float2 { float x, y; };
-static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
-static char g_harness_err[512];
-static void mve_set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_harness_err, sizeof g_harness_err, fmt, ap); va_end(ap); }
-#define MVE_ARG(cond, msg) do { if (!(cond)) { mve_set_error("bad argument: %s", msg); return -1; } } while (0)
-#define MVE_CHECK_LAUNCH(name) do { } while (0)
-static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
-static inline void atomic_add_f(float* p, float v) { *p += v; }
-static inline void atomic_min_u64(unsigned long long* p, unsigned long long v) { if (v < *p) *p = v; }
-static inline uint32_t atomic_inc_u32(uint32_t* p) { return (*p)++; }
-#define MVE_ELEMENT_KERNEL(kname, P, fn) static void kname(const P& p, uint32_t n) { for (uint32_t i = 0; i < n; ++i) fn(p, i); }
-#define MVE_LAUNCH(kname, p, n, st) kname(p, n)
-#define MVE_MEMSET(ptr, byte, bytes, st) memset(ptr, byte, bytes)
-#define MVE_MEMCPY(dst, src, bytes, st) memcpy(dst, src, bytes)
-#define MVE_EXPORT extern "C" __attribute__((visibility("default")))
-#else
-#include "common.cuh"
-#define MVE_HD __device__ __forceinline__
-__device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
-__device__ __forceinline__ void atomic_add_f(float* p, float v) { atomicAdd(p, v); }
-__device__ __forceinline__ void atomic_min_u64(unsigned long long* p, unsigned long long v) { atomicMin(p, v); }
-__device__ __forceinline__ uint32_t atomic_inc_u32(uint32_t* p) { return atomicAdd(p, 1u); }
-#define MVE_ELEMENT_KERNEL(kname, P, fn)                                                  \
-    __global__ void __launch_bounds__(256) kname(const P p, uint32_t n) {                 \
-        uint32_t i = blockIdx.x * 256u + threadIdx.x;                                     \
-        if (i < n) fn(p, i);                                                              \
-    }
-#define MVE_LAUNCH(kname, p, n, st)                                                       \
-    do { if ((n) > 0) { kname<<<cdiv((n), 256), 256, 0, (cudaStream_t)(st)>>>(p, (uint32_t)(n)); MVE_CHECK_LAUNCH(#kname); } } while (0)
-#define MVE_MEMSET(ptr, byte, bytes, st) MVE_CUDA(cudaMemsetAsync(ptr, byte, bytes, (cudaStream_t)(st)))
-#define MVE_MEMCPY(dst, src, bytes, st) MVE_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)(st)))
-#define MVE_EXPORT extern "C"
-#endif
+#include "host_dual.cuh"
 
 namespace {
 

@@ -10,6 +10,7 @@ torch autograd over those kernels (the NeRF stage has it fused in ``nerf_loss.cu
 Not built (raise): target normals (``use_normal``: the normal model is absent), mesh simplification at the last step
 (``mesh_reduction < 1`` needs open3d's quadric decimation, ``:829-844``).
 """
+import ctypes
 import os
 
 import numpy as np
@@ -19,6 +20,7 @@ import torch.nn.functional as F
 from .mesh_renderer import (DMTet, Mesh, laplacian_smooth_loss, make_tet_grid, min_pool, normal_consistency,   # noqa: F401  (re-exported)
                             view_cosine)
 from .nerf import blur_masks, pixel_directions
+from ._lib import call, ptr, stream, c_u32, c_f32
 from . import view_shard
 
 
@@ -119,6 +121,47 @@ def lpips_patch_loss(patch_loss, pred_nchw, target_nchw, weight):
     return patch_loss(pred_nchw, target_nchw, weight=weight)
 
 
+class _MeshObjectiveFn(torch.autograd.Function):
+    """The per-pixel terms of the mesh objective (rgb L1, alpha L1, TV-normal, + the patch term on rgb') as three launches of
+    ``csrc/mesh_loss.cu`` -- loss AND gradient w.r.t. the antialiased (rgba, normal) in the forward call, like the NeRF stage's fused
+    objective.  Opt-in (``mesh_optim(..., fused_objective=True)``): checked against the eager composition on the CPU through the host
+    harness; it has not run on a GPU yet."""
+
+    @staticmethod
+    def forward(ctx, rgba, normal, gate, tgt_rgb, m_erode, m_blur, w_view, normal_bg, c_rgb, c_alpha, c_tv, patch):
+        f = lambda t: t.detach().to(torch.float32).contiguous()
+        rgba_c, normal_c, gate_c, tgt_c, me_c, mb_c, wv_c = f(rgba), f(normal), f(gate), f(tgt_rgb), f(m_erode), f(m_blur), f(w_view)
+        bs, h, w, _ = rgba_c.shape
+        dev = rgba_c.device
+        out_rgb = torch.empty(bs, h, w, 3, dtype=torch.float32, device=dev)
+        nfg, g_nfg = torch.empty(bs * h * w, 3, dtype=torch.float32, device=dev), torch.empty(bs * h * w, 3, dtype=torch.float32, device=dev)
+        loss = torch.zeros(3, dtype=torch.float32, device=dev)
+        nbg = (ctypes.c_float * 3)(*[float(v) for v in normal_bg])
+        call('mve_mesh_loss_forward', ptr(rgba_c), ptr(normal_c), ptr(tgt_c), ptr(me_c), ptr(mb_c), ptr(wv_c), nbg, c_u32(bs), c_u32(h), c_u32(w),
+             c_f32(c_rgb), c_f32(c_alpha), ptr(out_rgb), ptr(nfg), ptr(loss), stream())
+        g_extra, lp = None, None
+        if patch is not None:                                # the LPIPS patch term looks at rgb' (:784-801); its gradient is chained below
+            patch_loss, pick, ps, wgt, scale = patch
+            out_p = _patches(out_rgb, h, ps)[pick].permute(0, 2, 3, 1).contiguous()
+            tgt_p = _patches(tgt_c, h, ps)[pick].permute(0, 2, 3, 1).contiguous()
+            lp, gp, _ = patch_loss.loss_and_grad(out_p, tgt_p, wgt, scale)
+            g = h // ps
+            ge = torch.zeros(bs * g * g, ps, ps, 3, dtype=torch.float32, device=dev)
+            ge[pick] = gp.to(torch.float32)
+            g_extra = ge.reshape(bs, g, g, ps, ps, 3).permute(0, 1, 3, 2, 4, 5).reshape(bs, h, w, 3).contiguous()
+        g_rgba, g_normal = torch.empty_like(rgba_c), torch.empty_like(normal_c)
+        call('mve_mesh_loss_backward', ptr(rgba_c), ptr(tgt_c), ptr(me_c), ptr(mb_c), ptr(wv_c), ptr(gate_c), nbg, c_u32(bs), c_u32(h), c_u32(w),
+             c_f32(c_rgb), c_f32(c_alpha), c_f32(c_tv), ptr(nfg), ptr(g_extra), ptr(g_nfg), ptr(loss), ptr(g_rgba), ptr(g_normal), stream())
+        ctx.save_for_backward(g_rgba, g_normal)
+        total = loss.sum()
+        return total if lp is None else total + lp
+
+    @staticmethod
+    def backward(ctx, g):
+        g_rgba, g_normal = ctx.saved_tensors
+        return (g_rgba * g, g_normal * g) + (None,) * 10
+
+
 def normalize_depth(depths, alphas, far_depth=0.25, alpha_clip=0.5, eps=1e-5):
     """Inverse depth [n,h,w] + alpha [n,h,w,1] -> the ControlNet depth image in [0,1] (``geometry_utils.normalize_depth``): per view,
     foreground inverse depth rescaled so that the farthest confident (alpha >= alpha_clip) pixel maps to ``far_depth`` and the nearest to 1."""
@@ -169,14 +212,17 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
                patch_rgb_weight, patch_normal_weight, alpha_soften, normal_reg_weight, mesh_normal_reg_weight,  # loss weights
                nerf_code, tet_verts, deform, tet_sdf, tet_indices, dmtet, in_mesh,                          # mesh model
                render_size, intrinsics, intrinsics_size, camera_poses, cam_weights, lights, patch_size,     # cameras
-               is_end, ambient_light, mesh_reduction, debug=False, perturb=True, noise=None):
+               is_end, ambient_light, mesh_reduction, debug=False, perturb=True, noise=None, fused_objective=None):
     """``self``: the pipeline (``nerf``, ``mesh_renderer``, ``normal_bg``, ``tonemapping``).  ``noise`` (extension, for parity tests):
     dict with ``camera_perm`` [n], ``jitter`` [steps, render_bs, 2] in [0,1), ``patch_perm`` [steps, n_patches] replacing the draws.
 
     Multi-GPU (``nerf.data_parallel`` with torch.distributed up; the reference is single-GPU): data-parallel over VIEWS -- every rank
     renders its block of the iteration's ``render_bs`` views, the per-view loss terms are weighted by the block's share and the
     replicated regularisers by 1 / world, so that ONE all-reduce (sum) of the gradients reproduces the single-GPU gradient; the fused
-    Adam step and the marching-tets extraction then run replicated and bit-identical.  Random draws are rank 0's (one small broadcast)."""
+    Adam step and the marching-tets extraction then run replicated and bit-identical.  Random draws are rank 0's (one small broadcast).
+
+    ``fused_objective`` (default: ``self.mesh_fused_objective`` if set, else False): the per-pixel loss terms and their gradient as three
+    launches of ``csrc/mesh_loss.cu`` instead of ~60 eager torch ops + autograd (same values; CPU-checked, not yet run on a GPU)."""
     if tgt_normals is not None:
         raise NotImplementedError('mesh_optim: target normals need the normal model, which is not built')
     if mesh_reduction < 1 and is_end:
@@ -197,6 +243,8 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
     dec.grad_sink = optimizer if fused and hasattr(optimizer, 'grad_sink') else None
     rank, world = view_shard.world() if getattr(nerf, 'data_parallel', False) else (0, 1)
     shared = (lambda t: _from_rank0(t)) if world > 1 else (lambda t: t)
+    if fused_objective is None:
+        fused_objective = bool(getattr(self, 'mesh_fused_objective', False))
     try:
         with torch.enable_grad():
             if fused:
@@ -232,27 +280,36 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
                         [in_mesh], pose_b[k][lo:hi][None], intrinsics_batch[lo:hi][None], render_size, render_size,
                         make_nerf_shading_fun(dec, nerf_code, target_lights, ambient_light, self.tonemapping), normal_bg=self.normal_bg)
                     rgba = render_out['rgba'].squeeze(0)
-                    out_alphas = rgba[..., 3:]
-                    out_rgbs = rgba[..., :3] / out_alphas.clamp(min=1e-3)
-                    out_rgbs = out_rgbs * target_m_erode + target_rgbs * (1 - target_m_erode)
-                    out_normals = render_out['normal'].squeeze(0)
                     gate = view_cosine_gate(render_out['depth'].squeeze(0).detach(), target_dir)
-                    out_normals = out_normals * gate + out_normals.detach() * (1 - gate)      # value unchanged, gradient scaled by the gate
-                    out_normals_fg = (out_normals - normal_bg * (1 - out_alphas)) / out_alphas.clamp(min=1e-3)
                     wgt = target_w / cam_weights_mean
-                    views = nerf.pixel_loss(out_rgbs, target_rgbs, weight=wgt) * 4.5
-                    views = views + nerf.pixel_loss(out_alphas, target_m_blur, weight=wgt) * 2.0
-                    views = views + tv_normal_loss(out_normals_fg.permute(0, 3, 1, 2), out_alphas.detach().permute(0, 3, 1, 2)) * (normal_reg_weight * 2)
-                    if patch_rgb_weight > 0:
-                        out_p, tgt_p = _patches(out_rgbs, render_size, patch_size), _patches(target_rgbs, render_size, patch_size)
-                        w_p = _patches(target_w, render_size, patch_size)
-                        if world > 1:                        # each rank draws its share of the patches among its own views
-                            perm = torch.randperm(out_p.size(0), device=device)
-                            pick = perm[:max(patch_bs * (hi - lo) // bs, 1)]
+                    grid_n = render_size // patch_size
+                    if patch_rgb_weight > 0:                     # which patches the LPIPS term looks at (:793)
+                        if world > 1:                            # each rank draws its share of the patches among its own views
+                            pick = torch.randperm((hi - lo) * grid_n * grid_n, device=device)[:max(patch_bs * (hi - lo) // bs, 1)]
                         else:
-                            perm = noise['patch_perm'][step].to(device) if 'patch_perm' in noise else torch.randperm(out_p.size(0), device=device)
+                            perm = noise['patch_perm'][step].to(device) if 'patch_perm' in noise else torch.randperm((hi - lo) * grid_n * grid_n, device=device)
                             pick = perm[:patch_bs]
-                        views = views + lpips_patch_loss(nerf.patch_loss, out_p[pick], tgt_p[pick], w_p[pick, 0, 0, 0] / cam_weights_mean) * patch_rgb_weight
+                        w_pick = _patches(target_w, render_size, patch_size)[pick, 0, 0, 0] / cam_weights_mean
+                    if fused_objective:
+                        n_px = (hi - lo) * render_size * render_size
+                        lw = float(nerf.pixel_loss.loss_weight)
+                        views = _MeshObjectiveFn.apply(
+                            rgba, render_out['normal'].squeeze(0), gate.squeeze(-1), target_rgbs, target_m_erode.squeeze(-1), target_m_blur.squeeze(-1),
+                            w_b[k][lo:hi] / cam_weights_mean, self.normal_bg, lw * 4.5 / (n_px * 3), lw * 2.0 / n_px, normal_reg_weight * 2 / (n_px * 3),
+                            (nerf.patch_loss, pick, patch_size, w_pick, patch_rgb_weight) if patch_rgb_weight > 0 else None)
+                    else:
+                        out_alphas = rgba[..., 3:]
+                        out_rgbs = rgba[..., :3] / out_alphas.clamp(min=1e-3)
+                        out_rgbs = out_rgbs * target_m_erode + target_rgbs * (1 - target_m_erode)
+                        out_normals = render_out['normal'].squeeze(0)
+                        out_normals = out_normals * gate + out_normals.detach() * (1 - gate)      # value unchanged, gradient scaled by the gate
+                        out_normals_fg = (out_normals - normal_bg * (1 - out_alphas)) / out_alphas.clamp(min=1e-3)
+                        views = nerf.pixel_loss(out_rgbs, target_rgbs, weight=wgt) * 4.5
+                        views = views + nerf.pixel_loss(out_alphas, target_m_blur, weight=wgt) * 2.0
+                        views = views + tv_normal_loss(out_normals_fg.permute(0, 3, 1, 2), out_alphas.detach().permute(0, 3, 1, 2)) * (normal_reg_weight * 2)
+                        if patch_rgb_weight > 0:
+                            out_p, tgt_p = _patches(out_rgbs, render_size, patch_size), _patches(target_rgbs, render_size, patch_size)
+                            views = views + lpips_patch_loss(nerf.patch_loss, out_p[pick], tgt_p[pick], w_pick) * patch_rgb_weight
                     loss = loss + views * share
 
                 optimizer.zero_grad()

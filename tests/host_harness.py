@@ -1,6 +1,6 @@
 """Host harness of the mesh rasteriser -- TEST INFRASTRUCTURE ONLY.
 
-``mvedit_b200/csrc/mesh_raster.cu`` is written so that it also compiles as plain C++ (``-DMVE_HOST_HARNESS``): the per-triangle /
+``mvedit_b200/csrc/mesh_raster.cu`` and ``mesh_loss.cu`` are written so that they also compile as plain C++ (``-DMVE_HOST_HARNESS``): the per-triangle /
 per-pixel device functions are then driven by serial loops and the ``mve_*`` entry points take HOST pointers.  The CPU test-suite uses
 this to check, without a GPU, (1) the kernels' arithmetic bit for bit against ``oracle/raster_oracle.py`` and (2) the Python autograd
 mirror ``mvedit_b200/mesh_raster.py`` (argument order, gradient plumbing) by routing its ``call`` / ``ptr`` / ``stream`` to this
@@ -12,7 +12,9 @@ import os
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = os.path.join(ROOT, 'mvedit_b200', 'csrc', 'mesh_raster.cu')
+CSRC = os.path.join(ROOT, 'mvedit_b200', 'csrc')
+SRCS = [os.path.join(CSRC, f) for f in ('mesh_raster.cu', 'mesh_loss.cu')]
+DEPS = SRCS + [os.path.join(CSRC, 'host_dual.cuh')]
 OUT_DIR = os.path.join(ROOT, 'tests', '_host')
 LIB = os.path.join(OUT_DIR, 'libmesh_raster_host.so')
 _lib = None
@@ -20,9 +22,9 @@ _lib = None
 
 def build():
     os.makedirs(OUT_DIR, exist_ok=True)
-    if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+    if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in DEPS):
         cmd = ['g++', '-x', 'c++', '-std=c++17', '-O2', '-ffp-contract=off', '-fPIC', '-shared', '-fvisibility=hidden', '-DMVE_HOST_HARNESS',
-               SRC, '-o', LIB]
+               '-I', CSRC] + SRCS + ['-o', LIB]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('host harness build failed:\n' + r.stderr)

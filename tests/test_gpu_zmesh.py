@@ -313,3 +313,42 @@ def test_bake_and_textured_render_vs_oracle():
     om.albedo = baked.albedo.cpu()
     out_o = mo.mesh_renderer_forward(om, poses[None], intr[None], size, size)
     torch.testing.assert_close(out['rgba'].cpu(), out_o['rgba'], rtol=1e-3, atol=1e-3)
+
+
+def test_fused_mesh_objective_vs_eager_on_gpu():
+    """csrc/mesh_loss.cu against the torch ops + autograd it replaces (the same comparison runs on the CPU through the host harness)."""
+    from mvedit_b200 import mesh_optim as mopt
+    from mvedit_b200.nerf import L1LossMod
+    g = torch.Generator().manual_seed(0)
+    bs, size = 3, 64
+    yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing='ij')
+    disc = (((xx - 31.5) ** 2 + (yy - 30.5) ** 2).float().sqrt() < 22).float()
+    a = (disc * (0.3 + 0.7 * torch.rand(bs, size, size, generator=g)))[..., None]
+    rgba0 = torch.cat([torch.rand(bs, size, size, 3, generator=g) * a, a], dim=-1).to(DEV)
+    normal0 = (torch.rand(bs, size, size, 3, generator=g) * a + torch.tensor([0.5, 0.5, 1.0]) * (1 - a)).to(DEV)
+    gate, tgt = torch.rand(bs, size, size, 1, generator=g).to(DEV), torch.rand(bs, size, size, 3, generator=g).to(DEV)
+    m = (((xx - 32) ** 2 + (yy - 32) ** 2).float().sqrt() < 24).float()[None, :, :, None].expand(bs, -1, -1, -1).contiguous().to(DEV)
+    m_erode, m_blur = mopt.min_pool(m), m * 0.96 + 0.02
+    w_view = torch.tensor([0.7, 1.3, 1.0]).to(DEV)
+    nbg, n_px = [0.5, 0.5, 1.0], bs * size * size
+    res = {}
+    for mode in ('fused', 'eager'):
+        rgba, normal = rgba0.clone().requires_grad_(True), normal0.clone().requires_grad_(True)
+        if mode == 'fused':
+            val = mopt._MeshObjectiveFn.apply(rgba, normal, gate.squeeze(-1), tgt, m_erode.squeeze(-1), m_blur.squeeze(-1), w_view, nbg,
+                                              1.2 * 4.5 / (n_px * 3), 1.2 * 2.0 / n_px, 0.1 * 2 / (n_px * 3), None)
+        else:
+            al = rgba[..., 3:]
+            rgb = rgba[..., :3] / al.clamp(min=1e-3) * m_erode + tgt * (1 - m_erode)
+            n = normal * gate + normal.detach() * (1 - gate)
+            nfg = (n - torch.tensor(nbg, device=DEV) * (1 - al)) / al.clamp(min=1e-3)
+            w_px = w_view[:, None, None, None].expand(-1, size, size, 1)
+            l1 = L1LossMod(loss_weight=1.2)
+            val = l1(rgb, tgt, weight=w_px) * 4.5 + l1(al, m_blur, weight=w_px) * 2.0 \
+                + mopt.tv_normal_loss(nfg.permute(0, 3, 1, 2), al.detach().permute(0, 3, 1, 2)) * (0.1 * 2)
+        val.backward()
+        res[mode] = (float(val), rgba.grad.cpu(), normal.grad.cpu())
+    f, e = res['fused'], res['eager']
+    assert abs(f[0] - e[0]) < 1e-4 * max(1.0, abs(e[0]))
+    for x, y in zip(f[1:], e[1:]):
+        assert torch.isfinite(x).all() and (x - y).abs().max() <= 2e-4 * y.abs().max() + 1e-8

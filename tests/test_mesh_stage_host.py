@@ -360,3 +360,93 @@ def test_ssaa_and_edge_dilation_branches_match_oracle():
     assert ((r['rgba'][..., 3] > 0.05) & (r['rgba'][..., 3] < 0.95)).sum() > 8        # area-averaged 2x2 supersamples: soft outline
     grown = (d['rgba'][..., 3] > 0).sum() - (plain['rgba'][..., 3] > 0).sum()
     assert grown > 20                                                               # the coverage grew by the dilation ring
+
+
+def _objective_inputs(bs=2, size=24, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing='ij')
+    disc = (((xx - 11.5) ** 2 + (yy - 12.5) ** 2).float().sqrt() < 8).float()
+    a = (disc * (0.3 + 0.7 * torch.rand(bs, size, size, generator=g)))[..., None]
+    a[0, 3, 3] = 5e-4                                                       # below the 1e-3 clamp: no gradient through the division
+    rgba = torch.cat([torch.rand(bs, size, size, 3, generator=g) * a, a], dim=-1)
+    normal = torch.nn.functional.normalize(torch.randn(bs, size, size, 3, generator=g), dim=-1) / 2 + 0.5
+    normal = normal * a + torch.tensor([0.5, 0.5, 1.0]) * (1 - a)
+    gate = torch.rand(bs, size, size, 1, generator=g)
+    tgt = torch.rand(bs, size, size, 3, generator=g)
+    m = (((xx - 12) ** 2 + (yy - 12) ** 2).float().sqrt() < 9).float()[None, :, :, None].expand(bs, -1, -1, -1).contiguous()
+    return rgba, normal, gate, tgt, mopt.min_pool(m), (m * 0.96 + 0.02), torch.tensor([0.7, 1.3][:bs])
+
+
+@pytest.mark.parametrize('with_patch', [False, True])
+def test_fused_mesh_objective_matches_the_eager_composition(with_patch):
+    """csrc/mesh_loss.cu (through the host harness) against the torch ops + autograd it replaces: value and d/d(rgba, normal)."""
+    rgba0, normal0, gate, tgt, m_erode, m_blur, w_view = _objective_inputs()
+    bs, size = rgba0.shape[0], rgba0.shape[1]
+    nbg = [0.5, 0.5, 1.0]
+    ps, patch_w, reg_w = 8, 0.7, 0.1
+    pl = _FakePatchLoss()
+    pick = torch.tensor([4, 11, 0])
+    w_px = w_view[:, None, None, None].expand(-1, size, size, 1)
+    w_pick = mopt._patches(w_px, size, ps)[pick, 0, 0, 0]
+    n_px = bs * size * size
+    res = {}
+    with host_harness.routed(mopt):
+        for mode in ('fused', 'eager'):
+            rgba, normal = rgba0.clone().requires_grad_(True), normal0.clone().requires_grad_(True)
+            if mode == 'fused':
+                val = mopt._MeshObjectiveFn.apply(rgba, normal, gate.squeeze(-1), tgt, m_erode.squeeze(-1), m_blur.squeeze(-1), w_view, nbg,
+                                                  1.2 * 4.5 / (n_px * 3), 1.2 * 2.0 / n_px, reg_w * 2 / (n_px * 3),
+                                                  (pl, pick, ps, w_pick, patch_w) if with_patch else None)
+            else:
+                a = rgba[..., 3:]
+                rgb = rgba[..., :3] / a.clamp(min=1e-3)
+                rgb = rgb * m_erode + tgt * (1 - m_erode)
+                n = normal * gate + normal.detach() * (1 - gate)
+                nfg = (n - torch.tensor(nbg) * (1 - a)) / a.clamp(min=1e-3)
+                l1 = L1LossMod(loss_weight=1.2)
+                val = l1(rgb, tgt, weight=w_px) * 4.5 + l1(a, m_blur, weight=w_px) * 2.0 \
+                    + mopt.tv_normal_loss(nfg.permute(0, 3, 1, 2), a.detach().permute(0, 3, 1, 2)) * (reg_w * 2)
+                if with_patch:
+                    val = val + mopt.lpips_patch_loss(pl, mopt._patches(rgb, size, ps)[pick], mopt._patches(tgt, size, ps)[pick], w_pick) * patch_w
+            (val * 1.7).backward()
+            res[mode] = (val.detach(), rgba.grad.clone(), normal.grad.clone())
+    f, e = res['fused'], res['eager']
+    assert abs(float(f[0]) - float(e[0])) < 1e-5 * max(1.0, abs(float(e[0])))
+    for a_, b_ in zip(f[1:], e[1:]):
+        assert b_.abs().max() > 0 and (a_ - b_).abs().max() <= 1e-4 * b_.abs().max() + 1e-9
+
+
+def test_mesh_optim_with_the_fused_objective_matches_the_eager_one():
+    n, size, steps, ps = 2, 32, 2, 16
+    poses, intr = _cameras(n, size, seed=2)
+    lights = torch.nn.functional.normalize(torch.randn(n, 3, generator=torch.Generator().manual_seed(4)), dim=-1)
+    cam_weights = torch.tensor([1.0, 2.0])
+    yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing='ij')
+    disc = (((xx - 15.5) ** 2 + (yy - 15.5) ** 2).float().sqrt() < 9).float()
+    tgt_masks = disc[None, None, :, :, None].expand(1, n, -1, -1, -1).contiguous()
+    tgt_images = (torch.rand(1, n, size, size, 3, generator=torch.Generator().manual_seed(5)) * 0.5 + 0.25) * tgt_masks + (1 - tgt_masks)
+    g = torch.Generator().manual_seed(6)
+    noise = dict(camera_perm=torch.tensor([1, 0]), jitter=torch.rand(steps, 2, 2, generator=g),
+                 patch_perm=torch.stack([torch.randperm(n * (size // ps) ** 2, generator=g) for _ in range(steps)]))
+    grid = make_tet_grid(10)
+    res = {}
+    with host_harness.routed(mopt):
+        for fused in (True, False):
+            field = ToyField()
+            nerf = SimpleNamespace(decoder=field, pixel_loss=L1LossMod(loss_weight=1.2), patch_loss=_FakePatchLoss())
+            tet_verts, tet_indices, tet_sdf = mopt.init_tet(nerf, None, density_thresh=5.0, tets=grid)
+            deform = torch.zeros_like(tet_verts).requires_grad_(True)
+            tet_sdf.requires_grad_(True)
+            opt = torch.optim.Adam([{'params': list(field.parameters())}, {'params': [tet_sdf, deform], 'lr': 1e-3}], lr=0.01)
+            dm = DMTet('cpu')
+            with torch.enable_grad():
+                mv, mf = dm(tet_verts + deform, tet_sdf, tet_indices)
+                mesh = Mesh(v=mv, f=mf.int())
+                mesh.auto_normal()
+            pipe = SimpleNamespace(nerf=nerf, mesh_renderer=MeshRenderer(near=0.01, far=100), normal_bg=[0.5, 0.5, 1.0], tonemapping=None)
+            mopt.mesh_optim(pipe, tgt_images, tgt_masks, None, opt, 0.01, 0.8, steps, 2, 3, 24, 0.7, 0.0, 0.02, 0.1, 5.0, None,
+                            tet_verts, deform, tet_sdf, tet_indices, dm, mesh, size, intr, size, poses, cam_weights, lights, ps,
+                            False, 0.2, 1.0, noise=noise, fused_objective=fused)
+            res[fused] = (tet_sdf.detach().clone(), deform.detach().clone(), field.w.detach().clone())
+    for a_, b_ in zip(res[True], res[False]):
+        assert (a_ - b_).abs().max() < 2e-5
