@@ -799,6 +799,25 @@ def mesh_microbench(device, pk, V=6, S=1024, R=96):
     if 'mve_antialias_fwd' in calls:
         gbs = npx * (3 * 8 * 4 + 16) / m(calls['mve_antialias_fwd']) / 1e6
         out.update(antialias_gbs=round(gbs, 1), antialias_frac_hbm=round(gbs / pk['hbm_gbs'], 3))
+    try:        # the per-topology edge table antialias needs: stable sort (default) vs the opt-in hash kernel, same result required
+        from mvedit_b200 import mesh_raster as dr
+
+        def t_of(fn, reps=5):
+            fn()
+            torch.cuda.synchronize()
+            a, b = ev(), ev()
+            a.record()
+            for _ in range(reps):
+                r = fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps, r
+        faces = mesh.f.detach()
+        ts, o_sort = t_of(lambda: dr.edge_opposites(faces))
+        th, o_hash = t_of(lambda: dr.edge_opposites(faces, method='hash'))
+        out['edge_topology'] = dict(sort_ms=round(ts, 4), hash_ms=round(th, 4), identical=bool(torch.equal(o_sort, o_hash)))
+    except Exception as e:
+        out['edge_topology'] = dict(error=repr(e)[:300])
     return out
 
 

@@ -445,6 +445,13 @@ int mve_mesh_loss_backward(const float* rgba, const float* tgt_rgb, const float*
                            float c_tv, const float* nfg, const float* g_rgb_extra, float* g_nfg, float* loss, float* g_rgba,
                            float* g_normal, void* stream);
 
+/* opp [F,3] of mve_antialias_* by hashing instead of sorting (opt-in; mvedit_b200.mesh_raster.edge_opposites(method='hash')): the
+ * undirected edges of the 3F (triangle, edge) entries go into an open-addressing table of `slots` 64-bit keys (a power of two
+ * >= 6 F; keys [slots] u64, first / second [slots] u32, slot_of [3F] u32 are scratch), the two smallest entry indices per edge pair
+ * up -- the same rule as the stable sort, so both methods return the same table.  Vertex indices must be >= 0. */
+int mve_edge_opposites(const int32_t* tri, uint32_t F, uint32_t slots, void* keys, uint32_t* first, uint32_t* second,
+                       uint32_t* slot_of, int32_t* opp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

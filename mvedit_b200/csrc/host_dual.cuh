@@ -22,6 +22,8 @@ static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline void atomic_add_f(float* p, float v) { *p += v; }
 static inline void atomic_min_u64(unsigned long long* p, unsigned long long v) { if (v < *p) *p = v; }
 static inline uint32_t atomic_inc_u32(uint32_t* p) { return (*p)++; }
+static inline void atomic_min_u32(uint32_t* p, uint32_t v) { if (v < *p) *p = v; }
+static inline unsigned long long atomic_cas_u64(unsigned long long* p, unsigned long long cmp, unsigned long long v) { unsigned long long o = *p; if (o == cmp) *p = v; return o; }
 #define MVE_ELEMENT_KERNEL(kname, P, fn) static void kname(const P& p, uint32_t n) { for (uint32_t i = 0; i < n; ++i) fn(p, i); }
 // a per-element function that also accumulates K partial sums into p.field[0..K): fn(p, i, acc)
 #define MVE_REDUCE_KERNEL(kname, P, fn, K, field)                                          \
@@ -41,6 +43,8 @@ __device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
 __device__ __forceinline__ void atomic_add_f(float* p, float v) { atomicAdd(p, v); }
 __device__ __forceinline__ void atomic_min_u64(unsigned long long* p, unsigned long long v) { atomicMin(p, v); }
 __device__ __forceinline__ uint32_t atomic_inc_u32(uint32_t* p) { return atomicAdd(p, 1u); }
+__device__ __forceinline__ void atomic_min_u32(uint32_t* p, uint32_t v) { atomicMin(p, v); }
+__device__ __forceinline__ unsigned long long atomic_cas_u64(unsigned long long* p, unsigned long long cmp, unsigned long long v) { return atomicCAS(p, cmp, v); }
 #define MVE_ELEMENT_KERNEL(kname, P, fn)                                                  \
     __global__ void __launch_bounds__(256) kname(const P p, uint32_t n) {                 \
         uint32_t i = blockIdx.x * 256u + threadIdx.x;                                     \

@@ -509,6 +509,59 @@ MVE_HD void tex_mip_fold(const TexP& p, uint32_t i) {
     p.g_pyr[p.off[l - 1] + i] += 0.25f * g;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// edge topology by hashing (opt-in alternative to the stable sort of mesh_raster.edge_opposites): every (triangle, edge) entry
+// e = 3 f + k inserts its undirected edge key into an open-addressing table, the two smallest entry indices of every key are kept with
+// atomicMin (deterministic: "the first two users in (f, k) order pair up, later users see the first", exactly the sort's rule), and a
+// last pass writes the partner's opposite vertex.  Three launches over 3F entries instead of a radix sort of 3F 64-bit keys.
+struct TopoP {
+    const int32_t* tri;
+    uint32_t n_entries, mask;   // mask = slots - 1, slots a power of two >= 2 * n_entries
+    unsigned long long* keys;   // [slots], 0xFF.. = empty
+    uint32_t* first;            // [slots] smallest entry index of the key
+    uint32_t* second;           // [slots] second smallest
+    uint32_t* slot_of;          // [n_entries]
+    int32_t* opp;               // [F, 3]
+};
+
+MVE_HD unsigned long long edge_key(const TopoP& p, uint32_t e) {
+    uint32_t f = e / 3, k = e - f * 3;
+    uint32_t a = (uint32_t)p.tri[f * 3 + (k + 1) % 3], b = (uint32_t)p.tri[f * 3 + (k + 2) % 3];
+    return ((unsigned long long)(a < b ? a : b) << 32) | (unsigned long long)(a < b ? b : a);
+}
+
+MVE_HD void topo_insert(const TopoP& p, uint32_t e) {
+    unsigned long long key = edge_key(p, e);
+    uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & p.mask;
+    for (;;) {
+        unsigned long long prev = atomic_cas_u64(p.keys + slot, ~0ull, key);
+        if (prev == ~0ull || prev == key) break;
+        slot = (slot + 1) & p.mask;
+    }
+    p.slot_of[e] = slot;
+    atomic_min_u32(p.first + slot, e);
+}
+
+MVE_HD void topo_second(const TopoP& p, uint32_t e) {
+    uint32_t slot = p.slot_of[e];
+    if (p.first[slot] != e) atomic_min_u32(p.second + slot, e);
+}
+
+MVE_HD void topo_resolve(const TopoP& p, uint32_t e) {
+    uint32_t slot = p.slot_of[e], m0 = p.first[slot], m1 = p.second[slot];
+    int32_t o = -1;
+    if (m1 != 0xffffffffu) {
+        uint32_t partner = (e == m0) ? m1 : m0;
+        o = p.tri[partner];                                   // entry 3 f' + k' IS the flat index of vertex k' of triangle f'
+    }
+    p.opp[e] = o;
+}
+
+MVE_ELEMENT_KERNEL(k_topo_insert, TopoP, topo_insert)
+MVE_ELEMENT_KERNEL(k_topo_second, TopoP, topo_second)
+MVE_ELEMENT_KERNEL(k_topo_resolve, TopoP, topo_resolve)
+
 // ------------------------------------------------------------------------------------------------------------------------------
 MVE_ELEMENT_KERNEL(k_raster_tris, RasterP, raster_tri)
 MVE_ELEMENT_KERNEL(k_raster_resolve, RasterP, raster_resolve)
@@ -666,5 +719,23 @@ MVE_EXPORT int mve_texture_bwd(uint32_t Bt, uint32_t th, uint32_t tw, uint32_t C
         p.level = l;
         MVE_LAUNCH(k_texture_mip_fold, p, Bt * (th >> (l - 1)) * (tw >> (l - 1)) * C, stream);
     }
+    return 0;
+}
+
+/* ---- edge topology --------------------------------------------------------------------------------------------------------------- */
+MVE_EXPORT int mve_edge_opposites(const int32_t* tri, uint32_t F, uint32_t slots, void* keys, uint32_t* first, uint32_t* second,
+                                  uint32_t* slot_of, int32_t* opp, void* stream) {
+    if (F == 0) return 0;
+    MVE_ARG(tri && keys && first && second && slot_of && opp, "mve_edge_opposites: NULL pointer");
+    MVE_ARG(F < (1u << 30) / 3 && slots >= 6 * F && (slots & (slots - 1)) == 0, "mve_edge_opposites: slots must be a power of two >= 6 F");
+    TopoP p = {};
+    p.tri = tri; p.n_entries = 3 * F; p.mask = slots - 1; p.keys = (unsigned long long*)keys; p.first = first; p.second = second;
+    p.slot_of = slot_of; p.opp = opp;
+    MVE_MEMSET(keys, 0xff, (size_t)slots * 8, stream);
+    MVE_MEMSET(first, 0xff, (size_t)slots * 4, stream);
+    MVE_MEMSET(second, 0xff, (size_t)slots * 4, stream);
+    MVE_LAUNCH(k_topo_insert, p, 3 * F, stream);
+    MVE_LAUNCH(k_topo_second, p, 3 * F, stream);
+    MVE_LAUNCH(k_topo_resolve, p, 3 * F, stream);
     return 0;
 }

@@ -50,10 +50,14 @@ def _i32c(t):
     return t.detach().to(torch.int32).contiguous()
 
 
-def edge_opposites(tri):
+def edge_opposites(tri, method='sort'):
     """opp [F,3] int32: for the edge facing vertex k of triangle f, the vertex of the adjacent triangle that is not on the edge
     (-1 on an open edge) -- the topology ``antialias`` needs to tell silhouette edges from interior ones.  One stable sort of the
-    3F edge keys; edges used by more than two triangles pair their first two users, later users see the first."""
+    3F edge keys; edges used by more than two triangles pair their first two users, later users see the first.
+    ``method='hash'`` (opt-in): the same table from three launches of an open-addressing hash kernel instead of the sort
+    (``mve_edge_opposites``; CPU-checked against this function, timed by bench.py's mesh child process)."""
+    if method == 'hash':
+        return _edge_opposites_hash(tri)
     t = tri.detach().long()
     F = t.shape[0]
     if F == 0:
@@ -77,6 +81,21 @@ def edge_opposites(tri):
     opp = torch.empty(n, dtype=torch.long, device=t.device)
     opp[order] = opp_sorted
     return opp.reshape(F, 3).to(torch.int32)
+
+
+def _edge_opposites_hash(tri):
+    tri_c = _i32c(tri)
+    F = tri_c.shape[0]
+    dev = tri_c.device
+    opp = torch.empty(F, 3, dtype=torch.int32, device=dev)
+    if F == 0:
+        return opp
+    slots = 1 << max(int(6 * F - 1).bit_length(), 4)
+    keys = torch.empty(slots, dtype=torch.int64, device=dev)
+    first, second = torch.empty(slots, dtype=torch.int32, device=dev), torch.empty(slots, dtype=torch.int32, device=dev)
+    slot_of = torch.empty(3 * F, dtype=torch.int32, device=dev)
+    call('mve_edge_opposites', ptr(tri_c), c_u32(F), c_u32(slots), ptr(keys), ptr(first), ptr(second), ptr(slot_of), ptr(opp), stream())
+    return opp
 
 
 class _RasterizeFn(torch.autograd.Function):

@@ -286,3 +286,16 @@ def test_empty_face_list_is_rendered_as_an_empty_image():
     assert (out == 0).all() and torch.equal(aa, col)
     (out.sum() + aa.sum() + rast.sum()).backward()
     assert (attr.grad == 0).all() and (pos.grad == 0).all() and (col.grad == 1).all()
+
+
+def test_hash_edge_topology_equals_the_sorted_one():
+    rng = np.random.default_rng(5)
+    cases = [synth_mesh.icosphere(2)[1], synth_mesh.icosphere(3)[1][:-7]]                          # closed; with open edges
+    cases.append(np.concatenate([synth_mesh.icosphere(1)[1], synth_mesh.icosphere(1)[1][:9]]))      # edges with three and four users
+    cases += [rng.integers(0, 40, (int(rng.integers(1, 300)), 3)) for _ in range(6)]                # soups incl. degenerate edges (a == b)
+    for f in cases:
+        t = torch.from_numpy(np.asarray(f).astype(np.int32))
+        a, b = dr.edge_opposites(t), dr.edge_opposites(t, method='hash')
+        assert a.dtype == b.dtype == torch.int32 and torch.equal(a, b)
+        np.testing.assert_array_equal(a.numpy(), ro.edge_opposites(np.asarray(f)))
+    assert dr.edge_opposites(torch.zeros(0, 3, dtype=torch.int32), method='hash').shape == (0, 3)
