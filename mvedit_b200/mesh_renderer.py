@@ -239,14 +239,15 @@ def make_tet_grid(resolution, device='cpu'):
 # ---- MeshRenderer (base_mesh_renderer.py:191-395) -------------------------------------------------------------------------------
 
 def make_divisible(x, m=8):
-    return int(math.ceil(x / m) * m)
+    """Smallest multiple of ``m`` not below ``x`` (``base_mesh_renderer.py:11-12``)."""
+    return m * int(math.ceil(x / m))
 
 
 def interpolate_hwc(x, scale_factor, mode='area'):
-    batch_dim = x.shape[:-3]
-    y = x.reshape(batch_dim.numel(), *x.shape[-3:]).permute(0, 3, 1, 2)
-    y = F.interpolate(y, scale_factor=scale_factor, mode=mode).permute(0, 2, 3, 1)
-    return y.reshape(*batch_dim, *y.shape[1:])
+    """``F.interpolate`` on channel-last maps [..., h, w, c] (``base_mesh_renderer.py:15-19``; the renderer's ssaa down-sampling)."""
+    lead, (h, w, c) = x.shape[:-3], x.shape[-3:]
+    out = F.interpolate(x.reshape(-1, h, w, c).movedim(-1, 1), scale_factor=scale_factor, mode=mode).movedim(1, -1)
+    return out.reshape(*lead, *out.shape[1:])
 
 
 def min_pool(x_nhwc, k=5):
@@ -309,14 +310,13 @@ class MeshRenderer(nn.Module):
         """OpenCV c2w poses [..., 3, 4] and (fx, fy, cx, cy) -> (camera rotation with the y / z columns flipped to OpenGL, proj [..., 4, 4])
         (``:222-232``)."""
         r_mat_c2w = torch.cat([poses[..., :3, :1], -poses[..., :3, 1:3]], dim=-1)
-        proj = poses.new_zeros(poses.shape[:-2] + (4, 4))
-        proj[..., 0, 0] = 2 * intrinsics[..., 0] / w
-        proj[..., 0, 2] = -2 * intrinsics[..., 2] / w + 1
-        proj[..., 1, 1] = -2 * intrinsics[..., 1] / h
-        proj[..., 1, 2] = -2 * intrinsics[..., 3] / h + 1
-        proj[..., 2, 2] = -(self.far + self.near) / (self.far - self.near)
-        proj[..., 2, 3] = -(2 * self.far * self.near) / (self.far - self.near)
-        proj[..., 3, 2] = -1
+        fx, fy, cx, cy = intrinsics.unbind(-1)
+        zero, one = torch.zeros_like(fx), torch.ones_like(fx)
+        a, b = -(self.far + self.near) / (self.far - self.near), -(2 * self.far * self.near) / (self.far - self.near)
+        proj = torch.stack([2 * fx / w, zero, 1 - 2 * cx / w, zero,
+                            zero, -2 * fy / h, 1 - 2 * cy / h, zero,          # the row flip: image row 0 is the top
+                            zero, zero, a * one, b * one,
+                            zero, zero, -one, zero], dim=-1).reshape(intrinsics.shape[:-1] + (4, 4)).to(poses.dtype)
         return r_mat_c2w, proj
 
     def forward(self, meshes, poses, intrinsics, h, w, shading_fun=None, dilate_edges=0, normal_bg=[0.5, 0.5, 1.0], aa=True, render_vc=False):
