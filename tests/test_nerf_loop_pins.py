@@ -1,0 +1,37 @@
+"""``oracle/nerf_oracle.nerf_optim`` -- the restated reconstruction loop the GPU parity tests hold the product to -- against THE
+REFERENCE'S OWN ``nerf_optim`` code: tests/golden/make_nerf_loop_pins.py ran mvedit_3d_pipeline.py:452-656 unmodified (cut out by AST)
+on the same oracle stack (C ray-marching restatement, plain-torch hash grid) with the same draws; four iterations incl. two occupancy
+refreshes and a patch term.  CPU."""
+import importlib.util
+import os
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+spec = importlib.util.spec_from_file_location('make_nerf_loop_pins', os.path.join(HERE, 'golden', 'make_nerf_loop_pins.py'))
+gen = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(gen)
+PINS = np.load(os.path.join(HERE, 'golden', 'nerf_loop_pins.npz'))
+
+
+def test_oracle_nerf_optim_matches_the_reference_method():
+    from oracle import nerf_oracle as no
+    poses, intr, images, masks, cam_w, cam_lights, draws = gen.scene()
+    dec = gen.make_field()
+    p0 = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    nerf = no.OracleNeRF(dec, grid_size=gen.GRID, patch_size=gen.PS, update_extra_interval=2)
+    nerf.patch_loss = gen.WeightedMSE()
+    density_grid = torch.zeros(1, gen.GRID ** 3, dtype=torch.float16)
+    density_bitfield = torch.full((1, gen.GRID ** 3 // 8), 255, dtype=torch.uint8)
+    opt = torch.optim.Adam(dec.parameters(), lr=0.01)
+    per_batch = gen.N_RAYS // gen.PS ** 2
+    no.nerf_optim(nerf, images, masks, None, opt, 0.01, gen.ITERS, gen.N_RAYS, 0.4, 0.0, 0.02, 0.1, 0.01, [None], density_grid, density_bitfield,
+                  gen.RS, intr, gen.RS, poses, cam_w, cam_lights, gen.PS, False, 0.015, 0.2, 1.0, False,
+                  raybatch_inds=list(draws['raybatch'].split(per_batch, dim=1)), march_noises=draws['march'], grid_noises=draws['grid'])
+    for k, v in dec.state_dict().items():
+        ref = torch.from_numpy(PINS['p1_' + k])
+        assert (v.detach() - ref).abs().max() <= 2e-5 + 1e-4 * ref.abs().max(), k
+    assert max(float((dec.state_dict()[k] - p0[k]).abs().max()) for k in p0) > 1e-2              # four Adam steps did move the field
+    np.testing.assert_allclose(density_grid.float().numpy(), PINS['grid1'].astype(np.float32), rtol=2e-3, atol=1e-3)
+    assert (density_bitfield.numpy() == PINS['bits1']).mean() > 0.999
