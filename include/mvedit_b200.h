@@ -310,6 +310,24 @@ int mve_nerf_patch_loss(const float* image, const float* alpha, const float* dep
                         const float* w_alpha_mul, const float* w_normal_reg, const float* w_entropy,
                         float* scratch, float* g_image, float* g_alpha, float* g_depth, float* loss5, const float* g_out_extra,
                         const float* tonemap_knots, uint32_t tonemap_n, void* stream);
+/* The same objective with the optional targets of image-to-3D runs (mvedit_3d_pipeline.py:462-463; every pointer may be NULL):
+ *   tgt_normal [N,3]      opengl normals in [0,1] (:518-519, :527): the TV term becomes diff(normal_fg) - diff(tgt_normal) (:582-585,
+ *                         lib/models/losses/tv_loss.py:27)
+ *   g_normal_extra [N,3]  gradient of further terms w.r.t. out_normal = normal_fg * alpha + normal_bg * (1 - alpha) (:553-554) -- the
+ *                         high-passed normal patch term (:619-626), evaluated by the caller on mve_nerf_patch_out_normal's output
+ *   tgt_depth [N]         target 1/z (:520-521, :529): L1 on depth * |dir| weighted like the rgb term, x w_depth[0] (device scalar,
+ *                         depth_weight); its value is written to loss_depth[0] and added to loss5[0] (:586-592) */
+int mve_nerf_patch_loss_targets(const float* image, const float* alpha, const float* depth, const float* tgt_rgb, const float* tgt_mask,
+                                const float* dirs, const float* patch_w, const float* lights, uint32_t n_patches, uint32_t patch_size,
+                                int shaded, float ambient, float bg_color, float bg_width, float pixel_loss_weight,
+                                const float* w_alpha_mul, const float* w_normal_reg, const float* w_entropy, float* scratch, float* g_image,
+                                float* g_alpha, float* g_depth, float* loss5, const float* g_out_extra, const float* tonemap_knots,
+                                uint32_t tonemap_n, const float* tgt_normal, const float* g_normal_extra, float normal_bg_x,
+                                float normal_bg_y, float normal_bg_z, const float* tgt_depth, const float* w_depth, float* loss_depth,
+                                void* stream);
+/* out_normal [N,3]: depth -> normal_fg (geometry_utils.depth_to_normal :119-148) composited over normal_bg with alpha (:553-554). */
+int mve_nerf_patch_out_normal(const float* alpha, const float* depth, const float* dirs, uint32_t n_patches, uint32_t patch_size,
+                              float normal_bg_x, float normal_bg_y, float normal_bg_z, float* scratch, float* out_normal, void* stream);
 /* out_rgb [N,3]: what the pixel and patch losses compare with the target (mvedit_3d_pipeline.py:558-571); same scratch. */
 int mve_nerf_patch_out_rgb(const float* image, const float* alpha, const float* depth, const float* dirs, const float* lights,
                            uint32_t n_patches, uint32_t patch_size, int shaded, float ambient, float bg_color, float* scratch,

@@ -7,8 +7,9 @@ kernels, the hash-grid field kernel at the visible surface points), the objectiv
 kernels, one fused Adam step over (field parameters | sdf, deform), marching-tets re-extraction.  The objective's elementwise glue is
 torch autograd over those kernels (the NeRF stage has it fused in ``nerf_loss.cu``; the mesh stage's version is not fused yet).
 
-Not built (raise): target normals (``use_normal``: the normal model is absent), mesh simplification at the last step
-(``mesh_reduction < 1`` needs open3d's quadric decimation, ``:829-844``).
+Target normals (``tgt_normals``: TV term against the target's differences, geometry lr without the multiplier, high-passed normal
+patch term) are covered by the eager composition.  Not built (raises): mesh simplification at the last step (``mesh_reduction < 1``
+needs open3d's quadric decimation, ``:829-844``).
 """
 import ctypes
 import os
@@ -19,7 +20,7 @@ import torch.nn.functional as F
 
 from .mesh_renderer import (DMTet, Mesh, laplacian_smooth_loss, make_tet_grid, min_pool, normal_consistency,   # noqa: F401  (re-exported)
                             view_cosine)
-from .nerf import blur_masks, pixel_directions
+from .nerf import blur_masks, highpass, pixel_directions
 from ._lib import call, ptr, stream, c_u32, c_f32
 from . import view_shard
 
@@ -223,8 +224,8 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
 
     ``fused_objective`` (default: ``self.mesh_fused_objective`` if set, else False): the per-pixel loss terms and their gradient as three
     launches of ``csrc/mesh_loss.cu`` instead of ~60 eager torch ops + autograd (same values; CPU-checked, not yet run on a GPU)."""
-    if tgt_normals is not None:
-        raise NotImplementedError('mesh_optim: target normals need the normal model, which is not built')
+    use_normal = tgt_normals is not None                          # :667
+    use_pn = use_normal and patch_normal_weight > 0               # :806
     if mesh_reduction < 1 and is_end:
         raise NotImplementedError('mesh_optim: mesh simplification (open3d quadric decimation) is not built; use mesh_reduction=1')
     nerf, dec = self.nerf, self.nerf.decoder
@@ -245,19 +246,22 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
     shared = (lambda t: _from_rank0(t)) if world > 1 else (lambda t: t)
     if fused_objective is None:
         fused_objective = bool(getattr(self, 'mesh_fused_objective', False))
+    if fused_objective and use_normal:
+        raise NotImplementedError('mesh_optim: the fused objective kernels (mesh_loss.cu) do not take target normals; use fused_objective=False')
     try:
         with torch.enable_grad():
             if fused:
                 optimizer.set_lr(lr, group=0)
-                optimizer.set_lr(lr * 0.04 * lr_multiplier, group=1)
+                optimizer.set_lr(lr * (0.04 if use_normal else 0.04 * lr_multiplier), group=1)          # :688
             else:
                 optimizer.param_groups[0]['lr'] = lr
-                optimizer.param_groups[1]['lr'] = lr * 0.04 * lr_multiplier
+                optimizer.param_groups[1]['lr'] = lr * (0.04 if use_normal else 0.04 * lr_multiplier)
             camera_perm = noise['camera_perm'].to(device) if 'camera_perm' in noise else shared(torch.randperm(n_views, device=device))
             split = lambda x: x[camera_perm].split(render_bs, dim=0)
             pose_b, intr_b = split(camera_poses), split(intrinsics)
             img_b, mask_b, blur_b = split(tgt_images.squeeze(0)), split(tgt_masks.squeeze(0)), split(tgt_masks_blur)
             dir_b, w_b, light_b = split(directions), split(cam_weights), split(lights)
+            nrm_b = split(tgt_normals.squeeze(0)) if use_normal else None
             nb = len(pose_b)
             if is_end:
                 inverse_steps = max(inverse_steps, mesh_simplify_texture_steps)
@@ -283,12 +287,13 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
                     gate = view_cosine_gate(render_out['depth'].squeeze(0).detach(), target_dir)
                     wgt = target_w / cam_weights_mean
                     grid_n = render_size // patch_size
-                    if patch_rgb_weight > 0:                     # which patches the LPIPS term looks at (:793)
+                    def draw(key):                               # which patches an LPIPS term looks at (:793, :813)
                         if world > 1:                            # each rank draws its share of the patches among its own views
-                            pick = torch.randperm((hi - lo) * grid_n * grid_n, device=device)[:max(patch_bs * (hi - lo) // bs, 1)]
-                        else:
-                            perm = noise['patch_perm'][step].to(device) if 'patch_perm' in noise else torch.randperm((hi - lo) * grid_n * grid_n, device=device)
-                            pick = perm[:patch_bs]
+                            return torch.randperm((hi - lo) * grid_n * grid_n, device=device)[:max(patch_bs * (hi - lo) // bs, 1)]
+                        perm = noise[key][step].to(device) if key in noise else torch.randperm((hi - lo) * grid_n * grid_n, device=device)
+                        return perm[:patch_bs]
+                    if patch_rgb_weight > 0 or use_pn:
+                        pick = draw('patch_perm')
                         w_pick = _patches(target_w, render_size, patch_size)[pick, 0, 0, 0] / cam_weights_mean
                     if fused_objective:
                         n_px = (hi - lo) * render_size * render_size
@@ -306,10 +311,16 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
                         out_normals_fg = (out_normals - normal_bg * (1 - out_alphas)) / out_alphas.clamp(min=1e-3)
                         views = nerf.pixel_loss(out_rgbs, target_rgbs, weight=wgt) * 4.5
                         views = views + nerf.pixel_loss(out_alphas, target_m_blur, weight=wgt) * 2.0
-                        views = views + tv_normal_loss(out_normals_fg.permute(0, 3, 1, 2), out_alphas.detach().permute(0, 3, 1, 2)) * (normal_reg_weight * 2)
+                        target_n = nrm_b[k][lo:hi] if use_normal else None
+                        views = views + tv_normal_loss(out_normals_fg.permute(0, 3, 1, 2), out_alphas.detach().permute(0, 3, 1, 2),
+                                                       target=target_n.permute(0, 3, 1, 2) if use_normal else None) * (normal_reg_weight * 2)
                         if patch_rgb_weight > 0:
                             out_p, tgt_p = _patches(out_rgbs, render_size, patch_size), _patches(target_rgbs, render_size, patch_size)
                             views = views + lpips_patch_loss(nerf.patch_loss, out_p[pick], tgt_p[pick], w_pick) * patch_rgb_weight
+                        if use_pn:        # high-passed normal patch term (:806-821): its own patch draw, the rgb draw's weights (as the reference)
+                            pick_n = draw('patch_perm_normal')
+                            out_np, tgt_np = _patches(out_normals, render_size, patch_size), _patches(target_n, render_size, patch_size)
+                            views = views + lpips_patch_loss(nerf.patch_loss, highpass(out_np[pick_n]), highpass(tgt_np[pick_n]), w_pick) * patch_normal_weight
                     loss = loss + views * share
 
                 optimizer.zero_grad()

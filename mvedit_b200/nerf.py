@@ -9,8 +9,10 @@ shading is libmvedit_b200.  The op-by-op torch restatements of the reference (ge
 live in ``oracle/nerf_oracle.py`` as test infrastructure; nothing here falls back to them.
 
 The objective covers L1 rgb / alpha, TV-normal, entropy, the LPIPS patch term (``nerf.patch_loss`` = mvedit_b200.lpips.LPIPSLoss) and
-shading in tone-mapped space (``tonemapping``).  Target normals / depths (they need the normal model, a neighbour that is not built)
-raise ``NotImplementedError``: there is no eager fallback path.
+shading in tone-mapped space (``tonemapping``), and the optional targets of image-to-3D runs: target normals inside the TV term, the
+L1 term on 1/z against target depths (both inside ``mve_nerf_patch_loss_targets``) and the high-passed normal patch term (LPIPS on
+``mve_nerf_patch_out_normal``'s output; the 31-tap Gaussian of the high-pass is two depthwise torch convolutions).  There is no eager
+fallback path.
 """
 import collections
 import os
@@ -48,6 +50,11 @@ def blur_masks(x, kernel_size, sigma):
     c = x.shape[1]
     x = F.conv2d(F.pad(x, (r, r, 0, 0), mode='reflect'), k.view(1, 1, 1, -1).expand(c, 1, 1, -1), groups=c)
     return F.conv2d(F.pad(x, (0, 0, r, r), mode='reflect'), k.view(1, 1, -1, 1).expand(c, 1, -1, 1), groups=c)
+
+
+def highpass(x, std=5, offset=0.5):
+    """lib/pipelines/utils.py:187-188 on NCHW: offset + x - gaussian_blur(x, 6 round(std) + 1, std)."""
+    return offset + x - blur_masks(x, int(round(std)) * 6 + 1, std)
 
 
 class L1LossMod(nn.Module):
@@ -153,22 +160,47 @@ class BaseNeRF(nn.Module):
 
 
 def patch_loss(image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights, ps, shaded, ambient, bg_color, bg_width,
-               pixel_loss_weight, w_alpha_mul, w_normal_reg, w_entropy, tonemapping=None, g_out_extra=None):
+               pixel_loss_weight, w_alpha_mul, w_normal_reg, w_entropy, tonemapping=None, g_out_extra=None,
+               tgt_normal=None, g_normal_extra=None, normal_bg=(0.5, 0.5, 1.0), tgt_depth=None, w_depth=None):
     """Fused objective of one nerf_optim iteration on P patches of ps x ps rays (mve_nerf_patch_loss, four launches):
     -> (loss5 = [total, rgb, alpha, normal_reg, background-entropy], d total / d image [N,3], / d alpha [N], / d depth [N]).
-    w_* are device scalars (schedule dependent; they must stay valid inside a captured graph)."""
+    w_* are device scalars (schedule dependent; they must stay valid inside a captured graph).
+    Optional targets (mve_nerf_patch_loss_targets): ``tgt_normal`` [N,3] inside the TV term, ``g_normal_extra`` [N,3] the gradient of the
+    normal patch term w.r.t. the composited normals, ``tgt_depth`` [N] with the device scalar ``w_depth`` -- then a 6th value, the depth
+    term, is appended to the returned losses."""
     N = alpha.numel()
     P = N // (ps * ps)
     dev = alpha.device
-    f = lambda t: t.detach().float().contiguous()
+    f = lambda t: None if t is None else t.detach().float().contiguous()
     scratch = torch.empty(N * 10, dtype=torch.float32, device=dev)
     g_image, g_alpha, g_depth = torch.empty(N, 3, device=dev), torch.empty(N, device=dev), torch.empty(N, device=dev)
-    loss5 = torch.empty(5, dtype=torch.float32, device=dev)
-    call('mve_nerf_patch_loss', ptr(f(image).view(N, 3)), ptr(f(alpha).view(N)), ptr(f(depth).view(N)), ptr(f(tgt_rgb)), ptr(f(tgt_mask)),
-         ptr(f(dirs)), ptr(f(patch_w)), ptr(f(lights)), c_u32(P), c_u32(ps), c_int(int(shaded)), c_f32(ambient), c_f32(bg_color),
-         c_f32(bg_width), c_f32(pixel_loss_weight), ptr(w_alpha_mul), ptr(w_normal_reg), ptr(w_entropy), ptr(scratch), ptr(g_image),
-         ptr(g_alpha), ptr(g_depth), ptr(loss5), ptr(g_out_extra), *tone_args(tonemapping), stream())
+    loss5 = torch.empty(6 if tgt_depth is not None else 5, dtype=torch.float32, device=dev)
+    # named references: a converted copy must stay alive until the launches are enqueued
+    image_, alpha_, depth_, trgb, tmsk, dirs_, pw, lt, ge_rgb = (f(t) for t in (image, alpha, depth, tgt_rgb, tgt_mask, dirs, patch_w, lights,
+                                                                                g_out_extra))
+    base = (ptr(image_.view(N, 3)), ptr(alpha_.view(N)), ptr(depth_.view(N)), ptr(trgb), ptr(tmsk), ptr(dirs_), ptr(pw), ptr(lt),
+            c_u32(P), c_u32(ps), c_int(int(shaded)), c_f32(ambient), c_f32(bg_color), c_f32(bg_width), c_f32(pixel_loss_weight),
+            ptr(w_alpha_mul), ptr(w_normal_reg), ptr(w_entropy), ptr(scratch), ptr(g_image), ptr(g_alpha), ptr(g_depth), ptr(loss5),
+            ptr(ge_rgb), *tone_args(tonemapping))
+    if tgt_normal is None and g_normal_extra is None and tgt_depth is None:
+        call('mve_nerf_patch_loss', *base, stream())
+    else:
+        tn, ge, td = f(tgt_normal), f(g_normal_extra), f(tgt_depth)
+        loss_d = loss5[5:] if td is not None else None
+        call('mve_nerf_patch_loss_targets', *base, ptr(tn), ptr(ge), c_f32(normal_bg[0]), c_f32(normal_bg[1]), c_f32(normal_bg[2]),
+             ptr(td), ptr(w_depth if td is not None else None), ptr(loss_d), stream())
     return loss5, g_image, g_alpha, g_depth
+
+
+def patch_out_normal(alpha, depth, dirs, ps, normal_bg=(0.5, 0.5, 1.0)):
+    """-> [N,3] the alpha-composited normal map of P patches (mvedit_3d_pipeline.py:549-554), the input of the normal patch term."""
+    N = alpha.numel()
+    alpha_, depth_, dirs_ = (t.detach().float().contiguous() for t in (alpha, depth, dirs))
+    scratch = torch.empty(N * 10, dtype=torch.float32, device=alpha.device)
+    out = torch.empty(N, 3, dtype=torch.float32, device=alpha.device)
+    call('mve_nerf_patch_out_normal', ptr(alpha_.view(N)), ptr(depth_.view(N)), ptr(dirs_), c_u32(N // (ps * ps)), c_u32(ps),
+         c_f32(normal_bg[0]), c_f32(normal_bg[1]), c_f32(normal_bg[2]), ptr(scratch), ptr(out), stream())
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ nerf_optim
@@ -209,18 +241,17 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
         are all-reduced once per iteration (view_shard.allreduce_grads).
     Returns the per-iteration loss log when ``debug`` else None."""
     device = tgt_images.device
-    if tgt_normals is not None or (tgt_depths is not None and depth_weight > 0):
-        raise NotImplementedError('nerf_optim: target normals / depths are not covered by the fused objective kernels '
-                                  '(mve_nerf_patch_loss); there is no eager fallback')
+    use_normal = tgt_normals is not None              # :462-463
+    use_depth = tgt_depths is not None and depth_weight > 0
+    use_pn = use_normal and patch_normal_weight > 0   # :619
+    use_prgb = patch_rgb_weight > 0
     tone = tone_args(tonemapping)                     # knots by value into the kernels (static: safe inside the captured graph)
-    lpips = nerf.patch_loss if patch_rgb_weight > 0 else None
+    lpips = nerf.patch_loss if (use_prgb or use_pn) else None
     if lpips is not None and not hasattr(lpips, 'loss_and_grad'):
         raise NotImplementedError('nerf_optim: nerf.patch_loss must be a mvedit_b200.lpips.LPIPSLoss (kernels, no autograd graph); got %r'
                                   % type(lpips).__name__)
-    if patch_normal_weight > 0 and tgt_normals is not None:
-        raise NotImplementedError('nerf_optim: the high-passed normal patch term needs target normals (normal_model: not built)')
-    if not tgt_images.is_cuda:
-        raise RuntimeError('mvedit_b200 ops need CUDA tensors (no CPU fallback)')
+    hp = globals()['highpass'] if highpass is None else highpass
+    normal_bg = tuple(float(v) for v in normal_bg)
     ps = nerf.patch_size
     assert patch_size == ps
     dec = nerf.decoder
@@ -247,7 +278,7 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
            float(ambient_light), float(bg_width), float(intrinsics_size), id(optimizer), density_bitfield.data_ptr(), id(nerf_code),
            float(nerf.bg_color), float(nerf.pixel_loss.loss_weight), int(dec.sample_capacity), int(dec.max_steps),
            float(dec.weight_culling_th), bool(dec.mlp_tf32), int(nerf.grid_size), rank, world, id(lpips),
-           None if tonemapping is None else tuple(tonemapping.knots()[0]))
+           None if tonemapping is None else tuple(tonemapping.knots()[0]), use_normal, use_depth, use_pn, use_prgb, normal_bg)
     cache = nerf.__dict__.setdefault('_recon_programs', collections.OrderedDict())
     prog = cache.get(key) if use_graph else None
     if prog is None:
@@ -257,7 +288,9 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
             R=torch.empty(V, 3, 3, **f32), Tr=torch.empty(V, 3, **f32),
             camw=torch.empty(V, **f32), lights=torch.empty(V, 3, **f32), intr=torch.empty(V, 4, **f32),
             sc=dict(normal_reg=torch.zeros((), **f32), entropy=torch.zeros((), **f32), alpha_mul=torch.zeros((), **f32),
-                    patch_rgb=torch.zeros((), **f32)),
+                    patch_rgb=torch.zeros((), **f32), patch_normal=torch.zeros((), **f32), depth=torch.zeros((), **f32)),
+            nrm=torch.empty(1, V, render_size, render_size, 3, **f32) if use_normal else None,
+            dpt=torch.empty(1, V, render_size, render_size, 1, **f32) if use_depth else None,
             inds=torch.zeros(min(n_sel, n_patches_total), dtype=torch.long, device=device), graph=None, vals=None)
         if use_graph:
             cache[key] = prog
@@ -279,6 +312,12 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
         prog['sc']['entropy'].fill_(float(entropy_weight))
         prog['sc']['alpha_mul'].fill_(5.0 if is_init else 1.0)
         prog['sc']['patch_rgb'].fill_(float(patch_rgb_weight))
+        prog['sc']['patch_normal'].fill_(float(patch_normal_weight))
+        prog['sc']['depth'].fill_(float(depth_weight))
+        if use_normal:
+            prog['nrm'].copy_(tgt_normals)
+        if use_depth:
+            prog['dpt'].copy_(tgt_depths)
     R, Tr = prog['R'], prog['Tr']
     sc, inds_static = prog['sc'], prog['inds']
     decoder_training_prev = dec.training
@@ -296,8 +335,11 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
                     trgb=torch.empty(n, 3, **f32), tmsk=torch.empty(n, **f32), pw=torch.empty(P, **f32), pl=torch.empty(P, 3, **f32),
                     dtg=torch.empty(1, **f32), scratch=torch.empty(n * 10, **f32), g_img=torch.empty(n, 3, **f32),
                     g_a=torch.empty(n, **f32), g_d=torch.empty(n, **f32), loss5=torch.empty(5, **f32), out_rgb=torch.empty(n, 3, **f32),
-                    lp=torch.zeros((), **f32))
+                    lp=torch.zeros((), **f32), lpn=torch.zeros((), **f32), ld=torch.zeros(1, **f32),
+                    out_nrm=torch.empty(n, 3, **f32) if use_pn else None)
     b = prog
+    nrm_view = _patch_view(prog['nrm'], ps) if use_normal else None
+    dpt_view = _patch_view(prog['dpt'], ps) if use_depth else None
 
     def iteration():
         # 1. rays of this rank's strip + targets of the full patches: one launch (replaces ray_sample / get_rays / per-patch scalars)
@@ -322,17 +364,40 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
         shaded = int((not is_init) or init_shaded)
         # 4a. LPIPS patch term (:611-617) on the shaded, composited rgb: VGG16 forward over [rendered ; target] patches and the
         # gradient back to the rendered pixels, ~42 launches of the conv / lpips kernels (mvedit_b200.lpips), no autograd graph
-        g_extra = None
-        if lpips is not None:
+        g_extra = g_nextra = tn = td = None
+        if use_prgb:
             call('mve_nerf_patch_out_rgb', ptr(f_img), ptr(f_a), ptr(f_d), ptr(b['pdirs']), ptr(b['pl']), c_u32(P), c_u32(ps), c_int(shaded),
                  c_f32(ambient_light), c_f32(float(nerf.bg_color)), ptr(b['scratch']), ptr(b['out_rgb']), *tone, stream())
             lp, g_extra, _ = lpips.loss_and_grad(b['out_rgb'].view(P, ps, ps, 3), b['trgb'].view(P, ps, ps, 3), b['pw'], sc['patch_rgb'])
             b['lp'].copy_(lp)
+        # 4a'. image-to-3D targets (:517-529): normals / depths of the drawn patches, gathered from the static slots
+        if use_normal:
+            tn = _gather_patches(nrm_view, inds_static)[0].reshape(n, 3).contiguous()
+        if use_depth:
+            td = _gather_patches(dpt_view, inds_static)[0].reshape(n).contiguous()
+        if use_pn:
+            # high-passed normal patch term (:619-626): LPIPS between highpass(composited normals) and highpass(target normals); the
+            # Gaussian of the high-pass is two depthwise torch convolutions, its transpose comes from autograd
+            call('mve_nerf_patch_out_normal', ptr(f_a), ptr(f_d), ptr(b['pdirs']), c_u32(P), c_u32(ps), c_f32(normal_bg[0]),
+                 c_f32(normal_bg[1]), c_f32(normal_bg[2]), ptr(b['scratch']), ptr(b['out_nrm']), stream())
+            x = b['out_nrm'].view(P, ps, ps, 3).permute(0, 3, 1, 2).detach().requires_grad_(True)
+            hx = hp(x)
+            ht = hp(tn.view(P, ps, ps, 3).permute(0, 3, 1, 2))
+            lpn, g_hx, _ = lpips.loss_and_grad(hx.detach().permute(0, 2, 3, 1).contiguous(), ht.permute(0, 2, 3, 1).contiguous(), b['pw'],
+                                               sc['patch_normal'])
+            g_x, = torch.autograd.grad(hx, x, g_hx.permute(0, 3, 1, 2))
+            g_nextra = g_x.permute(0, 2, 3, 1).reshape(n, 3).contiguous()
+            b['lpn'].copy_(lpn)
         # 4b. objective on the full patches: loss terms and d/d(image, alpha, depth) in four launches (replicated: 16 384 pixels)
-        call('mve_nerf_patch_loss', ptr(f_img), ptr(f_a), ptr(f_d), ptr(b['trgb']), ptr(b['tmsk']), ptr(b['pdirs']), ptr(b['pw']), ptr(b['pl']),
-             c_u32(P), c_u32(ps), c_int(shaded), c_f32(ambient_light), c_f32(float(nerf.bg_color)), c_f32(bg_width),
-             c_f32(float(nerf.pixel_loss.loss_weight)), ptr(sc['alpha_mul']), ptr(sc['normal_reg']), ptr(sc['entropy']), ptr(b['scratch']),
-             ptr(b['g_img']), ptr(b['g_a']), ptr(b['g_d']), ptr(b['loss5']), ptr(g_extra), *tone, stream())
+        base = (ptr(f_img), ptr(f_a), ptr(f_d), ptr(b['trgb']), ptr(b['tmsk']), ptr(b['pdirs']), ptr(b['pw']), ptr(b['pl']),
+                c_u32(P), c_u32(ps), c_int(shaded), c_f32(ambient_light), c_f32(float(nerf.bg_color)), c_f32(bg_width),
+                c_f32(float(nerf.pixel_loss.loss_weight)), ptr(sc['alpha_mul']), ptr(sc['normal_reg']), ptr(sc['entropy']), ptr(b['scratch']),
+                ptr(b['g_img']), ptr(b['g_a']), ptr(b['g_d']), ptr(b['loss5']), ptr(g_extra), *tone)
+        if use_normal or use_depth:
+            call('mve_nerf_patch_loss_targets', *base, ptr(tn), ptr(g_nextra), c_f32(normal_bg[0]), c_f32(normal_bg[1]), c_f32(normal_bg[2]),
+                 ptr(td), ptr(sc['depth'] if use_depth else None), ptr(b['ld'] if use_depth else None), stream())
+        else:
+            call('mve_nerf_patch_loss', *base, stream())
         if world > 1:
             sel = lambda t: t.view(P, ps, ps, -1)[:, row_lo:row_hi].reshape(n_loc, -1)
             g_img, g_a, g_d = sel(b['g_img']), sel(b['g_a']).view(-1), sel(b['g_d']).view(-1)
@@ -397,8 +462,10 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
                 vals = vals_static
             if debug:
                 v = [float(x) for x in vals]
-                lpv = float(prog['lp']) if lpips is not None else 0.0
-                log.append(dict(loss=v[0] + lpv, pixel_rgb=v[1], alpha=v[2], normal_reg=v[3], entropy=v[4], patch_rgb=lpv))
+                lpv = float(prog['lp']) if use_prgb else 0.0
+                lpn = float(prog['lpn']) if use_pn else 0.0
+                log.append(dict(loss=v[0] + lpv + lpn, pixel_rgb=v[1], alpha=v[2], normal_reg=v[3], entropy=v[4], patch_rgb=lpv,
+                                patch_normal=lpn, depth=float(prog['ld']) if use_depth else 0.0))
     dec.grad_sink = None
     dec.note_sample_overflow()
     dec.train(decoder_training_prev)

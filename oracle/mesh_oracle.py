@@ -188,8 +188,12 @@ def mesh_renderer_forward(mesh, poses, intrinsics, h, w, shading_fun=None, norma
 def mesh_optim(decoder, tgt_images, tgt_masks, optimizer, lr, lr_multiplier, inverse_steps, render_bs, patch_bs, patch_rgb_weight,
                alpha_soften, normal_reg_weight, mesh_normal_reg_weight, nerf_code, tet_verts, deform, tet_sdf, tet_indices, dmtet, in_mesh,
                render_size, intrinsics, intrinsics_size, camera_poses, cam_weights, lights, patch_size, ambient_light, noise,
-               pixel_loss=None, patch_loss=None, normal_bg=(0.5, 0.5, 1.0), tonemapping=None, near=0.01, far=100.0):
-    """mvedit_3d_pipeline.py:658-872 without target normals / simplification; ``noise``: camera_perm, jitter [steps, bs, 2], patch_perm."""
+               pixel_loss=None, patch_loss=None, normal_bg=(0.5, 0.5, 1.0), tonemapping=None, near=0.01, far=100.0,
+               tgt_normals=None, patch_normal_weight=0.0):
+    """mvedit_3d_pipeline.py:658-872 without simplification; ``noise``: camera_perm, jitter [steps, bs, 2], patch_perm (and
+    patch_perm_normal for the high-passed normal patch term of ``tgt_normals``)."""
+    from .nerf_oracle import highpass
+    use_normal = tgt_normals is not None
     pixel_loss = pixel_loss or L1LossMod(loss_weight=1.2)
     loss_tv = TVLoss(loss_weight=1.0, power=1.5)
     cam_weights_mean = cam_weights.mean()
@@ -198,13 +202,14 @@ def mesh_optim(decoder, tgt_images, tgt_masks, optimizer, lr, lr_multiplier, inv
     directions = get_ray_directions(render_size, render_size, intrinsics[None] * (render_size / intrinsics_size), norm=False)
     normal_bg_t = tgt_images.new_tensor(list(normal_bg))
     optimizer.param_groups[0]['lr'] = lr
-    optimizer.param_groups[1]['lr'] = lr * 0.04 * lr_multiplier
+    optimizer.param_groups[1]['lr'] = lr * (0.04 if use_normal else 0.04 * lr_multiplier)
     camera_perm = noise['camera_perm']
     sp = lambda x: x[camera_perm].split(render_bs, dim=0)
     pose_batches, intrinsics_batches = sp(camera_poses), sp(intrinsics)
     tgt_image_batches, tgt_mask_batches = sp(tgt_images.squeeze(0)), sp(tgt_masks.squeeze(0))
     tgt_mask_blur_batches, tgt_dir_batches = sp(tgt_masks_blur.squeeze(0)), sp(directions.squeeze(0))
     cam_weights_batches, lights_batches = sp(cam_weights), sp(lights)
+    tgt_normals_batches = sp(tgt_normals.squeeze(0)) if use_normal else None
     nb = len(pose_batches)
     losses = []
     for step in range(inverse_steps):
@@ -242,21 +247,29 @@ def mesh_optim(decoder, tgt_images, tgt_masks, optimizer, lr, lr_multiplier, inv
         out_normals_fg_weight = out_alphas.detach()
         loss = pixel_loss(out_rgbs.reshape(target_rgbs.size()), target_rgbs, weight=target_w / cam_weights_mean) * 4.5
         alphas_loss = pixel_loss(out_alphas.reshape(target_m_blur.size()), target_m_blur, weight=target_w / cam_weights_mean) * 2.0
-        normal_reg_loss = loss_tv(out_normals_fg.permute(0, 3, 1, 2), None, weight=out_normals_fg_weight.permute(0, 3, 1, 2)) * (normal_reg_weight * 2)
+        target_n = tgt_normals_batches[k] if use_normal else None
+        normal_reg_loss = loss_tv(out_normals_fg.permute(0, 3, 1, 2), target_n.permute(0, 3, 1, 2) if use_normal else None,
+                                  weight=out_normals_fg_weight.permute(0, 3, 1, 2)) * (normal_reg_weight * 2)
         lapsmth_loss = laplacian_smooth_loss(in_mesh.v, in_mesh.f) * mesh_normal_reg_weight
         norm_const_loss = normal_consistency(in_mesh.face_normals, in_mesh.f) * mesh_normal_reg_weight
         loss = loss + alphas_loss + normal_reg_loss + lapsmth_loss + norm_const_loss
-        if patch_rgb_weight > 0:
-            g = render_size // patch_size
-            pt = lambda x: x.reshape(-1, g, patch_size, g, patch_size, x.shape[-1]).permute(0, 1, 3, 5, 2, 4).reshape(-1, x.shape[-1], patch_size, patch_size)
+        g = render_size // patch_size
+        pt = lambda x: x.reshape(-1, g, patch_size, g, patch_size, x.shape[-1]).permute(0, 1, 3, 5, 2, 4).reshape(-1, x.shape[-1], patch_size, patch_size)
+        if patch_rgb_weight > 0 or (use_normal and patch_normal_weight > 0):
             out_rgb_patch, tgt_rgb_patch, target_w_patch = pt(out_rgbs), pt(target_rgbs), pt(target_w)
             patch_batch = noise['patch_perm'][step][:patch_bs]
-            loss = loss + patch_loss(out_rgb_patch[patch_batch], tgt_rgb_patch[patch_batch],
-                                     weight=target_w_patch[patch_batch, 0, 0, 0] / cam_weights_mean) * patch_rgb_weight
+            target_w_patch_ = target_w_patch[patch_batch, 0, 0, 0]
+        if patch_rgb_weight > 0:
+            loss = loss + patch_loss(out_rgb_patch[patch_batch], tgt_rgb_patch[patch_batch], weight=target_w_patch_ / cam_weights_mean) * patch_rgb_weight
+        if use_normal and patch_normal_weight > 0:                                                # :806-821 (weights of the rgb draw)
+            out_normal_patch, tgt_normal_patch = pt(out_normals), pt(target_n)
+            patch_batch = noise['patch_perm_normal'][step][:patch_bs]
+            loss = loss + patch_loss(highpass(out_normal_patch[patch_batch]), highpass(tgt_normal_patch[patch_batch]),
+                                     weight=target_w_patch_ / cam_weights_mean) * patch_normal_weight
         optimizer.zero_grad()
         loss.backward()
         optimizer.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
         mesh_verts, mesh_faces = dmtet(tet_verts + deform, tet_sdf, tet_indices)
         in_mesh = make_mesh(mesh_verts, mesh_faces.int())
     return in_mesh, losses

@@ -524,6 +524,11 @@ class OracleNeRF:
         return out_image, out_depth, out_normal, out_normal_fg
 
 
+def highpass(x, std=5, offset=0.5):
+    """lib/pipelines/utils.py:187-188."""
+    return offset + x - gaussian_blur(x, int(round(std)) * 6 + 1, std)
+
+
 # ------------------------------------------------------------------------------------------------ nerf_optim (mvedit_3d_pipeline.py:452-656)
 def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_steps, n_inverse_rays, patch_rgb_weight,
                patch_normal_weight, alpha_soften, normal_reg_weight, entropy_weight, nerf_code, density_grid, density_bitfield,
@@ -625,12 +630,16 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
             if patch_rgb_weight > 0 and nerf.patch_loss is not None:
                 loss = loss + nerf.patch_loss(out_rgbs.reshape(target_rgbs.size()).permute(0, 3, 1, 2), target_rgbs.permute(0, 3, 1, 2),
                                               weight=target_w[:, 0, 0, 0] / cam_weights_mean) * patch_rgb_weight
+            if use_normal and patch_normal_weight > 0:                                            # :619-626
+                loss = loss + nerf.patch_loss(highpass(out_normals.reshape(target_n.size()).permute(0, 3, 1, 2)),
+                                              highpass(target_n.permute(0, 3, 1, 2)),
+                                              weight=target_w[:, 0, 0, 0] / cam_weights_mean) * patch_normal_weight
             optimizer.zero_grad()
             loss.backward()
             optimizer.step()
             if debug:
-                log.append(dict(loss=float(loss), pixel_rgb=float(pixel_rgb_loss), alpha=float(alphas_loss), normal_reg=float(normal_reg_loss),
-                                entropy=float(entropy_loss)))
+                log.append(dict(loss=float(loss.detach()), pixel_rgb=float(pixel_rgb_loss.detach()), alpha=float(alphas_loss.detach()), normal_reg=float(normal_reg_loss.detach()),
+                                entropy=float(entropy_loss.detach())))
     nerf.decoder.train(training_prev)
     return log if debug else None
 

@@ -13,9 +13,9 @@
 // Optional terms (mve_nerf_patch_loss_targets; every pointer NULL in the text-to-3D recipe): target normals inside the TV term
 // (tv_loss.py:27: diff(pred) - diff(target)), the L1 term on 1/z against target depths (:586-592) and the gradient of the high-passed
 // normal patch term (:619-626) w.r.t. the alpha-composited normals, chained here to d(normal_fg) and d(alpha).
-#include "common.cuh"
+#include "cuda_host_shim.h"
 #include "tonemap.cuh"
-#include "../../include/mvedit_b200.h"
+#include "mvedit_b200.h"
 
 namespace {
 
@@ -352,10 +352,10 @@ int mve_nerf_patch_loss_targets(const float* image, const float* alpha, const fl
     MVE_CUDA(cudaMemsetAsync(loss5, 0, 5 * sizeof(float), s));
     if (loss_depth) MVE_CUDA(cudaMemsetAsync(loss_depth, 0, sizeof(float), s));
     const uint32_t grid = cdiv(N, 256);
-    k_normals<<<grid, 256, 0, s>>>(p);
-    k_terms<<<grid, 256, 0, s>>>(p);
-    k_normal_bwd<<<grid, 256, 0, s>>>(p);
-    k_finish<<<grid, 256, 0, s>>>(p);
+    SHIM_LAUNCH(k_normals, grid, 256, p);
+    SHIM_LAUNCH(k_terms, grid, 256, p);
+    SHIM_LAUNCH(k_normal_bwd, grid, 256, p);
+    SHIM_LAUNCH(k_finish, grid, 256, p);
     MVE_CHECK_LAUNCH("mve_nerf_patch_loss");
     return 0;
 }
@@ -382,8 +382,8 @@ int mve_nerf_patch_out_normal(const float* alpha, const float* depth, const floa
     p.normals = scratch; p.fgw = scratch + (size_t)N * 3; p.out_normal = out_normal;
     p.normal_bg[0] = normal_bg_x; p.normal_bg[1] = normal_bg_y; p.normal_bg[2] = normal_bg_z;
     const uint32_t grid = cdiv(N, 256);
-    k_normals<<<grid, 256, 0, s>>>(p);
-    k_out_normal<<<grid, 256, 0, s>>>(p);
+    SHIM_LAUNCH(k_normals, grid, 256, p);
+    SHIM_LAUNCH(k_out_normal, grid, 256, p);
     MVE_CHECK_LAUNCH("mve_nerf_patch_out_normal");
     return 0;
 }
@@ -401,8 +401,8 @@ int mve_nerf_patch_out_rgb(const float* image, const float* alpha, const float* 
     p.normals = scratch; p.fgw = scratch + (size_t)N * 3; p.out_rgb = out_rgb;
     MVE_ARG(fill_tone_lut(p.tone, tonemap_knots, tonemap_n) == 0, "nerf_patch_out_rgb: tone curve needs 2..32 knots");
     const uint32_t grid = cdiv(N, 256);
-    if (shaded) k_normals<<<grid, 256, 0, s>>>(p);
-    k_out_rgb<<<grid, 256, 0, s>>>(p);
+    if (shaded) SHIM_LAUNCH(k_normals, grid, 256, p);
+    SHIM_LAUNCH(k_out_rgb, grid, 256, p);
     MVE_CHECK_LAUNCH("mve_nerf_patch_out_rgb");
     return 0;
 }

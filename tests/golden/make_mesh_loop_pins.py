@@ -193,6 +193,7 @@ def main():
     penv = dict(torch=rec, F=F, F_t=F_t, np=np, TVLoss=TVLoss, get_module_device=lambda mod: 'cpu', get_ray_directions=gu.get_ray_directions,
                 depth_to_normal=gu.depth_to_normal, laplacian_smooth_loss=R['laplacian_smooth_loss'], normal_consistency=R['normal_consistency'],
                 Mesh=RefMesh, o3d=None)
+    penv['highpass'] = extract('lib/pipelines/utils.py', ['highpass'], dict(F_t=F_t))['highpass']
     P = extract('lib/pipelines/mvedit_3d_pipeline.py', ['mesh_optim', 'make_nerf_shading_fun'], penv)
     n, size, steps, ps = 4, 32, 2, 16
     poses = torch.from_numpy(synth_mesh.surround_poses(n, 2)).float()
@@ -234,6 +235,35 @@ def main():
                mo_patch_perm=np.stack([draws[2 + 2 * s][1].numpy() for s in range(steps)]),
                mo_sdf=tet_sdf.detach().numpy(), mo_deform=deform.detach().numpy(), mo_w=field.w.detach().numpy(), mo_b=field.b.detach().numpy(),
                mo_faces=out_mesh.f.numpy(), mo_verts=out_mesh.v.detach().numpy())
+
+    # ---- the same loop with target normals: TV target, lr of the geometry group without the multiplier, high-passed normal patch term
+    rec.draws = []
+    field_n = ToyField()
+    sdf_n = sdf0.clone().requires_grad_(True)
+    deform_n = torch.zeros_like(tet_verts).requires_grad_(True)
+    opt_n = torch.optim.Adam([{'params': list(field_n.parameters())}, {'params': [sdf_n, deform_n], 'lr': 1e-3}], lr=0.01)
+    nx, ny = (xx - 15.5) / 12.0, -(yy - 15.5) / 12.0
+    nrm = F.normalize(torch.stack([nx, ny, (1 - nx ** 2 - ny ** 2).clamp(min=0.05).sqrt()], -1)
+                      + 0.05 * torch.randn(size, size, 3, generator=torch.Generator().manual_seed(6)), dim=-1)
+    tgt_normals = (nrm / 2 + 0.5)[None, None].expand(1, n, -1, -1, -1).contiguous()
+    with torch.enable_grad():
+        mv, mf = dm(tet_verts + deform_n, sdf_n, tet_indices)
+        mesh_n = RefMesh(v=mv, f=mf.int())
+        mesh_n.auto_normal()
+    self_n = types.SimpleNamespace(nerf=types.SimpleNamespace(decoder=field_n, pixel_loss=L1LossMod(loss_weight=1.2), patch_loss=_FakePatchLoss()),
+                                   mesh_renderer=renderer, normal_bg=[0.5, 0.5, 1.0], tonemapping=None)
+    self_n.make_nerf_shading_fun = lambda *a: P['make_nerf_shading_fun'](self_n, *a)
+    torch.manual_seed(12)
+    out_n = P['mesh_optim'](self_n, tgt_images, tgt_masks, tgt_normals, opt_n, 0.01, 0.8, steps, 2, 3, 24, 0.7, 0.9, 0.02, 0.1, 5.0, [None], tet_verts,
+                            deform_n, sdf_n, tet_indices, dm, mesh_n, size, intr, size, poses, cam_weights, lights, ps, False, 0.2, 1.0)
+    dn = rec.draws
+    assert [k for k, _ in dn] == ['randperm'] + ['rand_like', 'randperm', 'randperm'] * steps
+    out.update(mn_tgt_normals=tgt_normals.numpy(), mn_camera_perm=dn[0][1].numpy(),
+               mn_jitter=np.stack([dn[1 + 3 * s][1].numpy() for s in range(steps)]),
+               mn_patch_perm=np.stack([dn[2 + 3 * s][1].numpy() for s in range(steps)]),
+               mn_patch_perm_normal=np.stack([dn[3 + 3 * s][1].numpy() for s in range(steps)]),
+               mn_sdf=sdf_n.detach().numpy(), mn_deform=deform_n.detach().numpy(), mn_w=field_n.w.detach().numpy(), mn_b=field_n.b.detach().numpy(),
+               mn_faces=out_n.f.numpy(), mn_verts=out_n.v.detach().numpy())
 
     rec2 = TorchRecorder()
     tenv = dict(torch=rec2, F=F, np=np, get_module_device=lambda mod: 'cpu')

@@ -64,6 +64,17 @@ def scene(seed=0):
     return poses, intr, images, masks, torch.tensor([1.0, 0.5, 2.0]), F.normalize(torch.randn(V, 3, generator=g), dim=-1), draws
 
 
+def targets(seed=5):
+    """Target normals (opengl, [0,1]; a dome over the disc) and target 1/z for the image-to-3D case."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.arange(RS), torch.arange(RS), indexing='ij')
+    nx, ny = (xx - 15.5) / 12.0, -(yy - 15.5) / 12.0
+    n = F.normalize(torch.stack([nx, ny, (1 - nx ** 2 - ny ** 2).clamp(min=0.05).sqrt()], -1) + 0.05 * torch.randn(RS, RS, 3, generator=g), dim=-1)
+    normals = (n / 2 + 0.5)[None, None].expand(1, V, -1, -1, -1).contiguous()
+    depths = (0.25 + 0.1 * torch.rand(1, V, RS, RS, 1, generator=g))
+    return normals, depths
+
+
 def make_field(seed=1):
     from oracle import nerf_oracle as no
     dec = no.OracleDecoder(no.CpuOps(), **DEC)
@@ -104,39 +115,49 @@ def main():
 
     import torchvision.transforms.v2.functional as F_t
     env = dict(torch=torch, F=F, F_t=F_t, np=np, math=math, TVLoss=TVLoss, get_module_device=lambda m: 'cpu', get_ray_directions=gu.get_ray_directions,
-               get_rays=gu.get_rays, depth_to_normal=gu.depth_to_normal, highpass=None)
+               get_rays=gu.get_rays, depth_to_normal=gu.depth_to_normal)
+    env['highpass'] = extract('lib/pipelines/utils.py', ['highpass'], dict(F_t=F_t))['highpass']
     ref_nerf_optim = extract('lib/pipelines/mvedit_3d_pipeline.py', ['nerf_optim'], env)['nerf_optim']
 
-    poses, intr, images, masks, cam_w, cam_lights, draws = scene()
-    dec = make_field()
+    out = {}
+    for case in ('p1', 't1'):                    # p1: text-to-3D terms;  t1: + target normals (TV target, high-passed patch term) and depths
+        poses, intr, images, masks, cam_w, cam_lights, draws = scene()
+        dec = make_field()
 
-    class FedDecoder(type(dec)):                 # the reference loop calls decoder(...) / update_extra_state(...) without noise arguments
-        def forward(self, *a, **k):
-            return super().forward(*a, noises=self._march.pop(0), **k)
+        class FedDecoder(type(dec)):             # the reference loop calls decoder(...) / update_extra_state(...) without noise arguments
+            def forward(self, *a, **k):
+                return super().forward(*a, noises=self._march.pop(0), **k)
 
-        def update_extra_state(self, code, dg, db, it, **kw):
-            return super().update_extra_state(code, dg, db, it, noise=self._grid.pop(0), **kw)
-    dec.__class__ = FedDecoder
-    dec._march, dec._grid = list(draws['march']), list(draws['grid'])
+            def update_extra_state(self, code, dg, db, it, **kw):
+                return super().update_extra_state(code, dg, db, it, noise=self._grid.pop(0), **kw)
+        dec.__class__ = FedDecoder
+        dec._march, dec._grid = list(draws['march']), list(draws['grid'])
 
-    class FedNeRF(no.OracleNeRF):
-        def get_raybatch_inds(self, cond_imgs, n_inverse_rays):
-            b = draws['raybatch'].split(n_inverse_rays // (self.patch_size ** 2), dim=1)
-            return b, len(b)
-    nerf = FedNeRF(dec, grid_size=GRID, patch_size=PS, update_extra_interval=2)
-    nerf.patch_loss = WeightedMSE()
-    density_grid = torch.zeros(1, GRID ** 3, dtype=torch.float16)
-    density_bitfield = torch.full((1, GRID ** 3 // 8), 255, dtype=torch.uint8)
-    opt = torch.optim.Adam(dec.parameters(), lr=0.01)
-    p0 = {k: v.detach().clone() for k, v in dec.state_dict().items()}
-    self_ = types.SimpleNamespace(nerf=nerf, normal_bg=[0.5, 0.5, 1.0], tonemapping=None)
-    ref_nerf_optim(self_, images, masks, None, opt, 0.01, ITERS, N_RAYS, 0.4, 0.0, 0.02, 0.1, 0.01, [None], density_grid, density_bitfield, RS, intr,
-                   RS, poses, cam_w, cam_lights, PS, False, 0.015, 0.2, 1.0, False)
-    out = {'p1_' + k: v.detach().numpy() for k, v in dec.state_dict().items()}          # (the initial field is make_field(): not stored)
-    out.update(grid1=density_grid.numpy(), bits1=density_bitfield.numpy())
+        class FedNeRF(no.OracleNeRF):
+            def get_raybatch_inds(self, cond_imgs, n_inverse_rays):
+                b = draws['raybatch'].split(n_inverse_rays // (self.patch_size ** 2), dim=1)
+                return b, len(b)
+        nerf = FedNeRF(dec, grid_size=GRID, patch_size=PS, update_extra_interval=2)
+        nerf.patch_loss = WeightedMSE()
+        density_grid = torch.zeros(1, GRID ** 3, dtype=torch.float16)
+        density_bitfield = torch.full((1, GRID ** 3 // 8), 255, dtype=torch.uint8)
+        opt = torch.optim.Adam(dec.parameters(), lr=0.01)
+        p0 = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+        self_ = types.SimpleNamespace(nerf=nerf, normal_bg=[0.5, 0.5, 1.0], tonemapping=None)
+        if case == 'p1':
+            ref_nerf_optim(self_, images, masks, None, opt, 0.01, ITERS, N_RAYS, 0.4, 0.0, 0.02, 0.1, 0.01, [None], density_grid, density_bitfield,
+                           RS, intr, RS, poses, cam_w, cam_lights, PS, False, 0.015, 0.2, 1.0, False)
+        else:
+            normals, depths = targets()
+            ref_nerf_optim(self_, images, masks, normals, opt, 0.01, ITERS, N_RAYS, 0.4, 0.7, 0.02, 0.1, 0.01, [None], density_grid,
+                           density_bitfield, RS, intr, RS, poses, cam_w, cam_lights, PS, False, 0.015, 0.2, 1.0, False, tgt_depths=depths,
+                           depth_weight=0.3)
+        out.update({case + '_' + k: v.detach().numpy() for k, v in dec.state_dict().items()})   # (the initial field is make_field(): not stored)
+        out.update({'grid1' if case == 'p1' else 'grid_t1': density_grid.numpy(), 'bits1' if case == 'p1' else 'bits_t1': density_bitfield.numpy()})
+        moved = max(float((dec.state_dict()[k] - p0[k]).abs().max()) for k in p0)
+        print(case, 'max parameter change', moved, 'occupied bytes', int((density_bitfield != 0).sum()))
     np.savez_compressed(OUT, **out)
-    moved = max(float((dec.state_dict()[k] - p0[k]).abs().max()) for k in p0)
-    print('wrote', OUT, 'max parameter change', moved, 'occupied bytes', int((density_bitfield != 0).sum()))
+    print('wrote', OUT)
 
 
 if __name__ == '__main__':

@@ -18,6 +18,61 @@ DEPS = SRCS + [os.path.join(CSRC, 'host_dual.cuh')]
 OUT_DIR = os.path.join(ROOT, 'tests', '_host')
 LIB = os.path.join(OUT_DIR, 'libmesh_raster_host.so')
 _lib = None
+_shimmed = {}
+
+
+def shimmed(source):
+    """An element-wise kernel source of the product (e.g. ``nerf_loss.cu``) compiled UNCHANGED as C++ through tests/host_shim/cuda_host_shim.h:
+    launches become serial loops, ``common.cuh`` becomes the shim.  -> ctypes library whose ``mve_*`` entry points take host pointers."""
+    import re
+    if source in _shimmed:
+        return _shimmed[source]
+    os.makedirs(OUT_DIR, exist_ok=True)
+    src = os.path.join(CSRC, source)
+    shim_dir = os.path.join(ROOT, 'tests', 'host_shim')
+    out_cpp = os.path.join(OUT_DIR, source.replace('.cu', '_host.cpp'))
+    out_so = os.path.join(OUT_DIR, 'lib' + source.replace('.cu', '_host.so'))
+    deps = [src, os.path.join(shim_dir, 'cuda_host_shim.h'), os.path.join(CSRC, 'tonemap.cuh'), os.path.abspath(__file__)]
+    if (not os.path.exists(out_so)) or os.path.getmtime(out_so) < max(os.path.getmtime(d) for d in deps):
+        text = open(src).read()
+        text = text.replace('#include "common.cuh"', '#include "cuda_host_shim.h"').replace('#include "../../include/mvedit_b200.h"',
+                                                                                            '#include "mvedit_b200.h"')
+
+        def launch(m):
+            cfg, depth, cur = [], 0, ''
+            for ch in m.group(2):                # split the launch configuration at top-level commas only
+                depth += ch in '([' and 1 or (ch in ')]' and -1 or 0)
+                if ch == ',' and depth == 0:
+                    cfg.append(cur.strip()); cur = ''
+                else:
+                    cur += ch
+            cfg.append(cur.strip())
+            return 'SHIM_LAUNCH(%s, %s, %s, %s);' % (m.group(1), cfg[0], cfg[1], m.group(3))
+        text, n = re.subn(r'(\w+)<<<([^>]*)>>>\((.*?)\);', launch, text)
+        assert n > 0 and '<<<' not in text
+        open(out_cpp, 'w').write(text)
+        cmd = ['g++', '-std=c++17', '-O1', '-ffp-contract=off', '-fPIC', '-shared', '-Wno-unknown-pragmas', '-I', shim_dir, '-I', CSRC,
+               '-I', os.path.join(ROOT, 'include'), out_cpp, '-o', out_so]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('host shim build of %s failed:\n%s' % (source, r.stderr))
+    _shimmed[source] = ctypes.CDLL(out_so)
+    return _shimmed[source]
+
+
+class Libraries:
+    """Several host libraries behind one lookup (``routed(module, Libraries(a, b))``)."""
+
+    def __init__(self, *libs):
+        self.libs = libs
+
+    def __getattr__(self, name):
+        for l in self.libs:
+            try:
+                return getattr(l, name)
+            except AttributeError:
+                pass
+        raise AttributeError(name)
 
 
 def build():
@@ -39,9 +94,10 @@ def lib():
 
 
 @contextlib.contextmanager
-def routed(module):
-    """Route ``module``'s C-ABI calls (its ``call`` / ``ptr`` / ``stream`` names) to the host harness, for CPU tensors."""
-    h = lib()
+def routed(module, library=None):
+    """Route ``module``'s C-ABI calls (its ``call`` / ``ptr`` / ``stream`` names) to the host harness (or to ``library``, e.g. a
+    ``shimmed`` source), for CPU tensors."""
+    h = library if library is not None else lib()
 
     def call(name, *args, _meta=None):
         code = getattr(h, name)(*args)

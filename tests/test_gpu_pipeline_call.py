@@ -114,14 +114,17 @@ def test_call_runs_nerf_stage(parts, sched, mode, blend, ref):
         assert sch.model_outputs[-1].shape[0] == 3                  # multistep history pruned with the cameras
 
 
-def test_unbuilt_stages_raise_and_restore(parts):
+def test_unbuilt_options_raise_and_restore(parts):
+    """What is not built raises ``NotImplementedError`` (never a silent fallback) and leaves the decoder's weights restored; any other
+    failure is swallowed into ``(None, None)`` as the reference does (:1488-1494)."""
     sch = _schedulers()['euler']()
     pipe, dec = make_pipe(parts, sch)
     before = {k: v.detach().clone() for k, v in dec.state_dict().items()}
     with pytest.raises(NotImplementedError):
-        call(pipe, parts, progress_to_dmtet=0.3)                    # DMTet / mesh stage
+        call(pipe, parts, use_normal=True)                          # no normals handed in and no normal_model to predict them
     assert all(torch.equal(dec.state_dict()[k], before[k]) for k in before)
     with pytest.raises(NotImplementedError):
-        call(pipe, parts, use_normal=True)
-    with pytest.raises(NotImplementedError):
-        call(pipe, parts, init_images=None)
+        call(pipe, parts, ip_adapter=object())
+    mesh, state = call(pipe, parts, progress_to_dmtet=0.3)           # DMTet stage without a mesh_renderer: the reference-style swallow
+    assert mesh is None and state is None
+    assert all(torch.equal(dec.state_dict()[k], before[k]) for k in before)

@@ -124,6 +124,43 @@ def test_mesh_optim_matches_the_reference_method(impl):
     assert (T('mo_sdf') - T('mo_sdf0')).abs().max() > 1e-4
 
 
+@pytest.mark.parametrize('impl', ['product', 'oracle'])
+def test_mesh_optim_with_target_normals_matches_the_reference_method(impl):
+    """The reference's ``mesh_optim`` with ``tgt_normals`` (TV term against the target's differences, geometry lr without the multiplier,
+    the high-passed normal patch term with its own patch draw): same SDF, deformation, field and mesh after two iterations."""
+    grid, tet_verts, sdf, deform, field, opt, _ = _mesh_optim_setup()
+    noise = dict(camera_perm=T('mn_camera_perm'), jitter=T('mn_jitter'), patch_perm=T('mn_patch_perm'), patch_perm_normal=T('mn_patch_perm_normal'))
+    size, steps, ps = 32, 2, 16
+    pl = _FakePatchLoss()
+    if impl == 'product':
+        dm = DMTet('cpu')
+        with torch.enable_grad():
+            mv, mf = dm(tet_verts + deform, sdf, grid['indices'])
+            mesh = Mesh(v=mv, f=mf.int())
+            mesh.auto_normal()
+        pipe = SimpleNamespace(nerf=SimpleNamespace(decoder=field, pixel_loss=L1LossMod(loss_weight=1.2), patch_loss=pl),
+                               mesh_renderer=MeshRenderer(near=0.01, far=100), normal_bg=[0.5, 0.5, 1.0], tonemapping=None)
+        with host_harness.routed(mopt):
+            out = mopt.mesh_optim(pipe, T('mo_tgt_images'), T('mo_tgt_masks'), T('mn_tgt_normals'), opt, 0.01, 0.8, steps, 2, 3, 24, 0.7, 0.9, 0.02,
+                                  0.1, 5.0, None, tet_verts, deform, sdf, grid['indices'], dm, mesh, size, T('mo_intr'), size, T('mo_poses'),
+                                  T('mo_cam_weights'), T('mo_lights'), ps, False, 0.2, 1.0, noise=noise)
+            with pytest.raises(NotImplementedError):
+                mopt.mesh_optim(pipe, T('mo_tgt_images'), T('mo_tgt_masks'), T('mn_tgt_normals'), opt, 0.01, 0.8, steps, 2, 3, 24, 0.7, 0.9, 0.02,
+                                0.1, 5.0, None, tet_verts, deform, sdf, grid['indices'], dm, mesh, size, T('mo_intr'), size, T('mo_poses'),
+                                T('mo_cam_weights'), T('mo_lights'), ps, False, 0.2, 1.0, noise=noise, fused_objective=True)
+    else:
+        dm = mo.DMTetOracle()
+        mv, mf = dm(tet_verts + deform, sdf, grid['indices'])
+        out, _ = mo.mesh_optim(field, T('mo_tgt_images'), T('mo_tgt_masks'), opt, 0.01, 0.8, steps, 2, 3, 0.7, 0.02, 0.1, 5.0, None, tet_verts, deform,
+                               sdf, grid['indices'], dm, mo.make_mesh(mv, mf.int()), size, T('mo_intr'), size, T('mo_poses'), T('mo_cam_weights'),
+                               T('mo_lights'), ps, 0.2, noise, patch_loss=pl, tgt_normals=T('mn_tgt_normals'), patch_normal_weight=0.9)
+    for got, key in ((sdf, 'mn_sdf'), (deform, 'mn_deform'), (field.w, 'mn_w'), (field.b, 'mn_b')):
+        assert (got.detach() - T(key)).abs().max() < 2e-5, key
+    assert torch.equal(out.f.long(), T('mn_faces').long())
+    _close(out.v.detach(), T('mn_verts'))
+    assert (T('mn_sdf') - T('mo_sdf')).abs().max() > 1e-5                      # the target normals did change the trajectory
+
+
 def test_texture_optim_matches_the_reference_method():
     mesh = Mesh(v=T('fw_v'), f=T('fw_f'))
     mesh.auto_normal()

@@ -142,3 +142,53 @@ def test_call_initialises_from_an_input_mesh(monkeypatch):
     fg = tgt_masks[0, ..., 0] > 0.99
     assert 0.05 < fg.float().mean() < 0.5 and (tgt_images[0][~(tgt_masks[0, ..., 0] > 0)] == 1.0).all()       # composited on the background colour
     assert tgt_images[0][fg].std() > 0.02                                                                   # shaded vertex colours, not flat
+
+
+def test_call_threads_target_normals_and_depths_through_both_stages(monkeypatch):
+    """``use_normal`` with maps handed in and ``depths``: re-shaded inputs (``init_shaded``), targets re-ordered with ``keep_views``,
+    resized to the render size and passed to ``nerf_optim`` (with the depth weight) and to ``mesh_optim`` (which runs here, incl. the
+    high-passed normal patch term) -- mvedit_3d_pipeline.py:1082-1090,1166-1169,1272-1295,1298-1332."""
+    from tests.test_mesh_stage_host import _FakePatchLoss
+    n, size = 4, 32
+    monkeypatch.setattr(P, 'FusedAdam', AdamLike)
+    seen = dict(nerf=[], mesh=[])
+    monkeypatch.setattr(P, 'nerf_optim', lambda nerf, ti, tm, tn, *a, **k: seen['nerf'].append((ti, tn, a[5], a[-1], k['tgt_depths'], k['depth_weight'])))
+    real_mesh_optim = P.mesh_optim
+
+    def spy(self, ti, tm, tn, *a, **k):
+        seen['mesh'].append((tn, a[8]))                  # (tgt_normals, patch_normal_weight)
+        return real_mesh_optim(self, ti, tm, tn, *a, **k)
+    monkeypatch.setattr(P, 'mesh_optim', spy)
+    dec = ToyDecoder()
+    nerf = nn.Module()
+    nerf.decoder, nerf.bg_color, nerf.grid_size, nerf.pixel_loss, nerf.patch_loss = dec, 1.0, 8, L1LossMod(loss_weight=1.2), _FakePatchLoss()
+    nerf.get_init_density_grid = lambda ns, device=None: torch.zeros(ns, 8 ** 3, dtype=torch.float16)
+    nerf.get_init_density_bitfield = lambda ns, device=None: torch.zeros(ns, 8 ** 3 // 8, dtype=torch.uint8)
+    unet = nn.Module()
+    unet.device = torch.device('cpu')
+    pipe = P.MVEdit3DPipeline(None, None, None, unet, None, None, nerf, mesh_renderer=MeshRenderer(near=0.01, far=100))
+    poses = torch.from_numpy(synth_mesh.surround_poses(n, 1)).float()
+    intr = torch.from_numpy(synth_mesh.intrinsics(size)).float()
+    yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing='ij')
+    disc = (((xx - 15.5) ** 2 + (yy - 15.5) ** 2).float().sqrt() < 9).float()
+    init = torch.cat([torch.rand(n, 3, size, size, generator=torch.Generator().manual_seed(2)), disc[None, None].expand(n, -1, -1, -1)], dim=1)
+    colours = torch.tensor([[0.9, 0.5, 0.8], [0.5, 0.9, 0.8], [0.2, 0.5, 0.8], [0.5, 0.2, 0.8]])
+    normals = [c[:, None, None].expand(3, size, size) for c in colours]                   # one flat normal map per view, all different
+    depths = [torch.full((size, size), 0.1 * (k + 1)) for k in range(n)]
+    with pytest.raises(NotImplementedError):                                              # no maps and no normal model
+        pipe(init_images=init, camera_poses=poses, intrinsics=intr, intrinsics_size=size, use_reference=False, optim_only=True,
+             num_inference_steps=1)
+    mesh, state = pipe(init_images=init, camera_poses=poses, intrinsics=intr, intrinsics_size=size, use_reference=False, use_normal=True,
+                       normals=normals, depths=depths, depth_weight=0.3, keep_views=[2], optim_only=True, num_inference_steps=2,
+                       progress_to_dmtet=0.4, tet_resolution=12, tets=make_tet_grid(12), n_inverse_steps=1, init_inverse_steps=1,
+                       tet_init_inverse_steps=1, render_bs=2, patch_bs=2, patch_size=16, render_size_p=lambda p: size,
+                       patch_rgb_weight=lambda p: 0.0, patch_normal_weight=lambda p: 0.5, mesh_simplify_texture_steps=0, bake_texture=False)
+    assert mesh is not None and state is not None
+    ti, tn, pnw, init_shaded, td, dw = seen['nerf'][0]
+    assert tn.shape == (1, n, size, size, 3) and td.shape == (1, n, size, size, 1) and pnw == 0.5 and dw == 0.3 and init_shaded is True
+    fg = disc > 0.5
+    # keep_views=[2] moves view 2 first: its (normalised) flat normal and its depth come first
+    first = torch.nn.functional.normalize(colours[2] * 2 - 1, dim=0) / 2 + 0.5
+    assert torch.allclose(tn[0, 0][fg].mean(0), first, atol=2e-3) and torch.allclose(td[0, 0][fg], torch.tensor(0.3), atol=1e-5)
+    assert torch.allclose(tn[0, 0][~fg & (disc < 0.01)].mean(0), torch.tensor([0.5, 0.5, 1.0]), atol=1e-3)      # background normal
+    assert len(seen['mesh']) == 2 and all(m[0].shape == (1, n, size, size, 3) and m[1] == 0.5 for m in seen['mesh'])
