@@ -247,6 +247,8 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
     use_prgb = patch_rgb_weight > 0
     tone = tone_args(tonemapping)                     # knots by value into the kernels (static: safe inside the captured graph)
     lpips = nerf.patch_loss if (use_prgb or use_pn) else None
+    if lpips is None and (use_prgb or use_pn):
+        raise RuntimeError('nerf_optim: a patch term has a positive weight but nerf.patch_loss is None')
     if lpips is not None and not hasattr(lpips, 'loss_and_grad'):
         raise NotImplementedError('nerf_optim: nerf.patch_loss must be a mvedit_b200.lpips.LPIPSLoss (kernels, no autograd graph); got %r'
                                   % type(lpips).__name__)

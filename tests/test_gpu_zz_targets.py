@@ -93,3 +93,35 @@ def test_nerf_optim_with_target_normals_and_depths():
     nerf_optim(nerf, tgt_images, hit, tgt_normals, inverse_steps=6, **kw)
     torch.cuda.synchronize()
     assert all(torch.isfinite(p_).all() for p_ in nerf.decoder.parameters())
+
+
+# ---- the pipeline call with the options this round added after its GPU budget was spent (first GPU runs) -------------------------------
+from tests.test_gpu_pipeline_call import parts, make_pipe, call, _schedulers, N, IMG      # noqa: E402,F401  (``parts`` is a fixture)
+
+
+def test_call_with_target_normals_and_depths(parts):
+    """``use_normal`` with maps handed in + ``depths``: enable_normals / load_depths, then every nerf_optim of the run carries the target
+    terms (TV target, depth L1, and -- with an LPIPS patch loss and the default weight schedule -- the high-passed normal patch term)."""
+    sch = _schedulers()['euler']()
+    pipe, dec = make_pipe(parts, sch, lpips=True)
+    before = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    g = torch.Generator(device='cuda').manual_seed(7)
+    normals = [torch.nn.functional.normalize(torch.rand(3, 64, 64, device='cuda', generator=g) - 0.5 + torch.tensor([0.0, 0.0, 1.0], device='cuda')[:, None, None],
+                                             dim=0) / 2 + 0.5 for _ in range(N)]
+    depths = [0.2 + 0.2 * torch.rand(64, 64, device='cuda', generator=g) for _ in range(N)]
+    mesh, state = call(pipe, parts, mode='2-pass', use_normal=True, normals=normals, depths=depths, depth_weight=0.3)
+    assert mesh is None and state is not None, 'the run raised inside __call__ (traceback printed above)'
+    assert all(torch.isfinite(v).all() for v in state.values() if torch.is_floating_point(v))
+    assert max(float((state[k].float() - before[k].float()).abs().max()) for k in before if torch.is_floating_point(before[k])) > 1e-3
+
+
+def test_call_initialises_from_the_field(parts):
+    """Without ``init_images`` and ``in_model`` the initial targets are renders of the field handed in (``load_init_nerf``,
+    mvedit_3d_pipeline.py:138-173,1060-1064)."""
+    sch = _schedulers()['euler']()
+    pipe, dec = make_pipe(parts, sch)
+    mesh0, state0 = call(pipe, parts, patch_rgb_weight=lambda p: 0.0)                    # a fitted field to start from
+    assert state0 is not None
+    mesh, state = call(pipe, parts, init_images=None, ingp_states=state0, patch_rgb_weight=lambda p: 0.0, num_inference_steps=4)
+    assert mesh is None and state is not None, 'the run raised inside __call__ (traceback printed above)'
+    assert all(torch.isfinite(v).all() for v in state.values() if torch.is_floating_point(v))
