@@ -470,6 +470,17 @@ int mve_mesh_loss_backward(const float* rgba, const float* tgt_rgb, const float*
 int mve_edge_opposites(const int32_t* tri, uint32_t F, uint32_t slots, void* keys, uint32_t* first, uint32_t* second,
                        uint32_t* slot_of, int32_t* opp, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * a-10: decimation of the final DMTet mesh (lib/pipelines/mvedit_3d_pipeline.py:829-844)
+ * ------------------------------------------------------------------------- */
+
+/* Quadric-error edge-collapse decimation ON THE HOST (all pointers are HOST pointers; this entry launches no kernel): replaces
+ * open3d's TriangleMesh.simplify_quadric_decimation(target, boundary_weight=0) that mesh_optim calls on the CPU when mesh_reduction < 1
+ * at the last step.  verts [V,3], faces [F,3] int32 -> out_verts (room for V), out_faces (room for F), out_counts = {n_verts, n_faces}.
+ * Stops at target_faces or when no legal collapse is left (link condition + normal-flip rejection keep a closed manifold closed). */
+int mve_mesh_simplify(const float* verts, uint32_t V, const int32_t* faces, uint32_t F, uint32_t target_faces, float* out_verts,
+                      int32_t* out_faces, uint32_t* out_counts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,8 +8,9 @@ kernels, one fused Adam step over (field parameters | sdf, deform), marching-tet
 torch autograd over those kernels (the NeRF stage has it fused in ``nerf_loss.cu``; the mesh stage's version is not fused yet).
 
 Target normals (``tgt_normals``: TV term against the target's differences, geometry lr without the multiplier, high-passed normal
-patch term) are covered by the eager composition.  Not built (raises): mesh simplification at the last step (``mesh_reduction < 1``
-needs open3d's quadric decimation, ``:829-844``).
+patch term) are covered by the eager composition.  ``mesh_reduction < 1`` decimates the mesh of the last call by quadric-error edge
+collapses (``mesh_renderer.simplify_mesh`` = ``mve_mesh_simplify``, host C++ in place of open3d's ``simplify_quadric_decimation``,
+``:829-844``) and fits only the texture afterwards.
 """
 import ctypes
 import os
@@ -18,7 +19,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .mesh_renderer import (DMTet, Mesh, laplacian_smooth_loss, make_tet_grid, min_pool, normal_consistency,   # noqa: F401  (re-exported)
+from .mesh_renderer import (DMTet, Mesh, laplacian_smooth_loss, make_tet_grid, min_pool, normal_consistency, simplify_mesh,   # noqa: F401  (re-exported)
                             view_cosine)
 from .nerf import blur_masks, highpass, pixel_directions
 from ._lib import call, ptr, stream, c_u32, c_f32
@@ -226,8 +227,6 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
     launches of ``csrc/mesh_loss.cu`` instead of ~60 eager torch ops + autograd (same values; CPU-checked, not yet run on a GPU)."""
     use_normal = tgt_normals is not None                          # :667
     use_pn = use_normal and patch_normal_weight > 0               # :806
-    if mesh_reduction < 1 and is_end:
-        raise NotImplementedError('mesh_optim: mesh simplification (open3d quadric decimation) is not built; use mesh_reduction=1')
     nerf, dec = self.nerf, self.nerf.decoder
     device = tet_verts.device
     noise = noise or {}
@@ -265,6 +264,7 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
             nb = len(pose_b)
             if is_end:
                 inverse_steps = max(inverse_steps, mesh_simplify_texture_steps)
+            mesh_is_simplified = False                          # (:713) set by the decimation of the last call
             for step in range(inverse_steps):
                 k = step % nb
                 bs = img_b[k].shape[0]
@@ -274,7 +274,9 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
                 if perturb:                                  # +-0.5 px principal-point jitter (:733-735)
                     u = noise['jitter'][step, :bs].to(device) if 'jitter' in noise else shared(torch.rand_like(intrinsics_batch[:, 2:]))
                     intrinsics_batch = torch.cat([intrinsics_batch[:, :2], intrinsics_batch[:, 2:] + (u - 0.5) / self.mesh_renderer.ssaa], dim=1)
-                loss = (laplacian_smooth_loss(in_mesh.v, in_mesh.f) + normal_consistency(in_mesh.face_normals, in_mesh.f)) * (mesh_normal_reg_weight / world)
+                geo = 0.0 if mesh_is_simplified else 1.0         # a decimated mesh is fixed: only the colour terms remain (:764-779, :806)
+                loss = 0.0 if mesh_is_simplified else (laplacian_smooth_loss(in_mesh.v, in_mesh.f)
+                                                        + normal_consistency(in_mesh.face_normals, in_mesh.f)) * (mesh_normal_reg_weight / world)
                 if hi > lo:
                     target_rgbs, target_m, target_m_blur, target_dir = img_b[k][lo:hi], mask_b[k][lo:hi], blur_b[k][lo:hi], dir_b[k][lo:hi]
                     target_m_erode = min_pool(target_m)
@@ -300,7 +302,8 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
                         lw = float(nerf.pixel_loss.loss_weight)
                         views = _MeshObjectiveFn.apply(
                             rgba, render_out['normal'].squeeze(0), gate.squeeze(-1), target_rgbs, target_m_erode.squeeze(-1), target_m_blur.squeeze(-1),
-                            w_b[k][lo:hi] / cam_weights_mean, self.normal_bg, lw * 4.5 / (n_px * 3), lw * 2.0 / n_px, normal_reg_weight * 2 / (n_px * 3),
+                            w_b[k][lo:hi] / cam_weights_mean, self.normal_bg, lw * 4.5 / (n_px * 3), geo * lw * 2.0 / n_px,
+                            geo * normal_reg_weight * 2 / (n_px * 3),
                             (nerf.patch_loss, pick, patch_size, w_pick, patch_rgb_weight) if patch_rgb_weight > 0 else None)
                     else:
                         out_alphas = rgba[..., 3:]
@@ -310,21 +313,23 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
                         out_normals = out_normals * gate + out_normals.detach() * (1 - gate)      # value unchanged, gradient scaled by the gate
                         out_normals_fg = (out_normals - normal_bg * (1 - out_alphas)) / out_alphas.clamp(min=1e-3)
                         views = nerf.pixel_loss(out_rgbs, target_rgbs, weight=wgt) * 4.5
-                        views = views + nerf.pixel_loss(out_alphas, target_m_blur, weight=wgt) * 2.0
                         target_n = nrm_b[k][lo:hi] if use_normal else None
-                        views = views + tv_normal_loss(out_normals_fg.permute(0, 3, 1, 2), out_alphas.detach().permute(0, 3, 1, 2),
-                                                       target=target_n.permute(0, 3, 1, 2) if use_normal else None) * (normal_reg_weight * 2)
+                        if not mesh_is_simplified:
+                            views = views + nerf.pixel_loss(out_alphas, target_m_blur, weight=wgt) * 2.0
+                            views = views + tv_normal_loss(out_normals_fg.permute(0, 3, 1, 2), out_alphas.detach().permute(0, 3, 1, 2),
+                                                           target=target_n.permute(0, 3, 1, 2) if use_normal else None) * (normal_reg_weight * 2)
                         if patch_rgb_weight > 0:
                             out_p, tgt_p = _patches(out_rgbs, render_size, patch_size), _patches(target_rgbs, render_size, patch_size)
                             views = views + lpips_patch_loss(nerf.patch_loss, out_p[pick], tgt_p[pick], w_pick) * patch_rgb_weight
-                        if use_pn:        # high-passed normal patch term (:806-821): its own patch draw, the rgb draw's weights (as the reference)
+                        if use_pn and not mesh_is_simplified:        # high-passed normal patch term (:806-821): its own patch draw, the rgb draw's weights (as the reference)
                             pick_n = draw('patch_perm_normal')
                             out_np, tgt_np = _patches(out_normals, render_size, patch_size), _patches(target_n, render_size, patch_size)
                             views = views + lpips_patch_loss(nerf.patch_loss, highpass(out_np[pick_n]), highpass(tgt_np[pick_n]), w_pick) * patch_normal_weight
                     loss = loss + views * share
 
                 optimizer.zero_grad()
-                loss.backward()
+                if torch.is_tensor(loss):                    # (a rank without a view of this batch has nothing to add on a decimated mesh)
+                    loss.backward()
                 if world > 1:
                     if fused and hasattr(optimizer, 'flat_grad'):
                         optimizer.fold_grads()
@@ -333,10 +338,21 @@ def mesh_optim(self, tgt_images, tgt_masks, tgt_normals,                        
                         view_shard.allreduce_grads([p_ for g_ in optimizer.param_groups for p_ in g_['params']])
                 optimizer.step()
 
-                with torch.enable_grad():
-                    mesh_verts, mesh_faces = dmtet(tet_verts + deform, tet_sdf, tet_indices)
-                    in_mesh = Mesh(v=mesh_verts, f=mesh_faces.int(), device=device)
-                    in_mesh.auto_normal()
+                if not mesh_is_simplified:
+                    with torch.enable_grad():
+                        mesh_verts, mesh_faces = dmtet(tet_verts + deform, tet_sdf, tet_indices)
+                        if mesh_reduction < 1 and is_end and (inverse_steps - (step + 1)) <= mesh_simplify_texture_steps:
+                            # (:829-844) decimate once, then fit only the texture: the field's parameters under a fresh optimiser.  The
+                            # reference calls open3d on the CPU here; so does mve_mesh_simplify (host C++, identical on every rank)
+                            mesh_verts, mesh_faces = simplify_mesh(mesh_verts.detach(), mesh_faces, round(mesh_faces.shape[0] * mesh_reduction))
+                            mesh_verts, indices = torch.unique(mesh_verts, dim=0, return_inverse=True, sorted=False)
+                            mesh_faces = indices[mesh_faces]
+                            optimizer = optimizer.__class__(list(dec.parameters()), lr=lr)
+                            if dec.grad_sink is not None:
+                                dec.grad_sink = optimizer
+                            mesh_is_simplified = True
+                        in_mesh = Mesh(v=mesh_verts, f=mesh_faces.int(), device=device)
+                        in_mesh.auto_normal()
                 if debug:
                     print('mesh_optim step %d: loss %.5f, %d vertices, %d faces' % (step, float(loss), mesh_verts.shape[0], mesh_faces.shape[0]))
     finally:

@@ -238,6 +238,24 @@ def make_tet_grid(resolution, device='cpu'):
 
 # ---- MeshRenderer (base_mesh_renderer.py:191-395) -------------------------------------------------------------------------------
 
+def simplify_mesh(verts, faces, target_faces):
+    """Quadric-error edge-collapse decimation of a triangle mesh to ``target_faces`` faces: what ``mesh_optim`` asks of open3d's
+    ``simplify_quadric_decimation(target, boundary_weight=0)`` at the last step when ``mesh_reduction < 1``
+    (``mvedit_3d_pipeline.py:829-844``) -- on the host there as here (``mve_mesh_simplify``, C++; no kernel is launched).
+    ``verts`` [V,3] float, ``faces`` [F,3] int (any device) -> (verts', faces' int64) on the device of ``verts``."""
+    import ctypes
+    import numpy as np
+    from ._lib import get_lib, check
+    v = np.ascontiguousarray(verts.detach().float().cpu().numpy())
+    f = np.ascontiguousarray(faces.detach().cpu().numpy().astype(np.int32))
+    out_v, out_f, counts = np.empty_like(v), np.empty_like(f), np.zeros(2, np.uint32)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    check(get_lib().mve_mesh_simplify(p(v), ctypes.c_uint32(len(v)), p(f), ctypes.c_uint32(len(f)), ctypes.c_uint32(int(target_faces)), p(out_v), p(out_f),
+                                      p(counts)), 'mve_mesh_simplify')
+    return (torch.from_numpy(out_v[:counts[0]].copy()).to(verts.device, verts.dtype),
+            torch.from_numpy(out_f[:counts[1]].astype(np.int64)).to(faces.device))
+
+
 def make_divisible(x, m=8):
     """Smallest multiple of ``m`` not below ``x`` (``base_mesh_renderer.py:11-12``)."""
     return m * int(math.ceil(x / m))

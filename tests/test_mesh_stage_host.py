@@ -450,3 +450,85 @@ def test_mesh_optim_with_the_fused_objective_matches_the_eager_one():
             res[fused] = (tet_sdf.detach().clone(), deform.detach().clone(), field.w.detach().clone())
     for a_, b_ in zip(res[True], res[False]):
         assert (a_ - b_).abs().max() < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ decimation of the final mesh
+def _manifold_stats(v, f):
+    import numpy as np
+    und = np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]), axis=1)
+    _, c = np.unique(und, axis=0, return_counts=True)
+    _, cd = np.unique(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]), axis=0, return_counts=True)
+    vol = np.einsum('ij,ij->i', v[f[:, 0]], np.cross(v[f[:, 1]], v[f[:, 2]])).sum() / 6
+    return bool((c == 2).all()), bool((cd == 1).all()), len(v) - len(c) + len(f), float(vol)
+
+
+def test_simplify_mesh_properties():
+    """``mve_mesh_simplify`` (host C++ in place of open3d's quadric decimation -- parity unpinned, so properties): exact face budget, a
+    closed oriented 2-manifold stays one (Euler characteristic 2), the enclosed volume and the surface are preserved."""
+    import numpy as np
+    from scipy.spatial import cKDTree
+    from mvedit_b200.mesh_renderer import simplify_mesh
+    grid = make_tet_grid(32)
+    tv = -grid['vertices'] * 2 * 0.9
+    sdf = 0.5 - tv.norm(dim=-1) + 0.08 * torch.sin(7 * tv[:, 0]) * torch.sin(6 * tv[:, 1])
+    mv, mf = DMTet('cpu')(tv, sdf, grid['indices'])
+    closed, oriented, euler, vol = _manifold_stats(mv.numpy(), mf.numpy())
+    assert closed and oriented and euler == 2
+    for frac in (0.5, 0.25, 0.05):
+        target = round(mf.shape[0] * frac)
+        v2, f2 = simplify_mesh(mv, mf, target)
+        assert target - 1 <= f2.shape[0] <= target and f2.dtype == torch.int64 and v2.dtype == mv.dtype        # a collapse removes two faces
+        c2, o2, e2, vol2 = _manifold_stats(v2.numpy(), f2.numpy())
+        assert c2 and o2 and e2 == 2 and abs(vol2 - vol) < 0.01 * vol / frac ** 0.5, (frac, c2, o2, e2, vol2, vol)
+        d, _ = cKDTree(mv.numpy()).query(v2.numpy())
+        assert d.max() < 0.03 / frac ** 0.5                                    # vertices stay on the input surface (grid spacing 0.056)
+        assert int(f2.max()) == v2.shape[0] - 1 and len(torch.unique(f2)) == v2.shape[0]          # compact vertex list
+    v3, f3 = simplify_mesh(mv, mf, mf.shape[0] + 10)                           # nothing to do
+    assert f3.shape == mf.shape and torch.equal(torch.sort(v3.norm(dim=-1)).values, torch.sort(mv.norm(dim=-1)).values)
+    v4, f4 = simplify_mesh(mv, mf, 0)                                          # as far as legal collapses go: never below a tetrahedron
+    assert 4 <= f4.shape[0] < 100 and _manifold_stats(v4.numpy(), f4.numpy())[:3] == (True, True, 2)
+
+
+def test_mesh_optim_decimates_at_the_end_and_then_fits_only_the_texture():
+    """``mesh_reduction < 1`` on the last call (mvedit_3d_pipeline.py:829-844): geometry steps, one decimation once the remaining steps fit in
+    ``mesh_simplify_texture_steps``, then colour-only steps on the fixed mesh under a fresh optimiser."""
+    n, size = 4, 32
+    poses, intr = _cameras(n, size, seed=2)
+    lights = torch.nn.functional.normalize(torch.randn(n, 3, generator=torch.Generator().manual_seed(4)), dim=-1)
+    yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing='ij')
+    disc = (((xx - 15.5) ** 2 + (yy - 15.5) ** 2).float().sqrt() < 9).float()
+    tgt_masks = disc[None, None, :, :, None].expand(1, n, -1, -1, -1).contiguous()
+    tgt_images = (torch.rand(1, n, size, size, 3, generator=torch.Generator().manual_seed(5)) * 0.5 + 0.25) * tgt_masks + (1 - tgt_masks)
+    field = ToyField()
+    nerf = SimpleNamespace(decoder=field, pixel_loss=L1LossMod(loss_weight=1.2), patch_loss=_FakePatchLoss())
+    with host_harness.routed(dr):
+        tet_verts, tet_indices, tet_sdf = mopt.init_tet(nerf, None, density_thresh=5.0, tets=make_tet_grid(16))
+        deform = torch.zeros_like(tet_verts).requires_grad_(True)
+        tet_sdf.requires_grad_(True)
+        opt = torch.optim.Adam([{'params': list(field.parameters())}, {'params': [tet_sdf, deform], 'lr': 1e-3}], lr=0.01)
+        dm = DMTet('cpu')
+        with torch.enable_grad():
+            mv, mf = dm(tet_verts + deform, tet_sdf, tet_indices)
+            mesh = Mesh(v=mv, f=mf.int())
+            mesh.auto_normal()
+        pipe = SimpleNamespace(nerf=nerf, mesh_renderer=MeshRenderer(near=0.01, far=100), normal_bg=[0.5, 0.5, 1.0], tonemapping=None)
+        snaps = []
+        real_simplify = mopt.simplify_mesh
+
+        def spy(v, f, target):
+            snaps.append((tet_sdf.detach().clone(), deform.detach().clone(), field.w.detach().clone(), f.shape[0], target,
+                          _manifold_stats(v.numpy(), f.numpy())[:3]))
+            return real_simplify(v, f, target)
+        mopt.simplify_mesh = spy
+        try:
+            out = mopt.mesh_optim(pipe, tgt_images, tgt_masks, None, opt, 0.01, 0.8, 2, 2, 2, 3, 0.5, 0.0, 0.02, 0.1, 5.0, None, tet_verts, deform,
+                                  tet_sdf, tet_indices, dm, mesh, size, intr, size, poses, torch.ones(n), lights, 16, True, 0.2, 0.5)
+        finally:
+            mopt.simplify_mesh = real_simplify
+    # inverse_steps = max(2, 3) = 3 and 3 - (step + 1) <= 3 at step 0: one geometry step, the decimation, two texture steps
+    assert len(snaps) == 1
+    sdf1, deform1, w1, n_faces, target, topo = snaps[0]
+    assert target == round(n_faces * 0.5) and target - 1 <= out.f.shape[0] <= target and not out.v.requires_grad
+    assert torch.equal(tet_sdf.detach(), sdf1) and torch.equal(deform.detach(), deform1)       # the geometry is frozen afterwards ...
+    assert (field.w.detach() - w1).abs().max() > 1e-3                                          # ... the colour field keeps fitting
+    assert _manifold_stats(out.v.numpy(), out.f.long().numpy())[:3] == topo                     # same topology as the marching-tets mesh
