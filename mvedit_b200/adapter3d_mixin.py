@@ -44,8 +44,8 @@ class Adapter3DMixin:
 
     def load_init_mesh(self, in_model, camera_poses, intrinsics, intrinsics_size, render_bs, shading_fun=None, diff_size=512):
         """Render an input mesh from every camera at 2x supersampling (adapter3d_mixin.py:21-66) -> (mesh, images [N,s,s,3] composited on
-        ``self.bg_color``, alphas [N,s,s,1], inverse depths [N,s,s]).  ``in_model`` is a ``mesh_renderer.Mesh`` or a path to an ``.obj`` / binary ``.ply``
-        (``Mesh.load``; ``.glb`` reading is not built)."""
+        ``self.bg_color``, alphas [N,s,s,1], inverse depths [N,s,s]).  ``in_model`` is a ``mesh_renderer.Mesh`` or a path to an ``.obj`` / ``.glb`` / binary
+        ``.ply`` (``Mesh.load``)."""
         if isinstance(in_model, str):
             from .mesh_renderer import Mesh
             in_mesh = Mesh.load(in_model, flip_yz=in_model.endswith(('.obj', '.glb'))).to(camera_poses.device)

@@ -190,14 +190,94 @@ def load_ply(path, device=None):
     return Mesh(v=torch.from_numpy(v.copy()).to(device), f=torch.from_numpy(faces['i'].copy()).to(device), device=device, textureless=True)
 
 
+_GLTF_DTYPES = {5120: 'i1', 5121: 'u1', 5122: '<i2', 5123: '<u2', 5125: '<u4', 5126: '<f4'}
+_GLTF_NCOMP = {'SCALAR': 1, 'VEC2': 2, 'VEC3': 3, 'VEC4': 4, 'MAT4': 16}
+
+
+def load_glb(path, device=None):
+    """Binary glTF 2.0 with ONE mesh of one triangle primitive -- what ``Mesh.load_trimesh`` accepts (mesh_utils.py:262-345; the runner's
+    3D-to-3D inputs are the ``.glb`` files the pipelines write): positions, indices, optional normals / TEXCOORD_0 / COLOR_0 and the
+    base-colour texture.  As the reference (which reads ``geometry[key]`` of the trimesh scene) the node transforms are not applied, and
+    ``vt`` is the file's TEXCOORD_0 as stored (trimesh flips v on load, the reference flips it back, :301-302)."""
+    from .mesh_renderer import Mesh
+    raw = open(path, 'rb').read()
+    magic, version, total = struct.unpack_from('<4sII', raw, 0)
+    if magic != b'glTF' or version != 2:
+        raise ValueError('%s is not a binary glTF 2.0 file' % path)
+    off, js, bin_chunk = 12, None, b''
+    while off + 8 <= min(total, len(raw)):
+        n, kind = struct.unpack_from('<I4s', raw, off)
+        body = raw[off + 8:off + 8 + n]
+        if kind == b'JSON':
+            js = json.loads(body.decode('utf-8'))
+        elif kind == b'BIN\x00':
+            bin_chunk = body
+        off += 8 + n
+    meshes = js.get('meshes', [])
+    if len(meshes) != 1 or len(meshes[0]['primitives']) != 1:
+        raise NotImplementedError('%s contains more than one mesh / primitive, not supported!' % path)
+    prim = meshes[0]['primitives'][0]
+    if prim.get('mode', 4) != 4:
+        raise NotImplementedError('load_glb: only triangle lists (mode 4) are read')
+
+    def view_bytes(i):
+        bv = js['bufferViews'][i]
+        if bv.get('buffer', 0) != 0 or 'uri' in js['buffers'][0]:
+            raise NotImplementedError('load_glb: external buffers are not read')
+        return bin_chunk[bv.get('byteOffset', 0):bv.get('byteOffset', 0) + bv['byteLength']], bv.get('byteStride')
+
+    def accessor(i):
+        acc = js['accessors'][i]
+        data, stride = view_bytes(acc['bufferView'])
+        dt, nc = np.dtype(_GLTF_DTYPES[acc['componentType']]), _GLTF_NCOMP[acc['type']]
+        start, count, item = acc.get('byteOffset', 0), acc['count'], dt.itemsize * nc
+        if stride in (None, 0, item):
+            arr = np.frombuffer(data, dt, count * nc, start).reshape(count, nc)
+        else:
+            arr = np.stack([np.frombuffer(data, dt, nc, start + k * stride) for k in range(count)])
+        if acc.get('normalized', False) and dt.kind in 'iu':
+            arr = arr.astype(np.float32) / np.iinfo(dt).max
+        return arr
+    attr = prim['attributes']
+    v = accessor(attr['POSITION']).astype(np.float32)
+    f = accessor(prim['indices']).reshape(-1, 3).astype(np.int32) if 'indices' in prim else np.arange(len(v), dtype=np.int32).reshape(-1, 3)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dt)
+    mesh = Mesh(v=t(v, torch.float32), f=t(f, torch.int32), device=device)
+    if 'NORMAL' in attr:
+        mesh.vn, mesh.fn = t(accessor(attr['NORMAL']).astype(np.float32), torch.float32), mesh.f
+    if 'TEXCOORD_0' in attr:
+        mesh.vt, mesh.ft = t(accessor(attr['TEXCOORD_0']).astype(np.float32), torch.float32), mesh.f
+    if 'COLOR_0' in attr:
+        col = accessor(attr['COLOR_0'])
+        col = col.astype(np.float32) / (np.iinfo(col.dtype).max if col.dtype.kind in 'iu' else 1.0)
+        mesh.vc = t(np.concatenate([col, np.ones((len(col), 1), np.float32)], axis=1) if col.shape[1] == 3 else col, torch.float32)
+    tex = js.get('materials', [{}])[prim.get('material', 0)].get('pbrMetallicRoughness', {}).get('baseColorTexture') if js.get('materials') else None
+    if tex is not None:
+        import io
+        from PIL import Image
+        img = js['images'][js['textures'][tex['index']]['source']]
+        if 'bufferView' in img:
+            blob = view_bytes(img['bufferView'])[0]
+        elif img.get('uri', '').startswith('data:'):
+            import base64
+            blob = base64.b64decode(img['uri'].split(',', 1)[1])
+        else:
+            blob = open(os.path.join(os.path.dirname(path), img['uri']), 'rb').read()
+        mesh.albedo = t(np.asarray(Image.open(io.BytesIO(blob))).astype(np.float32) / 255, torch.float32)
+    mesh.textureless = mesh.albedo is None
+    return mesh
+
+
 def load(path, resize=False, auto_uv=True, flip_yz=False, force_auto_normal=False, device=None):
     """``Mesh.load`` (mesh_utils.py:80-113): read, fix normals / UVs, optional y-up -> z-up flip (the inverse of ``write``'s)."""
     if path.endswith('.obj'):
         mesh = load_obj(path, device)
     elif path.endswith('.ply'):
         mesh = load_ply(path, device)
+    elif path.endswith('.glb'):
+        mesh = load_glb(path, device)
     else:
-        raise NotImplementedError('Mesh.load: %s -- only .obj and the binary .ply of Mesh.write are read (.glb needs a glTF reader)' % path)
+        raise NotImplementedError('Mesh.load: %s -- .obj, .glb and the binary .ply of Mesh.write are read' % path)
     if resize:
         vmin, vmax = mesh.v.min(dim=0).values, mesh.v.max(dim=0).values
         mesh.ori_center, mesh.ori_scale = (vmax + vmin) / 2, 1.2 / float((vmax - vmin).max())

@@ -96,3 +96,45 @@ def test_obj_and_ply_load_back(tmp_path):
     (tmp_path / 'quad.obj').write_text('v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n')
     quad = Mesh.load(str(tmp_path / 'quad.obj'), auto_uv=False)
     assert quad.f.tolist() == [[0, 1, 2], [0, 2, 3]] and quad.vt is None
+
+
+def test_glb_load_back(tmp_path):
+    """``Mesh.load`` of a binary glTF (the reference goes through trimesh, mesh_utils.py:262-345): the file the writer produced comes back
+    with the same triangles, uvs, normals and texture; a hand-built file with strided / normalised accessors, vertex colours and no
+    indices is decoded too."""
+    m = _mesh()
+    p = str(tmp_path / 'a.glb')
+    m.write(p, flip_yz=True)
+    r = Mesh.load(p, flip_yz=True)
+    np.testing.assert_allclose(r.v.numpy()[r.f.numpy()], m.v.numpy()[m.f.numpy()], atol=1e-6)              # same triangles (vertices re-indexed by the uvs)
+    np.testing.assert_allclose(r.vt.numpy()[r.ft.numpy()], m.vt.numpy()[m.ft.numpy()], atol=1e-6)
+    np.testing.assert_allclose(r.vn.numpy()[r.fn.numpy()], m.vn.numpy()[m.fn.numpy()], atol=1e-5)
+    assert r.textureless is False and r.albedo.shape == (16, 16, 3) and (r.albedo - m.albedo[..., :3]).abs().max() < 1 / 255 + 1e-6
+    # hand-built: interleaved POSITION (stride 16), normalised u16 TEXCOORD_0, u8 COLOR_0, no indices, no material
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32)
+    inter = np.zeros((6, 4), np.float32)
+    inter[:, :3] = pos
+    uv = (np.array([[0, 0], [1, 0], [0, 1], [1, 0], [1, 1], [0, 1]], np.float32) * 65535).astype('<u2')
+    col = np.array([[255, 0, 0, 255]] * 3 + [[0, 255, 0, 128]] * 3, np.uint8)
+    blobs = [inter.tobytes(), uv.tobytes(), col.tobytes()]
+    views, off = [], 0
+    for k, b in enumerate(blobs):
+        views.append(dict(buffer=0, byteOffset=off, byteLength=len(b), **({'byteStride': 16} if k == 0 else {})))
+        off += len(b) + (-len(b)) % 4
+    gltf = dict(asset=dict(version='2.0'), meshes=[dict(primitives=[dict(attributes=dict(POSITION=0, TEXCOORD_0=1, COLOR_0=2))])],
+                buffers=[dict(byteLength=off)], bufferViews=views,
+                accessors=[dict(bufferView=0, componentType=5126, count=6, type='VEC3'),
+                           dict(bufferView=1, componentType=5123, count=6, type='VEC2', normalized=True),
+                           dict(bufferView=2, componentType=5121, count=6, type='VEC4', normalized=True)])
+    js = json.dumps(gltf).encode()
+    js += b' ' * ((-len(js)) % 4)
+    bin_ = b''.join(b + b'\x00' * ((-len(b)) % 4) for b in blobs)
+    q = str(tmp_path / 'hand.glb')
+    with open(q, 'wb') as fp:
+        fp.write(struct.pack('<4sII', b'glTF', 2, 28 + len(js) + len(bin_)) + struct.pack('<I4s', len(js), b'JSON') + js
+                 + struct.pack('<I4s', len(bin_), b'BIN\x00') + bin_)
+    h = Mesh.load(q, auto_uv=False)
+    assert h.f.tolist() == [[0, 1, 2], [3, 4, 5]] and h.textureless is True and h.vn is not None
+    np.testing.assert_allclose(h.v.numpy(), pos)
+    np.testing.assert_allclose(h.vt.numpy(), uv.astype(np.float32) / 65535)
+    np.testing.assert_allclose(h.vc.numpy(), col.astype(np.float32) / 255)
