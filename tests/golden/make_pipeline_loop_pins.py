@@ -1,0 +1,324 @@
+"""Generates tests/golden/pipeline_loop_pins.npz by RUNNING the reference's own ``MVEdit3DPipeline.__call__``
+(lib/pipelines/mvedit_3d_pipeline.py:875-1500) -- cut out by AST and executed unmodified on the CPU -- around deterministic toy components,
+together with the reference's own ``load_init_images`` / ``load_cond_images`` (same file), ``get_noise_pred`` / ``_p1`` / ``_p2``
+(adapter3d_mixin.py), ``get_noise_scales`` (lib/core/diffusion.py), ``light_sampling`` (camera_utils.py), ``get_camera_dists`` /
+``prune_cameras`` / ``join_prompts`` (lib/pipelines/utils.py), ``normalize_depth`` (geometry_utils.py) and the default schedules.  What is
+pinned is the LOOP BODY: camera re-ordering and pruning, the denoise batches of both modes (plain CFG and the
+reference-image pairs), pred_x0, the targets and every argument handed to ``nerf_optim`` at every step, the render -> enhancer -> resize
+hand-over, dynamic blending through ``vae.encode``, the merged noise incl. the reference half, the solver calls and the latent restart.
+
+Toys shared with the test (tests/test_pipeline_loop_pins.py): a pooling VAE, the toy UNet / ControlNets of make_mixin_pins.py, a
+procedural "field" whose renders depend on pose, intrinsics and on how often it was fitted, a threshold segmenter, a 4x upsampler as
+enhancer; ``nerf_optim`` is a recorder.  The solver is this repo's ``EulerAncestralScheduler`` (closed-form checks elsewhere) behind a
+diffusers-shaped adapter that draws its ancestral noise from the global RNG exactly where the product's loop draws it.
+
+Run:  python tests/golden/make_pipeline_loop_pins.py      (CPU, ~1 min)
+"""
+import ast
+import importlib.util
+import math
+import os
+import sys
+import types
+from copy import deepcopy
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = '/root/reference'
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'pipeline_loop_pins.npz')
+N, IMG, D = 5, 512, 8
+spec = importlib.util.spec_from_file_location('make_mixin_pins', os.path.join(os.path.dirname(os.path.abspath(__file__)), 'make_mixin_pins.py'))
+mixin_gen = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(mixin_gen)
+
+
+# ------------------------------------------------------------------------------------------------ toys (both sides)
+class ToyUNet(mixin_gen.ToyUNet):
+    dtype, device = torch.float32, torch.device('cpu')
+
+
+class _Dist:
+    def __init__(self, z):
+        self.mean = z
+
+    def sample(self):
+        return self.mean
+
+
+class ToyVAE:
+    """encode: 8x average pooling + a 3 -> 4 channel mix; decode: the transposed mix + nearest upsampling.  Both APIs: diffusers'
+    (``encode(x).latent_dist``, ``decode(z, return_dict=False)[0]``) and the product's ``decode_images``."""
+    config = types.SimpleNamespace(scaling_factor=0.18215)
+
+    def __init__(self):
+        g = torch.Generator().manual_seed(21)
+        self.m = torch.randn(3, 4, generator=g) * 0.6
+
+    def encode(self, x, return_dict=True):
+        d = _Dist(torch.einsum('nchw,cd->ndhw', F.avg_pool2d(x.float(), 8), self.m))
+        return types.SimpleNamespace(latent_dist=d) if return_dict else (d,)
+
+    def decode(self, z, return_dict=True):
+        img = torch.tanh(F.interpolate(torch.einsum('ndhw,cd->nchw', z.float(), self.m), scale_factor=8, mode='nearest') * 0.8)
+        return types.SimpleNamespace(sample=img) if return_dict else (img,)
+
+    def decode_images(self, pred_x0):
+        return (self.decode(pred_x0 / self.config.scaling_factor, return_dict=False)[0] / 2 + 0.5).clamp(min=0, max=1).permute(0, 2, 3, 1).float()
+
+
+def toy_segmentation(images_nchw):
+    return torch.sigmoid((0.62 - images_nchw.float().mean(dim=1, keepdim=True)) * 25)
+
+
+class ToyEnhancer(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.gain = nn.Parameter(torch.tensor(1.03))
+
+    def forward(self, x):
+        return F.interpolate(x.float(), scale_factor=4, mode='bilinear', align_corners=False) * self.gain - 0.01
+
+
+class ToyDecoder(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w = nn.Parameter(torch.ones(3))
+        self.state_dict_bak = None
+        self.grad_sink = None
+
+    def backup_state_dict(self):
+        self.state_dict_bak = deepcopy(self.state_dict())
+
+    def restore_state_dict(self):
+        self.load_state_dict(self.state_dict_bak)
+
+
+class ToyField(nn.Module):
+    """Stands for BaseNeRF: ``render`` is a procedural blob whose phase moves with the camera position and with ``fits`` (the number of
+    ``nerf_optim`` calls so far), so every step of the loop renders something new."""
+
+    def __init__(self):
+        super().__init__()
+        self.decoder, self.bg_color, self.fits, self.grid_size = ToyDecoder(), 1.0, 0, 8
+
+    def get_init_density_grid(self, n, device=None):
+        return torch.zeros(n, 8 ** 3, dtype=torch.float16)
+
+    def get_init_density_bitfield(self, n, device=None):
+        return torch.zeros(n, 8 ** 3 // 8, dtype=torch.uint8)
+
+    def render(self, decoder, code, density_bitfield, h, w, intrinsics, poses, cfg=None, perturb=False, normal_bg=(0.5, 0.5, 1.0)):
+        K, P = intrinsics[0].float(), poses[0].float()
+        yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32) + 0.5, torch.arange(w, dtype=torch.float32) + 0.5, indexing='ij')
+        u = (xx[None] - K[:, 2, None, None]) / K[:, 0, None, None]
+        v = (yy[None] - K[:, 3, None, None]) / K[:, 1, None, None]
+        ph = (P[:, :3, 3] * torch.tensor([1.0, 0.7, 0.4])).sum(-1)[:, None, None] + 0.35 * self.fits
+        alpha = torch.sigmoid((0.035 - (u * u + v * v)) * 120)
+        rgb = torch.stack([0.5 + 0.45 * torch.sin(ph + 9 * u + k) for k in range(3)], dim=-1) * alpha[..., None]
+        depth = alpha * (0.3 + 0.05 * torch.cos(ph + 7 * v))
+        nfg = F.normalize(torch.stack([3 * u, -3 * v, torch.ones_like(u)], dim=-1), dim=-1) / 2 + 0.5
+        normal = nfg * alpha[..., None] + nfg.new_tensor(list(normal_bg)) * (1 - alpha[..., None])
+        return torch.cat([rgb, alpha[..., None]], dim=-1)[None], depth[None], normal[None], nfg[None]
+
+
+def inputs():
+    from tests import synth
+    g = torch.Generator().manual_seed(2)
+    poses = torch.from_numpy(synth.surround_poses(N, seed=1)).float()
+    f = 0.5 * IMG / math.tan(math.radians(15))
+    intr = torch.tensor([f, f, IMG / 2, IMG / 2])
+    yy, xx = torch.meshgrid(torch.arange(IMG), torch.arange(IMG), indexing='ij')
+    init = []
+    for k in range(N):
+        a = ((((xx - 255.5 - 20 * k) ** 2 + (yy - 255.5) ** 2).float().sqrt() < 150).float() * 255).to(torch.uint8)
+        rgb = (torch.rand(3, generator=g)[None, None] * 200 + 30 + 20 * torch.sin(xx / 37.0 + k)[..., None]).clamp(0, 255).to(torch.uint8)
+        init.append(torch.cat([rgb, a[..., None]], dim=-1).numpy())
+    embeds = torch.randn(2 * N, 77, D, generator=g)
+    return poses, intr, init, embeds
+
+
+CASES = dict(
+    optim_only=dict(optim_only=True, num_inference_steps=4),
+    two_pass=dict(mode='2-pass', use_reference=False, blend_weight=0.0),
+    one_pass_dynamic=dict(mode='1-pass', use_reference=False, blend_weight='dynamic'),
+    reference_pairs=dict(mode='2-pass', use_reference=True, blend_weight='dynamic'),
+    from_noise=dict(mode='1-pass', use_reference=False, blend_weight=0.0, denoising_strength=None, num_inference_steps=3),
+    targets=dict(mode='1-pass', use_reference=False, blend_weight=0.0, use_normal=True, depth_weight=0.4),
+    from_noise_reference=dict(mode='2-pass', use_reference=True, blend_weight=0.0, denoising_strength=None, num_inference_steps=3))
+
+
+def call_kwargs(case, poses, intr, init):
+    kw = dict(prompt='a toy', negative_prompt='', init_images=init, camera_poses=poses, intrinsics=intr, intrinsics_size=IMG,
+              use_normal=False, keep_views=[3], guidance_scale=5.0, num_inference_steps=6, denoising_strength=0.5, progress_to_dmtet=1.0,
+              patch_size=64, diff_bs=4, render_bs=2, n_inverse_rays=4096, n_inverse_steps=7, init_inverse_steps=11,
+              render_size_p=lambda p: 128, max_num_views=lambda p, q: 5 if p < 0.5 else 3, ambient_light=0.2, bake_texture=False)
+    kw.update(CASES[case])
+    if kw['use_normal']:                          # image-to-3D targets: one normal map and one depth map per view, all different
+        g = torch.Generator().manual_seed(9)
+        kw['normals'] = [(F.normalize(torch.rand(64, 64, 3, generator=g) - 0.5 + torch.tensor([0.0, 0.0, 1.0 + k]), dim=-1) * 127.5 + 127.5
+                          ).to(torch.uint8).numpy() for k in range(N)]
+        kw['depths'] = [(0.1 * (k + 1) + 0.05 * torch.rand(96, 96, generator=g)).numpy() for k in range(N)]
+    return kw
+
+
+MAPS = ('tgt_images', 'tgt_masks', 'tgt_normals', 'tgt_depths')
+RECORD = ('tgt_images', 'tgt_masks', 'lr', 'inverse_steps', 'n_inverse_rays', 'patch_rgb_weight', 'patch_normal_weight', 'alpha_soften',
+          'normal_reg_weight', 'entropy_weight', 'render_size', 'intrinsics', 'intrinsics_size', 'camera_poses', 'cam_weights', 'cam_lights',
+          'patch_size', 'is_init', 'bg_width', 'ambient_light', 'dt_gamma_scale', 'init_shaded')
+
+
+def record_call(log, field, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_steps, n_inverse_rays, patch_rgb_weight,
+                patch_normal_weight, alpha_soften, normal_reg_weight, entropy_weight, nerf_code, density_grid, density_bitfield, render_size,
+                intrinsics, intrinsics_size, camera_poses, cam_weights, cam_lights, patch_size, is_init, bg_width, ambient_light,
+                dt_gamma_scale, init_shaded, **kw):
+    loc = locals()
+    rec = {k: (loc[k].detach().float().clone() if torch.is_tensor(loc[k]) else loc[k]) for k in RECORD}
+    if tgt_normals is not None:
+        rec['tgt_normals'] = tgt_normals.detach().float().clone()
+    if kw.get('tgt_depths') is not None:
+        rec['tgt_depths'], rec['depth_weight'] = kw['tgt_depths'].detach().float().clone(), kw['depth_weight']
+    log.append(rec)
+    field.fits += 1
+
+
+def flatten(log, prefix):
+    """The recorded calls as arrays; the per-view target maps as 8x8 block means plus per-view standard deviations (the fixture stays small;
+    a swapped view, a missed blend or a wrong resize moves both)."""
+    out = {prefix + 'steps': np.array(len(log))}
+    for i, rec in enumerate(log):
+        for k, v in rec.items():
+            if k in MAPS:
+                x = v[0].permute(0, 3, 1, 2)
+                out['%s%d_%s_pooled' % (prefix, i, k)] = F.avg_pool2d(x, 8).numpy()
+                out['%s%d_%s_std' % (prefix, i, k)] = x.flatten(2).std(dim=2).numpy()
+                out['%s%d_%s_shape' % (prefix, i, k)] = np.array(v.shape)
+            else:
+                out['%s%d_%s' % (prefix, i, k)] = v.numpy() if torch.is_tensor(v) else np.array(float(v))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ the reference side
+class DiffusersShapedScheduler:
+    """``EulerAncestralScheduler`` behind the call shapes the reference's loop uses (``step(..., return_dict=False)[0]`` drawing its own
+    ancestral noise from the global RNG, like diffusers' ``randn_tensor`` without a generator)."""
+    order = 1
+
+    def __init__(self):
+        from mvedit_b200.schedulers import EulerAncestralScheduler
+        self.s = EulerAncestralScheduler()
+        self.betas, self.num_train_timesteps = self.s.betas, self.s.num_train_timesteps
+
+    def set_timesteps(self, n, device=None):
+        self.s.set_timesteps(n, device='cpu')
+        self.timesteps, self.init_noise_sigma = self.s.timesteps, self.s.init_noise_sigma
+
+    def scale_model_input(self, sample, t):
+        return self.s.scale_model_input(sample, t)
+
+    def add_noise(self, x, noise, timesteps):
+        return self.s.add_noise(x, noise, timesteps)
+
+    def step(self, model_output, t, sample, return_dict=True):
+        return (self.s.step(model_output, t, sample, torch.randn(sample.shape)),)
+
+
+def extract(rel, names, env, methods=False):
+    tree = ast.parse(open(os.path.join(REF, rel)).read())
+    found = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in names and node.name not in found:
+            node.decorator_list, node.returns = [], None
+            for a in node.args.args + node.args.kwonlyargs:
+                a.annotation = None
+            mod = ast.Module(body=[node], type_ignores=[])
+            ast.fix_missing_locations(mod)
+            exec(compile(mod, rel, 'exec'), env)
+            found[node.name] = env[node.name]
+    assert not (set(names) - set(found)), set(names) - set(found)
+    return found
+
+
+def load(name, rel):
+    s = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    m = importlib.util.module_from_spec(s)
+    s.loader.exec_module(m)
+    return m
+
+
+def main():
+    import PIL
+    import PIL.Image
+    for stub in ('mcubes', 'skimage'):
+        sys.modules.setdefault(stub, types.ModuleType(stub))
+    sys.modules['skimage'].morphology = types.ModuleType('morphology')
+    cam, gu, diff, rot = (load('ref_cam', 'lib/core/utils/camera_utils.py'), load('ref_gu', 'lib/core/utils/geometry_utils.py'),
+                          load('ref_diffusion', 'lib/core/diffusion.py'), load('ref_rot', 'lib/ops/rotation_conversions.py'))
+    uenv = dict(torch=torch, F=F, np=np, matrix_to_quaternion=rot.matrix_to_quaternion)
+    U = extract('lib/pipelines/utils.py', ['get_camera_dists', 'prune_cameras', 'join_prompts'], uenv)
+
+    class MultiControlNetModel:
+        def __init__(self, nets):
+            self.nets = list(nets)
+
+        def __call__(self, sample, t, encoder_hidden_states=None, controlnet_cond=None, conditioning_scale=None, guess_mode=False,
+                     added_cond_kwargs=None, return_dict=True):
+            acc = None
+            for net, cond, sc in zip(self.nets, controlnet_cond, conditioning_scale):
+                acc = net(sample, t, encoder_hidden_states=encoder_hidden_states, controlnet_cond=cond, conditioning_scale=sc, accumulate=acc)
+            return acc
+    menv = dict(torch=torch, copy=__import__('copy').copy, MultiControlNetModel=MultiControlNetModel,
+                unet_enc=lambda unet, *a, **k: unet.enc(*a, **k), unet_dec=lambda unet, *a, **k: unet.dec(*a, **k))
+    M = extract('lib/pipelines/adapter3d_mixin.py', ['get_noise_pred', 'get_noise_pred_p1', 'get_noise_pred_p2'], menv)
+
+    class _Never:
+        pass
+    tb = []
+    class _NumpyCompat:                         # the reference was written against numpy 1.x (np.cumproduct, :1103)
+        cumproduct = staticmethod(np.cumprod)
+
+        def __getattr__(self, k):
+            return getattr(np, k)
+    penv = dict(torch=torch, F=F, np=_NumpyCompat(), PIL=PIL, math=math, deepcopy=deepcopy, get_module_device=lambda m: 'cpu', DMTet=lambda device: None,
+                light_sampling=cam.light_sampling, join_prompts=U['join_prompts'], get_camera_dists=U['get_camera_dists'],
+                prune_cameras=U['prune_cameras'], DPMSolverSDEScheduler=_Never, DPMSolverMultistepScheduler=_Never,
+                get_noise_scales=diff.get_noise_scales, normalize_depth=gu.normalize_depth, apply_cross_image_attn_proc=lambda u: None,
+                remove_cross_image_attn_proc=lambda u: None, do_segmentation=None, tqdm=lambda x: x,
+                traceback=types.SimpleNamespace(format_exc=lambda: tb.append(__import__('traceback').format_exc()) or tb[-1]))
+    names = ['default_lr_multiplier', 'default_max_num_views', 'default_render_size_p', 'default_lr_schedule', 'default_patch_rgb_weight',
+             'default_patch_normal_weight', 'default_entropy_weight', 'default_normal_reg_weight']
+    extract('lib/pipelines/mvedit_3d_pipeline.py', names, penv)
+    Pm = extract('lib/pipelines/mvedit_3d_pipeline.py', ['__call__', 'load_init_images', 'load_cond_images', 'enable_normals', 'load_depths'], penv)
+    poses, intr, init, embeds = inputs()
+    out = {}
+    for case in CASES:
+        field, log = ToyField(), []
+        self_ = types.SimpleNamespace(
+            nerf=field, unet=ToyUNet(), controlnet=MultiControlNetModel(mixin_gen.toy_nets(2)), vae=ToyVAE(), scheduler=DiffusersShapedScheduler(),
+            image_enhancer=ToyEnhancer(), segmentation=toy_segmentation, tonemapping=None, bg_color=field.bg_color, normal_bg=[0.5, 0.5, 1.0],
+            mesh_renderer=None, normal_model=None)
+        for n in ('load_init_images', 'load_cond_images', 'enable_normals', 'load_depths'):
+            setattr(self_, n, types.MethodType(Pm[n], self_))
+        for n, fn in M.items():
+            setattr(self_, n, types.MethodType(fn, self_))
+        self_.get_prompt_embeds = lambda *a, **k: embeds.clone()
+        self_.get_tgt_masks = lambda tgt_images, pad: toy_segmentation(tgt_images.squeeze(0).clip(min=0, max=1).permute(0, 3, 1, 2))[:, 0][None, ..., None]
+        self_.nerf_optim = lambda *a, **k: record_call(log, field, *a, **k)
+        del tb[:]
+        torch.manual_seed(1234)
+        res = Pm['__call__'](self_, prog_bar=lambda x: x, **call_kwargs(case, poses, intr, [a.copy() for a in init]))
+        # the reference cannot return from a run that never enters the DMTet stage (``in_mesh`` is unbound at :1482): that NameError, caught
+        # by its own try / except, is the ONLY failure allowed here -- everything recorded happened before it
+        assert res == (None, None) and len(tb) == 1 and 'in_mesh' in tb[0].strip().splitlines()[-1], tb
+        out.update(flatten(log, case + '_'))
+        print(case, 'steps', len(log), 'views', [int(r['camera_poses'].shape[0]) for r in log], 'render sizes', [r['render_size'] for r in log])
+    np.savez_compressed(OUT, **out)
+    print('wrote', OUT, sum(v.nbytes for v in out.values()) // 1024, 'KiB')
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,71 @@
+"""The loop body of ``MVEdit3DPipeline.__call__`` against THE REFERENCE'S OWN ``__call__``:
+tests/golden/make_pipeline_loop_pins.py ran mvedit_3d_pipeline.py:875-1500 unmodified (with the reference's own input loaders, denoiser
+mixin, noise scales, light sampling, camera pruning, depth normalisation and schedules) around toy components and recorded every
+``nerf_optim`` call.  Here the product's ``__call__`` runs around the same toys: at every step it must hand the same targets, cameras
+(i.e. the same re-ordering and pruning decisions), lights, weights and flags to ``nerf_optim`` -- in the optimisation-only mode, in both
+denoise modes, with dynamic blending, with reference-image pairs and from pure noise.  CPU.
+
+The product keeps the rendered conditions in bf16 where the reference run here used fp32: value comparisons carry that tolerance."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as no
+from mvedit_b200 import mvedit_3d_pipeline as P
+from mvedit_b200.schedulers import EulerAncestralScheduler
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+spec = importlib.util.spec_from_file_location('make_pipeline_loop_pins', os.path.join(HERE, 'golden', 'make_pipeline_loop_pins.py'))
+gen = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(gen)
+PINS = np.load(os.path.join(HERE, 'golden', 'pipeline_loop_pins.npz'))
+
+
+class AdamLike(torch.optim.Adam):
+    def __init__(self, params, lr=1e-3, **kw):
+        super().__init__(params, lr=lr)
+
+
+class _FieldForOracleRender:
+    """``oracle.nerf_oracle.render_views`` (the restatement of the reference's render + shading lines, :1363-1395) over the toy field."""
+
+    def __init__(self, field):
+        self.field, self.bg_color = field, field.bg_color
+
+    def render(self, density_bitfield, h, w, intrinsics, poses, cfg=None, normal_bg=(0.5, 0.5, 1.0)):
+        return self.field.render(None, None, density_bitfield, h, w, intrinsics, poses, cfg=cfg, normal_bg=normal_bg)
+
+
+@pytest.mark.parametrize('case', list(gen.CASES))
+def test_call_hands_nerf_optim_what_the_reference_loop_hands_it(case, monkeypatch):
+    field, log = gen.ToyField(), []
+    monkeypatch.setattr(P, 'FusedAdam', AdamLike)
+    monkeypatch.setattr(P, 'nerf_optim', lambda nerf, *a, **k: gen.record_call(log, field, *a, **k))
+    pipe = P.MVEdit3DPipeline(gen.ToyVAE(), None, None, gen.ToyUNet(), gen.mixin_gen.toy_nets(2), EulerAncestralScheduler(), field,
+                              image_enhancer=gen.ToyEnhancer(), segmentation=gen.toy_segmentation)
+    wrapped = _FieldForOracleRender(field)
+    pipe.render_views = lambda bitfield, poses, intr, intr_size, rs, cam_lights, ambient, tdg, render_bs=None, **kw: no.render_views(
+        wrapped, bitfield, poses, intr, intr_size, rs, cam_lights, ambient, tdg, render_bs=render_bs, out_dtype=torch.float32)
+    poses, intr, init, embeds = gen.inputs()
+    torch.manual_seed(1234)
+    mesh, state = pipe(prompt_embeds=embeds.clone(), **gen.call_kwargs(case, poses, intr, init))
+    assert mesh is None and state is not None, 'the run raised inside __call__ (traceback printed above)'
+    assert len(log) == int(PINS[case + '_steps'])
+    for i, rec in enumerate(log):
+        for opt in ('tgt_normals', 'tgt_depths'):                                       # handed over exactly when the reference does
+            assert (opt in rec) == ('%s_%d_%s_pooled' % (case, i, opt) in PINS.files), (i, opt)
+        for k, v in rec.items():
+            key = '%s_%d_%s' % (case, i, k)
+            if k in gen.MAPS:
+                assert tuple(v.shape) == tuple(PINS[key + '_shape']), (key, v.shape)
+                x = v[0].permute(0, 3, 1, 2)
+                np.testing.assert_allclose(torch.nn.functional.avg_pool2d(x, 8).numpy(), PINS[key + '_pooled'], rtol=0, atol=1.5e-2, err_msg=key)
+                np.testing.assert_allclose(x.flatten(2).std(dim=2).numpy(), PINS[key + '_std'], rtol=0, atol=1.5e-2, err_msg=key)
+            elif torch.is_tensor(v):
+                np.testing.assert_allclose(v.numpy(), PINS[key], rtol=1e-5, atol=1e-6, err_msg=key)       # cameras, intrinsics, weights, lights
+            else:
+                assert float(v) == pytest.approx(float(PINS[key]), rel=1e-6), key                       # schedules, sizes, flags
+    assert field.decoder.state_dict_bak is not None
