@@ -126,6 +126,46 @@ class ToyField(nn.Module):
         return torch.cat([rgb, alpha[..., None]], dim=-1)[None], depth[None], normal[None], nfg[None]
 
 
+class ToyMeshRenderer:
+    """Stands for MeshRenderer in the per-step render of the DMTet stage: the same procedural blob, tinted, so that the hand-over of the mesh
+    branch (:1345-1362) is visible in the next step's targets."""
+    ssaa = 1
+
+    def __init__(self, field):
+        self.field = field
+
+    def __call__(self, meshes, poses, intrinsics, h, w, shading_fun=None, normal_bg=(0.5, 0.5, 1.0), **kw):
+        rgba, depth, normal, _ = self.field.render(None, None, None, h, w, intrinsics, poses, normal_bg=normal_bg)
+        return dict(rgba=torch.cat([rgba[..., :3] * 0.8, rgba[..., 3:]], dim=-1), depth=depth * 1.1, normal=normal)
+
+
+def toy_init_tet(nerf, nerf_code=None, density_thresh=5.0, resolution=128, **kw):
+    """-> (tet_verts, tet_indices, tet_sdf): a small sphere on a Kuhn grid (the real one samples the field, lib/pipelines/utils.py:156-184)."""
+    from mvedit_b200.mesh_renderer import make_tet_grid
+    grid = make_tet_grid(8)
+    tv = (-grid['vertices'] * 2 * 0.9).contiguous()
+    return tv, grid['indices'], (0.5 - tv.norm(dim=-1)).clamp(-1, 1)
+
+
+MESH_RECORD = ('tgt_images', 'tgt_masks', 'lr', 'lr_multiplier', 'inverse_steps', 'render_bs', 'patch_bs', 'mesh_simplify_texture_steps',
+               'patch_rgb_weight', 'patch_normal_weight', 'alpha_soften', 'normal_reg_weight', 'mesh_normal_reg_weight', 'render_size',
+               'intrinsics', 'intrinsics_size', 'camera_poses', 'cam_weights', 'lights', 'patch_size', 'is_end', 'ambient_light', 'mesh_reduction')
+
+
+def record_mesh_call(log, field, tgt_images, tgt_masks, tgt_normals, optimizer, lr, lr_multiplier, inverse_steps, render_bs, patch_bs,
+                     mesh_simplify_texture_steps, patch_rgb_weight, patch_normal_weight, alpha_soften, normal_reg_weight, mesh_normal_reg_weight,
+                     nerf_code, tet_verts, deform, tet_sdf, tet_indices, dmtet, in_mesh, render_size, intrinsics, intrinsics_size, camera_poses,
+                     cam_weights, lights, patch_size, is_end, ambient_light, mesh_reduction, **kw):
+    loc = locals()
+    rec = {k: (loc[k].detach().float().clone() if torch.is_tensor(loc[k]) else loc[k]) for k in MESH_RECORD}
+    rec['stage'] = 1.0                                                       # a mesh_optim call (nerf_optim calls carry no 'stage')
+    rec['n_param_groups'], rec['geometry_lr'] = len(optimizer.param_groups), optimizer.param_groups[-1]['lr']
+    assert in_mesh.v.requires_grad and deform.requires_grad and tet_sdf.requires_grad
+    log.append(rec)
+    field.fits += 1
+    return in_mesh
+
+
 def inputs():
     from tests import synth
     g = torch.Generator().manual_seed(2)
@@ -149,6 +189,8 @@ CASES = dict(
     reference_pairs=dict(mode='2-pass', use_reference=True, blend_weight='dynamic'),
     from_noise=dict(mode='1-pass', use_reference=False, blend_weight=0.0, denoising_strength=None, num_inference_steps=3),
     targets=dict(mode='1-pass', use_reference=False, blend_weight=0.0, use_normal=True, depth_weight=0.4),
+    dmtet=dict(mode='2-pass', use_reference=False, blend_weight=0.0, progress_to_dmtet=0.5, tet_init_inverse_steps=13, tet_resolution=8,
+               mesh_reduction=1.0),
     from_noise_reference=dict(mode='2-pass', use_reference=True, blend_weight=0.0, denoising_strength=None, num_inference_steps=3))
 
 
@@ -277,13 +319,14 @@ def main():
 
     class _Never:
         pass
+    from mvedit_b200.mesh_renderer import DMTet as PDMTet, Mesh as PMesh       # (pinned against the reference's classes by test_mesh_pins.py)
     tb = []
     class _NumpyCompat:                         # the reference was written against numpy 1.x (np.cumproduct, :1103)
         cumproduct = staticmethod(np.cumprod)
 
         def __getattr__(self, k):
             return getattr(np, k)
-    penv = dict(torch=torch, F=F, np=_NumpyCompat(), PIL=PIL, math=math, deepcopy=deepcopy, get_module_device=lambda m: 'cpu', DMTet=lambda device: None,
+    penv = dict(torch=torch, F=F, np=_NumpyCompat(), PIL=PIL, math=math, deepcopy=deepcopy, get_module_device=lambda m: 'cpu', DMTet=PDMTet, Mesh=PMesh, init_tet=toy_init_tet,
                 light_sampling=cam.light_sampling, join_prompts=U['join_prompts'], get_camera_dists=U['get_camera_dists'],
                 prune_cameras=U['prune_cameras'], DPMSolverSDEScheduler=_Never, DPMSolverMultistepScheduler=_Never,
                 get_noise_scales=diff.get_noise_scales, normalize_depth=gu.normalize_depth, apply_cross_image_attn_proc=lambda u: None,
@@ -300,7 +343,7 @@ def main():
         self_ = types.SimpleNamespace(
             nerf=field, unet=ToyUNet(), controlnet=MultiControlNetModel(mixin_gen.toy_nets(2)), vae=ToyVAE(), scheduler=DiffusersShapedScheduler(),
             image_enhancer=ToyEnhancer(), segmentation=toy_segmentation, tonemapping=None, bg_color=field.bg_color, normal_bg=[0.5, 0.5, 1.0],
-            mesh_renderer=None, normal_model=None)
+            mesh_renderer=ToyMeshRenderer(field), normal_model=None)
         for n in ('load_init_images', 'load_cond_images', 'enable_normals', 'load_depths'):
             setattr(self_, n, types.MethodType(Pm[n], self_))
         for n, fn in M.items():
@@ -308,12 +351,17 @@ def main():
         self_.get_prompt_embeds = lambda *a, **k: embeds.clone()
         self_.get_tgt_masks = lambda tgt_images, pad: toy_segmentation(tgt_images.squeeze(0).clip(min=0, max=1).permute(0, 3, 1, 2))[:, 0][None, ..., None]
         self_.nerf_optim = lambda *a, **k: record_call(log, field, *a, **k)
+        self_.mesh_optim = lambda *a, **k: record_mesh_call(log, field, *a, **k)
+        self_.make_nerf_shading_fun = lambda *a, **k: None
         del tb[:]
         torch.manual_seed(1234)
         res = Pm['__call__'](self_, prog_bar=lambda x: x, **call_kwargs(case, poses, intr, [a.copy() for a in init]))
         # the reference cannot return from a run that never enters the DMTet stage (``in_mesh`` is unbound at :1482): that NameError, caught
         # by its own try / except, is the ONLY failure allowed here -- everything recorded happened before it
-        assert res == (None, None) and len(tb) == 1 and 'in_mesh' in tb[0].strip().splitlines()[-1], tb
+        if case == 'dmtet':
+            assert not tb and res[0] is not None and res[1] is not None, tb
+        else:
+            assert res == (None, None) and len(tb) == 1 and 'in_mesh' in tb[0].strip().splitlines()[-1], tb
         out.update(flatten(log, case + '_'))
         print(case, 'steps', len(log), 'views', [int(r['camera_poses'].shape[0]) for r in log], 'render sizes', [r['render_size'] for r in log])
     np.savez_compressed(OUT, **out)

@@ -3,7 +3,9 @@ tests/golden/make_pipeline_loop_pins.py ran mvedit_3d_pipeline.py:875-1500 unmod
 mixin, noise scales, light sampling, camera pruning, depth normalisation and schedules) around toy components and recorded every
 ``nerf_optim`` call.  Here the product's ``__call__`` runs around the same toys: at every step it must hand the same targets, cameras
 (i.e. the same re-ordering and pruning decisions), lights, weights and flags to ``nerf_optim`` -- in the optimisation-only mode, in both
-denoise modes, with dynamic blending, with reference-image pairs and from pure noise.  CPU.
+denoise modes, with dynamic blending, with reference-image pairs, from pure noise, with image-to-3D targets -- and, past
+``progress_to_dmtet``, the same arguments to ``mesh_optim`` (tet initialisation, two-group optimiser, ``is_end``) with the mesh branch of
+the per-step render feeding the next step.  CPU.
 
 The product keeps the rendered conditions in bf16 where the reference run here used fp32: value comparisons carry that tolerance."""
 import importlib.util
@@ -44,15 +46,18 @@ def test_call_hands_nerf_optim_what_the_reference_loop_hands_it(case, monkeypatc
     field, log = gen.ToyField(), []
     monkeypatch.setattr(P, 'FusedAdam', AdamLike)
     monkeypatch.setattr(P, 'nerf_optim', lambda nerf, *a, **k: gen.record_call(log, field, *a, **k))
+    monkeypatch.setattr(P, 'mesh_optim', lambda pipe_, *a, **k: gen.record_mesh_call(log, field, *a, **k))
+    monkeypatch.setattr(P, 'init_tet', gen.toy_init_tet)
     pipe = P.MVEdit3DPipeline(gen.ToyVAE(), None, None, gen.ToyUNet(), gen.mixin_gen.toy_nets(2), EulerAncestralScheduler(), field,
-                              image_enhancer=gen.ToyEnhancer(), segmentation=gen.toy_segmentation)
+                              mesh_renderer=gen.ToyMeshRenderer(field), image_enhancer=gen.ToyEnhancer(), segmentation=gen.toy_segmentation)
     wrapped = _FieldForOracleRender(field)
     pipe.render_views = lambda bitfield, poses, intr, intr_size, rs, cam_lights, ambient, tdg, render_bs=None, **kw: no.render_views(
         wrapped, bitfield, poses, intr, intr_size, rs, cam_lights, ambient, tdg, render_bs=render_bs, out_dtype=torch.float32)
     poses, intr, init, embeds = gen.inputs()
     torch.manual_seed(1234)
     mesh, state = pipe(prompt_embeds=embeds.clone(), **gen.call_kwargs(case, poses, intr, init))
-    assert mesh is None and state is not None, 'the run raised inside __call__ (traceback printed above)'
+    assert state is not None, 'the run raised inside __call__ (traceback printed above)'
+    assert (mesh is not None) == (case == 'dmtet')                              # the DMTet mesh comes back once that stage was entered
     assert len(log) == int(PINS[case + '_steps'])
     for i, rec in enumerate(log):
         for opt in ('tgt_normals', 'tgt_depths'):                                       # handed over exactly when the reference does
