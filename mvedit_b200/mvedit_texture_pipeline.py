@@ -140,7 +140,8 @@ class MVEditTexturePipeline(MVEdit3DPipeline):
                         init_latents = init_latents[order]
                         ref_latents = ref_latents[order] if use_reference else None
                         pe = pe[torch.cat([order, order + num_cameras])]
-                    dists = get_camera_dists(camera_poses, cam_weights[order] if weighted_cam_pruning else None)
+                    # as the reference (:349-350): the weights are NOT re-ordered with the cameras here
+                    dists = get_camera_dists(camera_poses, cam_weights if weighted_cam_pruning else None)
                 else:
                     max_num_cameras = max(int(round(max_num_views(progress))), num_keep_views)
                     if max_num_cameras < num_cameras:
@@ -204,8 +205,9 @@ class MVEditTexturePipeline(MVEdit3DPipeline):
                 elif denoising_strength is None:
                     shared = lambda: torch.randn_like(init_latents[0]).expand(init_latents.size(0), -1, -1, -1) * sch.init_noise_sigma
                     latents = shared()
-                    if use_reference:
-                        latents = torch.cat([shared(), latents], dim=2)
+                    if use_reference:        # as the reference (:511-514): ``ref_latents`` is REPLACED by the noise the reference half starts from
+                        ref_latents = shared()
+                        latents = torch.cat([ref_latents, latents], dim=2)
                 else:
                     latents = torch.cat([ref_latents, init_latents], dim=2) if use_reference else init_latents
                     latents = sch.add_noise(latents, torch.randn_like(latents[0]).expand(latents.size(0), -1, -1, -1), timesteps[0:1])
@@ -339,8 +341,9 @@ class MVEditTextureSuperResPipeline(MVEditTexturePipeline):
                 elif denoising_strength is None:
                     shared = lambda: torch.randn_like(init_latents[0]).expand(init_latents.size(0), -1, -1, -1) * sch.init_noise_sigma
                     latents = shared()
-                    if use_reference:
-                        latents = torch.cat([shared(), latents], dim=2)
+                    if use_reference:        # as the reference (:511-514): ``ref_latents`` is REPLACED by the noise the reference half starts from
+                        ref_latents = shared()
+                        latents = torch.cat([ref_latents, latents], dim=2)
                 else:
                     latents = torch.cat([ref_latents, init_latents], dim=2) if use_reference else init_latents
                     latents = sch.add_noise(latents, torch.randn_like(latents[0]).expand(latents.size(0), -1, -1, -1), timesteps[0:1])
