@@ -1,0 +1,116 @@
+"""Generates tests/golden/stage_glue_pins.npz by RUNNING two more of the reference's own functions unmodified on the CPU:
+``init_tet`` (lib/pipelines/utils.py:156-184; its tet grid is read from a temporary ``demo/tets/12_tets.npz`` written from
+``make_tet_grid(12)``, and its hard-wired ``device='cuda'`` is mapped to the CPU) and ``Adapter3DMixin.load_init_mesh``
+(lib/pipelines/adapter3d_mixin.py:21-66) around a recording toy renderer.
+
+Run:  python tests/golden/make_stage_glue_pins.py      (CPU, seconds)
+"""
+import ast
+import os
+import sys
+import tempfile
+import types
+from copy import copy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = '/root/reference'
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'stage_glue_pins.npz')
+
+
+class BlobDensity(nn.Module):
+    """decoder.point_density_decode of an off-centre ellipsoid (so that the fitted box is neither centred nor cubic)."""
+
+    def __init__(self):
+        super().__init__()
+        self.p = nn.Parameter(torch.zeros(1))
+
+    def point_density_decode(self, xyzs, code, **kw):
+        x = xyzs[0]
+        r = ((x - x.new_tensor([0.1, -0.05, 0.15])) / x.new_tensor([0.45, 0.3, 0.35])).norm(dim=-1)
+        return 30 * (1 - r), [len(x)]
+
+
+class RecordingRenderer:
+    def __init__(self):
+        self.ssaa, self.calls = 1, []
+
+    def __call__(self, meshes, poses, intrinsics, h, w, shading_fun=None, **kw):
+        self.calls.append(dict(ssaa=self.ssaa, poses=poses.clone(), intrinsics=intrinsics.clone(), h=h, w=w, fun=shading_fun))
+        n = poses.shape[1]
+        g = torch.Generator().manual_seed(len(self.calls))
+        rgba = torch.rand(1, n, h, w, 4, generator=g) * 1.2 - 0.1
+        return dict(rgba=rgba, depth=torch.rand(1, n, h, w, generator=g))
+
+
+class ToyMesh:
+    def detach(self):
+        return self
+
+    def to(self, device):
+        return self
+
+
+def glue_inputs():
+    from tests import synth
+    poses = torch.from_numpy(synth.surround_poses(5, seed=4)).float()
+    return poses, torch.tensor([[70.0, 72.0, 16.0, 15.0]] * 5) * torch.linspace(1, 1.2, 5)[:, None]
+
+
+def extract(rel, name, env):
+    tree = ast.parse(open(os.path.join(REF, rel)).read())
+    node = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == name)
+    node.decorator_list = []
+    mod = ast.Module(body=[node], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    exec(compile(mod, rel, 'exec'), env)
+    return env[name]
+
+
+def main():
+    from mvedit_b200.mesh_renderer import make_tet_grid
+    out = {}
+    # ---- init_tet
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, 'demo', 'tets'))
+        os.makedirs(os.path.join(tmp, 'lib', 'pipelines'))
+        grid = make_tet_grid(12)
+        np.savez(os.path.join(tmp, 'demo', 'tets', '12_tets.npz'), vertices=grid['vertices'].numpy(), indices=grid['indices'].numpy())
+
+        class TorchOnCpu:
+            def __getattr__(self, k):
+                return getattr(torch, k)
+
+            def tensor(self, *a, **k):
+                k.pop('device', None)
+                return torch.tensor(*a, **k)
+        fn = extract('lib/pipelines/utils.py', 'init_tet', dict(torch=TorchOnCpu(), np=np, os=os, hf_hub_download=None,
+                                                              __file__=os.path.join(tmp, 'lib', 'pipelines', 'utils.py')))
+        verts, indices, sdf = fn(types.SimpleNamespace(decoder=BlobDensity()), None, density_thresh=5.0, resolution=12)
+    out.update(tet_verts=verts.numpy(), tet_indices=indices.numpy(), tet_sdf=sdf.numpy())
+    # ---- load_init_mesh
+    poses, intr = glue_inputs()
+    rend = RecordingRenderer()
+    self_ = types.SimpleNamespace(unet=types.SimpleNamespace(device='cpu'), mesh_renderer=rend, bg_color=0.7)
+    fn = extract('lib/pipelines/adapter3d_mixin.py', 'load_init_mesh', dict(torch=torch, copy=copy, Mesh=None))
+    funs = ['f0', 'f1', 'f2']
+    mesh = ToyMesh()
+    m, images, alphas, depths = fn(self_, mesh, poses, intr, 32, 2, funs, diff_size=48)
+    assert m is mesh and rend.ssaa == 1                     # the 2x supersampling is set on a COPY of the renderer
+    out.update(lim_images=images.numpy(), lim_alphas=alphas.numpy(), lim_depths=depths.numpy(), lim_ssaa=np.array([c['ssaa'] for c in rend.calls]),
+               lim_intr=torch.cat([c['intrinsics'][0] for c in rend.calls]).numpy(), lim_sizes=np.array([[c['h'], c['w']] for c in rend.calls]),
+               lim_funs=np.array([funs.index(c['fun']) for c in rend.calls]))
+    rend2 = RecordingRenderer()
+    self_.mesh_renderer = rend2
+    fn(self_, mesh, poses, intr, 32, 4, None)
+    out.update(lim_default_sizes=np.array([[c['h'], c['w']] for c in rend2.calls]), lim_default_fun_none=np.array([c['fun'] is None for c in rend2.calls]))
+    np.savez_compressed(OUT, **out)
+    print('wrote', OUT, {k: v.shape for k, v in out.items()})
+
+
+if __name__ == '__main__':
+    main()

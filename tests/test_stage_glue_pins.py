@@ -1,0 +1,49 @@
+"""``init_tet`` and ``Adapter3DMixin.load_init_mesh`` against THE REFERENCE'S OWN functions (tests/golden/make_stage_glue_pins.py ran
+lib/pipelines/utils.py:156-184 and adapter3d_mixin.py:21-66 unmodified).  CPU."""
+import importlib.util
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+spec = importlib.util.spec_from_file_location('make_stage_glue_pins', os.path.join(HERE, 'golden', 'make_stage_glue_pins.py'))
+gen = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(gen)
+PINS = np.load(os.path.join(HERE, 'golden', 'stage_glue_pins.npz'))
+
+
+def test_init_tet_matches_the_reference_function():
+    from mvedit_b200.mesh_optim import init_tet
+    from mvedit_b200.mesh_renderer import make_tet_grid
+    verts, indices, sdf = init_tet(SimpleNamespace(decoder=gen.BlobDensity()), None, density_thresh=5.0, resolution=12, tets=make_tet_grid(12))
+    np.testing.assert_allclose(verts.numpy(), PINS['tet_verts'], rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(indices.numpy(), PINS['tet_indices'])
+    np.testing.assert_allclose(sdf.numpy(), PINS['tet_sdf'], rtol=1e-5, atol=1e-6)
+    assert (sdf == -1).any() and (sdf == 1).any() and ((sdf > -1) & (sdf < 1)).any()
+
+
+def test_load_init_mesh_matches_the_reference_method():
+    from mvedit_b200.adapter3d_mixin import Adapter3DMixin
+
+    class Pipe(Adapter3DMixin):
+        pass
+    poses, intr = gen.glue_inputs()
+    pipe, rend = Pipe(), gen.RecordingRenderer()
+    pipe.mesh_renderer, pipe.bg_color = rend, 0.7
+    mesh = gen.ToyMesh()
+    mesh.vn = 1                                               # (the product computes vertex normals when the input mesh has none)
+    funs = ['f0', 'f1', 'f2']
+    m, images, alphas, depths = pipe.load_init_mesh(mesh, poses, intr, 32, 2, funs, diff_size=48)
+    assert m is mesh and rend.ssaa == 1
+    for got, key in ((images, 'lim_images'), (alphas, 'lim_alphas'), (depths, 'lim_depths')):
+        np.testing.assert_allclose(got.numpy(), PINS[key], rtol=1e-6, atol=1e-7)
+    assert [c['ssaa'] for c in rend.calls] == PINS['lim_ssaa'].tolist() == [2, 2, 2]
+    np.testing.assert_allclose(torch.cat([c['intrinsics'][0] for c in rend.calls]).numpy(), PINS['lim_intr'], rtol=1e-6)
+    assert [[c['h'], c['w']] for c in rend.calls] == PINS['lim_sizes'].tolist()
+    assert [funs.index(c['fun']) for c in rend.calls] == PINS['lim_funs'].tolist()
+    rend2 = gen.RecordingRenderer()
+    pipe.mesh_renderer = rend2
+    pipe.load_init_mesh(mesh, poses, intr, 32, 4, None)
+    assert [[c['h'], c['w']] for c in rend2.calls] == PINS['lim_default_sizes'].tolist() and all(c['fun'] is None for c in rend2.calls)
