@@ -122,6 +122,9 @@ class MVEdit3DStep(Adapter3DMixin):
         mark('decode')
         tgt_images, tgt_masks = view_shard.gather_views(tgt_images, tgt_masks, camera_poses.shape[0])     # ONE collective
         tgt_images, tgt_masks = tgt_images[None], tgt_masks[None]
+        if render_size != tgt_images.shape[2]:              # the fit runs at the render size (:1284-1288)
+            rs_ = lambda x: torch.nn.functional.interpolate(x.squeeze(0).permute(0, 3, 1, 2), size=render_size, mode='bilinear').permute(0, 2, 3, 1)[None]
+            tgt_images, tgt_masks = rs_(tgt_images), rs_(tgt_masks)
         mark('gather')
         # ---- reconstruct (:1296-1305)
         nerf_optim(self.nerf, tgt_images, tgt_masks, None, optimizer, lr, n_inverse_steps, n_inverse_rays, patch_rgb_weight,

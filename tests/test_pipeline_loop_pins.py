@@ -74,3 +74,51 @@ def test_call_hands_nerf_optim_what_the_reference_loop_hands_it(case, monkeypatc
             else:
                 assert float(v) == pytest.approx(float(PINS[key]), rel=1e-6), key                       # schedules, sizes, flags
     assert field.decoder.state_dict_bak is not None
+
+
+def test_step_is_one_iteration_of_the_pinned_loop(monkeypatch):
+    """``MVEdit3DStep.step`` -- the function bench.py times -- against the 2-pass iterations of ``__call__`` (which the test above holds to
+    the reference's own loop): from the latents ``__call__`` had before a solver step, with the ancestral noise it drew, ``step`` must hand
+    ``nerf_optim`` the same targets and return the same latents and conditions."""
+    field, log, solver = gen.ToyField(), [], []
+    field.patch_size = 64                                                        # (step() reads the patch size off the field)
+    monkeypatch.setattr(P, 'FusedAdam', AdamLike)
+    monkeypatch.setattr(P, 'nerf_optim', lambda nerf, *a, **k: gen.record_call(log, field, *a, **k))
+    sch = EulerAncestralScheduler()
+    pipe = P.MVEdit3DPipeline(gen.ToyVAE(), None, None, gen.ToyUNet(), gen.mixin_gen.toy_nets(2), sch, field, segmentation=gen.toy_segmentation)
+    wrapped = _FieldForOracleRender(field)
+    pipe.render_views = lambda bitfield, poses, intr, intr_size, rs, cam_lights, ambient, tdg, render_bs=None, **kw: no.render_views(
+        wrapped, bitfield, poses, intr, intr_size, rs, cam_lights, ambient, tdg, render_bs=render_bs, out_dtype=torch.float32)
+    real_step = sch.step
+
+    def spy(model_output, t, sample, noise):
+        out = real_step(model_output, t, sample, noise)
+        solver.append(dict(t=t, latents_in=sample.clone(), noise=noise.clone(), latents_out=out.clone(), fits=field.fits))
+        return out
+    sch.step = spy
+    poses, intr, init, embeds = gen.inputs()
+    kw = gen.call_kwargs('two_pass', poses, intr, init)
+    kw.update(keep_views=None, max_num_views=lambda p, q: gen.N)                 # no re-ordering, no pruning: step() works on a fixed view set
+    torch.manual_seed(99)
+    mesh, state = pipe(prompt_embeds=embeds.clone(), **kw)
+    assert state is not None and len(solver) == 2 and len(log) == 4              # the last iteration fits and stops: no solver step (:1409)
+    sch.step = real_step
+    import mvedit_b200.pipeline as S
+    for k, sv in enumerate(solver):
+        rec, step_log = log[k + 1], []                                           # log[0] is the initial fit (t is None)
+        monkeypatch.setattr(S, 'nerf_optim', lambda nerf, *a, **kk: gen.record_call(step_log, field, *a, **kk))
+        field.fits = sv['fits'] - 1                                              # the field as it was before this iteration's fit
+        i = int((sch.timesteps == float(sv['t'])).nonzero()[0])
+        latents, ctrl_images, ctrl_depths = pipe.step(
+            i, sv['latents_in'], embeds.clone(), None, None, None, None, rec['camera_poses'], rec['intrinsics'], rec['intrinsics_size'],
+            rec['cam_weights'], rec['cam_lights'], sv['noise'], guidance_scale=kw['guidance_scale'], render_size=rec['render_size'],
+            n_inverse_steps=rec['inverse_steps'], n_inverse_rays=rec['n_inverse_rays'], lr=rec['lr'], alpha_soften=rec['alpha_soften'],
+            normal_reg_weight=rec['normal_reg_weight'], entropy_weight=rec['entropy_weight'], patch_rgb_weight=rec['patch_rgb_weight'],
+            bg_width=rec['bg_width'], ambient_light=rec['ambient_light'], dt_gamma_scale=rec['dt_gamma_scale'], render_bs=kw['render_bs'])
+        assert len(step_log) == 1
+        for name in ('tgt_images', 'tgt_masks', 'camera_poses', 'cam_lights'):
+            torch.testing.assert_close(step_log[0][name], rec[name], rtol=1e-5, atol=1e-5)
+        for name in ('lr', 'inverse_steps', 'n_inverse_rays', 'render_size', 'is_init', 'init_shaded'):
+            assert step_log[0][name] == rec[name], name
+        torch.testing.assert_close(latents, sv['latents_out'], rtol=1e-4, atol=1e-4)
+        assert ctrl_images.shape == (gen.N, 3, 512, 512) and ctrl_depths.shape == (gen.N, 3, 512, 512)
