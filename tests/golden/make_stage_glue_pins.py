@@ -61,6 +61,16 @@ def glue_inputs():
     return poses, torch.tensor([[70.0, 72.0, 16.0, 15.0]] * 5) * torch.linspace(1, 1.2, 5)[:, None]
 
 
+def decode_inputs():
+    from oracle import field_oracle as fo
+    levels, n = fo.level_table(12, 16, 320)
+    g = torch.Generator().manual_seed(5)
+    xyz = torch.rand(4096, 3, generator=g) * 2 - 1
+    xyz[:64] *= 0.2                                          # inside the density blob's clamp radius
+    params = fo.init_params(levels, n, seed=6, table_scale=0.5)
+    return xyz, (params[0], params[1], params[2] + 0.1, params[3], params[4] - 0.2), levels
+
+
 def extract(rel, name, env):
     tree = ast.parse(open(os.path.join(REF, rel)).read())
     node = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == name)
@@ -108,6 +118,34 @@ def main():
     self_.mesh_renderer = rend2
     fn(self_, mesh, poses, intr, 32, 4, None)
     out.update(lim_default_sizes=np.array([[c['h'], c['w']] for c in rend2.calls]), lim_default_fun_none=np.array([c['fun'] is None for c in rend2.calls]))
+    # ---- iNGPDecoder.point_decode / density_blob / MLP (ingp_decoder.py:20-40,101-120) and TruncExp (lib/ops/activation.py) around the
+    # plain-torch hash grid of oracle/field_oracle.py in place of tinycudann's encoder (absent; "parity unpinned" for the grid itself)
+    import importlib.util
+    import torch.nn.functional as F
+    from oracle import field_oracle as fo
+    sp = importlib.util.spec_from_file_location('ref_activation', os.path.join(REF, 'lib/ops/activation.py'))
+    act = importlib.util.module_from_spec(sp)
+    sp.loader.exec_module(act)
+    tree = ast.parse(open(os.path.join(REF, 'lib/models/decoders/ingp_decoder.py')).read())
+    env = dict(torch=torch, nn=nn, F=F)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == 'MLP' or isinstance(node, ast.FunctionDef) and node.name in ('density_blob', 'point_decode', 'point_density_decode'):
+            mod = ast.Module(body=[node], type_ignores=[])
+            ast.fix_missing_locations(mod)
+            exec(compile(mod, 'ingp_decoder.py', 'exec'), env)
+    xyz, (table, w1, b1, w2, b2), levels = decode_inputs()
+    mlp = env['MLP'](w1.shape[1], 4, 64, 2)
+    with torch.no_grad():
+        mlp.net[0].weight.copy_(w1); mlp.net[0].bias.copy_(b1); mlp.net[1].weight.copy_(w2); mlp.net[1].bias.copy_(b2)
+    dec = types.SimpleNamespace(encoder=lambda x01: fo.hash_encode(x01, table, levels), mlp=mlp, bound=1, sigma_activation=act.TruncExp(),
+                                blob_density=1.0, blob_radius=0.2, sigmoid_saturation=0.001)
+    for n in ('density_blob', 'point_decode', 'point_density_decode'):
+        setattr(dec, n, types.MethodType(env[n], dec))
+    with torch.no_grad():
+        sig, rgb, num = dec.point_decode([xyz], None, [None])
+        sig2, num2 = dec.point_density_decode([xyz], [None])
+    assert num == [len(xyz)] and torch.equal(sig, sig2)
+    out.update(dec_sigma=sig.numpy(), dec_rgb=rgb.numpy())
     np.savez_compressed(OUT, **out)
     print('wrote', OUT, {k: v.shape for k, v in out.items()})
 

@@ -47,3 +47,14 @@ def test_load_init_mesh_matches_the_reference_method():
     pipe.mesh_renderer = rend2
     pipe.load_init_mesh(mesh, poses, intr, 32, 4, None)
     assert [[c['h'], c['w']] for c in rend2.calls] == PINS['lim_default_sizes'].tolist() and all(c['fun'] is None for c in rend2.calls)
+
+
+def test_field_composition_matches_the_reference_decoder():
+    """``iNGPDecoder.point_decode`` (input normalisation, MLP, density blob, TruncExp, saturated sigmoid) run unmodified around the oracle's
+    hash grid == ``oracle/field_oracle.point_decode`` (what the GPU tests hold the field kernels to)."""
+    from oracle import field_oracle as fo
+    xyz, (table, w1, b1, w2, b2), levels = gen.decode_inputs()
+    sig, rgb = fo.point_decode(xyz, table, w1, b1, w2, b2, levels)
+    np.testing.assert_allclose(sig.numpy(), PINS['dec_sigma'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rgb.numpy(), PINS['dec_rgb'], rtol=1e-5, atol=1e-6)
+    assert PINS['dec_sigma'].std() > 0.1 and PINS['dec_rgb'].std() > 0.02
