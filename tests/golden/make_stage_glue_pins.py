@@ -71,6 +71,18 @@ def decode_inputs():
     return xyz, (params[0], params[1], params[2] + 0.1, params[3], params[4] - 0.2), levels
 
 
+def triplane_inputs():
+    from oracle import field_oracle as fo
+    levels, n = fo.level_table(12, 16, 320)
+    g = torch.Generator().manual_seed(7)
+    r = lambda *sh: torch.randn(*sh, generator=g)
+    C, H = 6, 32
+    sd = {'encoder.params': (torch.rand(n * 2, generator=g) - 0.5), 'base_net.0.weight': r(H, 3 * C) * 0.3, 'base_net.0.bias': r(H) * 0.1,
+          'ingp_base_net.0.weight': r(H, 24) * 0.3, 'ingp_base_net.0.bias': r(H) * 0.1, 'density_net.0.weight': r(1, H) * 0.3,
+          'density_net.0.bias': r(1) * 0.1, 'color_net.0.weight': r(3, H) * 0.3, 'color_net.0.bias': r(3) * 0.1}
+    return torch.rand(2048, 3, generator=g) * 2.2 - 1.1, r(1, 3, C, 20, 20), sd, levels      # some points beyond the planes: border padding
+
+
 def extract(rel, name, env):
     tree = ast.parse(open(os.path.join(REF, rel)).read())
     node = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == name)
@@ -146,6 +158,33 @@ def main():
         sig2, num2 = dec.point_density_decode([xyz], [None])
     assert num == [len(xyz)] and torch.equal(sig, sig2)
     out.update(dec_sigma=sig.numpy(), dec_rgb=rgb.numpy())
+    # ---- TriPlaneiNGPDecoder.point_decode (triplane_ingp_decoder.py:142-212) + TriPlaneDecoder.xyz_transform (triplane_decoder.py:106-130):
+    # the reference's code with Sequential(Linear[, activation]) nets as its constructor builds them (:59-92) around the oracle's hash grid
+    t1 = ast.parse(open(os.path.join(REF, 'lib/models/decoders/triplane_ingp_decoder.py')).read())
+    t2 = ast.parse(open(os.path.join(REF, 'lib/models/decoders/triplane_decoder.py')).read())
+    tenv = dict(torch=torch, nn=nn, F=F)
+    pd = next(n for n in ast.walk(t1) if isinstance(n, ast.FunctionDef) and n.name == 'point_decode')
+    xt = next(n for n in ast.walk(t2) if isinstance(n, ast.FunctionDef) and n.name == 'xyz_transform')
+    for node in (pd, xt):
+        mod = ast.Module(body=[node], type_ignores=[])
+        ast.fix_missing_locations(mod)
+        exec(compile(mod, 'triplane', 'exec'), tenv)
+    xyz_t, code, sd, tl = triplane_inputs()
+    lin = lambda k: nn.Linear(sd[k + '.0.weight'].shape[1], sd[k + '.0.weight'].shape[0])
+    nets = {k: lin(k) for k in ('base_net', 'ingp_base_net', 'density_net', 'color_net')}
+    with torch.no_grad():
+        for k, m in nets.items():
+            m.weight.copy_(sd[k + '.0.weight']); m.bias.copy_(sd[k + '.0.bias'])
+    for cfg_name, plane_cfg, flip in (('a', ('xy', 'xz', 'yz'), False), ('b', ['yx', 'yz', 'xz'], True)):
+        tp = types.SimpleNamespace(encoder=lambda x01: fo.hash_encode(x01, sd['encoder.params'].view(-1, 2), tl), bound=1, code_dropout=None,
+                                   scene_base=None, interp_mode='bilinear', plane_cfg=plane_cfg, flip_z=flip, use_dir_enc=False,
+                                   base_net=nn.Sequential(nets['base_net']), ingp_base_net=nn.Sequential(nets['ingp_base_net']),
+                                   base_activation=nn.SiLU(), density_net=nn.Sequential(nets['density_net'], act.TruncExp()),
+                                   color_net=nn.Sequential(nets['color_net'], nn.Sigmoid()), sigmoid_saturation=0.001)
+        tp.xyz_transform = types.MethodType(tenv['xyz_transform'], tp)
+        with torch.no_grad():
+            s_, c_, _ = tenv['point_decode'](tp, [xyz_t], None, code)
+        out['tri_sigma_' + cfg_name], out['tri_rgb_' + cfg_name] = s_.numpy(), c_.numpy()
     np.savez_compressed(OUT, **out)
     print('wrote', OUT, {k: v.shape for k, v in out.items()})
 

@@ -58,3 +58,15 @@ def test_field_composition_matches_the_reference_decoder():
     np.testing.assert_allclose(sig.numpy(), PINS['dec_sigma'], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(rgb.numpy(), PINS['dec_rgb'], rtol=1e-5, atol=1e-6)
     assert PINS['dec_sigma'].std() > 0.1 and PINS['dec_rgb'].std() > 0.02
+
+
+def test_triplane_composition_matches_the_reference_decoder():
+    """``TriPlaneiNGPDecoder.point_decode`` + ``xyz_transform`` run unmodified (two plane layouts, with and without the z flip) ==
+    ``oracle/field_oracle.triplane_point_decode`` (what tests/test_gpu_triplane.py holds the kernels to)."""
+    from oracle import field_oracle as fo
+    xyz, code, sd, levels = gen.triplane_inputs()
+    for name, plane_cfg, flip in (('a', ('xy', 'xz', 'yz'), False), ('b', ['yx', 'yz', 'xz'], True)):
+        sig, rgb = fo.triplane_point_decode(xyz, code, sd, levels, plane_cfg=plane_cfg, flip_z=flip)
+        np.testing.assert_allclose(sig.numpy(), PINS['tri_sigma_' + name], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(rgb.numpy(), PINS['tri_rgb_' + name], rtol=1e-5, atol=1e-6)
+    assert np.abs(PINS['tri_rgb_a'] - PINS['tri_rgb_b']).max() > 0.05
