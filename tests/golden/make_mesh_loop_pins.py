@@ -285,6 +285,21 @@ def main():
     assert [k for k, _ in d2] == ['randperm'] + ['rand_like', 'randperm'] * 3
     out.update(to_tgt=t_tgt.numpy(), to_w=t_w.numpy(), to_camera_perm=d2[0][1].numpy(), to_jitter=np.stack([d2[1 + 2 * s][1].numpy() for s in range(3)]),
                to_patch_perm=np.stack([d2[2 + 2 * s][1].numpy() for s in range(3)]), to_w_out=field3.w.detach().numpy(), to_b_out=field3.b.detach().numpy())
+    # ---- the super-resolution pipeline's own texture_optim (mvedit_texture_superres_pipeline.py:89-168): patch term on the first num_cameras
+    # views of every rendered batch only ("ignore regularization views")
+    rec3 = TorchRecorder()
+    T2 = extract('lib/pipelines/mvedit_texture_superres_pipeline.py', ['texture_optim'], dict(torch=rec3, F=F, np=np, get_module_device=lambda mod: 'cpu'))
+    field4 = ToyField()
+    opt4 = torch.optim.Adam(field4.parameters(), lr=0.01)
+    self4 = types.SimpleNamespace(nerf=types.SimpleNamespace(decoder=field4, pixel_loss=L1LossMod(loss_weight=1.2), patch_loss=_FakePatchLoss()),
+                                  mesh_renderer=renderer, bg_color=0.5)
+    self4.make_nerf_albedo_shading_fun = lambda *a: A['make_nerf_albedo_shading_fun'](self4, *a)
+    torch.manual_seed(14)
+    T2['texture_optim'](self4, t_tgt, 1, opt4, 0.02, 3, 2, 2, 0.6, [None], fixed, size, intr, size, poses, t_w, ps)
+    d3 = rec3.draws
+    assert [k for k, _ in d3] == ['randperm'] + ['rand_like', 'randperm'] * 3
+    out.update(ts_camera_perm=d3[0][1].numpy(), ts_jitter=np.stack([d3[1 + 2 * s][1].numpy() for s in range(3)]),
+               ts_patch_perm=np.stack([d3[2 + 2 * s][1].numpy() for s in range(3)]), ts_w_out=field4.w.detach().numpy(), ts_b_out=field4.b.detach().numpy())
     np.savez_compressed(OUT, **out)
     print('wrote', OUT, sum(v.nbytes for v in out.values()) // 1024, 'KiB')
 

@@ -172,3 +172,19 @@ def test_texture_optim_matches_the_reference_method():
     mopt.texture_optim(pipe, T('to_tgt'), opt, 0.02, 3, 2, 2, 0.6, None, mesh, 32, T('mo_intr'), 32, T('mo_poses'), T('to_w'), 16, noise=noise)
     assert (field.w.detach() - T('to_w_out')).abs().max() < 2e-5 and (field.b.detach() - T('to_b_out')).abs().max() < 2e-5
     assert (field.w.detach() - ToyField().w.detach()).abs().max() > 1e-2
+
+
+def test_superres_texture_optim_matches_the_reference_method():
+    """The super-resolution pipeline's own ``texture_optim`` (mvedit_texture_superres_pipeline.py:89-168, ``num_cameras`` = 1 of the two views
+    per batch): the product's ``texture_optim(patch_views=)``."""
+    mesh = Mesh(v=T('fw_v'), f=T('fw_f'))
+    mesh.auto_normal()
+    field = ToyField()
+    opt = torch.optim.Adam(field.parameters(), lr=0.01)
+    pipe = SimpleNamespace(nerf=SimpleNamespace(decoder=field, pixel_loss=L1LossMod(loss_weight=1.2), patch_loss=_FakePatchLoss()),
+                           mesh_renderer=MeshRenderer(near=0.01, far=100), bg_color=0.5)
+    noise = dict(camera_perm=T('ts_camera_perm'), jitter=T('ts_jitter'), patch_perm=T('ts_patch_perm'))
+    mopt.texture_optim(pipe, T('to_tgt'), opt, 0.02, 3, 2, 2, 0.6, None, mesh, 32, T('mo_intr'), 32, T('mo_poses'), T('to_w'), 16, noise=noise,
+                       patch_views=1)
+    assert (field.w.detach() - T('ts_w_out')).abs().max() < 2e-5 and (field.b.detach() - T('ts_b_out')).abs().max() < 2e-5
+    assert (T('ts_w_out') - T('to_w_out')).abs().max() > 1e-4                  # not the plain variant's trajectory
