@@ -1,0 +1,99 @@
+"""The product's mirrors of the reference's call surface keep its argument names, order and defaults (tests/golden/signatures.json, read
+from the reference's source by AST): a caller of the reference can pass the same positional / keyword arguments.  A mirror may (1) take a
+leading object where the reference has a method (``nerf_optim(nerf, ...)``), (2) append arguments of its own after the reference's, and
+(3) name a default differently only where listed in ``ALLOWED`` with the reason."""
+import ast
+import inspect
+import json
+import os
+
+import pytest
+
+PINS = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'signatures.json')))
+
+
+def _targets():
+    from mvedit_b200 import (adapter3d_mixin, ingp_decoder, mesh_optim, mesh_renderer, mvedit_3d_pipeline as p3, mvedit_texture_pipeline as tp, nerf,
+                             raymarching)
+    R3, RT, RS, RM, RU = ('lib/pipelines/mvedit_3d_pipeline.py::', 'lib/pipelines/mvedit_texture_pipeline.py::',
+                          'lib/pipelines/mvedit_texture_superres_pipeline.py::', 'lib/pipelines/adapter3d_mixin.py::', 'lib/pipelines/utils.py::')
+    RB, RN, RV, RI, RR = ('lib/models/decoders/mesh_renderer/base_mesh_renderer.py::', 'lib/models/autoencoders/base_nerf.py::',
+                          'lib/models/decoders/base_volume_renderer.py::', 'lib/models/decoders/ingp_decoder.py::', 'lib/ops/raymarching/raymarching.py::')
+    t = {
+        R3 + 'MVEdit3DPipeline.__init__': (p3.MVEdit3DPipeline.__init__, 1), R3 + 'MVEdit3DPipeline.__call__': (p3.MVEdit3DPipeline.__call__, 1),
+        R3 + 'MVEdit3DPipeline.nerf_optim': (nerf.nerf_optim, 1), R3 + 'MVEdit3DPipeline.mesh_optim': (mesh_optim.mesh_optim, 1),
+        R3 + 'MVEdit3DPipeline.load_init_nerf': (p3.MVEdit3DPipeline.load_init_nerf, 1),
+        R3 + 'MVEdit3DPipeline.load_init_images': (p3.MVEdit3DPipeline.load_init_images, 1),
+        R3 + 'MVEdit3DPipeline.load_depths': (p3.MVEdit3DPipeline.load_depths, 1), R3 + 'MVEdit3DPipeline.enable_normals': (p3.MVEdit3DPipeline.enable_normals, 1),
+        R3 + 'MVEdit3DPipeline.load_cond_images': (p3.MVEdit3DPipeline.load_cond_images, 1),
+        RT + 'MVEditTexturePipeline.__call__': (tp.MVEditTexturePipeline.__call__, 1), RT + 'MVEditTexturePipeline.texture_optim': (mesh_optim.texture_optim, 1),
+        RT + 'camera_dense_weighting': (tp.camera_dense_weighting, 0), RT + 'default_patch_rgb_weight': (tp.default_patch_rgb_weight, 0),
+        RT + 'default_max_num_views': (tp.default_max_num_views, 0),
+        RS + 'MVEditTextureSuperResPipeline.__call__': (tp.MVEditTextureSuperResPipeline.__call__, 1),
+        RM + 'Adapter3DMixin.get_noise_pred': (adapter3d_mixin.Adapter3DMixin.get_noise_pred, 1),
+        RM + 'Adapter3DMixin.get_noise_pred_p1': (adapter3d_mixin.Adapter3DMixin.get_noise_pred_p1, 1),
+        RM + 'Adapter3DMixin.get_noise_pred_p2': (adapter3d_mixin.Adapter3DMixin.get_noise_pred_p2, 1),
+        RM + 'Adapter3DMixin.load_init_mesh': (adapter3d_mixin.Adapter3DMixin.load_init_mesh, 1),
+        RU + 'init_tet': (mesh_optim.init_tet, 0), RU + 'get_camera_dists': (p3.get_camera_dists, 0), RU + 'prune_cameras': (p3.prune_cameras, 0),
+        RU + 'highpass': (nerf.highpass, 0), RU + 'join_prompts': (p3.join_prompts, 0),
+        RB + 'MeshRenderer.__init__': (mesh_renderer.MeshRenderer.__init__, 1), RB + 'MeshRenderer.forward': (mesh_renderer.MeshRenderer.forward, 1),
+        RB + 'MeshRenderer.bake_xyz_shading_fun': (mesh_renderer.MeshRenderer.bake_xyz_shading_fun, 1),
+        RB + 'MeshRenderer.bake_multiview': (mesh_renderer.MeshRenderer.bake_multiview, 1),
+        RB + 'MeshRenderer.get_cam_weights_uv': (mesh_renderer.MeshRenderer.get_cam_weights_uv, 1), RB + 'DMTet.__call__': (mesh_renderer.DMTet.__call__, 1),
+        RN + 'BaseNeRF.render': (nerf.BaseNeRF.render, 1), RN + 'BaseNeRF.get_raybatch_inds': (nerf.BaseNeRF.get_raybatch_inds, 1),
+        RI + 'iNGPDecoder.point_decode': (ingp_decoder.iNGPDecoder.point_decode, 1),
+        RR + 'near_far_from_aabb': (raymarching.near_far_from_aabb, 0), RR + 'march_rays_train': (raymarching.march_rays_train, 0),
+        RR + 'composite_rays_train': (raymarching.composite_rays_train, 0), RR + 'march_rays': (raymarching.march_rays, 0),
+        RR + 'composite_rays': (raymarching.composite_rays, 0), RR + 'morton3D': (raymarching.morton3D, 0),
+        RR + 'morton3D_invert': (raymarching.morton3D_invert, 0), RR + 'packbits': (raymarching.packbits, 0)}
+    for n in ('default_lr_multiplier', 'default_max_num_views', 'default_render_size_p', 'default_lr_schedule', 'default_patch_rgb_weight',
+              'default_patch_normal_weight', 'default_entropy_weight', 'default_normal_reg_weight'):
+        t[R3 + n] = (getattr(p3, n), 0)
+    return t
+
+
+# (reference key, argument) -> why the product's default may differ
+ALLOWED = {
+    ('lib/pipelines/mvedit_3d_pipeline.py::MVEdit3DPipeline.__call__', 'prog_bar'): 'tqdm is the reference default; None = plain iteration',
+    ('lib/pipelines/mvedit_texture_pipeline.py::MVEditTexturePipeline.__call__', 'prog_bar'): 'same',
+    ('lib/pipelines/mvedit_texture_superres_pipeline.py::MVEditTextureSuperResPipeline.__call__', 'prog_bar'): 'same',
+    ('lib/pipelines/utils.py::get_camera_dists', 'device'): 'the device follows the poses',
+    ('lib/pipelines/utils.py::prune_cameras', 'device'): 'the device follows the distances',
+}
+
+
+def _norm(v):
+    if v is None:
+        return None
+    try:
+        return repr(eval(v, {'__builtins__': {}}, {'dict': dict}))        # literals and constant expressions ("2 ** 14", "dict()")
+    except Exception:
+        return v.replace(' ', '')
+
+
+@pytest.mark.parametrize('key', sorted(_targets()))
+def test_mirror_keeps_the_reference_signature(key):
+    fn, skip = _targets()[key]
+    if inspect.ismethod(fn) and inspect.isclass(fn.__self__) and fn.__name__ == 'apply':      # autograd Function: its forward minus ctx
+        fn, skip = fn.__self__.forward, 1
+    ref = [a for a in PINS[key] if not a[0].startswith('*')]
+    params = [p for p in inspect.signature(fn).parameters.values() if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD, p.KEYWORD_ONLY)][skip:]
+    names = [p.name for p in params]
+    assert names[:len(ref)] == [a[0] for a in ref], (key, names, [a[0] for a in ref])
+    for p, (name, default) in zip(params, ref):
+        if (key, name) in ALLOWED:
+            continue
+        if default is None:                          # required in the reference: the mirror may be more permissive
+            continue
+        got = p.default
+        if callable(got) and hasattr(got, '__name__') and not isinstance(got, type):
+            assert got.__name__ == default or getattr(got, '__qualname__', '') == default or _name_of(fn, got) == default, (key, name, default)
+        elif isinstance(got, (tuple, list)) and default.startswith(('[', '(')):
+            assert list(got) == list(ast.literal_eval(default)), (key, name, got, default)
+        else:
+            assert _norm(repr(got)) == _norm(default), (key, name, got, default)
+
+
+def _name_of(fn, value):
+    mod = inspect.getmodule(fn)
+    return next((k for k, v in vars(mod).items() if v is value and k.startswith('default_')), None)
