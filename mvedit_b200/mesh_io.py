@@ -268,7 +268,7 @@ def load_glb(path, device=None):
     return mesh
 
 
-def load(path, resize=False, auto_uv=True, flip_yz=False, force_auto_normal=False, device=None):
+def load(path, resize=False, auto_uv=True, flip_yz=False, force_auto_normal=False, auto_normal_seamless=False, device=None):
     """``Mesh.load`` (mesh_utils.py:80-113): read, fix normals / UVs, optional y-up -> z-up flip (the inverse of ``write``'s)."""
     if path.endswith('.obj'):
         mesh = load_obj(path, device)
@@ -283,7 +283,7 @@ def load(path, resize=False, auto_uv=True, flip_yz=False, force_auto_normal=Fals
         mesh.ori_center, mesh.ori_scale = (vmax + vmin) / 2, 1.2 / float((vmax - vmin).max())
         mesh.v = (mesh.v - mesh.ori_center) * mesh.ori_scale
     if mesh.vn is None or force_auto_normal:
-        mesh.auto_normal()
+        mesh.auto_normal(seamless=auto_normal_seamless)
     if mesh.vt is None and auto_uv:
         mesh.auto_uv()
     if flip_yz:

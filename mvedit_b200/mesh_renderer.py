@@ -59,10 +59,11 @@ class Mesh:
                     textureless=self.textureless)
 
     @classmethod
-    def load(cls, path, resize=False, auto_uv=True, flip_yz=False, force_auto_normal=False, device=None):
-        """``.obj`` (face uvs / normals, ``map_Kd`` texture) and the binary ``.ply`` of ``write`` (``mesh_utils.py:80-260``)."""
+    def load(cls, path, resize=False, auto_uv=True, flip_yz=False, force_auto_normal=False, auto_normal_seamless=False, device=None):
+        """``.obj`` (face uvs / normals, ``map_Kd`` texture), ``.glb`` and the binary ``.ply`` of ``write`` (``mesh_utils.py:80-345``)."""
         from . import mesh_io
-        return mesh_io.load(path, resize=resize, auto_uv=auto_uv, flip_yz=flip_yz, force_auto_normal=force_auto_normal, device=device)
+        return mesh_io.load(path, resize=resize, auto_uv=auto_uv, flip_yz=flip_yz, force_auto_normal=force_auto_normal,
+                            auto_normal_seamless=auto_normal_seamless, device=device)
 
     def write(self, path, flip_yz=False):
         """``.obj`` (+ .mtl + albedo PNG) / ``.ply`` / ``.glb`` (``mesh_utils.py:461-692``; containers written by ``mesh_io``)."""

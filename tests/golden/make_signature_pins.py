@@ -23,10 +23,15 @@ TARGETS = {
                                          'Adapter3DMixin.load_init_mesh'],
     'lib/pipelines/utils.py': ['init_tet', 'get_camera_dists', 'prune_cameras', 'highpass', 'join_prompts'],
     'lib/models/decoders/mesh_renderer/base_mesh_renderer.py': ['MeshRenderer.__init__', 'MeshRenderer.forward', 'MeshRenderer.bake_xyz_shading_fun',
-                                                                'MeshRenderer.bake_multiview', 'MeshRenderer.get_cam_weights_uv', 'DMTet.__call__'],
+                                                                'MeshRenderer.bake_multiview', 'MeshRenderer.get_cam_weights_uv', 'DMTet.__call__',
+                                                                'normal_consistency', 'laplacian_smooth_loss', 'compute_edge_to_face_mapping'],
     'lib/models/autoencoders/base_nerf.py': ['BaseNeRF.render', 'BaseNeRF.ray_sample', 'BaseNeRF.get_raybatch_inds'],
     'lib/models/decoders/base_volume_renderer.py': ['VolumeRenderer.forward', 'VolumeRenderer.update_extra_state'],
     'lib/models/decoders/ingp_decoder.py': ['iNGPDecoder.__init__', 'iNGPDecoder.point_decode'],
+    'lib/models/decoders/mesh_renderer/mesh_utils.py': ['Mesh.__init__', 'Mesh.load', 'Mesh.auto_normal', 'Mesh.to', 'Mesh.write'],
+    'lib/ops/edge_dilation.py': ['edge_dilation'],
+    'lib/models/decoders/tonemapping.py': ['Tonemapping.__init__', 'Tonemapping.lut', 'Tonemapping.inverse_lut', 'Tonemapping.smooth_forward'],
+    'lib/core/utils/camera_utils.py': ['light_sampling'],
     'lib/ops/raymarching/raymarching.py': ['near_far_from_aabb', 'march_rays_train', 'composite_rays_train', 'march_rays', 'composite_rays',
                                            'morton3D', 'morton3D_invert', 'packbits'],
 }

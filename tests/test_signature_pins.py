@@ -46,6 +46,18 @@ def _targets():
         RR + 'composite_rays_train': (raymarching.composite_rays_train, 0), RR + 'march_rays': (raymarching.march_rays, 0),
         RR + 'composite_rays': (raymarching.composite_rays, 0), RR + 'morton3D': (raymarching.morton3D, 0),
         RR + 'morton3D_invert': (raymarching.morton3D_invert, 0), RR + 'packbits': (raymarching.packbits, 0)}
+    from mvedit_b200 import tonemapping
+    RMU, RT2 = 'lib/models/decoders/mesh_renderer/mesh_utils.py::', 'lib/models/decoders/tonemapping.py::'
+    t.update({
+        RMU + 'Mesh.__init__': (mesh_renderer.Mesh.__init__, 1), RMU + 'Mesh.load': (mesh_renderer.Mesh.load.__func__, 1),
+        RMU + 'Mesh.auto_normal': (mesh_renderer.Mesh.auto_normal, 1), RMU + 'Mesh.to': (mesh_renderer.Mesh.to, 1),
+        RMU + 'Mesh.write': (mesh_renderer.Mesh.write, 1),
+        RB + 'normal_consistency': (mesh_renderer.normal_consistency, 0), RB + 'laplacian_smooth_loss': (mesh_renderer.laplacian_smooth_loss, 0),
+        RB + 'compute_edge_to_face_mapping': (mesh_renderer.compute_edge_to_face_mapping, 0),
+        'lib/ops/edge_dilation.py::edge_dilation': (mesh_renderer.edge_dilation, 0),
+        RT2 + 'Tonemapping.__init__': (tonemapping.Tonemapping.__init__, 1), RT2 + 'Tonemapping.lut': (tonemapping.Tonemapping.lut, 1),
+        RT2 + 'Tonemapping.inverse_lut': (tonemapping.Tonemapping.inverse_lut, 1), RT2 + 'Tonemapping.smooth_forward': (tonemapping.Tonemapping.smooth_forward, 1),
+        'lib/core/utils/camera_utils.py::light_sampling': (p3.light_sampling, 0)})
     for n in ('default_lr_multiplier', 'default_max_num_views', 'default_render_size_p', 'default_lr_schedule', 'default_patch_rgb_weight',
               'default_patch_normal_weight', 'default_entropy_weight', 'default_normal_reg_weight'):
         t[R3 + n] = (getattr(p3, n), 0)
