@@ -268,9 +268,12 @@ def load_glb(path, device=None):
     return mesh
 
 
-def load(path, resize=False, auto_uv=True, flip_yz=False, force_auto_normal=False, auto_normal_seamless=False, device=None):
-    """``Mesh.load`` (mesh_utils.py:80-113): read, fix normals / UVs, optional y-up -> z-up flip (the inverse of ``write``'s)."""
-    if path.endswith('.obj'):
+def load(path, resize=False, auto_uv=True, flip_yz=False, force_auto_normal=False, auto_normal_seamless=False, device=None, mesh=None):
+    """``Mesh.load`` (mesh_utils.py:80-113): read (or take ``mesh``, the reference's ``path=None`` + constructor kwargs), fix normals / UVs,
+    optional y-up -> z-up flip (the inverse of ``write``'s)."""
+    if mesh is not None:
+        pass
+    elif path.endswith('.obj'):
         mesh = load_obj(path, device)
     elif path.endswith('.ply'):
         mesh = load_ply(path, device)

@@ -59,11 +59,12 @@ class Mesh:
                     textureless=self.textureless)
 
     @classmethod
-    def load(cls, path, resize=False, auto_uv=True, flip_yz=False, force_auto_normal=False, auto_normal_seamless=False, device=None):
-        """``.obj`` (face uvs / normals, ``map_Kd`` texture), ``.glb`` and the binary ``.ply`` of ``write`` (``mesh_utils.py:80-345``)."""
+    def load(cls, path=None, resize=False, auto_uv=True, flip_yz=False, force_auto_normal=False, auto_normal_seamless=False, device=None, **kwargs):
+        """``.obj`` (face uvs / normals, ``map_Kd`` texture), ``.glb`` and the binary ``.ply`` of ``write`` (``mesh_utils.py:80-345``); with
+        ``path=None`` the mesh is built from the constructor ``kwargs`` and then fixed up the same way."""
         from . import mesh_io
         return mesh_io.load(path, resize=resize, auto_uv=auto_uv, flip_yz=flip_yz, force_auto_normal=force_auto_normal,
-                            auto_normal_seamless=auto_normal_seamless, device=device)
+                            auto_normal_seamless=auto_normal_seamless, device=device, mesh=cls(device=device, **kwargs) if path is None else None)
 
     def write(self, path, flip_yz=False):
         """``.obj`` (+ .mtl + albedo PNG) / ``.ply`` / ``.glb`` (``mesh_utils.py:461-692``; containers written by ``mesh_io``)."""
