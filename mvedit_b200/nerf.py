@@ -57,6 +57,9 @@ def highpass(x, std=5, offset=0.5):
     return offset + x - blur_masks(x, int(round(std)) * 6 + 1, std)
 
 
+_default_highpass = highpass          # (``nerf_optim`` has an argument of the same name)
+
+
 class L1LossMod(nn.Module):
     """Holder of the pixel-loss weight (lib/models/losses/pixelwise_loss.py:9-35; the pipelines build it with loss_weight=1.2,
     lib/pipelines/utils.py:231).  The fused objective kernel reads ``loss_weight``; ``forward`` is the plain weighted-mean L1."""
@@ -252,7 +255,7 @@ def nerf_optim(nerf, tgt_images, tgt_masks, tgt_normals, optimizer, lr, inverse_
     if lpips is not None and not hasattr(lpips, 'loss_and_grad'):
         raise NotImplementedError('nerf_optim: nerf.patch_loss must be a mvedit_b200.lpips.LPIPSLoss (kernels, no autograd graph); got %r'
                                   % type(lpips).__name__)
-    hp = globals()['highpass'] if highpass is None else highpass
+    hp = _default_highpass if highpass is None else highpass
     normal_bg = tuple(float(v) for v in normal_bg)
     ps = nerf.patch_size
     assert patch_size == ps
