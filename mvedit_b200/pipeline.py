@@ -29,6 +29,22 @@ from ._lib import call, ptr, stream, c_u32, c_f32
 from .tonemapping import tone_args
 
 
+def segment(images, seg_model, padding=0, bg_color=None, color_threshold=0.25):
+    """The tensor path of ``do_segmentation`` (lib/pipelines/utils.py:73-96; what ``get_tgt_masks`` runs on the decoded views every step,
+    adapter3d_mixin.py:14-19) around the segmentation network: replicate padding "helps to detect foreground objects", and every pixel that is
+    not within ``color_threshold`` of the background colour in all channels is foreground whatever the network says.
+    images (N,3,H,W) in [0,1] -> masks (N,1,H,W)."""
+    if padding > 0:
+        masks = seg_model(torch.nn.functional.pad(images, (padding, padding, padding, padding), mode='replicate'))[:, :, padding:-padding, padding:-padding]
+    else:
+        masks = seg_model(images)
+    if bg_color is not None:
+        bg = images.new_tensor(bg_color)[..., None, None]
+        non_fg = torch.all(bg - color_threshold <= images, dim=1) & torch.all(images <= bg + color_threshold, dim=1)
+        masks = torch.where(non_fg.unsqueeze(1), masks, torch.ones_like(masks))
+    return masks
+
+
 class MVEdit3DStep(Adapter3DMixin):
     """The loop body of MVEdit3DPipeline.__call__ (NeRF stage) on B200 components."""
 
@@ -55,8 +71,8 @@ class MVEdit3DStep(Adapter3DMixin):
         imgs = self.vae.decode_images(pred_x0)
         if self.segmentation is None:
             raise RuntimeError('MVEdit3DStep: no segmentation callable for the target masks (TRACER is not built)')
-        masks = self.segmentation(imgs.permute(0, 3, 1, 2)).permute(0, 2, 3, 1).float()
-        return imgs, masks
+        masks = segment(imgs.permute(0, 3, 1, 2), self.segmentation, padding=seg_padding, bg_color=getattr(self, 'bg_color', self.nerf.bg_color))
+        return imgs, masks.permute(0, 2, 3, 1).float()
 
     # ------------------------------------------------------------------ render all (local) views, mvedit_3d_pipeline.py:1341-1395
     def render_views(self, density_bitfield, camera_poses, intrinsics, intrinsics_size, render_size, cam_lights, ambient_light,

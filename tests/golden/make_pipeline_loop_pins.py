@@ -71,8 +71,20 @@ class ToyVAE:
         return (self.decode(pred_x0 / self.config.scaling_factor, return_dict=False)[0] / 2 + 0.5).clamp(min=0, max=1).permute(0, 2, 3, 1).float()
 
 
-def toy_segmentation(images_nchw):
-    return torch.sigmoid((0.62 - images_nchw.float().mean(dim=1, keepdim=True)) * 25)
+class ToySegmentation(nn.Module):
+    """Stands for TRACER: images (n,3,H,W) -> soft masks (n,1,H,W); not shift invariant (a 5x5 box filter), so the replicate padding of
+    ``do_segmentation`` shows."""
+
+    def __init__(self):
+        super().__init__()
+        self.bias = nn.Parameter(torch.tensor(0.62))
+
+    def forward(self, images_nchw):
+        m = F.avg_pool2d(images_nchw.float().mean(dim=1, keepdim=True), 5, stride=1, padding=2, count_include_pad=True)
+        return torch.sigmoid((self.bias - m) * 25)
+
+
+toy_segmentation = ToySegmentation()
 
 
 class ToyEnhancer(nn.Module):
@@ -184,7 +196,7 @@ def inputs():
 
 CASES = dict(
     optim_only=dict(optim_only=True, num_inference_steps=4),
-    two_pass=dict(mode='2-pass', use_reference=False, blend_weight=0.0),
+    two_pass=dict(mode='2-pass', use_reference=False, blend_weight=0.0, seg_padding=16),
     one_pass_dynamic=dict(mode='1-pass', use_reference=False, blend_weight='dynamic'),
     reference_pairs=dict(mode='2-pass', use_reference=True, blend_weight='dynamic'),
     from_noise=dict(mode='1-pass', use_reference=False, blend_weight=0.0, denoising_strength=None, num_inference_steps=3),
@@ -315,7 +327,8 @@ def main():
             return acc
     menv = dict(torch=torch, copy=__import__('copy').copy, MultiControlNetModel=MultiControlNetModel,
                 unet_enc=lambda unet, *a, **k: unet.enc(*a, **k), unet_dec=lambda unet, *a, **k: unet.dec(*a, **k))
-    M = extract('lib/pipelines/adapter3d_mixin.py', ['get_noise_pred', 'get_noise_pred_p1', 'get_noise_pred_p2'], menv)
+    menv['do_segmentation'] = extract('lib/pipelines/utils.py', ['do_segmentation'], dict(torch=torch, F=F, np=np))['do_segmentation']
+    M = extract('lib/pipelines/adapter3d_mixin.py', ['get_noise_pred', 'get_noise_pred_p1', 'get_noise_pred_p2', 'get_tgt_masks'], menv)
 
     class _Never:
         pass
@@ -349,7 +362,6 @@ def main():
         for n, fn in M.items():
             setattr(self_, n, types.MethodType(fn, self_))
         self_.get_prompt_embeds = lambda *a, **k: embeds.clone()
-        self_.get_tgt_masks = lambda tgt_images, pad: toy_segmentation(tgt_images.squeeze(0).clip(min=0, max=1).permute(0, 3, 1, 2))[:, 0][None, ..., None]
         self_.nerf_optim = lambda *a, **k: record_call(log, field, *a, **k)
         self_.mesh_optim = lambda *a, **k: record_mesh_call(log, field, *a, **k)
         self_.make_nerf_shading_fun = lambda *a, **k: None

@@ -67,7 +67,9 @@ def test_call_hands_nerf_optim_what_the_reference_loop_hands_it(case, monkeypatc
             if k in gen.MAPS:
                 assert tuple(v.shape) == tuple(PINS[key + '_shape']), (key, v.shape)
                 x = v[0].permute(0, 3, 1, 2)
-                np.testing.assert_allclose(torch.nn.functional.avg_pool2d(x, 8).numpy(), PINS[key + '_pooled'], rtol=0, atol=1.5e-2, err_msg=key)
+                d = np.abs(torch.nn.functional.avg_pool2d(x, 8).numpy() - PINS[key + '_pooled'])
+                # the masks carry a hard colour threshold (do_segmentation's background rule): a bf16-rounded pixel may sit on the other side
+                assert d.max() <= (0.1 if k == 'tgt_masks' else 1.5e-2) and (d > 1.5e-2).mean() <= 0.005, (key, float(d.max()), float((d > 1.5e-2).mean()))
                 np.testing.assert_allclose(x.flatten(2).std(dim=2).numpy(), PINS[key + '_std'], rtol=0, atol=1.5e-2, err_msg=key)
             elif torch.is_tensor(v):
                 np.testing.assert_allclose(v.numpy(), PINS[key], rtol=1e-5, atol=1e-6, err_msg=key)       # cameras, intrinsics, weights, lights
@@ -98,7 +100,7 @@ def test_step_is_one_iteration_of_the_pinned_loop(monkeypatch):
     sch.step = spy
     poses, intr, init, embeds = gen.inputs()
     kw = gen.call_kwargs('two_pass', poses, intr, init)
-    kw.update(keep_views=None, max_num_views=lambda p, q: gen.N)                 # no re-ordering, no pruning: step() works on a fixed view set
+    kw.update(keep_views=None, max_num_views=lambda p, q: gen.N, seg_padding=0)  # no re-ordering, no pruning, no padding: what step() does
     torch.manual_seed(99)
     mesh, state = pipe(prompt_embeds=embeds.clone(), **kw)
     assert state is not None and len(solver) == 2 and len(log) == 4              # the last iteration fits and stops: no solver step (:1409)
