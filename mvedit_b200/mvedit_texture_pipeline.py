@@ -9,8 +9,7 @@ as the next step's tile condition; after the last step ``texture_optim`` fits th
 Host-side helpers with the reference's definitions: ``default_patch_rgb_weight`` / ``default_max_num_views`` (``:32-37``) and
 ``camera_dense_weighting`` (``:40-50``), pinned against the reference's functions by tests/test_mesh_pins.py.
 
-Not built: IP-Adapter image prompts (``ip_adapter=`` raises, as in the 3D pipeline), ``in_model`` given as a file path, the
-super-resolution variant's regulariser cameras (``mvedit_texture_superres_pipeline.py``; its ``texture_optim`` is the same function).
+``ip_adapter`` is any object with the reference IPAdapter's ``get_prompt_embeds`` (as in the 3D pipeline).
 """
 import traceback
 from copy import deepcopy
@@ -72,8 +71,6 @@ class MVEditTexturePipeline(MVEdit3DPipeline):
                                     'blurry, jpeg artifacts, macro',
                  bake_texture=True, bake_texture_kwargs=None, mode='1-pass', prog_bar=None, prompt_embeds=None):
         """-> (textured mesh | None, ingp state dict | None), as mvedit_texture_pipeline.py:175-544."""
-        if ip_adapter is not None:
-            raise NotImplementedError('MVEditTexturePipeline: ip_adapter image prompts are not built on the B200 path')
         assert in_model is not None
         assert optim_only or mode in ('1-pass', '2-pass')
         nerf, dec, sch = self.nerf, self.nerf.decoder, self.scheduler
@@ -111,8 +108,9 @@ class MVEditTexturePipeline(MVEdit3DPipeline):
                 if denoising_strength is not None:
                     timesteps = timesteps[min(int(round(len(timesteps) * (1 - denoising_strength) / sch.order)) * sch.order,
                                               len(timesteps) - 1):]
-                pe = self.get_prompt_embeds([join_prompts(p, default_prompt) for p in prompt],
-                                            [join_prompts(p, default_neg_prompt) for p in negative_prompt], prompt_embeds)
+                pe = self.get_prompt_embeds(in_images, [join_prompts(p, default_prompt) for p in prompt],
+                                            [join_prompts(p, default_neg_prompt) for p in negative_prompt], ip_adapter=ip_adapter,
+                                            cond_images=cond_images, prompt_embeds=prompt_embeds)
                 encode = lambda x: torch.cat([self.vae.encode(b * 2 - 1).latent_dist.sample() * self.vae.config.scaling_factor
                                               for b in x.split(diff_bs, dim=0)], dim=0)
                 init_latents = encode(in_images)
@@ -235,6 +233,22 @@ class MVEditTextureSuperResPipeline(MVEditTexturePipeline):
     field is blended with the original texture by per-texel camera confidence (``get_cam_weights_uv``, cos^4, original weight 0.2^4).
     Returns the mesh only, as the reference (``:493-496``)."""
 
+    def get_prompt_embeds(self, in_images, rgb_prompt, rgb_negative_prompt, ip_adapter=None, ip_adapter_use_cond_idx=None, cond_images=None,
+                          prompt_embeds=None):
+        """mvedit_texture_superres_pipeline.py:62-87: as the 3D pipeline's, but the IP-Adapter looks at the INPUT renders, replaced by the
+        conditioning image only for the views listed in ``ip_adapter_use_cond_idx``."""
+        if ip_adapter is None:
+            return super().get_prompt_embeds(in_images, rgb_prompt, rgb_negative_prompt, prompt_embeds=prompt_embeds)
+        size = (self.clip_img_size, self.clip_img_size)
+        ipa = F.interpolate(in_images, size=size, mode='bilinear')
+        if isinstance(ip_adapter_use_cond_idx, list) and cond_images is not None:
+            ipa = ipa.clone()
+            for idx, c in enumerate(cond_images):
+                if idx in ip_adapter_use_cond_idx:
+                    ipa[idx] = F.interpolate(c, size=size, mode='bilinear')[0]
+        return ip_adapter.get_prompt_embeds((ipa - ipa.new_tensor(self.clip_img_mean)[:, None, None]) / ipa.new_tensor(self.clip_img_std)[:, None, None],
+                                            prompt=rgb_prompt, negative_prompt=rgb_negative_prompt)
+
     def __call__(self, prompt='', negative_prompt='', in_model=None, ingp_states=None, init_images=None, cond_images=None,
                  extra_control_images=None, nerf_code=None, camera_poses=None, reg_camera_poses=None, intrinsics=None, intrinsics_size=256,
                  use_reference=True, cam_weights=None, reg_cam_weights=None, guidance_scale=7, num_inference_steps=26, denoising_strength=0.5,
@@ -244,8 +258,6 @@ class MVEditTextureSuperResPipeline(MVEditTexturePipeline):
                  default_prompt='best quality, sharp focus, photorealistic, extremely detailed',
                  default_neg_prompt='worst quality, low quality, depth of field, blurry, out of focus, low-res, illustration, painting, drawing',
                  bake_texture_kwargs=None, prog_bar=None, prompt_embeds=None):
-        if ip_adapter is not None:
-            raise NotImplementedError('MVEditTextureSuperResPipeline: ip_adapter image prompts are not built on the B200 path')
         assert in_model is not None
         from .mesh_renderer import edge_dilation
         nerf, dec, sch = self.nerf, self.nerf.decoder, self.scheduler
@@ -291,8 +303,9 @@ class MVEditTextureSuperResPipeline(MVEditTexturePipeline):
                 if denoising_strength is not None:
                     timesteps = timesteps[min(int(round(len(timesteps) * (1 - denoising_strength) / sch.order)) * sch.order,
                                               len(timesteps) - 1):]
-                pe = self.get_prompt_embeds([join_prompts(p, default_prompt) for p in prompt],
-                                            [join_prompts(p, default_neg_prompt) for p in negative_prompt], prompt_embeds)
+                pe = self.get_prompt_embeds(in_images, [join_prompts(p, default_prompt) for p in prompt],
+                                            [join_prompts(p, default_neg_prompt) for p in negative_prompt], ip_adapter=ip_adapter,
+                                            ip_adapter_use_cond_idx=ip_adapter_use_cond_idx, cond_images=cond_images, prompt_embeds=prompt_embeds)
                 encode = lambda x: torch.cat([self.vae.encode(b * 2 - 1).latent_dist.sample() * self.vae.config.scaling_factor
                                               for b in x.split(diff_bs, dim=0)], dim=0)
                 init_latents = encode(in_images)

@@ -138,6 +138,22 @@ class ToyField(nn.Module):
         return torch.cat([rgb, alpha[..., None]], dim=-1)[None], depth[None], normal[None], nfg[None]
 
 
+class ToyIPAdapter:
+    """Stands for the reference IPAdapter object (ip_adapter.py:151-168): text tokens + 4 image tokens per view, [neg ; pos]; keeps the images
+    it was shown (the pipeline's CLIP-size, CLIP-normalised hand-over)."""
+
+    def __init__(self, embeds):
+        self.embeds, self.seen = embeds, []
+        self.proj = torch.randn(3, embeds.shape[-1], generator=torch.Generator().manual_seed(31))
+
+    def get_prompt_embeds(self, images, negative_images=None, prompt=None, negative_prompt=None):
+        self.seen.append(images.detach().float().clone())
+        assert len(prompt) == len(negative_prompt) == images.shape[0]
+        neg, pos = self.embeds.chunk(2)
+        tokens = (images.float().mean(dim=(2, 3)) @ self.proj)[:, None, :].repeat(1, 4, 1) * torch.tensor([1.0, 0.5, -0.5, 2.0])[None, :, None]
+        return torch.cat([torch.cat([neg, torch.zeros_like(tokens)], dim=1), torch.cat([pos, tokens], dim=1)], dim=0)
+
+
 class ToyMeshRenderer:
     """Stands for MeshRenderer in the per-step render of the DMTet stage: the same procedural blob, tinted, so that the hand-over of the mesh
     branch (:1345-1362) is visible in the next step's targets."""
@@ -203,15 +219,22 @@ CASES = dict(
     targets=dict(mode='1-pass', use_reference=False, blend_weight=0.0, use_normal=True, depth_weight=0.4),
     dmtet=dict(mode='2-pass', use_reference=False, blend_weight=0.0, progress_to_dmtet=0.5, tet_init_inverse_steps=13, tet_resolution=8,
                mesh_reduction=1.0),
+    ip_adapter=dict(mode='1-pass', use_reference=False, blend_weight=0.0, ip=True),
+    ip_adapter_cond=dict(mode='2-pass', use_reference=True, blend_weight=0.0, ip=True, cond=True),
     from_noise_reference=dict(mode='2-pass', use_reference=True, blend_weight=0.0, denoising_strength=None, num_inference_steps=3))
 
 
-def call_kwargs(case, poses, intr, init):
+def call_kwargs(case, poses, intr, init, embeds=None):
     kw = dict(prompt='a toy', negative_prompt='', init_images=init, camera_poses=poses, intrinsics=intr, intrinsics_size=IMG,
               use_normal=False, keep_views=[3], guidance_scale=5.0, num_inference_steps=6, denoising_strength=0.5, progress_to_dmtet=1.0,
               patch_size=64, diff_bs=4, render_bs=2, n_inverse_rays=4096, n_inverse_steps=7, init_inverse_steps=11,
               render_size_p=lambda p: 128, max_num_views=lambda p, q: 5 if p < 0.5 else 3, ambient_light=0.2, bake_texture=False)
     kw.update(CASES[case])
+    if kw.pop('ip', False):
+        kw['ip_adapter'] = ToyIPAdapter(embeds)
+    if kw.pop('cond', False):                    # separate conditioning images: the reference pairs and the IP-Adapter look at these
+        g = torch.Generator().manual_seed(12)
+        kw['cond_images'] = [(torch.rand(96, 96, 3, generator=g) * 255).to(torch.uint8).numpy() for _ in range(N)]
     if kw['use_normal']:                          # image-to-3D targets: one normal map and one depth map per view, all different
         g = torch.Generator().manual_seed(9)
         kw['normals'] = [(F.normalize(torch.rand(64, 64, 3, generator=g) - 0.5 + torch.tensor([0.0, 0.0, 1.0 + k]), dim=-1) * 127.5 + 127.5
@@ -348,7 +371,8 @@ def main():
     names = ['default_lr_multiplier', 'default_max_num_views', 'default_render_size_p', 'default_lr_schedule', 'default_patch_rgb_weight',
              'default_patch_normal_weight', 'default_entropy_weight', 'default_normal_reg_weight']
     extract('lib/pipelines/mvedit_3d_pipeline.py', names, penv)
-    Pm = extract('lib/pipelines/mvedit_3d_pipeline.py', ['__call__', 'load_init_images', 'load_cond_images', 'enable_normals', 'load_depths'], penv)
+    Pm = extract('lib/pipelines/mvedit_3d_pipeline.py', ['__call__', 'load_init_images', 'load_cond_images', 'enable_normals', 'load_depths',
+                                                         'get_prompt_embeds'], penv)
     poses, intr, init, embeds = inputs()
     out = {}
     for case in CASES:
@@ -356,18 +380,20 @@ def main():
         self_ = types.SimpleNamespace(
             nerf=field, unet=ToyUNet(), controlnet=MultiControlNetModel(mixin_gen.toy_nets(2)), vae=ToyVAE(), scheduler=DiffusersShapedScheduler(),
             image_enhancer=ToyEnhancer(), segmentation=toy_segmentation, tonemapping=None, bg_color=field.bg_color, normal_bg=[0.5, 0.5, 1.0],
-            mesh_renderer=ToyMeshRenderer(field), normal_model=None)
-        for n in ('load_init_images', 'load_cond_images', 'enable_normals', 'load_depths'):
+            mesh_renderer=ToyMeshRenderer(field), normal_model=None, clip_img_size=224, clip_img_mean=[0.48145466, 0.4578275, 0.40821073],
+            clip_img_std=[0.26862954, 0.26130258, 0.27577711], controlnet_=None)
+        for n in ('load_init_images', 'load_cond_images', 'enable_normals', 'load_depths', 'get_prompt_embeds'):
             setattr(self_, n, types.MethodType(Pm[n], self_))
         for n, fn in M.items():
             setattr(self_, n, types.MethodType(fn, self_))
-        self_.get_prompt_embeds = lambda *a, **k: embeds.clone()
+        self_._encode_prompt = lambda *a, **k: embeds.clone()
         self_.nerf_optim = lambda *a, **k: record_call(log, field, *a, **k)
         self_.mesh_optim = lambda *a, **k: record_mesh_call(log, field, *a, **k)
         self_.make_nerf_shading_fun = lambda *a, **k: None
         del tb[:]
         torch.manual_seed(1234)
-        res = Pm['__call__'](self_, prog_bar=lambda x: x, **call_kwargs(case, poses, intr, [a.copy() for a in init]))
+        kw = call_kwargs(case, poses, intr, [a.copy() for a in init], embeds)
+        res = Pm['__call__'](self_, prog_bar=lambda x: x, **kw)
         # the reference cannot return from a run that never enters the DMTet stage (``in_mesh`` is unbound at :1482): that NameError, caught
         # by its own try / except, is the ONLY failure allowed here -- everything recorded happened before it
         if case == 'dmtet':
@@ -375,6 +401,9 @@ def main():
         else:
             assert res == (None, None) and len(tb) == 1 and 'in_mesh' in tb[0].strip().splitlines()[-1], tb
         out.update(flatten(log, case + '_'))
+        if kw.get('ip_adapter') is not None:
+            assert len(kw['ip_adapter'].seen) == 1
+            out[case + '_ipa_images'] = F.avg_pool2d(kw['ip_adapter'].seen[0], 16).numpy()
         print(case, 'steps', len(log), 'views', [int(r['camera_poses'].shape[0]) for r in log], 'render sizes', [r['render_size'] for r in log])
     np.savez_compressed(OUT, **out)
     print('wrote', OUT, sum(v.nbytes for v in out.values()) // 1024, 'KiB')

@@ -102,10 +102,12 @@ CASES = dict(
     tex_two_pass_reference=dict(pipe='texture', mode='2-pass', use_reference=True, weighted_cam_pruning=True, cam_weights=[1.0, 2.0, 0.5, 1.0, 1.5]),
     tex_from_noise_reference=dict(pipe='texture', mode='1-pass', use_reference=True, denoising_strength=None, num_inference_steps=3),
     sr_plain=dict(pipe='superres', use_reference=False),
-    sr_reference_reg=dict(pipe='superres', use_reference=True, reg=True))
+    sr_reference_reg=dict(pipe='superres', use_reference=True, reg=True),
+    tex_ip_adapter=dict(pipe='texture', mode='1-pass', use_reference=True, ip=True, cond=True),
+    sr_ip_adapter_some_cond=dict(pipe='superres', use_reference=False, ip=True, cond=True, ip_adapter_use_cond_idx=[0, 3]))
 
 
-def call_kwargs(case, poses, intr):
+def call_kwargs(case, poses, intr, embeds=None):
     c = dict(CASES[case])
     kind = c.pop('pipe')
     kw = dict(prompt='a toy', in_model=ToyMesh(), camera_poses=poses[:N], intrinsics=intr, intrinsics_size=S, guidance_scale=5.0,
@@ -117,6 +119,11 @@ def call_kwargs(case, poses, intr):
         kw['camera_poses'] = poses[:N, :3]                   # the reference's empty regulariser set is (0, 3, 4): 3 x 4 poses throughout
         if c.pop('reg', False):
             kw.update(reg_camera_poses=poses[N:, :3], reg_cam_weights=[0.5, 0.25])
+    if c.pop('ip', False):
+        kw['ip_adapter'] = L.ToyIPAdapter(embeds)
+    if c.pop('cond', False):
+        g = torch.Generator().manual_seed(12)
+        kw['cond_images'] = [(torch.rand(96, 96, 3, generator=g) * 255).to(torch.uint8).numpy() for _ in range(N)]
     kw.update(c)
     if case == 'sr_reference_reg':                   # an input mesh that brings its own texture: the baked result is blended with it (:468-487)
         kw['in_model'].albedo, kw['in_model'].textureless = torch.rand(32, 32, 4, generator=torch.Generator().manual_seed(8)), False
@@ -184,7 +191,8 @@ def main():
     T.update(L.extract('lib/pipelines/mvedit_texture_pipeline.py', ['__call__'], tenv))
     senv['camera_dense_weighting'], senv['default_patch_rgb_weight'] = T['camera_dense_weighting'], T['default_patch_rgb_weight']      # (:25-26)
     Sx = L.extract('lib/pipelines/mvedit_texture_superres_pipeline.py', ['__call__'], senv)
-    P3 = L.extract('lib/pipelines/mvedit_3d_pipeline.py', ['load_init_images', 'load_cond_images'], env())
+    P3 = L.extract('lib/pipelines/mvedit_3d_pipeline.py', ['load_init_images', 'load_cond_images', 'get_prompt_embeds'], env())
+    SP = L.extract('lib/pipelines/mvedit_texture_superres_pipeline.py', ['get_prompt_embeds'], env())
     poses, intr, embeds = inputs()
     out = {}
     for case in CASES:
@@ -193,13 +201,16 @@ def main():
         self_ = types.SimpleNamespace(
             nerf=renderer.field, unet=L.ToyUNet(), controlnet=MultiControlNetModel(L.mixin_gen.toy_nets(2)), vae=L.ToyVAE(),
             scheduler=L.DiffusersShapedScheduler(), image_enhancer=L.ToyEnhancer(), segmentation=None, tonemapping=None, bg_color=0.5,
-            normal_bg=[0.5, 0.5, 1.0], mesh_renderer=renderer)
+            normal_bg=[0.5, 0.5, 1.0], mesh_renderer=renderer, clip_img_size=224, clip_img_mean=[0.48145466, 0.4578275, 0.40821073],
+            clip_img_std=[0.26862954, 0.26130258, 0.27577711])
         for n, fn in list(P3.items()) + list(M.items()):
             setattr(self_, n, types.MethodType(fn, self_))
         self_.load_init_mesh = toy_load_init_mesh(renderer)
-        self_.get_prompt_embeds = lambda *a, **k: embeds.clone()
+        self_._encode_prompt = lambda *a, **k: embeds.clone()
         self_.make_nerf_albedo_shading_fun = lambda code: None
-        kind, kw = call_kwargs(case, poses, intr)
+        kind, kw = call_kwargs(case, poses, intr, embeds)
+        if kind == 'superres':                   # the super-resolution class overrides get_prompt_embeds (:62-87)
+            self_.get_prompt_embeds = types.MethodType(SP['get_prompt_embeds'], self_)
         if kind == 'texture':
             self_.texture_optim = lambda *a, **k: record_texture_optim(log, *a, **k)
         else:       # the super-resolution variant's own texture_optim takes num_cameras second (:89-91); the product passes it as patch_views=
@@ -211,6 +222,9 @@ def main():
         if kind == 'superres':
             log.append(dict(kind=4.0, maps=res.albedo[..., :3][None].clone()))       # the returned texture
         out.update(flatten(log, case + '_'))
+        if kw.get('ip_adapter') is not None:
+            assert len(kw['ip_adapter'].seen) == 1
+            out[case + '_ipa_images'] = F.avg_pool2d(kw['ip_adapter'].seen[0], 16).numpy()
         print(case, [int(r['kind']) for r in log], [tuple(r['maps'].shape) for r in log if 'maps' in r][-1])
     np.savez_compressed(OUT, **out)
     print('wrote', OUT, sum(v.nbytes for v in out.values()) // 1024, 'KiB')

@@ -54,8 +54,9 @@ def test_call_hands_nerf_optim_what_the_reference_loop_hands_it(case, monkeypatc
     pipe.render_views = lambda bitfield, poses, intr, intr_size, rs, cam_lights, ambient, tdg, render_bs=None, **kw: no.render_views(
         wrapped, bitfield, poses, intr, intr_size, rs, cam_lights, ambient, tdg, render_bs=render_bs, out_dtype=torch.float32)
     poses, intr, init, embeds = gen.inputs()
+    kw = gen.call_kwargs(case, poses, intr, init, embeds)
     torch.manual_seed(1234)
-    mesh, state = pipe(prompt_embeds=embeds.clone(), **gen.call_kwargs(case, poses, intr, init))
+    mesh, state = pipe(prompt_embeds=embeds.clone(), **kw)
     assert state is not None, 'the run raised inside __call__ (traceback printed above)'
     assert (mesh is not None) == (case == 'dmtet')                              # the DMTet mesh comes back once that stage was entered
     assert len(log) == int(PINS[case + '_steps'])
@@ -76,6 +77,9 @@ def test_call_hands_nerf_optim_what_the_reference_loop_hands_it(case, monkeypatc
             else:
                 assert float(v) == pytest.approx(float(PINS[key]), rel=1e-6), key                       # schedules, sizes, flags
     assert field.decoder.state_dict_bak is not None
+    if kw.get('ip_adapter') is not None:                                         # what the IP-Adapter was shown: CLIP size, CLIP normalisation
+        assert len(kw['ip_adapter'].seen) == 1
+        np.testing.assert_allclose(torch.nn.functional.avg_pool2d(kw['ip_adapter'].seen[0], 16).numpy(), PINS[case + '_ipa_images'], rtol=1e-4, atol=1e-4)
 
 
 def test_step_is_one_iteration_of_the_pinned_loop(monkeypatch):
@@ -99,7 +103,7 @@ def test_step_is_one_iteration_of_the_pinned_loop(monkeypatch):
         return out
     sch.step = spy
     poses, intr, init, embeds = gen.inputs()
-    kw = gen.call_kwargs('two_pass', poses, intr, init)
+    kw = gen.call_kwargs('two_pass', poses, intr, init, embeds)
     kw.update(keep_views=None, max_num_views=lambda p, q: gen.N, seg_padding=0)  # no re-ordering, no pruning, no padding: what step() does
     torch.manual_seed(99)
     mesh, state = pipe(prompt_embeds=embeds.clone(), **kw)

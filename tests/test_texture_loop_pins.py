@@ -32,7 +32,7 @@ def test_texture_pipelines_hand_over_what_the_reference_loops_hand_over(case, mo
     log = []
     renderer = gen.ToyTexRenderer(log)
     poses, intr, embeds = gen.inputs()
-    kind, kw = gen.call_kwargs(case, poses, intr)
+    kind, kw = gen.call_kwargs(case, poses, intr, embeds)
     cls = TP.MVEditTexturePipeline if kind == 'texture' else TP.MVEditTextureSuperResPipeline
     pipe = cls(gen.L.ToyVAE(), None, None, gen.L.ToyUNet(), gen.L.mixin_gen.toy_nets(2), EulerAncestralScheduler(), renderer.field, renderer)
     pipe.load_init_mesh = gen.toy_load_init_mesh(renderer)
@@ -46,6 +46,9 @@ def test_texture_pipelines_hand_over_what_the_reference_loops_hand_over(case, mo
         assert res is not None, 'the run raised inside __call__ (traceback printed above)'
         log.append(dict(kind=4.0, maps=res.albedo[..., :3][None].clone()))
     assert len(log) == int(PINS[case + '_calls']), [r['kind'] for r in log]
+    if kw.get('ip_adapter') is not None:
+        assert len(kw['ip_adapter'].seen) == 1
+        np.testing.assert_allclose(torch.nn.functional.avg_pool2d(kw['ip_adapter'].seen[0], 16).numpy(), PINS[case + '_ipa_images'], rtol=1e-4, atol=1e-4)
     for i, rec in enumerate(log):
         assert rec['kind'] == float(PINS['%s_%d_kind' % (case, i)]), (i, rec['kind'])
         for k, v in rec.items():
