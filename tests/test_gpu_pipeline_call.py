@@ -123,8 +123,6 @@ def test_unbuilt_options_raise_and_restore(parts):
     with pytest.raises(NotImplementedError):
         call(pipe, parts, use_normal=True)                          # no normals handed in and no normal_model to predict them
     assert all(torch.equal(dec.state_dict()[k], before[k]) for k in before)
-    with pytest.raises(NotImplementedError):
-        call(pipe, parts, ip_adapter=object())
     mesh, state = call(pipe, parts, progress_to_dmtet=0.3)           # DMTet stage without a mesh_renderer: the reference-style swallow
     assert mesh is None and state is None
     assert all(torch.equal(dec.state_dict()[k], before[k]) for k in before)
