@@ -58,6 +58,8 @@ def _targets():
         RT2 + 'Tonemapping.__init__': (tonemapping.Tonemapping.__init__, 1), RT2 + 'Tonemapping.lut': (tonemapping.Tonemapping.lut, 1),
         RT2 + 'Tonemapping.inverse_lut': (tonemapping.Tonemapping.inverse_lut, 1), RT2 + 'Tonemapping.smooth_forward': (tonemapping.Tonemapping.smooth_forward, 1),
         'lib/core/utils/camera_utils.py::light_sampling': (p3.light_sampling, 0)})
+    t[RV + 'VolumeRenderer.forward'] = (ingp_decoder.iNGPDecoder.forward, 1)
+    t[RV + 'VolumeRenderer.update_extra_state'] = (ingp_decoder.iNGPDecoder.update_extra_state, 1)
     for n in ('default_lr_multiplier', 'default_max_num_views', 'default_render_size_p', 'default_lr_schedule', 'default_patch_rgb_weight',
               'default_patch_normal_weight', 'default_entropy_weight', 'default_normal_reg_weight'):
         t[R3 + n] = (getattr(p3, n), 0)
@@ -109,3 +111,14 @@ def test_mirror_keeps_the_reference_signature(key):
 def _name_of(fn, value):
     mod = inspect.getmodule(fn)
     return next((k for k, v in vars(mod).items() if v is value and k.startswith('default_')), None)
+
+
+def test_decoder_constructor_keywords():
+    """``iNGPDecoder(*args, base_resolution=..., ...)`` (ingp_decoder.py:47-58) is configured by keyword from the reference's config dicts
+    (lib/pipelines/utils.py:216-227): every keyword of the reference exists in the mirror with the same default."""
+    from mvedit_b200.ingp_decoder import iNGPDecoder
+    mine = inspect.signature(iNGPDecoder.__init__).parameters
+    for name, default in PINS['lib/models/decoders/ingp_decoder.py::iNGPDecoder.__init__']:
+        if name.startswith('*'):
+            continue
+        assert name in mine and _norm(repr(mine[name].default)) == _norm(default), (name, default)
