@@ -83,6 +83,14 @@ def triplane_inputs():
     return torch.rand(2048, 3, generator=g) * 2.2 - 1.1, r(1, 3, C, 20, 20), sd, levels      # some points beyond the planes: border padding
 
 
+def shading_inputs():
+    g = torch.Generator().manual_seed(11)
+    fg = torch.rand(1, 3, 16, 16, generator=g) > 0.4
+    n = int(fg.sum())
+    lights = torch.nn.functional.normalize(torch.randn(3, 16, 16, 3, generator=g), dim=-1)
+    return lights, torch.rand(n, 3, generator=g) * 0.9 + 0.05, torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1), fg
+
+
 def extract(rel, name, env):
     tree = ast.parse(open(os.path.join(REF, rel)).read())
     node = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == name)
@@ -185,6 +193,15 @@ def main():
         with torch.no_grad():
             s_, c_, _ = tenv['point_decode'](tp, [xyz_t], None, code)
         out['tri_sigma_' + cfg_name], out['tri_rgb_' + cfg_name] = s_.numpy(), c_.numpy()
+    # ---- MVEdit3DPipeline.make_shading_fun (mvedit_3d_pipeline.py:410-423): Lambert shading of a mesh's own albedo, plain and tone-mapped
+    sp2 = importlib.util.spec_from_file_location('ref_tonemapping', os.path.join(REF, 'lib/models/decoders/tonemapping.py'))
+    tmm = importlib.util.module_from_spec(sp2)
+    sp2.loader.exec_module(tmm)
+    msf = extract('lib/pipelines/mvedit_3d_pipeline.py', 'make_shading_fun', dict(torch=torch))
+    lights, albedo, normal, fg = shading_inputs()
+    for name, tone in (('plain', None), ('tone', tmm.Tonemapping())):
+        fun = msf(types.SimpleNamespace(tonemapping=tone), lights, 0.2)
+        out['shade_' + name] = fun(world_pos=None, albedo=albedo, world_normal=normal, fg_mask=fg).numpy()
     np.savez_compressed(OUT, **out)
     print('wrote', OUT, {k: v.shape for k, v in out.items()})
 

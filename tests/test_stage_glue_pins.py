@@ -70,3 +70,14 @@ def test_triplane_composition_matches_the_reference_decoder():
         np.testing.assert_allclose(sig.numpy(), PINS['tri_sigma_' + name], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(rgb.numpy(), PINS['tri_rgb_' + name], rtol=1e-5, atol=1e-6)
     assert np.abs(PINS['tri_rgb_a'] - PINS['tri_rgb_b']).max() > 0.05
+
+
+def test_make_shading_fun_matches_the_reference_method():
+    from mvedit_b200.mvedit_3d_pipeline import MVEdit3DPipeline
+    from mvedit_b200.tonemapping import Tonemapping
+    lights, albedo, normal, fg = gen.shading_inputs()
+    for name, tone in (('plain', None), ('tone', Tonemapping())):
+        pipe = object.__new__(MVEdit3DPipeline)
+        pipe.tonemapping = tone
+        got = pipe.make_shading_fun(lights, 0.2)(world_pos=None, albedo=albedo, world_normal=normal, fg_mask=fg)
+        np.testing.assert_allclose(got.numpy(), PINS['shade_' + name], rtol=1e-5, atol=1e-6)
