@@ -91,6 +91,17 @@ def shading_inputs():
     return lights, torch.rand(n, 3, generator=g) * 0.9 + 0.05, torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1), fg
 
 
+def init_nerf_inputs():
+    import importlib.util as iu
+    sp = iu.spec_from_file_location('make_pipeline_loop_pins', os.path.join(os.path.dirname(os.path.abspath(__file__)), 'make_pipeline_loop_pins.py'))
+    L = iu.module_from_spec(sp)
+    sp.loader.exec_module(L)
+    poses, intr = glue_inputs()
+    g = torch.Generator().manual_seed(13)
+    lw = torch.nn.functional.normalize(torch.randn(5, 3, generator=g), dim=-1)
+    return L.ToyField(), poses, intr * 2, lw, (lw[:, None, :] @ poses[:, :3, :3]).squeeze(-2)
+
+
 def extract(rel, name, env):
     tree = ast.parse(open(os.path.join(REF, rel)).read())
     node = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == name)
@@ -202,6 +213,13 @@ def main():
     for name, tone in (('plain', None), ('tone', tmm.Tonemapping())):
         fun = msf(types.SimpleNamespace(tonemapping=tone), lights, 0.2)
         out['shade_' + name] = fun(world_pos=None, albedo=albedo, world_normal=normal, fg_mask=fg).numpy()
+    # ---- MVEdit3DPipeline.load_init_nerf (mvedit_3d_pipeline.py:138-173): initial targets rendered from the field, shaded per view
+    lin = extract('lib/pipelines/mvedit_3d_pipeline.py', 'load_init_nerf', dict(torch=torch))
+    field, poses5, intr5, l_world, l_cam = init_nerf_inputs()
+    for name, tone in (('plain', None), ('tone', tmm.Tonemapping())):
+        im, al = lin(types.SimpleNamespace(nerf=field, tonemapping=tone, normal_bg=[0.5, 0.5, 1.0]), [None], None, poses5, intr5, 64, l_world, l_cam, 0.2,
+                     2, 0.25, diff_size=48)
+        out['lin_images_' + name], out['lin_alphas_' + name] = im.numpy(), al.numpy()
     np.savez_compressed(OUT, **out)
     print('wrote', OUT, {k: v.shape for k, v in out.items()})
 

@@ -81,3 +81,15 @@ def test_make_shading_fun_matches_the_reference_method():
         pipe.tonemapping = tone
         got = pipe.make_shading_fun(lights, 0.2)(world_pos=None, albedo=albedo, world_normal=normal, fg_mask=fg)
         np.testing.assert_allclose(got.numpy(), PINS['shade_' + name], rtol=1e-5, atol=1e-6)
+
+
+def test_load_init_nerf_matches_the_reference_method():
+    from mvedit_b200.mvedit_3d_pipeline import MVEdit3DPipeline
+    from mvedit_b200.tonemapping import Tonemapping
+    field, poses, intr, l_world, l_cam = gen.init_nerf_inputs()
+    for name, tone in (('plain', None), ('tone', Tonemapping())):
+        pipe = object.__new__(MVEdit3DPipeline)
+        pipe.nerf, pipe.tonemapping, pipe.normal_bg = field, tone, [0.5, 0.5, 1.0]
+        im, al = pipe.load_init_nerf([None], None, poses, intr, 64, l_world, l_cam, 0.2, 2, 0.25, diff_size=48)
+        np.testing.assert_allclose(im.numpy(), PINS['lin_images_' + name], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(al.numpy(), PINS['lin_alphas_' + name], rtol=1e-6, atol=1e-7)
