@@ -13,6 +13,26 @@ from tests import synth
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
+def test_simplify_mesh_from_device_tensors():
+    """``simplify_mesh`` (host C++) fed from CUDA tensors, and the decimated mesh through the rasteriser."""
+    from mvedit_b200.mesh_renderer import DMTet, Mesh, MeshRenderer, make_tet_grid, simplify_mesh
+    grid = make_tet_grid(24, device='cuda')
+    tv = -grid['vertices'] * 2 * 0.9
+    sdf = 0.5 - tv.norm(dim=-1) + 0.06 * torch.sin(7 * tv[:, 0]) * torch.sin(6 * tv[:, 1])
+    mv, mf = DMTet('cuda')(tv, sdf, grid['indices'])
+    v2, f2 = simplify_mesh(mv, mf, mf.shape[0] // 2)
+    assert v2.is_cuda and f2.is_cuda and f2.dtype == torch.int64 and mf.shape[0] // 2 - 1 <= f2.shape[0] <= mf.shape[0] // 2
+    assert int(f2.max()) == v2.shape[0] - 1
+    mesh = Mesh(v=v2, f=f2.int(), device='cuda')
+    mesh.auto_normal()
+    poses = torch.from_numpy(synth.surround_poses(2, seed=0)).cuda()
+    f = 0.5 * 128 / math.tan(math.radians(15))
+    out = MeshRenderer(near=0.01, far=100)([mesh], poses[None], torch.tensor([[f, f, 64.0, 64.0]] * 2, device='cuda')[None], 128, 128,
+                                           lambda world_pos=None, **kw: torch.full_like(world_pos, 0.5))
+    cover = (out['rgba'][0, ..., 3] > 0.5).float().mean().item()
+    assert 0.02 < cover < 0.6, cover
+
+
 @pytest.mark.parametrize('which', ['normal', 'depth', 'patch_normal', 'all', 'all_tone'])
 def test_patch_loss_targets_match_torch_chain(which):
     from tests.test_nerf_loss_host import make_inputs, torch_chain, check, NORMAL_BG
@@ -125,23 +145,3 @@ def test_call_initialises_from_the_field(parts):
     mesh, state = call(pipe, parts, init_images=None, ingp_states=state0, patch_rgb_weight=lambda p: 0.0, num_inference_steps=4)
     assert mesh is None and state is not None, 'the run raised inside __call__ (traceback printed above)'
     assert all(torch.isfinite(v).all() for v in state.values() if torch.is_floating_point(v))
-
-
-def test_simplify_mesh_from_device_tensors():
-    """``simplify_mesh`` (host C++) fed from CUDA tensors, and the decimated mesh through the rasteriser."""
-    from mvedit_b200.mesh_renderer import DMTet, Mesh, MeshRenderer, make_tet_grid, simplify_mesh
-    grid = make_tet_grid(24, device='cuda')
-    tv = -grid['vertices'] * 2 * 0.9
-    sdf = 0.5 - tv.norm(dim=-1) + 0.06 * torch.sin(7 * tv[:, 0]) * torch.sin(6 * tv[:, 1])
-    mv, mf = DMTet('cuda')(tv, sdf, grid['indices'])
-    v2, f2 = simplify_mesh(mv, mf, mf.shape[0] // 2)
-    assert v2.is_cuda and f2.is_cuda and f2.dtype == torch.int64 and mf.shape[0] // 2 - 1 <= f2.shape[0] <= mf.shape[0] // 2
-    assert int(f2.max()) == v2.shape[0] - 1
-    mesh = Mesh(v=v2, f=f2.int(), device='cuda')
-    mesh.auto_normal()
-    poses = torch.from_numpy(synth.surround_poses(2, seed=0)).cuda()
-    f = 0.5 * 128 / math.tan(math.radians(15))
-    out = MeshRenderer(near=0.01, far=100)([mesh], poses[None], torch.tensor([[f, f, 64.0, 64.0]] * 2, device='cuda')[None], 128, 128,
-                                           lambda world_pos=None, **kw: torch.full_like(world_pos, 0.5))
-    cover = (out['rgba'][0, ..., 3] > 0.5).float().mean().item()
-    assert 0.02 < cover < 0.6, cover
