@@ -31,7 +31,8 @@ def shimmed(source):
     src = os.path.join(CSRC, source)
     shim_dir = os.path.join(ROOT, 'tests', 'host_shim')
     out_cpp = os.path.join(OUT_DIR, source.replace('.cu', '_host.cpp'))
-    out_so = os.path.join(OUT_DIR, 'lib' + source.replace('.cu', '_host.so'))
+    asan = os.environ.get('MVE_HOST_ASAN') == '1'          # AddressSanitizer build (run pytest under LD_PRELOAD=$(gcc -print-file-name=libasan.so))
+    out_so = os.path.join(OUT_DIR, 'lib' + source.replace('.cu', '_host_asan.so' if asan else '_host.so'))
     deps = [src, os.path.join(shim_dir, 'cuda_host_shim.h'), os.path.join(CSRC, 'tonemap.cuh'), os.path.abspath(__file__)]
     if (not os.path.exists(out_so)) or os.path.getmtime(out_so) < max(os.path.getmtime(d) for d in deps):
         text = open(src).read()
@@ -52,7 +53,7 @@ def shimmed(source):
         assert n > 0 and '<<<' not in text
         open(out_cpp, 'w').write(text)
         cmd = ['g++', '-std=c++17', '-O1', '-ffp-contract=off', '-fPIC', '-shared', '-Wno-unknown-pragmas', '-I', shim_dir, '-I', CSRC,
-               '-I', os.path.join(ROOT, 'include'), out_cpp, '-o', out_so]
+               '-I', os.path.join(ROOT, 'include'), out_cpp, '-o', out_so] + (['-fsanitize=address', '-fno-omit-frame-pointer', '-g'] if asan else [])
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('host shim build of %s failed:\n%s' % (source, r.stderr))

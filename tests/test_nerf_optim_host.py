@@ -131,5 +131,5 @@ def test_product_nerf_optim_matches_the_oracle_loop(case):
     moved = 0.0
     for (k, p), q in zip(dec_p.named_parameters(), dec_o.parameters()):
         assert (p - q).abs().max() <= 2e-4, (k, float((p - q).abs().max()))
-        moved = max(moved, float((p - ToyField().state_dict()[k]).abs().max()))
+        moved = max(moved, float((p.detach() - ToyField().state_dict()[k]).abs().max()))
     assert moved > 0.05                                                        # four Adam steps at lr 0.02
