@@ -156,6 +156,23 @@ def main():
                fw_rgba=r['rgba'].detach().numpy(), fw_depth=r['depth'].detach().numpy(), fw_normal=r['normal'].detach().numpy(),
                fw_g_v=vt_v.grad.numpy(), fw_g_w=field.w.grad.numpy(), **{'fw_w_' + k: t.numpy() for k, t in ws.items()})
 
+    # ---- the renderer's options: 2x supersampling (load_init_mesh renders with it), vertex colours, edge dilation, antialiasing off
+    vc = torch.cat([torch.rand(1, len(v), 3, generator=torch.Generator().manual_seed(3)), torch.ones(1, len(v), 1)], dim=-1)
+    mo_ = RefMesh(v=vt_v.detach(), f=torch.from_numpy(f).int())
+    mo_.vc = vc
+    mo_.auto_normal()
+    r2 = R['MeshRenderer'](near=0.01, far=100, ssaa=2)
+    with torch.no_grad():
+        o1 = r2([mo_], poses[None], intr[None], size, size, None, dilate_edges=2, normal_bg=[0.5, 0.5, 1.0], render_vc=True)
+        lp2 = lights[:, None, None, :].expand(-1, 2 * size, 2 * size, -1)      # per-pixel lights at the supersampled size, as load_init_mesh's callers pass them
+
+        def shading_fun2(world_pos=None, albedo=None, world_normal=None, fg_mask=None, **kw):
+            base = field.point_decode([world_pos], None, None)[1]
+            return base * ((lp2[fg_mask.squeeze(0)][:, None, :] @ world_normal[:, :, None]).clamp(min=0) * 0.8 + 0.2).squeeze(-1)
+        o2 = r2([mo_], poses[None], intr[None], size, size, shading_fun2, normal_bg=[0.5, 0.5, 1.0], aa=False)
+    out.update(op_vc=vc.numpy(), **{'op1_' + k: o1[k].detach().numpy() for k in ('rgba', 'depth', 'normal')},
+               **{'op2_' + k: o2[k].detach().numpy() for k in ('rgba', 'depth', 'normal')})
+
     pm = ProductMesh(v=vt_v.detach(), f=torch.from_numpy(f).int())           # the per-triangle atlas is an INPUT here (xatlas is absent)
     pm.auto_uv()
     tm = RefMesh(v=vt_v.detach(), f=torch.from_numpy(f).int())

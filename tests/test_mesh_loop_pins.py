@@ -188,3 +188,28 @@ def test_superres_texture_optim_matches_the_reference_method():
                        patch_views=1)
     assert (field.w.detach() - T('ts_w_out')).abs().max() < 2e-5 and (field.b.detach() - T('ts_b_out')).abs().max() < 2e-5
     assert (T('ts_w_out') - T('to_w_out')).abs().max() > 1e-4                  # not the plain variant's trajectory
+
+
+@pytest.mark.parametrize('impl', ['product', 'oracle'])
+def test_renderer_options_match_the_reference_renderer(impl):
+    """2x supersampling (what ``load_init_mesh`` renders with), vertex colours with edge dilation, and antialiasing switched off."""
+    size = 40
+    poses, intr, lights = T('fw_poses'), T('fw_intr'), T('fw_lights')
+    lp2 = lights[:, None, None, :].expand(-1, 2 * size, 2 * size, -1)
+    field = ToyField()
+    fun = mopt.make_nerf_shading_fun(field, None, lp2, 0.2)
+    with torch.no_grad():
+        if impl == 'product':
+            mesh = Mesh(v=T('fw_v'), f=T('fw_f'), vc=T('op_vc'))
+            mesh.auto_normal()
+            rend = MeshRenderer(near=0.01, far=100, ssaa=2)
+            o1 = rend([mesh], poses[None], intr[None], size, size, None, dilate_edges=2, normal_bg=[0.5, 0.5, 1.0], render_vc=True)
+            o2 = rend([mesh], poses[None], intr[None], size, size, fun, normal_bg=[0.5, 0.5, 1.0], aa=False)
+        else:
+            m = mo.make_mesh(T('fw_v'), T('fw_f'))
+            m.vc = T('op_vc')
+            o1 = mo.mesh_renderer_forward(m, poses[None], intr[None], size, size, None, dilate_edges=2, ssaa=2)
+            o2 = mo.mesh_renderer_forward(m, poses[None], intr[None], size, size, fun, aa=False, ssaa=2)
+    for k in ('rgba', 'depth', 'normal'):
+        _close(o1[k], T('op1_' + k))
+        _close(o2[k], T('op2_' + k))
